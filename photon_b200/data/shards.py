@@ -1,0 +1,124 @@
+"""Token shard format (reader + writer).
+
+Plays the role of mosaicml-streaming's MDS shards in the reference
+(ref: photon/dataset/convert_dataset_hf.py:323-327 writes
+``columns={"tokens": "ndarray:int32"}`` zstd shards + ``index.json``).
+The on-disk layout is our own, sized for fast sequential reads into pinned
+host memory: a directory holding
+
+* ``index.json`` — ``{"version", "format": "pb200-tokens", "seq_len",
+  "dtype": "int32", "compression": null|"zlib", "shards": [{"basename",
+  "samples", "raw_bytes", "zip_bytes", "sha1"}...]}``
+* ``shard.00000.tok[.z]`` — a C-contiguous ``[samples, seq_len]`` int32 matrix.
+
+(zstd is not importable in this image; zlib is the optional codec.)
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import zlib
+from pathlib import Path
+from typing import Any, Iterable
+
+import numpy as np
+
+INDEX_NAME = "index.json"
+FORMAT = "pb200-tokens"
+
+
+class ShardWriter:
+    """Accumulates fixed-length int32 samples and cuts a shard every ``shard_samples``."""
+
+    def __init__(self, out_dir: str | os.PathLike, seq_len: int, shard_samples: int = 8192,
+                 compression: str | None = None) -> None:
+        if compression not in (None, "zlib"):
+            raise ValueError("compression must be null or 'zlib'")
+        self.out = Path(out_dir)
+        self.out.mkdir(parents=True, exist_ok=True)
+        self.seq_len, self.shard_samples, self.compression = int(seq_len), int(shard_samples), compression
+        self._buf: list[np.ndarray] = []
+        self._shards: list[dict[str, Any]] = []
+
+    def write(self, tokens: np.ndarray) -> None:
+        a = np.asarray(tokens, dtype=np.int32).reshape(-1)
+        if a.size != self.seq_len:
+            raise ValueError(f"sample has {a.size} tokens, expected {self.seq_len}")
+        self._buf.append(a)
+        if len(self._buf) >= self.shard_samples:
+            self._flush()
+
+    def write_many(self, rows: Iterable[np.ndarray]) -> None:
+        for r in rows:
+            self.write(r)
+
+    def _flush(self) -> None:
+        if not self._buf:
+            return
+        mat = np.stack(self._buf).astype(np.int32, copy=False)
+        raw = mat.tobytes()
+        base = f"shard.{len(self._shards):05d}.tok"
+        payload = raw
+        if self.compression == "zlib":
+            payload, base = zlib.compress(raw, 3), base + ".z"
+        (self.out / base).write_bytes(payload)
+        self._shards.append({"basename": base, "samples": int(mat.shape[0]), "raw_bytes": len(raw),
+                             "zip_bytes": len(payload), "sha1": hashlib.sha1(raw).hexdigest()})  # noqa: S324
+        self._buf = []
+
+    def finish(self) -> dict[str, Any]:
+        self._flush()
+        index = {"version": 1, "format": FORMAT, "seq_len": self.seq_len, "dtype": "int32",
+                 "compression": self.compression, "shards": self._shards}
+        (self.out / INDEX_NAME).write_text(json.dumps(index, indent=1))
+        return index
+
+    def __enter__(self) -> "ShardWriter":
+        return self
+
+    def __exit__(self, *exc: Any) -> None:
+        self.finish()
+
+
+class ShardReader:
+    """Random access over one shard directory (memory-maps raw shards)."""
+
+    def __init__(self, directory: str | os.PathLike, validate_hash: bool = False) -> None:
+        self.dir = Path(directory)
+        idx = self.dir / INDEX_NAME
+        if not idx.exists():
+            raise FileNotFoundError(f"no {INDEX_NAME} under {self.dir}")
+        self.index = json.loads(idx.read_text())
+        if self.index.get("format") != FORMAT:
+            raise ValueError(f"{idx}: unknown shard format {self.index.get('format')!r}")
+        self.seq_len = int(self.index["seq_len"])
+        self.validate_hash = validate_hash
+        counts = [int(s["samples"]) for s in self.index["shards"]]
+        self._starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self._cache: dict[int, np.ndarray] = {}
+
+    def __len__(self) -> int:
+        return int(self._starts[-1])
+
+    def _shard(self, i: int) -> np.ndarray:
+        if i not in self._cache:
+            meta = self.index["shards"][i]
+            path = self.dir / meta["basename"]
+            if self.index.get("compression") == "zlib":
+                raw = zlib.decompress(path.read_bytes())
+                mat = np.frombuffer(raw, dtype=np.int32).reshape(meta["samples"], self.seq_len)
+            else:
+                mat = np.memmap(path, dtype=np.int32, mode="r", shape=(meta["samples"], self.seq_len))
+            if self.validate_hash and hashlib.sha1(np.ascontiguousarray(mat).tobytes()).hexdigest() != meta["sha1"]:  # noqa: S324
+                raise OSError(f"hash mismatch in {path}")
+            if len(self._cache) > 8:
+                self._cache.pop(next(iter(self._cache)))
+            self._cache[i] = mat
+        return self._cache[i]
+
+    def __getitem__(self, idx: int) -> np.ndarray:
+        if not 0 <= idx < len(self):
+            raise IndexError(idx)
+        s = int(np.searchsorted(self._starts, idx, side="right") - 1)
+        return np.asarray(self._shard(s)[idx - int(self._starts[s])])

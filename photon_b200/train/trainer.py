@@ -1,0 +1,443 @@
+"""Trainer: the local-training engine a federated client (or the centralised
+entry point) drives.
+
+Replaces the Composer ``Trainer`` the reference wraps (ref:
+photon/clients/trainer_utils.py:1675-1719 construction; photon/clients/
+llm_client_functions.py:206-208 ``trainer.fit(duration=local_steps)``;
+photon/centralised_train.py:151-153).  Semantics kept:
+
+* ``fit(duration=X)`` trains X *more* from the current timestamp;
+* a batch is split into microbatches of ``device_train_microbatch_size``
+  (``auto`` = halve on CUDA OOM, ranks agree on the min);
+* DDP "forced sync": every microbatch accumulates locally, ONE gradient
+  all-reduce after the last one (ref: trainer_utils.py:1714) — here a single
+  fused NVLink kernel on the flat grad buffer instead of 148 NCCL calls;
+* algorithms → grad clipping; optimizer step; scheduler stepped every batch
+  and indexed by the global batch counter;
+* checkpoints ``ep{E}-ba{B}-rank{R}.pt`` + ``latest-rank{R}.pt`` with
+  ``save_num_checkpoints_to_keep`` and glob ``load_ignore_keys``.
+
+B200-first differences: one flat fp32 parameter/gradient/moment buffer, H2D
+copies on a side stream from pinned memory, device-side loss/clip scalars (no
+per-step host sync besides the configurable metric read-back).
+"""
+from __future__ import annotations
+
+import fnmatch
+import os
+import time
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any, Iterable, Iterator
+
+import torch
+import torch.distributed as dist
+
+from photon_b200.metrics.language import Metric, build_metrics, sync_metrics
+from photon_b200.models.mpt import MPTConfig
+from photon_b200.train.backend import build_backend
+from photon_b200.train.callbacks import Callback, InMemoryLogger, Logger
+from photon_b200.train.optim import FlatOptimizer, build_optimizer, clip_coefficient
+from photon_b200.train.schedulers import Scheduler, build_scheduler
+from photon_b200.train.timestamp import Time, Timestamp
+from photon_b200.utils.flat import FlatParams
+
+
+@dataclass
+class TrainerState:
+    backend: Any
+    flat: FlatParams
+    optimizer: FlatOptimizer
+    scheduler: Scheduler
+    timestamp: Timestamp = field(default_factory=Timestamp)
+    eval_timestamp: Timestamp = field(default_factory=Timestamp)
+    train_metrics: dict[str, Metric] = field(default_factory=dict)
+    eval_metrics: dict[str, dict[str, Metric]] = field(default_factory=dict)
+    run_name: str = "run"
+
+    @property
+    def model(self) -> Any:
+        return getattr(self.backend, "model", self.backend)
+
+    @property
+    def train_metric_values(self) -> dict[str, float]:
+        return {k: m.compute() for k, m in self.train_metrics.items() if m.count}
+
+    @property
+    def eval_metric_values(self) -> dict[str, float]:
+        out: dict[str, float] = {}
+        for label, ms in self.eval_metrics.items():
+            for k, m in ms.items():
+                if m.count:
+                    out[f"{label}/{k}" if label else k] = m.compute()
+        return out
+
+
+class GradScaler:
+    """Dynamic loss scaling for ``amp_fp16`` (growth 2× / 2000 good steps, back-off ½)."""
+
+    def __init__(self, init: float = 2.0 ** 16, growth_interval: int = 2000) -> None:
+        self.scale, self.growth_interval, self._good = float(init), growth_interval, 0
+
+    def update(self, found_inf: bool) -> None:
+        if found_inf:
+            self.scale, self._good = max(self.scale * 0.5, 1.0), 0
+        else:
+            self._good += 1
+            if self._good % self.growth_interval == 0:
+                self.scale *= 2.0
+
+
+def _is_oom(e: BaseException) -> bool:
+    return isinstance(e, torch.cuda.OutOfMemoryError) or "out of memory" in str(e).lower()
+
+
+class Trainer:
+    def __init__(self, model_cfg: MPTConfig | dict[str, Any], *, optimizer_cfg: dict[str, Any],
+                 scheduler_cfg: dict[str, Any] | None = None, train_loader: Any = None,
+                 eval_loaders: dict[str, Any] | None = None, global_train_batch_size: int = 8,
+                 device_train_microbatch_size: int | str = "auto", device_eval_batch_size: int | None = None,
+                 precision: str = "amp_bf16", max_duration: str | int | None = None,
+                 grad_clip_norm: float | None = None, callbacks: Iterable[Callback] = (),
+                 loggers: Iterable[Logger] = (), save_folder: str | None = None, save_interval: str | int | None = None,
+                 save_num_checkpoints_to_keep: int = -1, save_overwrite: bool = True,
+                 eval_interval: str | int | None = None, eval_subset_num_batches: int = -1,
+                 device: torch.device | str | None = None, rank: int = 0, world_size: int = 1,
+                 process_group: Any = None, grad_comm: Any = None, kernels: dict[str, Any] | None = None,
+                 seed: int = 17, run_name: str = "run", use_unigram_metrics: bool = False,
+                 unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
+                 unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
+                 backend: Any = None) -> None:
+        self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.rank, self.world_size, self.process_group = int(rank), int(world_size), process_group
+        self.precision = precision
+        if global_train_batch_size % self.world_size:
+            raise ValueError(f"global_train_batch_size={global_train_batch_size} not divisible by world_size={world_size}")
+        self.global_batch = int(global_train_batch_size)
+        self.device_batch = self.global_batch // self.world_size
+        self.microbatch = device_train_microbatch_size
+        self._auto_mb = self.device_batch if device_train_microbatch_size == "auto" else None
+        self.device_eval_batch_size = device_eval_batch_size or self.device_batch
+        self.grad_clip_norm = grad_clip_norm
+        self.train_loader, self.eval_loaders = train_loader, dict(eval_loaders or {})
+        self.callbacks, self.loggers = list(callbacks), list(loggers) or [InMemoryLogger()]
+        self.save_folder, self.save_overwrite = save_folder, save_overwrite
+        self.save_keep = int(save_num_checkpoints_to_keep)
+        self.eval_subset_num_batches = int(eval_subset_num_batches)
+        self.metric_sync_interval = max(1, int(metric_sync_interval))
+        self.grad_comm = grad_comm
+        self.seed = seed
+        self.scaler = GradScaler() if precision == "amp_fp16" else None
+        self._pending: dict[str, float] = {}
+        self._saved: list[Path] = []
+        self._train_iter: Iterator[Any] | None = None
+        self.fit_start_batch, self.fit_end_batch = 0, None
+        self.closed = False
+        self.last_batch_stats: dict[str, float] = {}
+
+        seq = self.model_cfg.max_seq_len
+        self.max_duration = Time.parse(max_duration) if max_duration is not None else None
+        geom = dict(samples_per_batch=self.global_batch, tokens_per_batch=self.global_batch * seq,
+                    batches_per_epoch=len(train_loader) if train_loader is not None and hasattr(train_loader, "__len__") else None)
+        self._geom = geom
+        self.save_interval = Time.parse(save_interval).to_batches(max_duration=self.max_duration, **geom) if save_interval else None
+        self.eval_interval = Time.parse(eval_interval).to_batches(max_duration=self.max_duration, **geom) if eval_interval else None
+
+        be = backend or build_backend(self.model_cfg, self.device, precision, kernels, seed=seed,
+                                      frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers,
+                                      unigram_log_probs=unigram_log_probs)
+        shadow = getattr(be, "bf16_params", None)
+        use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
+        opt = build_optimizer(optimizer_cfg, be.flat, use_kernel=use_kernel, bf16_shadow=shadow)
+        sched = build_scheduler(scheduler_cfg, max_duration=self.max_duration, **geom)
+        self.state = TrainerState(backend=be, flat=be.flat, optimizer=opt, scheduler=sched, run_name=run_name,
+                                  train_metrics=build_metrics(use_unigram_metrics),
+                                  eval_metrics={lbl: build_metrics(use_unigram_metrics) for lbl in self.eval_loaders})
+        self._copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    # ------------------------------------------------------------------ helpers
+    def log(self, metrics: dict[str, float]) -> None:
+        self._pending.update(metrics)
+
+    def _flush_logs(self) -> None:
+        if self._pending:
+            step = self.state.timestamp.batch
+            for lg in self.loggers:
+                lg.log_metrics(self._pending, step)
+            self._pending = {}
+
+    def flops_per_token(self) -> float:
+        return self.model_cfg.flops_per_token()
+
+    def peak_flops(self) -> float | None:
+        if self.device.type != "cuda":
+            return None
+        from photon_b200.utils.hw import measured_peaks
+
+        return measured_peaks().get("bf16_flops")
+
+    def _emit(self, event: str) -> None:
+        for cb in self.callbacks:
+            getattr(cb, event)(self)
+
+    def _to_device(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.device.type != "cuda":
+            return ids.to(self.device)
+        assert self._copy_stream is not None
+        with torch.cuda.stream(self._copy_stream):
+            out = ids.to(self.device, non_blocking=True)
+        torch.cuda.current_stream(self.device).wait_stream(self._copy_stream)
+        return out
+
+    def _next_batch(self) -> dict[str, torch.Tensor]:
+        if self.train_loader is None:
+            raise RuntimeError("Trainer has no train_loader")
+        while True:
+            if self._train_iter is None:
+                self._train_iter = iter(self.train_loader)
+            try:
+                return next(self._train_iter)
+            except StopIteration:
+                self._train_iter = None
+                self.state.timestamp.advance_epoch()
+
+    def _agree_min(self, v: int) -> int:
+        if self.world_size > 1 and dist.is_initialized():
+            t = torch.tensor([v], device=self.device if dist.get_backend(self.process_group) == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.process_group)
+            return int(t.item())
+        return v
+
+    # ------------------------------------------------------------------ training
+    def _train_batch(self, batch: dict[str, torch.Tensor]) -> None:
+        st = self.state
+        ids_host = batch["input_ids"]
+        B, S = ids_host.shape
+        n_tok_target = float(B * (S - 1))  # packed sequences: only the last position is ignored
+        scale = self.scaler.scale if self.scaler else 1.0
+        while True:
+            mb = int(self._auto_mb if self._auto_mb is not None else self.microbatch)
+            mb = max(1, min(mb, B))
+            try:
+                st.flat.zero_grad()
+                loss_sum = torch.zeros((), device=self.device, dtype=torch.float32)
+                n_tok = torch.zeros((), device=self.device, dtype=torch.float32)
+                for lo in range(0, B, mb):
+                    ids = self._to_device(ids_host[lo:lo + mb])
+                    ls, n = st.backend.fwd_bwd(ids, n_tok_target, scale)
+                    loss_sum += ls.float()
+                    n_tok += n.float() if torch.is_tensor(n) else float(n)
+                break
+            except RuntimeError as e:  # auto microbatch: halve on OOM (ref: SURVEY App. C)
+                if self._auto_mb is None or not _is_oom(e) or mb == 1:
+                    raise
+                if self.device.type == "cuda":
+                    torch.cuda.empty_cache()
+                self._auto_mb = self._agree_min(max(1, mb // 2))
+                print(f"[trainer] CUDA OOM at microbatch {mb}; retrying with {self._auto_mb}")
+        if self._auto_mb is not None and self.world_size > 1 and st.timestamp.batch == self.fit_start_batch:
+            self._auto_mb = self._agree_min(self._auto_mb)
+
+        # N1: ONE gradient all-reduce on the flat bucket (mean over ranks)
+        if self.world_size > 1:
+            self._allreduce_grads()
+        self._emit("after_backward")
+
+        grad_mult: torch.Tensor | float | None = None
+        skip = False
+        if self.grad_clip_norm is not None or self.scaler is not None:
+            gnorm = self._grad_norm() / scale
+            if self.scaler is not None:
+                skip = not bool(torch.isfinite(gnorm))
+                self.scaler.update(skip)
+            coef = clip_coefficient(gnorm, self.grad_clip_norm) if self.grad_clip_norm is not None else 1.0
+            grad_mult = coef / scale if scale != 1.0 else coef
+            self.log({"l2_norm/grad/clipped_from": gnorm})  # device scalar; floated lazily below
+        if not skip:
+            st.optimizer.step(st.scheduler(st.timestamp.batch), grad_mult)
+            st.backend.params_updated()
+        self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok}
+        st.timestamp.advance_batch(samples=B * self.world_size, tokens=B * S * self.world_size)
+
+    def _grad_norm(self) -> torch.Tensor:
+        g = self.state.flat.grads
+        if g.is_cuda and self.state.optimizer.use_kernel:
+            from photon_b200 import ops
+
+            return ops.flat_l2_norm(g)
+        return g.norm()
+
+    def _allreduce_grads(self) -> None:
+        g = self.state.flat.grads
+        if self.grad_comm is not None:
+            self.grad_comm.all_reduce_mean_(g)  # fused NVLink kernel (photon_b200.parallel.ddp)
+            return
+        dist.all_reduce(g, group=self.process_group)
+        g.div_(self.world_size)
+
+    def fit(self, duration: str | int | None = None, reset_time: bool = False) -> None:
+        """Train ``duration`` more (default: until ``max_duration``)."""
+        if self.closed:
+            raise RuntimeError("Trainer is closed")
+        st = self.state
+        if reset_time:
+            st.timestamp.reset()
+        if duration is not None:
+            n = Time.parse(duration).to_batches(max_duration=self.max_duration, **self._geom)
+            end = st.timestamp.batch + n
+        elif self.max_duration is not None:
+            end = self.max_duration.to_batches(**self._geom)
+        else:
+            raise ValueError("fit() needs a duration or max_duration")
+        self.fit_start_batch, self.fit_end_batch = st.timestamp.batch, end
+        st.backend.train_mode(True)
+        for m in st.train_metrics.values():
+            m.reset()
+        self._emit("fit_start")
+        while st.timestamp.batch < end:
+            t0 = time.perf_counter()
+            self._emit("batch_start")
+            self._train_batch(self._next_batch())
+            if (st.timestamp.batch - self.fit_start_batch) % self.metric_sync_interval == 0 or st.timestamp.batch == end:
+                self._collect_train_metrics()
+            st.timestamp.total_wct_s += time.perf_counter() - t0
+            self._emit("batch_end")
+            self._flush_logs()
+            if self.save_interval and self.save_folder and st.timestamp.batch % self.save_interval == 0:
+                self.save_checkpoint()
+            if self.eval_interval and self.eval_loaders and st.timestamp.batch % self.eval_interval == 0 \
+                    and st.timestamp.batch < end:
+                self.eval()
+                st.backend.train_mode(True)
+        self._emit("fit_end")
+        self._flush_logs()
+
+    def _collect_train_metrics(self) -> None:
+        """D2H read of the step's loss (the only host sync in the step)."""
+        stats = {k: float(v) for k, v in self.last_batch_stats.items()}
+        if self.world_size > 1 and dist.is_initialized():
+            t = torch.tensor([stats["loss_sum"], stats["n_tokens"]], dtype=torch.float64,
+                             device=self.device if dist.get_backend(self.process_group) == "nccl" else "cpu")
+            dist.all_reduce(t, group=self.process_group)
+            stats = {"loss_sum": float(t[0]), "n_tokens": float(t[1])}
+        for m in self.state.train_metrics.values():
+            m.update(stats)
+        loss = stats["loss_sum"] / max(stats["n_tokens"], 1.0)
+        out = {"loss/train/total": loss, "metrics/train/LanguageCrossEntropy": loss}
+        for k, v in list(self._pending.items()):
+            if torch.is_tensor(v):
+                self._pending[k] = float(v)
+        self.log(out)
+
+    # ---------------------------------------------------------------- evaluation
+    @torch.no_grad()
+    def eval(self, subset_num_batches: int | None = None) -> dict[str, float]:
+        st = self.state
+        st.backend.train_mode(False)
+        limit = self.eval_subset_num_batches if subset_num_batches is None else subset_num_batches
+        st.eval_timestamp.reset()
+        for label, loader in self.eval_loaders.items():
+            metrics = st.eval_metrics.setdefault(label, build_metrics(bool(getattr(st.backend, "unigram_log_probs", None) is not None)))
+            for m in metrics.values():
+                m.reset()
+            for i, batch in enumerate(loader):
+                if 0 <= limit <= i:
+                    break
+                ids = self._to_device(batch["input_ids"])
+                stats = st.backend.eval_stats(ids)
+                stats = {k: float(v) for k, v in stats.items()}
+                for m in metrics.values():
+                    m.update(stats)
+                st.eval_timestamp.advance_batch(samples=ids.shape[0] * self.world_size,
+                                                tokens=ids.numel() * self.world_size)
+            sync_metrics(metrics, self.process_group)
+        vals = st.eval_metric_values
+        self.log({f"metrics/{k}": v for k, v in vals.items()})
+        self._emit("eval_end")
+        self._flush_logs()
+        return vals
+
+    # --------------------------------------------------------------- checkpoints
+    def state_dict(self) -> dict[str, Any]:
+        st = self.state
+        names = st.flat.layout.names
+        return {
+            "state": {
+                "model": {n: st.flat.layout.view(st.flat.params, i).detach().cpu().clone() for i, n in enumerate(names)},
+                "optimizers": {type(st.optimizer).__name__: st.optimizer.state_dict()},
+                "schedulers": {"lr": {"last_batch": st.timestamp.batch}},
+                "timestamp": st.timestamp.state_dict(),
+                "dataset_state": {"train": self.train_loader.state_dict() if hasattr(self.train_loader, "state_dict") else {}},
+                "callbacks": {type(c).__name__: c.state_dict() for c in self.callbacks},
+                "run_name": st.run_name,
+                "scaler": {"scale": self.scaler.scale} if self.scaler else None,
+            },
+            "rng": {"torch": torch.get_rng_state(), "seed": self.seed},
+        }
+
+    def checkpoint_name(self) -> str:
+        ts = self.state.timestamp
+        return f"ep{ts.epoch}-ba{ts.batch}-rank{self.rank}.pt"
+
+    def save_checkpoint(self, folder: str | None = None) -> Path:
+        folder_p = Path(folder or self.save_folder or ".")
+        folder_p.mkdir(parents=True, exist_ok=True)
+        path = folder_p / self.checkpoint_name()
+        if path.exists() and not self.save_overwrite:
+            raise FileExistsError(path)
+        tmp = path.with_suffix(".pt.tmp")
+        torch.save(self.state_dict(), tmp)
+        os.replace(tmp, path)
+        latest = folder_p / f"latest-rank{self.rank}.pt"
+        if latest.is_symlink() or latest.exists():
+            latest.unlink()
+        latest.symlink_to(path.name)
+        self._saved.append(path)
+        if self.save_keep >= 0:
+            while len(self._saved) > max(self.save_keep, 1):
+                old = self._saved.pop(0)
+                if old.exists() and old != path:
+                    old.unlink()
+        return path
+
+    def load_checkpoint(self, path: str | os.PathLike, ignore_keys: Iterable[str] = ()) -> None:
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        pats = list(ignore_keys)
+
+        def ignored(key: str) -> bool:
+            return any(fnmatch.fnmatch(key, p) or fnmatch.fnmatch("state/" + key, p) for p in pats)
+
+        s = ck["state"]
+        st = self.state
+        if not ignored("model"):
+            with torch.no_grad():
+                for i, n in enumerate(st.flat.layout.names):
+                    if n in s["model"]:
+                        st.flat.layout.view(st.flat.params, i).copy_(s["model"][n])
+            st.backend.params_updated()
+        if not ignored("optimizers") and s.get("optimizers"):
+            sd = s["optimizers"].get(type(st.optimizer).__name__)
+            if sd is not None:
+                st.optimizer.load_state_dict(sd)
+        if not ignored("timestamp"):
+            st.timestamp.load_state_dict(s["timestamp"])
+        if not ignored("dataset_state") and hasattr(self.train_loader, "load_state_dict"):
+            ds = (s.get("dataset_state") or {}).get("train")
+            if ds:
+                self.train_loader.load_state_dict(ds)
+                self._train_iter = None
+        if self.scaler and s.get("scaler") and not ignored("scaler"):
+            self.scaler.scale = float(s["scaler"]["scale"])
+        if not ignored("rng") and "rng" in ck and "torch" in ck["rng"]:
+            torch.set_rng_state(ck["rng"]["torch"])
+
+    # --------------------------------------------------------------------- close
+    def close(self) -> None:
+        if self.closed:
+            return
+        for lg in self.loggers:
+            lg.close()
+        self.state.backend.close()
+        self.closed = True
