@@ -1,0 +1,362 @@
+// Python bindings (torch extension `photon_b200._C`) for the sm_100a kernels in this directory.
+// Tensors are passed as torch::Tensor; every op runs on the current CUDA stream of the tensor's device.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+#include <pybind11/pybind11.h>
+#include <torch/extension.h>
+
+#include <atomic>
+#include <cmath>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "fused_ops.h"
+#include "gemm_tcgen05.h"
+#include "attention_tcgen05.h"
+
+namespace py = pybind11;
+using torch::Tensor;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+inline cudaStream_t stream_of(const Tensor& t) { return at::cuda::getCurrentCUDAStream(t.device().index()).stream(); }
+
+inline void check_cuda(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+}
+inline void check_bf16(const Tensor& t, const char* name) {
+  check_cuda(t, name);
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bfloat16");
+}
+inline void check_f32(const Tensor& t, const char* name) {
+  check_cuda(t, name);
+  TORCH_CHECK(t.scalar_type() == at::kFloat, name, " must be float32");
+}
+inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    TORCH_CHECK(e__ == cudaSuccess, #expr " failed: ", cudaGetErrorString(e__));             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------- GEMM
+// a: [M,K] (a_mn=0) or [K,M] (a_mn=1);  b: [N,K] (b_mn=0) or [K,N] (b_mn=1);  d: [M,N]
+void gemm(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int epi, const c10::optional<Tensor>& bias,
+          const c10::optional<Tensor>& aux, c10::optional<Tensor> d2, bool accumulate, double alpha) {
+  check_bf16(a, "a");
+  check_bf16(b, "b");
+  check_cuda(d, "d");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && d.dim() == 2, "gemm operands must be 2-D");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1, "gemm operands must have unit inner stride");
+  c10::cuda::CUDAGuard guard(a.device());
+  pb::GemmArgs g;
+  g.M = int(a_mn ? a.size(1) : a.size(0));
+  g.K = int(a_mn ? a.size(0) : a.size(1));
+  g.N = int(b_mn ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == g.K, "gemm: K mismatch between a and b");
+  TORCH_CHECK(d.size(0) == g.M && d.size(1) == g.N, "gemm: output shape mismatch");
+  g.A = a.data_ptr(), g.B = b.data_ptr(), g.D = d.data_ptr();
+  g.lda = a.stride(0), g.ldb = b.stride(0), g.ldd = d.stride(0);
+  g.a_mn = a_mn, g.b_mn = b_mn, g.epi = epi, g.accumulate = accumulate ? 1 : 0, g.alpha = float(alpha);
+  if (epi == pb::EPI_F32) {
+    TORCH_CHECK(d.scalar_type() == at::kFloat, "EPI_F32 needs a float32 output");
+  } else {
+    TORCH_CHECK(d.scalar_type() == at::kBFloat16, "bf16 epilogues need a bfloat16 output");
+  }
+  if (bias.has_value()) {
+    check_f32(*bias, "bias");
+    TORCH_CHECK(bias->numel() == g.N, "bias length must equal N");
+    g.bias = bias->data_ptr<float>();
+  }
+  if (aux.has_value()) {
+    check_bf16(*aux, "aux");
+    TORCH_CHECK(aux->size(0) == g.M && aux->size(1) == g.N && aux->stride(1) == 1, "aux must be [M,N]");
+    g.aux = aux->data_ptr(), g.ld_aux = aux->stride(0);
+  }
+  if (d2.has_value()) {
+    check_bf16(*d2, "d2");
+    TORCH_CHECK(d2->size(0) == g.M && d2->size(1) == g.N && d2->stride(1) == 1, "d2 must be [M,N]");
+    g.D2 = d2->data_ptr(), g.ldd2 = d2->stride(0);
+  }
+  g.num_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  pb::gemm_bf16_launch(g, stream_of(a));
+  g_launches += 1;
+}
+
+// ---------------------------------------------------------------------------------- attention
+void attention_fwd(const Tensor& qkv, Tensor& out, Tensor& lse, int n_heads, double scale, bool causal) {
+  check_bf16(qkv, "qkv");
+  check_bf16(out, "out");
+  check_f32(lse, "lse");
+  TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous(), "qkv must be contiguous [B,S,3*d]");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  const int B = int(qkv.size(0)), S = int(qkv.size(1)), d = int(qkv.size(2) / 3);
+  pb::attention_fwd_launch(qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, S, n_heads, d / n_heads, float(scale), causal,
+                           at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv));
+  g_launches += 1;
+}
+void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, const Tensor& lse, Tensor& dqkv, Tensor& delta,
+                   int n_heads, double scale, bool causal) {
+  check_bf16(qkv, "qkv");
+  check_bf16(out, "out");
+  check_bf16(dout, "dout");
+  check_bf16(dqkv, "dqkv");
+  check_f32(lse, "lse");
+  check_f32(delta, "delta");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  const int B = int(qkv.size(0)), S = int(qkv.size(1)), d = int(qkv.size(2) / 3);
+  const int launched = pb::attention_bwd_launch(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
+                                                delta.data_ptr<float>(), B, S, n_heads, d / n_heads, float(scale), causal,
+                                                at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv));
+  g_launches += launched;
+}
+
+// ---------------------------------------------------------------------------------- fused ops
+void embed_fwd(const Tensor& ids, const Tensor& wte, const c10::optional<Tensor>& wpe, Tensor& out, int S) {
+  check_cuda(ids, "ids");
+  TORCH_CHECK(ids.scalar_type() == at::kLong && ids.is_contiguous(), "ids must be contiguous int64");
+  check_bf16(wte, "wte");
+  check_bf16(out, "out");
+  c10::cuda::CUDAGuard guard(ids.device());
+  pb::embed_fwd(ids.data_ptr<int64_t>(), wte.data_ptr(), opt_ptr(wpe), out.data_ptr(), ids.numel(), S, int(wte.size(1)),
+                int(wte.size(0)), stream_of(ids));
+  g_launches += 1;
+}
+void embed_bwd(const Tensor& ids, const Tensor& dh, Tensor& dwte, c10::optional<Tensor> dwpe, int S) {
+  check_bf16(dh, "dh");
+  check_f32(dwte, "dwte");
+  c10::cuda::CUDAGuard guard(ids.device());
+  pb::embed_bwd(ids.data_ptr<int64_t>(), dh.data_ptr(), dwte.data_ptr<float>(), dwpe.has_value() ? dwpe->data_ptr<float>() : nullptr,
+                ids.numel(), S, int(dwte.size(1)), int(dwte.size(0)), stream_of(ids));
+  g_launches += dwpe.has_value() ? 2 : 1;
+}
+void layernorm_fwd(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta, Tensor& y, Tensor& mean, Tensor& rstd,
+                   double eps) {
+  check_bf16(x, "x");
+  check_f32(gamma, "gamma");
+  TORCH_CHECK(x.is_contiguous() && y.is_contiguous(), "layernorm tensors must be contiguous");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int d = int(x.size(-1));
+  pb::layernorm_fwd(x.data_ptr(), gamma.data_ptr<float>(), beta.has_value() ? beta->data_ptr<float>() : nullptr, y.data_ptr(),
+                    mean.data_ptr<float>(), rstd.data_ptr<float>(), x.numel() / d, d, float(eps), stream_of(x));
+  g_launches += 1;
+}
+void layernorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& gamma, const Tensor& mean, const Tensor& rstd,
+                   const c10::optional<Tensor>& dres, Tensor& dx, c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta) {
+  check_bf16(dy, "dy");
+  check_bf16(x, "x");
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous(), "layernorm tensors must be contiguous");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int d = int(x.size(-1));
+  pb::layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), opt_ptr(dres),
+                    dx.data_ptr(), dgamma.has_value() ? dgamma->data_ptr<float>() : nullptr,
+                    dbeta.has_value() ? dbeta->data_ptr<float>() : nullptr, x.numel() / d, d, stream_of(x));
+  g_launches += (dgamma.has_value() || dbeta.has_value()) ? 2 : 1;
+}
+void col_sum(const Tensor& dy, Tensor& out) {
+  check_bf16(dy, "dy");
+  check_f32(out, "out");
+  TORCH_CHECK(dy.dim() == 2 && dy.stride(1) == 1, "col_sum expects [T,N] with unit inner stride");
+  c10::cuda::CUDAGuard guard(dy.device());
+  pb::col_reduce(dy.data_ptr(), dy.stride(0), nullptr, nullptr, nullptr, out.data_ptr<float>(), nullptr, dy.size(0), int(dy.size(1)),
+                 stream_of(dy));
+  g_launches += 1;
+}
+void cross_entropy(Tensor& logits, const Tensor& targets, double grad_scale, bool write_grad, Tensor& stats,
+                   c10::optional<Tensor> row_lse, const c10::optional<Tensor>& unigram_logp) {
+  check_bf16(logits, "logits");
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1, "logits must be [rows,V]");
+  TORCH_CHECK(targets.scalar_type() == at::kLong && targets.is_contiguous(), "targets must be contiguous int64");
+  TORCH_CHECK(stats.scalar_type() == at::kDouble && stats.numel() >= 4, "stats must be float64[>=4]");
+  c10::cuda::CUDAGuard guard(logits.device());
+  pb::cross_entropy(logits.data_ptr(), logits.stride(0), targets.data_ptr<int64_t>(), logits.size(0), int(logits.size(1)), float(grad_scale),
+                    write_grad, stats.data_ptr<double>(), row_lse.has_value() ? row_lse->data_ptr<float>() : nullptr,
+                    unigram_logp.has_value() ? unigram_logp->data_ptr<float>() : nullptr, stream_of(logits));
+  g_launches += 1;
+}
+void flat_l2_norm(const Tensor& x, Tensor& scratch_f64, Tensor& out_f32) {
+  check_f32(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  cudaStream_t st = stream_of(x);
+  CUDA_OK(cudaMemsetAsync(scratch_f64.data_ptr(), 0, sizeof(double), st));
+  pb::flat_sqnorm(x.data_ptr<float>(), x.numel(), scratch_f64.data_ptr<double>(), st);
+  pb::sqrt_finalize(scratch_f64.data_ptr<double>(), out_f32.data_ptr<float>(), st);
+  g_launches += 2;
+}
+void axpby(Tensor& acc, const Tensor& x, double a, double b) {
+  check_f32(acc, "acc");
+  check_f32(x, "x");
+  TORCH_CHECK(acc.numel() == x.numel() && acc.numel() % 4 == 0, "axpby: sizes must match and be multiples of 4");
+  c10::cuda::CUDAGuard guard(acc.device());
+  pb::axpby(acc.data_ptr<float>(), x.data_ptr<float>(), float(a), float(b), acc.numel(), stream_of(acc));
+  g_launches += 1;
+}
+void cast_bf16(const Tensor& src, Tensor& dst) {
+  check_f32(src, "src");
+  check_bf16(dst, "dst");
+  TORCH_CHECK(src.numel() == dst.numel() && src.numel() % 4 == 0, "cast: sizes must match and be multiples of 4");
+  c10::cuda::CUDAGuard guard(src.device());
+  pb::cast_fp32_to_bf16(src.data_ptr<float>(), dst.data_ptr(), src.numel(), stream_of(src));
+  g_launches += 1;
+}
+void fused_optimizer(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, c10::optional<Tensor> shadow, int kind, bool first_step, double lr,
+                     double beta1, double beta2, double eps, double decay, double clip, double step_size, double inv_sqrt_bc2,
+                     const c10::optional<Tensor>& grad_mult) {
+  check_f32(p, "p");
+  check_f32(g, "g");
+  TORCH_CHECK(p.numel() % 4 == 0, "flat buffers must be multiples of 4 elements");
+  c10::cuda::CUDAGuard guard(p.device());
+  pb::OptimHyper h;
+  h.kind = kind, h.first_step = first_step ? 1 : 0;
+  h.lr = float(lr), h.beta1 = float(beta1), h.beta2 = float(beta2), h.eps = float(eps), h.decay = float(decay);
+  h.clip = std::isfinite(clip) ? float(clip) : std::numeric_limits<float>::infinity();
+  h.step_size = float(step_size), h.inv_sqrt_bc2 = float(inv_sqrt_bc2);
+  pb::fused_optimizer(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                      shadow.has_value() ? shadow->data_ptr() : nullptr, p.numel(), h,
+                      grad_mult.has_value() ? grad_mult->data_ptr<float>() : nullptr, stream_of(p));
+  g_launches += 1;
+}
+
+// ---------------------------------------------------------------------------------- symmetric arena (CUDA IPC)
+int64_t ipc_alloc(int64_t nbytes, int device) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, size_t(nbytes)));
+  CUDA_OK(cudaMemset(p, 0, size_t(nbytes)));
+  return reinterpret_cast<int64_t>(p);
+}
+py::bytes ipc_get_handle(int64_t ptr) {
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(ptr)));
+  return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+int64_t ipc_open_handle(const std::string& handle, int device) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return reinterpret_cast<int64_t>(p);
+}
+void ipc_close(int64_t ptr) { CUDA_OK(cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr))); }
+void ipc_free(int64_t ptr) { CUDA_OK(cudaFree(reinterpret_cast<void*>(ptr))); }
+bool enable_peer_access(int device, int peer) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  int can = 0;
+  CUDA_OK(cudaDeviceCanAccessPeer(&can, device, peer));
+  if (!can) return false;
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return true;
+  }
+  CUDA_OK(e);
+  return true;
+}
+Tensor tensor_from_ptr(int64_t ptr, int64_t numel, const std::string& dtype, int device) {
+  auto dt = dtype == "float32" ? at::kFloat : dtype == "bfloat16" ? at::kBFloat16 : dtype == "int32" ? at::kInt
+          : dtype == "float64" ? at::kDouble : at::kByte;
+  auto opts = torch::TensorOptions().dtype(dt).device(torch::kCUDA, device);
+  return torch::from_blob(reinterpret_cast<void*>(ptr), {numel}, [](void*) {}, opts);
+}
+
+pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
+  TORCH_CHECK(ctl_ptrs.size() >= 1 && ctl_ptrs.size() <= pb::MAX_PEERS, "1..8 peers supported");
+  pb::CommCtl c{};
+  c.n = int(ctl_ptrs.size());
+  c.rank = rank;
+  for (int i = 0; i < c.n; ++i) c.ctl[i] = reinterpret_cast<uint32_t*>(ctl_ptrs[i]);
+  return c;
+}
+
+void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& acc_ptrs,
+               const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi,
+               int kind, double avg_scale, double lr, double mu, double eta, double beta1, double beta2, double tau, int64_t round_t,
+               bool sign_compat) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  pb::CommCtl c = make_ctl(ctl_ptrs, rank);
+  pb::FedRoundArgs a{};
+  for (int i = 0; i < c.n; ++i) {
+    a.acc[i] = reinterpret_cast<const float*>(acc_ptrs[i]);
+    a.xg[i] = reinterpret_cast<float*>(xg_ptrs[i]);
+    a.xs[i] = xs_ptrs.empty() ? nullptr : reinterpret_cast<void*>(xs_ptrs[i]);
+  }
+  a.x = a.xg[rank];
+  a.m = reinterpret_cast<float*>(m_ptr);
+  a.v = reinterpret_cast<float*>(v_ptr);
+  a.lo = lo, a.hi = hi, a.kind = kind, a.avg_scale = float(avg_scale), a.lr = float(lr), a.mu = float(mu);
+  a.eta = float(eta), a.beta1 = float(beta1), a.beta2 = float(beta2), a.tau = float(tau);
+  const double t = double(round_t < 1 ? 1 : round_t);
+  a.inv_bc1 = float(1.0 / (1.0 - std::pow(beta1, t)));
+  a.inv_bc2 = float(1.0 / (1.0 - std::pow(beta2, t)));
+  a.sign = sign_compat ? 1.0f : -1.0f;
+  pb::fed_round_launch(a, c, uint32_t(epoch), at::cuda::getCurrentDeviceProperties()->multiProcessorCount,
+                       at::cuda::getCurrentCUDAStream(device).stream());
+  g_launches += 1;
+}
+void ddp_allreduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& buf_ptrs, int64_t lo,
+                   int64_t hi, c10::optional<Tensor> out_norm) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  pb::CommCtl c = make_ctl(ctl_ptrs, rank);
+  pb::AllReduceArgs a{};
+  for (int i = 0; i < c.n; ++i) a.buf[i] = reinterpret_cast<float*>(buf_ptrs[i]);
+  a.lo = lo, a.hi = hi;
+  pb::ddp_allreduce_launch(a, c, uint32_t(epoch), out_norm.has_value() ? out_norm->data_ptr<float>() : nullptr,
+                           at::cuda::getCurrentDeviceProperties()->multiProcessorCount, at::cuda::getCurrentCUDAStream(device).stream());
+  g_launches += out_norm.has_value() ? 2 : 1;
+}
+void set_wsum(int64_t ctl_ptr, int device, double w, bool zero_sums) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  pb::set_wsum(reinterpret_cast<uint32_t*>(ctl_ptr), float(w), zero_sums, at::cuda::getCurrentCUDAStream(device).stream());
+  g_launches += 1;
+}
+
+long long launch_count() { return g_launches.load(); }
+void reset_launch_count() { g_launches = 0; }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "photon_b200 sm_100a kernels (tcgen05/TMEM/TMA GEMM + attention, fused norm/loss/optimizer, NVLink collectives)";
+  m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("d"), py::arg("a_mn") = 0, py::arg("b_mn") = 0, py::arg("epi") = 0,
+        py::arg("bias") = py::none(), py::arg("aux") = py::none(), py::arg("d2") = py::none(), py::arg("accumulate") = false,
+        py::arg("alpha") = 1.0);
+  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
+  m.def("embed_fwd", &embed_fwd);
+  m.def("embed_bwd", &embed_bwd);
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("col_sum", &col_sum);
+  m.def("cross_entropy", &cross_entropy);
+  m.def("flat_l2_norm", &flat_l2_norm);
+  m.def("axpby", &axpby);
+  m.def("cast_bf16", &cast_bf16);
+  m.def("fused_optimizer", &fused_optimizer);
+  m.def("ipc_alloc", &ipc_alloc);
+  m.def("ipc_get_handle", &ipc_get_handle);
+  m.def("ipc_open_handle", &ipc_open_handle);
+  m.def("ipc_close", &ipc_close);
+  m.def("ipc_free", &ipc_free);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("fed_round", &fed_round);
+  m.def("ddp_allreduce", &ddp_allreduce);
+  m.def("set_wsum", &set_wsum);
+  m.def("ctl_sums_word_offset", &pb::ctl_sums_word_offset);
+  m.def("launch_count", &launch_count);
+  m.def("reset_launch_count", &reset_launch_count);
+  m.attr("CTL_WORDS") = pb::CTL_WORDS;
+  m.attr("EPI_BF16") = int(pb::EPI_BF16);
+  m.attr("EPI_RESIDUAL") = int(pb::EPI_RESIDUAL);
+  m.attr("EPI_GELU_DUAL") = int(pb::EPI_GELU_DUAL);
+  m.attr("EPI_DGELU") = int(pb::EPI_DGELU);
+  m.attr("EPI_F32") = int(pb::EPI_F32);
+}

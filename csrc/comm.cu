@@ -1,0 +1,261 @@
+// In-kernel NVLink collectives fused with their adjacent compute (no NCCL on these paths):
+//
+//   fed_round_kernel   R1+R2 of a federated round: every GPU owns 1/n of the flat
+//                      parameter index space; it pulls that slice of every peer's weighted client sum
+//                      with P2P loads, forms the pseudo-gradient, applies the server optimizer
+//                      (FedAvg / Nesterov / FedMom / FedAdam / FedYogi) on its shard of (x, m, v) in
+//                      registers, accumulates the L2-norm by-products, and pushes the new fp32 values
+//                      AND their bf16 cast straight into every peer's parameter planes with P2P stores.
+//   ddp_allreduce_kernel  N1: one-pass reduce-scatter + all-gather of the flat gradient bucket over peer
+//                      pointers, fused with the mean (1/n) and the squared-norm partials for clipping.
+//
+// Cross-GPU ordering uses epoch-valued flags in each rank's control page (st.release.sys /
+// ld.acquire.sys); all CTAs are co-resident (grid <= #SMs) so in-kernel spinning is deadlock-free.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "comm.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  return v;
+}
+
+// Control page layout (uint32 words) inside every rank's arena:
+//   [0,8)   start flags (slot r written by rank r)      [8,16)  end flags
+//   [16]    local "go" flag (block 0 -> other blocks)   [17]    local done-block counter
+//   [32,34) float wsum (this rank's sum of client weights)   [64..) double sq_parts[8], double sums[8]
+constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
+
+__device__ __forceinline__ void grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
+  uint32_t* mine = c.ctl[c.rank];
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < c.n) {
+      st_release_sys(c.ctl[threadIdx.x] + CP_START + c.rank, epoch);                 // tell peer t "rank is here"
+      while (ld_acquire_sys(mine + CP_START + threadIdx.x) < epoch) {                 // wait for peer t
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mine + CP_GO), "r"(epoch) : "memory");
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + CP_GO) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+  }
+}
+
+// returns true in the LAST block to finish (after all blocks' peer stores were fenced)
+__device__ __forceinline__ bool grid_done(const CommCtl& c) {
+  __shared__ int last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(c.ctl[c.rank] + CP_DONE, 1u);
+    last = (prev == gridDim.x - 1);
+    if (last) c.ctl[c.rank][CP_DONE] = 0;
+  }
+  __syncthreads();
+  return last != 0;
+}
+
+__device__ __forceinline__ void peer_barrier_end(const CommCtl& c, uint32_t epoch) {
+  uint32_t* mine = c.ctl[c.rank];
+  __threadfence_system();
+  if (threadIdx.x < c.n) {
+    st_release_sys(c.ctl[threadIdx.x] + CP_END + c.rank, epoch);
+    while (ld_acquire_sys(mine + CP_END + threadIdx.x) < epoch) {
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------ R1 + R2
+__global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, const CommCtl c, const uint32_t epoch) {
+  grid_peer_barrier_start(c, epoch);
+
+  // total client weight = sum over ranks (each rank published its own before the launch)
+  float wtot = 0.f;
+  for (int p = 0; p < c.n; ++p) wtot += __uint_as_float(ld_acquire_sys(c.ctl[p] + CP_WSUM));
+  const bool skip = !(wtot > 0.f);  // no successful client anywhere -> keep the model (ignore_failed_rounds)
+  const float inv = skip ? 0.f : a.avg_scale / wtot;
+
+  float s_pg = 0.f, s_a = 0.f, s_x = 0.f, s_m = 0.f, s_v = 0.f;
+  const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
+  for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4 && !skip;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
+      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    float av[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+    const float4 X = reinterpret_cast<const float4*>(a.x)[i];
+    float xv[4] = {X.x, X.y, X.z, X.w};
+    float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
+    if (a.kind >= 1) {
+      const float4 Mv = reinterpret_cast<const float4*>(a.m)[i];
+      mv[0] = Mv.x, mv[1] = Mv.y, mv[2] = Mv.z, mv[3] = Mv.w;
+    }
+    if (a.kind >= 3) {
+      const float4 Vv = reinterpret_cast<const float4*>(a.v)[i];
+      vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float pg = xv[k] - av[k];
+      s_pg += pg * pg;
+      s_a += av[k] * av[k];
+      switch (a.kind) {
+        case 0:  // FedAvg
+          xv[k] -= a.lr * pg;
+          break;
+        case 1:  // Nesterov (torch SGD form)
+          mv[k] = a.mu * mv[k] + pg;
+          xv[k] -= a.lr * (pg + a.mu * mv[k]);
+          break;
+        case 2: {  // FedMom
+          const float vn = xv[k] - a.lr * pg;
+          xv[k] = (1.f + a.mu) * vn - a.mu * mv[k];
+          mv[k] = vn;
+          break;
+        }
+        default: {  // 3 FedAdam, 4 FedYogi
+          mv[k] = a.beta1 * mv[k] + (1.f - a.beta1) * pg;
+          const float g2 = pg * pg;
+          if (a.kind == 3) {
+            vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g2;
+          } else {
+            const float d = g2 - vv[k];
+            vv[k] += (1.f - a.beta2) * g2 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+          }
+          const float step = a.eta * (mv[k] * a.inv_bc1) / (sqrtf(vv[k] * a.inv_bc2) + a.tau);
+          xv[k] += a.sign * step;
+          break;
+        }
+      }
+      s_x += xv[k] * xv[k];
+      s_m += mv[k] * mv[k];
+      s_v += vv[k] * vv[k];
+    }
+    if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    // R2: broadcast the updated slice (fp32 master + bf16 compute copy) into every rank's planes
+    const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    uint2 nb;
+    nb.x = pack_bf16(xv[0], xv[1]), nb.y = pack_bf16(xv[2], xv[3]);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {
+      st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
+      if (a.xs[p]) st_peer_u2(reinterpret_cast<uint2*>(a.xs[p]) + i, nb);
+    }
+  }
+  // norm by-products (this rank's shard): block reduce -> fp64 atomics in the local control page
+  __shared__ float red[5][16];
+  float vals[5] = {s_pg, s_a, s_x, s_m, s_v};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    vals[j] = warp_sum(vals[j]);
+    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = vals[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    atomicAdd(reinterpret_cast<double*>(c.ctl[c.rank] + CP_SUMS) + threadIdx.x, double(t));
+  }
+  if (grid_done(c)) peer_barrier_end(c, epoch);
+}
+
+// ------------------------------------------------------------------------------------------ N1
+__global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs a, const CommCtl c, const uint32_t epoch) {
+  grid_peer_barrier_start(c, epoch);
+  const float inv = 1.0f / c.n;
+  float sq = 0.f;
+  const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
+  for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {
+      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.buf[p]) + i);
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    acc.x *= inv, acc.y *= inv, acc.z *= inv, acc.w *= inv;
+    sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.buf[p]) + i, acc);
+  }
+  __shared__ float red[16];
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  double* sums = reinterpret_cast<double*>(c.ctl[c.rank] + CP_SUMS);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(sums + 7, double(t));
+  }
+  if (grid_done(c)) {
+    if (threadIdx.x < c.n) {  // publish this shard's squared norm to every rank
+      const double mine = *reinterpret_cast<volatile double*>(sums + 7);
+      double* dst = reinterpret_cast<double*>(c.ctl[threadIdx.x] + CP_SQPARTS) + c.rank;
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(mine) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sums[7] = 0.0;
+    peer_barrier_end(c, epoch);
+  }
+}
+
+__global__ void allreduce_norm_finalize_kernel(const uint32_t* ctl, int n, float* out_norm) {
+  const double* parts = reinterpret_cast<const double*>(ctl + CP_SQPARTS);
+  double t = 0.0;
+  for (int p = 0; p < n; ++p) t += parts[p];
+  *out_norm = float(sqrt(t));
+}
+
+__global__ void set_wsum_kernel(uint32_t* ctl, float w, int zero_sums) {
+  ctl[CP_WSUM] = __float_as_uint(w);
+  if (zero_sums) {
+    double* s = reinterpret_cast<double*>(ctl + CP_SUMS);
+    for (int i = 0; i < 7; ++i) s[i] = 0.0;
+  }
+}
+
+}  // namespace
+
+int ctl_sums_word_offset() { return CP_SUMS; }
+
+void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st) {
+  if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("fed_round: shard bounds must be multiples of 4");
+  fed_round_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fed_round launch: ") + cudaGetErrorString(e));
+}
+void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st) {
+  if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("ddp_allreduce: shard bounds must be multiples of 4");
+  ddp_allreduce_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_allreduce launch: ") + cudaGetErrorString(e));
+  if (out_norm) allreduce_norm_finalize_kernel<<<1, 1, 0, st>>>(c.ctl[c.rank], c.n, out_norm);
+}
+void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st) { set_wsum_kernel<<<1, 1, 0, st>>>(ctl, w, zero_sums ? 1 : 0); }
+
+}  // namespace pb

@@ -1,0 +1,41 @@
+// Host API of the fused NVLink collectives (see comm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+constexpr int MAX_PEERS = 8;
+constexpr int CTL_WORDS = 256;  // control page size in uint32 words (1 KiB)
+
+struct CommCtl {
+  uint32_t* ctl[MAX_PEERS];  // control page of every rank (peer-mapped)
+  int n;
+  int rank;
+};
+
+struct FedRoundArgs {
+  const float* acc[MAX_PEERS];  // per-rank unnormalised weighted sum of its clients' params (full length)
+  float* xg[MAX_PEERS];         // per-rank fp32 global/master plane (broadcast target); xg[rank] == x
+  void* xs[MAX_PEERS];          // per-rank bf16 compute copy (may be null)
+  float* x;                     // local server copy (only [lo,hi) is read/updated)
+  float* m;
+  float* v;
+  long long lo, hi;             // this rank's shard, multiples of 4
+  int kind;                     // 0 fedavg, 1 nesterov, 2 fedmom, 3 fedadam, 4 fedyogi
+  float avg_scale;              // scaling_fn(K)
+  float lr, mu;                 // fedavg / nesterov / fedmom
+  float eta, beta1, beta2, tau, inv_bc1, inv_bc2, sign;  // adam / yogi (sign=-1 descent, +1 reference compat)
+};
+
+struct AllReduceArgs {
+  float* buf[MAX_PEERS];
+  long long lo, hi;
+};
+
+void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st);
+void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
+void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st);
+int ctl_sums_word_offset();
+
+}  // namespace pb

@@ -1,0 +1,394 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
+//
+//   * operands staged global->shared by TMA (cp.async.bulk.tensor, 128B swizzle), 3-stage mbarrier ring
+//   * tcgen05.mma (kind::f16, M=128 N=256 K=16) issued by ONE thread, accumulators in TMEM
+//     (2 x 256 fp32 columns, double-buffered so tile i's epilogue overlaps tile i+1's MMAs)
+//   * epilogue warps: tcgen05.ld TMEM->registers, fused bias / residual / GELU / dGELU, pack,
+//     swizzled st.shared, TMA store (or TMA reduce-add for fp32 weight-gradient accumulation)
+//   * either operand may be K-major ([rows,K] row-major) or MN-major ([K,rows] row-major) so forward,
+//     dgrad (B = W as stored) and wgrad (A = dY^T, B = X^T as stored) need no transposes.
+//
+// Replaces the cuBLASLt calls the reference reaches through torch (SURVEY §2.5 K3,K5-K8,K10).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "gemm_tcgen05.h"
+#include "ptx.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int STAGES = 3;
+constexpr int A_STAGE = BM * BK * 2;  // 16 KiB
+constexpr int B_STAGE = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+constexpr int EPI_BUFS = 4;
+constexpr int EPI_BUF = 128 * 128;  // 128 rows x 128 B (one swizzle atom wide)
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF + 256 + 1024;
+constexpr int TMEM_COLS = 512;
+
+struct Params {
+  int M, N, K;
+  int tiles_m, tiles_n, m_fastest;
+  const float* bias;            // [N] fp32 or nullptr
+  const __nv_bfloat16* aux;     // residual (EPI_RESIDUAL) or pre-activation z (EPI_DGELU)
+  long long ld_aux;             // row stride of aux, elements
+  int accumulate;               // EPI_F32: reduce-add into D instead of overwrite
+  float alpha;                  // scale applied to the accumulator before the epilogue
+};
+
+template <int A_MN, int B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * A_STAGE;
+  uint8_t* sE = sB + STAGES * B_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPI_BUFS * EPI_BUF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+    if (EPI == EPI_GELU_DUAL) prefetch_tmap(&tmD2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ======================= TMA producer (one thread) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
+        const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE;
+          uint8_t* b_dst = sB + stage * B_STAGE;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * (BK * 128), &tmB, &full[stage], n_blk * BN + j * 64, kb * BK);
+          } else {
+            tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_blk * BN);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
+          const uint32_t b_base = smem_u32(sB + stage * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * (UK * 128), BK * 128, 1024)
+                                        : make_smem_desc_sw128(a_base + k * (UK * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * (UK * 128), BK * 128, 1024)
+                                        : make_smem_desc_sw128(b_base + k * (UK * 2), 16, 1024);
+            tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue (4 warps, one TMEM lane quadrant each) =======================
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    constexpr int CW = (EPI == EPI_F32) ? 32 : 64;             // columns per staged chunk (128 B wide)
+    constexpr int STORES = (EPI == EPI_GELU_DUAL) ? 2 : 1;      // staging buffers consumed per chunk
+    int ebuf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t swz = (row_in_tile & 7);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
+      const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / CW; ++c) {
+        const int col0 = n_blk * BN + c * CW;
+        if (col0 >= p.N) break;  // whole chunk out of range (uniform)
+        float v[CW];
+        {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * CW;
+          tmem_ld_32x32(taddr, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (CW == 64) {
+            tmem_ld_32x32(taddr + 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[(CW == 64 ? 32 : 0) + j] = __uint_as_float(r[j]) * p.alpha;
+          }
+        }
+        if (EPI != EPI_F32 && p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            if (col0 + j < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+        }
+        uint8_t* buf0 = sE + ebuf * EPI_BUF;
+        uint8_t* buf1 = sE + ((ebuf + 1) % EPI_BUFS) * EPI_BUF;
+        if (issuer) tma_wait_read<EPI_BUFS / STORES - 1>();
+        named_bar_sync(1, 128);
+        if (EPI == EPI_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(buf0 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;
+          }
+        } else {
+          if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
+            const __nv_bfloat16* arow = p.aux + row * p.ld_aux + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (row_ok && col0 + 8 * j < p.N) {
+                const uint4 a = *reinterpret_cast<const uint4*>(arow + 8 * j);
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = unpack_bf16(w[t]);
+                  if (EPI == EPI_RESIDUAL) {
+                    v[8 * j + 2 * t] += f.x;
+                    v[8 * j + 2 * t + 1] += f.y;
+                  } else {
+                    v[8 * j + 2 * t] *= gelu_grad(f.x);
+                    v[8 * j + 2 * t + 1] *= gelu_grad(f.y);
+                  }
+                }
+              }
+            }
+          }
+          if (EPI == EPI_GELU_DUAL) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+              o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(buf1 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;  // z (pre-activation)
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = gelu_exact(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+            o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(buf0 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          if (EPI == EPI_F32 && p.accumulate) {
+            tma_reduce_add_2d(&tmD, buf0, col0, m_blk * BM);
+          } else {
+            tma_store_2d(&tmD, buf0, col0, m_blk * BM);
+          }
+          if (EPI == EPI_GELU_DUAL) tma_store_2d(&tmD2, buf1, col0, m_blk * BM);
+          tma_commit();
+        }
+        ebuf = (ebuf + STORES) % EPI_BUFS;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer) tma_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------ host
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      throw std::runtime_error("photon_b200: cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint64_t inner, uint64_t outer,
+                         uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld_bytes & 15))
+    throw std::runtime_error("photon_b200 TMA: base pointer and row stride must be 16-byte aligned");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = is_float32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = get_encode()(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("photon_b200: cuTensorMapEncodeTiled failed, code " + std::to_string(int(r)));
+  return m;
+}
+
+template <int A_MN, int B_MN, int EPI>
+static void launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
+                        const Params& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("gemm smem attr: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, td, td2, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
+}
+
+void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return;
+  if (g.N % 8) throw std::runtime_error("photon_b200 gemm: N must be a multiple of 8");
+  const bool f32 = g.epi == EPI_F32;
+  // A: K-major -> dims {K, M}, box {64, 128};  MN-major -> dims {M, K}, box {64(M), 64(K)}
+  CUtensorMap ta = g.a_mn ? make_tmap_2d(g.A, 2, false, g.M, g.K, g.lda * 2, 64, BK)
+                          : make_tmap_2d(g.A, 2, false, g.K, g.M, g.lda * 2, BK, BM);
+  CUtensorMap tb = g.b_mn ? make_tmap_2d(g.B, 2, false, g.N, g.K, g.ldb * 2, 64, BK)
+                          : make_tmap_2d(g.B, 2, false, g.K, g.N, g.ldb * 2, BK, BN);
+  CUtensorMap td = f32 ? make_tmap_2d(g.D, 4, true, g.N, g.M, g.ldd * 4, 32, BM)
+                       : make_tmap_2d(g.D, 2, false, g.N, g.M, g.ldd * 2, 64, BM);
+  CUtensorMap td2 = td;
+  if (g.epi == EPI_GELU_DUAL) {
+    if (!g.D2) throw std::runtime_error("photon_b200 gemm: EPI_GELU_DUAL needs the pre-activation output");
+    td2 = make_tmap_2d(g.D2, 2, false, g.N, g.M, g.ldd2 * 2, 64, BM);
+  }
+  if ((g.epi == EPI_RESIDUAL || g.epi == EPI_DGELU) && (!g.aux || (g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)))
+    throw std::runtime_error("photon_b200 gemm: aux operand missing or not 16-byte aligned");
+  if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) throw std::runtime_error("photon_b200 gemm: bias must be 16-byte aligned");
+  Params p;
+  p.M = g.M, p.N = g.N, p.K = g.K;
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  // keep the larger operand streaming once: iterate the other dimension fastest
+  p.m_fastest = (double(g.N) > double(g.M)) ? 1 : 0;
+  p.bias = g.bias;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(g.aux);
+  p.ld_aux = g.ld_aux;
+  p.accumulate = g.accumulate;
+  p.alpha = g.alpha;
+  int sms = g.num_sms > 0 ? g.num_sms : 148;
+  int grid = p.tiles_m * p.tiles_n < sms ? p.tiles_m * p.tiles_n : sms;
+
+#define PB_CASE(AM, BMJ, E)                                            \
+  if (g.a_mn == AM && g.b_mn == BMJ && g.epi == E) {                   \
+    launch_inst<AM, BMJ, E>(ta, tb, td, td2, p, grid, stream);         \
+    return;                                                            \
+  }
+  PB_CASE(0, 0, EPI_BF16)
+  PB_CASE(0, 0, EPI_RESIDUAL)
+  PB_CASE(0, 0, EPI_GELU_DUAL)
+  PB_CASE(0, 0, EPI_F32)
+  PB_CASE(0, 1, EPI_BF16)
+  PB_CASE(0, 1, EPI_DGELU)
+  PB_CASE(0, 1, EPI_F32)
+  PB_CASE(1, 1, EPI_F32)
+  PB_CASE(1, 1, EPI_BF16)
+  PB_CASE(1, 0, EPI_F32)
+  PB_CASE(1, 0, EPI_BF16)
+#undef PB_CASE
+  throw std::runtime_error("photon_b200 gemm: unsupported (a_major, b_major, epilogue) combination");
+}
+
+}  // namespace pb

@@ -1,0 +1,38 @@
+// Host API of the tcgen05 GEMM family (see gemm_tcgen05.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+enum Epilogue : int {
+  EPI_BF16 = 0,       // D = bf16(acc*alpha + bias)
+  EPI_RESIDUAL = 1,   // D = bf16(acc*alpha + bias + aux)
+  EPI_GELU_DUAL = 2,  // D2 = bf16(z = acc*alpha + bias);  D = bf16(gelu(z))
+  EPI_DGELU = 3,      // D = bf16((acc*alpha + bias) * gelu'(aux))
+  EPI_F32 = 4,        // D (fp32) = acc*alpha   or  D += acc*alpha   (accumulate, TMA reduce-add)
+};
+
+struct GemmArgs {
+  const void* A = nullptr;  // bf16: K-major [M,K] (lda = row stride) or MN-major [K,M]
+  const void* B = nullptr;  // bf16: K-major [N,K] or MN-major [K,N]
+  void* D = nullptr;        // [M,N] bf16 (fp32 for EPI_F32), ldd = row stride in elements
+  void* D2 = nullptr;       // second output (EPI_GELU_DUAL), bf16 [M,N]
+  const float* bias = nullptr;
+  const void* aux = nullptr;  // bf16 [M,N]
+  int M = 0, N = 0, K = 0;
+  long long lda = 0, ldb = 0, ldd = 0, ldd2 = 0, ld_aux = 0;
+  int a_mn = 0, b_mn = 0;
+  int epi = EPI_BF16;
+  int accumulate = 0;
+  float alpha = 1.0f;
+  int num_sms = 0;
+};
+
+void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream);
+
+CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint64_t inner, uint64_t outer,
+                         uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace pb

@@ -1,0 +1,255 @@
+"""B200Engine — the MPT training step on hand-written sm_100a kernels.
+
+No autograd, no per-op dispatcher: forward and backward are an explicit
+schedule of our own kernels over preallocated bf16 activations, flat fp32
+master parameters/gradients and a flat bf16 compute shadow
+(SURVEY §2.5 (a) K1–K15 → one engine):
+
+* every linear layer = ``csrc/gemm_tcgen05.cu`` (TMA → tcgen05.mma → TMEM →
+  fused epilogue): bias, bias+residual, bias+GELU (pre-activation and
+  activation written by the same epilogue), dgrad with the stored weight
+  consumed MN-major (no transposes), dGELU fused into the dgrad epilogue, wgrad
+  with both operands MN-major accumulating in fp32 by TMA reduce-add straight
+  into the flat gradient bucket that the DDP all-reduce / optimizer consume;
+* LM head + cross-entropy chunked over tokens so the ``[T, 50368]`` logits are
+  never materialised (``[chunk, V]`` scratch that stays L2/HBM friendly);
+  the chunk's dlogits feed the dgrad/wgrad GEMMs immediately;
+* LayerNorm fwd/bwd (+ residual-gradient add), embedding gather/scatter,
+  bias-gradient column sums, loss statistics: ``csrc/fused_ops.cu``;
+* attention: ``csrc/attention_tcgen05.cu`` (``attention: b200``) or, when
+  ``kernels.attention: torch``, cuDNN/FA2 SDPA as an explicit library fallback.
+
+The module tree of :class:`MPTForCausalLM` is kept only as the *owner of names
+and initial values*: its parameters are views into the flat fp32 buffer, so the
+federated payload / checkpoint order (sorted names) is shared with the torch
+backend and the two are directly comparable in tests.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+import torch.nn.functional as F
+
+from photon_b200 import ops
+from photon_b200.models.mpt import MPTConfig, MPTForCausalLM, shift_labels
+from photon_b200.train.backend import apply_freeze
+from photon_b200.utils.flat import FlatParams
+
+
+class _LayerW:
+    """Per-block handles: bf16 weights (shadow plane), fp32 small params and fp32 grads."""
+
+    __slots__ = ("wqkv", "bqkv", "wo", "bo", "wup", "bup", "wdown", "bdown", "g1", "b1", "g2", "b2",
+                 "d_wqkv", "d_bqkv", "d_wo", "d_bo", "d_wup", "d_bup", "d_wdown", "d_bdown", "d_g1", "d_b1", "d_g2", "d_b2")
+
+
+class B200Engine:
+    kind = "b200"
+
+    def __init__(self, cfg: MPTConfig, device: torch.device | str = "cuda", precision: str = "amp_bf16",
+                 kernels: dict[str, Any] | None = None, seed: int | None = 17, frozen_layers: list[str] | None = None,
+                 unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
+                 lm_head_chunk: int = 8192) -> None:
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("B200Engine needs a CUDA (sm_100a) device")
+        if precision not in ("amp_bf16", "amp_fp8"):
+            raise NotImplementedError(f"B200Engine computes in bf16 (got precision={precision}); use kernels.*=torch for fp32/fp16")
+        if cfg.alibi or cfg.rope or cfg.qk_ln or cfg.clip_qkv or cfg.no_bias or not cfg.learned_pos_emb:
+            raise NotImplementedError("B200Engine covers the shipped MPT configs (learned positions, biases, no qk_ln/clip_qkv); "
+                                      "set kernels.*=torch for ALiBi/RoPE variants")
+        if frozen_layers or unfrozen_layers:
+            raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
+        ops.ext()  # fail loudly if the extension is missing
+        self.precision = precision
+        kernels = dict(kernels or {})
+        self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
+        self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
+        self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
+        self.flat = FlatParams(self.model, device=self.device)
+        self.bf16_params = torch.zeros(self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
+        self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
+        self.lm_head_chunk = int(lm_head_chunk)
+        self.collect_activation_stats = False
+        self.activation_stats: dict[str, float] = {}
+        self.launches_per_microbatch = 0
+        self._ws: dict[tuple[int, int], dict[str, Any]] = {}
+        self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._bind()
+        self.params_updated()
+
+    # ------------------------------------------------------------------ binding
+    def _bind(self) -> None:
+        lay, P, G, Sd = self.flat.layout, self.flat.params, self.flat.grads, self.bf16_params
+        v32 = lambda n: lay.view(P, "transformer." + n)  # noqa: E731
+        vg = lambda n: lay.view(G, "transformer." + n)  # noqa: E731
+        v16 = lambda n: lay.view(Sd, "transformer." + n)  # noqa: E731
+        self.wte16, self.wpe16 = v16("wte.weight"), v16("wpe.weight")
+        self.d_wte, self.d_wpe = vg("wte.weight"), vg("wpe.weight")
+        self.gf, self.bf, self.d_gf, self.d_bf = v32("norm_f.weight"), v32("norm_f.bias"), vg("norm_f.weight"), vg("norm_f.bias")
+        self.layers: list[_LayerW] = []
+        for i in range(self.cfg.n_layers):
+            p = f"blocks.{i}."
+            w = _LayerW()
+            w.wqkv, w.wo, w.wup, w.wdown = (v16(p + "attn.Wqkv.weight"), v16(p + "attn.out_proj.weight"),
+                                            v16(p + "ffn.up_proj.weight"), v16(p + "ffn.down_proj.weight"))
+            w.bqkv, w.bo, w.bup, w.bdown = (v32(p + "attn.Wqkv.bias"), v32(p + "attn.out_proj.bias"),
+                                            v32(p + "ffn.up_proj.bias"), v32(p + "ffn.down_proj.bias"))
+            w.g1, w.b1, w.g2, w.b2 = v32(p + "norm_1.weight"), v32(p + "norm_1.bias"), v32(p + "norm_2.weight"), v32(p + "norm_2.bias")
+            w.d_wqkv, w.d_wo, w.d_wup, w.d_wdown = (vg(p + "attn.Wqkv.weight"), vg(p + "attn.out_proj.weight"),
+                                                    vg(p + "ffn.up_proj.weight"), vg(p + "ffn.down_proj.weight"))
+            w.d_bqkv, w.d_bo, w.d_bup, w.d_bdown = (vg(p + "attn.Wqkv.bias"), vg(p + "attn.out_proj.bias"),
+                                                    vg(p + "ffn.up_proj.bias"), vg(p + "ffn.down_proj.bias"))
+            w.d_g1, w.d_b1, w.d_g2, w.d_b2 = vg(p + "norm_1.weight"), vg(p + "norm_1.bias"), vg(p + "norm_2.weight"), vg(p + "norm_2.bias")
+            self.layers.append(w)
+
+    def params_updated(self) -> None:
+        """Re-cast the bf16 compute shadow from the fp32 masters. Only needed after host-side
+        parameter loads: the fused optimizer and the round-broadcast kernels write the shadow
+        themselves (the Trainer skips this call in that case)."""
+        ops.cast_bf16(self.flat.params, self.bf16_params)
+
+    # ---------------------------------------------------------------- workspace
+    def _workspace(self, b: int, S: int) -> dict[str, Any]:
+        key = (b, S)
+        if key in self._ws:
+            return self._ws[key]
+        self._ws.clear()  # one live shape at a time (activations dominate memory)
+        c, dev = self.cfg, self.device
+        T, d, H, L = b * S, c.d_model, c.n_heads, c.n_layers
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        ws: dict[str, Any] = {"h": [bf(T, d) for _ in range(L + 1)], "layers": []}
+        for _ in range(L):
+            ws["layers"].append({"ln1": bf(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d),
+                                 "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": bf(T, d), "m2": f32(T), "r2": f32(T),
+                                 "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
+        ws.update(lnf=bf(T, d), mf=f32(T), rf=f32(T), dlnf=bf(T, d), dh=bf(T, d), dhmid=bf(T, d), dln=bf(T, d),
+                  dqkv=bf(T, 3 * d), dattn=bf(T, d), dz=bf(T, c.expansion_ratio * d), delta=f32(b, H, S),
+                  logits=bf(min(self.lm_head_chunk, T), c.vocab_size))
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _attention_fwd(self, lw: dict[str, Any], b: int, S: int) -> None:
+        c = self.cfg
+        scale = 1.0 / math.sqrt(c.d_head)
+        if self.attn_mode == "b200":
+            ops.attention_fwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model), lw["lse"], c.n_heads, scale, True)
+            return
+        q, k, v = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
+        lw["attn"].view(b, S, c.n_heads, c.d_head).copy_(o.transpose(1, 2))
+
+    def _attention_bwd(self, lw: dict[str, Any], ws: dict[str, Any], b: int, S: int) -> None:
+        c = self.cfg
+        scale = 1.0 / math.sqrt(c.d_head)
+        if self.attn_mode == "b200":
+            ops.attention_bwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model),
+                              ws["dattn"].view(b, S, c.d_model), lw["lse"], ws["dqkv"].view(b, S, 3 * c.d_model), ws["delta"],
+                              c.n_heads, scale, True)
+            return
+        with torch.enable_grad():
+            qkv = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).detach().requires_grad_(True)
+            q, k, v = qkv.permute(2, 0, 3, 1, 4)
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
+            (g,) = torch.autograd.grad(o, qkv, ws["dattn"].view(b, S, c.n_heads, c.d_head).transpose(1, 2))
+        ws["dqkv"].view(b, S, 3, c.n_heads, c.d_head).copy_(g)
+
+    def _forward(self, ids: torch.Tensor, ws: dict[str, Any]) -> None:
+        c = self.cfg
+        b, S = ids.shape
+        h = ws["h"]
+        ops.embed_fwd(ids.reshape(-1), self.wte16, self.wpe16, h[0], S)
+        for i, (w, lw) in enumerate(zip(self.layers, ws["layers"])):
+            ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
+            ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
+            self._attention_fwd(lw, b, S)
+            ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
+            ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)
+            ops.linear_gelu_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])
+            ops.linear_fwd(lw["u"], w.wdown, w.bdown, h[i + 1], residual=lw["hmid"])
+            if self.collect_activation_stats:
+                x = h[i + 1][:S].float()
+                self.activation_stats[f"l2_norm/block_{i}"] = float(x.norm(dim=-1).mean())
+                self.activation_stats[f"max/block_{i}"] = float(x.abs().max())
+        ops.layernorm_fwd(h[c.n_layers], self.gf, self.bf, ws["lnf"], ws["mf"], ws["rf"], c.norm_eps)
+
+    def _head(self, ws: dict[str, Any], targets: torch.Tensor, grad_scale: float, train: bool) -> None:
+        """Chunked LM head + fused CE (+ immediate head backward when training)."""
+        T = targets.numel()
+        step = ws["logits"].shape[0]
+        for lo in range(0, T, step):
+            hi = min(T, lo + step)
+            logits = ws["logits"][: hi - lo]
+            ops.gemm(ws["lnf"][lo:hi], self.wte16, logits)
+            ops.cross_entropy(logits, targets[lo:hi], grad_scale, train, self._stats, None, self.unigram_log_probs)
+            if train:
+                ops.linear_dgrad(logits, self.wte16, ws["dlnf"][lo:hi])
+                ops.linear_wgrad(logits, ws["lnf"][lo:hi], self.d_wte, accumulate=True)
+
+    # ----------------------------------------------------------------- backward
+    def _backward(self, ids: torch.Tensor, ws: dict[str, Any]) -> None:
+        c = self.cfg
+        b, S = ids.shape
+        h = ws["h"]
+        dh, dhmid, dln = ws["dh"], ws["dhmid"], ws["dln"]
+        ops.layernorm_bwd(ws["dlnf"], h[c.n_layers], self.gf, ws["mf"], ws["rf"], None, dh, self.d_gf, self.d_bf)
+        for i in range(c.n_layers - 1, -1, -1):
+            w, lw = self.layers[i], ws["layers"][i]
+            # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
+            ops.col_sum(dh, w.d_bdown)
+            ops.linear_wgrad(dh, lw["u"], w.d_wdown)
+            ops.linear_dgrad(dh, w.wdown, ws["dz"], gelu_pre=lw["z"])
+            ops.col_sum(ws["dz"], w.d_bup)
+            ops.linear_wgrad(ws["dz"], lw["ln2"], w.d_wup)
+            ops.linear_dgrad(ws["dz"], w.wup, dln)
+            ops.layernorm_bwd(dln, lw["hmid"], w.g2, lw["m2"], lw["r2"], dh, dhmid, w.d_g2, w.d_b2)
+            # ---- attention: hmid = h[i] + out_proj(attn(qkv(ln1(h[i]))))
+            ops.col_sum(dhmid, w.d_bo)
+            ops.linear_wgrad(dhmid, lw["attn"], w.d_wo)
+            ops.linear_dgrad(dhmid, w.wo, ws["dattn"])
+            self._attention_bwd(lw, ws, b, S)
+            ops.col_sum(ws["dqkv"], w.d_bqkv)
+            ops.linear_wgrad(ws["dqkv"], lw["ln1"], w.d_wqkv)
+            ops.linear_dgrad(ws["dqkv"], w.wqkv, dln)
+            ops.layernorm_bwd(dln, h[i], w.g1, lw["m1"], lw["r1"], dhmid, dh, w.d_g1, w.d_b1)
+        ops.embed_bwd(ids.reshape(-1), dh, self.d_wte, self.d_wpe, S)
+
+    # ---------------------------------------------------------------- protocol
+    def fwd_bwd(self, ids: torch.Tensor, denom: float, scale: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
+        """Accumulate d(Σ token-loss · scale / denom) into ``flat.grads``; returns (loss_sum, n_tokens)."""
+        n0 = ops.launch_count()
+        b, S = ids.shape
+        ws = self._workspace(b, S)
+        targets = shift_labels(ids).reshape(-1)
+        self._stats.zero_()
+        self._forward(ids, ws)
+        self._head(ws, targets, scale / denom, train=True)
+        self._backward(ids, ws)
+        self.launches_per_microbatch = ops.launch_count() - n0
+        st = self._stats.clone()
+        return st[0], st[1]
+
+    @torch.no_grad()
+    def eval_stats(self, ids: torch.Tensor) -> dict[str, torch.Tensor]:
+        b, S = ids.shape
+        ws = self._workspace(b, S)
+        targets = shift_labels(ids).reshape(-1)
+        self._stats.zero_()
+        self._forward(ids, ws)
+        self._head(ws, targets, 0.0, train=False)
+        st = self._stats.clone()
+        out = {"loss_sum": st[0], "n_tokens": st[1], "n_correct": st[2]}
+        if self.unigram_log_probs is not None:
+            out["unigram_loss_sum"] = st[3]
+        return out
+
+    def train_mode(self, on: bool = True) -> None:
+        self.model.train(on)
+
+    def close(self) -> None:
+        self._ws.clear()

@@ -1,1 +1,178 @@
+"""Python face of the hand-written sm_100a kernels (``photon_b200._C``).
 
+Every function here launches OUR kernels; nothing silently falls back to a
+PyTorch op.  If the extension is missing on a machine that has a CUDA device
+the import error is raised loudly (the driver records which ``.so`` files the
+GPU tests actually loaded).  On CPU-only machines the extension still imports
+(it is cross-compiled) but these wrappers are never called.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+
+_EXT: Any = None
+
+
+def ext() -> Any:
+    """Load (and cache) the in-tree extension; raise loudly if it is absent."""
+    global _EXT
+    if _EXT is None:
+        try:
+            from photon_b200 import _C  # type: ignore[attr-defined]
+        except ImportError as e:  # pragma: no cover - depends on the box
+            raise ImportError(
+                "photon_b200._C (sm_100a kernels) is not built. Run `python -m photon_b200.build` "
+                "(or __graft_entry__.build()) — refusing to fall back to PyTorch ops on the GPU path.") from e
+        _EXT = _C
+    return _EXT
+
+
+def have_ext() -> bool:
+    try:
+        ext()
+        return True
+    except ImportError:
+        return False
+
+
+def launch_count() -> int:
+    return int(ext().launch_count())
+
+
+def reset_launch_count() -> None:
+    ext().reset_launch_count()
+
+
+# --------------------------------------------------------------------------------- GEMM
+EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         epi: int = EPI_BF16, bias: torch.Tensor | None = None, aux: torch.Tensor | None = None,
+         out2: torch.Tensor | None = None, accumulate: bool = False, alpha: float = 1.0) -> torch.Tensor:
+    """``out[M,N] = epilogue(alpha * A @ B^T)`` on tcgen05 tensor cores.
+
+    ``a``: ``[M,K]`` (K-major) or ``[K,M]`` when ``a_mn``; ``b``: ``[N,K]`` or ``[K,N]`` when ``b_mn``."""
+    ext().gemm(a, b, out, int(a_mn), int(b_mn), int(epi), bias, aux, out2, bool(accumulate), float(alpha))
+    return out
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, out: torch.Tensor,
+               residual: torch.Tensor | None = None) -> torch.Tensor:
+    """y = x @ w^T + bias (+ residual) — x [T,K], w [N,K] (bf16), bias fp32."""
+    return gemm(x, w, out, epi=EPI_RESIDUAL if residual is not None else EPI_BF16, bias=bias, aux=residual)
+
+
+def linear_gelu_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, pre: torch.Tensor,
+                    act: torch.Tensor) -> torch.Tensor:
+    """pre = x @ w^T + bias ; act = gelu(pre) — both written by the same epilogue."""
+    return gemm(x, w, act, epi=EPI_GELU_DUAL, bias=bias, out2=pre)
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, gelu_pre: torch.Tensor | None = None) -> torch.Tensor:
+    """dx = dy @ w  (w stored [N,K] → consumed MN-major, no transpose); optional ``* gelu'(pre)``."""
+    return gemm(dy, w, dx, b_mn=True, epi=EPI_DGELU if gelu_pre is not None else EPI_BF16, aux=gelu_pre)
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, accumulate: bool = True, alpha: float = 1.0) -> torch.Tensor:
+    """dw[N,K] (+)= dy^T @ x in fp32 (both operands consumed MN-major; TMA reduce-add when accumulating)."""
+    return gemm(dy, x, dw, a_mn=True, b_mn=True, epi=EPI_F32, accumulate=accumulate, alpha=alpha)
+
+
+# ---------------------------------------------------------------------------- fused ops
+def embed_fwd(ids: torch.Tensor, wte: torch.Tensor, wpe: torch.Tensor | None, out: torch.Tensor, seq_len: int) -> torch.Tensor:
+    ext().embed_fwd(ids, wte, wpe, out, int(seq_len))
+    return out
+
+
+def embed_bwd(ids: torch.Tensor, dh: torch.Tensor, dwte: torch.Tensor, dwpe: torch.Tensor | None, seq_len: int) -> None:
+    ext().embed_bwd(ids, dh, dwte, dwpe, int(seq_len))
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, y: torch.Tensor, mean: torch.Tensor,
+                  rstd: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    ext().layernorm_fwd(x, gamma, beta, y, mean, rstd, float(eps))
+    return y
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                  dres: torch.Tensor | None, dx: torch.Tensor, dgamma: torch.Tensor | None, dbeta: torch.Tensor | None) -> torch.Tensor:
+    ext().layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta)
+    return dx
+
+
+def col_sum(dy: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[j] += Σ_t dy[t,j] (bias gradients)."""
+    ext().col_sum(dy, out)
+    return out
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, grad_scale: float, write_grad: bool, stats: torch.Tensor,
+                  row_lse: torch.Tensor | None = None, unigram_logp: torch.Tensor | None = None) -> None:
+    """In place: logits → dlogits (when ``write_grad``); stats[0..3] += (Σloss, #valid, #correct, Σunigram)."""
+    ext().cross_entropy(logits, targets, float(grad_scale), bool(write_grad), stats, row_lse, unigram_logp)
+
+
+_NORM_SCRATCH: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def flat_l2_norm(x: torch.Tensor) -> torch.Tensor:
+    """‖x‖₂ of a flat fp32 buffer as a 0-dim device tensor (no host sync)."""
+    key = x.device.index or 0
+    if key not in _NORM_SCRATCH:
+        _NORM_SCRATCH[key] = (torch.zeros(1, dtype=torch.float64, device=x.device), torch.zeros(1, dtype=torch.float32, device=x.device))
+    scratch, out = _NORM_SCRATCH[key]
+    ext().flat_l2_norm(x, scratch, out)
+    return out[0]
+
+
+def axpby_(acc: torch.Tensor, x: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    ext().axpby(acc, x, float(a), float(b))
+    return acc
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    ext().cast_bf16(src, dst)
+    return dst
+
+
+_KIND = {"adopt": 0, "decoupled_adamw": 1, "sgd": 2}
+
+
+def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | None) -> None:
+    """One fused multi-tensor step for a :class:`photon_b200.train.optim.FlatOptimizer`."""
+    flat = opt.flat
+    kind = _KIND[opt.name]
+    first = kind == 0 and opt.step_count == 0
+    decay, clip, step_size, inv_sqrt_bc2 = 1.0, float("inf"), 0.0, 1.0
+    if kind == 0:
+        if opt.weight_decay and getattr(opt, "decouple", True):
+            decay = 1.0 - lr * opt.weight_decay
+        if opt.clip_exp is not None and not first:
+            clip = float(opt.step_count) ** opt.clip_exp
+    elif kind == 1:
+        t = opt.step_count + 1
+        decay = 1.0 - (lr / opt.initial_lr) * opt.weight_decay if opt.weight_decay else 1.0
+        step_size = lr / (1.0 - opt.beta1 ** t)
+        inv_sqrt_bc2 = 1.0 / math.sqrt(1.0 - opt.beta2 ** t)
+    else:
+        decay = 1.0 - lr * opt.weight_decay if opt.weight_decay else 1.0
+    gm = None
+    if grad_mult is not None:
+        gm = grad_mult if torch.is_tensor(grad_mult) else torch.tensor(float(grad_mult), device=flat.params.device)
+        gm = gm.to(torch.float32).reshape(1)
+    ext().fused_optimizer(flat.params, flat.grads, opt.exp_avg, opt.exp_avg_sq, opt.bf16_shadow, kind, first, float(lr),
+                          opt.beta1, opt.beta2, opt.eps, float(decay), float(clip), float(step_size), float(inv_sqrt_bc2), gm)
+
+
+# ---------------------------------------------------------------------------- attention
+def attention_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, n_heads: int, scale: float, causal: bool = True) -> None:
+    ext().attention_fwd(qkv, out, lse, int(n_heads), float(scale), bool(causal))
+
+
+def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor,
+                  delta: torch.Tensor, n_heads: int, scale: float, causal: bool = True) -> None:
+    ext().attention_bwd(qkv, out, dout, lse, dqkv, delta, int(n_heads), float(scale), bool(causal))

@@ -1,1 +1,4 @@
-
+from photon_b200.strategy.aggregation import StreamingMean, aggregate_inplace, weighted_average, weighted_loss_avg
+from photon_b200.strategy.dispatcher import dispatch_strategy
+from photon_b200.strategy.strategies import (FedAdam, FedAvgEfficient, FedMom, FedNesterov, FedYogi, ServerStrategy,
+                                            server_opt_step)

@@ -257,7 +257,8 @@ class Trainer:
             self.log({"l2_norm/grad/clipped_from": gnorm})  # device scalar; floated lazily below
         if not skip:
             st.optimizer.step(st.scheduler(st.timestamp.batch), grad_mult)
-            st.backend.params_updated()
+            if not (st.optimizer.use_kernel and st.optimizer.bf16_shadow is not None):
+                st.backend.params_updated()
         self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok}
         st.timestamp.advance_batch(samples=B * self.world_size, tokens=B * S * self.world_size)
 
