@@ -1,0 +1,133 @@
+"""R1 + R2 of a federated round as ONE fused NVLink kernel per GPU.
+
+Host protocol (per round, per GPU):
+
+1. ``begin_round()`` zeroes the local accumulation plane;
+2. every client that finishes on this GPU calls ``add_client(params, n_k)`` —
+   ``acc += n_k · params`` (one fused axpby; the streaming mean of
+   ref: photon/strategy/aggregation.py:57-75 without ever leaving HBM);
+3. ``finish_round(t)`` publishes this GPU's Σn_k and launches
+   ``fed_round_kernel`` (``csrc/comm.cu``): P2P-pull the peers' slices of
+   ``acc``, normalise by the global Σn_k, server optimizer on this GPU's shard of
+   (x, m, v), P2P-push the new fp32 slice **and its bf16 cast** into every GPU's
+   global planes, L2-norm by-products.  No NCCL, no host copies
+   (ref host path: photon/server/fit_utils.py:41-217,
+   photon/server/broadcast_utils.py:60-201).
+
+A failed client simply never calls ``add_client`` → its weight is absent from Σn_k,
+which is the participation-mask semantics of SURVEY §5.3.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+
+from photon_b200 import ops
+from photon_b200.parallel.symm import SymmArena
+from photon_b200.strategy.strategies import ServerStrategy
+
+_KIND = {"fedavg": 0, "nesterov": 1, "fedmom": 2, "fedadam": 3, "fedyogi": 4}
+
+
+class NvlFedRound:
+    def __init__(self, total: int, strategy: ServerStrategy, *, rank: int = 0, world_size: int = 1,
+                 device: torch.device | int | None = None, group: Any = None, devices: list[int] | None = None,
+                 bf16_shadow: bool = True) -> None:
+        if total % 4:
+            raise ValueError("flat length must be a multiple of 4")
+        self.total, self.strategy = int(total), strategy
+        planes = {"acc": (total, torch.float32), "xg": (total, torch.float32)}
+        if bf16_shadow:
+            planes["xs"] = (total, torch.bfloat16)
+        self.arena = SymmArena(planes, rank=rank, world_size=world_size, device=device, group=group, devices=devices)
+        self.n_local = len(self.arena.devices) if self.arena.single else 1
+        self.has_shadow = bf16_shadow
+        self._wsum = [0.0] * self.n_local
+        # server moment shards live outside the arena (never read by peers); full length keeps indexing trivial
+        self._m: list[torch.Tensor | None] = []
+        self._v: list[torch.Tensor | None] = []
+        for i in range(self.n_local):
+            dev = torch.device("cuda", self.arena.devices[i])
+            self._m.append(torch.zeros(total, device=dev) if strategy.n_moments >= 1 else None)
+            self._v.append(torch.zeros(total, device=dev) if strategy.n_moments >= 2 else None)
+
+    # ------------------------------------------------------------------ planes
+    def _r(self, local: int) -> int | None:
+        return local if self.arena.single else None
+
+    def global_params(self, local: int = 0) -> torch.Tensor:
+        return self.arena.plane("xg", self._r(local))
+
+    def global_shadow(self, local: int = 0) -> torch.Tensor | None:
+        return self.arena.plane("xs", self._r(local)) if self.has_shadow else None
+
+    def acc(self, local: int = 0) -> torch.Tensor:
+        return self.arena.plane("acc", self._r(local))
+
+    def set_global(self, params: torch.Tensor) -> None:
+        """Install the initial global model on every local GPU (fp32 + bf16 cast)."""
+        for i in range(self.n_local):
+            g = self.global_params(i)
+            g.copy_(params.to(g.device))
+            if self.has_shadow:
+                ops.cast_bf16(g, self.global_shadow(i))
+
+    def set_moments(self, m: torch.Tensor | None, v: torch.Tensor | None) -> None:
+        for i in range(self.n_local):
+            if m is not None and self._m[i] is not None:
+                self._m[i].copy_(m.to(self._m[i].device))
+            if v is not None and self._v[i] is not None:
+                self._v[i].copy_(v.to(self._v[i].device))
+
+    # ------------------------------------------------------------------ round protocol
+    def begin_round(self) -> None:
+        for i in range(self.n_local):
+            self.acc(i).zero_()
+            self._wsum[i] = 0.0
+
+    def add_client(self, params: torch.Tensor, weight: float, local: int = 0) -> None:
+        if weight <= 0:
+            raise ValueError("client weight must be positive")
+        ops.axpby_(self.acc(local), params, 1.0, float(weight))
+        self._wsum[local] += float(weight)
+
+    def finish_round(self, server_round: int) -> None:
+        """Launch the fused reduce + server-opt + broadcast kernel on every local GPU."""
+        st, hp, ext, ar = self.strategy, self.strategy.hp, ops.ext(), self.arena
+        epoch = ar.next_epoch()
+        kind = _KIND[st.kind]
+        launches = []
+        for i in range(self.n_local):
+            rank = i if ar.single else ar.rank
+            dev = ar.devices[i if ar.single else 0]
+            lo, hi = ar.shard(self.total, rank)
+            ext.set_wsum(ar.ctl_ptrs()[rank], dev, self._wsum[i], True)
+            launches.append((rank, dev, lo, hi, i))
+        for rank, dev, lo, hi, i in launches:
+            ext.fed_round(ar.ctl_ptrs(), rank, dev, epoch, ar.ptrs("acc"), ar.ptrs("xg"), ar.ptrs("xs") if self.has_shadow else [],
+                          self._m[i].data_ptr() if self._m[i] is not None else 0, self._v[i].data_ptr() if self._v[i] is not None else 0,
+                          lo, hi, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
+                          hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat))
+
+    def round_norms(self, group: Any = None) -> dict[str, float]:
+        """Global L2 norms from the kernel's per-shard Σx² by-products (tiny host read; off the hot path)."""
+        sums = torch.zeros(5, dtype=torch.float64)
+        for i in range(self.n_local):
+            sums += self.arena.ctl_sums(self._r(i))[:5].cpu()
+        if not self.arena.single and self.arena.world_size > 1:
+            import torch.distributed as dist
+
+            t = sums.to(torch.device("cuda", self.arena.devices[0]))
+            dist.all_reduce(t, group=group)
+            sums = t.cpu()
+        names = ["pseudo_gradient", "fedavg_result", "model", "momentum_vector", "second_momentum_vector"]
+        keep = 3 + self.strategy.n_moments
+        return {f"server/l2_norm_{n}": math.sqrt(max(float(s), 0.0)) for n, s in list(zip(names, sums.tolist()))[:keep]}
+
+    def moments(self, local: int = 0) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        return self._m[local], self._v[local]
+
+    def close(self) -> None:
+        self.arena.close()

@@ -93,14 +93,22 @@ class FlatParams:
     module's ``Parameter.data`` / ``.grad`` at views of them."""
 
     def __init__(self, model: nn.Module, align: int = 256, with_grad: bool = True,
-                 device: torch.device | str | None = None) -> None:
+                 device: torch.device | str | None = None, params_storage: torch.Tensor | None = None,
+                 grads_storage: torch.Tensor | None = None) -> None:
         named = sorted(((n, p) for n, p in model.named_parameters() if p.requires_grad), key=lambda kv: kv[0])
         if not named:
             raise ValueError("model has no trainable parameters")
         dev = torch.device(device) if device is not None else named[0][1].device
         self.layout = FlatLayout.build(((n, p.shape) for n, p in named), align=align)
-        self.params = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(self.layout.total, dtype=torch.float32, device=dev) if with_grad else None
+        # external storage = a plane of the symmetric NVLink arena (so the round / all-reduce
+        # kernels can address this buffer on every peer)
+        for st in (params_storage, grads_storage):
+            if st is not None and (st.numel() < self.layout.total or st.dtype != torch.float32):
+                raise ValueError("external flat storage must be float32 with >= layout.total elements")
+        self.params = params_storage[: self.layout.total].zero_() if params_storage is not None else \
+            torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        self.grads = (grads_storage[: self.layout.total].zero_() if grads_storage is not None else
+                      torch.zeros(self.layout.total, dtype=torch.float32, device=dev)) if with_grad else None
         self._named = named
         with torch.no_grad():
             for i, (_, p) in enumerate(named):

@@ -1,0 +1,89 @@
+"""Kernel microbenchmarks on one B200: our tcgen05 GEMM vs cuBLAS (torch.matmul) on the MPT shapes,
+bandwidth of the fused memory-bound kernels. CUDA-event timed, L2 flushed between iterations."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from photon_b200 import ops  # noqa: E402
+from photon_b200.utils.hw import measured_peaks  # noqa: E402
+
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    pk = measured_peaks()
+    rows = []
+    T = 32768
+    shapes = [("qkv fwd", T, 2304, 768, 0, 0), ("out fwd", T, 768, 768, 0, 0), ("up fwd", T, 3072, 768, 0, 0),
+              ("down fwd", T, 768, 3072, 0, 0), ("up dgrad", T, 768, 3072, 0, 1), ("up wgrad", 3072, 768, T, 1, 1),
+              ("lmhead fwd", 8192, 50368, 768, 0, 0), ("lmhead dgrad", 8192, 768, 50368, 0, 1), ("lmhead wgrad", 50368, 768, 8192, 1, 1),
+              ("square 8192", 8192, 8192, 8192, 0, 0)]
+    for name, M, N, K, amn, bmn in shapes:
+        a = torch.randn((K, M) if amn else (M, K), device=dev).to(torch.bfloat16)
+        b = torch.randn((K, N) if bmn else (N, K), device=dev).to(torch.bfloat16) * 0.05
+        f32 = amn and bmn
+        out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        ours = timeit(lambda: ops.gemm(a, b, out, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16))
+        A = a.t() if amn else a
+        Bt = b if bmn else b.t()
+        if f32:
+            cub = timeit(lambda: torch.matmul(A, Bt).float())
+        else:
+            cub = timeit(lambda: torch.matmul(A, Bt))
+        fl = 2.0 * M * N * K
+        rows.append(dict(op=name, M=M, N=N, K=K, ours_ms=ours, cublas_ms=cub, ours_tflops=fl / ours / 1e9, cublas_tflops=fl / cub / 1e9,
+                         frac_of_measured_peak=fl / ours / 1e-3 / pk["bf16_flops"]))
+        print(rows[-1], flush=True)
+    # memory-bound kernels
+    d = 768
+    x = torch.randn(T, d, device=dev).to(torch.bfloat16)
+    y = torch.empty_like(x)
+    g, b_ = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    mean, rstd = torch.empty(T, device=dev), torch.empty(T, device=dev)
+    t = timeit(lambda: ops.layernorm_fwd(x, g, b_, y, mean, rstd))
+    rows.append(dict(op="layernorm_fwd", ms=t, gbs=2 * x.numel() * 2 / t / 1e6, frac_hbm=2 * x.numel() * 2 / t / 1e-3 / pk["hbm_bytes_per_s"]))
+    print(rows[-1])
+    tl = timeit(lambda: torch.nn.functional.layer_norm(x, (d,), g.bfloat16(), b_.bfloat16()))
+    rows.append(dict(op="layernorm_fwd_torch", ms=tl))
+    n = 125_400_000 // 4 * 4
+    p, gr, m, v = (torch.randn(n, device=dev) for _ in range(4))
+    v.abs_()
+    sh = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.ext().fused_optimizer(p, gr, m, v, sh, 0, False, 1e-4, 0.9, 0.9999, 1e-6, 1.0, 3.0, 0.0, 1.0, None))
+    rows.append(dict(op="fused_adopt_125M", ms=t, gbs=n * 30 / t / 1e6, frac_hbm=n * 30 / t / 1e-3 / pk["hbm_bytes_per_s"]))
+    print(rows[-1])
+    lg = torch.randn(4096, 50368, device=dev).to(torch.bfloat16)
+    tg = torch.randint(0, 50368, (4096,), device=dev)
+    st = torch.zeros(4, dtype=torch.float64, device=dev)
+    t = timeit(lambda: ops.cross_entropy(lg, tg, 1e-3, True, st))
+    rows.append(dict(op="cross_entropy_4096x50368", ms=t, gbs=lg.numel() * 2 * 3 / t / 1e6))
+    print(rows[-1])
+    out = Path("gpurun_out")
+    out.mkdir(exist_ok=True)
+    (out / "bench_kernels.json").write_text(json.dumps(dict(peaks=pk, rows=rows, when=time.time()), indent=1))
+
+
+if __name__ == "__main__":
+    main()

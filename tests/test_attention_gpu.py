@@ -1,0 +1,61 @@
+"""tcgen05 flash attention (fwd + bwd) vs an fp32 PyTorch reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, H, causal=True):
+    B, S, D3 = qkv.shape
+    d = D3 // 3
+    dh = d // H
+    q, k, v = qkv.float().view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if causal:
+        att = att.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril(), float("-inf"))
+    lse = torch.logsumexp(att, dim=-1)
+    o = torch.softmax(att, dim=-1) @ v
+    return o.transpose(1, 2).reshape(B, S, d), lse
+
+
+@pytest.mark.parametrize("B,S,H,dh", [(1, 128, 1, 64), (2, 256, 4, 64), (1, 512, 2, 64), (2, 256, 2, 128), (1, 2048, 2, 64)])
+def test_attention_fwd(B, S, H, dh):
+    from photon_b200 import ops
+
+    d = H * dh
+    qkv = (torch.randn(B, S, 3 * d, device="cuda:0") * 1.0).to(torch.bfloat16)
+    out = torch.empty(B, S, d, device="cuda:0", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device="cuda:0", dtype=torch.float32)
+    ops.attention_fwd(qkv, out, lse, H, 1.0 / math.sqrt(dh), True)
+    torch.cuda.synchronize()
+    ro, rl = _ref(qkv, H)
+    err = (out.float() - ro).abs().max().item()
+    assert err < 3e-2, f"attention fwd max err {err}"
+    assert (lse - rl).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 256, 2), (2, 512, 4), (1, 2048, 2)])
+def test_attention_bwd(B, S, H):
+    from photon_b200 import ops
+
+    dh, d = 64, H * 64
+    qkv = (torch.randn(B, S, 3 * d, device="cuda:0")).to(torch.bfloat16)
+    dout = (torch.randn(B, S, d, device="cuda:0")).to(torch.bfloat16)
+    out = torch.empty(B, S, d, device="cuda:0", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device="cuda:0", dtype=torch.float32)
+    scale = 1.0 / math.sqrt(dh)
+    ops.attention_fwd(qkv, out, lse, H, scale, True)
+    dqkv = torch.zeros_like(qkv)
+    delta = torch.empty_like(lse)
+    ops.attention_bwd(qkv, out, dout, lse, dqkv, delta, H, scale, True)
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    ro, _ = _ref(x, H)
+    ro.backward(dout.float())
+    g = x.grad
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        a, b = dqkv[..., sl].float(), g[..., sl]
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel < 3e-2, f"{name} rel err {rel}"
