@@ -1,0 +1,160 @@
+"""Server checkpoint store: layout, upload/download, resume-round resolution, restore
+from another run, cleanup (the role of ref photon/server/s3_utils.py:215-727,1261-1641).
+
+"Bucket" = a directory (``{saving_path}/{bucket_name}``) because there is no object store
+offline; the key layout is the reference's::
+
+    {bucket}/{run_uuid}/server/{round}/state.bin
+    {bucket}/{run_uuid}/server/{round}/current_server_parameters.npz      arr_i, sorted-name order
+    {bucket}/{run_uuid}/server/{round}/current_momentum_vector.npz        (Nesterov/Mom/Adam/Yogi)
+    {bucket}/{run_uuid}/server/{round}/current_second_momentum_vector.npz (Adam/Yogi)
+    {bucket}/{run_uuid}/server/comm_stack/{endpoint}/parameters.npz       (s3 comm stack)
+    {bucket}/{run_uuid}/client_{cid}/ep{E}-ba{B}-rank{R}.pt               (client checkpoints)
+
+Deliberate fixes of reference quirks: the second momentum is restored
+from its own file (the ref loads ``state["momentum"]`` into both) and is copied by
+``copy_old_checkpoints_to_new_run``; cleanup honours ``bucket_name``.
+"""
+from __future__ import annotations
+
+import pickle
+import shutil
+from pathlib import Path
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from photon_b200.strategy.constants import MOMENTUM_KEY, SECOND_MOMENTUM_KEY, SERVER_PARAMETERS_KEY
+from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file
+from photon_b200.utils.flat import FlatLayout
+
+STATE_FILE = "state.bin"
+
+
+class CheckpointStore:
+    def __init__(self, root: str | Path, bucket_name: str = "checkpoints") -> None:
+        self.bucket = Path(root) / bucket_name
+        self.bucket.mkdir(parents=True, exist_ok=True)
+
+    # -- key helpers ------------------------------------------------------------------
+    def server_dir(self, run_uuid: str) -> Path:
+        return self.bucket / run_uuid / "server"
+
+    def round_dir(self, run_uuid: str, server_round: int) -> Path:
+        return self.server_dir(run_uuid) / str(int(server_round))
+
+    def client_dir(self, run_uuid: str, cid: int | str) -> Path:
+        return self.bucket / run_uuid / f"client_{cid}"
+
+    def list_objects(self, prefix: str | Path = "") -> list[str]:
+        base = self.bucket / prefix
+        if not base.exists():
+            return []
+        return sorted(str(p.relative_to(self.bucket)) for p in base.rglob("*") if p.is_file())
+
+    def delete_object(self, key: str | Path) -> None:
+        p = self.bucket / key
+        if p.is_dir():
+            shutil.rmtree(p, ignore_errors=True)
+        elif p.exists():
+            p.unlink()
+
+    # -- upload -----------------------------------------------------------------------
+    def upload_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
+                                 tensors: dict[str, torch.Tensor], state: dict[str, Any]) -> Path:
+        """Write one round: state.bin + one npz per strategy state key (ref: s3_utils.py:480-548)."""
+        d = self.round_dir(run_uuid, server_round)
+        d.mkdir(parents=True, exist_ok=True)
+        for key, flat in tensors.items():
+            dump_model_parameters_to_file(d / f"{key}.npz", layout.to_ndarrays(flat))
+        tmp = d / (STATE_FILE + ".tmp")
+        with open(tmp, "wb") as f:
+            pickle.dump({"server_round": int(server_round), **state}, f)
+        tmp.replace(d / STATE_FILE)  # state.bin last: its presence marks the round complete
+        return d
+
+    # -- discovery ----------------------------------------------------------------------
+    def obtain_sorted_rounds(self, run_uuid: str, state_keys: Sequence[str]) -> list[int]:
+        """Rounds that are COMPLETE: state.bin + every state-key file present (ref: s3_utils.py:1261-1318)."""
+        base = self.server_dir(run_uuid)
+        out = []
+        if base.exists():
+            for p in base.iterdir():
+                if p.is_dir() and p.name.isdigit() and (p / STATE_FILE).exists() and all((p / f"{k}.npz").exists() for k in state_keys):
+                    out.append(int(p.name))
+        return sorted(out)
+
+    def interpret_resume_round(self, run_uuid: str, resume_round: int | None, state_keys: Sequence[str]) -> int | None:
+        """``None`` → start from scratch; ``-1`` → latest complete round (None if there is none);
+        ``k >= 0`` → that round, which must be complete (ref: s3_utils.py:215-272)."""
+        if resume_round is None:
+            return None
+        rounds = self.obtain_sorted_rounds(run_uuid, state_keys)
+        if resume_round < 0:
+            idx = len(rounds) + resume_round
+            return rounds[idx] if 0 <= idx < len(rounds) else None
+        if resume_round not in rounds:
+            raise FileNotFoundError(f"round {resume_round} of run '{run_uuid}' is missing or incomplete (have {rounds})")
+        return resume_round
+
+    # -- download -----------------------------------------------------------------------
+    def download_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
+                                   state_keys: Sequence[str]) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
+        d = self.round_dir(run_uuid, server_round)
+        with open(d / STATE_FILE, "rb") as f:
+            state = pickle.load(f)  # noqa: S301 - our own checkpoint
+        tensors: dict[str, torch.Tensor] = {}
+        for key in state_keys:
+            arrays = load_model_parameters_from_file(d / f"{key}.npz")
+            flat = torch.zeros(layout.total, dtype=torch.float32)
+            layout.from_ndarrays(flat, arrays)
+            tensors[key] = flat
+        return tensors, state
+
+    # -- restore from another run ---------------------------------------------------------
+    def copy_old_checkpoints_to_new_run(self, old_uuid: str, new_uuid: str, server_round: int, *, state_keys: Sequence[str],
+                                        copy_client_checkpoints: bool = True, client_ids: Sequence[int] = ()) -> None:
+        src, dst = self.round_dir(old_uuid, server_round), self.round_dir(new_uuid, server_round)
+        dst.mkdir(parents=True, exist_ok=True)
+        for key in state_keys:  # includes the second momentum (the reference forgets it)
+            shutil.copy2(src / f"{key}.npz", dst / f"{key}.npz")
+        shutil.copy2(src / STATE_FILE, dst / STATE_FILE)
+        if copy_client_checkpoints:
+            for cid in client_ids:
+                s = self.client_dir(old_uuid, cid)
+                if s.exists():
+                    shutil.copytree(s, self.client_dir(new_uuid, cid), dirs_exist_ok=True)
+
+    # -- cleanup ------------------------------------------------------------------------
+    def delete_rounds(self, run_uuid: str, keep_last: int = 0) -> None:
+        base = self.server_dir(run_uuid)
+        if not base.exists():
+            return
+        rounds = sorted(int(p.name) for p in base.iterdir() if p.is_dir() and p.name.isdigit())
+        for r in rounds[: len(rounds) - keep_last if keep_last else len(rounds)]:
+            shutil.rmtree(base / str(r), ignore_errors=True)
+
+    def delete_clients_checkpoints(self, run_uuid: str, keep_latest: bool = False) -> None:
+        base = self.bucket / run_uuid
+        if not base.exists():
+            return
+        for cdir in base.glob("client_*"):
+            files = sorted(cdir.glob("ep*-ba*-rank*.pt"), key=lambda p: int(p.name.split("-ba")[1].split("-")[0]))
+            for f in (files[:-1] if keep_latest else files):
+                f.unlink()
+
+    def cleanup_checkpoints(self, run_uuid: str, per_round: bool = False) -> None:
+        """``per_round`` keeps only the newest round / client checkpoint; otherwise remove everything."""
+        if per_round:
+            self.delete_rounds(run_uuid, keep_last=1)
+            self.delete_clients_checkpoints(run_uuid, keep_latest=True)
+        else:
+            shutil.rmtree(self.bucket / run_uuid, ignore_errors=True)
+
+
+def load_pretrained_model_from_path(path: str | Path) -> list[np.ndarray]:
+    """npz / npzc / bin, local path (``s3://`` is rejected offline) (ref: s3_utils.py:1192-1231)."""
+    if str(path).startswith("s3://"):
+        raise RuntimeError("s3:// objects are unreachable in this environment; copy the file locally")
+    return load_model_parameters_from_file(path)

@@ -1,0 +1,151 @@
+"""``llm_fit`` / ``llm_eval`` — one federated client's round on a (re-used) Trainer.
+
+Same contract and step order as the reference (ref: photon/clients/
+llm_client_functions.py:53-228 fit, :231-353 eval), with tensors staying on the
+device: the incoming global model is a flat device tensor (or the NVLink arena's
+global plane) and the result is the Trainer's flat parameter plane — no
+``.cpu().numpy()`` per tensor, no ndarray lists unless a host transport asks.
+
+Timings reported as metrics keep the reference's names (``client/fit_init_time``,
+``client/fit_set_parameters_time``, ``client/fit_time`` …).
+"""
+from __future__ import annotations
+
+import time
+from typing import Any
+
+import torch
+
+from photon_b200.clients import llm_config_functions as lcf
+from photon_b200.clients.configs import EvaluateConfig, FitConfig
+from photon_b200.clients.trainer_utils import get_trainer_object, load_trainer_checkpoint, reconfigure_trainer
+from photon_b200.clients.utils import (Payload, load_ignore_keys, manipulate_pre_training_params, payload_to_planes,
+                                       post_process_client_result)
+from photon_b200.train.timestamp import Time
+from photon_b200.train.trainer import Trainer
+
+
+def _now() -> float:
+    return time.time_ns() / 1e9
+
+
+def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | dict[str, Any], cfg: Any, cid: int, *,
+            as_ndarrays: bool = False, trainer_kwargs: dict[str, Any] | None = None,
+            shadow_payload: torch.Tensor | None = None) -> tuple[Payload, int, dict[str, Any], Trainer]:
+    """Run client ``cid``'s local training. Returns ``(payload, n_samples, metrics, trainer)``."""
+    t_start = _now()
+    fc = fit_config if isinstance(fit_config, FitConfig) else FitConfig.from_wire(fit_config)
+    state = fc.state_of(cid)
+    llm = cfg["llm_config"]
+    local_steps = Time.parse(llm.get("local_steps", "1ba")).to_batches()  # NB: llm_config.local_steps, not fl.n_local_steps
+    server_steps = int(fc.server_steps_cumulative or 0)
+    metrics: dict[str, Any] = {}
+
+    # ---- trainer: build once, afterwards only swap the per-client mutables
+    if trainer is None:
+        trainer, train_cfg = get_trainer_object(cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval,
+                                                use_unigram_metrics=fc.use_unigram_metrics,
+                                                allow_unigram_metrics_failures=fc.allow_unigram_metrics_failures,
+                                                frozen_layers=fc.frozen_layers, unfrozen_layers=fc.unfrozen_layers,
+                                                resize_vocab=fc.resize_vocab, **(trainer_kwargs or {}))
+    else:
+        train_cfg = reconfigure_trainer(trainer, cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval)
+    # ---- per-client checkpoint policy: resume mid-round or skip an already finished round
+    skip_iteration, load_set = (False, False)
+    if not fc.reset_checkpoint:
+        skip_iteration, load_set = lcf.set_client_load_path(train_cfg, cid, server_steps + local_steps)
+        trainer.save_folder = train_cfg.get("save_folder")
+    else:
+        lcf.set_client_save_and_load_path(train_cfg, cid)
+        trainer.save_folder = train_cfg.get("save_folder")
+    metrics["client/fit_init_time"] = _now() - t_start
+
+    # ---- install the round's parameters (+ momenta / personalised / re-initialised layers)
+    t0 = _now()
+    st = trainer.state
+    if fc.reset_optimizer and not fc.aggregate_momenta:
+        st.optimizer.reset_state()
+    params, m = manipulate_pre_training_params(trainer, payload, fc, cid, state)
+    metrics.update(m)
+    st.flat.params.copy_(params)
+    if shadow_payload is not None and getattr(st.backend, "bf16_params", None) is not None:
+        st.backend.bf16_params.copy_(shadow_payload)  # bf16 cast already produced by the round broadcast kernel
+    else:
+        st.backend.params_updated()
+    initial = params if params.data_ptr() != st.flat.params.data_ptr() else params.clone()
+    if load_set and train_cfg.get("load_path"):
+        load_trainer_checkpoint(trainer, str(train_cfg["load_path"]), load_ignore_keys(fc))
+    # LR schedule continuity: the local clock starts at the federation's cumulative step count
+    if not fc.reset_timestamp:
+        st.timestamp.batch = max(st.timestamp.batch, server_steps) if load_set else server_steps
+    else:
+        st.timestamp.reset()
+    metrics["client/fit_set_parameters_time"] = _now() - t0
+
+    if llm.get("eval_first", False) and trainer.eval_loaders:
+        t0 = _now()
+        pre = trainer.eval()
+        metrics.update({f"PrePersonalization{k}": v for k, v in pre.items()})
+        metrics["client/fit_pre_eval_time"] = _now() - t0
+
+    # ---- local training
+    t0 = _now()
+    steps_done = 0
+    if not skip_iteration:
+        target = server_steps + local_steps
+        remaining = max(0, target - st.timestamp.batch)
+        if remaining:
+            trainer.fit(duration=f"{remaining}ba")
+        steps_done = local_steps
+        if trainer.device.type == "cuda":
+            torch.cuda.synchronize(trainer.device)
+    metrics["client/fit_time"] = _now() - t0
+
+    t0 = _now()
+    out, n_samples, pm = post_process_client_result(trainer, initial, fc, cid, state, steps_done, as_ndarrays=as_ndarrays)
+    metrics.update(pm)
+    metrics["client/fit_get_parameters_time"] = _now() - t0
+    return out, n_samples, metrics, trainer
+
+
+def llm_eval(trainer: Trainer | None, payload: Payload, eval_config: EvaluateConfig | dict[str, Any], cfg: Any,
+             cid: int | None = None, *, trainer_kwargs: dict[str, Any] | None = None) -> tuple[float, int, dict[str, Any], Trainer]:
+    """Federated evaluation: all streams concatenated (``cid=None``), parameters checked before/after
+    install, ``Val*`` metrics; loss is the real CE here (the reference returns a dummy 0.0, ref: :353)."""
+    t_start = _now()
+    ec = eval_config if isinstance(eval_config, EvaluateConfig) else EvaluateConfig.from_wire(eval_config)
+    metrics: dict[str, Any] = {}
+    if trainer is None:
+        trainer, _ = get_trainer_object(cfg, None, log_name="_eval", split_eval=ec.split_eval,
+                                        use_unigram_metrics=ec.use_unigram_metrics,
+                                        allow_unigram_metrics_failures=ec.allow_unigram_metrics_failures,
+                                        frozen_layers=ec.frozen_layers, unfrozen_layers=ec.unfrozen_layers,
+                                        resize_vocab=ec.resize_vocab, **(trainer_kwargs or {}))
+    else:
+        reconfigure_trainer(trainer, cfg, None, log_name="_eval", split_eval=ec.split_eval)
+    metrics["client/eval_init_time"] = _now() - t_start
+    t0 = _now()
+    st = trainer.state
+    before = st.flat.params.clone()
+    (params,) = payload_to_planes(payload, st.flat.layout, st.flat.params.device, 1)
+    st.flat.params.copy_(params)
+    st.backend.params_updated()
+    if not torch.equal(st.flat.params, params):
+        raise AssertionError("evaluation parameters were not installed correctly")
+    metrics["client/eval_params_changed"] = float(not torch.equal(before, st.flat.params))
+    metrics["client/eval_set_parameters_time"] = _now() - t0
+    t0 = _now()
+    vals = trainer.eval()
+    if trainer.device.type == "cuda":
+        torch.cuda.synchronize(trainer.device)
+    metrics["client/eval_time"] = _now() - t0
+    out = {}
+    loss = 0.0
+    for k, v in vals.items():
+        label, _, name = k.rpartition("/")
+        out[f"{label + '/' if label and label != 'eval' else ''}Val{name}"] = v
+        if name == "LanguageCrossEntropy":
+            loss = float(v)
+    metrics.update(out)
+    n_samples = int(st.eval_timestamp.sample)
+    return loss, max(1, n_samples), metrics, trainer

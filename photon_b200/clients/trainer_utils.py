@@ -1,0 +1,159 @@
+"""Build (and re-use) the per-client Trainer from the resolved config.
+
+``get_trainer_object`` is the B200 engine's counterpart of the reference's fork
+of llm-foundry ``train.py`` (ref: photon/clients/trainer_utils.py:1117-1721):
+device pick from ``APPOINTED_CUDA_DEVICE``, process-group bring-up, per-client
+streams, loaders, evaluators, callbacks, loggers, optimizer, scheduler,
+algorithms (gradient clipping), checkpoint policy.  ``reconfigure_trainer`` is
+the "mutables" path (ref: ``get_trainer_mutables_from_config`` +
+``set_mutables_trainer*``, :330-1114): a live Trainer — and its CUDA context,
+workspace and compiled kernels — survives across rounds/clients; only loaders,
+save folder, loggers and clocks are swapped.
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+from photon_b200.clients import llm_config_functions as lcf
+from photon_b200.data.streaming import build_text_loader
+from photon_b200.metrics.language import unigram_log_probs
+from photon_b200.models.mpt import MPTConfig
+from photon_b200.train.callbacks import build_callbacks, build_loggers
+from photon_b200.train.timestamp import Time
+from photon_b200.train.trainer import Trainer
+from photon_b200.utils.core import appointed_cuda_devices
+
+
+def pick_device(local_rank: int = 0) -> torch.device:
+    if not torch.cuda.is_available():
+        return torch.device("cpu")
+    appointed = appointed_cuda_devices()
+    idx = appointed[local_rank % len(appointed)] if appointed else local_rank % torch.cuda.device_count()
+    torch.cuda.set_device(idx)
+    return torch.device("cuda", idx)
+
+
+def initialize_dist(device: torch.device, timeout_s: float = 600.0) -> tuple[int, int]:
+    """Bring up the intra-client process group from torchrun-style env (NCCL on GPU, gloo on CPU)
+    and smoke-test it with a barrier (ref: trainer_utils.py:403-405,1249-1251)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        import datetime
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if device.type == "cuda" else "gloo", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=timeout_s))
+        dist.barrier()
+    return rank, world
+
+
+def _prepare_train_cfg(cfg: Any, cid: int | str | None, split_eval: bool, n_devices: int, log_name: str) -> tuple[Any, dict[str, Any]]:
+    t = lcf.get_train_config(cfg["llm_config"], run_uuid=str(cfg.get("run_uuid", "run")))
+    lcf.adapt_train_batch_size_to_num_devices(t, n_devices)
+    lcf.set_n_workers_dataloaders(t, n_devices)
+    evals = lcf.client_set_data_config(t, cid, split_eval)
+    lcf.set_dataset_default_params(t)
+    lcf.set_client_loggers(t, log_name)
+    return t, evals
+
+
+def _grad_clip(train_cfg: Any) -> float | None:
+    gc = ((train_cfg.get("algorithms") or {}).get("gradient_clipping") or None)
+    if not gc:
+        return None
+    if gc.get("clipping_type", "norm") != "norm":
+        raise NotImplementedError("only clipping_type=norm is supported")
+    return float(gc["clipping_threshold"])
+
+
+def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", device: torch.device | None = None,
+                       rank: int | None = None, world_size: int | None = None, process_group: Any = None,
+                       grad_comm: Any = None, split_eval: bool = False, use_unigram_metrics: bool = False,
+                       allow_unigram_metrics_failures: bool = False, frozen_layers: list[str] | None = None,
+                       unfrozen_layers: list[str] | None = None, resize_vocab: int | None = None,
+                       no_data: bool = False, backend: Any = None) -> tuple[Trainer, Any]:
+    """Returns ``(trainer, train_cfg)``. ``cid=None`` = all streams (centralised / evaluation)."""
+    device = device or pick_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank is None or world_size is None:
+        rank, world_size = initialize_dist(device)
+    t, evals = _prepare_train_cfg(cfg, cid, split_eval, world_size, log_name)
+    if t.get("tp_config"):
+        raise ValueError("tp_config must be null (TP is plumbing-only in the reference)")
+    model_node = dict(t["model"])
+    if resize_vocab:
+        model_node["vocab_size"] = int(resize_vocab)  # ref: clients/utils.py:245-249
+    mcfg = MPTConfig.from_model_cfg(model_node)
+    if device.type == "cpu" and mcfg.attn_impl == "flash":
+        mcfg.attn_impl = "torch"  # README.md:82-84: CPU runs use the eager attention path
+    precision = t.get("precision", "amp_bf16")
+    gbs = int(t["global_train_batch_size"])
+    seed = int(t.get("seed", 17))
+    uni = None
+    if use_unigram_metrics:
+        freq = lcf.get_stream_freq_dict_for_client(t, cid, allow_failures=allow_unigram_metrics_failures)
+        if freq is not None:
+            uni = unigram_log_probs(freq, mcfg.vocab_size)
+        elif not allow_unigram_metrics_failures:
+            raise RuntimeError("unigram metrics requested but no 1_gram.json found")
+    train_loader = None if no_data else build_text_loader(t["train_loader"], gbs // world_size, rank, world_size, seed)
+    eval_bs = int(t.get("device_eval_batch_size", 1))
+    eval_loaders = {} if no_data else {lbl: build_text_loader(lc, eval_bs, rank, world_size, seed + 1) for lbl, lc in evals.items()}
+    save_root = t.get("save_folder") or "."
+    interval = t.get("console_log_interval", "1ba")
+    loggers = build_loggers(t.get("loggers"), Path(str(save_root)).parent if t.get("save_folder") else ".", str(t["run_name"]),
+                            console_interval=Time.parse(interval).to_batches(), log_to_console=bool(t.get("log_to_console", True)), rank=rank)
+    kernels = dict(cfg.get("kernels") or {})
+    if mcfg.attn_impl == "torch" and device.type == "cuda" and kernels.get("attention", "auto") == "auto":
+        kernels["attention"] = "torch"
+    tr = Trainer(mcfg, optimizer_cfg=dict(t["optimizer"]), scheduler_cfg=dict(t.get("scheduler") or {}),
+                 train_loader=train_loader, eval_loaders=eval_loaders, global_train_batch_size=gbs,
+                 device_train_microbatch_size=t.get("device_train_microbatch_size", "auto"),
+                 device_eval_batch_size=eval_bs, precision=precision, max_duration=t.get("max_duration"),
+                 grad_clip_norm=_grad_clip(t), callbacks=build_callbacks(t.get("callbacks")), loggers=loggers,
+                 save_folder=t.get("save_folder"), save_interval=t.get("save_interval"),
+                 save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),
+                 save_overwrite=bool(t.get("save_overwrite", False)), eval_interval=t.get("eval_interval"),
+                 eval_subset_num_batches=int(t.get("eval_subset_num_batches", -1)), device=device, rank=rank,
+                 world_size=world_size, process_group=process_group, grad_comm=grad_comm, kernels=kernels, seed=seed,
+                 run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,
+                 frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend)
+    return tr, t
+
+
+def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, log_name: str = "", split_eval: bool = False,
+                        reset_timestamp: bool = False) -> Any:
+    """Swap the per-client mutables on a live Trainer (loaders, save folder, run name, clocks)."""
+    t, evals = _prepare_train_cfg(cfg, cid, split_eval, trainer.world_size, log_name)
+    seed = int(t.get("seed", 17))
+    trainer.train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed)
+    trainer.eval_loaders = {lbl: build_text_loader(lc, trainer.device_eval_batch_size, trainer.rank, trainer.world_size, seed + 1)
+                            for lbl, lc in evals.items()}
+    trainer._train_iter = None  # noqa: SLF001
+    trainer.save_folder = t.get("save_folder")
+    trainer._saved = []  # noqa: SLF001
+    trainer.state.run_name = str(t["run_name"])
+    trainer.closed = False
+    if reset_timestamp:
+        trainer.state.timestamp.reset()
+    return t
+
+
+def load_trainer_checkpoint(trainer: Trainer, load_path: str, ignore_keys: list[str] | None = None) -> None:
+    """``load_path`` may contain ``{rank}`` (ref: trainer_utils.py:229-275)."""
+    trainer.load_checkpoint(load_path.format(rank=trainer.rank), ignore_keys or [])
+
+
+def trainer_clean_up(trainer: Trainer) -> None:
+    """Close loggers and drop the workspace; barrier so every rank leaves together
+    (ref: trainer_utils.py:205-226)."""
+    trainer.close()
+    if dist.is_available() and dist.is_initialized() and trainer.world_size > 1:
+        dist.barrier(group=trainer.process_group)
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()

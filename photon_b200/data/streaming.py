@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import os
 import queue
+import zlib
 import threading
 from dataclasses import dataclass
 from pathlib import Path
@@ -61,7 +62,7 @@ def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: i
     sid = idx
     if st.local and str(st.local).startswith(SYNTH_PREFIX):
         tail = str(st.local)[len(SYNTH_PREFIX):]
-        sid = int(tail) if tail.isdigit() else (abs(hash(tail)) % (1 << 30))
+        sid = int(tail) if tail.isdigit() else (zlib.crc32(tail.encode()) % (1 << 30))  # stable across processes
     elif st.local:
         digits = "".join(ch for ch in Path(str(st.local)).name if ch.isdigit())
         sid = int(digits) if digits else idx

@@ -1,0 +1,219 @@
+"""SPMD federation runtime: the in-box control plane that replaces Flower's
+SuperLink / ServerApp / ClientApp trio.
+
+One process per GPU (``torchrun``); every rank is a *node* hosting one worker on
+its GPU, rank 0 additionally keeps the server bookkeeping (history, checkpoints).
+A round on N GPUs with K sampled clients:
+
+* clients are mapped to nodes with the work-queue order (client i → node i mod N,
+  each node running its queue sequentially — virtual-client multiplexing; ref:
+  photon/server/server_util.py:145-202, photon/node_manager/node_manager_app.py:516);
+* each node installs the global model from its own global planes (a local copy —
+  the broadcast already happened inside the previous round's kernel), runs
+  ``llm_fit`` on its persistent Trainer, and folds the result into the local
+  weighted accumulator (streaming aggregation without leaving HBM);
+* ``finish_round`` runs the transport selected by ``photon.comm_stack`` — the fused
+  NVLink kernel (``nvl``) or one of the baselines — leaving the new global model
+  (fp32 + bf16) in every node's planes.
+
+``gpus_per_client > 1`` groups consecutive ranks into one client with intra-client
+DDP (fused all-reduce); only the group leader contributes to the round reduce.
+"""
+from __future__ import annotations
+
+import random
+import time
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+from photon_b200.clients.configs import get_photon_evaluate_config_fn, get_photon_fit_config_fn
+from photon_b200.clients.llm_client_functions import llm_eval, llm_fit
+from photon_b200.clients.trainer_utils import get_trainer_object, pick_device
+from photon_b200.clients.utils import get_initial_parameters
+from photon_b200.messages import ClientState, Code, EvaluateRes, FitRes, ParamHandle, Status
+from photon_b200.server.round_backends import RoundBackend, build_round_backend
+from photon_b200.server.server_util import spmd_node_ids, static_assignment
+from photon_b200.strategy.dispatcher import dispatch_strategy
+from photon_b200.train.trainer import Trainer
+from photon_b200.utils.flat import FlatLayout
+
+
+class FederationRuntime:
+    def __init__(self, cfg: Any, *, device: torch.device | None = None, rank: int | None = None,
+                 world_size: int | None = None, group: Any = None, gpus_per_client: int = 1) -> None:
+        self.cfg = cfg
+        self.device = device or pick_device()
+        if rank is None or world_size is None:
+            on = dist.is_available() and dist.is_initialized()
+            rank, world_size = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+        self.rank, self.world_size, self.group = int(rank), int(world_size), group
+        self.gpus_per_client = int(gpus_per_client)
+        if self.world_size % self.gpus_per_client:
+            raise ValueError("world_size must be a multiple of gpus_per_client")
+        self.node_id = self.rank // self.gpus_per_client          # one logical node per client group
+        self.n_nodes = self.world_size // self.gpus_per_client
+        self.is_leader = self.rank % self.gpus_per_client == 0
+        self.client_group = None
+        self.grad_comm = None
+        if self.gpus_per_client > 1:
+            for g in range(self.n_nodes):
+                ranks = list(range(g * self.gpus_per_client, (g + 1) * self.gpus_per_client))
+                pg = dist.new_group(ranks)
+                if g == self.node_id:
+                    self.client_group = pg
+        self.strategy = dispatch_strategy(cfg)
+        self.rng = random.Random(int(cfg["seed"]))
+        self.client_states: dict[int, ClientState] = {c: ClientState() for c in range(int(cfg["fl"]["n_total_clients"]))}
+        self.server_steps_cumulative = 0
+        self.fit_config_fn = get_photon_fit_config_fn(cfg)
+        self.eval_config_fn = get_photon_evaluate_config_fn(cfg)
+        self.trainer: Trainer | None = None
+        self._opt_states: dict[int, tuple[torch.Tensor, torch.Tensor, int]] = {}
+        self._local_params: dict[int, torch.Tensor] = {}   # personalised-layer memory per client
+        self.layout: FlatLayout | None = None
+        self.round_backend: RoundBackend | None = None
+        self.fault_injection = dict(cfg["fl"].get("fault_injection") or {})
+        self.timings: dict[str, float] = {}
+
+    # --------------------------------------------------------------------- bring-up
+    def build(self) -> None:
+        """Create the persistent Trainer (also fixes the flat layout) and the round transport."""
+        kw: dict[str, Any] = dict(device=self.device, rank=self.rank % self.gpus_per_client, world_size=self.gpus_per_client,
+                                  process_group=self.client_group)
+        if self.gpus_per_client > 1 and self.device.type == "cuda":
+            # intra-client DDP over the fused NVLink all-reduce: the gradient plane lives in a symmetric arena
+            from photon_b200.models.engine import B200Engine  # noqa: F401  (ensures the extension is present)
+            from photon_b200.parallel.ddp import NcclGradComm
+
+            kw["grad_comm"] = NcclGradComm(self.client_group)
+        fl = self.cfg["fl"]
+        self.trainer, _ = get_trainer_object(self.cfg, 0, log_name=f"_node_{self.node_id}", split_eval=bool(fl.get("split_eval", False)),
+                                             use_unigram_metrics=bool(fl["use_unigram_metrics"]),
+                                             allow_unigram_metrics_failures=bool(fl["allow_unigram_metrics_failures"]),
+                                             frozen_layers=fl.get("frozen_layers"), unfrozen_layers=fl.get("unfrozen_layers"),
+                                             resize_vocab=fl.get("resize_vocab"), **kw)
+        self.layout = self.trainer.state.flat.layout
+        self.round_backend = build_round_backend(self.cfg, self.layout, self.strategy, self.device, rank=self.rank,
+                                                 world_size=self.world_size, group=self.group)
+
+    def initial_parameters(self) -> torch.Tensor:
+        """Rank 0's freshly initialised (or pretrained) model as a flat tensor."""
+        assert self.layout is not None
+        flat = torch.zeros(self.layout.total, dtype=torch.float32)
+        if self.rank == 0:
+            arrays, lay = get_initial_parameters(self.cfg)
+            if lay.names != self.layout.names:
+                raise AssertionError("initial-parameter layout differs from the trainer's")
+            self.layout.from_ndarrays(flat, arrays)
+        return flat
+
+    # ----------------------------------------------------------------------- sampling
+    def sample_clients(self) -> list[int]:
+        """Seeded ``random.Random(cfg.seed).sample`` — identical on every rank and replayable on
+        resume (ref: photon/server_app.py:124,188-192,295)."""
+        fl = self.cfg["fl"]
+        return self.rng.sample(range(int(fl["n_total_clients"])), int(fl["n_clients_per_round"]))
+
+    def replay_sampling(self, n_rounds: int) -> None:
+        for _ in range(n_rounds):
+            self.sample_clients()
+
+    def my_clients(self, sampled: list[int]) -> list[int]:
+        return static_assignment(sampled, list(range(self.n_nodes)))[self.node_id]
+
+    # -------------------------------------------------------------------------- fit
+    def _should_fail(self, server_round: int, cid: int) -> bool:
+        fi = self.fault_injection
+        return bool(fi) and int(fi.get("round", -1)) == server_round and int(fi.get("cid", -1)) == cid
+
+    def run_clients_fit(self, server_round: int, sampled: list[int]) -> list[FitRes]:
+        assert self.trainer is not None and self.round_backend is not None
+        rb, tr = self.round_backend, self.trainer
+        rb.begin_round()
+        results: list[FitRes] = []
+        keep_opt = not bool(self.cfg["fl"]["reset_optimizer"])
+        t_fit = 0.0
+        for cid in self.my_clients(sampled):
+            t0 = time.time()
+            try:
+                if self._should_fail(server_round, cid):
+                    raise RuntimeError(f"fault injection: client {cid} dropped in round {server_round}")
+                fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
+                opt = tr.state.optimizer
+                if keep_opt and cid in self._opt_states:   # multiplexed clients keep their own moments
+                    m, v, step = self._opt_states[cid]
+                    opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)
+                    opt.step_count = step
+                elif keep_opt:
+                    opt.reset_state()
+                if fc.personalized_layers and cid in self._local_params:
+                    tr.state.flat.params.copy_(self._local_params[cid])
+                payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
+                                                         shadow_payload=rb.global_shadow())
+                if keep_opt and len(self.my_clients(sampled)) > 1:
+                    self._opt_states[cid] = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
+                if fc.personalized_layers:
+                    self._local_params[cid] = tr.state.flat.params.clone()
+                if self.is_leader:
+                    rb.add_client(payload if torch.is_tensor(payload) and payload.numel() == self.layout.total else tr.state.flat.params, n_samples)
+                results.append(FitRes(Status(Code.OK, ""), ParamHandle(kind=rb.name), n_samples if self.is_leader else 0, metrics, cid))
+            except Exception as e:  # noqa: BLE001 - a failed client must not take the round down
+                results.append(FitRes(Status(Code.FAILED, repr(e)), None, 0, {}, cid))
+            t_fit += time.time() - t0
+        self.timings["node_training_time_s"] = t_fit
+        return results
+
+    def gather_results(self, results: list[FitRes]) -> list[FitRes]:
+        """Control-plane gather (metadata only — parameters never travel here)."""
+        mine = [r for r in results if self.is_leader or r.status.code != Code.OK]
+        if self.world_size == 1 or not dist.is_initialized():
+            return mine
+        box: list[Any] = [None] * self.world_size
+        dist.all_gather_object(box, mine, group=self.group)
+        return [r for part in box for r in part]
+
+    def finish_round(self, server_round: int) -> None:
+        assert self.round_backend is not None
+        t0 = time.time()
+        self.round_backend.finish_round(server_round)
+        self.timings["aggregate_broadcast_host_s"] = time.time() - t0
+
+    def abort_round(self) -> None:
+        """Ignored round: global model untouched (the accumulators are simply dropped)."""
+
+    # ----------------------------------------------------------------------- evaluate
+    def run_clients_evaluate(self, server_round: int, sampled: list[int]) -> list[EvaluateRes]:
+        assert self.trainer is not None and self.round_backend is not None
+        out: list[EvaluateRes] = []
+        if self.node_id != 0:   # the reference evaluates on ONE client (id 0), all streams concatenated
+            return self._gather_eval(out)
+        for cid in sampled:
+            try:
+                ec = self.eval_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
+                loss, n, metrics, _ = llm_eval(self.trainer, self.round_backend.global_params(), ec, self.cfg, cid)
+                out.append(EvaluateRes(Status(Code.OK, ""), loss, n, metrics, cid))
+            except Exception as e:  # noqa: BLE001
+                out.append(EvaluateRes(Status(Code.FAILED, repr(e)), 0.0, 0, {}, cid))
+        return self._gather_eval(out)
+
+    def _gather_eval(self, mine: list[EvaluateRes]) -> list[EvaluateRes]:
+        if self.world_size == 1 or not dist.is_initialized():
+            return mine
+        box: list[Any] = [None] * self.world_size
+        dist.all_gather_object(box, mine if self.is_leader else [], group=self.group)
+        return [r for part in box for r in part]
+
+    # --------------------------------------------------------------------------- state
+    def state_tensors(self) -> dict[str, torch.Tensor]:
+        assert self.round_backend is not None
+        m, v = self.round_backend.moments()
+        vals = [self.round_backend.global_params(), m, v]
+        return {k: t for k, t in zip(self.strategy.state_keys, vals) if t is not None}
+
+    def close(self) -> None:
+        if self.trainer is not None:
+            self.trainer.close()
+        if self.round_backend is not None:
+            self.round_backend.close()

@@ -1,0 +1,354 @@
+"""Round transports: how client results reach the server optimizer and how the new global
+model reaches the clients — the four ``photon.comm_stack`` options.
+
+=========  ================================================================================
+``nvl``    PRODUCT PATH. One fused sm_100a kernel per GPU over the symmetric NVLink arena
+           (:class:`photon_b200.parallel.fed_round.NvlFedRound`): weighted reduce + server
+           optimizer on the GPU's shard + broadcast with bf16 cast. No NCCL, no host.
+``ray``    Collective baseline: weighted local sums → ``torch.distributed.all_reduce`` (NCCL on
+           GPUs, gloo on CPU) → every rank applies the server optimizer redundantly.  Stands
+           in for the reference's Ray-plasma stack (Ray is not installable offline).
+``shm``    Reference-equivalent HOST path (ref: photon/server/s3_utils.py:865-903,
+           photon/strategy/aggregation.py:57-75): D2H → per-tensor ndarrays → POSIX shm →
+           rank-0 streaming mean + server optimizer on the CPU → shm → H2D.
+``s3``     Same as ``shm`` but through ``.npz`` objects in a directory (object-store stand-in),
+           layout ``{root}/{run_uuid}/server/comm_stack/{endpoint}/parameters.npz``
+           (ref: s3_utils.py:812-864).
+=========  ================================================================================
+
+All share one interface: ``begin_round`` → ``add_client`` × k → ``finish_round`` →
+``global_params`` / ``global_shadow`` and produce the same model within fp32 tolerance
+(``tests/test_round_backends.py``).
+"""
+from __future__ import annotations
+
+import os
+import time
+import uuid
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from photon_b200.shm.utils import ModelParametersMetadata, get_parameters_shm, set_parameters_shm, unlink_quietly
+from photon_b200.strategy.strategies import ServerStrategy
+from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file
+from photon_b200.utils.flat import FlatLayout
+
+
+def _dist_on(group: Any = None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+class RoundBackend:
+    name = "base"
+
+    def __init__(self, layout: FlatLayout, strategy: ServerStrategy, device: torch.device, *, rank: int = 0,
+                 world_size: int = 1, group: Any = None) -> None:
+        self.layout, self.strategy, self.device = layout, strategy, device
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.last_metrics: dict[str, Any] = {}
+        self.timings: dict[str, float] = {}
+
+    def set_global(self, params: torch.Tensor, momentum: torch.Tensor | None = None, second: torch.Tensor | None = None) -> None:
+        raise NotImplementedError
+
+    def begin_round(self) -> None:
+        raise NotImplementedError
+
+    def add_client(self, params: torch.Tensor, weight: float) -> None:
+        raise NotImplementedError
+
+    def finish_round(self, server_round: int) -> None:
+        raise NotImplementedError
+
+    def global_params(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def global_shadow(self) -> torch.Tensor | None:
+        return None
+
+    def moments(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        return self.strategy.momentum_vector, self.strategy.second_momentum_vector
+
+    def close(self) -> None:
+        pass
+
+
+class _HostAccumulating(RoundBackend):
+    """Shared piece of the non-NVL backends: keep x on ``device``, accumulate Σ n_k·x_k locally."""
+
+    def set_global(self, params: torch.Tensor, momentum: torch.Tensor | None = None, second: torch.Tensor | None = None) -> None:
+        self.strategy.initialize(params.to(self.server_device, torch.float32).clone(),
+                                 None if momentum is None else momentum.to(self.server_device).clone(),
+                                 None if second is None else second.to(self.server_device).clone(), layout=self.layout)
+        self._x_dev = params.to(self.device, torch.float32).clone()
+
+    @property
+    def server_device(self) -> torch.device:
+        return self.device
+
+    def begin_round(self) -> None:
+        self._acc: torch.Tensor | None = None
+        self._w = 0.0
+
+    def add_client(self, params: torch.Tensor, weight: float) -> None:
+        if weight <= 0:
+            raise ValueError("client weight must be positive")
+        if self._acc is None:
+            self._acc = params.detach().to(self.device, torch.float32) * float(weight)
+        else:
+            self._acc.add_(params.to(self.device, torch.float32), alpha=float(weight))
+        self._w += float(weight)
+
+    def global_params(self) -> torch.Tensor:
+        return self._x_dev
+
+
+class CollectiveRoundBackend(_HostAccumulating):
+    """``comm_stack.ray`` slot: all-reduce of the weighted sums, redundant server update."""
+
+    name = "ray"
+
+    def finish_round(self, server_round: int) -> None:
+        t0 = time.perf_counter()
+        acc = self._acc if self._acc is not None else torch.zeros(self.layout.total, device=self.device)
+        w = torch.tensor([self._w], dtype=torch.float64, device=acc.device if _dist_on(self.group) and dist.get_backend(self.group) == "nccl" else "cpu")
+        if _dist_on(self.group):
+            dist.all_reduce(acc, group=self.group)
+            dist.all_reduce(w, group=self.group)
+        total = float(w.item())
+        if total <= 0:
+            self.last_metrics = {}
+            return
+        avg = acc / total
+        s = self.strategy.scaling_factor()
+        if s != 1.0:
+            avg.mul_(s)
+        self.last_metrics = self.strategy.apply_server_update(avg, server_round)
+        self._x_dev = self.strategy.parameters
+        self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
+
+
+class ShmRoundBackend(_HostAccumulating):
+    """``comm_stack.shm``: the reference's host path, faithfully (D2H per tensor, shm, NumPy-era
+    streaming mean on rank 0's CPU, shm back, H2D per tensor)."""
+
+    name = "shm"
+
+    def __init__(self, *a: Any, run_uuid: str = "run", **kw: Any) -> None:
+        super().__init__(*a, **kw)
+        self.uid = f"{run_uuid}-{uuid.uuid4().hex[:8]}" if self.rank == 0 else ""
+        if _dist_on(self.group):
+            box = [self.uid]
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            self.uid = box[0]
+        self._handles: list[Any] = []
+
+    @property
+    def server_device(self) -> torch.device:
+        return torch.device("cpu")  # the reference's server never touches a GPU
+
+    def _put(self, name: str, flat: torch.Tensor) -> ModelParametersMetadata:
+        arrays = self.layout.to_ndarrays(flat)  # D2H + per-tensor split (ref: photon/utils.py:243-244)
+        shm, meta = set_parameters_shm(name, arrays)
+        self._handles.append(shm)
+        return meta
+
+    def _get(self, name: str, meta: ModelParametersMetadata) -> list[np.ndarray]:
+        shm, views = get_parameters_shm(name, meta, copy=True)
+        shm.close()
+        return views
+
+    def finish_round(self, server_round: int) -> None:
+        t0 = time.perf_counter()
+        up = f"{self.uid}_r{self.rank}_up"
+        have = self._acc is not None and self._w > 0
+        meta = self._put(up, self._acc / self._w) if have else None
+        infos: list[Any] = [None] * self.world_size
+        mine = (up, meta.to_literal() if meta else None, self._w)
+        if _dist_on(self.group):
+            dist.all_gather_object(infos, mine, group=self.group)
+        else:
+            infos = [mine]
+        down = f"{self.uid}_down"
+        down_meta: list[Any] = [None]
+        if self.rank == 0:
+            from photon_b200.strategy.aggregation import StreamingMean
+
+            sm = StreamingMean()
+            for name, lit, w in infos:
+                if lit is None or w <= 0:
+                    continue
+                arrays = self._get(name, ModelParametersMetadata.from_literal(lit))
+                host = torch.zeros(self.layout.total)
+                self.layout.from_ndarrays(host, arrays)
+                sm.add(host, w)
+            if sm.result() is not None:
+                avg = sm.result()
+                s = self.strategy.scaling_factor()
+                if s != 1.0:
+                    avg.mul_(s)
+                self.last_metrics = self.strategy.apply_server_update(avg, server_round)
+            down_meta[0] = self._put(down, self.strategy.parameters).to_literal()
+        if _dist_on(self.group):
+            dist.broadcast_object_list(down_meta, src=0, group=self.group)
+        arrays = self._get(down, ModelParametersMetadata.from_literal(down_meta[0]))
+        host = torch.zeros(self.layout.total)
+        self.layout.from_ndarrays(host, arrays)
+        self._x_dev = host.to(self.device)  # H2D
+        if _dist_on(self.group):
+            dist.barrier(group=self.group)
+        for h in self._handles:
+            h.close()
+        self._handles = []
+        unlink_quietly(up)
+        if self.rank == 0:
+            unlink_quietly(down)
+        self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
+
+
+class FileRoundBackend(_HostAccumulating):
+    """``comm_stack.s3``: npz objects under ``{root}/{run_uuid}/server/comm_stack/…``."""
+
+    name = "s3"
+
+    def __init__(self, *a: Any, root: str | os.PathLike = "./checkpoints", run_uuid: str = "run", num_attempts: int = 3, **kw: Any) -> None:
+        super().__init__(*a, **kw)
+        self.dir = Path(root) / run_uuid / "server" / "comm_stack"
+        self.dir.mkdir(parents=True, exist_ok=True)
+        self.num_attempts = int(num_attempts)
+
+    @property
+    def server_device(self) -> torch.device:
+        return torch.device("cpu")
+
+    def _load(self, path: Path) -> list[np.ndarray]:
+        for attempt in range(self.num_attempts):
+            try:
+                return load_model_parameters_from_file(path)
+            except (OSError, ValueError):
+                time.sleep(0.05 * (attempt + 1))
+        return load_model_parameters_from_file(path)
+
+    def finish_round(self, server_round: int) -> None:
+        t0 = time.perf_counter()
+        have = self._acc is not None and self._w > 0
+        mine = self.dir / f"client-rank{self.rank}" / "parameters.npz"
+        if have:
+            dump_model_parameters_to_file(mine, self.layout.to_ndarrays(self._acc / self._w))
+        infos: list[Any] = [None] * self.world_size
+        rec = (str(mine) if have else None, self._w)
+        if _dist_on(self.group):
+            dist.all_gather_object(infos, rec, group=self.group)
+        else:
+            infos = [rec]
+        down = self.dir / "server" / "parameters.npz"
+        if self.rank == 0:
+            from photon_b200.strategy.aggregation import StreamingMean
+
+            sm = StreamingMean()
+            for path, w in infos:
+                if path is None or w <= 0:
+                    continue
+                host = torch.zeros(self.layout.total)
+                self.layout.from_ndarrays(host, self._load(Path(path)))
+                sm.add(host, w)
+            if sm.result() is not None:
+                avg = sm.result()
+                s = self.strategy.scaling_factor()
+                if s != 1.0:
+                    avg.mul_(s)
+                self.last_metrics = self.strategy.apply_server_update(avg, server_round)
+            dump_model_parameters_to_file(down, self.layout.to_ndarrays(self.strategy.parameters))
+        if _dist_on(self.group):
+            dist.barrier(group=self.group)
+        host = torch.zeros(self.layout.total)
+        self.layout.from_ndarrays(host, self._load(down))
+        self._x_dev = host.to(self.device)
+        if _dist_on(self.group):
+            dist.barrier(group=self.group)
+        self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
+
+
+class NvlRoundBackend(RoundBackend):
+    """``comm_stack.nvl``: the fused NVLink kernel (see :mod:`photon_b200.parallel.fed_round`)."""
+
+    name = "nvl"
+
+    def __init__(self, layout: FlatLayout, strategy: ServerStrategy, device: torch.device, *, rank: int = 0,
+                 world_size: int = 1, group: Any = None, track_norms: bool = True) -> None:
+        super().__init__(layout, strategy, device, rank=rank, world_size=world_size, group=group)
+        from photon_b200.parallel.fed_round import NvlFedRound
+
+        self.fed = NvlFedRound(layout.total, strategy, rank=rank, world_size=world_size, device=device, group=group)
+        self.track_norms = track_norms
+
+    def set_global(self, params: torch.Tensor, momentum: torch.Tensor | None = None, second: torch.Tensor | None = None) -> None:
+        self.fed.set_global(params)
+        self.fed.set_moments(momentum, second)
+        # keep the strategy object's state pointing at the device planes (checkpointing reads them)
+        self.strategy.parameters = self.fed.global_params()
+        self.strategy.layout = self.layout
+        m, v = self.fed.moments()
+        self.strategy.momentum_vector, self.strategy.second_momentum_vector = m, v
+
+    def begin_round(self) -> None:
+        self.fed.begin_round()
+
+    def add_client(self, params: torch.Tensor, weight: float) -> None:
+        self.fed.add_client(params, weight)
+
+    def finish_round(self, server_round: int) -> None:
+        self.fed.finish_round(server_round)
+        self.last_metrics = {}
+
+    def collect_metrics(self) -> dict[str, Any]:
+        """Norm by-products of the last round (host read; call outside timed regions)."""
+        if self.track_norms:
+            self.last_metrics = self.fed.round_norms(self.group)
+        return self.last_metrics
+
+    def global_params(self) -> torch.Tensor:
+        return self.fed.global_params()
+
+    def global_shadow(self) -> torch.Tensor | None:
+        return self.fed.global_shadow()
+
+    def moments(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        """Full-length server moments. Each rank only maintains its shard, so the shards are
+        stitched with one all-reduce of zero-padded copies (checkpoint path, not the hot path)."""
+        out = []
+        for t in self.fed.moments():
+            if t is None or self.world_size == 1 or not _dist_on(self.group):
+                out.append(t)
+                continue
+            lo, hi = self.fed.arena.shard(self.layout.total)
+            full = torch.zeros_like(t)
+            full[lo:hi] = t[lo:hi]
+            dist.all_reduce(full, group=self.group)
+            out.append(full)
+        return out[0], out[1]
+
+    def close(self) -> None:
+        self.fed.close()
+
+
+def build_round_backend(cfg: Any, layout: FlatLayout, strategy: ServerStrategy, device: torch.device, *, rank: int = 0,
+                        world_size: int = 1, group: Any = None) -> RoundBackend:
+    cs = dict(cfg["photon"]["comm_stack"])
+    active = next((k for k in ("nvl", "shm", "ray", "s3") if cs.get(k)), "shm")
+    common = dict(rank=rank, world_size=world_size, group=group)
+    if active == "nvl":
+        if device.type != "cuda":
+            raise RuntimeError("photon.comm_stack.nvl needs CUDA devices; use shm/ray on CPU")
+        return NvlRoundBackend(layout, strategy, device, **common)
+    if active == "ray":
+        return CollectiveRoundBackend(layout, strategy, device, **common)
+    if active == "s3":
+        root = cfg["photon"].get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
+        return FileRoundBackend(layout, strategy, device, root=Path(root) / str(cfg["s3_comm_config"]["bucket_name"]),
+                                run_uuid=str(cfg["run_uuid"]), num_attempts=int(cfg["s3_comm_config"].get("num_attempts", 3)), **common)
+    return ShmRoundBackend(layout, strategy, device, run_uuid=str(cfg["run_uuid"]), **common)

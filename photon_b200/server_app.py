@@ -1,0 +1,127 @@
+"""Federated server entry point: the round loop.
+
+Same control flow as the reference's Flower ``ServerApp`` (ref: photon/server_app.py:85-424):
+init | resume | restore → broadcast → optional eval → for each round: health check, seeded
+client sampling, ``fit_round`` (which ends with the fused aggregate+broadcast), periodic
+evaluation, server checkpoint, timing metrics, optional per-round cleanup.  It runs SPMD:
+launch it on every GPU with ``torchrun`` (or as one process for 1 GPU / CPU); rank 0 owns the
+history and the checkpoint store.
+
+    PHOTON_SAVE_PATH=... python -m photon_b200.hydra_resolver <overrides>
+    PHOTON_SAVE_PATH=... torchrun --nproc-per-node 8 -m photon_b200.server_app
+"""
+from __future__ import annotations
+
+import os
+import time
+from pathlib import Path
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+from photon_b200.checkpoint.store import CheckpointStore
+from photon_b200.clients.trainer_utils import initialize_dist, pick_device
+from photon_b200.config import load_config
+from photon_b200.federation import FederationRuntime
+from photon_b200.server.evaluate_utils import evaluate_round
+from photon_b200.server.fit_utils import fit_round
+from photon_b200.server.init_utils import initialize_round, resume_from_round, server_state_dict
+from photon_b200.server.server_util import spmd_node_ids, wait_for_nodes_to_connect
+from photon_b200.utils.core import wandb_init
+from photon_b200.wandb_history import WandbHistory
+
+
+def _store_for(cfg: Any) -> CheckpointStore | None:
+    if not (cfg["photon"]["checkpoint"] or cfg["photon"]["comm_stack"].get("s3")):
+        return None
+    root = cfg["photon"].get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
+    return CheckpointStore(root, str(cfg["s3_comm_config"]["bucket_name"]))
+
+
+def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int | None = None) -> WandbHistory:
+    own = runtime is None
+    if runtime is None:
+        device = pick_device(int(os.environ.get("LOCAL_RANK", "0")))
+        rank, world = initialize_dist(device)
+        runtime = FederationRuntime(cfg, device=device, rank=rank, world_size=world)
+    runtime.build()
+    fl, ph, run_uuid = cfg["fl"], cfg["photon"], str(cfg["run_uuid"])
+    store = _store_for(cfg)
+    history = WandbHistory(bool(cfg.get("use_wandb", False)))
+    wandb_run = wandb_init(bool(cfg.get("use_wandb", False)) and runtime.rank == 0, **dict((cfg.get("wandb") or {}).get("setup") or {}))
+    t_zero = time.time()
+
+    # ---- init / resume / restore from another run
+    start_round, time_offset = 0, 0.0
+    resume = None
+    if store is not None:
+        if ph.get("restore_run_uuid") and runtime.rank == 0:
+            src = str(ph["restore_run_uuid"])
+            r = store.interpret_resume_round(src, ph.get("resume_round", -1), runtime.strategy.state_keys)
+            if r is not None and not store.obtain_sorted_rounds(run_uuid, runtime.strategy.state_keys):
+                store.copy_old_checkpoints_to_new_run(src, run_uuid, r, state_keys=runtime.strategy.state_keys,
+                                                      copy_client_checkpoints=bool(ph.get("copy_client_checkpoints", True)),
+                                                      client_ids=range(int(fl["n_total_clients"])))
+        if runtime.world_size > 1:
+            dist.barrier(group=runtime.group)
+        resume = store.interpret_resume_round(run_uuid, ph.get("resume_round"), runtime.strategy.state_keys)
+    if resume is not None and resume > 0:
+        history, time_offset = resume_from_round(runtime, store, run_uuid, resume)
+        start_round = resume
+    else:
+        initialize_round(runtime, store, history)
+
+    wait_for_nodes_to_connect(runtime.n_nodes, lambda: spmd_node_ids(runtime.group)[:: runtime.gpus_per_client], poll_s=0.0)
+    eval_period = fl.get("eval_period")
+    if eval_period and start_round == 0:
+        loss, em = evaluate_round(runtime, 0)
+        if runtime.rank == 0 and loss is not None:
+            history.add_loss_distributed(0, loss)
+            history.add_metrics_distributed(0, em)
+
+    total = int(fl["n_rounds"]) if n_rounds is None else start_round + n_rounds
+    for server_round in range(start_round + 1, total + 1):
+        t_round = time.time()
+        node_ids = spmd_node_ids(runtime.group)                    # health check (ref: server_app.py:285)
+        sampled = runtime.sample_clients()
+        metrics = fit_round(runtime, server_round, sampled)
+        metrics["server/n_nodes"] = len(node_ids) // runtime.gpus_per_client
+        if runtime.rank == 0:
+            history.add_metrics_distributed_fit(server_round, metrics)
+        if eval_period and server_round % int(eval_period) == 0:
+            loss, em = evaluate_round(runtime, server_round)
+            if runtime.rank == 0 and loss is not None:
+                history.add_loss_distributed(server_round, loss)
+                history.add_metrics_distributed(server_round, em)
+        if store is not None:
+            tensors = runtime.state_tensors()                      # collective when moments are sharded
+            if runtime.rank == 0:
+                store.upload_server_checkpoint(run_uuid, server_round, layout=runtime.layout, tensors=tensors,
+                                               state=server_state_dict(runtime, history, time_offset + time.time() - t_zero))
+                if cfg.get("cleanup_checkpoints_per_round"):
+                    store.cleanup_checkpoints(run_uuid, per_round=True)
+        if runtime.rank == 0:
+            history.add_metrics_centralized(server_round, {"server/round_time": time.time() - t_round})
+    if store is not None and cfg.get("cleanup_checkpoints") and runtime.rank == 0:
+        store.cleanup_checkpoints(run_uuid)
+    if wandb_run is not None:
+        wandb_run.finish()
+    if own:
+        runtime.close()
+    return history
+
+
+def main() -> None:
+    save_path = os.environ.get("PHOTON_SAVE_PATH")
+    if not save_path:
+        raise SystemExit("PHOTON_SAVE_PATH must point at the directory holding config.yaml")
+    cfg = load_config(Path(save_path) / "config.yaml")
+    hist = run_server(cfg)
+    if int(os.environ.get("RANK", "0")) == 0:
+        last = {k: v[-1][1] for k, v in hist.metrics_distributed_fit.items() if "/layer/" not in k}
+        print("[server] done. last round fit metrics:", {k: (round(v, 5) if isinstance(v, float) else v) for k, v in last.items()})
+
+
+if __name__ == "__main__":
+    main()

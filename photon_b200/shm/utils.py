@@ -1,0 +1,200 @@
+"""POSIX shared-memory codecs for the host hand-off path.
+
+Role of ref photon/shm/utils.py (:138-651): model parameters travel between the
+node manager, its workers and the server as ONE flat segment described by
+``ModelParametersMetadata`` (per-tensor byte bounds, shapes, dtypes); scalars
+(n_samples int64, eval loss float64) and pickled dicts (configs, metrics) get
+their own tiny segments.  On the B200 path this is the *fallback / baseline*
+transport (``photon.comm_stack.shm``) — the product path is the NVLink arena —
+but it is also what the CPU plumbing tests and the multi-process node manager use.
+
+Differences from the reference, on purpose: segments are unregistered from
+Python's resource tracker through the public ``track=False`` flag where
+available (instead of monkey-patching, ref :403-429) and ``close_all_shms``
+removes every suffixed segment of a uuid (the reference leaks them).
+"""
+from __future__ import annotations
+
+import pickle
+import sys
+from dataclasses import asdict, dataclass, field
+from multiprocessing import shared_memory
+from typing import Any, Sequence
+
+import numpy as np
+
+from photon_b200.shm import constants as C
+
+
+def _open(name: str, create: bool = False, size: int = 0, untrack: bool = True) -> shared_memory.SharedMemory:
+    kw: dict[str, Any] = {}
+    if sys.version_info >= (3, 13):
+        kw["track"] = False
+    shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0, **kw)
+    if sys.version_info < (3, 13) and untrack:
+        remove_shm_from_resource_tracker(shm)
+    return shm
+
+
+def remove_shm_from_resource_tracker(shm: shared_memory.SharedMemory) -> None:
+    """Detach the segment from the creating process' resource tracker so it survives that
+    process (the consumer unlinks it)."""
+    try:
+        from multiprocessing import resource_tracker
+
+        resource_tracker.unregister(shm._name, "shared_memory")  # type: ignore[attr-defined]  # noqa: SLF001
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def shm_exists(name: str) -> bool:
+    try:
+        s = _open(name)
+    except FileNotFoundError:
+        return False
+    s.close()
+    return True
+
+
+def unlink_quietly(name: str) -> None:
+    try:
+        s = _open(name, untrack=False)  # stays registered so that unlink()'s unregister is balanced
+    except FileNotFoundError:
+        return
+    s.close()
+    try:
+        s.unlink()
+    except FileNotFoundError:
+        pass
+
+
+@dataclass
+class ModelParametersMetadata:
+    """Layout of a flat parameter segment (ref: shm/utils.py:138-247)."""
+
+    total_num_bytes: int = 0
+    array_bounds: list[tuple[int, int]] = field(default_factory=list)
+    shapes: list[tuple[int, ...]] = field(default_factory=list)
+    dtypes: list[str] = field(default_factory=list)
+
+    @classmethod
+    def from_ndarrays(cls, arrays: Sequence[np.ndarray], align: int = 64) -> "ModelParametersMetadata":
+        bounds, shapes, dtypes, off = [], [], [], 0
+        for a in arrays:
+            a = np.asarray(a)
+            lo = (off + align - 1) // align * align
+            hi = lo + a.nbytes
+            bounds.append((lo, hi)), shapes.append(tuple(a.shape)), dtypes.append(str(a.dtype))
+            off = hi
+        return cls(total_num_bytes=max(off, 1), array_bounds=bounds, shapes=shapes, dtypes=dtypes)
+
+    def to_literal(self) -> str:
+        return str(asdict(self))
+
+    @classmethod
+    def from_literal(cls, s: str | dict[str, Any]) -> "ModelParametersMetadata":
+        import ast
+
+        d = ast.literal_eval(s) if isinstance(s, str) else s
+        return cls(total_num_bytes=int(d["total_num_bytes"]), array_bounds=[tuple(b) for b in d["array_bounds"]],
+                   shapes=[tuple(x) for x in d["shapes"]], dtypes=list(d["dtypes"]))
+
+    def same_layout(self, other: "ModelParametersMetadata") -> bool:
+        return self.shapes == other.shapes and self.dtypes == other.dtypes
+
+
+def set_parameters_shm(name: str, arrays: Sequence[np.ndarray], meta: ModelParametersMetadata | None = None,
+                       create: bool = True) -> tuple[shared_memory.SharedMemory, ModelParametersMetadata]:
+    """Write ``arrays`` into segment ``name`` (created if missing). Caller keeps the handle alive."""
+    meta = meta or ModelParametersMetadata.from_ndarrays(arrays)
+    try:
+        shm = _open(name)
+        if shm.size < meta.total_num_bytes:
+            shm.close()
+            unlink_quietly(name)
+            raise FileNotFoundError
+    except FileNotFoundError:
+        if not create:
+            raise
+        shm = _open(name, create=True, size=meta.total_num_bytes)
+    for a, (lo, hi), shp, dt in zip(arrays, meta.array_bounds, meta.shapes, meta.dtypes):
+        dst = np.ndarray(shp, dtype=np.dtype(dt), buffer=shm.buf[lo:hi])
+        np.copyto(dst, np.asarray(a, dtype=np.dtype(dt)).reshape(shp))
+    return shm, meta
+
+
+def get_parameters_shm(name: str, meta: ModelParametersMetadata, copy: bool = False
+                       ) -> tuple[shared_memory.SharedMemory, list[np.ndarray]]:
+    """Zero-copy per-tensor views over segment ``name`` (ref: shm/utils.py:569-623).
+    Keep the returned handle referenced for as long as the views are used."""
+    shm = _open(name)
+    views = [np.ndarray(shp, dtype=np.dtype(dt), buffer=shm.buf[lo:hi])
+             for (lo, hi), shp, dt in zip(meta.array_bounds, meta.shapes, meta.dtypes)]
+    if copy:
+        views = [v.copy() for v in views]
+    return shm, views
+
+
+# ----------------------------------------------------------------------------- scalars
+def _scalar(name: str, dtype: str, value: Any | None) -> Any:
+    nbytes = np.dtype(dtype).itemsize
+    if value is not None:
+        try:
+            shm = _open(name)
+        except FileNotFoundError:
+            shm = _open(name, create=True, size=nbytes)
+        np.ndarray((1,), dtype=dtype, buffer=shm.buf[:nbytes])[0] = value
+        shm.close()
+        return value
+    shm = _open(name)
+    out = np.ndarray((1,), dtype=dtype, buffer=shm.buf[:nbytes])[0].item()
+    shm.close()
+    return out
+
+
+def set_n_samples_shm(uuid: str, n: int) -> None:
+    _scalar(uuid + C.W_N_SAMPLES_SHM, "int64", int(n))
+
+
+def get_n_samples_shm(uuid: str) -> int:
+    return int(_scalar(uuid + C.W_N_SAMPLES_SHM, "int64", None))
+
+
+def set_eval_loss_shm(uuid: str, loss: float) -> None:
+    _scalar(uuid + C.W_EVAL_LOSS_SHM, "float64", float(loss))
+
+
+def get_eval_loss_shm(uuid: str) -> float:
+    return float(_scalar(uuid + C.W_EVAL_LOSS_SHM, "float64", None))
+
+
+# --------------------------------------------------------------------- pickled dict segments
+def set_dict_shm(name: str, obj: Any) -> None:
+    """8-byte length header + pickle payload; the segment is re-created when it must grow."""
+    blob = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    need = 8 + len(blob)
+    try:
+        shm = _open(name)
+        if shm.size < need:
+            shm.close()
+            unlink_quietly(name)
+            raise FileNotFoundError
+    except FileNotFoundError:
+        shm = _open(name, create=True, size=max(need, 4096))
+    shm.buf[:8] = len(blob).to_bytes(8, "little")
+    shm.buf[8:need] = blob
+    shm.close()
+
+
+def get_dict_shm(name: str) -> Any:
+    shm = _open(name)
+    n = int.from_bytes(bytes(shm.buf[:8]), "little")
+    obj = pickle.loads(bytes(shm.buf[8:8 + n]))  # noqa: S301 - same-host IPC between our own processes
+    shm.close()
+    return obj
+
+
+def close_all_shms(uuid: str) -> None:
+    """Unlink every segment this uuid may own (bare + all suffixes)."""
+    for suffix in ("", C.NM_CONFIG_SHM, C.NM_PARAMS_SHM, C.W_PARAMS_SHM, C.W_N_SAMPLES_SHM, C.W_EVAL_LOSS_SHM, C.W_METRICS_SHM):
+        unlink_quietly(uuid + suffix)

@@ -1,0 +1,128 @@
+"""Core helpers shared by server and clients (the role of ref photon/utils.py):
+parameter get/set by (filtered, sorted) name, freeze lists, npz/bin model files,
+norm helpers, device/core counts, parameter sanity checker, wandb init."""
+from __future__ import annotations
+
+import os
+import pickle
+from pathlib import Path
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+_STRIP = ("model.", "module.", "_fsdp_wrapped_module.", "_checkpoint_wrapped_module.")
+
+
+def clean_parameter_name(name: str) -> str:
+    """Strip wrapper prefixes so names match the bare ``transformer.*`` tree
+    (ref: photon/utils.py:602-637)."""
+    changed = True
+    while changed:
+        changed = False
+        for s in _STRIP:
+            if s in name:
+                name = name.replace(s, "")
+                changed = True
+    return name
+
+
+def get_list_of_parameters_names(model: torch.nn.Module, key_filter: str | None = None) -> list[str]:
+    names = sorted(clean_parameter_name(n) for n, p in model.named_parameters() if p.requires_grad)
+    return [n for n in names if key_filter is None or key_filter in n]
+
+
+def construct_parameters_dict(names: Sequence[str], arrays: Sequence[Any], key_filter: str | None = None) -> dict[str, Any]:
+    """Zip sorted names with payload arrays, keeping only keys that contain ``key_filter``
+    (ref: photon/utils.py:640-670)."""
+    if len(names) != len(arrays):
+        raise ValueError(f"{len(names)} names vs {len(arrays)} arrays")
+    return {n: a for n, a in zip(names, arrays) if key_filter is None or key_filter in n}
+
+
+def parameters_checker(a: Sequence[np.ndarray], b: Sequence[np.ndarray], *, expect_equal: bool, what: str = "") -> None:
+    """Shapes must match; values must be all-equal / not-all-equal (ref: photon/utils.py:147-224)."""
+    if len(a) != len(b):
+        raise AssertionError(f"{what}: {len(a)} vs {len(b)} tensors")
+    same = True
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x.shape != y.shape:
+            raise AssertionError(f"{what}: tensor {i} shape {x.shape} vs {y.shape}")
+        same = same and bool(np.array_equal(x, y))
+    if expect_equal and not same:
+        raise AssertionError(f"{what}: parameters differ but were expected to be equal")
+    if not expect_equal and same:
+        raise AssertionError(f"{what}: parameters are identical but were expected to change")
+
+
+# ------------------------------------------------------------------- model files (npz / npzc / bin)
+def dump_model_parameters_to_file(path: str | os.PathLike, arrays: Sequence[np.ndarray], compressed: bool = False) -> Path:
+    """``np.savez(*arrays)`` → keys ``arr_0..arr_{n-1}`` in sorted-name order (ref: photon/utils.py:733-761)."""
+    p = Path(path)
+    p.parent.mkdir(parents=True, exist_ok=True)
+    tmp = p.with_name(p.name + ".tmp")
+    with open(tmp, "wb") as f:
+        (np.savez_compressed if compressed else np.savez)(f, *arrays)
+    os.replace(tmp, p)
+    return p
+
+
+def load_model_parameters_from_file(path: str | os.PathLike) -> list[np.ndarray]:
+    """Accepts ``.npz``, ``.npzc`` (compressed) and ``.bin`` (pickled list / Flower-like Parameters)."""
+    p = Path(path)
+    if p.suffix in (".npz", ".npzc"):
+        with np.load(p, allow_pickle=False) as z:
+            keys = sorted(z.files, key=lambda k: int(k.split("_")[1]))
+            return [z[k] for k in keys]
+    if p.suffix == ".bin":
+        with open(p, "rb") as f:
+            obj = pickle.load(f)  # noqa: S301 - our own checkpoints
+        if hasattr(obj, "tensors"):
+            import io
+
+            return [np.load(io.BytesIO(t), allow_pickle=False) for t in obj.tensors]
+        return [np.asarray(a) for a in obj]
+    raise ValueError(f"unsupported parameter file {p}")
+
+
+# ----------------------------------------------------------------------------------- norms
+def sum_of_squares(arrays: Sequence[np.ndarray | torch.Tensor]) -> float:
+    return float(sum(float((torch.as_tensor(a).double() ** 2).sum()) for a in arrays))
+
+
+def l2_norm(arrays: Sequence[np.ndarray | torch.Tensor]) -> float:
+    return float(np.sqrt(sum_of_squares(arrays)))
+
+
+# ----------------------------------------------------------------------------- environment
+def get_n_cuda_devices() -> int:
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def get_n_cpu_cores() -> int | None:
+    conc = os.environ.get("CPU_CONCURRENCY")
+    return int(conc) if conc else os.cpu_count()
+
+
+def get_device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+
+def appointed_cuda_devices() -> list[int]:
+    """``APPOINTED_CUDA_DEVICE="0,1,…"`` contract of the launch scripts (ref: worker/utils.py:94-120)."""
+    s = os.environ.get("APPOINTED_CUDA_DEVICE", "")
+    return [int(x) for x in s.split(",") if x.strip() != ""]
+
+
+def wandb_init(enabled: bool, **kwargs: Any) -> Any:
+    """Returns a wandb run or None (no network here → offline / disabled; ref: photon/utils.py:780-816)."""
+    if not enabled:
+        return None
+    try:
+        import wandb  # type: ignore[import-not-found]
+
+        kwargs.setdefault("mode", "offline")
+        return wandb.init(**kwargs)
+    except Exception as e:  # noqa: BLE001
+        print(f"[wandb] unavailable ({e}); metrics stay in the History object")
+        return None
