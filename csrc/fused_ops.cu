@@ -108,6 +108,7 @@ __global__ void embed_bwd_wpe_kernel(const __nv_bfloat16* __restrict__ dh, float
 // ------------------------------------------------------------------ LayerNorm (one warp per row, row in registers)
 constexpr int LN_MAXCH = 16;  // 16 chunks x 32 lanes x 8 elems = d <= 4096
 
+template <int LN_NCH>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                       float* __restrict__ mean, float* __restrict__ rstd, long long T,
@@ -116,10 +117,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-  uint4 buf[LN_MAXCH];
+  uint4 buf[LN_NCH];
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c) {
+  for (int c = 0; c < LN_NCH; ++c) {
     const int e = c * 256 + lane * 8;
     if (e < d) {
       buf[c] = xr[c * 32 + lane];
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
   const float mu = warp_sum(s) / d;
   float ss = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c) {
+  for (int c = 0; c < LN_NCH; ++c) {
     const int e = c * 256 + lane * 8;
     if (e < d) {
       float f[8];
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
   }
   uint4* yr = reinterpret_cast<uint4*>(y + row * d);
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c) {
+  for (int c = 0; c < LN_NCH; ++c) {
     const int e = c * 256 + lane * 8;
     if (e < d) {
       float f[8];
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
 }
 
 // dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))  [+ dres]   (row-wise part of LN backward)
+template <int LN_NCH>
 __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                          const float* __restrict__ gamma, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
@@ -176,10 +178,10 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const __nv_bfloat16* __r
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
   const uint4* gr = reinterpret_cast<const uint4*>(dy + row * d);
   const float mu = mean[row], rs = rstd[row];
-  uint4 bx[LN_MAXCH], bg[LN_MAXCH];
+  uint4 bx[LN_NCH], bg[LN_NCH];
   float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c) {
+  for (int c = 0; c < LN_NCH; ++c) {
     const int e = c * 256 + lane * 8;
     if (e < d) {
       bx[c] = xr[c * 32 + lane];
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const __nv_bfloat16* __r
   uint4* outr = reinterpret_cast<uint4*>(dx + row * d);
   const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * d) : nullptr;
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c) {
+  for (int c = 0; c < LN_NCH; ++c) {
     const int e = c * 256 + lane * 8;
     if (e < d) {
       float fx[8], fg[8], fr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -472,8 +474,15 @@ void embed_bwd(const int64_t* ids, const void* dh, float* dwte, float* dwpe, lon
 void layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long T, int d,
                    float eps, cudaStream_t st) {
   if (d % 8 || d > LN_MAXCH * 256) throw std::runtime_error("layernorm: d must be a multiple of 8 and <= 4096");
-  ln_fwd_kernel<<<int((T + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, T, d, eps);
-  PB_CHECK_LAUNCH("layernorm_fwd");
+  const int nch = (d + 255) / 256;
+#define PB_LN_FWD(N)                                                                                                            \
+  if (nch <= N) {                                                                                                               \
+    ln_fwd_kernel<N><<<int((T + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, T, d, eps); \
+    PB_CHECK_LAUNCH("layernorm_fwd");                                                                                           \
+    return;                                                                                                                     \
+  }
+  PB_LN_FWD(1) PB_LN_FWD(2) PB_LN_FWD(3) PB_LN_FWD(4) PB_LN_FWD(6) PB_LN_FWD(8) PB_LN_FWD(10) PB_LN_FWD(12) PB_LN_FWD(16)
+#undef PB_LN_FWD
 }
 void col_reduce(const void* dy, long long ld, const void* x, const float* mean, const float* rstd, float* out_sum, float* out_dot,
                 long long T, int d, cudaStream_t st) {
@@ -489,8 +498,16 @@ void col_reduce(const void* dy, long long ld, const void* x, const float* mean, 
 void layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres, void* dx,
                    float* dgamma, float* dbeta, long long T, int d, cudaStream_t st) {
   if (d % 8 || d > LN_MAXCH * 256) throw std::runtime_error("layernorm: d must be a multiple of 8 and <= 4096");
-  ln_bwd_dx_kernel<<<int((T + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd,
-                                                     (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, T, d);
+  const int nch = (d + 255) / 256;
+  bool done = false;
+#define PB_LN_BWD(N)                                                                                                  \
+  if (!done && nch <= N) {                                                                                            \
+    ln_bwd_dx_kernel<N><<<int((T + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd, \
+                                                          (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, T, d);      \
+    done = true;                                                                                                      \
+  }
+  PB_LN_BWD(1) PB_LN_BWD(2) PB_LN_BWD(3) PB_LN_BWD(4) PB_LN_BWD(6) PB_LN_BWD(8) PB_LN_BWD(10) PB_LN_BWD(12) PB_LN_BWD(16)
+#undef PB_LN_BWD
   PB_CHECK_LAUNCH("layernorm_bwd_dx");
   if (dgamma || dbeta) col_reduce(dy, d, x, mean, rstd, dbeta, dgamma, T, d, st);
 }

@@ -41,6 +41,7 @@ struct Params {
   long long ld_aux;             // row stride of aux, elements
   int accumulate;               // EPI_F32: reduce-add into D instead of overwrite
   float alpha;                  // scale applied to the accumulator before the epilogue
+  int splits, kb_per_split;     // split-K (EPI_F32 + accumulate): work item = (tile, k-range)
 };
 
 template <int A_MN, int B_MN, int EPI>
@@ -86,16 +87,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int num_work = num_tiles * p.splits;
 
   if (warp == 0) {
     // ======================= TMA producer (one thread) =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w % num_tiles, sp = w / num_tiles;
         const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
         const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE;
@@ -129,11 +133,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int sp = w / num_tiles;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
@@ -144,7 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : make_smem_desc_sw128(a_base + k * (UK * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * (UK * 128), BK * 128, 1024)
                                         : make_smem_desc_sw128(b_base + k * (UK * 2), 16, 1024);
-            tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -168,7 +174,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t swz = (row_in_tile & 7);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int tile = w % num_tiles;
       const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
       const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
       mbar_wait(&tfull[acc], acc_phase);
@@ -261,7 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          if (EPI == EPI_F32 && p.accumulate) {
+          if (EPI == EPI_F32 && (p.accumulate || p.splits > 1)) {
             tma_reduce_add_2d(&tmD, buf0, col0, m_blk * BM);
           } else {
             tma_store_2d(&tmD, buf0, col0, m_blk * BM);
@@ -369,7 +376,21 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   p.accumulate = g.accumulate;
   p.alpha = g.alpha;
   int sms = g.num_sms > 0 ? g.num_sms : 148;
-  int grid = p.tiles_m * p.tiles_n < sms ? p.tiles_m * p.tiles_n : sms;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+  p.splits = 1;
+  if (f32 && g.accumulate && tiles < sms && num_kb >= 16) {
+    // few output tiles, long K (weight gradients): split K across CTAs, partials meet in the fp32
+    // gradient bucket through TMA reduce-add. Aim for ~2 waves, >= 8 k-blocks per split.
+    int s = (2 * sms + tiles / 2) / tiles;
+    if (s > num_kb / 8) s = num_kb / 8;
+    if (s < 1) s = 1;
+    p.splits = s;
+  }
+  p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty tails
+  const int work = tiles * p.splits;
+  int grid = work < sms ? work : sms;
 
 #define PB_CASE(AM, BMJ, E)                                            \
   if (g.a_mn == AM && g.b_mn == BMJ && g.epi == E) {                   \

@@ -208,20 +208,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
 }
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): plenty below bf16 resolution, ~12 instr.
-__device__ __forceinline__ float fast_erf(float x) {
-  float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f);
-  float e = __expf(-ax * ax);
-  float r = fmaf(-p * t, e, 1.0f);
-  return copysignf(r, x);
+// Exact-erf GELU pieces via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution).
+// One MUFU.RCP + one MUFU.EX2 per element; the exp(-x^2/2) term is shared between the CDF (erf) and the PDF.
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * ax * ax);   // exp(-x^2/2)
+  const float half_erfc = 0.5f * p * t * e;                // 0.5 * erfc(|x|/sqrt2)
+  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  pdf = 0.3989422804f * e;
 }
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118f)); }
+__device__ __forceinline__ float gelu_exact(float x) {
+  float c, d;
+  gelu_cdf_pdf(x, c, d);
+  return x * c;
+}
 __device__ __forceinline__ float gelu_grad(float x) {
-  float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118f));
-  float pdf = 0.3989422804f * __expf(-0.5f * x * x);
-  return fmaf(x, pdf, cdf);
+  float c, d;
+  gelu_cdf_pdf(x, c, d);
+  return fmaf(x, d, c);
 }
 
 // ---------------------------------------------------------------- cross-GPU flags (sys scope)

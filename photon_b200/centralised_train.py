@@ -1,0 +1,115 @@
+"""Centralised (non-federated) training entry point — the DDP baseline path of the reference
+(ref: photon/centralised_train.py:56-166; launched by ``composer --world_size N`` at
+scripts/centralised_training.sh:132).  Launch with torchrun; on >1 GPU the gradient all-reduce
+is ONE fused NVLink kernel on the flat bucket (``photon_b200.parallel.ddp.NvlGradComm``),
+fused with the clipping norm — not 148 NCCL calls.
+
+    PHOTON_SAVE_PATH=... torchrun --nproc-per-node 8 -m photon_b200.centralised_train
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+
+from photon_b200.clients.configs import CentralizedConfig
+from photon_b200.clients.trainer_utils import get_trainer_object, initialize_dist, pick_device
+from photon_b200.config import load_config
+from photon_b200.train.trainer import Trainer
+from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file
+
+
+def _centralized_config(cfg: Any) -> CentralizedConfig:
+    c, fl = dict(cfg.get("centralized") or {}), dict(cfg.get("fl") or {})
+    return CentralizedConfig(**c, use_unigram_metrics=bool(fl.get("use_unigram_metrics", False)),
+                             allow_unigram_metrics_failures=bool(fl.get("allow_unigram_metrics_failures", False)),
+                             resize_vocab=fl.get("resize_vocab"), frozen_layers=fl.get("frozen_layers"),
+                             unfrozen_layers=fl.get("unfrozen_layers"), pretrained_model_path=cfg.get("pretrained_model_path"),
+                             wte_parameters_path=cfg.get("wte_parameters_path"))
+
+
+def set_wte_parameters(trainer: Trainer, wte: np.ndarray) -> None:
+    """Transplant only the token embedding (ref: photon/utils.py:585-599)."""
+    st = trainer.state
+    view = st.flat.layout.view(st.flat.params, "transformer.wte.weight")
+    if tuple(view.shape) != tuple(wte.shape):
+        raise ValueError(f"wte shape {wte.shape} != model {tuple(view.shape)}")
+    view.copy_(torch.from_numpy(np.asarray(wte, dtype=np.float32)).to(view.device))
+    st.backend.params_updated()
+
+
+def dump_checkpoint_npz(trainer: Trainer, run_uuid: str, out_dir: str | Path = ".") -> Path:
+    """``{run_uuid}-{n_steps}-checkpoint.npz`` with arr_i in sorted-name order (ref: :139-166)."""
+    st = trainer.state
+    path = Path(out_dir) / f"{run_uuid}-{st.timestamp.batch}-checkpoint.npz"
+    return dump_model_parameters_to_file(path, st.flat.to_ndarrays())
+
+
+def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int | None = None, world_size: int | None = None,
+                    duration: str | None = None, use_nvl_allreduce: bool | None = None) -> Trainer:
+    cc = _centralized_config(cfg)
+    device = device or pick_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank is None or world_size is None:
+        rank, world_size = initialize_dist(device)
+    grad_comm = None
+    if world_size > 1:
+        if use_nvl_allreduce is None:
+            use_nvl_allreduce = device.type == "cuda" and not all(
+                (cfg.get("kernels") or {}).get(k, "auto") == "torch" for k in ("gemm", "optimizer"))
+        if use_nvl_allreduce:
+            from photon_b200.models.mpt import MPTConfig
+            from photon_b200.parallel.ddp import NvlGradComm
+            from photon_b200.utils.flat import FlatLayout
+            from photon_b200.models.mpt import MPTForCausalLM
+
+            mc = MPTConfig.from_model_cfg(dict(cfg["llm_config"]["model"]))
+            with torch.device("meta"):
+                shapes = [(n, p.shape) for n, p in MPTForCausalLM(mc, device="meta", init=False).named_parameters()]
+            grad_comm = NvlGradComm(FlatLayout.build(shapes).total, rank=rank, world_size=world_size, device=device)
+        else:
+            from photon_b200.parallel.ddp import NcclGradComm
+
+            grad_comm = NcclGradComm()
+    trainer, _ = get_trainer_object(cfg, cc.stream_id, log_name="_centralised", device=device, rank=rank, world_size=world_size,
+                                    grad_comm=grad_comm, split_eval=cc.split_eval, use_unigram_metrics=cc.use_unigram_metrics,
+                                    allow_unigram_metrics_failures=cc.allow_unigram_metrics_failures, frozen_layers=cc.frozen_layers,
+                                    unfrozen_layers=cc.unfrozen_layers, resize_vocab=cc.resize_vocab)
+    if cc.pretrained_model_path:
+        arrays = load_model_parameters_from_file(cc.pretrained_model_path)
+        trainer.state.flat.load_ndarrays(arrays[: len(trainer.state.flat.names)])
+        trainer.state.backend.params_updated()
+    if cc.wte_parameters_path:
+        set_wte_parameters(trainer, load_model_parameters_from_file(cc.wte_parameters_path)[0])
+    if world_size > 1:  # identical start on every rank
+        torch.distributed.broadcast(trainer.state.flat.params, src=0)
+        trainer.state.backend.params_updated()
+    run_uuid = str(cfg["run_uuid"])
+    if cfg["llm_config"].get("eval_first") and trainer.eval_loaders:
+        trainer.eval()
+    if cc.store_init_model and rank == 0:
+        dump_checkpoint_npz(trainer, run_uuid)
+    if not cc.eval_only:
+        trainer.fit(duration=duration, reset_time=cc.reset_timestamp)
+    elif trainer.eval_loaders:
+        trainer.eval()
+    if cc.store_final_model and rank == 0:
+        dump_checkpoint_npz(trainer, run_uuid)
+    return trainer
+
+
+def main() -> None:
+    save_path = os.environ.get("PHOTON_SAVE_PATH")
+    if not save_path:
+        raise SystemExit("PHOTON_SAVE_PATH must point at the directory holding config.yaml")
+    cfg = load_config(Path(save_path) / "config.yaml")
+    tr = run_centralised(cfg)
+    if tr.rank == 0:
+        print("[centralised_train] done:", tr.state.timestamp, tr.state.train_metric_values)
+    tr.close()
+
+
+if __name__ == "__main__":
+    main()

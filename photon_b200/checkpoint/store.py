@@ -132,8 +132,11 @@ class CheckpointStore:
         if not base.exists():
             return
         rounds = sorted(int(p.name) for p in base.iterdir() if p.is_dir() and p.name.isdigit())
-        for r in rounds[: len(rounds) - keep_last if keep_last else len(rounds)]:
-            shutil.rmtree(base / str(r), ignore_errors=True)
+        complete = [r for r in rounds if (base / str(r) / STATE_FILE).exists()]
+        keep = set(complete[-keep_last:]) if keep_last else set()
+        for r in rounds:
+            if r not in keep:
+                shutil.rmtree(base / str(r), ignore_errors=True)
 
     def delete_clients_checkpoints(self, run_uuid: str, keep_latest: bool = False) -> None:
         base = self.bucket / run_uuid

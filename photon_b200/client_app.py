@@ -1,0 +1,66 @@
+"""Node-side message handlers: ``train`` / ``evaluate`` / ``query`` / ``lifespan``
+(ref: photon/client_app.py:78-291), bound to a :class:`NodeManagerApp`.
+
+In the reference these are Flower ``ClientApp`` callbacks fed by gRPC; here they consume the
+in-memory :class:`photon_b200.messages.Message` objects of our control plane and reply with the
+same record fields (``fitres.*``, ``evaluateres.*``, ``{"broadcast": {"status": "OK"}}``).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Any, Iterator
+
+from photon_b200.messages import Code, EvaluateRes, FitRes, Message, Status
+from photon_b200.node_manager.node_manager_app import NodeManagerApp
+
+
+class ClientApp:
+    def __init__(self, cfg: Any, n_workers: int | None = None, node_id: int = 0) -> None:
+        self.cfg, self.node_id = cfg, node_id
+        self.nm = NodeManagerApp(cfg, n_workers=n_workers)
+        self.refresh_period = int(cfg["photon"].get("refresh_period", 50))
+
+    @contextlib.contextmanager
+    def lifespan(self) -> Iterator["ClientApp"]:
+        """Workers live as long as the app (the reference's ``--persist-client`` fork feature)."""
+        self.nm.create_and_start_workers()
+        try:
+            yield self
+        finally:
+            self.nm.close()
+
+    # ------------------------------------------------------------------------- handlers
+    def set_parameters(self, msg: Message) -> Message:
+        self.nm.set_parameters(msg.content["parameters"])
+        return Message("query", {"broadcast": {"status": "OK"}}, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
+
+    def train(self, msg: Message) -> Message:
+        ins = msg.content
+        server_round = int(ins.config["server_round"])
+        if self.refresh_period and server_round > 1 and server_round % self.refresh_period == 0:
+            self.nm.refresh_workers()                     # shed leaked memory (ref: client_app.py:175-177)
+        per_client = getattr(msg, "per_client", {})
+        results = self.nm.fit({cid: {"fit_config": fc} for cid, fc in per_client.items()})
+        return Message("train", results, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
+
+    def evaluate(self, msg: Message) -> Message:
+        per_client = getattr(msg, "per_client", {})
+        res = self.nm.eval({cid: {"eval_config": ec} for cid, ec in per_client.items()})
+        return Message("evaluate", res, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
+
+    def query(self, msg: Message) -> Message:
+        kind = (msg.content or {}).get("type")
+        if kind == "broadcast_parameters":
+            return self.set_parameters(msg)
+        if kind == "free_resources":
+            self.nm.refresh_workers()
+            return Message("query", {"free_resources": {"status": "OK"}}, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
+        return Message("query", None, node_id=self.node_id, error=f"unknown query type {kind!r}", reply_to=msg.msg_id)
+
+    def handle(self, msg: Message) -> Message:
+        try:
+            return {"train": self.train, "evaluate": self.evaluate, "query": self.query}[msg.kind](msg)
+        except Exception as e:  # noqa: BLE001 - a node never crashes the federation; it replies with an error
+            bad: Any = [FitRes(Status(Code.FAILED, repr(e)), None, 0, {})] if msg.kind == "train" else (
+                EvaluateRes(Status(Code.FAILED, repr(e)), 0.0, 0, {}) if msg.kind == "evaluate" else None)
+            return Message(msg.kind, bad, node_id=self.node_id, error=repr(e), reply_to=msg.msg_id)

@@ -51,7 +51,7 @@ class B200Engine:
     def __init__(self, cfg: MPTConfig, device: torch.device | str = "cuda", precision: str = "amp_bf16",
                  kernels: dict[str, Any] | None = None, seed: int | None = 17, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
-                 lm_head_chunk: int = 8192) -> None:
+                 lm_head_chunk: int = 8192, grads_storage: torch.Tensor | None = None) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -69,7 +69,7 @@ class B200Engine:
         self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
-        self.flat = FlatParams(self.model, device=self.device)
+        self.flat = FlatParams(self.model, device=self.device, grads_storage=grads_storage)
         self.bf16_params = torch.zeros(self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.lm_head_chunk = int(lm_head_chunk)

@@ -67,13 +67,14 @@ class TorchBackend:
 
     def __init__(self, cfg: MPTConfig, device: torch.device | str = "cpu", precision: str = "amp_bf16",
                  seed: int | None = 17, frozen_layers: list[str] | None = None,
-                 unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None) -> None:
+                 unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
+                 grads_storage: torch.Tensor | None = None) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         self.precision = precision
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
-        self.flat = FlatParams(self.model, device=self.device)
+        self.flat = FlatParams(self.model, device=self.device, grads_storage=grads_storage)
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.collect_activation_stats = False
         self.activation_stats: dict[str, float] = {}
@@ -138,6 +139,17 @@ def build_backend(model_cfg: MPTConfig, device: torch.device, precision: str, ke
     if any(m == "b200" for m in modes) and device.type != "cuda":
         raise RuntimeError("kernels.*=b200 requires a CUDA (sm_100a) device")
     if want_engine:
+        unsupported = []
+        if precision not in ("amp_bf16", "amp_fp8"):
+            unsupported.append(f"precision={precision}")
+        if model_cfg.alibi or model_cfg.rope or model_cfg.qk_ln or model_cfg.clip_qkv or model_cfg.no_bias or not model_cfg.learned_pos_emb:
+            unsupported.append("attn/bias variant (alibi|rope|qk_ln|clip_qkv|no_bias)")
+        if kw.get("frozen_layers") or kw.get("unfrozen_layers"):
+            unsupported.append("frozen/unfrozen layers")
+        if unsupported:
+            print(f"[backend] {', '.join(unsupported)} not covered by the sm_100a engine -> stock PyTorch backend "
+                  "(explicit, logged; set kernels.*=torch to silence)", flush=True)
+            return TorchBackend(model_cfg, device=device, precision=precision, **kw)
         from photon_b200.models.engine import B200Engine
 
         return B200Engine(model_cfg, device=device, precision=precision, kernels=kernels, **kw)

@@ -147,7 +147,8 @@ class Trainer:
 
         be = backend or build_backend(self.model_cfg, self.device, precision, kernels, seed=seed,
                                       frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers,
-                                      unigram_log_probs=unigram_log_probs)
+                                      unigram_log_probs=unigram_log_probs,
+                                      grads_storage=getattr(grad_comm, "grads", None))
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
         opt = build_optimizer(optimizer_cfg, be.flat, use_kernel=use_kernel, bf16_shadow=shadow)

@@ -1,0 +1,136 @@
+"""Shard format, streaming dataset, shm codecs, checkpoint store, client load-path table — CPU."""
+import numpy as np
+import pytest
+import torch
+
+from photon_b200.checkpoint import CheckpointStore
+from photon_b200.clients.llm_config_functions import (client_set_data_config, get_train_config, set_client_load_path,
+                                                      set_dataset_default_params)
+from photon_b200.config import compose
+from photon_b200.data.shards import ShardReader, ShardWriter
+from photon_b200.data.streaming import Stream, StreamingTokenDataset, TokenLoader, build_text_loader
+from photon_b200.data.synthetic import SyntheticC4
+from photon_b200.shm import ModelParametersMetadata, close_all_shms, get_parameters_shm, set_parameters_shm, shm_exists
+from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file, parameters_checker
+from photon_b200.utils.flat import FlatLayout
+
+
+@pytest.mark.parametrize("comp", [None, "zlib"])
+def test_shard_roundtrip(tmp_path, comp):
+    rows = [np.arange(i, i + 16, dtype=np.int32) for i in range(37)]
+    with ShardWriter(tmp_path / "s", seq_len=16, shard_samples=10, compression=comp) as w:
+        w.write_many(rows)
+    r = ShardReader(tmp_path / "s", validate_hash=True)
+    assert len(r) == 37 and len(r.index["shards"]) == 4
+    assert all(np.array_equal(r[i], rows[i]) for i in (0, 9, 10, 36))
+    with pytest.raises(IndexError):
+        r[37]
+
+
+def test_synthetic_deterministic_and_c4_shaped():
+    a, b = SyntheticC4(seed=1, stream_id=2)[5], SyntheticC4(seed=1, stream_id=2)[5]
+    assert np.array_equal(a, b) and a.dtype == np.int32 and a.shape == (2048,) and a.max() < 50277
+    assert (a == 0).sum() >= 1 and not np.array_equal(a, SyntheticC4(seed=1, stream_id=3)[5])
+    assert abs(SyntheticC4().unigram_probabilities().sum() - 1.0) < 1e-9
+
+
+def test_streaming_partition_resume_and_mixing(tmp_path):
+    for c in range(2):
+        with ShardWriter(tmp_path / f"c{c}" / "train", seq_len=8, shard_samples=16) as w:
+            w.write_many([np.full(8, 100 * c + i, dtype=np.int32) for i in range(20)])
+    streams = [Stream(local=str(tmp_path / "c0"), split="train"), Stream(local=str(tmp_path / "c1"), split="train", choose=10)]
+    seen = []
+    for rank in range(2):
+        ds = StreamingTokenDataset(streams, seq_len=8, rank=rank, world_size=2, shuffle=True, allow_synthetic=False)
+        seen.append([int(x[0]) for x in ds])
+    assert len(seen[0]) == len(seen[1]) == 15 and not set(seen[0]) & set(seen[1])
+    ds = StreamingTokenDataset(streams, seq_len=8, shuffle=True)
+    it = iter(ds)
+    first = [int(next(it)[0]) for _ in range(7)]
+    sd = ds.state_dict()
+    rest = [int(x[0]) for x in it]
+    ds2 = StreamingTokenDataset(streams, seq_len=8, shuffle=True)
+    ds2.load_state_dict(sd)
+    assert [int(x[0]) for x in ds2] == rest and len(first) + len(rest) == 30
+    ld = TokenLoader(StreamingTokenDataset(streams, seq_len=8), batch_size=4, num_workers=1)
+    batches = list(ld)
+    assert len(batches) == len(ld) == 7 and batches[0]["input_ids"].shape == (4, 8) and batches[0]["input_ids"].dtype == torch.int64
+
+
+def test_client_stream_selection_from_config():
+    cfg = compose(["dataset.train.root_local=/data/x", "dataset/streams@dataset.val.streams=8_clients"])
+    t = get_train_config(cfg.llm_config, run_uuid="r")
+    evals = client_set_data_config(t, cid=10, split_eval=True)
+    st = t.train_loader.dataset.streams
+    assert list(st) == ["stream_2"] and st["stream_2"]["local"] == "/data/x/c8/en/client_2" and st["stream_2"]["split"] == "train"   # 10 % 8
+    assert sorted(evals) == [f"client_{i}" for i in range(8)]
+    t2 = get_train_config(cfg.llm_config)
+    client_set_data_config(t2, cid=None)
+    assert len(t2.train_loader.dataset.streams) == 8                                           # cid=None concatenates all
+    set_dataset_default_params(t2)
+    d = t2.train_loader.dataset
+    assert d.predownload == 8 * 256 and d.num_canonical_nodes == 64 and d.shuffle_block_size == 1 << 18
+    ld = build_text_loader({"dataset": {"streams": {"s": {"local": "synthetic://7"}}, "max_seq_len": 32}, "drop_last": True}, 2)
+    assert next(iter(ld))["input_ids"].shape == (2, 32)
+
+
+def test_shm_metadata_and_views():
+    arrays = [np.random.randn(5, 3).astype(np.float32), np.arange(7, dtype=np.float32)]
+    shm, meta = set_parameters_shm("pb200_ut_par", arrays)
+    m2 = ModelParametersMetadata.from_literal(meta.to_literal())
+    assert m2.same_layout(meta) and m2.total_num_bytes == meta.total_num_bytes
+    h, views = get_parameters_shm("pb200_ut_par", m2)
+    parameters_checker(arrays, views, expect_equal=True)
+    views[1][0] = 42.0                                                    # zero-copy: visible through the writer's handle
+    assert np.ndarray((7,), dtype=np.float32, buffer=shm.buf[meta.array_bounds[1][0]:meta.array_bounds[1][1]])[0] == 42.0
+    with pytest.raises(AssertionError):
+        parameters_checker(arrays, views, expect_equal=True)
+    del views
+    h.close(), shm.close()
+    close_all_shms("pb200_ut_par")
+    assert not shm_exists("pb200_ut_par")
+
+
+def test_npz_sorted_order_and_checkpoint_store(tmp_path):
+    lay = FlatLayout.build([("transformer.blocks.10.w", (2, 2)), ("transformer.blocks.2.w", (3,)), ("transformer.a", (1,))], align=4, total_multiple=4)
+    assert lay.names == ("transformer.a", "transformer.blocks.10.w", "transformer.blocks.2.w")
+    flat = torch.arange(lay.total, dtype=torch.float32)
+    p = dump_model_parameters_to_file(tmp_path / "m.npz", lay.to_ndarrays(flat))
+    with np.load(p) as z:
+        assert z.files == ["arr_0", "arr_1", "arr_2"] and z["arr_1"].shape == (2, 2)
+    assert [a.shape for a in load_model_parameters_from_file(p)] == [(1,), (2, 2), (3,)]
+    store = CheckpointStore(tmp_path, "checkpoints")
+    keys = ["current_server_parameters", "current_momentum_vector"]
+    for r in (0, 1, 2):
+        store.upload_server_checkpoint("runA", r, layout=lay, tensors={k: flat + r for k in keys}, state={"client_state": "{}", "server_steps_cumulative": r * 8})
+    (store.round_dir("runA", 3)).mkdir()                                    # incomplete round: ignored
+    assert store.obtain_sorted_rounds("runA", keys) == [0, 1, 2]
+    assert store.interpret_resume_round("runA", -1, keys) == 2 and store.interpret_resume_round("runA", None, keys) is None
+    with pytest.raises(FileNotFoundError):
+        store.interpret_resume_round("runA", 3, keys)
+    tensors, state = store.download_server_checkpoint("runA", 1, layout=lay, state_keys=keys)
+    assert all(torch.equal(lay.view(tensors[keys[1]], i), lay.view(flat + 1, i)) for i in range(3)) and state["server_steps_cumulative"] == 8
+    store.copy_old_checkpoints_to_new_run("runA", "runB", 2, state_keys=keys)
+    assert store.obtain_sorted_rounds("runB", keys) == [2]
+    store.cleanup_checkpoints("runA", per_round=True)
+    assert store.obtain_sorted_rounds("runA", keys) == [2]
+    store.cleanup_checkpoints("runA")
+    assert store.list_objects("runA") == []
+
+
+def test_set_client_load_path_decision_table(tmp_path):
+    def cfg():
+        return get_train_config({"save_folder": str(tmp_path / "ck"), "run_name": "r"})
+
+    t = cfg()
+    assert set_client_load_path(t, 3, 128) == (False, False) and t.save_folder.endswith("client_3")
+    d = tmp_path / "ck" / "client_3"
+    d.mkdir(parents=True)
+    (d / "ep0-ba64-rank0.pt").write_bytes(b"x")
+    t = cfg()
+    assert set_client_load_path(t, 3, 128) == (False, True) and t.load_path.endswith("ep0-ba64-rank{rank}.pt")   # resume mid-round
+    (d / "ep0-ba128-rank0.pt").write_bytes(b"x")
+    t = cfg()
+    assert set_client_load_path(t, 3, 128) == (True, True) and t.save_folder is None                             # round already done: skip
+    t = cfg()
+    assert set_client_load_path(t, 3, 32) == (False, False)                                                     # only newer checkpoints

@@ -1,0 +1,164 @@
+"""Timestamp / schedulers / optimizers (closed forms) / metrics / trainer checkpoints — CPU."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from photon_b200.metrics import build_metrics, unigram_log_probs, unigram_loss_sum
+from photon_b200.models.mpt import MPTConfig, MPTForCausalLM, shift_labels, trainable_named_parameters
+from photon_b200.train.optim import ADOPT, DecoupledAdamW, build_optimizer, clip_coefficient
+from photon_b200.train.schedulers import build_scheduler
+from photon_b200.train.timestamp import Time, Timestamp
+from photon_b200.utils.flat import FlatLayout, FlatParams
+
+
+def test_time_strings():
+    assert Time.parse("500ba").to_batches() == 500 and str(Time.parse("1e3ba")) == "1000ba"
+    assert Time.parse("1ep").to_batches(batches_per_epoch=7) == 7
+    assert Time.parse("1024sp").to_batches(samples_per_batch=256) == 4
+    assert Time.parse("0.5dur").to_batches(max_duration=Time.parse("4800ba")) == 2400
+    assert Time.parse("1e6tok").to_batches(tokens_per_batch=65536) == 15
+    with pytest.raises(ValueError):
+        Time.parse("12 parsecs")
+    ts = Timestamp()
+    ts.advance_batch(32, 65536)
+    sd = ts.state_dict()
+    t2 = Timestamp()
+    t2.load_state_dict(sd)
+    assert t2 == ts and t2.batch == 1 and t2.token == 65536
+
+
+def test_schedulers_closed_form():
+    f = build_scheduler({"schedulers": {"lr": {"name": "cosine_with_warmup", "t_warmup": "100ba", "alpha_f": 0.1, "t_max": "4800ba"}}})
+    assert f(0) == 0.0 and math.isclose(f(50), 0.5) and math.isclose(f(100), 1.0)
+    assert math.isclose(f(2450), 0.1 + 0.9 * 0.5, rel_tol=1e-6) and math.isclose(f(4800), 0.1) and math.isclose(f(9999), 0.1)
+    g = build_scheduler({"name": "constant_with_sqrt_cooldown_with_warmup", "t_warmup": "100ba", "t_max": "5120ba", "t_cooldown": "240ba"})
+    assert math.isclose(g(100), 1.0) and math.isclose(g(4880), 1.0) and math.isclose(g(4880 + 60), 1 - math.sqrt(0.25)) and math.isclose(g(5120), 0.0, abs_tol=1e-9)
+    h = build_scheduler({"name": "linear_decay_with_warmup", "t_warmup": "0ba", "t_max": "10ba", "alpha_f": 0.0})
+    assert math.isclose(h(5), 0.5)
+
+
+def _flat(n=64):
+    torch.manual_seed(0)
+    m = nn.Linear(n, 1, bias=False)
+    return FlatParams(m)
+
+
+def test_adopt_closed_form():
+    fp = _flat()
+    opt = ADOPT(fp, lr=0.1, betas=(0.9, 0.99), eps=1e-6, use_kernel=False)
+    n = fp.layout.numels[0]
+    p0 = fp.params.clone()
+    g1, g2 = torch.full((fp.layout.total,), 2.0), torch.full((fp.layout.total,), -1.0)
+    fp.grads.copy_(g1)
+    opt.step()
+    assert torch.equal(fp.params, p0) and torch.allclose(opt.exp_avg_sq[:n], torch.full((n,), 4.0))    # step 0 only seeds v
+    fp.grads.copy_(g2)
+    opt.step()
+    ng = max(-1.0 / 2.0, -1.0)          # g / sqrt(v) = -0.5, clip = 1**0.25 = 1
+    m = 0.1 * ng
+    assert torch.allclose(fp.params[:n], p0[:n] - 0.1 * m, atol=1e-7)
+    assert torch.allclose(opt.exp_avg_sq[:n], torch.full((n,), 0.99 * 4 + 0.01 * 1.0))
+
+
+def test_decoupled_adamw_matches_torch_adamw_without_decay():
+    fp = _flat()
+    ref = torch.nn.Parameter(fp.params[: fp.layout.numels[0]].clone())
+    topt = torch.optim.AdamW([ref], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    opt = DecoupledAdamW(fp, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, use_kernel=False)
+    for i in range(5):
+        g = torch.randn(fp.layout.total)
+        fp.grads.copy_(g)
+        ref.grad = g[: ref.numel()].clone()
+        opt.step()
+        topt.step()
+    assert torch.allclose(fp.params[: ref.numel()], ref.detach(), atol=1e-6)
+    o2 = build_optimizer({"name": "decoupled_adamw", "lr": 1.0, "weight_decay": 0.1}, _flat(), use_kernel=False)
+    p = o2.flat.params.clone()
+    o2.flat.grads.zero_()
+    o2.step(0.5)                                          # lr factor 0.5 -> decay 1 - 0.5*0.1
+    assert torch.allclose(o2.flat.params, p * 0.95, atol=1e-6)
+    assert math.isclose(float(clip_coefficient(torch.tensor(4.0), 1.0)), 1.0 / (4.0 + 1e-6), rel_tol=1e-6)
+
+
+def test_flat_layout_sorted_and_roundtrip():
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=11, max_seq_len=16, vocab_size=64, attn_impl="torch")
+    model = MPTForCausalLM(cfg, seed=1)
+    names = [n for n, _ in trainable_named_parameters(model)]
+    assert names == sorted(names) and names.index("transformer.blocks.10.attn.Wqkv.bias") < names.index("transformer.blocks.2.attn.Wqkv.bias")
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    fp = FlatParams(model)
+    assert all(torch.equal(before[n], p) for n, p in model.named_parameters())       # re-pointing keeps values
+    assert all(o % 256 == 0 for o in fp.layout.offsets) and fp.layout.n_params == cfg.num_params()
+    arrays = fp.to_ndarrays()
+    fp.params.zero_()
+    fp.load_ndarrays(arrays)
+    assert all(torch.equal(before[n], p) for n, p in model.named_parameters())
+    assert MPTConfig().num_params() == 125_311_488
+    with pytest.raises(ValueError):
+        fp.load_ndarrays(arrays[:-1])
+
+
+def test_mpt_loss_shift_and_tied_head():
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=1, max_seq_len=8, vocab_size=50, attn_impl="torch")
+    model = MPTForCausalLM(cfg, seed=0)
+    ids = torch.randint(0, 50, (2, 8))
+    t = shift_labels(ids)
+    assert torch.equal(t[:, :-1], ids[:, 1:]) and (t[:, -1] == -100).all()
+    loss, n = model.loss(ids)
+    assert int(n) == 2 * 7 and abs(float(loss) - math.log(50)) < 1.5
+    logits = model(ids)
+    assert logits.shape == (2, 8, 50)
+    # causal: changing a future token must not change past logits
+    ids2 = ids.clone()
+    ids2[:, -1] = (ids2[:, -1] + 1) % 50
+    assert torch.allclose(model(ids2)[:, :-1], logits[:, :-1], atol=1e-5)
+    for variant in (dict(alibi=True), dict(rope=True)):
+        m2 = MPTForCausalLM(MPTConfig(d_model=32, n_heads=2, n_layers=1, max_seq_len=8, vocab_size=50, attn_impl="torch", learned_pos_emb=False, **variant), seed=0)
+        assert torch.isfinite(m2.loss(ids)[0])
+
+
+def test_metrics_and_unigram():
+    ms = build_metrics(True)
+    lp = unigram_log_probs({"1": 90, "2": 10}, 4)
+    tg = torch.tensor([1, 1, 2, -100])
+    uni = float(unigram_loss_sum(tg, lp))
+    for m in ms.values():
+        m.update({"loss_sum": 6.0, "n_tokens": 3.0, "n_correct": 2.0, "unigram_loss_sum": uni})
+    assert math.isclose(ms["LanguageCrossEntropy"].compute(), 2.0) and math.isclose(ms["LanguagePerplexity"].compute(), math.exp(2.0))
+    assert math.isclose(ms["TokenAccuracy"].compute(), 2 / 3)
+    assert math.isclose(ms["UnigramNormalizedLanguageCrossEntropy"].compute(), 2.0 - uni / 3)
+    assert math.isclose(ms["PureUnigramPerplexity"].compute(), math.exp(uni / 3))
+
+
+def test_trainer_checkpoint_resume_and_ignore_keys(tmp_path):
+    from photon_b200.data.streaming import Stream, StreamingTokenDataset, TokenLoader
+    from photon_b200.train.trainer import Trainer
+
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=1, max_seq_len=16, vocab_size=50277, attn_impl="torch")
+
+    def mk():
+        ds = StreamingTokenDataset([Stream(local="synthetic://3")], seq_len=16, synthetic_samples=64)
+        return Trainer(cfg, optimizer_cfg=dict(name="adopt", lr=1e-2, betas=[0.9, 0.99], eps=1e-6), train_loader=TokenLoader(ds, 4),
+                       scheduler_cfg=dict(name="cosine_with_warmup", t_warmup="2ba", t_max="20ba", alpha_f=0.1),
+                       global_train_batch_size=4, device_train_microbatch_size=2, precision="fp32", max_duration="20ba", grad_clip_norm=1.0,
+                       device="cpu", save_folder=str(tmp_path), save_interval="3ba", save_num_checkpoints_to_keep=1, seed=5)
+
+    a = mk()
+    a.fit("6ba")
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files == ["ep0-ba6-rank0.pt", "latest-rank0.pt"]                 # keep=1 removed ba3
+    a.fit("2ba")
+    b = mk()
+    b.load_checkpoint(tmp_path / "latest-rank0.pt")
+    assert b.state.timestamp.batch == 6 and b.state.optimizer.step_count == 6
+    b.fit("2ba")                                                            # same data position + state => same weights
+    assert torch.allclose(a.state.flat.params, b.state.flat.params, atol=1e-6)
+    c = mk()
+    c.load_checkpoint(tmp_path / "latest-rank0.pt", ignore_keys=["*optim*", "*timestamp*"])
+    assert c.state.optimizer.step_count == 0 and c.state.timestamp.batch == 0
+    saved = torch.load(tmp_path / "latest-rank0.pt", weights_only=False)["state"]["model"]
+    lay = c.state.flat.layout
+    assert all(torch.equal(lay.view(c.state.flat.params, n), saved[n]) for n in lay.names)
