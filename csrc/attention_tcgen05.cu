@@ -155,28 +155,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const bool diag = causal && (j == qt);
-      // pass 1: row max
+      // S row (128 fp32) is read from TMEM ONCE: four 32-column loads in flight, one wait
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld_32x32(tl + C::COL_S, r0);
+      tmem_ld_32x32(tl + C::COL_S + 32, r1);
+      tmem_ld_32x32(tl + C::COL_S + 64, r2);
+      tmem_ld_32x32(tl + C::COL_S + 96, r3);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tl + C::COL_S + c * 32, r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float v = __uint_as_float(r[t]);
-          if (!diag || (c * 32 + t) <= row) mx = fmaxf(mx, v);
+      for (int t = 0; t < 32; ++t) {
+        const float v0 = __uint_as_float(r0[t]), v1 = __uint_as_float(r1[t]), v2 = __uint_as_float(r2[t]), v3 = __uint_as_float(r3[t]);
+        if (!diag) {
+          mx = fmaxf(fmaxf(mx, fmaxf(v0, v1)), fmaxf(v2, v3));
+        } else {
+          if (t <= row) mx = fmaxf(mx, v0);
+          if (32 + t <= row) mx = fmaxf(mx, v1);
+          if (64 + t <= row) mx = fmaxf(mx, v2);
+          if (96 + t <= row) mx = fmaxf(mx, v3);
         }
       }
-      const float m_new = fmaxf(m, mx * sc);
-      const float alpha = exp2f(m - m_new);  // m = -inf on the first tile -> 0
-      // pass 2: p = exp2(s*sc - m_new), packed bf16 into the P columns
+      // lazy rescale: keep the old reference max unless it grew by more than 2^8 (bounded overflow, exact result)
+      const float m_cand = fmaxf(m, mx * sc);
+      const bool bump = (m_cand - m) > 8.0f;   // also true on the first tile (m = -inf)
+      const float m_new = bump ? m_cand : m;
+      const float alpha = bump ? exp2f(m - m_new) : 1.0f;
       float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tl + C::COL_S + c * 32, r);
-        tmem_ld_wait();
+      auto emit = [&](const uint32_t (&r)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
@@ -189,21 +194,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
           rs += p0 + p1;
           pk[t >> 1] = pack_bf16(p0, p1);
         }
-        // 16 packed columns per 32 source columns
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
                 tl + C::COL_P + c * 16),
             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
             "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
             : "memory");
-      }
+      };
+      emit(r0, 0);
+      emit(r1, 1);
+      emit(r2, 2);
+      emit(r3, 3);
       l = l * alpha + rs;
       m = m_new;
-      // rescale the running O (previous P V must have retired); skipped when no row of the warp moved its max
+      // rescale the running O only when some row of this warp actually moved its reference max
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffff, alpha != 1.0f)) {
+        if (__any_sync(0xffffffff, bump)) {
 #pragma unroll 1
           for (int c = 0; c < DH / 32; ++c) {
             uint32_t r[32];

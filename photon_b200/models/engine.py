@@ -51,7 +51,7 @@ class B200Engine:
     def __init__(self, cfg: MPTConfig, device: torch.device | str = "cuda", precision: str = "amp_bf16",
                  kernels: dict[str, Any] | None = None, seed: int | None = 17, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
-                 lm_head_chunk: int = 8192, grads_storage: torch.Tensor | None = None) -> None:
+                 lm_head_chunk: int = 18944, grads_storage: torch.Tensor | None = None) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":

@@ -1,0 +1,47 @@
+import json
+
+import numpy as np
+import yaml
+
+from photon_b200.data.shards import ShardReader
+from photon_b200.dataset.constants import DATASETS_CONSTANTS
+from photon_b200.dataset.convert_dataset_hf import main as convert_main
+from photon_b200.dataset.samples_generators import generate_samples_from_shards
+from photon_b200.dataset.stream_partitioner import partition_stream_list, partition_streams
+from photon_b200.dataset.utils import ByteTokenizer, concat_tokens
+
+
+def test_constants_table():
+    assert len(DATASETS_CONSTANTS) == 13 and DATASETS_CONSTANTS["c4_en"].splits["train_small"].truncated_samples == 100_000
+    assert DATASETS_CONSTANTS["c4_it"].splits["val_xxsmall"].truncated_samples == 100
+
+
+def test_concat_tokens_packs_with_eos():
+    tok = ByteTokenizer()
+    samples = list(concat_tokens(["ab", "cde", "f" * 10], tok, max_length=8))
+    flat = np.concatenate(samples)
+    assert all(s.shape == (8,) and s.dtype == np.int32 for s in samples)
+    assert flat[2] == 0 and flat[6] == 0                     # eos after "ab" and after "cde"
+
+
+def test_converter_contiguous_partitions_and_unigram(tmp_path):
+    out = convert_main(["--source", "synthetic://200", "--out_root", str(tmp_path), "--num_clients", "4", "--concat_tokens", "32",
+                        "--splits", "train_small", "--compression", "none"])
+    counts = out["train_small"]
+    assert len(counts) == 4 and max(counts) - min(counts) <= 3
+    r = ShardReader(tmp_path / "c4" / "en" / "client_1" / "train_small")
+    assert len(r) == counts[1] and r[0].shape == (32,)
+    freq = json.loads((tmp_path / "c4" / "en" / "client_1" / "train_small" / "1_gram.json").read_text())
+    assert sum(freq.values()) == counts[1] * 32
+    assert (tmp_path / "tokenizer" / "tokenizer_config.json").exists()
+    re64 = list(generate_samples_from_shards(tmp_path / "c4" / "en" / "client_1" / "train_small", new_seq_len=64))
+    assert len(re64) == counts[1] // 2 and re64[0]["tokens"].shape == (64,)
+
+
+def test_stream_partitioner(tmp_path):
+    entries = [{"client_streams": {f"stream_{i}": {"local": f"c8/en/client_{i}"}}} for i in range(8)]
+    two = partition_stream_list(entries, 2)
+    assert [len(e["client_streams"]) for e in two] == [4, 4] and two[1]["client_streams"]["stream_0"]["local"] == "c8/en/client_4"
+    (tmp_path / "in.yaml").write_text(yaml.safe_dump(entries))
+    partition_streams(tmp_path / "in.yaml", tmp_path / "out.yaml", 4)
+    assert len(yaml.safe_load((tmp_path / "out.yaml").read_text())) == 4
