@@ -40,14 +40,16 @@ template <int DH>
 struct FwdCfg {
   static constexpr int CH = DH / 64;              // 64-column swizzle chunks per tile
   static constexpr int TILE = 128 * 128 * CH;     // bytes of one [128 x DH] bf16 tile
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (DH == 64) ? 4 : 2;
   static constexpr int SMEM = TILE * (1 + 2 * STAGES) + 256 + 1024;
-  static constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
-  static constexpr int TMEM_COLS = (DH == 64) ? 256 : 512;
+  // two S buffers (128 fp32 columns each); P_j (packed bf16, 64 columns) aliases the head of S_j once the row
+  // threads hold S_j in registers; O after them
+  static constexpr int COL_S = 0, COL_O = 256;
+  static constexpr int TMEM_COLS = 512;
 };
 
 template <int DH>
-__global__ void __launch_bounds__(192, (DH == 64) ? 2 : 1)
+__global__ void __launch_bounds__(192, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
                 float scale, int causal) {
   using C = FwdCfg<DH>;
@@ -58,13 +60,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   uint8_t* sV = sK + C::STAGES * C::TILE;       // [STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::STAGES * C::TILE);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;                  // [2]
-  uint64_t* v_full = bars + 3;                  // [2]
-  uint64_t* kv_empty = bars + 5;                // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_ready = bars + 8;
-  uint64_t* o_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;                  // [STAGES]
+  uint64_t* v_full = bars + 5;                  // [STAGES]
+  uint64_t* kv_empty = bars + 9;                // [STAGES]
+  uint64_t* s_full = bars + 13;                 // [2]
+  uint64_t* p_ready = bars + 15;                // [2]
+  uint64_t* o_done = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -78,13 +80,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+    }
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -101,8 +105,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
 #pragma unroll
       for (int c = 0; c < C::CH; ++c) tma_load_2d(sQ + c * 16384, &tmQKV, q_full, h * DH + c * 64, row0);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % C::STAGES;
+        mbar_wait(&kv_empty[st], ((j / C::STAGES) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], C::TILE);
 #pragma unroll
         for (int c = 0; c < C::CH; ++c)
@@ -120,26 +124,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH, 0, 1);
       const uint32_t q_base = smem_u32(sQ);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const uint32_t k_base = smem_u32(sK + st * C::TILE), v_base = smem_u32(sV + st * C::TILE);
-        mbar_wait(&k_full[st], ph);
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer (j & 1)
+        const int st = j % C::STAGES;
+        const uint32_t k_base = smem_u32(sK + st * C::TILE);
+        mbar_wait(&k_full[st], (j / C::STAGES) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
           const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          tc_mma_f16_ss(tmem + C::COL_S, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024),
-                        idesc_s, kk != 0);
+          tc_mma_f16_ss(tmem + C::COL_S + (j & 1) * 128, make_smem_desc_sw128(q_base + off, 16, 1024),
+                        make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0);
         }
-        tc_commit(s_full);
-        mbar_wait(p_ready, j & 1);
-        mbar_wait(&v_full[st], ph);
+        tc_commit(&s_full[j & 1]);
+      };
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        // S_{j+1} is issued BEFORE waiting for softmax_j: it runs on the tensor pipe while the row threads work.
+        // Buffer (j+1)&1 is free: softmax_{j-1} finished reading S_{j-1} (p_ready) and P_{j-1} is consumed by
+        // P V_{j-1}, which was issued earlier on the in-order tensor pipe.
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int st = j % C::STAGES;
+        const uint32_t v_base = smem_u32(sV + st * C::TILE);
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        mbar_wait(&v_full[st], (j / C::STAGES) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          tc_mma_f16_ts(tmem + C::COL_O, tmem + C::COL_P + kk * 8, make_smem_desc_sw128(v_base + kk * 2048, 16384, 1024), idesc_o,
-                        (j | kk) != 0);
+          tc_mma_f16_ts(tmem + C::COL_O, tmem + C::COL_S + (j & 1) * 128 + kk * 8, make_smem_desc_sw128(v_base + kk * 2048, 16384, 1024),
+                        idesc_o, (j | kk) != 0);
         }
         tc_commit(&kv_empty[st]);
         tc_commit(o_done);
@@ -152,15 +164,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     const float sc = scale * LOG2E;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const bool diag = causal && (j == qt);
+      const uint32_t ts = tl + C::COL_S + (j & 1) * 128;
       // S row (128 fp32) is read from TMEM ONCE: four 32-column loads in flight, one wait
       uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld_32x32(tl + C::COL_S, r0);
-      tmem_ld_32x32(tl + C::COL_S + 32, r1);
-      tmem_ld_32x32(tl + C::COL_S + 64, r2);
-      tmem_ld_32x32(tl + C::COL_S + 96, r3);
+      tmem_ld_32x32(ts, r0);
+      tmem_ld_32x32(ts + 32, r1);
+      tmem_ld_32x32(ts + 64, r2);
+      tmem_ld_32x32(ts + 96, r3);
       tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
@@ -196,7 +209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-                tl + C::COL_P + c * 16),
+                ts + c * 16),
             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
             "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
             : "memory");
@@ -225,7 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[j & 1]);
     }
     // ---- epilogue: O / l -> bf16 -> global; lse
     mbar_wait(o_done, (n_kv - 1) & 1);
@@ -380,12 +393,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
       const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
       mbar_wait(kv_full, 0);
-      for (int t = 0; t < n_it; ++t) {
+      auto issue_sdp = [&](int t) {  // S_t = Q_t K^T ; dP_t = dO_t V^T  (contraction over d_head = 64: 4 k-steps in one swizzle atom)
         const int st = t & 1;
         const uint32_t q_base = smem_u32(sQ + st * C::TILE), do_base = smem_u32(sDO + st * C::TILE);
         mbar_wait(&qd_full[st], (t >> 1) & 1);
         tc_fence_after();
-        // S = Q K^T ; dP = dO V^T   (contraction over d_head = 64 -> 4 k-steps inside one swizzle atom)
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
           tc_mma_f16_ss(tmem + C::COL_S, make_smem_desc_sw128(q_base + kk * 32, 16, 1024), make_smem_desc_sw128(k_base + kk * 32, 16, 1024),
@@ -395,7 +407,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tc_mma_f16_ss(tmem + C::COL_DP, make_smem_desc_sw128(do_base + kk * 32, 16, 1024), make_smem_desc_sw128(v_base + kk * 32, 16, 1024),
                         idesc_kk, kk != 0);
         tc_commit(sdp_full);
-        mbar_wait(pds_ready, t & 1);
+      };
+      issue_sdp(0);
+      for (int t = 0; t < n_it; ++t) {
+        const int st = t & 1;
+        const uint32_t q_base = smem_u32(sQ + st * C::TILE), do_base = smem_u32(sDO + st * C::TILE);
+        mbar_wait(pds_ready, t & 1);   // row threads consumed S_t / dP_t and staged P_t / dS_t in smem
+        // next tile's S / dP go first: the row threads start on them while dV / dK / dQ of this tile run
+        if (t + 1 < n_it) issue_sdp(t + 1);
         if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
         tc_fence_after();
         // contraction over the 128 query rows of this tile: 8 k-steps, 16 rows (2048 B) each
@@ -430,49 +449,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const float sc = scale * LOG2E;
     const uint32_t swz = row & 7;
     const bool issuer = (threadIdx.x == 0);
-    for (int t = 0; t < n_it; ++t) {
-      const int it = i0 + t;
-      const long long grow = (long long)(b * H + h) * S + it * 128 + row;
-      const float lse2 = lse[grow] * LOG2E;
-      const float dl = delta[grow];
-      mbar_wait(sdp_full, t & 1);
-      tc_fence_after();
-      if (t > 0) mbar_wait(mma_done, (t - 1) & 1);  // previous tile's MMAs no longer read sP / sDS
-      const bool diag = causal && (it == jt);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
-        tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
-        tmem_ld_wait();
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
-          float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
-          if (diag) {
-            if (c * 32 + e > row) p0 = 0.f;
-            if (c * 32 + e + 1 > row) p1 = 0.f;
-          }
-          const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
-          const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
-          pk[e >> 1] = pack_bf16(p0, p1);
-          dk[e >> 1] = pack_bf16(s0, s1);
-        }
-        // columns [32c, 32c+32) of row `row`: chunk = c/2, 16-byte groups (c&1)*4 .. +3 inside the 128-byte swizzled row
-        uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
-        uint8_t* drow = sDS + (c >> 1) * 16384 + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t slot = (uint32_t((c & 1) * 4 + g) ^ swz) << 4;
-          *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(pds_ready);
-      // drain this tile's dQ partial: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
+    auto drain_dq = [&](int t) {  // dQ partial of tile t: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
       mbar_wait(dq_full, t & 1);
       tc_fence_after();
       if (issuer) tma_wait_read<0>();
@@ -492,11 +469,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (issuer) {
-        tma_reduce_add_2d(&tmDQ, sDQ, h * DH, b * S + it * 128);
-        tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * DH + 32, b * S + it * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ, h * DH, b * S + (i0 + t) * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * DH + 32, b * S + (i0 + t) * 128);
         tma_commit();
       }
+    };
+    for (int t = 0; t < n_it; ++t) {
+      const int it = i0 + t;
+      const long long grow = (long long)(b * H + h) * S + it * 128 + row;
+      const float lse2 = lse[grow] * LOG2E;
+      const float dl = delta[grow];
+      mbar_wait(sdp_full, t & 1);
+      tc_fence_after();
+      const bool diag = causal && (it == jt);
+      uint32_t pk[64], dk[64];  // packed bf16 P and dS of this row (128 columns each), kept in registers
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
+        tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
+          float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+          if (diag) {
+            if (c * 32 + e > row) p0 = 0.f;
+            if (c * 32 + e + 1 > row) p1 = 0.f;
+          }
+          const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
+          const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
+          pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
+          dk[c * 16 + (e >> 1)] = pack_bf16(s0, s1);
+        }
+      }
+      // S_t / dP_t are consumed (the MMA warp may overwrite them); the smem staging is reusable once the
+      // previous tile's dV / dK / dQ MMAs retired
+      if (t > 0) mbar_wait(mma_done, (t - 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // columns [32c, 32c+32) of row `row`: chunk = c/2, 16-byte groups (c&1)*4 .. +3 inside the 128-byte swizzled row
+        uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
+        uint8_t* drow = sDS + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t slot = (uint32_t((c & 1) * 4 + g) ^ swz) << 4;
+          *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]);
+          *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[c * 16 + 4 * g], dk[c * 16 + 4 * g + 1], dk[c * 16 + 4 * g + 2], dk[c * 16 + 4 * g + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+      if (t > 0) drain_dq(t - 1);   // overlaps with S_{t+1}/dP_{t+1} and dV/dK/dQ_t on the tensor pipe
     }
+    drain_dq(n_it - 1);
     // ---- epilogue: dK (x scale), dV -> bf16 -> dqkv
     mbar_wait(final_done, 0);
     tc_fence_after();

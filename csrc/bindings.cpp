@@ -48,7 +48,7 @@ inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value(
 // ---------------------------------------------------------------------------------- GEMM
 // a: [M,K] (a_mn=0) or [K,M] (a_mn=1);  b: [N,K] (b_mn=0) or [K,N] (b_mn=1);  d: [M,N]
 void gemm(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int epi, const c10::optional<Tensor>& bias,
-          const c10::optional<Tensor>& aux, c10::optional<Tensor> d2, bool accumulate, double alpha) {
+          const c10::optional<Tensor>& aux, c10::optional<Tensor> d2, bool accumulate, double alpha, int cluster) {
   check_bf16(a, "a");
   check_bf16(b, "b");
   check_cuda(d, "d");
@@ -85,6 +85,7 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int e
     g.D2 = d2->data_ptr(), g.ldd2 = d2->stride(0);
   }
   g.num_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  g.cluster = cluster;
   pb::gemm_bf16_launch(g, stream_of(a));
   g_launches += 1;
 }
@@ -327,7 +328,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "photon_b200 sm_100a kernels (tcgen05/TMEM/TMA GEMM + attention, fused norm/loss/optimizer, NVLink collectives)";
   m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("d"), py::arg("a_mn") = 0, py::arg("b_mn") = 0, py::arg("epi") = 0,
         py::arg("bias") = py::none(), py::arg("aux") = py::none(), py::arg("d2") = py::none(), py::arg("accumulate") = false,
-        py::arg("alpha") = 1.0);
+        py::arg("alpha") = 1.0, py::arg("cluster") = 0);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
   m.def("embed_fwd", &embed_fwd);

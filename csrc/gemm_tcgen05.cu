@@ -44,7 +44,10 @@ struct Params {
   int splits, kb_per_split;     // split-K (EPI_F32 + accumulate): work item = (tile, k-range)
 };
 
-template <int A_MN, int B_MN, int EPI>
+// CL = thread-block-cluster size along M (1 or 2). With CL = 2 the two CTAs of a cluster work on M-adjacent tiles
+// of the same N block: each loads HALF of the shared B tile and TMA-multicasts it into both CTAs' smem, cutting the
+// L2->SM operand traffic per CTA from 48 KiB to 32 KiB per k-block (the 1-CTA kernel is L2-bandwidth bound).
+template <int A_MN, int B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const Params p) {
@@ -68,10 +71,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     prefetch_tmap(&tmD);
     if (EPI == EPI_GELU_DUAL) prefetch_tmap(&tmD2);
   }
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);  // CL > 1: a stage is reusable once BOTH CTAs' MMAs consumed it (peer multicasts into it)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -82,28 +86,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // work decomposition: units of CL M-adjacent tiles; every CTA of a cluster walks the same unit sequence
+  const int tiles_mu = (p.tiles_m + CL - 1) / CL;
+  const int num_tiles = tiles_mu * p.tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_work = num_tiles * p.splits;
+  const int w0 = blockIdx.x / CL, wstride = gridDim.x / CL;
 
   if (warp == 0) {
     // ======================= TMA producer (one thread) =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = w0; w < num_work; w += wstride) {
         const int tile = w % num_tiles, sp = w / num_tiles;
-        const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
-        const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
+        const int m_blk = (p.m_fastest ? tile % tiles_mu : tile / p.tiles_n) * CL + crank;
+        const int n_blk = p.m_fastest ? tile / tiles_mu : tile % p.tiles_n;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE;
           uint8_t* b_dst = sB + stage * B_STAGE;
+          if (CL > 1) {
+            // A: own tile; B: my half of the shared tile, multicast to both CTAs
+            if (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
+            } else {
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int c = crank * (BN / 128) + j;
+                tma_load_2d_mc(b_dst + c * (BK * 128), &tmB, &full[stage], n_blk * BN + c * 64, kb * BK, 0x3);
+              }
+            } else {
+              tma_load_2d_mc(b_dst + crank * (B_STAGE / 2), &tmB, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2), 0x3);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
@@ -133,7 +165,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = w0; w < num_work; w += wstride) {
         const int sp = w / num_tiles;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -152,7 +184,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : make_smem_desc_sw128(b_base + k * (UK * 2), 16, 1024);
             tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (CL > 1) tc_commit_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs
+          else tc_commit(&empty[stage]);                 // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -174,10 +207,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t swz = (row_in_tile & 7);
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = w0; w < num_work; w += wstride) {
       const int tile = w % num_tiles;
-      const int m_blk = p.m_fastest ? tile % p.tiles_m : tile / p.tiles_n;
-      const int n_blk = p.m_fastest ? tile / p.tiles_m : tile % p.tiles_n;
+      const int m_blk = (p.m_fastest ? tile % tiles_mu : tile / p.tiles_n) * CL + crank;
+      const int n_blk = p.m_fastest ? tile / tiles_mu : tile % p.tiles_n;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)m_blk * BM + row_in_tile;
@@ -289,6 +322,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while the peer may still multicast / arrive into this CTA
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -330,19 +364,37 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint6
   return m;
 }
 
-template <int A_MN, int B_MN, int EPI>
-static void launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
-                        const Params& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+template <int A_MN, int B_MN, int EPI, int CL>
+static void launch_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
+                      const Params& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm smem attr: ") + cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, td, td2, p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
+}
+
+template <int A_MN, int B_MN, int EPI>
+static void launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
+                        const Params& p, int grid, int cluster, cudaStream_t stream) {
+  if (cluster == 2) launch_cl<A_MN, B_MN, EPI, 2>(ta, tb, td, td2, p, grid, stream);
+  else launch_cl<A_MN, B_MN, EPI, 1>(ta, tb, td, td2, p, grid, stream);
 }
 
 void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
@@ -352,8 +404,10 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   // A: K-major -> dims {K, M}, box {64, 128};  MN-major -> dims {M, K}, box {64(M), 64(K)}
   CUtensorMap ta = g.a_mn ? make_tmap_2d(g.A, 2, false, g.M, g.K, g.lda * 2, 64, BK)
                           : make_tmap_2d(g.A, 2, false, g.K, g.M, g.lda * 2, BK, BM);
+  // 2-CTA clusters (B tile multicast: each CTA fetches half of the N rows) whenever there are >= 2 M tiles
+  const int cluster = (g.cluster > 0 ? g.cluster : ((g.M + BM - 1) / BM >= 2 ? 2 : 1));
   CUtensorMap tb = g.b_mn ? make_tmap_2d(g.B, 2, false, g.N, g.K, g.ldb * 2, 64, BK)
-                          : make_tmap_2d(g.B, 2, false, g.K, g.N, g.ldb * 2, BK, BN);
+                          : make_tmap_2d(g.B, 2, false, g.K, g.N, g.ldb * 2, BK, BN / cluster);
   CUtensorMap td = f32 ? make_tmap_2d(g.D, 4, true, g.N, g.M, g.ldd * 4, 32, BM)
                        : make_tmap_2d(g.D, 2, false, g.N, g.M, g.ldd * 2, 64, BM);
   CUtensorMap td2 = td;
@@ -389,12 +443,12 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   }
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty tails
-  const int work = tiles * p.splits;
-  int grid = work < sms ? work : sms;
+  const int work_units = ((p.tiles_m + cluster - 1) / cluster) * p.tiles_n * p.splits;
+  int grid = work_units * cluster < sms ? work_units * cluster : (sms / cluster) * cluster;
 
 #define PB_CASE(AM, BMJ, E)                                            \
   if (g.a_mn == AM && g.b_mn == BMJ && g.epi == E) {                   \
-    launch_inst<AM, BMJ, E>(ta, tb, td, td2, p, grid, stream);         \
+    launch_inst<AM, BMJ, E>(ta, tb, td, td2, p, grid, cluster, stream); \
     return;                                                            \
   }
   PB_CASE(0, 0, EPI_BF16)

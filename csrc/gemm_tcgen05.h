@@ -28,6 +28,7 @@ struct GemmArgs {
   int accumulate = 0;
   float alpha = 1.0f;
   int num_sms = 0;
+  int cluster = 0;   // 0 = auto (2-CTA clusters with B multicast when >= 2 M tiles), 1 or 2 to force
 };
 
 void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream);

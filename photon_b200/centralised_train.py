@@ -60,15 +60,11 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
             use_nvl_allreduce = device.type == "cuda" and not all(
                 (cfg.get("kernels") or {}).get(k, "auto") == "torch" for k in ("gemm", "optimizer"))
         if use_nvl_allreduce:
-            from photon_b200.models.mpt import MPTConfig
             from photon_b200.parallel.ddp import NvlGradComm
-            from photon_b200.utils.flat import FlatLayout
-            from photon_b200.models.mpt import MPTForCausalLM
+            from photon_b200.utils.flat import layout_for_model_cfg
 
-            mc = MPTConfig.from_model_cfg(dict(cfg["llm_config"]["model"]))
-            with torch.device("meta"):
-                shapes = [(n, p.shape) for n, p in MPTForCausalLM(mc, device="meta", init=False).named_parameters()]
-            grad_comm = NvlGradComm(FlatLayout.build(shapes).total, rank=rank, world_size=world_size, device=device)
+            total = layout_for_model_cfg(cfg["llm_config"]["model"], cc.frozen_layers, cc.unfrozen_layers).total
+            grad_comm = NvlGradComm(total, rank=rank, world_size=world_size, device=device)
         else:
             from photon_b200.parallel.ddp import NcclGradComm
 

@@ -52,11 +52,11 @@ EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          epi: int = EPI_BF16, bias: torch.Tensor | None = None, aux: torch.Tensor | None = None,
-         out2: torch.Tensor | None = None, accumulate: bool = False, alpha: float = 1.0) -> torch.Tensor:
+         out2: torch.Tensor | None = None, accumulate: bool = False, alpha: float = 1.0, cluster: int = 0) -> torch.Tensor:
     """``out[M,N] = epilogue(alpha * A @ B^T)`` on tcgen05 tensor cores.
 
     ``a``: ``[M,K]`` (K-major) or ``[K,M]`` when ``a_mn``; ``b``: ``[N,K]`` or ``[K,N]`` when ``b_mn``."""
-    ext().gemm(a, b, out, int(a_mn), int(b_mn), int(epi), bias, aux, out2, bool(accumulate), float(alpha))
+    ext().gemm(a, b, out, int(a_mn), int(b_mn), int(epi), bias, aux, out2, bool(accumulate), float(alpha), int(cluster))
     return out
 
 

@@ -135,3 +135,15 @@ class FlatParams:
     def load_ndarrays(self, arrays: Sequence[np.ndarray]) -> None:
         with torch.no_grad():
             self.layout.from_ndarrays(self.params, arrays)
+
+
+def layout_for_model_cfg(model_cfg: "object", frozen: list[str] | None = None, unfrozen: list[str] | None = None) -> FlatLayout:
+    """Flat layout of an MPT config WITHOUT materialising weights (meta device) — lets callers size
+    symmetric-memory planes before the Trainer exists."""
+    from photon_b200.models.mpt import MPTConfig, MPTForCausalLM
+
+    mc = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(dict(model_cfg))
+    model = MPTForCausalLM(mc, device="meta", init=False)
+    names = [(n, tuple(p.shape)) for n, p in model.named_parameters()
+             if not (frozen and n in frozen) and not (unfrozen and n not in unfrozen)]
+    return FlatLayout.build(names)

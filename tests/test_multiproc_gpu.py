@@ -1,0 +1,79 @@
+"""torchrun (one process per GPU) paths: centralised DDP with the fused NVLink all-reduce (config #3), the SPMD
+federation with the nvl transport, and 2 GPUs per client (config #5). Need >= 2 GPUs."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+TINY = ["llm_config.model.d_model=256", "llm_config.model.n_heads=4", "llm_config.model.n_layers=2", "llm_config.max_seq_len=256",
+        "llm_config.model.vocab_size=50368", "llm_config.global_train_batch_size=8", "llm_config.device_train_microbatch_size=4",
+        "llm_config.local_steps=2ba", "llm_config.log_to_console=false", "~llm_config.loggers.wandb", "~llm_config.loggers.tensorboard",
+        "~llm_config.callbacks", "llm_config.save_folder=null", "llm_config.optimizer.lr=1.0e-3", "llm_config.scheduler.schedulers.lr.t_warmup=1ba",
+        "fl.eval_period=null", "photon.resume_round=null"]
+
+
+def _torchrun(tmp_path, n, body, port):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs >= {n} GPUs")
+    script = tmp_path / "run.py"
+    script.write_text("import os, sys, torch, torch.distributed as dist\n" f"sys.path.insert(0, {str(ROOT)!r})\n"
+                      "torch.cuda.set_device(int(os.environ['LOCAL_RANK']))\n"
+                      "dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))\n"
+                      f"TINY = {TINY!r}\n" + textwrap.dedent(body) + "\ndist.barrier(); dist.destroy_process_group()\n")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert out.returncode == 0 and "RESULT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-4000:]
+
+
+def test_centralised_ddp_fused_allreduce_matches_nccl(tmp_path):
+    _torchrun(tmp_path, 2, """
+        from photon_b200.config import compose
+        from photon_b200.centralised_train import run_centralised
+        rank = dist.get_rank(); dev = torch.device('cuda', rank)
+        outs = []
+        for nvl in (True, False):
+            cfg = compose(TINY + ['run_uuid=ddp', 'dataset/streams@dataset.train.streams=centralised', 'dataset.train.root_local=synthetic://7'])
+            tr = run_centralised(cfg, device=dev, rank=rank, world_size=2, duration='3ba', use_nvl_allreduce=nvl)
+            assert (type(tr.grad_comm).__name__ == 'NvlGradComm') == nvl
+            outs.append(tr.state.flat.params.clone()); tr.close()
+        ref = outs[0].clone(); dist.broadcast(ref, src=0)
+        assert torch.equal(ref, outs[0]), 'ranks diverged'
+        rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+        assert rel < 2e-3, rel
+        if rank == 0: print('RESULT_OK', rel)
+    """, 29541)
+
+
+def test_spmd_federation_nvl_and_two_gpus_per_client(tmp_path):
+    _torchrun(tmp_path, 2, """
+        from photon_b200.config import compose
+        from photon_b200.federation import FederationRuntime
+        from photon_b200.server_app import run_server
+        rank = dist.get_rank(); dev = torch.device('cuda', rank)
+        finals = {}
+        for name, extra, gpc in (('nvl', ['photon.comm_stack.shm=false', 'photon.comm_stack.nvl=true'], 1),
+                                 ('ray', ['photon.comm_stack.shm=false', 'photon.comm_stack.ray=true'], 1),
+                                 ('nvl2', ['photon.comm_stack.shm=false', 'photon.comm_stack.nvl=true'], 2)):
+            cfg = compose(TINY + ['run_uuid=fed-' + name, 'fl.n_total_clients=4', 'fl.n_clients_per_round=4', 'fl.n_rounds=2',
+                                  'fl.strategy_name=fedadam', 'fl.strategy_kwargs={eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}',
+                                  'dataset.train.root_local=synthetic://c'] + extra)
+            rt = FederationRuntime(cfg, device=dev, rank=rank, world_size=2, gpus_per_client=gpc)
+            h = run_server(cfg, runtime=rt)
+            x = rt.round_backend.global_params().clone()
+            ref = x.clone(); dist.broadcast(ref, src=0)
+            assert torch.equal(ref, x), name + ': ranks hold different global models'
+            finals[name] = x
+            if rank == 0: assert h.latest('server/n_failures') == 0, (name, h.metrics_distributed_fit)
+            rt.close()
+        rel = ((finals['nvl'] - finals['ray']).norm() / finals['ray'].norm()).item()
+        assert rel < 1e-3, rel          # fused NVLink round == NCCL all-reduce baseline
+        assert torch.isfinite(finals['nvl2']).all()
+        if rank == 0: print('RESULT_OK', rel)
+    """, 29543)
