@@ -22,6 +22,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 
 #include "attention_tcgen05.h"
 #include "gemm_tcgen05.h"
@@ -163,10 +164,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     const uint32_t tl = tmem + (uint32_t(warp * 32) << 16);
     const float sc = scale * LOG2E;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
+    // one key tile of online softmax for this thread's row; DIAG is a compile-time flag so that the
+    // (n_kv - 1) off-diagonal tiles carry no per-element causal compares at all
+    auto tile = [&](int j, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const bool diag = causal && (j == qt);
       const uint32_t ts = tl + C::COL_S + (j & 1) * 128;
       // S row (128 fp32) is read from TMEM ONCE: four 32-column loads in flight, one wait
       uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -175,36 +178,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       tmem_ld_32x32(ts + 64, r2);
       tmem_ld_32x32(ts + 96, r3);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      if (DIAG) {  // causal mask: columns beyond this row -> -inf (exp2 -> 0)
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float v0 = __uint_as_float(r0[t]), v1 = __uint_as_float(r1[t]), v2 = __uint_as_float(r2[t]), v3 = __uint_as_float(r3[t]);
-        if (!diag) {
-          mx = fmaxf(fmaxf(mx, fmaxf(v0, v1)), fmaxf(v2, v3));
-        } else {
-          if (t <= row) mx = fmaxf(mx, v0);
-          if (32 + t <= row) mx = fmaxf(mx, v1);
-          if (64 + t <= row) mx = fmaxf(mx, v2);
-          if (96 + t <= row) mx = fmaxf(mx, v3);
+        for (int t = 0; t < 32; ++t) {
+          if (t > row) r0[t] = 0xff800000u;
+          if (32 + t > row) r1[t] = 0xff800000u;
+          if (64 + t > row) r2[t] = 0xff800000u;
+          if (96 + t > row) r3[t] = 0xff800000u;
         }
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;  // 4 independent chains
+#pragma unroll
+      for (int t = 0; t < 32; t += 2) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[t]), __uint_as_float(r0[t + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r1[t]), __uint_as_float(r1[t + 1])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r2[t]), __uint_as_float(r2[t + 1])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r3[t]), __uint_as_float(r3[t + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // lazy rescale: keep the old reference max unless it grew by more than 2^8 (bounded overflow, exact result)
       const float m_cand = fmaxf(m, mx * sc);
       const bool bump = (m_cand - m) > 8.0f;   // also true on the first tile (m = -inf)
       const float m_new = bump ? m_cand : m;
       const float alpha = bump ? exp2f(m - m_new) : 1.0f;
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f;
       auto emit = [&](const uint32_t (&r)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(r[t]), sc, -m_new));
-          float p1 = exp2f(fmaf(__uint_as_float(r[t + 1]), sc, -m_new));
-          if (diag) {
-            if (c * 32 + t > row) p0 = 0.f;
-            if (c * 32 + t + 1 > row) p1 = 0.f;
-          }
-          rs += p0 + p1;
+          const float p0 = exp2f(fmaf(__uint_as_float(r[t]), sc, -m_new));
+          const float p1 = exp2f(fmaf(__uint_as_float(r[t + 1]), sc, -m_new));
+          rs0 += p0;
+          rs1 += p1;
           pk[t >> 1] = pack_bf16(p0, p1);
         }
         asm volatile(
@@ -218,13 +223,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       emit(r1, 1);
       emit(r2, 2);
       emit(r3, 3);
-      l = l * alpha + rs;
+      l = l * alpha + (rs0 + rs1);
       m = m_new;
       // rescale the running O only when some row of this warp actually moved its reference max
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
         if (__any_sync(0xffffffff, bump)) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < DH / 32; ++c) {
             uint32_t r[32];
@@ -239,7 +244,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[j & 1]);
-    }
+    };
+    const int n_plain = causal ? n_kv - 1 : n_kv;
+    for (int j = 0; j < n_plain; ++j) tile(j, std::false_type{});
+    if (causal) tile(n_kv - 1, std::true_type{});
     // ---- epilogue: O / l -> bf16 -> global; lse
     mbar_wait(o_done, (n_kv - 1) & 1);
     tc_fence_after();
@@ -474,14 +482,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_commit();
       }
     };
-    for (int t = 0; t < n_it; ++t) {
+    auto row_tile = [&](int t, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       const int it = i0 + t;
       const long long grow = (long long)(b * H + h) * S + it * 128 + row;
       const float lse2 = lse[grow] * LOG2E;
       const float dl = delta[grow];
       mbar_wait(sdp_full, t & 1);
       tc_fence_after();
-      const bool diag = causal && (it == jt);
       uint32_t pk[64], dk[64];  // packed bf16 P and dS of this row (128 columns each), kept in registers
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -493,7 +501,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int e = 0; e < 32; e += 2) {
           float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
           float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
-          if (diag) {
+          if (DIAG) {
             if (c * 32 + e > row) p0 = 0.f;
             if (c * 32 + e + 1 > row) p1 = 0.f;
           }
@@ -522,6 +530,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       mbar_arrive(pds_ready);
       if (t > 0) drain_dq(t - 1);   // overlaps with S_{t+1}/dP_{t+1} and dV/dK/dQ_t on the tensor pipe
+    };
+    // causal: only the first query tile (it == jt) touches the diagonal; every other tile runs the mask-free body
+    for (int t = 0; t < n_it; ++t) {
+      if (causal && t == 0) row_tile(t, std::true_type{});
+      else row_tile(t, std::false_type{});
     }
     drain_dq(n_it - 1);
     // ---- epilogue: dK (x scale), dV -> bf16 -> dqkv

@@ -219,6 +219,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int c = 0; c < BN / CW; ++c) {
         const int col0 = n_blk * BN + c * CW;
         if (col0 >= p.N) break;  // whole chunk out of range (uniform)
+        // aux tile (residual / pre-activation) for this chunk: issue the global loads FIRST so their latency
+        // overlaps the TMEM read below
+        uint4 ax[8];
+        if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
+          const __nv_bfloat16* arow = p.aux + row * p.ld_aux + col0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ax[j] = (row_ok && col0 + 8 * j < p.N) ? __ldg(reinterpret_cast<const uint4*>(arow + 8 * j)) : make_uint4(0, 0, 0, 0);
+        }
         float v[CW];
         {
           uint32_t r[32];
@@ -255,11 +264,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else {
           if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
-            const __nv_bfloat16* arow = p.aux + row * p.ld_aux + col0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              if (row_ok && col0 + 8 * j < p.N) {
-                const uint4 a = *reinterpret_cast<const uint4*>(arow + 8 * j);
+              {
+                const uint4 a = ax[j];
                 const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {

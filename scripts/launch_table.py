@@ -13,9 +13,9 @@ def table(path):
     for row in csv.DictReader(lines):
         name, v, unit = row["Kernel Name"], float(row["Metric Value"].replace(",", "")), row["Metric Unit"]
         v = v / 1e3 if unit == "us" else v / 1e6 if unit == "ns" else v * 1e3 if unit == "s" else v
-        m = re.search(r"gemm_kernel<(\d+), (\d+), (\d+)>", name)
+        m = re.search(r"gemm_kernel<(\d+), (\d+), (\d+)(?:, (\d+))?>", name)
         if m:
-            k = f"gemm_tcgen05<A_MN={m.group(1)},B_MN={m.group(2)},EPI={m.group(3)}>"
+            k = f"gemm_tcgen05<A_MN={m.group(1)},B_MN={m.group(2)},EPI={m.group(3)},CL={m.group(4)}>"
         else:
             m = re.search(r"(\w+_kernel)(<\d+>)?", name)
             k = (m.group(1) + (m.group(2) or "")) if m else name[:60]
