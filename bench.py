@@ -31,7 +31,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -57,54 +56,64 @@ def reference_arm() -> None:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE long-lived
+    ``nvidia-smi -lms 200`` child started before the region (no fork/exec while the step is being timed)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int) -> None:
-        self.idx, self.rows, self._stop = gpu_index, [], threading.Event()
-        self._th = threading.Thread(target=self._run, daemon=True)
+    def __init__(self, gpu_index: int, enabled: bool = True) -> None:
+        self.idx, self.rows, self.proc, self.enabled = gpu_index, [], None, enabled
 
-    def _run(self) -> None:
-        while not self._stop.is_set():
+    def start(self) -> "ClockSampler":
+        if self.enabled:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx),
+                                              "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
-
-    def __enter__(self) -> "ClockSampler":
-        self._th.start()
+                self.proc = None
         return self
 
-    def __exit__(self, *a: object) -> None:
-        self._stop.set()
-        self._th.join(timeout=3)
+    def mark(self) -> None:
+        """Timed region starts now: drop what was sampled while idle."""
+        self._t0 = time.time()
+
+    def stop(self) -> None:
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        self.rows = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.strip()]
 
     def summary(self) -> dict:
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        load = [r for r in self.rows if len(r) > 3 and r[3].replace(".", "").isdigit() and float(r[3]) > 300.0] or self.rows
+        sm = sorted(float(r[1]) for r in load if len(r) > 2 and r[1].replace(".", "").isdigit())
         mx = max((float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()), default=0.0)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in load for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "note": "median over samples with power draw > 300 W (under load)"}
 
 
-def build_cfg(impl: str, steps: int, model: str, attention: str):
+def build_cfg(impl: str, steps: int, model: str, attention: str, microbatch: int = LOCAL_BATCH, server: str = "fedavg"):
     from photon_b200.config import compose
 
     ov = [f"llm_config={model}", "run_uuid=bench", f"fl.n_total_clients={N_CLIENTS}", f"fl.n_clients_per_round={N_CLIENTS}",
           "fl.strategy_name=NESTOROV", "fl.strategy_kwargs.server_learning_rate=1.0", "fl.strategy_kwargs.server_momentum=0.0",
           "fl.reset_optimizer=false", "fl.eval_period=null", f"llm_config.global_train_batch_size={LOCAL_BATCH}",
-          f"llm_config.device_train_microbatch_size={LOCAL_BATCH}", f"llm_config.local_steps={steps}ba",
+          f"llm_config.device_train_microbatch_size={microbatch}", f"llm_config.local_steps={steps}ba",
           "llm_config.max_duration=40960ba", "llm_config.scheduler.schedulers.lr.t_max=40960ba",
           "llm_config.scheduler.schedulers.lr.t_warmup=800ba", "llm_config.precision=amp_bf16", "llm_config.log_to_console=false",
           "~llm_config.loggers.wandb", "~llm_config.loggers.tensorboard", "llm_config.save_folder=null", "llm_config.save_interval=1000000ba",
           "llm_config.eval_interval=1000000ba", "~llm_config.callbacks", "photon.checkpoint=false", "photon.comm_stack.shm=false",
           "dataset.train.root_local=synthetic://c4", "dataset.val.root_local=synthetic://c4"]
+    if server == "fedadam":   # BASELINE config #4 flavour
+        ov += ["fl.strategy_name=fedadam", "fl.strategy_kwargs={eta: 0.1, beta_1: 0.9, beta_2: 0.95, tau: 1.0e-9}", "fl.reset_optimizer=true"]
     if impl == "ours":
         ov += ["photon.comm_stack.nvl=true", f"kernels.attention={attention}"]
     else:  # reference-equivalent stock path: torch ops + SDPA/FA2 attention + host shm round
@@ -121,6 +130,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch"])
     ap.add_argument("--model", default="mpt-125m")
     ap.add_argument("--attention", default="b200", choices=["b200", "torch"])
+    ap.add_argument("--microbatch", type=int, default=0, help="device microbatch (0 = 32 for mpt-125m, 8 otherwise)")
+    ap.add_argument("--server", default="fedavg", choices=["fedavg", "fedadam"])
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm()
@@ -149,7 +160,8 @@ def main() -> None:
     sampled = list(range(N_CLIENTS))
 
     def make_runtime(local_steps: int) -> FederationRuntime:
-        rt = FederationRuntime(build_cfg(args.impl, local_steps, args.model, args.attention), device=dev, rank=rank, world_size=world)
+        mb = args.microbatch or (LOCAL_BATCH if args.model == "mpt-125m" else 8)
+        rt = FederationRuntime(build_cfg(args.impl, local_steps, args.model, args.attention, mb, args.server), device=dev, rank=rank, world_size=world)
         rt.build()
         broadcast_parameters_to_nodes(rt, rt.initial_parameters())
         return rt
@@ -178,11 +190,13 @@ def main() -> None:
     if args.impl == "ours":
         ops.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        ev0.record()
-        res = one_round(rt, 2)
-        ev1.record()
-        sync()
+    clk = ClockSampler(local, enabled=(rank == 0)).start()
+    sync()
+    clk.mark()
+    ev0.record()
+    res = one_round(rt, 2)
+    ev1.record()
+    sync()
     dev_ms = ev0.elapsed_time(ev1)
     launches = ops.launch_count() if args.impl == "ours" else 0
     failed = [r for r in res if r.status.code != 0]
@@ -195,6 +209,7 @@ def main() -> None:
     one_round(rt, 3)
     sync()
     e2e_s = time.perf_counter() - t0
+    clk.stop()   # sampled across both timed rounds
     # ---- (3) aggregate + broadcast alone (round hot path), device-timed
     rt.round_backend.begin_round()
     rt.round_backend.add_client(rt.trainer.state.flat.params, 1.0)
@@ -224,7 +239,7 @@ def main() -> None:
             "dtype": "bf16", "data": "synthetic C4-shaped tokens, random-init weights", "impl": args.impl,
             "config": {"model": args.model, "global_batch": N_CLIENTS * LOCAL_BATCH, "seq_len": SEQ,
                        "parallelism": f"fed{N_CLIENTS}clients_on_{world}gpu", "clients_per_gpu": clients_per_gpu,
-                       "local_steps_per_round": K, "local_batch": LOCAL_BATCH, "optimizer": "adopt", "server": "fedavg(nesterov lr=1 mu=0)",
+                       "local_steps_per_round": K, "local_batch": LOCAL_BATCH, "optimizer": str(rt.cfg["llm_config"]["optimizer"]["name"]), "server": "fedavg(nesterov lr=1 mu=0)" if args.server == "fedavg" else "fedadam",
                        "comm_stack": rt.round_backend.name, "attention": args.attention if args.impl == "ours" else "sdpa",
                        "l2_flush": "256 MiB memset before each timed region; per-step activations (~19 GB) exceed L2",
                        "timed_region": "one full round: K local steps x 8 clients + aggregate + server-opt + broadcast"},

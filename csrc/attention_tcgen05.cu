@@ -42,7 +42,7 @@ struct FwdCfg {
   static constexpr int CH = DH / 64;              // 64-column swizzle chunks per tile
   static constexpr int TILE = 128 * 128 * CH;     // bytes of one [128 x DH] bf16 tile
   static constexpr int STAGES = (DH == 64) ? 4 : 2;
-  static constexpr int SMEM = TILE * (1 + 2 * STAGES) + 256 + 1024;
+  static constexpr int SMEM = TILE * (1 + 2 * STAGES) + 256 + 2048 + 1024;   // tiles + barriers + row-max exchange + align
   // two S buffers (128 fp32 columns each); P_j (packed bf16, 64 columns) aliases the head of S_j once the row
   // threads hold S_j in registers; O after them
   static constexpr int COL_S = 0, COL_O = 256;
@@ -50,7 +50,10 @@ struct FwdCfg {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(192, 1)
+// 320 threads: warps 0-7 = softmax (warp w and w+4 own the same 32 query rows / TMEM lanes and split the 128 key
+// columns 64/64, so every SMSP has two softmax warps to interleave; row max / row sum halves meet through smem),
+// warp 8 = TMA producer, warp 9 = MMA issuer + TMEM allocator.
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
                 float scale, int causal) {
   using C = FwdCfg<DH>;
@@ -68,6 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   uint64_t* p_ready = bars + 15;                // [2]
   uint64_t* o_done = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* xch = reinterpret_cast<float*>(bars + 20);   // [2 tiles][2 halves][128 rows] row-max exchange (+ reused for the final row sums)
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -78,7 +82,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   const int n_kv = causal ? qt + 1 : S / BKV;
   const int row0 = b * S + qt * BQ;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < C::STAGES; ++s) {
@@ -88,18 +92,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], 256);
     }
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(q_full, C::TILE);
@@ -118,7 +122,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
           tma_load_2d(sV + st * C::TILE + c * 16384, &tmQKV, &v_full[st], 2 * d_model + h * DH + c * 64, b * S + j * BKV);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
@@ -159,50 +163,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax rows (warps 0..3)
-    const int row = warp * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t tl = tmem + (uint32_t(warp * 32) << 16);
+    // ------------------------------------------------------------------ softmax rows (warps 0..7)
+    const int half = warp >> 2;                         // which 64 key columns of the row this thread owns
+    const int row = (warp & 3) * 32 + lane;             // query row inside the tile == TMEM lane
+    const uint32_t tl = tmem + (uint32_t((warp & 3) * 32) << 16);
     const float sc = scale * LOG2E;
-    float m = -INFINITY, l = 0.f;
-    // one key tile of online softmax for this thread's row; DIAG is a compile-time flag so that the
-    // (n_kv - 1) off-diagonal tiles carry no per-element causal compares at all
+    float m = -INFINITY, l = 0.f;                        // l = partial row sum over this thread's columns
     auto tile = [&](int j, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t ts = tl + C::COL_S + (j & 1) * 128;
-      // S row (128 fp32) is read from TMEM ONCE: four 32-column loads in flight, one wait
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld_32x32(ts, r0);
-      tmem_ld_32x32(ts + 32, r1);
-      tmem_ld_32x32(ts + 64, r2);
-      tmem_ld_32x32(ts + 96, r3);
+      uint32_t r0[32], r1[32];                           // this thread's 64 S values, read from TMEM once
+      tmem_ld_32x32(ts + half * 64, r0);
+      tmem_ld_32x32(ts + half * 64 + 32, r1);
       tmem_ld_wait();
       if (DIAG) {  // causal mask: columns beyond this row -> -inf (exp2 -> 0)
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          if (t > row) r0[t] = 0xff800000u;
-          if (32 + t > row) r1[t] = 0xff800000u;
-          if (64 + t > row) r2[t] = 0xff800000u;
-          if (96 + t > row) r3[t] = 0xff800000u;
+          if (half * 64 + t > row) r0[t] = 0xff800000u;
+          if (half * 64 + 32 + t > row) r1[t] = 0xff800000u;
         }
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;  // 4 independent chains
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int t = 0; t < 32; t += 2) {
         mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[t]), __uint_as_float(r0[t + 1])));
         mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r1[t]), __uint_as_float(r1[t + 1])));
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r2[t]), __uint_as_float(r2[t + 1])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r3[t]), __uint_as_float(r3[t + 1])));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // the two halves of a row agree on the row max through smem (double-buffered per tile parity)
+      float* xb = xch + (j & 1) * 256;
+      const float mine = fmaxf(mx0, mx1);
+      xb[half * 128 + row] = mine;
+      named_bar_sync(2, 256);
+      const float mx = fmaxf(mine, xb[(half ^ 1) * 128 + row]);
       // lazy rescale: keep the old reference max unless it grew by more than 2^8 (bounded overflow, exact result)
       const float m_cand = fmaxf(m, mx * sc);
       const bool bump = (m_cand - m) > 8.0f;   // also true on the first tile (m = -inf)
       const float m_new = bump ? m_cand : m;
       const float alpha = bump ? exp2f(m - m_new) : 1.0f;
       float rs0 = 0.f, rs1 = 0.f;
-      auto emit = [&](const uint32_t (&r)[32], int c) {
+      auto emit = [&](const uint32_t (&r)[32], int cc) {
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
@@ -214,24 +215,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-                ts + c * 16),
+                ts + half * 32 + cc * 16),
             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
             "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
             : "memory");
       };
+      // NOTE: P (64 packed columns) aliases S columns [0,64): the OTHER half of this row may still be reading its S
+      // values from columns [64,128) -> only columns [0,64) are overwritten, and half 0 has them in registers already;
+      // half 1's stores land in [32,64), which half 0 read before the named barrier above.
       emit(r0, 0);
       emit(r1, 1);
-      emit(r2, 2);
-      emit(r3, 3);
       l = l * alpha + (rs0 + rs1);
       m = m_new;
-      // rescale the running O only when some row of this warp actually moved its reference max
+      // rescale the running O only when some row of this warp actually moved its reference max (DH/2 columns per thread)
       if (j > 0) {
         if (__any_sync(0xffffffff, bump)) {
           mbar_wait(o_done, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
+          for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
             uint32_t r[32];
             tmem_ld_32x32(tl + C::COL_O + c * 32, r);
             tmem_ld_wait();
@@ -248,13 +250,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     const int n_plain = causal ? n_kv - 1 : n_kv;
     for (int j = 0; j < n_plain; ++j) tile(j, std::false_type{});
     if (causal) tile(n_kv - 1, std::true_type{});
-    // ---- epilogue: O / l -> bf16 -> global; lse
+    // ---- epilogue: row sum = both halves; O / l -> bf16 -> global (DH/2 columns per thread); lse
+    named_bar_sync(2, 256);                 // everyone is past its last max exchange: xch can be reused
+    xch[half * 128 + row] = l;
+    named_bar_sync(2, 256);
+    const float l_tot = l + xch[(half ^ 1) * 128 + row];
     mbar_wait(o_done, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
+    const float inv_l = 1.0f / l_tot;
     __nv_bfloat16* orow = out + (long long)(row0 + row) * d_model + h * DH;
 #pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
+    for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tl + C::COL_O + c * 32, r);
       tmem_ld_wait();
@@ -268,11 +274,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
       }
     }
-    lse[((long long)b * H + h) * S + qt * BQ + row] = m * LN2 + __logf(l);
+    if (half == 0) lse[((long long)b * H + h) * S + qt * BQ + row] = m * LN2 + __logf(l_tot);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<C::TMEM_COLS>(tmem);
+  if (warp == 9) tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
 // ======================================================================================= backward
@@ -322,7 +328,10 @@ struct BwdCfg {
   static constexpr int TMEM_COLS = 512;
 };
 
-__global__ void __launch_bounds__(192, 1)
+// 320 threads: warps 0-7 = row threads (two per SMSP: warp w and w+4 own the same 32 query rows / TMEM lanes and
+// split the 128 key columns 64/64 - no cross-thread exchange is needed because lse and delta are per-row inputs),
+// warp 8 = TMA producer, warp 9 = MMA issuer + TMEM allocator.
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale,
                 int causal) {
@@ -358,7 +367,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int i0 = causal ? jt : 0;
   const int n_it = n_t - i0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmDQ);
@@ -368,20 +377,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&qd_empty[s], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 128);
+    mbar_init(pds_ready, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
+    mbar_init(dq_free, 256);
     mbar_init(mma_done, 1);
     mbar_init(final_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * C::TILE);
       tma_load_2d(sK, &tmQKV, kv_full, d_model + h * DH, b * S + jt * 128);
@@ -394,7 +403,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_load_2d(sDO + st * C::TILE, &tmDO, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both K-major, N = 128
       constexpr uint32_t idesc_mm = make_idesc_bf16(128, DH, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q) MN-major
@@ -451,9 +460,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_commit(final_done);
     }
   } else {
-    // ------------------------------------------------------------------ row threads (warps 0..3)
-    const int row = warp * 32 + lane;
-    const uint32_t tl = tmem + (uint32_t(warp * 32) << 16);
+    // ------------------------------------------------------------------ row threads (warps 0..7)
+    const int half = warp >> 2;                      // which 64 key columns of the row this thread owns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tl = tmem + (uint32_t((warp & 3) * 32) << 16);
     const float sc = scale * LOG2E;
     const uint32_t swz = row & 7;
     const bool issuer = (threadIdx.x == 0);
@@ -461,9 +471,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(dq_full, t & 1);
       tc_fence_after();
       if (issuer) tma_wait_read<0>();
-      named_bar_sync(1, 128);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      named_bar_sync(1, 256);
+      {
+        const int c = half;  // 32 of the 64 dQ columns per thread
         uint32_t r[32];
         tmem_ld_32x32(tl + C::COL_DQ + c * 32, r);
         tmem_ld_wait();
@@ -475,7 +485,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       mbar_arrive(dq_free);
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (issuer) {
         tma_reduce_add_2d(&tmDQ, sDQ, h * DH, b * S + (i0 + t) * 128);
         tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * DH + 32, b * S + (i0 + t) * 128);
@@ -490,9 +500,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float dl = delta[grow];
       mbar_wait(sdp_full, t & 1);
       tc_fence_after();
-      uint32_t pk[64], dk[64];  // packed bf16 P and dS of this row (128 columns each), kept in registers
+      uint32_t pk[32], dk[32];  // packed bf16 P and dS of this thread's 64 columns, kept in registers
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;  // 32-column block of the row
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
         tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
@@ -507,23 +518,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
           const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
           const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
-          pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
-          dk[c * 16 + (e >> 1)] = pack_bf16(s0, s1);
+          pk[cc * 16 + (e >> 1)] = pack_bf16(p0, p1);
+          dk[cc * 16 + (e >> 1)] = pack_bf16(s0, s1);
         }
       }
       // S_t / dP_t are consumed (the MMA warp may overwrite them); the smem staging is reusable once the
       // previous tile's dV / dK / dQ MMAs retired
       if (t > 0) mbar_wait(mma_done, (t - 1) & 1);
+      {
+        // this thread's 64 columns = swizzle chunk `half` of row `row`: eight 16-byte groups
+        uint8_t* prow = sP + half * 16384 + row * 128;
+        uint8_t* drow = sDS + half * 16384 + row * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        // columns [32c, 32c+32) of row `row`: chunk = c/2, 16-byte groups (c&1)*4 .. +3 inside the 128-byte swizzled row
-        uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
-        uint8_t* drow = sDS + (c >> 1) * 16384 + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t slot = (uint32_t((c & 1) * 4 + g) ^ swz) << 4;
-          *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]);
-          *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[c * 16 + 4 * g], dk[c * 16 + 4 * g + 1], dk[c * 16 + 4 * g + 2], dk[c * 16 + 4 * g + 3]);
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t slot = (uint32_t(g) ^ swz) << 4;
+          *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
       }
       fence_proxy_async_smem();
@@ -542,8 +552,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tc_fence_after();
     __nv_bfloat16* krow = dqkv + (long long)(b * S + jt * 128 + row) * (3 * d_model) + d_model + h * DH;
     __nv_bfloat16* vrow = krow + d_model;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t rk[32], rv[32];
       tmem_ld_32x32(tl + C::COL_DK + c * 32, rk);
       tmem_ld_32x32(tl + C::COL_DV + c * 32, rv);
@@ -567,7 +577,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<C::TMEM_COLS>(tmem);
+  if (warp == 9) tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
 template <typename K>
@@ -591,11 +601,11 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
   if (dh == 64) {
     static bool once = (set_smem(attn_fwd_kernel<64>, FwdCfg<64>::SMEM), true);
     (void)once;
-    attn_fwd_kernel<64><<<grid, 192, FwdCfg<64>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
+    attn_fwd_kernel<64><<<grid, 320, FwdCfg<64>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
   } else {
     static bool once = (set_smem(attn_fwd_kernel<128>, FwdCfg<128>::SMEM), true);
     (void)once;
-    attn_fwd_kernel<128><<<grid, 192, FwdCfg<128>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
+    attn_fwd_kernel<128><<<grid, 320, FwdCfg<128>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention fwd launch: ") + cudaGetErrorString(e));
@@ -626,7 +636,7 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
   static bool once = (set_smem(attn_bwd_kernel, BwdCfg::SMEM), true);
   (void)once;
   dim3 grid(S / 128, H, B);
-  attn_bwd_kernel<<<grid, 192, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0);
+  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0);
   attn_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(g_dq_acc, (__nv_bfloat16*)dqkv, rows, d, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention bwd launch: ") + cudaGetErrorString(e));

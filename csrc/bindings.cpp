@@ -278,7 +278,7 @@ pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
 }
 
 void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& acc_ptrs,
-               const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi,
+               const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi, int64_t total,
                int kind, double avg_scale, double lr, double mu, double eta, double beta1, double beta2, double tau, int64_t round_t,
                bool sign_compat) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
@@ -292,7 +292,7 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
   a.x = a.xg[rank];
   a.m = reinterpret_cast<float*>(m_ptr);
   a.v = reinterpret_cast<float*>(v_ptr);
-  a.lo = lo, a.hi = hi, a.kind = kind, a.avg_scale = float(avg_scale), a.lr = float(lr), a.mu = float(mu);
+  a.lo = lo, a.hi = hi, a.total = total, a.kind = kind, a.avg_scale = float(avg_scale), a.lr = float(lr), a.mu = float(mu);
   a.eta = float(eta), a.beta1 = float(beta1), a.beta2 = float(beta2), a.tau = float(tau);
   const double t = double(round_t < 1 ? 1 : round_t);
   a.inv_bc1 = float(1.0 / (1.0 - std::pow(beta1, t)));

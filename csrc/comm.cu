@@ -35,7 +35,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   [0,8)   start flags (slot r written by rank r)      [8,16)  end flags
 //   [16]    local "go" flag (block 0 -> other blocks)   [17]    local done-block counter
 //   [32,34) float wsum (this rank's sum of client weights)   [64..) double sq_parts[8], double sums[8]
-constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
+constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_GO2 = 18, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
 
 __device__ __forceinline__ void grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
   uint32_t* mine = c.ctl[c.rank];
@@ -157,15 +157,10 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
     }
     if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
     if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    // R2: broadcast the updated slice (fp32 master + bf16 compute copy) into every rank's planes
+    // R2 (a): push the updated fp32 slice into every rank's global plane over NVLink
     const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
-    uint2 nb;
-    nb.x = pack_bf16(xv[0], xv[1]), nb.y = pack_bf16(xv[2], xv[3]);
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) {
-      st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
-      if (a.xs[p]) st_peer_u2(reinterpret_cast<uint2*>(a.xs[p]) + i, nb);
-    }
+    for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
   }
   // norm by-products (this rank's shard): block reduce -> fp64 atomics in the local control page
   __shared__ float red[5][16];
@@ -181,7 +176,34 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
     for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
     atomicAdd(reinterpret_cast<double*>(c.ctl[c.rank] + CP_SUMS) + threadIdx.x, double(t));
   }
-  if (grid_done(c)) peer_barrier_end(c, epoch);
+  // every rank's slice has landed everywhere once the end barrier completes; the last block runs it and then
+  // releases the whole grid into R2 (b): the bf16 compute copy is cast LOCALLY from the received fp32 plane
+  // (halves the NVLink bytes of the broadcast compared with also pushing the bf16 copy to 7 peers)
+  uint32_t* mine = c.ctl[c.rank];
+  if (grid_done(c)) {
+    peer_barrier_end(c, epoch);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mine + CP_GO2), "r"(epoch) : "memory");
+    }
+  }
+  void* xs = a.xs[c.rank];
+  if (xs != nullptr && !skip) {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + CP_GO2) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(a.xg[c.rank]);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.total / 4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = ld_peer_f4(src + i);  // written by peers during this launch: bypass the non-coherent path
+      uint2 o;
+      o.x = pack_bf16(v.x, v.y), o.y = pack_bf16(v.z, v.w);
+      reinterpret_cast<uint2*>(xs)[i] = o;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ N1

@@ -22,6 +22,7 @@ struct FedRoundArgs {
   float* m;
   float* v;
   long long lo, hi;             // this rank's shard, multiples of 4
+  long long total;              // full flat length (local bf16 cast phase)
   int kind;                     // 0 fedavg, 1 nesterov, 2 fedmom, 3 fedadam, 4 fedyogi
   float avg_scale;              // scaling_fn(K)
   float lr, mu;                 // fedavg / nesterov / fedmom

@@ -23,15 +23,24 @@ namespace pb {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int STAGES = 3;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KiB
-constexpr int B_STAGE = BN * BK * 2;  // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-constexpr int EPI_BUFS = 4;
-constexpr int EPI_BUF = 128 * 128;  // 128 rows x 128 B (one swizzle atom wide)
+constexpr int EPI_BUF = 128 * 128;    // 128 rows x 128 B (one swizzle atom wide)
 constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF + 256 + 1024;
 constexpr int TMEM_COLS = 512;
+
+// Shared-memory plan per (epilogue, cluster) variant. A CTA of a pair stages only HALF of the B tile, so a stage is
+// 32 instead of 48 KiB and the same 227 KiB hold a 6-deep (5 for the two-output GELU epilogue) instead of a 3-deep TMA
+// pipeline: ~3000 instead of ~1500 tensor-core clocks of loads in flight per SM.
+template <int EPI, int CL>
+struct Cfg {
+  static constexpr int B_STAGE = (BN / CL) * BK * 2;   // 32 KiB (CL=1) / 16 KiB (CL=2)
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+  static constexpr int STORES = (EPI == EPI_GELU_DUAL) ? 2 : 1;   // staging buffers consumed per epilogue chunk
+  static constexpr int EPI_BUFS = (CL == 1) ? 4 : 2 * STORES;
+  static constexpr int STAGES = (CL == 1) ? 3 : (EPI == EPI_GELU_DUAL ? 5 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory of sm_100");
+};
 
 struct Params {
   int M, N, K;
@@ -44,13 +53,18 @@ struct Params {
   int splits, kb_per_split;     // split-K (EPI_F32 + accumulate): work item = (tile, k-range)
 };
 
-// CL = thread-block-cluster size along M (1 or 2). With CL = 2 the two CTAs of a cluster work on M-adjacent tiles
-// of the same N block: each loads HALF of the shared B tile and TMA-multicasts it into both CTAs' smem, cutting the
-// L2->SM operand traffic per CTA from 48 KiB to 32 KiB per k-block (the 1-CTA kernel is L2-bandwidth bound).
+// CL = 1: one CTA per 128x256 tile (tcgen05 cta_group::1).
+// CL = 2: a CTA PAIR (two SMs of one TPC, cluster 2x1x1) computes a 256x256 tile with ONE tcgen05.mma.cta_group::2
+//         per k-step, issued by the leader CTA: each CTA stages its own 128 A rows and HALF of the B tile (128 of the
+//         256 N rows), the tensor cores of both SMs read both halves, each SM accumulates its 128 rows in its own TMEM.
+//         Per SM this halves the B traffic through shared memory (the 1-CTA form is smem-bandwidth bound: 96 B/clk of
+//         MMA operand reads + 96 B/clk of TMA writes against a 128 B/clk port) and needs 32 instead of 48 KiB per stage.
 template <int A_MN, int B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const Params p) {
+  using C = Cfg<EPI, CL>;
+  constexpr int STAGES = C::STAGES, B_STAGE = C::B_STAGE, STAGE_BYTES = C::STAGE_BYTES, EPI_BUFS = C::EPI_BUFS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -74,19 +88,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);  // CL > 1: a stage is reusable once BOTH CTAs' MMAs consumed it (peer multicasts into it)
+      mbar_init(&full[s], CL);   // CL = 2: leader's arrive.expect_tx + the peer's remote arrive (bytes of both land here)
+      mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[a], 4 * CL);  // one arrival per epilogue warp (of both CTAs: the leader's MMA warp waits for the pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (CL > 1) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive
+  if (CL > 1) cluster_sync_all();  // peer barriers initialised before any remote arrive / 2-SM TMA / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -108,34 +125,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n_blk = p.m_fastest ? tile / tiles_mu : tile % p.tiles_n;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
-          uint8_t* a_dst = sA + stage * A_STAGE;
-          uint8_t* b_dst = sB + stage * B_STAGE;
           if (CL > 1) {
-            // A: own tile; B: my half of the shared tile, multicast to both CTAs
+            // CTA pair: stage = own A rows (16 KiB) + own half of B (16 KiB); all bytes are credited to the LEADER's
+            // full barrier, which expects 2 x 32 KiB; the peer additionally arrives remotely
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* a_dst = sA + stage * A_STAGE;
+            uint8_t* b_dst = sB + stage * B_STAGE;
+            if (crank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
+                tma_load_2d_2sm(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
             } else {
-              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
+              tma_load_2d_2sm(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) {
-                const int c = crank * (BN / 128) + j;
-                tma_load_2d_mc(b_dst + c * (BK * 128), &tmB, &full[stage], n_blk * BN + c * 64, kb * BK, 0x3);
-              }
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_2sm(b_dst + j * (BK * 128), &tmB, &full[stage], n_blk * BN + (crank * (BN / 128) + j) * 64, kb * BK);
             } else {
-              tma_load_2d_mc(b_dst + crank * (B_STAGE / 2), &tmB, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2), 0x3);
+              tma_load_2d_2sm(b_dst, &tmB, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2));
             }
+            if (crank != 0) mbar_arrive_remote(&full[stage], 0);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
             continue;
           }
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE;
+          uint8_t* b_dst = sB + stage * B_STAGE;
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
@@ -159,8 +180,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -182,16 +203,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : make_smem_desc_sw128(a_base + k * (UK * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * (UK * 128), BK * 128, 1024)
                                         : make_smem_desc_sw128(b_base + k * (UK * 2), 16, 1024);
-            tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CL > 1) tc_mma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL > 1) tc_commit_mc(&empty[stage], 0x3);  // release the stage in BOTH CTAs
-          else tc_commit(&empty[stage]);                 // frees the smem slot once these MMAs retire
+          if (CL > 1) tc_commit_2sm(&empty[stage], 0x3);  // release the stage in BOTH CTAs
+          else tc_commit(&empty[stage]);                  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (CL > 1) tc_commit_2sm(&tfull[acc], 0x3);  // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -202,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = q * 32 + lane;
     const bool issuer = (threadIdx.x == 128);
     constexpr int CW = (EPI == EPI_F32) ? 32 : 64;             // columns per staged chunk (128 B wide)
-    constexpr int STORES = (EPI == EPI_GELU_DUAL) ? 2 : 1;      // staging buffers consumed per chunk
+    constexpr int STORES = C::STORES;                           // staging buffers consumed per chunk
     int ebuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -321,7 +344,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CL > 1 && crank != 0) mbar_arrive_remote(&tempty[acc], 0);
+        else mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -330,8 +356,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // nobody leaves while the peer may still multicast / arrive into this CTA
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (CL > 1) cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 2) {
+    if (CL > 1) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -378,14 +407,14 @@ static void launch_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   auto kern = gemm_kernel<A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<EPI, CL>::SMEM_BYTES);
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm smem attr: ") + cudaGetErrorString(e));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.dynamicSmemBytes = Cfg<EPI, CL>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

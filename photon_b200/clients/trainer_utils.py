@@ -111,6 +111,10 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
     kernels = dict(cfg.get("kernels") or {})
     if mcfg.attn_impl == "torch" and device.type == "cuda" and kernels.get("attention", "auto") == "auto":
         kernels["attention"] = "torch"
+    # fsdp_config present (YAML default) → shard the optimizer state over the client's GPUs; the launch scripts delete the
+    # node (or set NO_SHARD) for plain DDP (ref: scripts/cen_125m_example.sh:87, trainer_utils.py:1378-1393: 1 GPU → DDP)
+    fsdp = t.get("fsdp_config") or None
+    shard_state = bool(fsdp) and world_size > 1 and str(dict(fsdp).get("sharding_strategy", "FULL_SHARD")).upper() != "NO_SHARD"
     tr = Trainer(mcfg, optimizer_cfg=dict(t["optimizer"]), scheduler_cfg=dict(t.get("scheduler") or {}),
                  train_loader=train_loader, eval_loaders=eval_loaders, global_train_batch_size=gbs,
                  device_train_microbatch_size=t.get("device_train_microbatch_size", "auto"),
@@ -122,7 +126,8 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  eval_subset_num_batches=int(t.get("eval_subset_num_batches", -1)), device=device, rank=rank,
                  world_size=world_size, process_group=process_group, grad_comm=grad_comm, kernels=kernels, seed=seed,
                  run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,
-                 frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend)
+                 frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend,
+                 shard_optimizer_state=shard_state)
     return tr, t
 
 

@@ -77,16 +77,16 @@ def set_optimizer_state(trainer: Trainer, exp_avg: torch.Tensor, exp_avg_sq: tor
     (``fl.aggregate_momenta``; ref: clients/utils.py:257-402). Personalised layers keep theirs."""
     opt, lay = trainer.state.optimizer, trainer.state.flat.layout
     if personalized:
+        cur_m, cur_v = opt.full_moments()
         for i, name in enumerate(lay.names):
             if any(p in name for p in personalized):
-                lay.view(exp_avg, i).copy_(lay.view(opt.exp_avg, i))
-                lay.view(exp_avg_sq, i).copy_(lay.view(opt.exp_avg_sq, i))
-    opt.exp_avg.copy_(exp_avg)
-    opt.exp_avg_sq.copy_(exp_avg_sq.clamp_(min=0.0))
+                lay.view(exp_avg, i).copy_(lay.view(cur_m, i))
+                lay.view(exp_avg_sq, i).copy_(lay.view(cur_v, i))
+    opt.set_full_moments(exp_avg, exp_avg_sq.clamp_(min=0.0))   # sharded state keeps only this rank's slice
     opt.step_count = int(step)
     name = opt.name
-    return {f"client/local_{name}/l2_norm_exp_avg": float(opt.exp_avg.norm()),
-            f"client/local_{name}/l2_norm_exp_avg_sq": float(opt.exp_avg_sq.norm()),
+    return {f"client/local_{name}/l2_norm_exp_avg": float(exp_avg.norm()),
+            f"client/local_{name}/l2_norm_exp_avg_sq": float(exp_avg_sq.norm()),
             f"client/local_{name}/step": float(step)}
 
 
@@ -162,7 +162,7 @@ def post_process_client_result(trainer: Trainer, initial: torch.Tensor, fit_conf
         metrics[f"client/layer/{i}/l2_norm_of_pseudo_gradient"] = vals[i]
     planes = [st.flat.params]
     if fit_config.aggregate_momenta:
-        planes += [st.optimizer.exp_avg, st.optimizer.exp_avg_sq]
+        planes += list(st.optimizer.full_moments())
     new_state = ClientState(local_steps_cumulative=client_state.local_steps_cumulative + int(steps_done),
                             local_timestamp={k: v for k, v in st.timestamp.state_dict().items() if isinstance(v, (int, float))},
                             steps_done=int(steps_done))

@@ -38,6 +38,7 @@ from photon_b200.server.server_util import spmd_node_ids, static_assignment
 from photon_b200.strategy.dispatcher import dispatch_strategy
 from photon_b200.train.trainer import Trainer
 from photon_b200.utils.flat import FlatLayout
+from photon_b200.utils.trace import tracer
 
 
 class FederationRuntime:
@@ -151,14 +152,15 @@ class FederationRuntime:
                 opt = tr.state.optimizer
                 if keep_opt and cid in self._opt_states:   # multiplexed clients keep their own moments
                     m, v, step = self._opt_states[cid]
-                    opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)
+                    opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)  # per-rank planes (a slice when the state is sharded)
                     opt.step_count = step
                 elif keep_opt:
                     opt.reset_state()
                 if fc.personalized_layers and cid in self._local_params:
                     tr.state.flat.params.copy_(self._local_params[cid])
-                payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
-                                                         shadow_payload=rb.global_shadow())
+                with tracer().span("client_fit", cat="client", device=True, cid=cid, server_round=server_round):
+                    payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
+                                                             shadow_payload=rb.global_shadow())
                 if keep_opt and len(self.my_clients(sampled)) > 1:
                     self._opt_states[cid] = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
                 if fc.personalized_layers:
@@ -184,7 +186,8 @@ class FederationRuntime:
     def finish_round(self, server_round: int) -> None:
         assert self.round_backend is not None
         t0 = time.time()
-        self.round_backend.finish_round(server_round)
+        with tracer().span("aggregate_server_opt_broadcast", cat="round", device=True, server_round=server_round, transport=self.round_backend.name):
+            self.round_backend.finish_round(server_round)
         self.timings["aggregate_broadcast_host_s"] = time.time() - t0
 
     def abort_round(self) -> None:

@@ -67,6 +67,11 @@ class B200Engine:
         self.precision = precision
         kernels = dict(kernels or {})
         self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
+        if self.attn_mode == "b200" and cfg.d_head != 64:
+            # our tcgen05 backward is d_head-64 only (TMEM budget); forward exists for 128. Use the library attention for
+            # BOTH directions rather than mixing (explicit + logged; GEMM/LN/CE/optimizer stay on our kernels)
+            print(f"[engine] d_head={cfg.d_head}: attention falls back to SDPA (tcgen05 backward covers d_head=64)", flush=True)
+            self.attn_mode = "torch"
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
         self.flat = FlatParams(self.model, device=self.device, grads_storage=grads_storage)

@@ -164,7 +164,8 @@ def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | 
     if grad_mult is not None:
         gm = grad_mult if torch.is_tensor(grad_mult) else torch.tensor(float(grad_mult), device=flat.params.device)
         gm = gm.to(torch.float32).reshape(1)
-    ext().fused_optimizer(flat.params, flat.grads, opt.exp_avg, opt.exp_avg_sq, opt.bf16_shadow, kind, first, float(lr),
+    params, grads, shadow = opt.local_views()   # the whole flat buffer, or this rank's slice when the state is sharded
+    ext().fused_optimizer(params, grads, opt.exp_avg, opt.exp_avg_sq, shadow, kind, first, float(lr),
                           opt.beta1, opt.beta2, opt.eps, float(decay), float(clip), float(step_size), float(inv_sqrt_bc2), gm)
 
 

@@ -108,7 +108,7 @@ class NvlFedRound:
         for rank, dev, lo, hi, i in launches:
             ext.fed_round(ar.ctl_ptrs(), rank, dev, epoch, ar.ptrs("acc"), ar.ptrs("xg"), ar.ptrs("xs") if self.has_shadow else [],
                           self._m[i].data_ptr() if self._m[i] is not None else 0, self._v[i].data_ptr() if self._v[i] is not None else 0,
-                          lo, hi, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
+                          lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
                           hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat))
 
     def round_norms(self, group: Any = None) -> dict[str, float]:

@@ -18,6 +18,31 @@ def server_state_dict(runtime: Any, history: WandbHistory, time_offset: float) -
             "server_steps_cumulative": int(runtime.server_steps_cumulative)}
 
 
+def get_centralized_run_parameters(cfg: Any, layout: Any) -> torch.Tensor | None:
+    """Warm-start the federation from a centralised run's ``{uuid}-{batches}-checkpoint.npz``
+    (``photon.restore_cent_run_uuid`` / ``restore_cent_run_batches``; ref: init_utils.py:43-125 — which is
+    broken there: it dereferences non-existent ``llm_config.fl`` keys; SURVEY App. D #4)."""
+    import glob
+    import os
+
+    ph = cfg["photon"]
+    uuid = ph.get("restore_cent_run_uuid")
+    if not uuid:
+        return None
+    root = ph.get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
+    batches = ph.get("restore_cent_run_batches")
+    pattern = f"{uuid}-{batches if batches is not None else '*'}-checkpoint.npz"
+    cands = sorted(glob.glob(os.path.join(root, "**", pattern), recursive=True) + glob.glob(pattern),
+                   key=lambda p: int(p.rsplit("-", 2)[-2]))
+    if not cands:
+        raise FileNotFoundError(f"no centralised checkpoint matching {pattern} under {root}")
+    from photon_b200.utils.core import load_model_parameters_from_file
+
+    flat = torch.zeros(layout.total, dtype=torch.float32)
+    layout.from_ndarrays(flat, load_model_parameters_from_file(cands[-1])[: len(layout.names)])
+    return flat
+
+
 def initialize_round(runtime: Any, store: CheckpointStore | None, history: WandbHistory) -> int:
     """Zero state, fresh ``ClientState`` per client, initial parameters, zero momenta, round-0
     checkpoint (ref: init_utils.py:128-223). Returns the round to start from (0)."""
@@ -25,6 +50,9 @@ def initialize_round(runtime: Any, store: CheckpointStore | None, history: Wandb
     runtime.client_states = {c: ClientState() for c in range(n)}
     runtime.server_steps_cumulative = 0
     params = runtime.initial_parameters()
+    if runtime.rank == 0:
+        cent = get_centralized_run_parameters(runtime.cfg, runtime.layout)
+        params = cent if cent is not None else params
     broadcast_parameters_to_nodes(runtime, params)
     if store is not None and runtime.rank == 0:
         store.upload_server_checkpoint(str(runtime.cfg["run_uuid"]), 0, layout=runtime.layout, tensors=runtime.state_tensors(),

@@ -29,6 +29,7 @@ from photon_b200.server.fit_utils import fit_round
 from photon_b200.server.init_utils import initialize_round, resume_from_round, server_state_dict
 from photon_b200.server.server_util import spmd_node_ids, wait_for_nodes_to_connect
 from photon_b200.utils.core import wandb_init
+from photon_b200.utils.trace import tracer
 from photon_b200.wandb_history import WandbHistory
 
 
@@ -85,7 +86,8 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
         t_round = time.time()
         node_ids = spmd_node_ids(runtime.group)                    # health check (ref: server_app.py:285)
         sampled = runtime.sample_clients()
-        metrics = fit_round(runtime, server_round, sampled)
+        with tracer().span("fit_round", cat="server", server_round=server_round, clients=str(sampled)):
+            metrics = fit_round(runtime, server_round, sampled)
         metrics["server/n_nodes"] = len(node_ids) // runtime.gpus_per_client
         if runtime.rank == 0:
             history.add_metrics_distributed_fit(server_round, metrics)
@@ -107,6 +109,7 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
         store.cleanup_checkpoints(run_uuid)
     if wandb_run is not None:
         wandb_run.finish()
+    tracer().flush()
     if own:
         runtime.close()
     return history

@@ -8,6 +8,14 @@ model is ONE flat buffer, so a step is one fused multi-tensor kernel on the
 GPU (``csrc/optim.cu``: update + bf16 shadow emit + clip-coefficient read from
 device memory, no host sync) and a handful of vectorised torch ops on CPU.
 The torch path below is also the numerics oracle for the kernel tests.
+
+**Sharded state** (``shard=(lo, hi)`` + ``group``): the in-client replacement for the
+reference's FSDP ``FULL_SHARD`` / ``SHARD_GRAD_OP`` (ref: photon/conf/llm_config/
+mpt-125m.yaml:85-91).  Every rank of the client keeps the two
+moment planes for its contiguous slice of the flat index space only (8 of the 16
+optimizer bytes/param divided by the group size), steps that slice, and the
+updated fp32 master + bf16 compute copy are all-gathered slice by slice over
+NCCL/NVLink.  Parameters themselves stay replicated: ≤7B fits a 180 GB B200.
 """
 from __future__ import annotations
 
@@ -26,16 +34,22 @@ class FlatOptimizer:
 
     def __init__(self, flat: FlatParams, lr: float, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, use_kernel: bool | None = None,
-                 bf16_shadow: torch.Tensor | None = None) -> None:
+                 bf16_shadow: torch.Tensor | None = None, shard: tuple[int, int] | None = None,
+                 group: Any = None, shard_bounds: list[tuple[int, int]] | None = None) -> None:
         self.flat = flat
+        total = flat.params.numel()
+        self.shard = (int(shard[0]), int(shard[1])) if shard is not None else (0, total)
+        self.sharded = self.shard != (0, total)
+        self.group, self.shard_bounds = group, shard_bounds
         self.lr = float(lr)
         self.initial_lr = float(lr)
         self.beta1, self.beta2 = float(betas[0]), float(betas[1])
         self.eps = float(eps)
         self.weight_decay = float(weight_decay)
         self.step_count = 0
-        self.exp_avg = torch.zeros_like(flat.params)
-        self.exp_avg_sq = torch.zeros_like(flat.params)
+        n_local = self.shard[1] - self.shard[0]
+        self.exp_avg = torch.zeros(n_local, dtype=flat.params.dtype, device=flat.params.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
         self.bf16_shadow = bf16_shadow
         if use_kernel is None:
             use_kernel = flat.params.is_cuda
@@ -52,13 +66,60 @@ class FlatOptimizer:
 
             ops.fused_optimizer_step(self, lr, grad_mult)
         else:
-            g = self.flat.grads
+            lo, hi = self.shard
+            g = self.flat.grads[lo:hi]
             if grad_mult is not None:
                 g = g * grad_mult
-            self._torch_step(self.flat.params, g, lr)
+            p = self.flat.params[lo:hi]
+            self._torch_step(p, g, lr)
             if self.bf16_shadow is not None:
-                self.bf16_shadow.copy_(self.flat.params)
+                self.bf16_shadow[lo:hi].copy_(p)
         self.step_count += 1
+        if self.sharded:
+            self.all_gather_params()
+
+    # -- sharded state ---------------------------------------------------------------
+    def local_views(self) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor | None]:
+        """(params, grads, bf16 shadow) restricted to this rank's slice."""
+        lo, hi = self.shard
+        sh = self.bf16_shadow[lo:hi] if self.bf16_shadow is not None else None
+        return self.flat.params[lo:hi], self.flat.grads[lo:hi], sh
+
+    def all_gather_params(self) -> None:
+        """Every rank publishes its freshly stepped slice of the fp32 master (and bf16 copy)."""
+        import torch.distributed as dist
+
+        if not self.shard_bounds:
+            raise RuntimeError("sharded optimizer needs shard_bounds (one (lo, hi) per group rank)")
+        for r, (lo, hi) in enumerate(self.shard_bounds):
+            if hi <= lo:
+                continue
+            src = dist.get_global_rank(self.group, r) if self.group is not None else r
+            dist.broadcast(self.flat.params[lo:hi], src=src, group=self.group)
+            if self.bf16_shadow is not None:
+                dist.broadcast(self.bf16_shadow[lo:hi], src=src, group=self.group)
+
+    def full_moments(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """(exp_avg, exp_avg_sq) over the whole flat index space (gathered when sharded)."""
+        if not self.sharded:
+            return self.exp_avg, self.exp_avg_sq
+        import torch.distributed as dist
+
+        out = []
+        for plane in (self.exp_avg, self.exp_avg_sq):
+            full = torch.zeros_like(self.flat.params)
+            full[self.shard[0]:self.shard[1]].copy_(plane)
+            for r, (lo, hi) in enumerate(self.shard_bounds or []):
+                if hi > lo:
+                    dist.broadcast(full[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                   group=self.group)
+            out.append(full)
+        return out[0], out[1]
+
+    def set_full_moments(self, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor) -> None:
+        lo, hi = self.shard
+        self.exp_avg.copy_(exp_avg[lo:hi])
+        self.exp_avg_sq.copy_(exp_avg_sq[lo:hi])
 
     def _torch_step(self, p: torch.Tensor, g: torch.Tensor, lr: float) -> None:
         raise NotImplementedError
@@ -71,10 +132,17 @@ class FlatOptimizer:
     def state_dict(self) -> dict[str, Any]:
         return {"name": self.name, "step": self.step_count, "lr": self.lr, "initial_lr": self.initial_lr,
                 "betas": (self.beta1, self.beta2), "eps": self.eps, "weight_decay": self.weight_decay,
+                "shard": self.shard,
                 "exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu()}
 
     def load_state_dict(self, sd: dict[str, Any]) -> None:
         self.step_count = int(sd["step"])
+        saved = tuple(sd.get("shard", self.shard))
+        if saved != self.shard:
+            if saved == (0, self.flat.params.numel()):  # full-state checkpoint into a sharded optimizer
+                self.set_full_moments(sd["exp_avg"].to(self.exp_avg.device), sd["exp_avg_sq"].to(self.exp_avg.device))
+                return
+            raise ValueError(f"optimizer checkpoint holds shard {saved}, this rank owns {self.shard}")
         self.exp_avg.copy_(sd["exp_avg"].to(self.exp_avg.device))
         self.exp_avg_sq.copy_(sd["exp_avg_sq"].to(self.exp_avg_sq.device))
 

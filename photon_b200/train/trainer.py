@@ -88,6 +88,13 @@ class GradScaler:
                 self.scale *= 2.0
 
 
+def shard_bounds(total: int, world_size: int, align: int = 256) -> list[tuple[int, int]]:
+    """Contiguous, ``align``-element-aligned [lo, hi) slices of the flat index space, one per rank."""
+    per = -(-total // world_size)
+    per = -(-per // align) * align
+    return [(min(total, r * per), min(total, (r + 1) * per)) for r in range(world_size)]
+
+
 def _is_oom(e: BaseException) -> bool:
     return isinstance(e, torch.cuda.OutOfMemoryError) or "out of memory" in str(e).lower()
 
@@ -107,7 +114,7 @@ class Trainer:
                  seed: int = 17, run_name: str = "run", use_unigram_metrics: bool = False,
                  unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
-                 backend: Any = None) -> None:
+                 backend: Any = None, shard_optimizer_state: bool = False) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -151,7 +158,12 @@ class Trainer:
                                       grads_storage=getattr(grad_comm, "grads", None))
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
-        opt = build_optimizer(optimizer_cfg, be.flat, use_kernel=use_kernel, bf16_shadow=shadow)
+        shard_kw: dict[str, Any] = {}
+        if shard_optimizer_state and self.world_size > 1:
+            # ZeRO-style state sharding inside the client (the reference's fsdp_config FULL_SHARD / SHARD_GRAD_OP)
+            bounds = shard_bounds(be.flat.params.numel(), self.world_size)
+            shard_kw = dict(shard=bounds[self.rank], shard_bounds=bounds, group=process_group)
+        opt = build_optimizer(optimizer_cfg, be.flat, use_kernel=use_kernel, bf16_shadow=shadow, **shard_kw)
         sched = build_scheduler(scheduler_cfg, max_duration=self.max_duration, **geom)
         self.state = TrainerState(backend=be, flat=be.flat, optimizer=opt, scheduler=sched, run_name=run_name,
                                   train_metrics=build_metrics(use_unigram_metrics),

@@ -36,6 +36,31 @@ def test_gemm_kk_bias(M, N, K):
     _close(out, ref, 2e-2, 2e-2, "gemm K/K + bias")
 
 
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("layout", ["kk", "kmn", "mnmn"])
+def test_gemm_cta_pair_matches_single_cta(cluster, layout):
+    """cta_group::2 (CTA pair, 256-row UMMA) and cta_group::1 produce the same numbers for every operand layout,
+    including odd tile counts (the pair's second CTA then runs out of range) and split-K accumulation."""
+    from photon_b200 import ops
+
+    M, N, K = 640, 520, 1088          # 5 M-tiles (odd), N tail, K tail
+    if layout == "kk":
+        a, b = _rand(M, K), _rand(N, K, scale=0.05)
+        out = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+        ops.gemm(a, b, out, cluster=cluster)
+        _close(out, a.float() @ b.float().t(), 2e-2, 3e-2, f"K/K cluster={cluster}")
+    elif layout == "kmn":
+        a, b = _rand(M, K), _rand(K, N, scale=0.05)
+        out = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+        ops.gemm(a, b, out, b_mn=True, cluster=cluster)
+        _close(out, a.float() @ b.float(), 2e-2, 3e-2, f"K/MN cluster={cluster}")
+    else:
+        a, b = _rand(K * 4, M), _rand(K * 4, N)     # long K -> split-K path
+        out = torch.zeros(M, N, device=_dev(), dtype=torch.float32)
+        ops.gemm(a, b, out, a_mn=True, b_mn=True, epi=ops.EPI_F32, accumulate=True, cluster=cluster)
+        _close(out, a.float().t() @ b.float(), 1e-2, 0.2, f"MN/MN cluster={cluster}")
+
+
 def test_gemm_residual_and_gelu_dual():
     from photon_b200 import ops
 
