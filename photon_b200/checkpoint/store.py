@@ -126,6 +126,30 @@ class CheckpointStore:
                 if s.exists():
                     shutil.copytree(s, self.client_dir(new_uuid, cid), dirs_exist_ok=True)
 
+    def import_checkpoints(self, cfg: Any, state_keys: Sequence[str]) -> int | None:
+        """Seed THIS run (``cfg.run_uuid``) from ``photon.restore_run_uuid``: resolve the round to restore
+        (``photon.resume_round``; -1 = newest complete), copy its server checkpoint (+ client checkpoints when
+        ``photon.copy_client_checkpoints``) under the new run id; no-op if this run already has checkpoints
+        (ref: server/s3_utils.py:275-345). Returns the restored round (also written back to the config)."""
+        ph = cfg["photon"]
+        src, dst = ph.get("restore_run_uuid"), cfg.get("run_uuid")
+        if not src or not dst:
+            raise ValueError("import_checkpoints needs both run_uuid and photon.restore_run_uuid")
+        rnd = self.interpret_resume_round(str(src), ph.get("resume_round", -1), state_keys)
+        if rnd is None or self.obtain_sorted_rounds(str(dst), state_keys):
+            return None
+        self.copy_old_checkpoints_to_new_run(str(src), str(dst), rnd, state_keys=state_keys,
+                                             copy_client_checkpoints=bool(ph.get("copy_client_checkpoints", True)),
+                                             client_ids=range(int(cfg["fl"]["n_total_clients"])))
+        ph["resume_round"] = rnd
+        return rnd
+
+    def obtain_sorted_runs(self) -> list[str]:
+        """Run ids in the bucket that hold at least one server round, oldest first by modification time
+        (ref: server/s3_utils.py:1261-1318 sorts run folders to pick what to garbage-collect)."""
+        runs = [p for p in self.bucket.iterdir() if p.is_dir() and (p / "server").is_dir()] if self.bucket.exists() else []
+        return [p.name for p in sorted(runs, key=lambda p: p.stat().st_mtime)]
+
     # -- cleanup ------------------------------------------------------------------------
     def delete_rounds(self, run_uuid: str, keep_last: int = 0) -> None:
         base = self.server_dir(run_uuid)

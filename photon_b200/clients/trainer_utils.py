@@ -127,7 +127,8 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  world_size=world_size, process_group=process_group, grad_comm=grad_comm, kernels=kernels, seed=seed,
                  run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,
                  frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend,
-                 shard_optimizer_state=shard_state)
+                 shard_optimizer_state=shard_state,
+                 activation_checkpointing=bool(fsdp) and bool(dict(fsdp).get("activation_checkpointing", False)))
     return tr, t
 
 

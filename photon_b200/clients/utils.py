@@ -213,3 +213,24 @@ def get_initial_parameters(cfg: Any) -> tuple[list[np.ndarray], FlatLayout]:
 
 def pseudo_gradient_norm(initial: torch.Tensor, final: torch.Tensor) -> float:
     return float(math.sqrt(float(((initial - final).double() ** 2).sum())))
+
+
+def streaming_shms_clean_up(prefixes: Sequence[str] = ("photon_", "pb200_")) -> int:
+    """Unlink stale POSIX shared-memory segments left by crashed workers / loaders and collect
+    garbage (ref: clients/utils.py:655-673, which leans on streaming's stale-shm sweep)."""
+    import gc
+    import os
+
+    removed = 0
+    try:
+        names = os.listdir("/dev/shm")
+    except OSError:
+        names = []
+    from photon_b200.shm.utils import unlink_quietly
+
+    for n in names:
+        if n.startswith(tuple(prefixes)):
+            unlink_quietly(n)
+            removed += 1
+    gc.collect()
+    return removed

@@ -51,7 +51,8 @@ class B200Engine:
     def __init__(self, cfg: MPTConfig, device: torch.device | str = "cuda", precision: str = "amp_bf16",
                  kernels: dict[str, Any] | None = None, seed: int | None = 17, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
-                 lm_head_chunk: int = 18944, grads_storage: torch.Tensor | None = None) -> None:
+                 lm_head_chunk: int = 18944, grads_storage: torch.Tensor | None = None,
+                 activation_checkpointing: bool = False) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -78,6 +79,9 @@ class B200Engine:
         self.bf16_params = torch.zeros(self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.lm_head_chunk = int(lm_head_chunk)
+        # keep only the block inputs h[i]; every block's internals are recomputed right before its backward
+        # (fsdp_config.activation_checkpointing, ref: conf/llm_config/mpt-1b.yaml:88): 16·T·d·L bytes of bf16 -> 16·T·d
+        self.activation_checkpointing = bool(activation_checkpointing)
         self.collect_activation_stats = False
         self.activation_stats: dict[str, float] = {}
         self.launches_per_microbatch = 0
@@ -128,7 +132,10 @@ class B200Engine:
         bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
         ws: dict[str, Any] = {"h": [bf(T, d) for _ in range(L + 1)], "layers": []}
-        for _ in range(L):
+        for i in range(L):
+            if self.activation_checkpointing and i > 0:
+                ws["layers"].append(ws["layers"][0])  # ONE set of block internals shared by all layers
+                continue
             ws["layers"].append({"ln1": bf(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d),
                                  "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": bf(T, d), "m2": f32(T), "r2": f32(T),
                                  "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
@@ -164,19 +171,24 @@ class B200Engine:
             (g,) = torch.autograd.grad(o, qkv, ws["dattn"].view(b, S, c.n_heads, c.d_head).transpose(1, 2))
         ws["dqkv"].view(b, S, 3, c.n_heads, c.d_head).copy_(g)
 
+    def _block_fwd(self, i: int, ws: dict[str, Any], b: int, S: int) -> None:
+        """h[i] -> h[i+1]; the block internals land in ws["layers"][i] (also the recompute step under checkpointing)."""
+        c, h, w, lw = self.cfg, ws["h"], self.layers[i], ws["layers"][i]
+        ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
+        ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
+        self._attention_fwd(lw, b, S)
+        ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
+        ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)
+        ops.linear_gelu_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])
+        ops.linear_fwd(lw["u"], w.wdown, w.bdown, h[i + 1], residual=lw["hmid"])
+
     def _forward(self, ids: torch.Tensor, ws: dict[str, Any]) -> None:
         c = self.cfg
         b, S = ids.shape
         h = ws["h"]
         ops.embed_fwd(ids.reshape(-1), self.wte16, self.wpe16, h[0], S)
-        for i, (w, lw) in enumerate(zip(self.layers, ws["layers"])):
-            ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
-            ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
-            self._attention_fwd(lw, b, S)
-            ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
-            ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)
-            ops.linear_gelu_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])
-            ops.linear_fwd(lw["u"], w.wdown, w.bdown, h[i + 1], residual=lw["hmid"])
+        for i in range(c.n_layers):
+            self._block_fwd(i, ws, b, S)
             if self.collect_activation_stats:
                 x = h[i + 1][:S].float()
                 self.activation_stats[f"l2_norm/block_{i}"] = float(x.norm(dim=-1).mean())
@@ -205,6 +217,8 @@ class B200Engine:
         ops.layernorm_bwd(ws["dlnf"], h[c.n_layers], self.gf, ws["mf"], ws["rf"], None, dh, self.d_gf, self.d_bf)
         for i in range(c.n_layers - 1, -1, -1):
             w, lw = self.layers[i], ws["layers"][i]
+            if self.activation_checkpointing and i < c.n_layers - 1:
+                self._block_fwd(i, ws, b, S)   # recompute (the shared buffers still hold the LAST block after the forward)
             # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
             ops.col_sum(dh, w.d_bdown)
             ops.linear_wgrad(dh, lw["u"], w.d_wdown)

@@ -191,6 +191,7 @@ class MPTForCausalLM(nn.Module):
     def __init__(self, cfg: MPTConfig, device: Any = None, init: bool = True, seed: int | None = None) -> None:
         super().__init__()
         self.cfg = cfg
+        self.activation_checkpointing = False   # fsdp_config.activation_checkpointing (ref: conf/llm_config/mpt-1b.yaml:88)
         with torch.device(device or "cpu"):
             self.transformer = MPTTransformer(cfg)
         if init:
@@ -258,7 +259,12 @@ class MPTForCausalLM(nn.Module):
             x = x + t.wpe(torch.arange(S, device=input_ids.device))[None]
         rope, alibi = self._aux(S, input_ids.device)
         for blk in t.blocks:
-            x = blk(x, rope, alibi)
+            if self.activation_checkpointing and self.training and torch.is_grad_enabled():
+                from torch.utils.checkpoint import checkpoint
+
+                x = checkpoint(blk, x, rope, alibi, use_reentrant=False)   # keep only block inputs, recompute in backward
+            else:
+                x = blk(x, rope, alibi)
         return t.norm_f(x).to(x.dtype)
 
     def forward(self, input_ids: torch.Tensor) -> torch.Tensor:

@@ -58,12 +58,7 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
     resume = None
     if store is not None:
         if ph.get("restore_run_uuid") and runtime.rank == 0:
-            src = str(ph["restore_run_uuid"])
-            r = store.interpret_resume_round(src, ph.get("resume_round", -1), runtime.strategy.state_keys)
-            if r is not None and not store.obtain_sorted_rounds(run_uuid, runtime.strategy.state_keys):
-                store.copy_old_checkpoints_to_new_run(src, run_uuid, r, state_keys=runtime.strategy.state_keys,
-                                                      copy_client_checkpoints=bool(ph.get("copy_client_checkpoints", True)),
-                                                      client_ids=range(int(fl["n_total_clients"])))
+            store.import_checkpoints(cfg, runtime.strategy.state_keys)
         if runtime.world_size > 1:
             dist.barrier(group=runtime.group)
         resume = store.interpret_resume_round(run_uuid, ph.get("resume_round"), runtime.strategy.state_keys)

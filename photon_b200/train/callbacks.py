@@ -279,6 +279,67 @@ _CALLBACKS = {"speed_monitor": SpeedMonitor, "lr_monitor": LRMonitor, "memory_mo
               "activation_monitor_full_model": ActivationMonitorFullModel}
 
 
+class MemorySnapshot(Callback):
+    """Dump ``torch.cuda.memory._snapshot()`` pickles for a window of batches (Composer's
+    ``memory_snapshot`` callback; viewable at pytorch.org/memory_viz)."""
+
+    def __init__(self, skip_batches: int = 1, interval: str | int = "3ba", max_entries: int = 100000,
+                 folder: str = "memory_snapshots") -> None:
+        self.skip, self.interval = int(skip_batches), max(1, Time.parse(interval).to_batches())
+        self.max_entries, self.folder = int(max_entries), folder
+        self._recording = False
+
+    def batch_start(self, tr: "Trainer") -> None:
+        if tr.device.type != "cuda":
+            return
+        b = tr.state.timestamp.batch - tr.fit_start_batch
+        if b == self.skip and not self._recording:
+            torch.cuda.memory._record_memory_history(max_entries=self.max_entries)
+            self._recording = True
+
+    def batch_end(self, tr: "Trainer") -> None:
+        if not self._recording:
+            return
+        b = tr.state.timestamp.batch - tr.fit_start_batch
+        if b >= self.skip + self.interval:
+            self.dump(tr, f"rank{tr.rank}_ba{tr.state.timestamp.batch}")
+            torch.cuda.memory._record_memory_history(enabled=None)
+            self._recording = False
+
+    def dump(self, tr: "Trainer", tag: str) -> Path:
+        out = Path(tr.save_folder or ".") / self.folder
+        out.mkdir(parents=True, exist_ok=True)
+        path = out / f"{tag}_memory_snapshot.pickle"
+        torch.cuda.memory._dump_snapshot(str(path))
+        return path
+
+
+class OOMObserver(Callback):
+    """Record allocator history from the first batch and dump it when the allocator raises
+    an out-of-memory error (Composer's ``oom_observer``)."""
+
+    def __init__(self, max_entries: int = 100000, folder: str = "oom_snapshots") -> None:
+        self.max_entries, self.folder = int(max_entries), folder
+        self.dumped: list[Path] = []
+
+    def fit_start(self, tr: "Trainer") -> None:
+        if tr.device.type != "cuda":
+            return
+        torch.cuda.memory._record_memory_history(max_entries=self.max_entries)
+        out = Path(tr.save_folder or ".") / self.folder
+
+        def observer(device: int, alloc: int, device_alloc: int, device_free: int) -> None:
+            out.mkdir(parents=True, exist_ok=True)
+            path = out / f"rank{tr.rank}_oom_memory_snapshot.pickle"
+            torch.cuda.memory._dump_snapshot(str(path))
+            self.dumped.append(path)
+
+        torch._C._cuda_attach_out_of_memory_observer(observer)
+
+
+_CALLBACKS.update({"memory_snapshot": MemorySnapshot, "oom_observer": OOMObserver})
+
+
 def build_callbacks(cfg: dict[str, Any] | None) -> list[Callback]:
     out: list[Callback] = []
     for name, kw in (cfg or {}).items():

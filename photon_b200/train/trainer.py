@@ -114,7 +114,7 @@ class Trainer:
                  seed: int = 17, run_name: str = "run", use_unigram_metrics: bool = False,
                  unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
-                 backend: Any = None, shard_optimizer_state: bool = False) -> None:
+                 backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -155,7 +155,8 @@ class Trainer:
         be = backend or build_backend(self.model_cfg, self.device, precision, kernels, seed=seed,
                                       frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers,
                                       unigram_log_probs=unigram_log_probs,
-                                      grads_storage=getattr(grad_comm, "grads", None))
+                                      grads_storage=getattr(grad_comm, "grads", None),
+                                      activation_checkpointing=activation_checkpointing)
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
         shard_kw: dict[str, Any] = {}

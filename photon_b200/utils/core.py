@@ -126,3 +126,97 @@ def wandb_init(enabled: bool, **kwargs: Any) -> Any:
     except Exception as e:  # noqa: BLE001
         print(f"[wandb] unavailable ({e}); metrics stay in the History object")
         return None
+
+
+# ------------------------------------------------------------------ freezing / unigram / object stores
+def freeze_blocks(model: torch.nn.Module, frozen_layers: Sequence[str] | None = None,
+                  unfrozen_layers: Sequence[str] | None = None) -> list[str]:
+    """``requires_grad=False`` for every parameter matched by ``frozen_layers`` — or, when
+    ``unfrozen_layers`` is given, for everything NOT matched by it (ref: photon/utils.py:322-387).
+    Returns the frozen parameter names."""
+    from photon_b200.train.backend import apply_freeze
+
+    return apply_freeze(model, list(frozen_layers or []) or None, list(unfrozen_layers or []) or None)
+
+
+def add_unigram_metrics(trainer: Any, unigram_freq: dict[int, int] | dict[str, int]) -> None:
+    """Attach the four unigram-normalised metrics to a live trainer (train + every eval label)
+    (ref: clients/trainer_utils.py:278-327)."""
+    from photon_b200.metrics.language import build_metrics, unigram_log_probs
+
+    st = trainer.state
+    logp = unigram_log_probs({int(k): int(v) for k, v in unigram_freq.items()}, trainer.model_cfg.vocab_size)
+    st.backend.unigram_log_probs = logp.to(st.flat.params.device)
+    st.train_metrics = build_metrics(True)
+    st.eval_metrics = {lbl: build_metrics(True) for lbl in st.eval_metrics}
+
+
+class RemoteUploaderDownloader:
+    """Object-store façade with the call surface the reference gets from Composer's
+    ``RemoteUploaderDownloader`` (ref: photon/utils.py:955-1014): ``upload_file`` /
+    ``download_file`` / ``list_objects`` / ``delete_object`` with retries. Buckets are directories
+    under ``root`` (this image has no network; an ``s3://`` endpoint would slot in behind the same
+    four calls)."""
+
+    def __init__(self, root: str | os.PathLike, bucket_name: str, prefix: str = "", num_attempts: int = 3) -> None:
+        from pathlib import Path
+
+        self.base = Path(root) / bucket_name / prefix
+        self.base.mkdir(parents=True, exist_ok=True)
+        self.num_attempts = max(1, int(num_attempts))
+        self.run_name: str | None = None
+
+    def init(self, run_name: str | None = None) -> None:
+        self.run_name = run_name
+
+    def _retry(self, fn: Any) -> Any:
+        import time
+
+        err: BaseException | None = None
+        for i in range(self.num_attempts):
+            try:
+                return fn()
+            except OSError as e:  # transient FS errors
+                err = e
+                time.sleep(0.05 * (i + 1))
+        raise RuntimeError(f"object store operation failed after {self.num_attempts} attempts") from err
+
+    def upload_file(self, remote_file_name: str, file_path: str | os.PathLike, overwrite: bool = True) -> None:
+        import shutil
+
+        dst = self.base / remote_file_name
+        if dst.exists() and not overwrite:
+            raise FileExistsError(str(dst))
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        tmp = dst.with_suffix(dst.suffix + ".part")
+        self._retry(lambda: (shutil.copyfile(file_path, tmp), os.replace(tmp, dst)))  # readers never see partial objects
+
+    def download_file(self, remote_file_name: str, destination: str | os.PathLike, overwrite: bool = True) -> None:
+        import shutil
+
+        if os.path.exists(destination) and not overwrite:
+            raise FileExistsError(str(destination))
+        os.makedirs(os.path.dirname(os.path.abspath(destination)), exist_ok=True)
+        self._retry(lambda: shutil.copyfile(self.base / remote_file_name, destination))
+
+    def list_objects(self, prefix: str = "") -> list[str]:
+        root = self.base / prefix
+        if not root.exists():
+            return []
+        return sorted(str(p.relative_to(self.base)) for p in root.rglob("*") if p.is_file() and not p.name.endswith(".part"))
+
+    def delete_object(self, remote_file_name: str) -> None:
+        (self.base / remote_file_name).unlink(missing_ok=True)
+
+    def close(self) -> None:
+        pass
+
+
+def create_remote_up_down(bucket_name: str, prefix: str, run_uuid: str | None, num_attempts: int,
+                          client_config: dict[str, Any] | None = None, *, root: str | os.PathLike | None = None,
+                          **_unused: Any) -> RemoteUploaderDownloader:
+    """(ref: photon/utils.py:955-1014) ``root`` defaults to ``$PHOTON_SAVE_PATH`` (or ./runs)."""
+    del client_config
+    r = RemoteUploaderDownloader(root or os.environ.get("PHOTON_SAVE_PATH", "runs"), bucket_name, prefix, num_attempts)
+    r.init(run_name=run_uuid)
+    return r
