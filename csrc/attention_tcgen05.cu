@@ -37,64 +37,90 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 // ======================================================================================= forward
+// Persistent kernel: one CTA per SM walks a list of (batch*head, query tile) work items; TMA, MMA and softmax pipelines
+// run ACROSS item boundaries (the per-CTA prologue/epilogue of a one-tile-per-CTA grid measured 3.9 us against 0.89 us per
+// KV tile, i.e. a third of the run time at S = 2048).
+//   warp 8  : TMA producer  — Q (double-buffered), K ring, V ring
+//   warp 9  : MMA issuer    — S_j = Q K_j^T (SS) into S buffer (j & 1); O_g += P_j V_j (TS, P read from TMEM)
+//   warps 0-3 (group 0) / 4-7 (group 1): softmax — group g owns the KV tiles with j & 1 == g, its own S buffer and its
+//             own O accumulator with its own running (max, sum): two independent online-softmax streams that never
+//             synchronise per tile; one group's exp2 work overlaps the other's MMA round trip. The two partial results
+//             are merged once per item (log-sum-exp combine) in the epilogue.
 template <int DH>
 struct FwdCfg {
   static constexpr int CH = DH / 64;              // 64-column swizzle chunks per tile
   static constexpr int TILE = 128 * 128 * CH;     // bytes of one [128 x DH] bf16 tile
-  static constexpr int STAGES = (DH == 64) ? 4 : 2;
-  static constexpr int SMEM = TILE * (1 + 2 * STAGES) + 256 + 2048 + 1024;   // tiles + barriers + row-max exchange + align
-  // two S buffers (128 fp32 columns each); P_j (packed bf16, 64 columns) aliases the head of S_j once the row
-  // threads hold S_j in registers; O after them
+  static constexpr int QBUF = (DH == 64) ? 2 : 1;
+  static constexpr int KST = (DH == 64) ? 4 : 3;  // K ring depth (S_{j+2} is issued right after P V_j: >= 3)
+  static constexpr int VST = (DH == 64) ? 4 : 2;
+  static constexpr int OSETS = (DH == 64) ? 2 : 1;  // O accumulator sets (item parity) x 2 groups
+  static constexpr int AUX = 4096;                // barriers (512 B) + per-row (m, l) exchange (2 parities x 2 groups x 128 x 8 B)
+  static constexpr int SMEM = TILE * (QBUF + KST + VST) + AUX + 1024;
+  // two S buffers (128 fp32 columns each); P_j (packed bf16, 64 columns) aliases the head of S_j once the row threads hold
+  // S_j in registers; O accumulators after them
   static constexpr int COL_S = 0, COL_O = 256;
   static constexpr int TMEM_COLS = 512;
+  static_assert(COL_O + OSETS * 2 * DH <= 512, "TMEM budget");
+  static_assert(SMEM <= 232448, "smem budget");
+};
+
+// work item k -> (bh, qt). The q-tiles of one (batch, head) are adjacent in k so that the CTAs working on them at the same
+// time share K/V through L2; the rotation by bh spreads the causal tile weights evenly over the CTAs of a static
+// round-robin schedule (grid % n_qt would otherwise pin every CTA to a few tile sizes).
+struct FwdSched {
+  int n_qt, n_items, cyc_rounds, grid;
+  __device__ __forceinline__ void decode(int k, int& bh, int& qt) const {
+    bh = k / n_qt;
+    const int slot = k - bh * n_qt;
+    const int shift = int((long long)bh * n_qt / grid) / cyc_rounds;
+    qt = n_qt - 1 - (slot + shift) % n_qt;
+  }
 };
 
 template <int DH>
-// 320 threads: warps 0-7 = softmax (warp w and w+4 own the same 32 query rows / TMEM lanes and split the 128 key
-// columns 64/64, so every SMSP has two softmax warps to interleave; row max / row sum halves meet through smem),
-// warp 8 = TMA producer, warp 9 = MMA issuer + TMEM allocator.
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
-                float scale, int causal) {
+                float scale, int causal, const FwdSched sched) {
   using C = FwdCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::TILE;                   // [STAGES]
-  uint8_t* sV = sK + C::STAGES * C::TILE;       // [STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::STAGES * C::TILE);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;                  // [STAGES]
-  uint64_t* v_full = bars + 5;                  // [STAGES]
-  uint64_t* kv_empty = bars + 9;                // [STAGES]
-  uint64_t* s_full = bars + 13;                 // [2]
-  uint64_t* p_ready = bars + 15;                // [2]
-  uint64_t* o_done = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* xch = reinterpret_cast<float*>(bars + 20);   // [2 tiles][2 halves][128 rows] row-max exchange (+ reused for the final row sums)
+  uint8_t* sQ = smem;                             // [QBUF]
+  uint8_t* sK = sQ + C::QBUF * C::TILE;           // [KST]
+  uint8_t* sV = sK + C::KST * C::TILE;            // [VST]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::VST * C::TILE);
+  uint64_t* q_full = bars;                        // [2]
+  uint64_t* q_empty = bars + 2;                   // [2]
+  uint64_t* k_full = bars + 4;                    // [4]
+  uint64_t* k_empty = bars + 8;                   // [4]
+  uint64_t* v_full = bars + 12;                   // [4]
+  uint64_t* v_empty = bars + 16;                  // [4]
+  uint64_t* s_full = bars + 20;                   // [2]  per group
+  uint64_t* p_ready = bars + 22;                  // [2]  per group (128 arrivals)
+  uint64_t* o_final = bars + 24;                  // all P V of an item retired
+  uint64_t* o_free = bars + 25;                   // [2]  O set drained by the epilogue (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  float2* xch = reinterpret_cast<float2*>(bars + 64);  // [2 item parities][2 groups][128 rows] (m, l)
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int n_qt = S / BQ;
-  const int qt = n_qt - 1 - blockIdx.x;  // heaviest (longest causal prefix) tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
   const int d_model = H * DH;
-  const int n_kv = causal ? qt + 1 : S / BKV;
-  const int row0 = b * S + qt * BQ;
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 256);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&o_free[s], 256);
     }
-    mbar_init(o_done, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(o_final, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -106,175 +132,278 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, C::TILE);
+      int it = 0, kc = 0, vc = 0;
+      for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
+        int bh, qt;
+        sched.decode(k, bh, qt);
+        const int b = bh / H, h = bh - b * H;
+        const int n_kv = causal ? qt + 1 : S / BKV;
+        const int qb = it % C::QBUF;
+        mbar_wait(&q_empty[qb], ((it / C::QBUF) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], C::TILE);
 #pragma unroll
-      for (int c = 0; c < C::CH; ++c) tma_load_2d(sQ + c * 16384, &tmQKV, q_full, h * DH + c * 64, row0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % C::STAGES;
-        mbar_wait(&kv_empty[st], ((j / C::STAGES) & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], C::TILE);
+        for (int c = 0; c < C::CH; ++c) tma_load_2d(sQ + qb * C::TILE + c * 16384, &tmQKV, &q_full[qb], h * DH + c * 64, b * S + qt * BQ);
+        for (int j = 0; j < n_kv; ++j) {
+          const int ks = kc % C::KST;
+          mbar_wait(&k_empty[ks], ((kc / C::KST) & 1) ^ 1);
+          mbar_expect_tx(&k_full[ks], C::TILE);
 #pragma unroll
-        for (int c = 0; c < C::CH; ++c)
-          tma_load_2d(sK + st * C::TILE + c * 16384, &tmQKV, &k_full[st], d_model + h * DH + c * 64, b * S + j * BKV);
-        mbar_expect_tx(&v_full[st], C::TILE);
+          for (int c = 0; c < C::CH; ++c)
+            tma_load_2d(sK + ks * C::TILE + c * 16384, &tmQKV, &k_full[ks], d_model + h * DH + c * 64, b * S + j * BKV);
+          ++kc;
+          const int vs = vc % C::VST;
+          mbar_wait(&v_empty[vs], ((vc / C::VST) & 1) ^ 1);
+          mbar_expect_tx(&v_full[vs], C::TILE);
 #pragma unroll
-        for (int c = 0; c < C::CH; ++c)
-          tma_load_2d(sV + st * C::TILE + c * 16384, &tmQKV, &v_full[st], 2 * d_model + h * DH + c * 64, b * S + j * BKV);
+          for (int c = 0; c < C::CH; ++c)
+            tma_load_2d(sV + vs * C::TILE + c * 16384, &tmQKV, &v_full[vs], 2 * d_model + h * DH + c * 64, b * S + j * BKV);
+          ++vc;
+        }
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks this loop in lock-step (waits included) and one elected lane issues each tcgen05
+    // instruction: addresses, descriptors and counters are then warp-uniform, live in uniform registers and feed
+    // UTCHMMA directly. With `if (lane == 0)` around the loop every operand took a ~20-instruction elect/broadcast
+    // round trip (12 MMAs x ~100 clk per KV tile — more than the tensor pipe needs for the tile).
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH, 0, 1);
-      const uint32_t q_base = smem_u32(sQ);
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer (j & 1)
-        const int st = j % C::STAGES;
-        const uint32_t k_base = smem_u32(sK + st * C::TILE);
-        mbar_wait(&k_full[st], (j / C::STAGES) & 1);
-        tc_fence_after();
+      int it = 0, kc = 0, vc = 0;
+      int pc0 = 0, pc1 = 0;  // P tiles consumed per group (p_ready parity)
+      for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
+        int bh, qt;
+        sched.decode(k, bh, qt);
+        const int n_kv = causal ? qt + 1 : S / BKV;
+        const int qb = it % C::QBUF;
+        const uint32_t q_base = smem_u32(sQ + qb * C::TILE);
+        const int oset = (C::OSETS == 2) ? (it & 1) : 0;
+        mbar_wait(&q_full[qb], (it / C::QBUF) & 1);
+        auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer (j & 1)
+          const int ks = kc % C::KST;
+          const uint32_t k_base = smem_u32(sK + ks * C::TILE);
+          mbar_wait(&k_full[ks], (kc / C::KST) & 1);
+          tc_fence_after();
+          const uint32_t d_col = tmem + C::COL_S + (j & 1) * 128;
+          const uint64_t qd = make_smem_desc_sw128(q_base, 16, 1024), kd = make_smem_desc_sw128(k_base, 16, 1024);
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          tc_mma_f16_ss(tmem + C::COL_S + (j & 1) * 128, make_smem_desc_sw128(q_base + off, 16, 1024),
-                        make_smem_desc_sw128(k_base + off, 16, 1024), idesc_s, kk != 0);
-        }
-        tc_commit(&s_full[j & 1]);
-      };
-      issue_s(0);
-      for (int j = 0; j < n_kv; ++j) {
-        // S_{j+1} is issued BEFORE waiting for softmax_j: it runs on the tensor pipe while the row threads work.
-        // Buffer (j+1)&1 is free: softmax_{j-1} finished reading S_{j-1} (p_ready) and P_{j-1} is consumed by
-        // P V_{j-1}, which was issued earlier on the in-order tensor pipe.
-        if (j + 1 < n_kv) issue_s(j + 1);
-        const int st = j % C::STAGES;
-        const uint32_t v_base = smem_u32(sV + st * C::TILE);
-        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-        mbar_wait(&v_full[st], (j / C::STAGES) & 1);
+          for (int kk = 0; kk < DH / 16; ++kk) {
+            const uint64_t off = uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);  // descriptor address field is addr >> 4
+            if (elect_one()) tc_mma_f16_ss(d_col, qd + off, kd + off, idesc_s, kk != 0);
+          }
+          if (elect_one()) {
+            tc_commit(&s_full[j & 1]);
+            tc_commit(&k_empty[ks]);
+            if (j == n_kv - 1) tc_commit(&q_empty[qb]);  // last read of this Q buffer
+          }
+          __syncwarp();
+          ++kc;
+        };
+        // S buffers are free here: the previous item's P tiles were consumed by P V MMAs issued earlier (in-order pipe)
+        issue_s(0);
+        if (n_kv > 1) issue_s(1);
+        // the O set of this item parity must have been drained by the epilogue two (one) items ago
+        mbar_wait(&o_free[oset], (((C::OSETS == 2) ? (it >> 1) : it) & 1) ^ 1);
         tc_fence_after();
+        for (int j = 0; j < n_kv; ++j) {
+          const int g = j & 1;
+          const int vs = vc % C::VST;
+          const uint32_t v_base = smem_u32(sV + vs * C::TILE);
+          if (g == 0) {
+            mbar_wait(&p_ready[0], pc0 & 1);
+            ++pc0;
+          } else {
+            mbar_wait(&p_ready[1], pc1 & 1);
+            ++pc1;
+          }
+          mbar_wait(&v_full[vs], (vc / C::VST) & 1);
+          tc_fence_after();
+          const uint32_t o_col = tmem + C::COL_O + (oset * 2 + g) * DH;
+          const uint32_t p_col = tmem + C::COL_S + g * 128;
+          const uint64_t vd = make_smem_desc_sw128(v_base, 16384, 1024);
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          tc_mma_f16_ts(tmem + C::COL_O, tmem + C::COL_S + (j & 1) * 128 + kk * 8, make_smem_desc_sw128(v_base + kk * 2048, 16384, 1024),
-                        idesc_o, (j | kk) != 0);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            if (elect_one()) tc_mma_f16_ts(o_col, p_col + kk * 8, vd + uint64_t((kk * 2048) >> 4), idesc_o, (j >= 2 || kk != 0) ? 1u : 0u);
+          }
+          if (elect_one()) {
+            tc_commit(&v_empty[vs]);
+            if (j == n_kv - 1) tc_commit(o_final);
+          }
+          __syncwarp();
+          ++vc;
+          // S_{j+2} reuses buffer g: P_j is consumed by the MMAs just issued (in-order), group g has released S_j (p_ready)
+          if (j + 2 < n_kv) issue_s(j + 2);
         }
-        tc_commit(&kv_empty[st]);
-        tc_commit(o_done);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax rows (warps 0..7)
-    const int half = warp >> 2;                         // which 64 key columns of the row this thread owns
+    const int g = warp >> 2;                            // group: KV tiles with j & 1 == g
     const int row = (warp & 3) * 32 + lane;             // query row inside the tile == TMEM lane
     const uint32_t tl = tmem + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t ts = tl + C::COL_S + g * 128;
     const float sc = scale * LOG2E;
-    float m = -INFINITY, l = 0.f;                        // l = partial row sum over this thread's columns
-    auto tile = [&](int j, auto diag_tag) {
-      constexpr bool DIAG = decltype(diag_tag)::value;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t ts = tl + C::COL_S + (j & 1) * 128;
-      uint32_t r0[32], r1[32];                           // this thread's 64 S values, read from TMEM once
-      tmem_ld_32x32(ts + half * 64, r0);
-      tmem_ld_32x32(ts + half * 64 + 32, r1);
-      tmem_ld_wait();
-      if (DIAG) {  // causal mask: columns beyond this row -> -inf (exp2 -> 0)
+    int it = 0, cnt = 0;                                // cnt = tiles this group has processed (s_full parity)
+    for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
+      int bh, qt;
+      sched.decode(k, bh, qt);
+      const int b = bh / H, h = bh - b * H;
+      const int n_kv = causal ? qt + 1 : S / BKV;
+      const int oset = (C::OSETS == 2) ? (it & 1) : 0;
+      const uint32_t to = tl + C::COL_O + (oset * 2 + g) * DH;
+      float m = -INFINITY, l = 0.f;
+      auto tile = [&](int j, auto diag_tag) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
+        mbar_wait(&s_full[g], cnt & 1);
+        ++cnt;
+        tc_fence_after();
+        // The row is streamed from TMEM in eight 16-column chunks (next chunk in flight while the current one is
+        // processed) and only the packed bf16 probabilities stay in registers. The exponentials are taken OPTIMISTICALLY
+        // against the running reference max m; the chunk maxima are tracked on the side and only if some row of the warp
+        // outgrew m by more than 2^8 (or on the group's first tile, m = -inf) the row is re-read (S is still intact in
+        // TMEM) and redone against the new max. Lazy rescaling keeps the result exact.
+        uint32_t pk[64];
+        float mx = -INFINITY, rs0 = 0.f, rs1 = 0.f;
+        auto sweep = [&](auto&& body) {   // body(chunk index, 16 raw S values); two chunks ping-pong
+          uint32_t ra[16], rb[16];
+          tmem_ld_32x16(ts, ra);
+          tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          if (half * 64 + t > row) r0[t] = 0xff800000u;
-          if (half * 64 + 32 + t > row) r1[t] = 0xff800000u;
+          for (int cc = 0; cc < 8; cc += 2) {
+            tmem_ld_32x16(ts + (cc + 1) * 16, rb);
+            body(cc, ra);
+            tmem_ld_wait();
+            if (cc + 2 < 8) tmem_ld_32x16(ts + (cc + 2) * 16, ra);
+            body(cc + 1, rb);
+            if (cc + 2 < 8) tmem_ld_wait();
+          }
+        };
+        auto masked = [&](const uint32_t (&r)[16], int cc, int t) -> float {
+          float v = __uint_as_float(r[t]);
+          if (DIAG && cc * 16 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
+          return v;
+        };
+        auto exp_pass = [&](float m_ref) {
+          rs0 = 0.f, rs1 = 0.f;
+          sweep([&](int cc, const uint32_t (&r)[16]) {
+            float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) {
+              const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
+              cm0 = fmaxf(cm0, v0);
+              cm1 = fmaxf(cm1, v1);
+              const float p0 = exp2f(fmaf(v0, sc, -m_ref));
+              const float p1 = exp2f(fmaf(v1, sc, -m_ref));
+              rs0 += p0;
+              rs1 += p1;
+              pk[cc * 8 + (t >> 1)] = pack_bf16(p0, p1);
+            }
+            mx = fmaxf(mx, fmaxf(cm0, cm1));
+          });
+        };
+        const bool first = (j < 2);   // this group's first tile of the item: no reference max yet
+        bool bump = true;
+        if (!first) {
+          exp_pass(m);
+          bump = (mx * sc - m) > 8.0f;
         }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+        float alpha = 1.0f;
+        const bool redo = first || __any_sync(0xffffffff, bump);
+        if (redo) {
+          if (first) {
+            sweep([&](int cc, const uint32_t (&r)[16]) {
+              float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-      for (int t = 0; t < 32; t += 2) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[t]), __uint_as_float(r0[t + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r1[t]), __uint_as_float(r1[t + 1])));
-      }
-      // the two halves of a row agree on the row max through smem (double-buffered per tile parity)
-      float* xb = xch + (j & 1) * 256;
-      const float mine = fmaxf(mx0, mx1);
-      xb[half * 128 + row] = mine;
-      named_bar_sync(2, 256);
-      const float mx = fmaxf(mine, xb[(half ^ 1) * 128 + row]);
-      // lazy rescale: keep the old reference max unless it grew by more than 2^8 (bounded overflow, exact result)
-      const float m_cand = fmaxf(m, mx * sc);
-      const bool bump = (m_cand - m) > 8.0f;   // also true on the first tile (m = -inf)
-      const float m_new = bump ? m_cand : m;
-      const float alpha = bump ? exp2f(m - m_new) : 1.0f;
-      float rs0 = 0.f, rs1 = 0.f;
-      auto emit = [&](const uint32_t (&r)[32], int cc) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(r[t]), sc, -m_new));
-          const float p1 = exp2f(fmaf(__uint_as_float(r[t + 1]), sc, -m_new));
-          rs0 += p0;
-          rs1 += p1;
-          pk[t >> 1] = pack_bf16(p0, p1);
+              for (int t = 0; t < 16; t += 2) {
+                cm0 = fmaxf(cm0, masked(r, cc, t));
+                cm1 = fmaxf(cm1, masked(r, cc, t + 1));
+              }
+              mx = fmaxf(mx, fmaxf(cm0, cm1));
+            });
+          }
+          const float m_new = bump ? fmaxf(m, mx * sc) : m;
+          alpha = bump ? exp2f(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
+          exp_pass(m_new);
+          m = m_new;
         }
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-                ts + half * 32 + cc * 16),
-            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
-            "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
-            : "memory");
-      };
-      // NOTE: P (64 packed columns) aliases S columns [0,64): the OTHER half of this row may still be reading its S
-      // values from columns [64,128) -> only columns [0,64) are overwritten, and half 0 has them in registers already;
-      // half 1's stores land in [32,64), which half 0 read before the named barrier above.
-      emit(r0, 0);
-      emit(r1, 1);
-      l = l * alpha + (rs0 + rs1);
-      m = m_new;
-      // rescale the running O only when some row of this warp actually moved its reference max (DH/2 columns per thread)
-      if (j > 0) {
-        if (__any_sync(0xffffffff, bump)) {
-          mbar_wait(o_done, (j - 1) & 1);
-          tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                  ts + cc * 16),
+              "r"(pk[cc * 16 + 0]), "r"(pk[cc * 16 + 1]), "r"(pk[cc * 16 + 2]), "r"(pk[cc * 16 + 3]), "r"(pk[cc * 16 + 4]),
+              "r"(pk[cc * 16 + 5]), "r"(pk[cc * 16 + 6]), "r"(pk[cc * 16 + 7]), "r"(pk[cc * 16 + 8]), "r"(pk[cc * 16 + 9]),
+              "r"(pk[cc * 16 + 10]), "r"(pk[cc * 16 + 11]), "r"(pk[cc * 16 + 12]), "r"(pk[cc * 16 + 13]), "r"(pk[cc * 16 + 14]),
+              "r"(pk[cc * 16 + 15])
+              : "memory");
+        }
+        l = l * alpha + (rs0 + rs1);
+        // rescale this group's running O only when some row of the warp moved its reference max. P V_{j-2} (the last MMA
+        // that wrote it) was issued before S_j, whose completion we waited for above: no extra wait is needed.
+        if (!first && redo) {
 #pragma unroll 1
-          for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tl + C::COL_O + c * 32, r);
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t ro[32];
+            tmem_ld_32x32(to + c * 32, ro);
             tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) r[t] = __float_as_uint(__uint_as_float(r[t]) * alpha);
-            tmem_st_32x32(tl + C::COL_O + c * 32, r);
+            for (int t = 0; t < 32; ++t) ro[t] = __float_as_uint(__uint_as_float(ro[t]) * alpha);
+            tmem_st_32x32(to + c * 32, ro);
           }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[g]);
+      };
+      const int j_diag = causal ? n_kv - 1 : -1;
+      for (int j = g; j < n_kv; j += 2) {
+        if (j == j_diag) tile(j, std::true_type{});
+        else tile(j, std::false_type{});
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[j & 1]);
-    };
-    const int n_plain = causal ? n_kv - 1 : n_kv;
-    for (int j = 0; j < n_plain; ++j) tile(j, std::false_type{});
-    if (causal) tile(n_kv - 1, std::true_type{});
-    // ---- epilogue: row sum = both halves; O / l -> bf16 -> global (DH/2 columns per thread); lse
-    named_bar_sync(2, 256);                 // everyone is past its last max exchange: xch can be reused
-    xch[half * 128 + row] = l;
-    named_bar_sync(2, 256);
-    const float l_tot = l + xch[(half ^ 1) * 128 + row];
-    mbar_wait(o_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_tot;
-    __nv_bfloat16* orow = out + (long long)(row0 + row) * d_model + h * DH;
+      // ---- epilogue: merge the two groups' partial softmax streams; O -> bf16 -> global (DH/2 columns per group); lse
+      float2* xb = xch + (it & 1) * 256;
+      xb[g * 128 + row] = make_float2(m, l);
+      named_bar_sync(2, 256);
+      const float2 other = xb[(g ^ 1) * 128 + row];
+      const float m_tot = fmaxf(m, other.x);
+      const float a_self = exp2f(m - m_tot);              // exp2(-inf) = 0 for a group without tiles (n_kv == 1)
+      const float a_oth = exp2f(other.x - m_tot);
+      const float l_tot = l * a_self + other.y * a_oth;
+      const float inv_l = 1.0f / l_tot;
+      const float w0 = (g == 0 ? a_self : a_oth) * inv_l;   // weight of group 0's accumulator
+      const float w1 = (g == 0 ? a_oth : a_self) * inv_l;
+      const bool has1 = n_kv > 1;                           // group 1's accumulator holds garbage when it had no tile
+      mbar_wait(o_final, it & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = out + (long long)(b * S + qt * BQ + row) * d_model + h * DH;
+      const uint32_t to0 = tl + C::COL_O + (oset * 2) * DH, to1 = to0 + DH;
 #pragma unroll 1
-    for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tl + C::COL_O + c * 32, r);
-      tmem_ld_wait();
+      for (int c = g * (DH / 64); c < (g + 1) * (DH / 64); ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(to0 + c * 32, r0);
+        if (has1) tmem_ld_32x32(to1 + c * 32, r1);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-      for (int t = 0; t < 32; t += 8) {
-        uint4 o;
-        o.x = pack_bf16(__uint_as_float(r[t]) * inv_l, __uint_as_float(r[t + 1]) * inv_l);
-        o.y = pack_bf16(__uint_as_float(r[t + 2]) * inv_l, __uint_as_float(r[t + 3]) * inv_l);
-        o.z = pack_bf16(__uint_as_float(r[t + 4]) * inv_l, __uint_as_float(r[t + 5]) * inv_l);
-        o.w = pack_bf16(__uint_as_float(r[t + 6]) * inv_l, __uint_as_float(r[t + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
+        for (int t = 0; t < 32; ++t) {
+          f[t] = __uint_as_float(r0[t]) * w0;
+          if (has1) f[t] = fmaf(__uint_as_float(r1[t]), w1, f[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 o;
+          o.x = pack_bf16(f[t], f[t + 1]);
+          o.y = pack_bf16(f[t + 2], f[t + 3]);
+          o.z = pack_bf16(f[t + 4], f[t + 5]);
+          o.w = pack_bf16(f[t + 6], f[t + 7]);
+          *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
+        }
       }
+      if (g == 0) lse[((long long)b * H + h) * S + qt * BQ + row] = m_tot * LN2 + __logf(l_tot);
+      tc_fence_before();
+      mbar_arrive(&o_free[oset]);
     }
-    if (half == 0) lse[((long long)b * H + h) * S + qt * BQ + row] = m * LN2 + __logf(l_tot);
   }
   tc_fence_before();
   __syncthreads();
@@ -404,60 +533,70 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp runs the loop (uniform operands -> no per-MMA elect/broadcast round trip), one elected
+    // lane issues each tcgen05 instruction (see the forward kernel).
+    {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both K-major, N = 128
       constexpr uint32_t idesc_mm = make_idesc_bf16(128, DH, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q) MN-major
       constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
       const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+      // descriptor bases; per-k-step offsets are added to the (addr >> 4) field
+      const uint64_t kd_k = make_smem_desc_sw128(k_base, 16, 1024), vd_k = make_smem_desc_sw128(v_base, 16, 1024);
+      const uint64_t pd_m = make_smem_desc_sw128(p_base, 16384, 1024), dsd_m = make_smem_desc_sw128(ds_base, 16384, 1024);
+      const uint64_t dsd_k = make_smem_desc_sw128(ds_base, 16, 1024), kd_m = make_smem_desc_sw128(k_base, 16384, 1024);
       mbar_wait(kv_full, 0);
       auto issue_sdp = [&](int t) {  // S_t = Q_t K^T ; dP_t = dO_t V^T  (contraction over d_head = 64: 4 k-steps in one swizzle atom)
         const int st = t & 1;
-        const uint32_t q_base = smem_u32(sQ + st * C::TILE), do_base = smem_u32(sDO + st * C::TILE);
+        const uint64_t qd_k = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16, 1024);
+        const uint64_t dod_k = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16, 1024);
         mbar_wait(&qd_full[st], (t >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          tc_mma_f16_ss(tmem + C::COL_S, make_smem_desc_sw128(q_base + kk * 32, 16, 1024), make_smem_desc_sw128(k_base + kk * 32, 16, 1024),
-                        idesc_kk, kk != 0);
+          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_S, qd_k + uint64_t(kk * 2), kd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          tc_mma_f16_ss(tmem + C::COL_DP, make_smem_desc_sw128(do_base + kk * 32, 16, 1024), make_smem_desc_sw128(v_base + kk * 32, 16, 1024),
-                        idesc_kk, kk != 0);
-        tc_commit(sdp_full);
+          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DP, dod_k + uint64_t(kk * 2), vd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
+        if (elect_one()) tc_commit(sdp_full);
+        __syncwarp();
       };
       issue_sdp(0);
       for (int t = 0; t < n_it; ++t) {
         const int st = t & 1;
-        const uint32_t q_base = smem_u32(sQ + st * C::TILE), do_base = smem_u32(sDO + st * C::TILE);
+        const uint64_t qd_m = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16384, 1024);
+        const uint64_t dod_m = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16384, 1024);
         mbar_wait(pds_ready, t & 1);   // row threads consumed S_t / dP_t and staged P_t / dS_t in smem
         // next tile's S / dP go first: the row threads start on them while dV / dK / dQ of this tile run
         if (t + 1 < n_it) issue_sdp(t + 1);
         if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
         tc_fence_after();
-        // contraction over the 128 query rows of this tile: 8 k-steps, 16 rows (2048 B) each
+        // contraction over the 128 query rows of this tile: 8 k-steps, 16 rows (2048 B = 128 descriptor units) each
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // dV[kv, dh] += P^T dO : A = P (MN-major: kv contiguous, 2 chunks of 64 -> LBO 16 KiB), B = dO (MN-major, N = 64)
-          tc_mma_f16_ss(tmem + C::COL_DV, make_smem_desc_sw128(p_base + kk * 2048, 16384, 1024),
-                        make_smem_desc_sw128(do_base + kk * 2048, 16384, 1024), idesc_mm, (t | kk) != 0);
+          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DV, pd_m + uint64_t(kk * 128), dod_m + uint64_t(kk * 128), idesc_mm, (t | kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // dK[kv, dh] += dS^T Q
-          tc_mma_f16_ss(tmem + C::COL_DK, make_smem_desc_sw128(ds_base + kk * 2048, 16384, 1024),
-                        make_smem_desc_sw128(q_base + kk * 2048, 16384, 1024), idesc_mm, (t | kk) != 0);
+          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DK, dsd_m + uint64_t(kk * 128), qd_m + uint64_t(kk * 128), idesc_mm, (t | kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // dQ[q, dh] = dS K_j : A = dS K-major (kv contiguous: chunk = kk/4, 32 B per k-step), B = K_j MN-major over kv rows
-          tc_mma_f16_ss(tmem + C::COL_DQ, make_smem_desc_sw128(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                        make_smem_desc_sw128(k_base + kk * 2048, 16384, 1024), idesc_km, kk != 0);
+          if (elect_one())
+            tc_mma_f16_ss(tmem + C::COL_DQ, dsd_k + uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint64_t(kk * 128), idesc_km,
+                          kk != 0);
         }
-        tc_commit(&qd_empty[st]);
-        tc_commit(dq_full);
-        tc_commit(mma_done);
+        if (elect_one()) {
+          tc_commit(&qd_empty[st]);
+          tc_commit(dq_full);
+          tc_commit(mma_done);
+        }
+        __syncwarp();
       }
-      tc_commit(final_done);
+      if (elect_one()) tc_commit(final_done);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ row threads (warps 0..7)
@@ -591,21 +730,31 @@ size_t g_dq_acc_bytes = 0;
 
 }  // namespace
 
-void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H, int dh, float scale, bool causal, int /*num_sms*/,
+void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H, int dh, float scale, bool causal, int num_sms,
                           cudaStream_t st) {
   if (S % 128) throw std::runtime_error("photon_b200 attention: sequence length must be a multiple of 128");
   if (dh != 64 && dh != 128) throw std::runtime_error("photon_b200 attention: d_head must be 64 or 128");
   const int d = H * dh;
   CUtensorMap tm = make_tmap_2d(qkv, 2, false, uint64_t(3) * d, uint64_t(B) * S, uint64_t(3) * d * 2, 64, 128);
-  dim3 grid(S / 128, H, B);
+  FwdSched sched;
+  sched.n_qt = S / 128;
+  sched.n_items = sched.n_qt * H * B;
+  const int sms = num_sms > 0 ? num_sms : 148;
+  const int grid = sched.n_items < sms ? sched.n_items : sms;
+  sched.grid = grid;
+  {  // rounds after which a CTA of the static round-robin has visited every slot class (see FwdSched)
+    int a = sched.n_qt, b2 = grid % sched.n_qt;
+    while (b2) { const int t = a % b2; a = b2; b2 = t; }
+    sched.cyc_rounds = sched.n_qt / a;
+  }
   if (dh == 64) {
     static bool once = (set_smem(attn_fwd_kernel<64>, FwdCfg<64>::SMEM), true);
     (void)once;
-    attn_fwd_kernel<64><<<grid, 320, FwdCfg<64>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
+    attn_fwd_kernel<64><<<grid, 320, FwdCfg<64>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0, sched);
   } else {
     static bool once = (set_smem(attn_fwd_kernel<128>, FwdCfg<128>::SMEM), true);
     (void)once;
-    attn_fwd_kernel<128><<<grid, 320, FwdCfg<128>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0);
+    attn_fwd_kernel<128><<<grid, 320, FwdCfg<128>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0, sched);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention fwd launch: ") + cudaGetErrorString(e));

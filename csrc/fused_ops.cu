@@ -237,7 +237,35 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const __nv_bfloat16* __
   const long long r1 = r0 + rows_per_block < T ? r0 + rows_per_block : T;
   float as[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < d) {
-    for (long long r = r0 + w; r < r1; r += 8) {
+    // 4 independent 16-byte loads per thread in flight (the row loop alone keeps one: ~16 KiB per SM, a quarter of what
+    // HBM3e needs to stay busy)
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      uint4 q[4], qx[4];
+      float mu[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        q[u] = *reinterpret_cast<const uint4*>(dy + (r + 8 * u) * ld + col);
+        if (x) {
+          qx[u] = *reinterpret_cast<const uint4*>(x + (r + 8 * u) * (long long)d + col);
+          mu[u] = mean[r + 8 * u], rs[u] = rstd[r + 8 * u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float g[8];
+        unpack8(q[u], g);
+        if (x) {
+          float fx[8];
+          unpack8(qx[u], fx);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ad[k] += g[k] * (fx[k] - mu[u]) * rs[u];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) as[k] += g[k];
+      }
+    }
+    for (; r < r1; r += 8) {
       float g[8];
       unpack8(*reinterpret_cast<const uint4*>(dy + r * ld + col), g);
       if (x) {

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -179,8 +180,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0 && crank == 0) {
+    // ======================= MMA issuer =======================
+    // The whole warp walks the loop (waits included) so every operand is warp-uniform; one elected lane issues the
+    // tcgen05 instructions. (`if (lane == 0)` around the loop costs a ~20-instruction elect/broadcast round trip per MMA.)
+    if (crank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -197,24 +200,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
           const uint32_t b_base = smem_u32(sB + stage * B_STAGE);
+          const uint64_t ad0 = A_MN ? make_smem_desc_sw128(a_base, BK * 128, 1024) : make_smem_desc_sw128(a_base, 16, 1024);
+          const uint64_t bd0 = B_MN ? make_smem_desc_sw128(b_base, BK * 128, 1024) : make_smem_desc_sw128(b_base, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * (UK * 128), BK * 128, 1024)
-                                        : make_smem_desc_sw128(a_base + k * (UK * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * (UK * 128), BK * 128, 1024)
-                                        : make_smem_desc_sw128(b_base + k * (UK * 2), 16, 1024);
-            if (CL > 1) tc_mma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // k-step inside the stage: UK rows of 128 B (MN-major) or UK elements of 2 B (K-major), in 16-byte descriptor units
+            const uint64_t adesc = ad0 + uint64_t(A_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
+            const uint64_t bdesc = bd0 + uint64_t(B_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
+            if (elect_one()) {
+              if (CL > 1) tc_mma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
-          if (CL > 1) tc_commit_2sm(&empty[stage], 0x3);  // release the stage in BOTH CTAs
-          else tc_commit(&empty[stage]);                  // frees the smem slot once these MMAs retire
+          if (elect_one()) {
+            if (CL > 1) tc_commit_2sm(&empty[stage], 0x3);  // release the stage in BOTH CTAs
+            else tc_commit(&empty[stage]);                  // frees the smem slot once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (CL > 1) tc_commit_2sm(&tfull[acc], 0x3);  // accumulator complete -> both CTAs' epilogues
-        else tc_commit(&tfull[acc]);
+        if (elect_one()) {
+          if (CL > 1) tc_commit_2sm(&tfull[acc], 0x3);  // accumulator complete -> both CTAs' epilogues
+          else tc_commit(&tfull[acc]);
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -477,6 +489,10 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
     if (s > num_kb / 8) s = num_kb / 8;
     if (s < 1) s = 1;
     p.splits = s;
+    if (const char* e = std::getenv("PB_GEMM_SPLITS")) {  // tuning knob (scripts/bench_kernels.py sweeps it)
+      const int v = std::atoi(e);
+      if (v >= 1 && v <= num_kb) p.splits = v;
+    }
   }
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty tails

@@ -42,6 +42,27 @@ def main():
             us_per_cta = ms * 1e3 * 148 / ctas
             rows.append(dict(causal=causal, S=S, b=b, ms=ms, ctas=ctas, avg_kv_tiles=n_kv, us_per_cta=us_per_cta))
             print(rows[-1], flush=True)
+    # backward: same fit (one CTA per (b, h, kv tile) walking the query tiles)
+    brow = []
+    for causal in (False, True):
+        for S in (256, 512, 1024, 2048, 4096):
+            b = max(1, (32 * 2048) // S)
+            qkv = torch.randn(b, S, 3 * H * dh, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(b, S, H * dh, device="cuda", dtype=torch.bfloat16)
+            lse = torch.empty(b, H, S, device="cuda", dtype=torch.float32)
+            ops.attention_fwd(qkv, out, lse, H, dh ** -0.5, causal)
+            dout = torch.randn_like(out)
+            dqkv = torch.empty_like(qkv)
+            delta = torch.empty(b, H, S, device="cuda", dtype=torch.float32)
+            ms = timed(lambda: ops.attention_bwd(qkv, out, dout, lse, dqkv, delta, H, dh ** -0.5, causal))
+            ctas = b * H * S // 128
+            n_q = (S // 128 + 1) / 2 if causal else S // 128
+            brow.append(dict(bwd=True, causal=causal, S=S, ms=ms, avg_q_tiles=n_q, us_per_cta=ms * 1e3 * 148 / ctas))
+            print(brow[-1], flush=True)
+    bn = [r for r in brow if not r["causal"]]
+    tb = (bn[-1]["us_per_cta"] - bn[0]["us_per_cta"]) / (bn[-1]["avg_q_tiles"] - bn[0]["avg_q_tiles"])
+    print(json.dumps({"bwd_per_q_tile_us": tb, "bwd_fixed_per_cta_us": bn[0]["us_per_cta"] - tb * bn[0]["avg_q_tiles"],
+                      "note": "includes the delta / dq-convert helper kernels"}))
     nc = [r for r in rows if not r["causal"]]
     x0, x1 = nc[0], nc[-1]
     t = (x1["us_per_cta"] - x0["us_per_cta"]) / (x1["avg_kv_tiles"] - x0["avg_kv_tiles"])
