@@ -37,30 +37,36 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 // ======================================================================================= forward
-// Persistent kernel: one CTA per SM walks a list of (batch*head, query tile) work items; TMA, MMA and softmax pipelines
-// run ACROSS item boundaries (the per-CTA prologue/epilogue of a one-tile-per-CTA grid measured 3.9 us against 0.89 us per
-// KV tile, i.e. a third of the run time at S = 2048).
+// Persistent kernel: one CTA per SM walks a list of (batch*head, query tile) work items; the TMA, MMA and softmax
+// pipelines run ACROSS item boundaries (a one-tile-per-CTA grid measured 3.9 us of prologue/epilogue per CTA against
+// 0.89 us per KV tile — a third of the run time at S = 2048).
 //   warp 8  : TMA producer  — Q (double-buffered), K ring, V ring
-//   warp 9  : MMA issuer    — S_j = Q K_j^T (SS) into S buffer (j & 1); O_g += P_j V_j (TS, P read from TMEM)
-//   warps 0-3 (group 0) / 4-7 (group 1): softmax — group g owns the KV tiles with j & 1 == g, its own S buffer and its
-//             own O accumulator with its own running (max, sum): two independent online-softmax streams that never
-//             synchronise per tile; one group's exp2 work overlaps the other's MMA round trip. The two partial results
-//             are merged once per item (log-sum-exp combine) in the epilogue.
+//   warp 9  : MMA issuer    — the KV tiles of all items form ONE stream n = 0, 1, 2, ...: S_n = Q K_n^T (SS) goes into
+//             S buffer (n & 1) one tile AHEAD of the softmax, O += P_n V_n (TS, P read from TMEM) follows softmax_n.
+//             The whole warp walks the loop (uniform operands), one elected lane issues (see gemm_tcgen05.cu).
+//   warps 0-7: softmax      — warps w and w+4 (same SM sub-partition, same 32 TMEM lanes) split a query row's 128 key
+//             columns 64/64, so every sub-partition has two warps to interleave (one warp alone reaches ~0.6 IPC and
+//             cannot keep the MUFU busy). The half row is streamed from TMEM in 32-column chunks (next chunk in
+//             flight while the current one is exponentiated), only packed bf16 P stays in registers.
+//             Exponentials are taken OPTIMISTICALLY against the running reference max; the tile max is tracked on the
+//             side and only if a row outgrew the reference by > 2^8 (or on an item's first tile) the tile is redone
+//             against the new max (S is still intact in TMEM); the two halves of a row agree on the tile max through
+//             smem and a 64-thread named barrier AFTER the exponentials. The epilogue of item i (O / l -> bf16 -> global) is
+//             deferred until after the first tile of item i+1, so its wait for the last P V never stalls the stream
+//             (O is double-buffered by item parity).
 template <int DH>
 struct FwdCfg {
   static constexpr int CH = DH / 64;              // 64-column swizzle chunks per tile
   static constexpr int TILE = 128 * 128 * CH;     // bytes of one [128 x DH] bf16 tile
-  static constexpr int QBUF = (DH == 64) ? 2 : 1;
-  static constexpr int KST = (DH == 64) ? 4 : 3;  // K ring depth (S_{j+2} is issued right after P V_j: >= 3)
+  static constexpr int QBUF = 2;
+  static constexpr int KST = (DH == 64) ? 4 : 2;
   static constexpr int VST = (DH == 64) ? 4 : 2;
-  static constexpr int OSETS = (DH == 64) ? 2 : 1;  // O accumulator sets (item parity) x 2 groups
-  static constexpr int AUX = 4096;                // barriers (512 B) + per-row (m, l) exchange (2 parities x 2 groups x 128 x 8 B)
+  static constexpr int AUX = 5120;                // barriers (512 B) + row max / row sum exchange (2 x 2 x 128 floats) + spare
   static constexpr int SMEM = TILE * (QBUF + KST + VST) + AUX + 1024;
-  // two S buffers (128 fp32 columns each); P_j (packed bf16, 64 columns) aliases the head of S_j once the row threads hold
-  // S_j in registers; O accumulators after them
+  // two S buffers (128 fp32 columns each); P_n (packed bf16, 64 columns) aliases the head of S_n; two O accumulators
   static constexpr int COL_S = 0, COL_O = 256;
   static constexpr int TMEM_COLS = 512;
-  static_assert(COL_O + OSETS * 2 * DH <= 512, "TMEM budget");
+  static_assert(COL_O + 2 * DH <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "smem budget");
 };
 
@@ -72,7 +78,7 @@ struct FwdSched {
   __device__ __forceinline__ void decode(int k, int& bh, int& qt) const {
     bh = k / n_qt;
     const int slot = k - bh * n_qt;
-    const int shift = int((long long)bh * n_qt / grid) / cyc_rounds;
+    const int shift = (bh * n_qt / grid) / cyc_rounds;
     qt = n_qt - 1 - (slot + shift) % n_qt;
   }
 };
@@ -94,16 +100,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   uint64_t* k_empty = bars + 8;                   // [4]
   uint64_t* v_full = bars + 12;                   // [4]
   uint64_t* v_empty = bars + 16;                  // [4]
-  uint64_t* s_full = bars + 20;                   // [2]  per group
-  uint64_t* p_ready = bars + 22;                  // [2]  per group (128 arrivals)
-  uint64_t* o_final = bars + 24;                  // all P V of an item retired
-  uint64_t* o_free = bars + 25;                   // [2]  O set drained by the epilogue (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
-  float2* xch = reinterpret_cast<float2*>(bars + 64);  // [2 item parities][2 groups][128 rows] (m, l)
+  uint64_t* s_full = bars + 20;                   // [2]  S_n landed in buffer n & 1
+  uint64_t* p_ready = bars + 22;                  // [2]  P_n stored (128 arrivals)
+  uint64_t* pv_done = bars + 24;                  // P V_n retired (per tile; only waited on a rescale)
+  uint64_t* o_final = bars + 25;                  // all P V of an item retired
+  uint64_t* o_free = bars + 26;                   // [2]  O buffer drained by the epilogue (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  float* xch = reinterpret_cast<float*>(bars + 64);    // [2 tile parities][2 halves][128 rows]
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int d_model = H * DH;
+  const int n_items = sched.n_items;
+  auto nkv_of = [&](int k) {
+    int bh, qt;
+    sched.decode(k, bh, qt);
+    return causal ? qt + 1 : S / BKV;
+  };
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQKV);
@@ -111,7 +124,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], 256);
       mbar_init(&o_free[s], 256);
     }
     for (int s = 0; s < 4; ++s) {
@@ -120,6 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
+    mbar_init(pv_done, 1);
     mbar_init(o_final, 1);
     fence_barrier_init();
   }
@@ -133,13 +147,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0, kc = 0, vc = 0;
-      for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
+      for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
         int bh, qt;
         sched.decode(k, bh, qt);
         const int b = bh / H, h = bh - b * H;
         const int n_kv = causal ? qt + 1 : S / BKV;
-        const int qb = it % C::QBUF;
-        mbar_wait(&q_empty[qb], ((it / C::QBUF) & 1) ^ 1);
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[qb], C::TILE);
 #pragma unroll
         for (int c = 0; c < C::CH; ++c) tma_load_2d(sQ + qb * C::TILE + c * 16384, &tmQKV, &q_full[qb], h * DH + c * 64, b * S + qt * BQ);
@@ -162,134 +176,166 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The WHOLE warp walks this loop in lock-step (waits included) and one elected lane issues each tcgen05
-    // instruction: addresses, descriptors and counters are then warp-uniform, live in uniform registers and feed
-    // UTCHMMA directly. With `if (lane == 0)` around the loop every operand took a ~20-instruction elect/broadcast
-    // round trip (12 MMAs x ~100 clk per KV tile — more than the tensor pipe needs for the tile).
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH, 0, 1);
-      int it = 0, kc = 0, vc = 0;
-      int pc0 = 0, pc1 = 0;  // P tiles consumed per group (p_ready parity)
-      for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
-        int bh, qt;
-        sched.decode(k, bh, qt);
-        const int n_kv = causal ? qt + 1 : S / BKV;
-        const int qb = it % C::QBUF;
-        const uint32_t q_base = smem_u32(sQ + qb * C::TILE);
-        const int oset = (C::OSETS == 2) ? (it & 1) : 0;
-        mbar_wait(&q_full[qb], (it / C::QBUF) & 1);
-        auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer (j & 1)
-          const int ks = kc % C::KST;
-          const uint32_t k_base = smem_u32(sK + ks * C::TILE);
-          mbar_wait(&k_full[ks], (kc / C::KST) & 1);
-          tc_fence_after();
-          const uint32_t d_col = tmem + C::COL_S + (j & 1) * 128;
-          const uint64_t qd = make_smem_desc_sw128(q_base, 16, 1024), kd = make_smem_desc_sw128(k_base, 16, 1024);
-#pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk) {
-            const uint64_t off = uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);  // descriptor address field is addr >> 4
-            if (elect_one()) tc_mma_f16_ss(d_col, qd + off, kd + off, idesc_s, kk != 0);
-          }
-          if (elect_one()) {
-            tc_commit(&s_full[j & 1]);
-            tc_commit(&k_empty[ks]);
-            if (j == n_kv - 1) tc_commit(&q_empty[qb]);  // last read of this Q buffer
-          }
-          __syncwarp();
-          ++kc;
-        };
-        // S buffers are free here: the previous item's P tiles were consumed by P V MMAs issued earlier (in-order pipe)
-        issue_s(0);
-        if (n_kv > 1) issue_s(1);
-        // the O set of this item parity must have been drained by the epilogue two (one) items ago
-        mbar_wait(&o_free[oset], (((C::OSETS == 2) ? (it >> 1) : it) & 1) ^ 1);
-        tc_fence_after();
-        for (int j = 0; j < n_kv; ++j) {
-          const int g = j & 1;
-          const int vs = vc % C::VST;
-          const uint32_t v_base = smem_u32(sV + vs * C::TILE);
-          if (g == 0) {
-            mbar_wait(&p_ready[0], pc0 & 1);
-            ++pc0;
-          } else {
-            mbar_wait(&p_ready[1], pc1 & 1);
-            ++pc1;
-          }
-          mbar_wait(&v_full[vs], (vc / C::VST) & 1);
-          tc_fence_after();
-          const uint32_t o_col = tmem + C::COL_O + (oset * 2 + g) * DH;
-          const uint32_t p_col = tmem + C::COL_S + g * 128;
-          const uint64_t vd = make_smem_desc_sw128(v_base, 16384, 1024);
-#pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            if (elect_one()) tc_mma_f16_ts(o_col, p_col + kk * 8, vd + uint64_t((kk * 2048) >> 4), idesc_o, (j >= 2 || kk != 0) ? 1u : 0u);
-          }
-          if (elect_one()) {
-            tc_commit(&v_empty[vs]);
-            if (j == n_kv - 1) tc_commit(o_final);
-          }
-          __syncwarp();
-          ++vc;
-          // S_{j+2} reuses buffer g: P_j is consumed by the MMAs just issued (in-order), group g has released S_j (p_ready)
-          if (j + 2 < n_kv) issue_s(j + 2);
-        }
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH, 0, 1);
+    struct Cur {
+      int k, it, j, n_kv;
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.j == c.n_kv) {
+        c.k += gridDim.x;
+        ++c.it;
+        c.j = 0;
+        c.n_kv = c.k < n_items ? nkv_of(c.k) : 0;
       }
+    };
+    int kc = 0, vc = 0, ns = 0, n = 0;
+    auto issue_s = [&](const Cur& c) {  // S_ns = Q K^T into S buffer (ns & 1)
+      const int qb = c.it & 1;
+      if (c.j == 0) mbar_wait(&q_full[qb], (c.it >> 1) & 1);
+      const int ks = kc % C::KST;
+      mbar_wait(&k_full[ks], (kc / C::KST) & 1);
+      tc_fence_after();
+      const uint32_t d_col = tmem + C::COL_S + (ns & 1) * 128;
+      const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + qb * C::TILE), 16, 1024);
+      const uint64_t kd = make_smem_desc_sw128(smem_u32(sK + ks * C::TILE), 16, 1024);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint64_t off = uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);  // descriptor address field is addr >> 4
+        if (elect_one()) tc_mma_f16_ss(d_col, qd + off, kd + off, idesc_s, kk != 0);
+      }
+      if (elect_one()) {
+        tc_commit(&s_full[ns & 1]);
+        tc_commit(&k_empty[ks]);
+        if (c.j == c.n_kv - 1) tc_commit(&q_empty[qb]);  // last read of this Q buffer
+      }
+      __syncwarp();
+      ++kc;
+      ++ns;
+    };
+    Cur nx{int(blockIdx.x), 0, 0, 0};
+    nx.n_kv = nx.k < n_items ? nkv_of(nx.k) : 0;
+    Cur cu = nx;
+    if (nx.k < n_items) {
+      issue_s(nx);
+      advance(nx);
+    }
+    while (cu.k < n_items) {
+      // S_{n+1} (possibly the next item's first tile) goes first: it runs while the row threads work on S_n. Its buffer
+      // held P_{n-1}, consumed by P V_{n-1} issued in the previous iteration (in-order pipe).
+      if (nx.k < n_items) {
+        issue_s(nx);
+        advance(nx);
+      }
+      const int ob = cu.it & 1;
+      if (cu.j == 0) {  // the O buffer of this item parity must have been drained by the epilogue two items ago
+        mbar_wait(&o_free[ob], ((cu.it >> 1) & 1) ^ 1);
+      }
+      const int vs = vc % C::VST;
+      mbar_wait(&p_ready[n & 1], (n >> 1) & 1);
+      mbar_wait(&v_full[vs], (vc / C::VST) & 1);
+      tc_fence_after();
+      const uint32_t o_col = tmem + C::COL_O + ob * DH;
+      const uint32_t p_col = tmem + C::COL_S + (n & 1) * 128;
+      const uint64_t vd = make_smem_desc_sw128(smem_u32(sV + vs * C::TILE), 16384, 1024);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk) {
+        // P of key columns [0,64) sits at S columns [0,32), P of [64,128) at S columns [64,96): each half of a row packs
+        // its probabilities over its OWN S columns
+        if (elect_one())
+          tc_mma_f16_ts(o_col, p_col + (kk >> 2) * 64 + (kk & 3) * 8, vd + uint64_t((kk * 2048) >> 4), idesc_o, (cu.j > 0 || kk != 0) ? 1u : 0u);
+      }
+      if (elect_one()) {
+        tc_commit(&v_empty[vs]);
+        tc_commit(pv_done);
+        if (cu.j == cu.n_kv - 1) tc_commit(o_final);
+      }
+      __syncwarp();
+      ++vc;
+      ++n;
+      advance(cu);
     }
   } else {
     // ------------------------------------------------------------------ softmax rows (warps 0..7)
-    const int g = warp >> 2;                            // group: KV tiles with j & 1 == g
-    const int row = (warp & 3) * 32 + lane;             // query row inside the tile == TMEM lane
-    const uint32_t tl = tmem + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t ts = tl + C::COL_S + g * 128;
+    const int half = warp >> 2;                         // which 64 key columns of the row
+    const int w4 = warp & 3;
+    const int row = w4 * 32 + lane;                     // query row inside the tile == TMEM lane
+    const uint32_t tl = tmem + (uint32_t(w4 * 32) << 16);
     const float sc = scale * LOG2E;
-    int it = 0, cnt = 0;                                // cnt = tiles this group has processed (s_full parity)
-    for (int k = blockIdx.x; k < sched.n_items; k += gridDim.x, ++it) {
+    int n = 0;                                          // KV tiles processed (stream index)
+    struct Pend {
+      int valid, b, h, qt, it;
+      float m, l;
+    } pend{0, 0, 0, 0, 0, 0.f, 0.f};
+    auto pair_exchange = [&](float mine, int slot) -> float {   // value of the other half of this row (64-thread barrier)
+      float* xb = xch + slot * 256;
+      xb[half * 128 + row] = mine;
+      named_bar_sync(2 + w4, 64);
+      return xb[(half ^ 1) * 128 + row];
+    };
+    auto epilogue = [&](const Pend& e) {  // O / l -> bf16 -> global (DH/2 columns per half); lse
+      // slots 2,3 of the exchange area: never used by the per-tile max exchange (slots 0,1)
+      const float l_tot = e.l + pair_exchange(e.l, 2 + (e.it & 1));
+      mbar_wait(o_final, e.it & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_tot;
+      __nv_bfloat16* orow = out + (long long)(e.b * S + e.qt * BQ + row) * d_model + e.h * DH;
+      const uint32_t to = tl + C::COL_O + (e.it & 1) * DH;
+#pragma unroll 1
+      for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(to + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[t]) * inv_l, __uint_as_float(r[t + 1]) * inv_l);
+          o.y = pack_bf16(__uint_as_float(r[t + 2]) * inv_l, __uint_as_float(r[t + 3]) * inv_l);
+          o.z = pack_bf16(__uint_as_float(r[t + 4]) * inv_l, __uint_as_float(r[t + 5]) * inv_l);
+          o.w = pack_bf16(__uint_as_float(r[t + 6]) * inv_l, __uint_as_float(r[t + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
+        }
+      }
+      if (half == 0) lse[((long long)e.b * H + e.h) * S + e.qt * BQ + row] = e.m * LN2 + __logf(l_tot);
+      tc_fence_before();
+      mbar_arrive(&o_free[e.it & 1]);
+    };
+    int it = 0;
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
       int bh, qt;
       sched.decode(k, bh, qt);
       const int b = bh / H, h = bh - b * H;
       const int n_kv = causal ? qt + 1 : S / BKV;
-      const int oset = (C::OSETS == 2) ? (it & 1) : 0;
-      const uint32_t to = tl + C::COL_O + (oset * 2 + g) * DH;
-      float m = -INFINITY, l = 0.f;
+      const uint32_t to = tl + C::COL_O + (it & 1) * DH;
+      float m = -INFINITY, l = 0.f;                     // l = partial row sum over this thread's 64 columns
       auto tile = [&](int j, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
-        mbar_wait(&s_full[g], cnt & 1);
-        ++cnt;
+        const uint32_t ts = tl + C::COL_S + (n & 1) * 128 + half * 64;   // this thread's 64 S columns; P goes over the first 32
+        mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tc_fence_after();
-        // The row is streamed from TMEM in eight 16-column chunks (next chunk in flight while the current one is
-        // processed) and only the packed bf16 probabilities stay in registers. The exponentials are taken OPTIMISTICALLY
-        // against the running reference max m; the chunk maxima are tracked on the side and only if some row of the warp
-        // outgrew m by more than 2^8 (or on the group's first tile, m = -inf) the row is re-read (S is still intact in
-        // TMEM) and redone against the new max. Lazy rescaling keeps the result exact.
-        uint32_t pk[64];
+        uint32_t pk[32];
         float mx = -INFINITY, rs0 = 0.f, rs1 = 0.f;
-        auto sweep = [&](auto&& body) {   // body(chunk index, 16 raw S values); two chunks ping-pong
-          uint32_t ra[16], rb[16];
-          tmem_ld_32x16(ts, ra);
+        auto sweep = [&](auto&& body) {   // body(chunk index, 32 raw S values); second chunk in flight during the first
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(ts, ra);
           tmem_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < 8; cc += 2) {
-            tmem_ld_32x16(ts + (cc + 1) * 16, rb);
-            body(cc, ra);
-            tmem_ld_wait();
-            if (cc + 2 < 8) tmem_ld_32x16(ts + (cc + 2) * 16, ra);
-            body(cc + 1, rb);
-            if (cc + 2 < 8) tmem_ld_wait();
-          }
+          tmem_ld_32x32(ts + 32, rb);
+          body(0, ra);
+          tmem_ld_wait();
+          body(1, rb);
         };
-        auto masked = [&](const uint32_t (&r)[16], int cc, int t) -> float {
+        auto masked = [&](const uint32_t (&r)[32], int cc, int t) -> float {
           float v = __uint_as_float(r[t]);
-          if (DIAG && cc * 16 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
+          if (DIAG && half * 64 + cc * 32 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
           return v;
         };
         auto exp_pass = [&](float m_ref) {
           rs0 = 0.f, rs1 = 0.f;
-          sweep([&](int cc, const uint32_t (&r)[16]) {
+          sweep([&](int cc, const uint32_t (&r)[32]) {
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < 16; t += 2) {
+            for (int t = 0; t < 32; t += 2) {
               const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
               cm0 = fmaxf(cm0, v0);
               cm1 = fmaxf(cm1, v1);
@@ -297,38 +343,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
               const float p1 = exp2f(fmaf(v1, sc, -m_ref));
               rs0 += p0;
               rs1 += p1;
-              pk[cc * 8 + (t >> 1)] = pack_bf16(p0, p1);
+              pk[cc * 16 + (t >> 1)] = pack_bf16(p0, p1);
             }
             mx = fmaxf(mx, fmaxf(cm0, cm1));
           });
         };
-        const bool first = (j < 2);   // this group's first tile of the item: no reference max yet
-        bool bump = true;
+        const bool first = (j == 0);   // no reference max yet
         if (!first) {
           exp_pass(m);
-          bump = (mx * sc - m) > 8.0f;
-        }
-        float alpha = 1.0f;
-        const bool redo = first || __any_sync(0xffffffff, bump);
-        if (redo) {
-          if (first) {
-            sweep([&](int cc, const uint32_t (&r)[16]) {
-              float cm0 = -INFINITY, cm1 = -INFINITY;
+        } else {
+          sweep([&](int cc, const uint32_t (&r)[32]) {
+            float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-              for (int t = 0; t < 16; t += 2) {
-                cm0 = fmaxf(cm0, masked(r, cc, t));
-                cm1 = fmaxf(cm1, masked(r, cc, t + 1));
-              }
-              mx = fmaxf(mx, fmaxf(cm0, cm1));
-            });
-          }
+            for (int t = 0; t < 32; t += 2) {
+              cm0 = fmaxf(cm0, masked(r, cc, t));
+              cm1 = fmaxf(cm1, masked(r, cc, t + 1));
+            }
+            mx = fmaxf(mx, fmaxf(cm0, cm1));
+          });
+        }
+        // both halves of the row now know the tile max -> identical decisions
+        mx = fmaxf(mx, pair_exchange(mx, n & 1));
+        const bool bump = first || (mx * sc - m) > 8.0f;
+        float alpha = 1.0f;
+        const bool redo = __any_sync(0xffffffff, bump);
+        if (redo) {
           const float m_new = bump ? fmaxf(m, mx * sc) : m;
           alpha = bump ? exp2f(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
           exp_pass(m_new);
           m = m_new;
         }
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
                   ts + cc * 16),
@@ -339,11 +385,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
               : "memory");
         }
         l = l * alpha + (rs0 + rs1);
-        // rescale this group's running O only when some row of the warp moved its reference max. P V_{j-2} (the last MMA
-        // that wrote it) was issued before S_j, whose completion we waited for above: no extra wait is needed.
+        // rescale the running O (DH/2 columns per half) only when some row of the warp moved its reference max: wait for
+        // P V_{n-1} (P V_{n-2} is known retired: it was issued before S_n, so the parity wait cannot alias)
         if (!first && redo) {
+          mbar_wait(pv_done, (n - 1) & 1);
+          tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
+          for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
             uint32_t ro[32];
             tmem_ld_32x32(to + c * 32, ro);
             tmem_ld_wait();
@@ -354,56 +402,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[g]);
+        mbar_arrive(&p_ready[n & 1]);
+        ++n;
       };
       const int j_diag = causal ? n_kv - 1 : -1;
-      for (int j = g; j < n_kv; j += 2) {
+      for (int j = 0; j < n_kv; ++j) {
         if (j == j_diag) tile(j, std::true_type{});
         else tile(j, std::false_type{});
-      }
-      // ---- epilogue: merge the two groups' partial softmax streams; O -> bf16 -> global (DH/2 columns per group); lse
-      float2* xb = xch + (it & 1) * 256;
-      xb[g * 128 + row] = make_float2(m, l);
-      named_bar_sync(2, 256);
-      const float2 other = xb[(g ^ 1) * 128 + row];
-      const float m_tot = fmaxf(m, other.x);
-      const float a_self = exp2f(m - m_tot);              // exp2(-inf) = 0 for a group without tiles (n_kv == 1)
-      const float a_oth = exp2f(other.x - m_tot);
-      const float l_tot = l * a_self + other.y * a_oth;
-      const float inv_l = 1.0f / l_tot;
-      const float w0 = (g == 0 ? a_self : a_oth) * inv_l;   // weight of group 0's accumulator
-      const float w1 = (g == 0 ? a_oth : a_self) * inv_l;
-      const bool has1 = n_kv > 1;                           // group 1's accumulator holds garbage when it had no tile
-      mbar_wait(o_final, it & 1);
-      tc_fence_after();
-      __nv_bfloat16* orow = out + (long long)(b * S + qt * BQ + row) * d_model + h * DH;
-      const uint32_t to0 = tl + C::COL_O + (oset * 2) * DH, to1 = to0 + DH;
-#pragma unroll 1
-      for (int c = g * (DH / 64); c < (g + 1) * (DH / 64); ++c) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(to0 + c * 32, r0);
-        if (has1) tmem_ld_32x32(to1 + c * 32, r1);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          f[t] = __uint_as_float(r0[t]) * w0;
-          if (has1) f[t] = fmaf(__uint_as_float(r1[t]), w1, f[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < 32; t += 8) {
-          uint4 o;
-          o.x = pack_bf16(f[t], f[t + 1]);
-          o.y = pack_bf16(f[t + 2], f[t + 3]);
-          o.z = pack_bf16(f[t + 4], f[t + 5]);
-          o.w = pack_bf16(f[t + 6], f[t + 7]);
-          *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
+        if (pend.valid) {   // the previous item's epilogue, deferred behind this item's first tile
+          epilogue(pend);
+          pend.valid = 0;
         }
       }
-      if (g == 0) lse[((long long)b * H + h) * S + qt * BQ + row] = m_tot * LN2 + __logf(l_tot);
-      tc_fence_before();
-      mbar_arrive(&o_free[oset]);
+      pend = Pend{1, b, h, qt, it, m, l};
     }
+    if (pend.valid) epilogue(pend);
   }
   tc_fence_before();
   __syncthreads();
@@ -452,56 +465,71 @@ struct BwdCfg {
   static constexpr int TILE = 128 * 128;                    // [128 x 64] bf16
   static constexpr int PS_TILE = 2 * 128 * 128;             // [128 x 128] bf16 as two 64-col chunks
   static constexpr int DQ_STAGE = 128 * 64 * 4;             // fp32 [128 x 64] staging (two 32-col chunks)
-  static constexpr int SMEM = 2 * TILE /*K,V*/ + 2 * 2 * TILE /*Q,dO x2 stages*/ + 2 * PS_TILE /*P,dS*/ + DQ_STAGE + 256 + 1024;
+  static constexpr int SMEM = 2 * 2 * TILE /*K,V x2 items*/ + 2 * 2 * TILE /*Q,dO x2 stages*/ + 2 * PS_TILE /*P,dS*/ + DQ_STAGE + 256 + 1024;
   static constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
   static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM <= 232448, "smem budget");
 };
 
+// Persistent: one CTA per SM walks (batch*head, key tile) items; the query tiles of ALL its items form one stream
+// n = 0, 1, 2, ... through the TMA / MMA / row-thread pipelines (K/V double-buffered by item parity), so the per-CTA
+// prologue and the dK/dV epilogue of a one-item-per-CTA grid (measured ~6 us per item against ~1.8 us per query tile)
+// overlap the next item's first tiles.
 // 320 threads: warps 0-7 = row threads (two per SMSP: warp w and w+4 own the same 32 query rows / TMEM lanes and
 // split the 128 key columns 64/64 - no cross-thread exchange is needed because lse and delta are per-row inputs),
-// warp 8 = TMA producer, warp 9 = MMA issuer + TMEM allocator.
+// warp 8 = TMA producer, warp 9 = MMA issuer (whole warp, elected lane) + TMEM allocator.
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale,
-                int causal) {
+                int causal, const FwdSched sched) {
   using C = BwdCfg;
   constexpr int DH = C::DH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + C::TILE;
-  uint8_t* sQ = sV + C::TILE;            // [2]
+  uint8_t* sK = smem;                    // [2] by item parity
+  uint8_t* sV = sK + 2 * C::TILE;        // [2]
+  uint8_t* sQ = sV + 2 * C::TILE;        // [2] by tile parity
   uint8_t* sDO = sQ + 2 * C::TILE;       // [2]
   uint8_t* sP = sDO + 2 * C::TILE;       // bf16 [128 q][128 kv] as 2 chunks of [128][64]
   uint8_t* sDS = sP + C::PS_TILE;
   uint8_t* sDQ = sDS + C::PS_TILE;       // fp32 staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + C::DQ_STAGE);
-  uint64_t* kv_full = bars;              // K_j and V_j
-  uint64_t* qd_full = bars + 1;          // [2] Q_i + dO_i
-  uint64_t* qd_empty = bars + 3;         // [2]
-  uint64_t* sdp_full = bars + 5;         // S and dP ready
-  uint64_t* pds_ready = bars + 6;        // P, dS in smem (128 arrivals)
-  uint64_t* dq_full = bars + 7;          // dQ partial tile in TMEM
-  uint64_t* dq_free = bars + 8;          // dQ TMEM columns drained (128 arrivals)
-  uint64_t* mma_done = bars + 9;         // dV/dK/dQ MMAs of the tile retired -> P/dS smem reusable
-  uint64_t* final_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars;              // [2] K_j and V_j of item parity
+  uint64_t* kv_empty = bars + 2;         // [2]
+  uint64_t* qd_full = bars + 4;          // [2] Q_i + dO_i
+  uint64_t* qd_empty = bars + 6;         // [2]
+  uint64_t* sdp_full = bars + 8;         // S and dP ready
+  uint64_t* pds_ready = bars + 9;        // P, dS in smem (256 arrivals)
+  uint64_t* dq_full = bars + 10;         // dQ partial tile in TMEM
+  uint64_t* dq_free = bars + 11;         // dQ TMEM columns drained (256 arrivals)
+  uint64_t* mma_done = bars + 12;        // dV/dK/dQ MMAs of the tile retired -> P/dS smem reusable
+  uint64_t* final_done = bars + 13;      // all MMAs of an item retired -> dK/dV complete
+  uint64_t* acc_free = bars + 14;        // dK/dV accumulators drained by the epilogue (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int n_t = S / 128;
-  const int jt = blockIdx.x;  // key tile (small j = most query tiles, launched first)
-  const int h = blockIdx.y, b = blockIdx.z;
   const int d_model = H * DH;
-  const int i0 = causal ? jt : 0;
-  const int n_it = n_t - i0;
+  const int n_items = sched.n_items;
+  // item k -> (b, h, key tile jt, first query tile i0, number of query tiles)
+  auto item_of = [&](int k, int& b, int& h, int& jt, int& i0, int& n_it) {
+    int bh, w;
+    sched.decode(k, bh, w);
+    b = bh / H;
+    h = bh - b * H;
+    jt = n_t - 1 - w;                    // decode() orders by weight w: heavy first == small key tile index
+    i0 = causal ? jt : 0;
+    n_it = n_t - i0;
+  };
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQKV);
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmDQ);
-    mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
       mbar_init(&qd_full[s], 1);
       mbar_init(&qd_empty[s], 1);
     }
@@ -511,6 +539,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(dq_free, 256);
     mbar_init(mma_done, 1);
     mbar_init(final_done, 1);
+    mbar_init(acc_free, 256);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -520,83 +549,123 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * C::TILE);
-      tma_load_2d(sK, &tmQKV, kv_full, d_model + h * DH, b * S + jt * 128);
-      tma_load_2d(sV, &tmQKV, kv_full, 2 * d_model + h * DH, b * S + jt * 128);
-      for (int t = 0; t < n_it; ++t) {
-        const int st = t & 1;
-        mbar_wait(&qd_empty[st], ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qd_full[st], 2 * C::TILE);
-        tma_load_2d(sQ + st * C::TILE, &tmQKV, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
-        tma_load_2d(sDO + st * C::TILE, &tmDO, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
+      int it = 0, n = 0;
+      for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
+        int b, h, jt, i0, n_it;
+        item_of(k, b, h, jt, i0, n_it);
+        const int kb = it & 1;
+        mbar_wait(&kv_empty[kb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[kb], 2 * C::TILE);
+        tma_load_2d(sK + kb * C::TILE, &tmQKV, &kv_full[kb], d_model + h * DH, b * S + jt * 128);
+        tma_load_2d(sV + kb * C::TILE, &tmQKV, &kv_full[kb], 2 * d_model + h * DH, b * S + jt * 128);
+        for (int t = 0; t < n_it; ++t, ++n) {
+          const int st = n & 1;
+          mbar_wait(&qd_empty[st], ((n >> 1) & 1) ^ 1);
+          mbar_expect_tx(&qd_full[st], 2 * C::TILE);
+          tma_load_2d(sQ + st * C::TILE, &tmQKV, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
+          tma_load_2d(sDO + st * C::TILE, &tmDO, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
+        }
       }
     }
   } else if (warp == 9) {
-    // MMA issuer: the whole warp runs the loop (uniform operands -> no per-MMA elect/broadcast round trip), one elected
-    // lane issues each tcgen05 instruction (see the forward kernel).
-    {
-      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both K-major, N = 128
-      constexpr uint32_t idesc_mm = make_idesc_bf16(128, DH, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q) MN-major
-      constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
-      // descriptor bases; per-k-step offsets are added to the (addr >> 4) field
-      const uint64_t kd_k = make_smem_desc_sw128(k_base, 16, 1024), vd_k = make_smem_desc_sw128(v_base, 16, 1024);
-      const uint64_t pd_m = make_smem_desc_sw128(p_base, 16384, 1024), dsd_m = make_smem_desc_sw128(ds_base, 16384, 1024);
-      const uint64_t dsd_k = make_smem_desc_sw128(ds_base, 16, 1024), kd_m = make_smem_desc_sw128(k_base, 16384, 1024);
-      mbar_wait(kv_full, 0);
-      auto issue_sdp = [&](int t) {  // S_t = Q_t K^T ; dP_t = dO_t V^T  (contraction over d_head = 64: 4 k-steps in one swizzle atom)
-        const int st = t & 1;
-        const uint64_t qd_k = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16, 1024);
-        const uint64_t dod_k = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16, 1024);
-        mbar_wait(&qd_full[st], (t >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_S, qd_k + uint64_t(kk * 2), kd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DP, dod_k + uint64_t(kk * 2), vd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
-        if (elect_one()) tc_commit(sdp_full);
-        __syncwarp();
-      };
-      issue_sdp(0);
-      for (int t = 0; t < n_it; ++t) {
-        const int st = t & 1;
-        const uint64_t qd_m = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16384, 1024);
-        const uint64_t dod_m = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16384, 1024);
-        mbar_wait(pds_ready, t & 1);   // row threads consumed S_t / dP_t and staged P_t / dS_t in smem
-        // next tile's S / dP go first: the row threads start on them while dV / dK / dQ of this tile run
-        if (t + 1 < n_it) issue_sdp(t + 1);
-        if (t > 0) mbar_wait(dq_free, (t - 1) & 1);
-        tc_fence_after();
-        // contraction over the 128 query rows of this tile: 8 k-steps, 16 rows (2048 B = 128 descriptor units) each
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // dV[kv, dh] += P^T dO : A = P (MN-major: kv contiguous, 2 chunks of 64 -> LBO 16 KiB), B = dO (MN-major, N = 64)
-          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DV, pd_m + uint64_t(kk * 128), dod_m + uint64_t(kk * 128), idesc_mm, (t | kk) != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // dK[kv, dh] += dS^T Q
-          if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DK, dsd_m + uint64_t(kk * 128), qd_m + uint64_t(kk * 128), idesc_mm, (t | kk) != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // dQ[q, dh] = dS K_j : A = dS K-major (kv contiguous: chunk = kk/4, 32 B per k-step), B = K_j MN-major over kv rows
-          if (elect_one())
-            tc_mma_f16_ss(tmem + C::COL_DQ, dsd_k + uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint64_t(kk * 128), idesc_km,
-                          kk != 0);
-        }
-        if (elect_one()) {
-          tc_commit(&qd_empty[st]);
-          tc_commit(dq_full);
-          tc_commit(mma_done);
-        }
-        __syncwarp();
+    // ------------------------------------------------------------------ MMA issuer (whole warp; elected lane issues)
+    constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both K-major, N = 128
+    constexpr uint32_t idesc_mm = make_idesc_bf16(128, DH, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q) MN-major
+    constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
+    const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+    // descriptor bases; per-k-step offsets are added to the (addr >> 4) field
+    const uint64_t pd_m = make_smem_desc_sw128(p_base, 16384, 1024), dsd_m = make_smem_desc_sw128(ds_base, 16384, 1024);
+    const uint64_t dsd_k = make_smem_desc_sw128(ds_base, 16, 1024);
+    struct Cur {
+      int k, it, t, n_it;
+    };
+    auto nit_of = [&](int k) {
+      int b, h, jt, i0, n_it;
+      item_of(k, b, h, jt, i0, n_it);
+      return n_it;
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.t == c.n_it) {
+        c.k += gridDim.x;
+        ++c.it;
+        c.t = 0;
+        c.n_it = c.k < n_items ? nit_of(c.k) : 0;
       }
-      if (elect_one()) tc_commit(final_done);
+    };
+    int ns = 0, n = 0;
+    auto issue_sdp = [&](const Cur& c) {  // S = Q K^T ; dP = dO V^T  (contraction over d_head = 64: 4 k-steps in one swizzle atom)
+      const int st = ns & 1, kb = c.it & 1;
+      if (c.t == 0) mbar_wait(&kv_full[kb], (c.it >> 1) & 1);
+      mbar_wait(&qd_full[st], (ns >> 1) & 1);
+      tc_fence_after();
+      const uint64_t qd_k = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16, 1024);
+      const uint64_t dod_k = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16, 1024);
+      const uint64_t kd_k = make_smem_desc_sw128(smem_u32(sK + kb * C::TILE), 16, 1024);
+      const uint64_t vd_k = make_smem_desc_sw128(smem_u32(sV + kb * C::TILE), 16, 1024);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_S, qd_k + uint64_t(kk * 2), kd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DP, dod_k + uint64_t(kk * 2), vd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
+      if (elect_one()) tc_commit(sdp_full);
       __syncwarp();
+      ++ns;
+    };
+    Cur nx{int(blockIdx.x), 0, 0, 0};
+    nx.n_it = nx.k < n_items ? nit_of(nx.k) : 0;
+    Cur cu = nx;
+    if (nx.k < n_items) {
+      issue_sdp(nx);
+      advance(nx);
+    }
+    while (cu.k < n_items) {
+      const int st = n & 1, kb = cu.it & 1;
+      const uint64_t qd_m = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16384, 1024);
+      const uint64_t dod_m = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16384, 1024);
+      const uint64_t kd_m = make_smem_desc_sw128(smem_u32(sK + kb * C::TILE), 16384, 1024);
+      mbar_wait(pds_ready, n & 1);   // row threads consumed S_n / dP_n and staged P_n / dS_n in smem
+      // next tile's S / dP go first (possibly the next item's): the row threads start on them while dV / dK / dQ run
+      if (nx.k < n_items) {
+        issue_sdp(nx);
+        advance(nx);
+      }
+      if (n > 0) mbar_wait(dq_free, (n - 1) & 1);
+      if (cu.t == 0 && cu.it > 0) mbar_wait(acc_free, (cu.it - 1) & 1);  // previous item's dK / dV drained
+      tc_fence_after();
+      const uint32_t acc = cu.t != 0;
+      // contraction over the 128 query rows of this tile: 8 k-steps, 16 rows (2048 B = 128 descriptor units) each
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // dV[kv, dh] += P^T dO : A = P (MN-major: kv contiguous, 2 chunks of 64 -> LBO 16 KiB), B = dO (MN-major, N = 64)
+        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DV, pd_m + uint64_t(kk * 128), dod_m + uint64_t(kk * 128), idesc_mm, (acc | kk) != 0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // dK[kv, dh] += dS^T Q
+        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DK, dsd_m + uint64_t(kk * 128), qd_m + uint64_t(kk * 128), idesc_mm, (acc | kk) != 0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // dQ[q, dh] = dS K_j : A = dS K-major (kv contiguous: chunk = kk/4, 32 B per k-step), B = K_j MN-major over kv rows
+        if (elect_one())
+          tc_mma_f16_ss(tmem + C::COL_DQ, dsd_k + uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint64_t(kk * 128), idesc_km,
+                        kk != 0);
+      }
+      if (elect_one()) {
+        tc_commit(&qd_empty[st]);
+        tc_commit(dq_full);
+        tc_commit(mma_done);
+        if (cu.t == cu.n_it - 1) {
+          tc_commit(final_done);
+          tc_commit(&kv_empty[kb]);
+        }
+      }
+      __syncwarp();
+      ++n;
+      advance(cu);
     }
   } else {
     // ------------------------------------------------------------------ row threads (warps 0..7)
@@ -606,8 +675,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const float sc = scale * LOG2E;
     const uint32_t swz = row & 7;
     const bool issuer = (threadIdx.x == 0);
-    auto drain_dq = [&](int t) {  // dQ partial of tile t: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
-      mbar_wait(dq_full, t & 1);
+    int n = 0;                                       // query tiles processed (stream index)
+    struct Prev {
+      int valid, b, h, qt;       // coordinates of tile n-1 (its dQ partial is still in TMEM)
+      int item_end, jt, it;      // tile n-1 was the last of item `it` (key tile jt): dK/dV epilogue pending
+    } pv{0, 0, 0, 0, 0, 0, 0};
+    auto drain_dq = [&](const Prev& p) {  // dQ partial of tile n-1: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
+      mbar_wait(dq_full, (n - 1) & 1);
       tc_fence_after();
       if (issuer) tma_wait_read<0>();
       named_bar_sync(1, 256);
@@ -626,77 +700,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (issuer) {
-        tma_reduce_add_2d(&tmDQ, sDQ, h * DH, b * S + (i0 + t) * 128);
-        tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * DH + 32, b * S + (i0 + t) * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ, p.h * DH, p.b * S + p.qt * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, p.h * DH + 32, p.b * S + p.qt * 128);
         tma_commit();
       }
     };
-    auto row_tile = [&](int t, auto diag_tag) {
-      constexpr bool DIAG = decltype(diag_tag)::value;
-      const int it = i0 + t;
-      const long long grow = (long long)(b * H + h) * S + it * 128 + row;
-      const float lse2 = lse[grow] * LOG2E;
-      const float dl = delta[grow];
-      mbar_wait(sdp_full, t & 1);
+    auto epilogue = [&](const Prev& p) {  // dK (x scale), dV of item p.it -> bf16 -> dqkv
+      mbar_wait(final_done, p.it & 1);
       tc_fence_after();
-      uint32_t pk[32], dk[32];  // packed bf16 P and dS of this thread's 64 columns, kept in registers
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;  // 32-column block of the row
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
-        tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
-          float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
-          if (DIAG) {
-            if (c * 32 + e > row) p0 = 0.f;
-            if (c * 32 + e + 1 > row) p1 = 0.f;
-          }
-          const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
-          const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
-          pk[cc * 16 + (e >> 1)] = pack_bf16(p0, p1);
-          dk[cc * 16 + (e >> 1)] = pack_bf16(s0, s1);
-        }
-      }
-      // S_t / dP_t are consumed (the MMA warp may overwrite them); the smem staging is reusable once the
-      // previous tile's dV / dK / dQ MMAs retired
-      if (t > 0) mbar_wait(mma_done, (t - 1) & 1);
-      {
-        // this thread's 64 columns = swizzle chunk `half` of row `row`: eight 16-byte groups
-        uint8_t* prow = sP + half * 16384 + row * 128;
-        uint8_t* drow = sDS + half * 16384 + row * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t slot = (uint32_t(g) ^ swz) << 4;
-          *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(pds_ready);
-      if (t > 0) drain_dq(t - 1);   // overlaps with S_{t+1}/dP_{t+1} and dV/dK/dQ_t on the tensor pipe
-    };
-    // causal: only the first query tile (it == jt) touches the diagonal; every other tile runs the mask-free body
-    for (int t = 0; t < n_it; ++t) {
-      if (causal && t == 0) row_tile(t, std::true_type{});
-      else row_tile(t, std::false_type{});
-    }
-    drain_dq(n_it - 1);
-    // ---- epilogue: dK (x scale), dV -> bf16 -> dqkv
-    mbar_wait(final_done, 0);
-    tc_fence_after();
-    __nv_bfloat16* krow = dqkv + (long long)(b * S + jt * 128 + row) * (3 * d_model) + d_model + h * DH;
-    __nv_bfloat16* vrow = krow + d_model;
-    {
+      __nv_bfloat16* krow = dqkv + (long long)(p.b * S + p.jt * 128 + row) * (3 * d_model) + d_model + p.h * DH;
+      __nv_bfloat16* vrow = krow + d_model;
       const int c = half;
       uint32_t rk[32], rv[32];
       tmem_ld_32x32(tl + C::COL_DK + c * 32, rk);
       tmem_ld_32x32(tl + C::COL_DV + c * 32, rv);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc_free);   // values are in registers: the next item's dV / dK MMAs may overwrite the accumulators
 #pragma unroll
       for (int e = 0; e < 32; e += 8) {
         uint4 ok, ov;
@@ -711,6 +731,76 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         *reinterpret_cast<uint4*>(krow + c * 32 + e) = ok;
         *reinterpret_cast<uint4*>(vrow + c * 32 + e) = ov;
       }
+    };
+    int it = 0;
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
+      int b, h, jt, i0, n_it;
+      item_of(k, b, h, jt, i0, n_it);
+      auto row_tile = [&](int t, auto diag_tag) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
+        const int qt = i0 + t;
+        const long long grow = (long long)(b * H + h) * S + qt * 128 + row;
+        const float lse2 = lse[grow] * LOG2E;
+        const float dl = delta[grow];
+        mbar_wait(sdp_full, n & 1);
+        tc_fence_after();
+        uint32_t pk[32], dk[32];  // packed bf16 P and dS of this thread's 64 columns, kept in registers
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;  // 32-column block of the row
+          uint32_t rs[32], rp[32];
+          tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
+          tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
+            float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+            if (DIAG) {
+              if (c * 32 + e > row) p0 = 0.f;
+              if (c * 32 + e + 1 > row) p1 = 0.f;
+            }
+            const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
+            const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
+            pk[cc * 16 + (e >> 1)] = pack_bf16(p0, p1);
+            dk[cc * 16 + (e >> 1)] = pack_bf16(s0, s1);
+          }
+        }
+        // S_n / dP_n are consumed (the MMA warp may overwrite them); the smem staging is reusable once the
+        // previous tile's dV / dK / dQ MMAs retired
+        if (n > 0) mbar_wait(mma_done, (n - 1) & 1);
+        {
+          // this thread's 64 columns = swizzle chunk `half` of row `row`: eight 16-byte groups
+          uint8_t* prow = sP + half * 16384 + row * 128;
+          uint8_t* drow = sDS + half * 16384 + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t slot = (uint32_t(g) ^ swz) << 4;
+            *reinterpret_cast<uint4*>(prow + slot) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            *reinterpret_cast<uint4*>(drow + slot) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_ready);
+        // previous tile's dQ partial (and, if it closed an item, that item's dK / dV): overlaps with S/dP of the next
+        // tile and dV/dK/dQ of this one on the tensor pipe
+        if (pv.valid) {
+          drain_dq(pv);
+          if (pv.item_end) epilogue(pv);
+        }
+        pv = Prev{1, b, h, qt, t == n_it - 1, jt, it};
+        ++n;
+      };
+      // causal: only the first query tile (qt == jt) touches the diagonal; every other tile runs the mask-free body
+      for (int t = 0; t < n_it; ++t) {
+        if (causal && t == 0) row_tile(t, std::true_type{});
+        else row_tile(t, std::false_type{});
+      }
+    }
+    if (pv.valid) {
+      drain_dq(pv);
+      epilogue(pv);
     }
     if (issuer) tma_wait_all<0>();
   }
@@ -761,7 +851,7 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
 }
 
 int attention_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B, int S, int H,
-                         int dh, float scale, bool causal, int /*num_sms*/, cudaStream_t st) {
+                         int dh, float scale, bool causal, int num_sms, cudaStream_t st) {
   if (S % 128) throw std::runtime_error("photon_b200 attention: sequence length must be a multiple of 128");
   if (dh != 64) throw std::runtime_error("photon_b200 attention backward: d_head must be 64 (use kernels.attention=torch otherwise)");
   const int d = H * dh;
@@ -784,8 +874,18 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
   CUtensorMap tmDQ = make_tmap_2d(g_dq_acc, 4, true, uint64_t(d), uint64_t(rows), uint64_t(d) * 4, 32, 128);
   static bool once = (set_smem(attn_bwd_kernel, BwdCfg::SMEM), true);
   (void)once;
-  dim3 grid(S / 128, H, B);
-  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0);
+  FwdSched sched;
+  sched.n_qt = S / 128;
+  sched.n_items = sched.n_qt * H * B;
+  const int sms = num_sms > 0 ? num_sms : 148;
+  const int grid = sched.n_items < sms ? sched.n_items : sms;
+  sched.grid = grid;
+  {
+    int a = sched.n_qt, b2 = grid % sched.n_qt;
+    while (b2) { const int t = a % b2; a = b2; b2 = t; }
+    sched.cyc_rounds = sched.n_qt / a;
+  }
+  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0, sched);
   attn_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(g_dq_acc, (__nv_bfloat16*)dqkv, rows, d, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention bwd launch: ") + cudaGetErrorString(e));
