@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -40,13 +41,13 @@ constexpr float LN2 = 0.6931471805599453f;
 // Persistent kernel: one CTA per SM walks a list of (batch*head, query tile) work items; the TMA, MMA and softmax
 // pipelines run ACROSS item boundaries (a one-tile-per-CTA grid measured 3.9 us of prologue/epilogue per CTA against
 // 0.89 us per KV tile — a third of the run time at S = 2048).
-//   warp 8  : TMA producer  — Q (double-buffered), K ring, V ring
-//   warp 9  : MMA issuer    — the KV tiles of all items form ONE stream n = 0, 1, 2, ...: S_n = Q K_n^T (SS) goes into
+//   warp 4*NS   : TMA producer  — Q (double-buffered), K ring, V ring
+//   warp 4*NS+1 : MMA issuer    — the KV tiles of all items form ONE stream n = 0, 1, 2, ...: S_n = Q K_n^T (SS) goes into
 //             S buffer (n & 1) one tile AHEAD of the softmax, O += P_n V_n (TS, P read from TMEM) follows softmax_n.
 //             The whole warp walks the loop (uniform operands), one elected lane issues (see gemm_tcgen05.cu).
-//   warps 0-7: softmax      — warps w and w+4 (same SM sub-partition, same 32 TMEM lanes) split a query row's 128 key
-//             columns 64/64, so every sub-partition has two warps to interleave (one warp alone reaches ~0.6 IPC and
-//             cannot keep the MUFU busy). The half row is streamed from TMEM in 32-column chunks (next chunk in
+//   warps 0 .. 4*NS-1: softmax — the NS warps w, w+4, ... (same SM sub-partition, same 32 TMEM lanes) split a query
+//             row's 128 key columns NS ways, so every sub-partition has NS warps to interleave (one warp alone reaches
+//             ~0.6 IPC; with two the MUFU pipe measured 54 % busy, the rest fixed-latency dependency stalls). The half row is streamed from TMEM in 32-column chunks (next chunk in
 //             flight while the current one is exponentiated), only packed bf16 P stays in registers.
 //             Exponentials are taken OPTIMISTICALLY against the running reference max; the tile max is tracked on the
 //             side and only if a row outgrew the reference by > 2^8 (or on an item's first tile) the tile is redone
@@ -61,7 +62,7 @@ struct FwdCfg {
   static constexpr int QBUF = 2;
   static constexpr int KST = (DH == 64) ? 4 : 2;
   static constexpr int VST = (DH == 64) ? 4 : 2;
-  static constexpr int AUX = 5120;                // barriers (512 B) + row max / row sum exchange (2 x 2 x 128 floats) + spare
+  static constexpr int AUX = 9216;                // barriers (512 B) + row max / row sum exchange (4 slots x NS<=4 x 128 floats)
   static constexpr int SMEM = TILE * (QBUF + KST + VST) + AUX + 1024;
   // two S buffers (128 fp32 columns each); P_n (packed bf16, 64 columns) aliases the head of S_n; two O accumulators
   static constexpr int COL_S = 0, COL_O = 256;
@@ -83,8 +84,8 @@ struct FwdSched {
   }
 };
 
-template <int DH>
-__global__ void __launch_bounds__(320, 1)
+template <int DH, int NS>
+__global__ void __launch_bounds__((4 * NS + 2) * 32, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
                 float scale, int causal, const FwdSched sched) {
   using C = FwdCfg<DH>;
@@ -103,10 +104,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   uint64_t* s_full = bars + 20;                   // [2]  S_n landed in buffer n & 1
   uint64_t* p_ready = bars + 22;                  // [2]  P_n stored (128 arrivals)
   uint64_t* pv_done = bars + 24;                  // P V_n retired (per tile; only waited on a rescale)
-  uint64_t* o_final = bars + 25;                  // all P V of an item retired
-  uint64_t* o_free = bars + 26;                   // [2]  O buffer drained by the epilogue (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-  float* xch = reinterpret_cast<float*>(bars + 64);    // [2 tile parities][2 halves][128 rows]
+  uint64_t* o_final = bars + 25;                  // [2]  all P V of an item (by item parity) retired
+  uint64_t* o_free = bars + 27;                   // [2]  O buffer drained by the epilogue (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  float* xch = reinterpret_cast<float*>(bars + 64);    // [4 slots][NS parts][128 rows]
+  constexpr int W_TMA = 4 * NS, W_MMA = 4 * NS + 1, COLS = 128 / NS;
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -118,14 +120,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
     return causal ? qt + 1 : S / BKV;
   };
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     prefetch_tmap(&tmQKV);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 256);
-      mbar_init(&o_free[s], 256);
+      mbar_init(&p_ready[s], 128 * NS);
+      mbar_init(&o_free[s], 128 * NS);
+      mbar_init(&o_final[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&k_full[s], 1);
@@ -134,16 +137,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       mbar_init(&v_empty[s], 1);
     }
     mbar_init(pv_done, 1);
-    mbar_init(o_final, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0, kc = 0, vc = 0;
@@ -175,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
     constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH, 0, 1);
@@ -198,12 +200,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       mbar_wait(&k_full[ks], (kc / C::KST) & 1);
       tc_fence_after();
       const uint32_t d_col = tmem + C::COL_S + (ns & 1) * 128;
-      const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + qb * C::TILE), 16, 1024);
-      const uint64_t kd = make_smem_desc_sw128(smem_u32(sK + ks * C::TILE), 16, 1024);
+      const uint32_t qd = smem_desc_lo(smem_u32(sQ + qb * C::TILE), 16);
+      const uint32_t kd = smem_desc_lo(smem_u32(sK + ks * C::TILE), 16);
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint64_t off = uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);  // descriptor address field is addr >> 4
-        if (elect_one()) tc_mma_f16_ss(d_col, qd + off, kd + off, idesc_s, kk != 0);
+        const uint32_t off = uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);  // descriptor address field is addr >> 4
+        if (elect_one()) tc_mma_f16_ss_lo(d_col, qd + off, kd + off, idesc_s, kk != 0);
       }
       if (elect_one()) {
         tc_commit(&s_full[ns & 1]);
@@ -238,18 +240,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       tc_fence_after();
       const uint32_t o_col = tmem + C::COL_O + ob * DH;
       const uint32_t p_col = tmem + C::COL_S + (n & 1) * 128;
-      const uint64_t vd = make_smem_desc_sw128(smem_u32(sV + vs * C::TILE), 16384, 1024);
+      const uint32_t vd = smem_desc_lo(smem_u32(sV + vs * C::TILE), 16384);
 #pragma unroll
       for (int kk = 0; kk < BKV / 16; ++kk) {
-        // P of key columns [0,64) sits at S columns [0,32), P of [64,128) at S columns [64,96): each half of a row packs
-        // its probabilities over its OWN S columns
+        // every column part of a row packs its probabilities over the head of its OWN S columns: keys [16 kk, 16 kk + 16)
+        // belong to part (16 kk) / COLS and sit at packed column ((16 kk) % COLS) / 2 inside it
         if (elect_one())
-          tc_mma_f16_ts(o_col, p_col + (kk >> 2) * 64 + (kk & 3) * 8, vd + uint64_t((kk * 2048) >> 4), idesc_o, (cu.j > 0 || kk != 0) ? 1u : 0u);
+          tc_mma_f16_ts_lo(o_col, p_col + ((kk * 16) / COLS) * COLS + ((kk * 16) % COLS) / 2, vd + uint32_t((kk * 2048) >> 4), idesc_o,
+                           (cu.j > 0 || kk != 0) ? 1u : 0u);
       }
       if (elect_one()) {
         tc_commit(&v_empty[vs]);
         tc_commit(pv_done);
-        if (cu.j == cu.n_kv - 1) tc_commit(o_final);
+        if (cu.j == cu.n_kv - 1) tc_commit(&o_final[ob]);
       }
       __syncwarp();
       ++vc;
@@ -257,47 +260,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       advance(cu);
     }
   } else {
-    // ------------------------------------------------------------------ softmax rows (warps 0..7)
-    const int half = warp >> 2;                         // which 64 key columns of the row
+    // ------------------------------------------------------------------ softmax rows (warps 0 .. 4*NS-1)
+    const int part = warp >> 2;                         // which COLS key columns of the row
     const int w4 = warp & 3;
     const int row = w4 * 32 + lane;                     // query row inside the tile == TMEM lane
     const uint32_t tl = tmem + (uint32_t(w4 * 32) << 16);
     const float sc = scale * LOG2E;
+    constexpr int OC = DH / (16 * NS);                  // 16-column O chunks per part
     int n = 0;                                          // KV tiles processed (stream index)
     struct Pend {
       int valid, b, h, qt, it;
       float m, l;
     } pend{0, 0, 0, 0, 0, 0.f, 0.f};
-    auto pair_exchange = [&](float mine, int slot) -> float {   // value of the other half of this row (64-thread barrier)
-      float* xb = xch + slot * 256;
-      xb[half * 128 + row] = mine;
-      named_bar_sync(2 + w4, 64);
-      return xb[(half ^ 1) * 128 + row];
+    // combine a per-thread value over the NS column parts of this row (32*NS-thread named barrier)
+    auto row_max = [&](float mine, int slot) -> float {
+      float* xb = xch + slot * (NS * 128);
+      xb[part * 128 + row] = mine;
+      named_bar_sync(2 + w4, 32 * NS);
+      float v = mine;
+#pragma unroll
+      for (int o = 1; o < NS; ++o) v = fmaxf(v, xb[((part + o) % NS) * 128 + row]);
+      return v;
     };
-    auto epilogue = [&](const Pend& e) {  // O / l -> bf16 -> global (DH/2 columns per half); lse
+    auto row_sum = [&](float mine, int slot) -> float {
+      float* xb = xch + slot * (NS * 128);
+      xb[part * 128 + row] = mine;
+      named_bar_sync(2 + w4, 32 * NS);
+      float v = 0.f;
+#pragma unroll
+      for (int o = 0; o < NS; ++o) v += xb[o * 128 + row];   // same order in every part: bit-identical totals
+      return v;
+    };
+    auto epilogue = [&](const Pend& e) {  // O / l -> bf16 -> global (DH/NS columns per part); lse
       // slots 2,3 of the exchange area: never used by the per-tile max exchange (slots 0,1)
-      const float l_tot = e.l + pair_exchange(e.l, 2 + (e.it & 1));
-      mbar_wait(o_final, e.it & 1);
+      const float l_tot = row_sum(e.l, 2 + (e.it & 1));
+      // one barrier per item parity: the epilogue of item i runs after the first tile of item i+1, whose LAST P V may
+      // retire (single-tile items) before a slow thread gets here - a shared barrier could then alias two phases
+      mbar_wait(&o_final[e.it & 1], (e.it >> 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l_tot;
       __nv_bfloat16* orow = out + (long long)(e.b * S + e.qt * BQ + row) * d_model + e.h * DH;
       const uint32_t to = tl + C::COL_O + (e.it & 1) * DH;
-#pragma unroll 1
-      for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(to + c * 32, r);
+#pragma unroll
+      for (int c = part * OC; c < (part + 1) * OC; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x16(to + c * 16, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; t += 8) {
+        for (int t = 0; t < 16; t += 8) {
           uint4 o;
           o.x = pack_bf16(__uint_as_float(r[t]) * inv_l, __uint_as_float(r[t + 1]) * inv_l);
           o.y = pack_bf16(__uint_as_float(r[t + 2]) * inv_l, __uint_as_float(r[t + 3]) * inv_l);
           o.z = pack_bf16(__uint_as_float(r[t + 4]) * inv_l, __uint_as_float(r[t + 5]) * inv_l);
           o.w = pack_bf16(__uint_as_float(r[t + 6]) * inv_l, __uint_as_float(r[t + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + t) = o;
+          *reinterpret_cast<uint4*>(orow + c * 16 + t) = o;
         }
       }
-      if (half == 0) lse[((long long)e.b * H + e.h) * S + e.qt * BQ + row] = e.m * LN2 + __logf(l_tot);
+      if (part == 0) lse[((long long)e.b * H + e.h) * S + e.qt * BQ + row] = e.m * LN2 + __logf(l_tot);
       tc_fence_before();
       mbar_arrive(&o_free[e.it & 1]);
     };
@@ -308,26 +327,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       const int b = bh / H, h = bh - b * H;
       const int n_kv = causal ? qt + 1 : S / BKV;
       const uint32_t to = tl + C::COL_O + (it & 1) * DH;
-      float m = -INFINITY, l = 0.f;                     // l = partial row sum over this thread's 64 columns
+      float m = -INFINITY, l = 0.f;                     // l = partial row sum over this thread's COLS columns
       auto tile = [&](int j, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
-        const uint32_t ts = tl + C::COL_S + (n & 1) * 128 + half * 64;   // this thread's 64 S columns; P goes over the first 32
+        const uint32_t ts = tl + C::COL_S + (n & 1) * 128 + part * COLS;   // this thread's S columns; P goes over their head
         mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tc_fence_after();
-        uint32_t pk[32];
+        uint32_t pk[COLS / 2];
         float mx = -INFINITY, rs0 = 0.f, rs1 = 0.f;
-        auto sweep = [&](auto&& body) {   // body(chunk index, 32 raw S values); second chunk in flight during the first
-          uint32_t ra[32], rb[32];
+        auto sweep = [&](auto&& body) {   // body(chunk index, 32 raw S values); with two chunks the second is in flight during the first
+          uint32_t ra[32];
           tmem_ld_32x32(ts, ra);
           tmem_ld_wait();
-          tmem_ld_32x32(ts + 32, rb);
-          body(0, ra);
-          tmem_ld_wait();
-          body(1, rb);
+          if constexpr (COLS == 64) {
+            uint32_t rb[32];
+            tmem_ld_32x32(ts + 32, rb);
+            body(0, ra);
+            tmem_ld_wait();
+            body(1, rb);
+          } else {
+            body(0, ra);
+          }
         };
         auto masked = [&](const uint32_t (&r)[32], int cc, int t) -> float {
           float v = __uint_as_float(r[t]);
-          if (DIAG && half * 64 + cc * 32 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
+          if (DIAG && part * COLS + cc * 32 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
           return v;
         };
         auto exp_pass = [&](float m_ref) {
@@ -362,8 +386,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             mx = fmaxf(mx, fmaxf(cm0, cm1));
           });
         }
-        // both halves of the row now know the tile max -> identical decisions
-        mx = fmaxf(mx, pair_exchange(mx, n & 1));
+        // all parts of the row now learn the tile max -> identical decisions
+        mx = row_max(mx, n & 1);
         const bool bump = first || (mx * sc - m) > 8.0f;
         float alpha = 1.0f;
         const bool redo = __any_sync(0xffffffff, bump);
@@ -374,7 +398,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
           m = m_new;
         }
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < COLS / 32; ++cc) {
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
                   ts + cc * 16),
@@ -385,19 +409,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
               : "memory");
         }
         l = l * alpha + (rs0 + rs1);
-        // rescale the running O (DH/2 columns per half) only when some row of the warp moved its reference max: wait for
+        // rescale the running O (DH/NS columns per part) only when some row of the warp moved its reference max: wait for
         // P V_{n-1} (P V_{n-2} is known retired: it was issued before S_n, so the parity wait cannot alias)
         if (!first && redo) {
           mbar_wait(pv_done, (n - 1) & 1);
           tc_fence_after();
-#pragma unroll 1
-          for (int c = half * (DH / 64); c < (half + 1) * (DH / 64); ++c) {
-            uint32_t ro[32];
-            tmem_ld_32x32(to + c * 32, ro);
+#pragma unroll
+          for (int c = part * OC; c < (part + 1) * OC; ++c) {
+            uint32_t ro[16];
+            tmem_ld_32x16(to + c * 16, ro);
             tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) ro[t] = __float_as_uint(__uint_as_float(ro[t]) * alpha);
-            tmem_st_32x32(to + c * 32, ro);
+            for (int t = 0; t < 16; ++t) ro[t] = __float_as_uint(__uint_as_float(ro[t]) * alpha);
+            tmem_st_32x16(to + c * 16, ro);
           }
         }
         tmem_st_wait();
@@ -420,7 +444,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<C::TMEM_COLS>(tmem);
+  if (warp == W_MMA) tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
 // ======================================================================================= backward
@@ -481,7 +505,7 @@ struct BwdCfg {
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale,
-                int causal, const FwdSched sched) {
+                int causal, const FwdSched sched, float* __restrict__ dq_acc, int dq_red) {
   using C = BwdCfg;
   constexpr int DH = C::DH;
   extern __shared__ uint8_t smem_raw[];
@@ -505,7 +529,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* mma_done = bars + 12;        // dV/dK/dQ MMAs of the tile retired -> P/dS smem reusable
   uint64_t* final_done = bars + 13;      // all MMAs of an item retired -> dK/dV complete
   uint64_t* acc_free = bars + 14;        // dK/dV accumulators drained by the epilogue (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* sdp_free = bars + 15;        // S / dP of the tile are in registers (256 arrivals) -> next S / dP may be issued
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -540,6 +565,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(mma_done, 1);
     mbar_init(final_done, 1);
     mbar_init(acc_free, 256);
+    mbar_init(sdp_free, 256);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -576,8 +602,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
     const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
     // descriptor bases; per-k-step offsets are added to the (addr >> 4) field
-    const uint64_t pd_m = make_smem_desc_sw128(p_base, 16384, 1024), dsd_m = make_smem_desc_sw128(ds_base, 16384, 1024);
-    const uint64_t dsd_k = make_smem_desc_sw128(ds_base, 16, 1024);
+    const uint32_t pd_m = smem_desc_lo(p_base, 16384), dsd_m = smem_desc_lo(ds_base, 16384);
+    const uint32_t dsd_k = smem_desc_lo(ds_base, 16);
+    // all stage / item-parity variants up front: nothing but 32-bit adds between the MMAs of a tile
+    uint32_t qd_k2[2], dod_k2[2], qd_m2[2], dod_m2[2], kd_k2[2], vd_k2[2], kd_m2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      qd_k2[i] = smem_desc_lo(smem_u32(sQ + i * C::TILE), 16), qd_m2[i] = smem_desc_lo(smem_u32(sQ + i * C::TILE), 16384);
+      dod_k2[i] = smem_desc_lo(smem_u32(sDO + i * C::TILE), 16), dod_m2[i] = smem_desc_lo(smem_u32(sDO + i * C::TILE), 16384);
+      kd_k2[i] = smem_desc_lo(smem_u32(sK + i * C::TILE), 16), kd_m2[i] = smem_desc_lo(smem_u32(sK + i * C::TILE), 16384);
+      vd_k2[i] = smem_desc_lo(smem_u32(sV + i * C::TILE), 16);
+    }
     struct Cur {
       int k, it, t, n_it;
     };
@@ -600,16 +635,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (c.t == 0) mbar_wait(&kv_full[kb], (c.it >> 1) & 1);
       mbar_wait(&qd_full[st], (ns >> 1) & 1);
       tc_fence_after();
-      const uint64_t qd_k = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16, 1024);
-      const uint64_t dod_k = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16, 1024);
-      const uint64_t kd_k = make_smem_desc_sw128(smem_u32(sK + kb * C::TILE), 16, 1024);
-      const uint64_t vd_k = make_smem_desc_sw128(smem_u32(sV + kb * C::TILE), 16, 1024);
+      const uint32_t qd_k = st ? qd_k2[1] : qd_k2[0], dod_k = st ? dod_k2[1] : dod_k2[0];
+      const uint32_t kd_k = kb ? kd_k2[1] : kd_k2[0], vd_k = kb ? vd_k2[1] : vd_k2[0];
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk)
-        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_S, qd_k + uint64_t(kk * 2), kd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_S, qd_k + uint32_t(kk * 2), kd_k + uint32_t(kk * 2), idesc_kk, kk != 0);
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk)
-        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DP, dod_k + uint64_t(kk * 2), vd_k + uint64_t(kk * 2), idesc_kk, kk != 0);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_DP, dod_k + uint32_t(kk * 2), vd_k + uint32_t(kk * 2), idesc_kk, kk != 0);
       if (elect_one()) tc_commit(sdp_full);
       __syncwarp();
       ++ns;
@@ -623,15 +656,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     while (cu.k < n_items) {
       const int st = n & 1, kb = cu.it & 1;
-      const uint64_t qd_m = make_smem_desc_sw128(smem_u32(sQ + st * C::TILE), 16384, 1024);
-      const uint64_t dod_m = make_smem_desc_sw128(smem_u32(sDO + st * C::TILE), 16384, 1024);
-      const uint64_t kd_m = make_smem_desc_sw128(smem_u32(sK + kb * C::TILE), 16384, 1024);
-      mbar_wait(pds_ready, n & 1);   // row threads consumed S_n / dP_n and staged P_n / dS_n in smem
-      // next tile's S / dP go first (possibly the next item's): the row threads start on them while dV / dK / dQ run
+      const uint32_t qd_m = st ? qd_m2[1] : qd_m2[0], dod_m = st ? dod_m2[1] : dod_m2[0];
+      const uint32_t kd_m = kb ? kd_m2[1] : kd_m2[0];
+      // next tile's S / dP (possibly the next item's) are issued as soon as the row threads hold S_n / dP_n in
+      // registers: they run on the tensor pipe while the rows are still computing P_n / dS_n
+      mbar_wait(sdp_free, n & 1);
       if (nx.k < n_items) {
         issue_sdp(nx);
         advance(nx);
       }
+      mbar_wait(pds_ready, n & 1);   // P_n / dS_n staged in smem
       if (n > 0) mbar_wait(dq_free, (n - 1) & 1);
       if (cu.t == 0 && cu.it > 0) mbar_wait(acc_free, (cu.it - 1) & 1);  // previous item's dK / dV drained
       tc_fence_after();
@@ -640,19 +674,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         // dV[kv, dh] += P^T dO : A = P (MN-major: kv contiguous, 2 chunks of 64 -> LBO 16 KiB), B = dO (MN-major, N = 64)
-        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DV, pd_m + uint64_t(kk * 128), dod_m + uint64_t(kk * 128), idesc_mm, (acc | kk) != 0);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_DV, pd_m + uint32_t(kk * 128), dod_m + uint32_t(kk * 128), idesc_mm, (acc | kk) != 0);
       }
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         // dK[kv, dh] += dS^T Q
-        if (elect_one()) tc_mma_f16_ss(tmem + C::COL_DK, dsd_m + uint64_t(kk * 128), qd_m + uint64_t(kk * 128), idesc_mm, (acc | kk) != 0);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_DK, dsd_m + uint32_t(kk * 128), qd_m + uint32_t(kk * 128), idesc_mm, (acc | kk) != 0);
       }
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         // dQ[q, dh] = dS K_j : A = dS K-major (kv contiguous: chunk = kk/4, 32 B per k-step), B = K_j MN-major over kv rows
         if (elect_one())
-          tc_mma_f16_ss(tmem + C::COL_DQ, dsd_k + uint64_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint64_t(kk * 128), idesc_km,
-                        kk != 0);
+          tc_mma_f16_ss_lo(tmem + C::COL_DQ, dsd_k + uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint32_t(kk * 128), idesc_km,
+                           kk != 0);
       }
       if (elect_one()) {
         tc_commit(&qd_empty[st]);
@@ -683,6 +717,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     auto drain_dq = [&](const Prev& p) {  // dQ partial of tile n-1: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
       mbar_wait(dq_full, (n - 1) & 1);
       tc_fence_after();
+      if (dq_red) {
+        // alternative: vector reductions straight from registers (no staging, fence or block barrier; 16-byte L2 atomics)
+        uint32_t r[32];
+        tmem_ld_32x32(tl + C::COL_DQ + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_free);
+        float* dst = dq_acc + (long long)(p.b * S + p.qt * 128 + row) * d_model + p.h * DH + half * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(r[4 * g])),
+                       "f"(__uint_as_float(r[4 * g + 1])), "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                       : "memory");
+        return;
+      }
       if (issuer) tma_wait_read<0>();
       named_bar_sync(1, 256);
       {
@@ -745,13 +794,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(sdp_full, n & 1);
         tc_fence_after();
         uint32_t pk[32], dk[32];  // packed bf16 P and dS of this thread's 64 columns, kept in registers
+        uint32_t rs2[2][32], rp2[2][32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld_32x32(tl + C::COL_S + (half * 2 + cc) * 32, rs2[cc]);
+          tmem_ld_32x32(tl + C::COL_DP + (half * 2 + cc) * 32, rp2[cc]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_free);   // S_n / dP_n are in registers: the MMA warp may overwrite them with tile n+1
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = half * 2 + cc;  // 32-column block of the row
-          uint32_t rs[32], rp[32];
-          tmem_ld_32x32(tl + C::COL_S + c * 32, rs);
-          tmem_ld_32x32(tl + C::COL_DP + c * 32, rp);
-          tmem_ld_wait();
+          const uint32_t(&rs)[32] = rs2[cc];
+          const uint32_t(&rp)[32] = rp2[cc];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
@@ -837,15 +893,21 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
     while (b2) { const int t = a % b2; a = b2; b2 = t; }
     sched.cyc_rounds = sched.n_qt / a;
   }
-  if (dh == 64) {
-    static bool once = (set_smem(attn_fwd_kernel<64>, FwdCfg<64>::SMEM), true);
-    (void)once;
-    attn_fwd_kernel<64><<<grid, 320, FwdCfg<64>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0, sched);
-  } else {
-    static bool once = (set_smem(attn_fwd_kernel<128>, FwdCfg<128>::SMEM), true);
-    (void)once;
-    attn_fwd_kernel<128><<<grid, 320, FwdCfg<128>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, causal ? 1 : 0, sched);
+  // NS = column parts per query row = softmax warps per SM sub-partition (PB_ATTN_NS=2|4 overrides for experiments)
+  static const int ns_env = [] { const char* e = std::getenv("PB_ATTN_NS"); return e ? std::atoi(e) : 0; }();
+  const int ns = (ns_env == 2 || ns_env == 4) ? ns_env : 2;   // measured: 407 us (NS=2) vs 432 us (NS=4) at b32 H12 S2048
+#define PB_FWD(DHV, NSV)                                                                                              \
+  {                                                                                                                   \
+    static bool once = (set_smem(attn_fwd_kernel<DHV, NSV>, FwdCfg<DHV>::SMEM), true);                                 \
+    (void)once;                                                                                                       \
+    attn_fwd_kernel<DHV, NSV><<<grid, (4 * NSV + 2) * 32, FwdCfg<DHV>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, \
+                                                                                 causal ? 1 : 0, sched);             \
   }
+  if (dh == 64 && ns == 4) PB_FWD(64, 4)
+  else if (dh == 64) PB_FWD(64, 2)
+  else if (ns == 4) PB_FWD(128, 4)
+  else PB_FWD(128, 2)
+#undef PB_FWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention fwd launch: ") + cudaGetErrorString(e));
 }
@@ -885,7 +947,9 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
     while (b2) { const int t = a % b2; a = b2; b2 = t; }
     sched.cyc_rounds = sched.n_qt / a;
   }
-  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0, sched);
+  static const int dq_red = [] { const char* e = std::getenv("PB_ATTN_DQ_RED"); return e ? std::atoi(e) : 0; }();
+  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0, sched,
+                                                   g_dq_acc, dq_red);
   attn_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(g_dq_acc, (__nv_bfloat16*)dqkv, rows, d, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention bwd launch: ") + cudaGetErrorString(e));

@@ -26,19 +26,23 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KiB
 constexpr int EPI_BUF = 128 * 128;    // 128 rows x 128 B (one swizzle atom wide)
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two groups of four)
 constexpr int TMEM_COLS = 512;
 
 // Shared-memory plan per (epilogue, cluster) variant. A CTA of a pair stages only HALF of the B tile, so a stage is
-// 32 instead of 48 KiB and the same 227 KiB hold a 6-deep (5 for the two-output GELU epilogue) instead of a 3-deep TMA
-// pipeline: ~3000 instead of ~1500 tensor-core clocks of loads in flight per SM.
+// 32 instead of 48 KiB and the same 227 KiB hold a 5-deep instead of a 3-deep TMA pipeline (plus 64 KiB of epilogue
+// staging): ~2500 instead of ~1500 tensor-core clocks of loads in flight per SM.
 template <int EPI, int CL>
 struct Cfg {
   static constexpr int B_STAGE = (BN / CL) * BK * 2;   // 32 KiB (CL=1) / 16 KiB (CL=2)
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
   static constexpr int STORES = (EPI == EPI_GELU_DUAL) ? 2 : 1;   // staging buffers consumed per epilogue chunk
-  static constexpr int EPI_BUFS = (CL == 1) ? 4 : 2 * STORES;
-  static constexpr int STAGES = (CL == 1) ? 3 : (EPI == EPI_GELU_DUAL ? 5 : 6);
+  // two epilogue groups (even / odd column chunks of a tile), two staging buffers each: the exact-erf GELU epilogues
+  // measured ALU-bound with one epilogue warp per SM sub-partition (dGELU dgrad 634 TFLOP/s against 1400+ for the
+  // plain epilogue on the same shape)
+  static constexpr int EPI_BUFS_G = 2;
+  static constexpr int EPI_BUFS = 2 * EPI_BUFS_G;
+  static constexpr int STAGES = (CL == 1) ? 3 : 5;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF + 256 + 1024;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB dynamic shared memory of sm_100");
 };
@@ -94,7 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4 * CL);  // one arrival per epilogue warp (of both CTAs: the leader's MMA warp waits for the pair)
+      mbar_init(&tempty[a], 8 * CL);  // one arrival per epilogue warp (of both CTAs: the leader's MMA warp waits for the pair)
     }
     fence_barrier_init();
   }
@@ -200,16 +204,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
           const uint32_t b_base = smem_u32(sB + stage * B_STAGE);
-          const uint64_t ad0 = A_MN ? make_smem_desc_sw128(a_base, BK * 128, 1024) : make_smem_desc_sw128(a_base, 16, 1024);
-          const uint64_t bd0 = B_MN ? make_smem_desc_sw128(b_base, BK * 128, 1024) : make_smem_desc_sw128(b_base, 16, 1024);
+          const uint32_t ad0 = smem_desc_lo(a_base, A_MN ? BK * 128 : 16);
+          const uint32_t bd0 = smem_desc_lo(b_base, B_MN ? BK * 128 : 16);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // k-step inside the stage: UK rows of 128 B (MN-major) or UK elements of 2 B (K-major), in 16-byte descriptor units
-            const uint64_t adesc = ad0 + uint64_t(A_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
-            const uint64_t bdesc = bd0 + uint64_t(B_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
+            const uint32_t adesc = ad0 + uint32_t(A_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
+            const uint32_t bdesc = bd0 + uint32_t(B_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
             if (elect_one()) {
-              if (CL > 1) tc_mma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CL > 1) tc_mma_f16_ss_2sm_lo(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_f16_ss_lo(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           if (elect_one()) {
@@ -232,10 +236,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    // ======================= epilogue (4 warps, one TMEM lane quadrant each) =======================
+    // ======================= epilogue (2 groups x 4 warps, one TMEM lane quadrant each) =======================
+    // group g takes the column chunks c = g, g+2, ... of every tile with its own staging buffers, named barrier and
+    // TMA-store issuer: two epilogue warps per SM sub-partition
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int row_in_tile = q * 32 + lane;
-    const bool issuer = (threadIdx.x == 128);
+    const bool issuer = (threadIdx.x == 128 + grp * 128);
+    uint8_t* sEg = sE + grp * (C::EPI_BUFS_G * EPI_BUF);
+    constexpr int EPI_BUFS_G = C::EPI_BUFS_G;
     constexpr int CW = (EPI == EPI_F32) ? 32 : 64;             // columns per staged chunk (128 B wide)
     constexpr int STORES = C::STORES;                           // staging buffers consumed per chunk
     int ebuf = 0;
@@ -251,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long row = (long long)m_blk * BM + row_in_tile;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / CW; ++c) {
+      for (int c = grp; c < BN / CW; c += 2) {
         const int col0 = n_blk * BN + c * CW;
         if (col0 >= p.N) break;  // whole chunk out of range (uniform)
         // aux tile (residual / pre-activation) for this chunk: issue the global loads FIRST so their latency
@@ -287,10 +296,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        uint8_t* buf0 = sE + ebuf * EPI_BUF;
-        uint8_t* buf1 = sE + ((ebuf + 1) % EPI_BUFS) * EPI_BUF;
-        if (issuer) tma_wait_read<EPI_BUFS / STORES - 1>();
-        named_bar_sync(1, 128);
+        uint8_t* buf0 = sEg + ebuf * EPI_BUF;
+        uint8_t* buf1 = sEg + ((ebuf + 1) % EPI_BUFS_G) * EPI_BUF;
+        if (issuer) tma_wait_read<EPI_BUFS_G / STORES - 1>();
+        named_bar_sync(1 + grp, 128);
         if (EPI == EPI_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -342,7 +351,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         if (issuer) {
           if (EPI == EPI_F32 && (p.accumulate || p.splits > 1)) {
             tma_reduce_add_2d(&tmD, buf0, col0, m_blk * BM);
@@ -352,7 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (EPI == EPI_GELU_DUAL) tma_store_2d(&tmD2, buf1, col0, m_blk * BM);
           tma_commit();
         }
-        ebuf = (ebuf + STORES) % EPI_BUFS;
+        ebuf = (ebuf + STORES) % EPI_BUFS_G;
       }
       tc_fence_before();
       __syncwarp();
