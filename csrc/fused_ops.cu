@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -219,6 +220,108 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const __nv_bfloat16* __r
         fx[k] = rs * (fg[k] * g[k] - c1 - xh * c2) + fr[k];
       }
       outr[c * 32 + lane] = pack8(fx);
+    }
+  }
+}
+
+// Same row-wise dx, plus the column reductions dbeta[j] += sum_t dy[t,j], dgamma[j] += sum_t dy[t,j] * xhat[t,j] in the SAME
+// pass (persistent warps keep per-lane column partials in registers; one smem reduction + one atomicAdd per column per
+// block at the end). Saves the second read of dy and x that a separate column-reduce kernel needs. d <= 1024.
+template <int LN_NCH>
+__global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, long long T, int d) {
+  __shared__ float sred[8][LN_NCH * 256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float ag[LN_NCH][8], ab[LN_NCH][8];
+#pragma unroll
+  for (int c = 0; c < LN_NCH; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ag[c][k] = 0.f, ab[c][k] = 0.f;
+  auto load_gamma = [&](int c, float (&g)[8]) {   // L1-resident after the first row; keeping it in registers costs occupancy
+    const int e = c * 256 + lane * 8;
+    if (e < d) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
+      g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w, g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = 0.f;
+    }
+  };
+  for (long long row = (long long)blockIdx.x * 8 + w; row < T; row += nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
+    const uint4* gr = reinterpret_cast<const uint4*>(dy + row * d);
+    const float mu = mean[row], rs = rstd[row];
+    uint4 bx[LN_NCH], bg[LN_NCH];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_NCH; ++c) {
+      const int e = c * 256 + lane * 8;
+      if (e < d) {
+        bx[c] = xr[c * 32 + lane];
+        bg[c] = gr[c * 32 + lane];
+      } else {
+        bx[c] = make_uint4(0, 0, 0, 0), bg[c] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < LN_NCH; ++c) {
+      float fx[8], fg[8], g[8];
+      unpack8(bx[c], fx);
+      unpack8(bg[c], fg);
+      load_gamma(c, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (fx[k] - mu) * rs;
+        const float dxh = fg[k] * g[k];
+        c1 += dxh;
+        c2 += dxh * xh;
+        ab[c][k] += fg[k];
+        ag[c][k] += fg[k] * xh;
+      }
+    }
+    c1 = warp_sum(c1) / d;
+    c2 = warp_sum(c2) / d;
+    uint4* outr = reinterpret_cast<uint4*>(dx + row * d);
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * d) : nullptr;
+#pragma unroll
+    for (int c = 0; c < LN_NCH; ++c) {
+      const int e = c * 256 + lane * 8;
+      if (e < d) {
+        float fx[8], fg[8], g[8], fr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unpack8(bx[c], fx);
+        unpack8(bg[c], fg);
+        load_gamma(c, g);
+        if (rr) unpack8(rr[c * 32 + lane], fr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (fx[k] - mu) * rs;
+          fx[k] = rs * (fg[k] * g[k] - c1 - xh * c2) + fr[k];
+        }
+        outr[c * 32 + lane] = pack8(fx);
+      }
+    }
+  }
+  // block reduction of the column partials: dbeta then dgamma through the same smem
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < LN_NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sred[w][c * 256 + lane * 8 + k] = pass == 0 ? ab[c][k] : ag[c][k];
+    __syncthreads();
+    float* out = pass == 0 ? dbeta : dgamma;
+    if (out) {
+      for (int j = threadIdx.x; j < d; j += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sred[i][j];
+        atomicAdd(out + j, t);
+      }
     }
   }
 }
@@ -527,6 +630,19 @@ void layernorm_bwd(const void* dy, const void* x, const float* gamma, const floa
                    float* dgamma, float* dbeta, long long T, int d, cudaStream_t st) {
   if (d % 8 || d > LN_MAXCH * 256) throw std::runtime_error("layernorm: d must be a multiple of 8 and <= 4096");
   const int nch = (d + 255) / 256;
+  if ((dgamma || dbeta) && nch <= 4) {
+    // d <= 1024: dx and the dgamma / dbeta column sums in ONE pass over dy and x
+    const int grid = int(std::min<long long>((T + 7) / 8, 148 * 2));   // 2 resident blocks per SM
+#define PB_LN_FUSED(N)                                                                                                      \
+  if (nch <= N) {                                                                                                           \
+    ln_bwd_fused_kernel<N><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd,           \
+                                                 (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, T, d);      \
+    PB_CHECK_LAUNCH("layernorm_bwd_fused");                                                                                 \
+    return;                                                                                                                 \
+  }
+    PB_LN_FUSED(1) PB_LN_FUSED(2) PB_LN_FUSED(3) PB_LN_FUSED(4)
+#undef PB_LN_FUSED
+  }
   bool done = false;
 #define PB_LN_BWD(N)                                                                                                  \
   if (!done && nch <= N) {                                                                                            \
