@@ -321,6 +321,7 @@ void set_wsum(int64_t ctl_ptr, int device, double w, bool zero_sums) {
 
 long long launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches = 0; }
+void add_launch_count(long long n) { g_launches += n; }  // launches replayed from a CUDA graph
 
 }  // namespace
 
@@ -354,6 +355,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ctl_sums_word_offset", &pb::ctl_sums_word_offset);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
+  m.def("add_launch_count", &add_launch_count);
   m.attr("CTL_WORDS") = pb::CTL_WORDS;
   m.attr("EPI_BF16") = int(pb::EPI_BF16);
   m.attr("EPI_RESIDUAL") = int(pb::EPI_RESIDUAL);

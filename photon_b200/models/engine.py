@@ -64,10 +64,18 @@ class B200Engine:
                                       "set kernels.*=torch for ALiBi/RoPE variants")
         if frozen_layers or unfrozen_layers:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
+        if precision == "amp_fp8":
+            # the reference only sketches fp8 (TransformerEngine line commented out, scripts/centralised_training.sh:91);
+            # here the config is accepted and computed in bf16 until the block-scaled kind::f8f6f4 GEMM lands
+            print("[engine] precision=amp_fp8: GEMMs run in bf16 on this build (fp8 tensor-core path not enabled)", flush=True)
         ops.ext()  # fail loudly if the extension is missing
         self.precision = precision
         kernels = dict(kernels or {})
         self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
+        # kernels.cuda_graph: the ~330 launches of one microbatch are captured once per (batch, seq, loss scaling) and
+        # replayed (the schedule is static: preallocated workspace, TMA descriptors baked into the launches)
+        self.use_graph = bool(kernels.get("cuda_graph", True))
+        self._graphs: dict[tuple, Any] = {}
         if self.attn_mode == "b200" and cfg.d_head != 64:
             # our tcgen05 backward is d_head-64 only (TMEM budget); forward exists for 128. Use the library attention for
             # BOTH directions rather than mixing (explicit + logged; GEMM/LN/CE/optimizer stay on our kernels)
@@ -127,6 +135,7 @@ class B200Engine:
         if key in self._ws:
             return self._ws[key]
         self._ws.clear()  # one live shape at a time (activations dominate memory)
+        self._graphs.clear()  # captured graphs point into the old workspace
         c, dev = self.cfg, self.device
         T, d, H, L = b * S, c.d_model, c.n_heads, c.n_layers
         bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
@@ -239,19 +248,56 @@ class B200Engine:
         ops.embed_bwd(ids.reshape(-1), dh, self.d_wte, self.d_wpe, S)
 
     # ---------------------------------------------------------------- protocol
-    def fwd_bwd(self, ids: torch.Tensor, denom: float, scale: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
-        """Accumulate d(Σ token-loss · scale / denom) into ``flat.grads``; returns (loss_sum, n_tokens)."""
-        n0 = ops.launch_count()
+    def _fwd_bwd_eager(self, ids: torch.Tensor, grad_scale: float) -> None:
         b, S = ids.shape
         ws = self._workspace(b, S)
         targets = shift_labels(ids).reshape(-1)
         self._stats.zero_()
         self._forward(ids, ws)
-        self._head(ws, targets, scale / denom, train=True)
+        self._head(ws, targets, grad_scale, train=True)
         self._backward(ids, ws)
-        self.launches_per_microbatch = ops.launch_count() - n0
+
+    def fwd_bwd(self, ids: torch.Tensor, denom: float, scale: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
+        """Accumulate d(Σ token-loss · scale / denom) into ``flat.grads``; returns (loss_sum, n_tokens)."""
+        b, S = ids.shape
+        grad_scale = scale / denom
+        graphable = self.use_graph and self.attn_mode == "b200" and not self.collect_activation_stats
+        if not graphable:
+            n0 = ops.launch_count()
+            self._fwd_bwd_eager(ids, grad_scale)
+            self.launches_per_microbatch = ops.launch_count() - n0
+        else:
+            key = (b, S, float(grad_scale))
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._capture(ids, grad_scale, key)
+            g["ids"].copy_(ids, non_blocking=True)
+            g["graph"].replay()
+            ops.add_launch_count(self.launches_per_microbatch)   # replayed launches are still our kernels
         st = self._stats.clone()
         return st[0], st[1]
+
+    def _capture(self, ids: torch.Tensor, grad_scale: float, key: tuple) -> dict[str, Any]:
+        """Warm up eagerly on a side stream (lazy allocations, kernel attributes), then capture one microbatch.
+        Gradients accumulate into ``flat.grads`` — they are saved around the warm-up / capture passes."""
+        if len(self._graphs) >= 4:      # shapes changed (auto microbatch, eval): drop old graphs with their static inputs
+            self._graphs.clear()
+        static_ids = ids.clone()
+        saved = self.flat.grads.clone()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            n0 = ops.launch_count()
+            self._fwd_bwd_eager(static_ids, grad_scale)
+            self.launches_per_microbatch = ops.launch_count() - n0
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._fwd_bwd_eager(static_ids, grad_scale)
+        self.flat.grads.copy_(saved)
+        g = {"graph": graph, "ids": static_ids}
+        self._graphs[key] = g
+        return g
 
     @torch.no_grad()
     def eval_stats(self, ids: torch.Tensor) -> dict[str, torch.Tensor]:
@@ -271,4 +317,5 @@ class B200Engine:
         self.model.train(on)
 
     def close(self) -> None:
+        self._graphs.clear()
         self._ws.clear()

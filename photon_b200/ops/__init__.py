@@ -46,6 +46,11 @@ def reset_launch_count() -> None:
     ext().reset_launch_count()
 
 
+def add_launch_count(n: int) -> None:
+    """Account for kernels replayed from a captured CUDA graph (they never pass through the bindings)."""
+    ext().add_launch_count(int(n))
+
+
 # --------------------------------------------------------------------------------- GEMM
 EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
 

@@ -21,7 +21,8 @@ def test_fed_round_multi_gpu_matches_oracle(kind):
     from photon_b200.strategy.strategies import FedAdam, FedAvgEfficient, FedMom, FedNesterov, FedYogi, server_opt_step
 
     mk = {"fedavg": lambda: FedAvgEfficient(0.7), "nesterov": lambda: FedNesterov(0.7, 0.9), "fedmom": lambda: FedMom(0.5, 0.8),
-          "fedadam": lambda: FedAdam(tau=1e-3), "fedyogi": lambda: FedYogi()}[kind]  # tau: keep m/sqrt(v) away from sign(pg)
+          "fedadam": lambda: FedAdam(tau=5e-2), "fedyogi": lambda: FedYogi()}[kind]
+    # tau: Adam-type steps are eta*pg/(|pg|+tau) in round 1 - a 1-ulp difference in the fp32 mean is amplified by eta/tau near pg = 0
     strat, ref = mk(), mk()
     total = 1 << 20
     torch.manual_seed(0)
