@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -448,27 +449,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
 }
 
 // ======================================================================================= backward
-// delta[b,h,q] = sum_d dO * O   (row-wise; feeds dS = P * (dP - delta))
-__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
-                                      int S, int H, int DH, long long rows) {
-  const int lane = threadIdx.x & 31;
-  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;  // one warp per (row, head)
-  if (gw >= rows * H) return;
-  const long long r = gw / H;
-  const int h = int(gw % H);
-  const __nv_bfloat16* po = o + r * (long long)(H * DH) + h * DH;
-  const __nv_bfloat16* pd = dout + r * (long long)(H * DH) + h * DH;
-  float acc = 0.f;
-  for (int i = lane * 2; i < DH; i += 64) {
-    const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(po + i));
-    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(pd + i));
-    acc += a.x * g.x + a.y * g.y;
-  }
+// delta[b,h,q] = sum_d dO * O   (row-wise; feeds dS = P * (dP - delta)).  One thread per 8 contiguous elements (16-byte
+// loads), DH/8 adjacent lanes form one (row, head) group and reduce with shuffles; the delta store is scattered but tiny.
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                              float* __restrict__ delta, int S, int H, int DH, long long rows) {
+  const int gl = DH / 8;                                  // lanes per (row, head): 8 for d_head 64, 16 for 128
+  const long long n8 = rows * H * gl;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o) + i);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout) + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    float acc = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, off);
-  if (lane == 0) {
-    const long long bb = r / S, s = r % S;
-    delta[(bb * H + h) * S + s] = acc;
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = unpack_bf16(aw[t]), fg = unpack_bf16(gw[t]);
+      acc += fa.x * fg.x + fa.y * fg.y;
+    }
+    for (int off = gl >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, off);
+    if ((i % gl) == 0) {
+      const long long rh = i / gl, r = rh / H;
+      const int h = int(rh - r * H);
+      const long long bb = r / S, sq = r - bb * S;
+      delta[(bb * H + h) * S + sq] = acc;
+    }
   }
 }
 
@@ -786,40 +789,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
       int b, h, jt, i0, n_it;
       item_of(k, b, h, jt, i0, n_it);
+      float nx_lse, nx_dl;
+      {
+        const long long g0 = (long long)(b * H + h) * S + i0 * 128 + row;
+        nx_lse = lse[g0];
+        nx_dl = delta[g0];
+      }
       auto row_tile = [&](int t, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
         const int qt = i0 + t;
-        const long long grow = (long long)(b * H + h) * S + qt * 128 + row;
-        const float lse2 = lse[grow] * LOG2E;
-        const float dl = delta[grow];
+        const float lse2 = nx_lse * LOG2E;   // this tile's row statistics were fetched one tile ahead
+        const float dl = nx_dl;
         mbar_wait(sdp_full, n & 1);
         tc_fence_after();
         uint32_t pk[32], dk[32];  // packed bf16 P and dS of this thread's 64 columns, kept in registers
         uint32_t rs2[2][32], rp2[2][32];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          tmem_ld_32x32(tl + C::COL_S + (half * 2 + cc) * 32, rs2[cc]);
-          tmem_ld_32x32(tl + C::COL_DP + (half * 2 + cc) * 32, rp2[cc]);
-        }
+        float pf[64];             // fp32 probabilities until dS is formed
+        // S first; the dP loads are in flight while the exponentials run (a TMEM x32 round trip is ~80 clk per warp)
+        tmem_ld_32x32(tl + C::COL_S + (half * 2) * 32, rs2[0]);
+        tmem_ld_32x32(tl + C::COL_S + (half * 2 + 1) * 32, rs2[1]);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(sdp_free);   // S_n / dP_n are in registers: the MMA warp may overwrite them with tile n+1
+        tmem_ld_32x32(tl + C::COL_DP + (half * 2) * 32, rp2[0]);
+        tmem_ld_32x32(tl + C::COL_DP + (half * 2 + 1) * 32, rp2[1]);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = half * 2 + cc;  // 32-column block of the row
-          const uint32_t(&rs)[32] = rs2[cc];
-          const uint32_t(&rp)[32] = rp2[cc];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            float p0 = exp2f(fmaf(__uint_as_float(rs[e]), sc, -lse2));
-            float p1 = exp2f(fmaf(__uint_as_float(rs[e + 1]), sc, -lse2));
+            float p0 = exp2f(fmaf(__uint_as_float(rs2[cc][e]), sc, -lse2));
+            float p1 = exp2f(fmaf(__uint_as_float(rs2[cc][e + 1]), sc, -lse2));
             if (DIAG) {
               if (c * 32 + e > row) p0 = 0.f;
               if (c * 32 + e + 1 > row) p1 = 0.f;
             }
-            const float s0 = p0 * (__uint_as_float(rp[e]) - dl);
-            const float s1 = p1 * (__uint_as_float(rp[e + 1]) - dl);
+            pf[cc * 32 + e] = p0, pf[cc * 32 + e + 1] = p1;
             pk[cc * 16 + (e >> 1)] = pack_bf16(p0, p1);
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_free);   // S_n / dP_n are in registers: the MMA warp may overwrite them with tile n+1
+        // row statistics of the next tile of this item (the first tile of an item fetches its own)
+        if (t + 1 < n_it) {
+          const long long gnext = (long long)(b * H + h) * S + (qt + 1) * 128 + row;
+          nx_lse = lse[gnext];
+          nx_dl = delta[gnext];
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float s0 = pf[cc * 32 + e] * (__uint_as_float(rp2[cc][e]) - dl);
+            const float s1 = pf[cc * 32 + e + 1] * (__uint_as_float(rp2[cc][e + 1]) - dl);
             dk[cc * 16 + (e >> 1)] = pack_bf16(s0, s1);
           }
         }
@@ -927,10 +948,9 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
   }
   cudaMemsetAsync(g_dq_acc, 0, need, st);
   {
-    const long long warps = rows * H;
-    const int threads = 256;
-    attn_bwd_delta_kernel<<<int((warps * 32 + threads - 1) / threads), threads, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
-                                                                                         delta, S, H, dh, rows);
+    const long long n8 = rows * H * (dh / 8);
+    const int blocks = int(std::min<long long>((n8 + 255) / 256, 148 * 16));
+    attn_bwd_delta_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, S, H, dh, rows);
   }
   CUtensorMap tmQKV = make_tmap_2d(qkv, 2, false, uint64_t(3) * d, uint64_t(rows), uint64_t(3) * d * 2, 64, 128);
   CUtensorMap tmDO = make_tmap_2d(dout, 2, false, uint64_t(d), uint64_t(rows), uint64_t(d) * 2, 64, 128);

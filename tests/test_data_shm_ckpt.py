@@ -134,3 +134,47 @@ def test_set_client_load_path_decision_table(tmp_path):
     assert set_client_load_path(t, 3, 128) == (True, True) and t.save_folder is None                             # round already done: skip
     t = cfg()
     assert set_client_load_path(t, 3, 32) == (False, False)                                                     # only newer checkpoints
+
+
+def test_object_store_facade_and_run_listing(tmp_path):
+    """RemoteUploaderDownloader call surface (ref: photon/utils.py:955-1014) and CheckpointStore.obtain_sorted_runs."""
+    from photon_b200.checkpoint.store import CheckpointStore
+    from photon_b200.utils.core import create_remote_up_down
+
+    r = create_remote_up_down("bkt", "pre", "run1", 2, root=tmp_path)
+    src = tmp_path / "a.bin"
+    src.write_bytes(b"hello")
+    r.upload_file("x/y/a.bin", src)
+    assert r.list_objects() == ["x/y/a.bin"] and r.list_objects("x") == ["x/y/a.bin"]
+    with pytest.raises(FileExistsError):
+        r.upload_file("x/y/a.bin", src, overwrite=False)
+    r.download_file("x/y/a.bin", tmp_path / "out" / "b.bin")
+    assert (tmp_path / "out" / "b.bin").read_bytes() == b"hello"
+    r.delete_object("x/y/a.bin")
+    assert r.list_objects() == []
+
+    store = CheckpointStore(tmp_path / "ck")
+    for run in ("r_old", "r_new"):
+        (store.server_dir(run) / "1").mkdir(parents=True)
+    import os
+    import time
+    os.utime(store.bucket / "r_old", (time.time() - 100, time.time() - 100))
+    assert store.obtain_sorted_runs() == ["r_old", "r_new"]
+
+
+def test_streaming_shm_cleanup_removes_only_our_segments():
+    from multiprocessing import shared_memory
+
+    from photon_b200.clients.utils import streaming_shms_clean_up
+
+    ours = shared_memory.SharedMemory(name="pb200_test_leak", create=True, size=64)
+    other = shared_memory.SharedMemory(name="zz_not_ours_seg", create=True, size=64)
+    try:
+        ours.close()
+        assert streaming_shms_clean_up() >= 1
+        with pytest.raises(FileNotFoundError):
+            shared_memory.SharedMemory(name="pb200_test_leak")
+        shared_memory.SharedMemory(name="zz_not_ours_seg").close()   # untouched
+    finally:
+        other.close()
+        other.unlink()

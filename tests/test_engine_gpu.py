@@ -100,3 +100,28 @@ def test_engine_activation_checkpointing_is_exact():
     rel = ((a.flat.grads - b.flat.grads).norm() / a.flat.grads.norm()).item()
     assert rel < 1e-3, rel   # split-K reduce-add order is the only non-determinism
     assert b.launches_per_microbatch > a.launches_per_microbatch
+
+
+def test_engine_cuda_graph_replay_matches_eager():
+    """kernels.cuda_graph: the captured microbatch schedule accumulates the same gradients as eager launches, for
+    fresh token ids on every replay."""
+    from photon_b200.models.engine import B200Engine
+    from photon_b200.models.mpt import MPTConfig
+
+    cfg = MPTConfig(d_model=256, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=2048, attn_impl="flash")
+    dev = torch.device("cuda", 0)
+    a = B200Engine(cfg, dev, "amp_bf16", {"cuda_graph": False}, seed=5)
+    b = B200Engine(cfg, dev, "amp_bf16", {"cuda_graph": True}, seed=5)
+    assert not a.use_graph and b.use_graph
+    a.flat.zero_grad(), b.flat.zero_grad()
+    denom = float(2 * (cfg.max_seq_len - 1))
+    for i in range(3):   # first call captures, the next two replay with different inputs
+        ids = torch.randint(0, cfg.vocab_size, (2, cfg.max_seq_len), device=dev)
+        la, na = a.fwd_bwd(ids, denom)
+        lb, nb = b.fwd_bwd(ids, denom)
+        torch.cuda.synchronize()
+        assert int(na) == int(nb) and abs(float(la) - float(lb)) <= 1e-3 * abs(float(la)), (i, float(la), float(lb))
+    assert len(b._graphs) == 1
+    rel = ((a.flat.grads - b.flat.grads).norm() / a.flat.grads.norm()).item()
+    assert rel < 1e-3, rel
+    assert b.launches_per_microbatch == a.launches_per_microbatch > 0
