@@ -313,6 +313,29 @@ void ddp_allreduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, i
                            at::cuda::getCurrentDeviceProperties()->multiProcessorCount, at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += out_norm.has_value() ? 2 : 1;
 }
+void ddp_zero_step(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& grad_ptrs,
+                   const std::vector<int64_t>& param_ptrs, const std::vector<int64_t>& shadow_ptrs, Tensor m, Tensor v, int64_t lo, int64_t hi,
+                   int64_t kind, bool first_step, double lr, double beta1, double beta2, double eps, double decay, double clip,
+                   double step_size, double inv_sqrt_bc2, double max_norm, double grad_mult, c10::optional<Tensor> out_norm) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  pb::CommCtl c = make_ctl(ctl_ptrs, rank);
+  pb::ZeroStepArgs a{};
+  for (int i = 0; i < c.n; ++i) {
+    a.grads[i] = reinterpret_cast<float*>(grad_ptrs[i]);
+    a.params[i] = reinterpret_cast<float*>(param_ptrs[i]);
+    a.shadow[i] = shadow_ptrs.empty() ? nullptr : reinterpret_cast<void*>(shadow_ptrs[i]);
+  }
+  TORCH_CHECK(m.numel() == hi - lo && v.numel() == hi - lo, "ddp_zero_step: moment shards must have hi - lo elements");
+  a.m = m.data_ptr<float>(), a.v = v.data_ptr<float>();
+  a.lo = lo, a.hi = hi;
+  a.h.kind = int(kind), a.h.first_step = first_step ? 1 : 0;
+  a.h.lr = float(lr), a.h.beta1 = float(beta1), a.h.beta2 = float(beta2), a.h.eps = float(eps), a.h.decay = float(decay);
+  a.h.clip = float(clip), a.h.step_size = float(step_size), a.h.inv_sqrt_bc2 = float(inv_sqrt_bc2);
+  a.max_norm = float(max_norm), a.grad_mult = float(grad_mult);
+  pb::ddp_zero_step_launch(a, c, uint32_t(epoch), out_norm.has_value() ? out_norm->data_ptr<float>() : nullptr,
+                           at::cuda::getCurrentDeviceProperties()->multiProcessorCount, at::cuda::getCurrentCUDAStream(device).stream());
+  g_launches += 1;
+}
 void set_wsum(int64_t ctl_ptr, int device, double w, bool zero_sums) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::set_wsum(reinterpret_cast<uint32_t*>(ctl_ptr), float(w), zero_sums, at::cuda::getCurrentCUDAStream(device).stream());
@@ -351,6 +374,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("fed_round", &fed_round);
   m.def("ddp_allreduce", &ddp_allreduce);
+  m.def("ddp_zero_step", &ddp_zero_step);
   m.def("set_wsum", &set_wsum);
   m.def("ctl_sums_word_offset", &pb::ctl_sums_word_offset);
   m.def("launch_count", &launch_count);

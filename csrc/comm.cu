@@ -19,6 +19,7 @@
 #include <string>
 
 #include "comm.h"
+#include "optim_dev.cuh"
 #include "ptx.cuh"
 
 namespace pb {
@@ -33,9 +34,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Control page layout (uint32 words) inside every rank's arena:
 //   [0,8)   start flags (slot r written by rank r)      [8,16)  end flags
-//   [16]    local "go" flag (block 0 -> other blocks)   [17]    local done-block counter
+//   [16]    local "go" flag (block 0 -> other blocks)   [17]    local done-block counter   [24,32) mid-kernel flags
 //   [32,34) float wsum (this rank's sum of client weights)   [64..) double sq_parts[8], double sums[8]
-constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_GO2 = 18, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
+constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_GO2 = 18, CP_MID = 24, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
 
 __device__ __forceinline__ void grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
   uint32_t* mine = c.ctl[c.rank];
@@ -246,6 +247,108 @@ __global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------ N1 + K11 + K12
+// Phase 1: every rank sums its shard of all gradient planes over NVLink (mean folded in), keeps the result in its own
+// plane and publishes the shard's squared norm to every rank. Mid barrier. Phase 2: clip coefficient from the global norm,
+// local optimizer on the shard of (p, m, v), new fp32 masters and bf16 casts pushed into every rank's planes.
+__global__ void __launch_bounds__(512) ddp_zero_step_kernel(const ZeroStepArgs a, const CommCtl c, const uint32_t epoch, float* out_norm) {
+  grid_peer_barrier_start(c, epoch);
+  uint32_t* mine = c.ctl[c.rank];
+  const float inv = a.grad_mult / c.n;
+  float sq = 0.f;
+  const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
+  float* gmine = a.grads[c.rank];
+  for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {
+      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.grads[p]) + i);
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    acc.x *= inv, acc.y *= inv, acc.z *= inv, acc.w *= inv;
+    sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    reinterpret_cast<float4*>(gmine)[i] = acc;   // re-read by the same thread in phase 2
+  }
+  __shared__ float red[16];
+  __shared__ float s_coef;
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  double* sums = reinterpret_cast<double*>(mine + CP_SUMS);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(sums + 7, double(t));
+  }
+  if (grid_done(c)) {   // last block: publish the shard norm to every rank, cross-GPU barrier, release the grid
+    if (threadIdx.x < c.n) {
+      const double part = *reinterpret_cast<volatile double*>(sums + 7);
+      double* dst = reinterpret_cast<double*>(c.ctl[threadIdx.x] + CP_SQPARTS) + c.rank;
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(part) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sums[7] = 0.0;
+    __threadfence_system();
+    if (threadIdx.x < c.n) {
+      st_release_sys(c.ctl[threadIdx.x] + CP_MID + c.rank, epoch);
+      while (ld_acquire_sys(mine + CP_MID + threadIdx.x) < epoch) {
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mine + CP_GO2), "r"(epoch) : "memory");
+    }
+  }
+  if (threadIdx.x == 0) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + CP_GO2) : "memory");
+    } while (v < epoch);
+    const double* parts = reinterpret_cast<const double*>(mine + CP_SQPARTS);
+    double t = 0.0;
+    for (int p = 0; p < c.n; ++p) {
+      double x;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(parts + p) : "memory");
+      t += x;
+    }
+    const float norm = float(sqrt(t));
+    s_coef = a.max_norm > 0.f ? fminf(1.0f, a.max_norm / (norm + 1e-6f)) : 1.0f;
+    if (blockIdx.x == 0 && out_norm) *out_norm = norm;
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  // ---- phase 2: optimizer on the shard, broadcast of the new masters + bf16 casts
+  for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 G = reinterpret_cast<const float4*>(gmine)[i];
+    const float4 P = reinterpret_cast<const float4*>(a.params[c.rank])[i];
+    float pp[4] = {P.x, P.y, P.z, P.w};
+    const float gg[4] = {G.x * coef, G.y * coef, G.z * coef, G.w * coef};
+    float mm[4] = {0.f, 0.f, 0.f, 0.f}, vv[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long li = i - lo4;   // moments are shard-local
+    if (a.h.kind != 2) {
+      const float4 Mv = reinterpret_cast<const float4*>(a.m)[li];
+      const float4 Vv = reinterpret_cast<const float4*>(a.v)[li];
+      mm[0] = Mv.x, mm[1] = Mv.y, mm[2] = Mv.z, mm[3] = Mv.w;
+      vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
+    }
+    optim_update4(pp, gg, mm, vv, a.h);
+    if (a.h.kind != 2) {
+      reinterpret_cast<float4*>(a.m)[li] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(a.v)[li] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    const float4 np = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    uint2 nb;
+    nb.x = pack_bf16(pp[0], pp[1]), nb.y = pack_bf16(pp[2], pp[3]);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {
+      st_peer_f4(reinterpret_cast<float4*>(a.params[p]) + i, np);
+      if (a.shadow[p]) st_peer_u2(reinterpret_cast<uint2*>(a.shadow[p]) + i, nb);
+    }
+  }
+  if (grid_done(c)) peer_barrier_end(c, epoch);
+}
+
 __global__ void allreduce_norm_finalize_kernel(const uint32_t* ctl, int n, float* out_norm) {
   const double* parts = reinterpret_cast<const double*>(ctl + CP_SQPARTS);
   double t = 0.0;
@@ -277,6 +380,12 @@ void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_allreduce launch: ") + cudaGetErrorString(e));
   if (out_norm) allreduce_norm_finalize_kernel<<<1, 1, 0, st>>>(c.ctl[c.rank], c.n, out_norm);
+}
+void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st) {
+  if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("ddp_zero_step: shard bounds must be multiples of 4");
+  ddp_zero_step_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch, out_norm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_zero_step launch: ") + cudaGetErrorString(e));
 }
 void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st) { set_wsum_kernel<<<1, 1, 0, st>>>(ctl, w, zero_sums ? 1 : 0); }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fused_ops.h"
+
 namespace pb {
 
 constexpr int MAX_PEERS = 8;
@@ -34,6 +36,21 @@ struct AllReduceArgs {
   long long lo, hi;
 };
 
+// N1 + K11 + K12 in one launch (ZeRO-style): reduce-scatter of the gradient planes, global-norm clipping, the local
+// optimizer on this rank's shard of (p, m, v), all-gather of the new fp32 masters and their bf16 cast.
+struct ZeroStepArgs {
+  float* grads[MAX_PEERS];      // per-rank flat gradient plane (full length)
+  float* params[MAX_PEERS];     // per-rank fp32 master plane (full length)
+  void* shadow[MAX_PEERS];      // per-rank bf16 compute copy (full length; may be null)
+  float* m;                     // this rank's moment shards (length hi - lo)
+  float* v;
+  long long lo, hi;             // this rank's shard, multiples of 4
+  OptimHyper h;
+  float max_norm;               // <= 0: no clipping
+  float grad_mult;              // 1 / loss scale
+};
+
+void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
 void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st);
 void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
 void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st);

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "fused_ops.h"
+#include "optim_dev.cuh"
 #include "ptx.cuh"
 
 namespace pb {
@@ -530,39 +531,16 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ p, const
     float4 P = reinterpret_cast<float4*>(p)[i];
     float4 G = reinterpret_cast<const float4*>(g)[i];
     float pp[4] = {P.x, P.y, P.z, P.w};
-    float gg[4] = {G.x * gm, G.y * gm, G.z * gm, G.w * gm};
-    if (h.kind == 2) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pp[k] = pp[k] * h.decay - h.lr * gg[k];
-    } else {
-      float4 Mv = reinterpret_cast<float4*>(m)[i];
-      float4 Vv = reinterpret_cast<float4*>(v)[i];
-      float mm[4] = {Mv.x, Mv.y, Mv.z, Mv.w};
-      float vv[4] = {Vv.x, Vv.y, Vv.z, Vv.w};
-      if (h.kind == 0) {  // ADOPT
-        if (h.first_step) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) vv[k] = gg[k] * gg[k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float ng = gg[k] / fmaxf(sqrtf(vv[k]), h.eps);
-            ng = fminf(fmaxf(ng, -h.clip), h.clip);
-            mm[k] = mm[k] + (1.0f - h.beta1) * (ng - mm[k]);
-            pp[k] = pp[k] * h.decay - h.lr * mm[k];
-            vv[k] = h.beta2 * vv[k] + (1.0f - h.beta2) * gg[k] * gg[k];
-          }
-        }
-      } else {  // DecoupledAdamW
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          pp[k] *= h.decay;
-          mm[k] = mm[k] + (1.0f - h.beta1) * (gg[k] - mm[k]);
-          vv[k] = h.beta2 * vv[k] + (1.0f - h.beta2) * gg[k] * gg[k];
-          const float denom = sqrtf(vv[k]) * h.inv_sqrt_bc2 + h.eps;
-          pp[k] -= h.step_size * mm[k] / denom;
-        }
-      }
+    const float gg[4] = {G.x * gm, G.y * gm, G.z * gm, G.w * gm};
+    float mm[4] = {0.f, 0.f, 0.f, 0.f}, vv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h.kind != 2) {
+      const float4 Mv = reinterpret_cast<float4*>(m)[i];
+      const float4 Vv = reinterpret_cast<float4*>(v)[i];
+      mm[0] = Mv.x, mm[1] = Mv.y, mm[2] = Mv.z, mm[3] = Mv.w;
+      vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
+    }
+    optim_update4(pp, gg, mm, vv, h);
+    if (h.kind != 2) {
       reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
       reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }

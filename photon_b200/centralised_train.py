@@ -60,11 +60,11 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
             use_nvl_allreduce = device.type == "cuda" and not all(
                 (cfg.get("kernels") or {}).get(k, "auto") == "torch" for k in ("gemm", "optimizer"))
         if use_nvl_allreduce:
-            from photon_b200.parallel.ddp import NvlGradComm
+            from photon_b200.parallel.ddp import build_nvl_comm, wants_sharded_step
             from photon_b200.utils.flat import layout_for_model_cfg
 
             total = layout_for_model_cfg(cfg["llm_config"]["model"], cc.frozen_layers, cc.unfrozen_layers).total
-            grad_comm = NvlGradComm(total, rank=rank, world_size=world_size, device=device)
+            grad_comm = build_nvl_comm(total, sharded=wants_sharded_step(cfg["llm_config"]), rank=rank, world_size=world_size, device=device)
         else:
             from photon_b200.parallel.ddp import NcclGradComm
 

@@ -85,13 +85,14 @@ class FederationRuntime:
                                   process_group=self.client_group)
         if self.gpus_per_client > 1 and self.device.type == "cuda":
             # intra-client DDP over the fused NVLink all-reduce: the gradient plane lives in a symmetric arena
-            from photon_b200.parallel.ddp import NvlGradComm
+            from photon_b200.parallel.ddp import build_nvl_comm, wants_sharded_step
             from photon_b200.utils.flat import layout_for_model_cfg
 
             fl_ = self.cfg["fl"]
             total = layout_for_model_cfg(self.cfg["llm_config"]["model"], fl_.get("frozen_layers"), fl_.get("unfrozen_layers")).total
-            kw["grad_comm"] = NvlGradComm(total, rank=self.rank % self.gpus_per_client, world_size=self.gpus_per_client,
-                                          device=self.device, group=self.client_group)
+            kw["grad_comm"] = build_nvl_comm(total, sharded=wants_sharded_step(self.cfg["llm_config"]),
+                                             rank=self.rank % self.gpus_per_client, world_size=self.gpus_per_client,
+                                             device=self.device, group=self.client_group)
         elif self.gpus_per_client > 1:
             from photon_b200.parallel.ddp import NcclGradComm
 

@@ -52,7 +52,8 @@ class B200Engine:
                  kernels: dict[str, Any] | None = None, seed: int | None = 17, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
                  lm_head_chunk: int = 18944, grads_storage: torch.Tensor | None = None,
-                 activation_checkpointing: bool = False) -> None:
+                 activation_checkpointing: bool = False, params_storage: torch.Tensor | None = None,
+                 shadow_storage: torch.Tensor | None = None) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -83,8 +84,12 @@ class B200Engine:
             self.attn_mode = "torch"
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
-        self.flat = FlatParams(self.model, device=self.device, grads_storage=grads_storage)
-        self.bf16_params = torch.zeros(self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
+        self.flat = FlatParams(self.model, device=self.device, params_storage=params_storage, grads_storage=grads_storage)
+        # bf16 compute copy; lives in a symmetric arena plane when a fused NVLink step writes it from peer GPUs
+        self.bf16_params = shadow_storage if shadow_storage is not None else torch.zeros(
+            self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
+        if self.bf16_params.numel() != self.flat.layout.total or self.bf16_params.dtype != torch.bfloat16:
+            raise ValueError("shadow_storage must be a bf16 tensor with layout.total elements")
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.lm_head_chunk = int(lm_head_chunk)
         # keep only the block inputs h[i]; every block's internals are recomputed right before its backward

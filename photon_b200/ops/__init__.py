@@ -147,9 +147,8 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 _KIND = {"adopt": 0, "decoupled_adamw": 1, "sgd": 2}
 
 
-def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | None) -> None:
-    """One fused multi-tensor step for a :class:`photon_b200.train.optim.FlatOptimizer`."""
-    flat = opt.flat
+def optimizer_hyper(opt: Any, lr: float) -> dict[str, Any]:
+    """Per-step scalar arguments of the fused optimizer kernels for a :class:`FlatOptimizer` at learning rate ``lr``."""
     kind = _KIND[opt.name]
     first = kind == 0 and opt.step_count == 0
     decay, clip, step_size, inv_sqrt_bc2 = 1.0, float("inf"), 0.0, 1.0
@@ -165,13 +164,21 @@ def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | 
         inv_sqrt_bc2 = 1.0 / math.sqrt(1.0 - opt.beta2 ** t)
     else:
         decay = 1.0 - lr * opt.weight_decay if opt.weight_decay else 1.0
+    return dict(kind=kind, first=first, lr=float(lr), beta1=opt.beta1, beta2=opt.beta2, eps=opt.eps, decay=float(decay),
+                clip=float(clip), step_size=float(step_size), inv_sqrt_bc2=float(inv_sqrt_bc2))
+
+
+def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | None) -> None:
+    """One fused multi-tensor step for a :class:`photon_b200.train.optim.FlatOptimizer`."""
+    flat = opt.flat
+    h = optimizer_hyper(opt, lr)
     gm = None
     if grad_mult is not None:
         gm = grad_mult if torch.is_tensor(grad_mult) else torch.tensor(float(grad_mult), device=flat.params.device)
         gm = gm.to(torch.float32).reshape(1)
     params, grads, shadow = opt.local_views()   # the whole flat buffer, or this rank's slice when the state is sharded
-    ext().fused_optimizer(params, grads, opt.exp_avg, opt.exp_avg_sq, shadow, kind, first, float(lr),
-                          opt.beta1, opt.beta2, opt.eps, float(decay), float(clip), float(step_size), float(inv_sqrt_bc2), gm)
+    ext().fused_optimizer(params, grads, opt.exp_avg, opt.exp_avg_sq, shadow, h["kind"], h["first"], h["lr"],
+                          h["beta1"], h["beta2"], h["eps"], h["decay"], h["clip"], h["step_size"], h["inv_sqrt_bc2"], gm)
 
 
 # ---------------------------------------------------------------------------- attention

@@ -68,14 +68,16 @@ class TorchBackend:
     def __init__(self, cfg: MPTConfig, device: torch.device | str = "cpu", precision: str = "amp_bf16",
                  seed: int | None = 17, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
-                 grads_storage: torch.Tensor | None = None, activation_checkpointing: bool = False) -> None:
+                 grads_storage: torch.Tensor | None = None, activation_checkpointing: bool = False,
+                 params_storage: torch.Tensor | None = None, shadow_storage: torch.Tensor | None = None) -> None:
         self.cfg = cfg
         self.device = torch.device(device)
         self.precision = precision
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.model.activation_checkpointing = bool(activation_checkpointing)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
-        self.flat = FlatParams(self.model, device=self.device, grads_storage=grads_storage)
+        self.flat = FlatParams(self.model, device=self.device, params_storage=params_storage, grads_storage=grads_storage)
+        self.bf16_params = shadow_storage   # only kept so a fused NVLink step has a plane to write (autocast casts on the fly)
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.collect_activation_stats = False
         self.activation_stats: dict[str, float] = {}

@@ -156,11 +156,17 @@ class Trainer:
                                       frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers,
                                       unigram_log_probs=unigram_log_probs,
                                       grads_storage=getattr(grad_comm, "grads", None),
+                                      params_storage=getattr(grad_comm, "params", None),
+                                      shadow_storage=getattr(grad_comm, "shadow", None),
                                       activation_checkpointing=activation_checkpointing)
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
         shard_kw: dict[str, Any] = {}
-        if shard_optimizer_state and self.world_size > 1:
+        self.fused_comm_step = bool(getattr(grad_comm, "fused_step", False)) and self.world_size > 1 and self.scaler is None
+        if self.fused_comm_step:
+            # reduce-scatter + clip + optimizer + all-gather in one NVLink kernel: moments sharded like the arena
+            shard_kw = dict(shard=grad_comm.shard(), shard_bounds=grad_comm.shard_bounds(), group=process_group)
+        elif shard_optimizer_state and self.world_size > 1:
             # ZeRO-style state sharding inside the client (the reference's fsdp_config FULL_SHARD / SHARD_GRAD_OP)
             bounds = shard_bounds(be.flat.params.numel(), self.world_size)
             shard_kw = dict(shard=bounds[self.rank], shard_bounds=bounds, group=process_group)
@@ -254,6 +260,16 @@ class Trainer:
         if self._auto_mb is not None and self.world_size > 1 and st.timestamp.batch == self.fit_start_batch:
             self._auto_mb = self._agree_min(self._auto_mb)
 
+        if self.fused_comm_step:
+            # N1 + K11 + K12 fused: nothing else to do for this batch
+            self._emit("after_backward")
+            gnorm = self.grad_comm.step(st.optimizer, st.optimizer.initial_lr * float(st.scheduler(st.timestamp.batch)),
+                                        self.grad_clip_norm, 1.0 / scale)
+            if self.grad_clip_norm is not None:
+                self.log({"l2_norm/grad/clipped_from": gnorm})
+            self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok}
+            st.timestamp.advance_batch(samples=B * self.world_size, tokens=B * S * self.world_size)
+            return
         # N1: ONE gradient all-reduce on the flat bucket (mean over ranks)
         if self.world_size > 1:
             self._allreduce_grads()

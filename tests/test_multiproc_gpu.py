@@ -33,21 +33,29 @@ def _torchrun(tmp_path, n, body, port):
 
 
 def test_centralised_ddp_fused_allreduce_matches_nccl(tmp_path):
+    """DDP inside one job: fused NVLink all-reduce (replicated optimizer), fused ZeRO step (fsdp_config: reduce-scatter +
+    clip + optimizer shard + all-gather in one kernel) and NCCL + sharded-state broadcast all end on the same parameters."""
     _torchrun(tmp_path, 2, """
         from photon_b200.config import compose
         from photon_b200.centralised_train import run_centralised
         rank = dist.get_rank(); dev = torch.device('cuda', rank)
-        outs = []
-        for nvl in (True, False):
-            cfg = compose(TINY + ['run_uuid=ddp', 'dataset/streams@dataset.train.streams=centralised', 'dataset.train.root_local=synthetic://7'])
+        outs = {}
+        for name, nvl, extra, cls in (('zero', True, [], 'NvlZeroComm'), ('nvl', True, ['~llm_config.fsdp_config'], 'NvlGradComm'),
+                                      ('nccl', False, ['~llm_config.fsdp_config'], 'NcclGradComm'),
+                                      ('nccl_sharded', False, [], 'NcclGradComm')):
+            cfg = compose(TINY + ['run_uuid=ddp', 'dataset/streams@dataset.train.streams=centralised', 'dataset.train.root_local=synthetic://7'] + extra)
             tr = run_centralised(cfg, device=dev, rank=rank, world_size=2, duration='3ba', use_nvl_allreduce=nvl)
-            assert (type(tr.grad_comm).__name__ == 'NvlGradComm') == nvl
-            outs.append(tr.state.flat.params.clone()); tr.close()
-        ref = outs[0].clone(); dist.broadcast(ref, src=0)
-        assert torch.equal(ref, outs[0]), 'ranks diverged'
-        rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
-        assert rel < 2e-3, rel
-        if rank == 0: print('RESULT_OK', rel)
+            assert type(tr.grad_comm).__name__ == cls, (name, type(tr.grad_comm).__name__)
+            assert tr.state.optimizer.sharded == (name in ('zero', 'nccl_sharded')), name
+            x = tr.state.flat.params.clone()
+            ref = x.clone(); dist.broadcast(ref, src=0)
+            assert torch.equal(ref, x), name + ': ranks diverged'
+            if name == 'zero':   # the bf16 compute copy written by the peers equals the cast of the masters
+                assert torch.equal(tr.state.backend.bf16_params, x.to(torch.bfloat16))
+            outs[name] = x; tr.close()
+        rels = {k: ((outs[k] - outs['nccl']).norm() / outs['nccl'].norm()).item() for k in outs}
+        assert all(r < 2e-3 for r in rels.values()), rels
+        if rank == 0: print('RESULT_OK', rels)
     """, 29541)
 
 
