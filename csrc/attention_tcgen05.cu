@@ -487,12 +487,22 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ dq_acc, __n
   }
 }
 
+// d_head = 128 runs the SAME pipeline in NP = 2 passes per (batch*head, key tile): S and dP contract over the full head
+// dimension, dV / dK / dQ are formed for one 64-column half of the head per pass (the B operands of those MMAs are simply
+// the pass-th 64-column swizzle chunk of the dO / Q / K tiles), so the TMEM plan (448 of 512 columns) is unchanged. The
+// price is recomputing S, dP and the exponentials once more, and - the 32 KiB Q / dO / K / V tiles leave no room for
+// double buffering - a serialised S/dP -> rows -> dV/dK/dQ chain per tile.
+template <int DH_>
 struct BwdCfg {
-  static constexpr int DH = 64;
-  static constexpr int TILE = 128 * 128;                    // [128 x 64] bf16
+  static constexpr int DH = DH_;
+  static constexpr int CH = DH / 64;                        // 64-column swizzle chunks per Q / K / V / dO tile
+  static constexpr int NP = CH;                             // passes per item (one 64-column half of the head each)
+  static constexpr int TILE = 128 * 128 * CH;               // [128 x DH] bf16
+  static constexpr int NKV = (DH == 64) ? 2 : 1;            // K/V buffers (by item parity)
+  static constexpr int NST = (DH == 64) ? 2 : 1;            // Q/dO stages (by tile parity)
   static constexpr int PS_TILE = 2 * 128 * 128;             // [128 x 128] bf16 as two 64-col chunks
   static constexpr int DQ_STAGE = 128 * 64 * 4;             // fp32 [128 x 64] staging (two 32-col chunks)
-  static constexpr int SMEM = 2 * 2 * TILE /*K,V x2 items*/ + 2 * 2 * TILE /*Q,dO x2 stages*/ + 2 * PS_TILE /*P,dS*/ + DQ_STAGE + 256 + 1024;
+  static constexpr int SMEM = 2 * NKV * TILE /*K,V*/ + 2 * NST * TILE /*Q,dO*/ + 2 * PS_TILE /*P,dS*/ + DQ_STAGE + 256 + 1024;
   static constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM <= 232448, "smem budget");
@@ -505,19 +515,20 @@ struct BwdCfg {
 // 320 threads: warps 0-7 = row threads (two per SMSP: warp w and w+4 own the same 32 query rows / TMEM lanes and
 // split the 128 key columns 64/64 - no cross-thread exchange is needed because lse and delta are per-row inputs),
 // warp 8 = TMA producer, warp 9 = MMA issuer (whole warp, elected lane) + TMEM allocator.
+template <int DH_>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale,
                 int causal, const FwdSched sched, float* __restrict__ dq_acc, int dq_red) {
-  using C = BwdCfg;
-  constexpr int DH = C::DH;
+  using C = BwdCfg<DH_>;
+  constexpr int DH = C::DH, NP = C::NP, NKV = C::NKV, NST = C::NST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                    // [2] by item parity
-  uint8_t* sV = sK + 2 * C::TILE;        // [2]
-  uint8_t* sQ = sV + 2 * C::TILE;        // [2] by tile parity
-  uint8_t* sDO = sQ + 2 * C::TILE;       // [2]
-  uint8_t* sP = sDO + 2 * C::TILE;       // bf16 [128 q][128 kv] as 2 chunks of [128][64]
+  uint8_t* sK = smem;                    // [NKV] by item parity
+  uint8_t* sV = sK + NKV * C::TILE;      // [NKV]
+  uint8_t* sQ = sV + NKV * C::TILE;      // [NST] by tile parity
+  uint8_t* sDO = sQ + NST * C::TILE;     // [NST]
+  uint8_t* sP = sDO + NST * C::TILE;     // bf16 [128 q][128 kv] as 2 chunks of [128][64]
   uint8_t* sDS = sP + C::PS_TILE;
   uint8_t* sDQ = sDS + C::PS_TILE;       // fp32 staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + C::DQ_STAGE);
@@ -539,11 +550,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int n_t = S / 128;
   const int d_model = H * DH;
-  const int n_items = sched.n_items;
-  // item k -> (b, h, key tile jt, first query tile i0, number of query tiles)
+  const int n_items = sched.n_items * NP;
+  // item k -> (b, h, key tile jt, first query tile i0, number of query tiles); pass = k % NP
   auto item_of = [&](int k, int& b, int& h, int& jt, int& i0, int& n_it) {
     int bh, w;
-    sched.decode(k, bh, w);
+    sched.decode(k / NP, bh, w);
     b = bh / H;
     h = bh - b * H;
     jt = n_t - 1 - w;                    // decode() orders by weight w: heavy first == small key tile index
@@ -584,25 +595,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int k = blockIdx.x; k < n_items; k += gridDim.x, ++it) {
         int b, h, jt, i0, n_it;
         item_of(k, b, h, jt, i0, n_it);
-        const int kb = it & 1;
-        mbar_wait(&kv_empty[kb], ((it >> 1) & 1) ^ 1);
+        const int kb = it % NKV;
+        mbar_wait(&kv_empty[kb], ((it / NKV) & 1) ^ 1);
         mbar_expect_tx(&kv_full[kb], 2 * C::TILE);
-        tma_load_2d(sK + kb * C::TILE, &tmQKV, &kv_full[kb], d_model + h * DH, b * S + jt * 128);
-        tma_load_2d(sV + kb * C::TILE, &tmQKV, &kv_full[kb], 2 * d_model + h * DH, b * S + jt * 128);
+#pragma unroll
+        for (int c = 0; c < C::CH; ++c) {
+          tma_load_2d(sK + kb * C::TILE + c * 16384, &tmQKV, &kv_full[kb], d_model + h * DH + c * 64, b * S + jt * 128);
+          tma_load_2d(sV + kb * C::TILE + c * 16384, &tmQKV, &kv_full[kb], 2 * d_model + h * DH + c * 64, b * S + jt * 128);
+        }
         for (int t = 0; t < n_it; ++t, ++n) {
-          const int st = n & 1;
-          mbar_wait(&qd_empty[st], ((n >> 1) & 1) ^ 1);
+          const int st = n % NST;
+          mbar_wait(&qd_empty[st], ((n / NST) & 1) ^ 1);
           mbar_expect_tx(&qd_full[st], 2 * C::TILE);
-          tma_load_2d(sQ + st * C::TILE, &tmQKV, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
-          tma_load_2d(sDO + st * C::TILE, &tmDO, &qd_full[st], h * DH, b * S + (i0 + t) * 128);
+#pragma unroll
+          for (int c = 0; c < C::CH; ++c) {
+            tma_load_2d(sQ + st * C::TILE + c * 16384, &tmQKV, &qd_full[st], h * DH + c * 64, b * S + (i0 + t) * 128);
+            tma_load_2d(sDO + st * C::TILE + c * 16384, &tmDO, &qd_full[st], h * DH + c * 64, b * S + (i0 + t) * 128);
+          }
         }
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer (whole warp; elected lane issues)
     constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP : both K-major, N = 128
-    constexpr uint32_t idesc_mm = make_idesc_bf16(128, DH, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q) MN-major
-    constexpr uint32_t idesc_km = make_idesc_bf16(128, DH, 0, 1);    // dQ    : A (dS) K-major, B (K_j) MN-major
+    constexpr uint32_t idesc_mm = make_idesc_bf16(128, 64, 1, 1);    // dV, dK: A (P/dS) MN-major, B (dO/Q half) MN-major, N = 64
+    constexpr uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);    // dQ    : A (dS) K-major, B (K_j half) MN-major
     const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
     // descriptor bases; per-k-step offsets are added to the (addr >> 4) field
     const uint32_t pd_m = smem_desc_lo(p_base, 16384), dsd_m = smem_desc_lo(ds_base, 16384);
@@ -611,10 +628,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint32_t qd_k2[2], dod_k2[2], qd_m2[2], dod_m2[2], kd_k2[2], vd_k2[2], kd_m2[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      qd_k2[i] = smem_desc_lo(smem_u32(sQ + i * C::TILE), 16), qd_m2[i] = smem_desc_lo(smem_u32(sQ + i * C::TILE), 16384);
-      dod_k2[i] = smem_desc_lo(smem_u32(sDO + i * C::TILE), 16), dod_m2[i] = smem_desc_lo(smem_u32(sDO + i * C::TILE), 16384);
-      kd_k2[i] = smem_desc_lo(smem_u32(sK + i * C::TILE), 16), kd_m2[i] = smem_desc_lo(smem_u32(sK + i * C::TILE), 16384);
-      vd_k2[i] = smem_desc_lo(smem_u32(sV + i * C::TILE), 16);
+      const int qi = i % NST, ki = i % NKV;   // single-buffered variants alias
+      qd_k2[i] = smem_desc_lo(smem_u32(sQ + qi * C::TILE), 16), qd_m2[i] = smem_desc_lo(smem_u32(sQ + qi * C::TILE), 16384);
+      dod_k2[i] = smem_desc_lo(smem_u32(sDO + qi * C::TILE), 16), dod_m2[i] = smem_desc_lo(smem_u32(sDO + qi * C::TILE), 16384);
+      kd_k2[i] = smem_desc_lo(smem_u32(sK + ki * C::TILE), 16), kd_m2[i] = smem_desc_lo(smem_u32(sK + ki * C::TILE), 16384);
+      vd_k2[i] = smem_desc_lo(smem_u32(sV + ki * C::TILE), 16);
     }
     struct Cur {
       int k, it, t, n_it;
@@ -633,19 +651,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     };
     int ns = 0, n = 0;
-    auto issue_sdp = [&](const Cur& c) {  // S = Q K^T ; dP = dO V^T  (contraction over d_head = 64: 4 k-steps in one swizzle atom)
-      const int st = ns & 1, kb = c.it & 1;
-      if (c.t == 0) mbar_wait(&kv_full[kb], (c.it >> 1) & 1);
-      mbar_wait(&qd_full[st], (ns >> 1) & 1);
+    auto issue_sdp = [&](const Cur& c) {  // S = Q K^T ; dP = dO V^T  (contraction over d_head: 4 k-steps per 64-column swizzle chunk)
+      const int st = ns % NST, kb = c.it % NKV;
+      if (c.t == 0) mbar_wait(&kv_full[kb], (c.it / NKV) & 1);
+      mbar_wait(&qd_full[st], (ns / NST) & 1);
       tc_fence_after();
       const uint32_t qd_k = st ? qd_k2[1] : qd_k2[0], dod_k = st ? dod_k2[1] : dod_k2[0];
       const uint32_t kd_k = kb ? kd_k2[1] : kd_k2[0], vd_k = kb ? vd_k2[1] : vd_k2[0];
 #pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk)
-        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_S, qd_k + uint32_t(kk * 2), kd_k + uint32_t(kk * 2), idesc_kk, kk != 0);
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint32_t off = uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_S, qd_k + off, kd_k + off, idesc_kk, kk != 0);
+      }
 #pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk)
-        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_DP, dod_k + uint32_t(kk * 2), vd_k + uint32_t(kk * 2), idesc_kk, kk != 0);
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const uint32_t off = uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+        if (elect_one()) tc_mma_f16_ss_lo(tmem + C::COL_DP, dod_k + off, vd_k + off, idesc_kk, kk != 0);
+      }
       if (elect_one()) tc_commit(sdp_full);
       __syncwarp();
       ++ns;
@@ -658,13 +680,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       advance(nx);
     }
     while (cu.k < n_items) {
-      const int st = n & 1, kb = cu.it & 1;
-      const uint32_t qd_m = st ? qd_m2[1] : qd_m2[0], dod_m = st ? dod_m2[1] : dod_m2[0];
-      const uint32_t kd_m = kb ? kd_m2[1] : kd_m2[0];
+      const int st = n % NST, kb = cu.it % NKV;
+      const uint32_t half = uint32_t(((cu.k % NP) * 16384) >> 4);   // 64-column chunk of dO / Q / K for this pass
+      const uint32_t qd_m = (st ? qd_m2[1] : qd_m2[0]) + half, dod_m = (st ? dod_m2[1] : dod_m2[0]) + half;
+      const uint32_t kd_m = (kb ? kd_m2[1] : kd_m2[0]) + half;
       // next tile's S / dP (possibly the next item's) are issued as soon as the row threads hold S_n / dP_n in
-      // registers: they run on the tensor pipe while the rows are still computing P_n / dS_n
+      // registers: they run on the tensor pipe while the rows are still computing P_n / dS_n. With a single Q/dO stage
+      // (d_head 128) the next tile cannot be loaded before this tile's dV / dK retire: S / dP follow them instead.
       mbar_wait(sdp_free, n & 1);
-      if (nx.k < n_items) {
+      if (NST > 1 && nx.k < n_items) {
         issue_sdp(nx);
         advance(nx);
       }
@@ -701,6 +725,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       }
       __syncwarp();
+      if (NST == 1 && nx.k < n_items) {
+        issue_sdp(nx);
+        advance(nx);
+      }
       ++n;
       advance(cu);
     }
@@ -716,7 +744,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     struct Prev {
       int valid, b, h, qt;       // coordinates of tile n-1 (its dQ partial is still in TMEM)
       int item_end, jt, it;      // tile n-1 was the last of item `it` (key tile jt): dK/dV epilogue pending
-    } pv{0, 0, 0, 0, 0, 0, 0};
+      int pass;                  // which 64-column half of the head this item covers
+    } pv{0, 0, 0, 0, 0, 0, 0, 0};
     auto drain_dq = [&](const Prev& p) {  // dQ partial of tile n-1: TMEM -> fp32 smem staging -> TMA reduce-add into dq_acc
       mbar_wait(dq_full, (n - 1) & 1);
       tc_fence_after();
@@ -728,7 +757,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(dq_free);
-        float* dst = dq_acc + (long long)(p.b * S + p.qt * 128 + row) * d_model + p.h * DH + half * 32;
+        float* dst = dq_acc + (long long)(p.b * S + p.qt * 128 + row) * d_model + p.h * DH + p.pass * 64 + half * 32;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g), "f"(__uint_as_float(r[4 * g])),
@@ -753,15 +782,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (issuer) {
-        tma_reduce_add_2d(&tmDQ, sDQ, p.h * DH, p.b * S + p.qt * 128);
-        tma_reduce_add_2d(&tmDQ, sDQ + 16384, p.h * DH + 32, p.b * S + p.qt * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ, p.h * DH + p.pass * 64, p.b * S + p.qt * 128);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, p.h * DH + p.pass * 64 + 32, p.b * S + p.qt * 128);
         tma_commit();
       }
     };
     auto epilogue = [&](const Prev& p) {  // dK (x scale), dV of item p.it -> bf16 -> dqkv
       mbar_wait(final_done, p.it & 1);
       tc_fence_after();
-      __nv_bfloat16* krow = dqkv + (long long)(p.b * S + p.jt * 128 + row) * (3 * d_model) + d_model + p.h * DH;
+      __nv_bfloat16* krow = dqkv + (long long)(p.b * S + p.jt * 128 + row) * (3 * d_model) + d_model + p.h * DH + p.pass * 64;
       __nv_bfloat16* vrow = krow + d_model;
       const int c = half;
       uint32_t rk[32], rv[32];
@@ -867,7 +896,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           drain_dq(pv);
           if (pv.item_end) epilogue(pv);
         }
-        pv = Prev{1, b, h, qt, t == n_it - 1, jt, it};
+        pv = Prev{1, b, h, qt, t == n_it - 1, jt, it, k % NP};
         ++n;
       };
       // causal: only the first query tile (qt == jt) touches the diagonal; every other tile runs the mask-free body
@@ -937,7 +966,7 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
 int attention_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B, int S, int H,
                          int dh, float scale, bool causal, int num_sms, cudaStream_t st) {
   if (S % 128) throw std::runtime_error("photon_b200 attention: sequence length must be a multiple of 128");
-  if (dh != 64) throw std::runtime_error("photon_b200 attention backward: d_head must be 64 (use kernels.attention=torch otherwise)");
+  if (dh != 64 && dh != 128) throw std::runtime_error("photon_b200 attention backward: d_head must be 64 or 128");
   const int d = H * dh;
   const long long rows = (long long)B * S;
   const size_t need = size_t(rows) * d * sizeof(float);
@@ -955,8 +984,6 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
   CUtensorMap tmQKV = make_tmap_2d(qkv, 2, false, uint64_t(3) * d, uint64_t(rows), uint64_t(3) * d * 2, 64, 128);
   CUtensorMap tmDO = make_tmap_2d(dout, 2, false, uint64_t(d), uint64_t(rows), uint64_t(d) * 2, 64, 128);
   CUtensorMap tmDQ = make_tmap_2d(g_dq_acc, 4, true, uint64_t(d), uint64_t(rows), uint64_t(d) * 4, 32, 128);
-  static bool once = (set_smem(attn_bwd_kernel, BwdCfg::SMEM), true);
-  (void)once;
   FwdSched sched;
   sched.n_qt = S / 128;
   sched.n_items = sched.n_qt * H * B;
@@ -969,8 +996,18 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
     sched.cyc_rounds = sched.n_qt / a;
   }
   static const int dq_red = [] { const char* e = std::getenv("PB_ATTN_DQ_RED"); return e ? std::atoi(e) : 0; }();
-  attn_bwd_kernel<<<grid, 320, BwdCfg::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, causal ? 1 : 0, sched,
-                                                   g_dq_acc, dq_red);
+  if (dh == 64) {
+    static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
+    (void)once;
+    attn_bwd_kernel<64><<<grid, 320, BwdCfg<64>::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale,
+                                                             causal ? 1 : 0, sched, g_dq_acc, dq_red);
+  } else {
+    static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
+    (void)once;
+    const int grid2 = 2 * sched.n_items < sms ? 2 * sched.n_items : sms;
+    attn_bwd_kernel<128><<<grid2, 320, BwdCfg<128>::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale,
+                                                                causal ? 1 : 0, sched, g_dq_acc, dq_red);
+  }
   attn_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(g_dq_acc, (__nv_bfloat16*)dqkv, rows, d, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention bwd launch: ") + cudaGetErrorString(e));

@@ -77,10 +77,10 @@ class B200Engine:
         # replayed (the schedule is static: preallocated workspace, TMA descriptors baked into the launches)
         self.use_graph = bool(kernels.get("cuda_graph", True))
         self._graphs: dict[tuple, Any] = {}
-        if self.attn_mode == "b200" and cfg.d_head != 64:
-            # our tcgen05 backward is d_head-64 only (TMEM budget); forward exists for 128. Use the library attention for
-            # BOTH directions rather than mixing (explicit + logged; GEMM/LN/CE/optimizer stay on our kernels)
-            print(f"[engine] d_head={cfg.d_head}: attention falls back to SDPA (tcgen05 backward covers d_head=64)", flush=True)
+        if self.attn_mode == "b200" and cfg.d_head not in (64, 128):
+            # the tcgen05 attention kernels cover d_head 64 and 128 (every shipped MPT config); anything else uses the
+            # library attention for BOTH directions (explicit + logged; GEMM/LN/CE/optimizer stay on our kernels)
+            print(f"[engine] d_head={cfg.d_head}: attention falls back to SDPA (tcgen05 kernels cover d_head 64 / 128)", flush=True)
             self.attn_mode = "torch"
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)

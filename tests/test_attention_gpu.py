@@ -36,11 +36,12 @@ def test_attention_fwd(B, S, H, dh):
     assert (lse - rl).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (1, 256, 2), (2, 512, 4), (1, 2048, 2)])
-def test_attention_bwd(B, S, H):
+@pytest.mark.parametrize("B,S,H,dh", [(1, 128, 1, 64), (1, 256, 2, 64), (2, 512, 4, 64), (1, 2048, 2, 64),
+                                      (1, 128, 1, 128), (2, 512, 3, 128), (1, 1024, 2, 128)])
+def test_attention_bwd(B, S, H, dh):
     from photon_b200 import ops
 
-    dh, d = 64, H * 64
+    d = H * dh
     qkv = (torch.randn(B, S, 3 * d, device="cuda:0")).to(torch.bfloat16)
     dout = (torch.randn(B, S, d, device="cuda:0")).to(torch.bfloat16)
     out = torch.empty(B, S, d, device="cuda:0", dtype=torch.bfloat16)
@@ -75,13 +76,14 @@ def _sdpa_ref(qkv, H, causal, dout=None):
     return o.detach(), x.grad
 
 
-@pytest.mark.parametrize("B,S,H,causal", [(4, 1024, 12, True), (8, 512, 12, True), (3, 768, 5, True), (4, 512, 12, False), (2, 1024, 3, False)])
-def test_attention_persistent_many_items(B, S, H, causal):
+@pytest.mark.parametrize("B,S,H,causal,dh", [(4, 1024, 12, True, 64), (8, 512, 12, True, 64), (3, 768, 5, True, 64), (4, 512, 12, False, 64),
+                                             (2, 1024, 3, False, 64), (4, 1024, 16, True, 128), (2, 512, 8, False, 128)])
+def test_attention_persistent_many_items(B, S, H, causal, dh):
     """More work items than SMs: every CTA walks several (batch*head, tile) items, so the cross-item pipelines
     (barrier parities, double-buffered O / K-V, deferred epilogues) and the non-causal path are exercised."""
     from photon_b200 import ops
 
-    dh, d = 64, H * 64
+    d = H * dh
     qkv = torch.randn(B, S, 3 * d, device="cuda:0").to(torch.bfloat16)
     dout = torch.randn(B, S, d, device="cuda:0").to(torch.bfloat16)
     out = torch.empty(B, S, d, device="cuda:0", dtype=torch.bfloat16)

@@ -125,3 +125,29 @@ def test_engine_cuda_graph_replay_matches_eager():
     rel = ((a.flat.grads - b.flat.grads).norm() / a.flat.grads.norm()).item()
     assert rel < 1e-3, rel
     assert b.launches_per_microbatch == a.launches_per_microbatch > 0
+
+
+def test_engine_d_head_128_runs_on_own_attention():
+    """MPT-1B/3B/7B geometry (d_head = 128): forward and backward attention stay on the tcgen05 kernels."""
+    from photon_b200.models.engine import B200Engine
+    from photon_b200.models.mpt import MPTConfig
+    from photon_b200.train.backend import TorchBackend
+
+    cfg = MPTConfig(d_model=256, n_heads=2, n_layers=2, max_seq_len=256, vocab_size=2048, attn_impl="flash")
+    assert cfg.d_head == 128
+    dev = torch.device("cuda", 0)
+    ref = TorchBackend(cfg, dev, "fp32", seed=3)
+    eng = B200Engine(cfg, dev, "amp_bf16", {"cuda_graph": False}, seed=5)
+    assert eng.attn_mode == "b200"
+    eng.flat.params.copy_(ref.flat.params)
+    eng.params_updated()
+    ids = torch.randint(0, cfg.vocab_size, (4, cfg.max_seq_len), device=dev)
+    denom = float(ids.shape[0] * (ids.shape[1] - 1))
+    ref.flat.zero_grad(), eng.flat.zero_grad()
+    l_ref, _ = ref.fwd_bwd(ids, denom)
+    l_eng, _ = eng.fwd_bwd(ids, denom)
+    torch.cuda.synchronize()
+    assert abs(float(l_ref) - float(l_eng)) / float(l_ref) < 5e-3
+    cos = torch.nn.functional.cosine_similarity(ref.flat.grads, eng.flat.grads, dim=0).item()
+    rel = ((ref.flat.grads - eng.flat.grads).norm() / ref.flat.grads.norm()).item()
+    assert cos > 0.995 and rel < 0.08, (cos, rel)
