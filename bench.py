@@ -233,7 +233,9 @@ def main() -> None:
         mcfg = rt.trainer.model_cfg
         peak = measured_peaks()
         out = {
-            "metric": "tokens/sec (whole box, device-timed, max over ranks) MPT-125M 8-client fed round",
+            "metric": "tokens/sec (whole box, device-timed, max over ranks) "
+                      + {"mpt-125m": "MPT-125M", "mpt-1b": "MPT-1B", "mpt-3b": "MPT-3B", "mpt-7b": "MPT-7B"}.get(args.model, args.model)
+                      + " 8-client fed round",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic C4-shaped tokens, random-init weights", "impl": args.impl,
