@@ -503,7 +503,7 @@ struct BwdCfg {
   static constexpr int PS_TILE = 2 * 128 * 128;             // [128 x 128] bf16 as two 64-col chunks
   static constexpr int DQ_STAGE = 128 * 64 * 4;             // fp32 [128 x 64] staging (two 32-col chunks)
   static constexpr int SMEM = 2 * NKV * TILE /*K,V*/ + 2 * NST * TILE /*Q,dO*/ + 2 * PS_TILE /*P,dS*/ + DQ_STAGE + 256 + 1024;
-  static constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+  static constexpr int COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;   // dQ: two 64-column buffers (tile parity)
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM <= 232448, "smem budget");
 };
@@ -539,12 +539,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* sdp_full = bars + 8;         // S and dP ready
   uint64_t* pds_ready = bars + 9;        // P, dS in smem (256 arrivals)
   uint64_t* dq_full = bars + 10;         // dQ partial tile in TMEM
-  uint64_t* dq_free = bars + 11;         // dQ TMEM columns drained (256 arrivals)
+  uint64_t* dq_free = bars + 11;         // (unused slot)
   uint64_t* mma_done = bars + 12;        // dV/dK/dQ MMAs of the tile retired -> P/dS smem reusable
   uint64_t* final_done = bars + 13;      // all MMAs of an item retired -> dK/dV complete
   uint64_t* acc_free = bars + 14;        // dK/dV accumulators drained by the epilogue (256 arrivals)
   uint64_t* sdp_free = bars + 15;        // S / dP of the tile are in registers (256 arrivals) -> next S / dP may be issued
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* dq_free2 = bars + 16;        // [2] dQ TMEM buffer (tile parity) drained (256 arrivals): the dQ MMAs of tile n
+                                         // never wait for the drain of tile n-1, only for that of tile n-2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -576,6 +578,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(pds_ready, 256);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 256);
+    mbar_init(&dq_free2[0], 256);
+    mbar_init(&dq_free2[1], 256);
     mbar_init(mma_done, 1);
     mbar_init(final_done, 1);
     mbar_init(acc_free, 256);
@@ -693,7 +697,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         advance(nx);
       }
       mbar_wait(pds_ready, n & 1);   // P_n / dS_n staged in smem
-      if (n > 0) mbar_wait(dq_free, (n - 1) & 1);
+      if (n >= 2) mbar_wait(&dq_free2[n & 1], ((n >> 1) & 1) ^ 1);
       if (cu.t == 0 && cu.it > 0) mbar_wait(acc_free, (cu.it - 1) & 1);  // previous item's dK / dV drained
       tc_fence_after();
       const uint32_t acc = cu.t != 0;
@@ -712,7 +716,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int kk = 0; kk < 8; ++kk) {
         // dQ[q, dh] = dS K_j : A = dS K-major (kv contiguous: chunk = kk/4, 32 B per k-step), B = K_j MN-major over kv rows
         if (elect_one())
-          tc_mma_f16_ss_lo(tmem + C::COL_DQ, dsd_k + uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint32_t(kk * 128), idesc_km,
+          tc_mma_f16_ss_lo(tmem + C::COL_DQ + (n & 1) * 64, dsd_k + uint32_t(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4), kd_m + uint32_t(kk * 128), idesc_km,
                            kk != 0);
       }
       if (elect_one()) {
@@ -753,10 +757,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // alternative (PB_ATTN_DQ_RED=1): vector reductions straight from registers - no staging, fence or block barrier,
         // but twice as many (16-byte) L2 atomics as the TMA reduce: measured 2.49 vs 1.85 us per query tile -> off by default
         uint32_t r[32];
-        tmem_ld_32x32(tl + C::COL_DQ + half * 32, r);
+        tmem_ld_32x32(tl + C::COL_DQ + ((n - 1) & 1) * 64 + half * 32, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(dq_free);
+        mbar_arrive(&dq_free2[(n - 1) & 1]);
         float* dst = dq_acc + (long long)(p.b * S + p.qt * 128 + row) * d_model + p.h * DH + p.pass * 64 + half * 32;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
@@ -770,7 +774,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       {
         const int c = half;  // 32 of the 64 dQ columns per thread
         uint32_t r[32];
-        tmem_ld_32x32(tl + C::COL_DQ + c * 32, r);
+        tmem_ld_32x32(tl + C::COL_DQ + ((n - 1) & 1) * 64 + c * 32, r);
         tmem_ld_wait();
         uint8_t* qrow = sDQ + c * 16384 + row * 128;
 #pragma unroll
@@ -778,7 +782,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           *reinterpret_cast<uint4*>(qrow + ((uint32_t(g) ^ swz) << 4)) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
       }
       tc_fence_before();
-      mbar_arrive(dq_free);
+      mbar_arrive(&dq_free2[(n - 1) & 1]);
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (issuer) {
