@@ -107,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
   uint64_t* pv_done = bars + 24;                  // P V_n retired (per tile; only waited on a rescale)
   uint64_t* o_final = bars + 25;                  // [2]  all P V of an item (by item parity) retired
   uint64_t* o_free = bars + 27;                   // [2]  O buffer drained by the epilogue (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);   // own line, away from the mbarrier words
   float* xch = reinterpret_cast<float*>(bars + 64);    // [4 slots][NS parts][128 rows]
   constexpr int W_TMA = 4 * NS, W_MMA = 4 * NS + 1, COLS = 128 / NS;
 
@@ -546,7 +546,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* sdp_free = bars + 15;        // S / dP of the tile are in registers (256 arrivals) -> next S / dP may be issued
   uint64_t* dq_free2 = bars + 16;        // [2] dQ TMEM buffer (tile parity) drained (256 arrivals): the dQ MMAs of tile n
                                          // never wait for the drain of tile n-1, only for that of tile n-2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);   // own line, away from the mbarrier words
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;

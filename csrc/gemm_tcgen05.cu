@@ -79,7 +79,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);   // own 64-byte line, away from the mbarrier words (<= 18 of them)
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
