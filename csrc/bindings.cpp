@@ -386,4 +386,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("EPI_GELU_DUAL") = int(pb::EPI_GELU_DUAL);
   m.attr("EPI_DGELU") = int(pb::EPI_DGELU);
   m.attr("EPI_F32") = int(pb::EPI_F32);
+  m.attr("EPI_GELU_GRAD") = int(pb::EPI_GELU_GRAD);
+  m.attr("EPI_MUL") = int(pb::EPI_MUL);
 }

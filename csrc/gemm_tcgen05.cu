@@ -36,7 +36,7 @@ template <int EPI, int CL>
 struct Cfg {
   static constexpr int B_STAGE = (BN / CL) * BK * 2;   // 32 KiB (CL=1) / 16 KiB (CL=2)
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-  static constexpr int STORES = (EPI == EPI_GELU_DUAL) ? 2 : 1;   // staging buffers consumed per epilogue chunk
+  static constexpr int STORES = (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD) ? 2 : 1;   // staging buffers consumed per epilogue chunk
   // two epilogue groups (even / odd column chunks of a tile), two staging buffers each: the exact-erf GELU epilogues
   // measured ALU-bound with one epilogue warp per SM sub-partition (dGELU dgrad 634 TFLOP/s against 1400+ for the
   // plain epilogue on the same shape)
@@ -88,7 +88,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmD);
-    if (EPI == EPI_GELU_DUAL) prefetch_tmap(&tmD2);
+    if (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD) prefetch_tmap(&tmD2);
   }
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
   if (warp == 1 && lane == 0) {
@@ -266,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // aux tile (residual / pre-activation) for this chunk: issue the global loads FIRST so their latency
         // overlaps the TMEM read below
         uint4 ax[8];
-        if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
+        if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU || EPI == EPI_MUL) {
           const __nv_bfloat16* arow = p.aux + row * p.ld_aux + col0;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -307,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             *reinterpret_cast<float4*>(buf0 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;
           }
         } else {
-          if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU) {
+          if (EPI == EPI_RESIDUAL || EPI == EPI_DGELU || EPI == EPI_MUL) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               {
@@ -319,12 +319,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   if (EPI == EPI_RESIDUAL) {
                     v[8 * j + 2 * t] += f.x;
                     v[8 * j + 2 * t + 1] += f.y;
+                  } else if (EPI == EPI_MUL) {
+                    v[8 * j + 2 * t] *= f.x;
+                    v[8 * j + 2 * t + 1] *= f.y;
                   } else {
                     v[8 * j + 2 * t] *= gelu_grad(f.x);
                     v[8 * j + 2 * t + 1] *= gelu_grad(f.y);
                   }
                 }
               }
+            }
+          }
+          if (EPI == EPI_GELU_GRAD) {
+            // gelu and its derivative share the CDF / PDF evaluation; the derivative replaces the pre-activation as the
+            // tensor saved for backward, so the dgrad epilogue is a plain multiply
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float d[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                float c, pd;
+                gelu_cdf_pdf(v[8 * j + t], c, pd);
+                d[t] = fmaf(v[8 * j + t], pd, c);
+                v[8 * j + t] *= c;
+              }
+              uint4 o;
+              o.x = pack_bf16(d[0], d[1]), o.y = pack_bf16(d[2], d[3]), o.z = pack_bf16(d[4], d[5]), o.w = pack_bf16(d[6], d[7]);
+              *reinterpret_cast<uint4*>(buf1 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;   // gelu'(z)
             }
           }
           if (EPI == EPI_GELU_DUAL) {
@@ -358,7 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             tma_store_2d(&tmD, buf0, col0, m_blk * BM);
           }
-          if (EPI == EPI_GELU_DUAL) tma_store_2d(&tmD2, buf1, col0, m_blk * BM);
+          if (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD) tma_store_2d(&tmD2, buf1, col0, m_blk * BM);
           tma_commit();
         }
         ebuf = (ebuf + STORES) % EPI_BUFS_G;
@@ -469,11 +490,11 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   CUtensorMap td = f32 ? make_tmap_2d(g.D, 4, true, g.N, g.M, g.ldd * 4, 32, BM)
                        : make_tmap_2d(g.D, 2, false, g.N, g.M, g.ldd * 2, 64, BM);
   CUtensorMap td2 = td;
-  if (g.epi == EPI_GELU_DUAL) {
-    if (!g.D2) throw std::runtime_error("photon_b200 gemm: EPI_GELU_DUAL needs the pre-activation output");
+  if (g.epi == EPI_GELU_DUAL || g.epi == EPI_GELU_GRAD) {
+    if (!g.D2) throw std::runtime_error("photon_b200 gemm: the two-output GELU epilogues need the second output");
     td2 = make_tmap_2d(g.D2, 2, false, g.N, g.M, g.ldd2 * 2, 64, BM);
   }
-  if ((g.epi == EPI_RESIDUAL || g.epi == EPI_DGELU) && (!g.aux || (g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)))
+  if ((g.epi == EPI_RESIDUAL || g.epi == EPI_DGELU || g.epi == EPI_MUL) && (!g.aux || (g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)))
     throw std::runtime_error("photon_b200 gemm: aux operand missing or not 16-byte aligned");
   if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) throw std::runtime_error("photon_b200 gemm: bias must be 16-byte aligned");
   Params p;
@@ -519,6 +540,8 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   PB_CASE(0, 0, EPI_F32)
   PB_CASE(0, 1, EPI_BF16)
   PB_CASE(0, 1, EPI_DGELU)
+  PB_CASE(0, 1, EPI_MUL)
+  PB_CASE(0, 0, EPI_GELU_GRAD)
   PB_CASE(0, 1, EPI_F32)
   PB_CASE(1, 1, EPI_F32)
   PB_CASE(1, 1, EPI_BF16)

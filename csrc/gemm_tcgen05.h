@@ -12,13 +12,15 @@ enum Epilogue : int {
   EPI_GELU_DUAL = 2,  // D2 = bf16(z = acc*alpha + bias);  D = bf16(gelu(z))
   EPI_DGELU = 3,      // D = bf16((acc*alpha + bias) * gelu'(aux))
   EPI_F32 = 4,        // D (fp32) = acc*alpha   or  D += acc*alpha   (accumulate, TMA reduce-add)
+  EPI_GELU_GRAD = 5,  // z = acc*alpha + bias;  D = bf16(gelu(z));  D2 = bf16(gelu'(z))  — the backward then needs no erf/exp
+  EPI_MUL = 6,        // D = bf16((acc*alpha + bias) * aux)
 };
 
 struct GemmArgs {
   const void* A = nullptr;  // bf16: K-major [M,K] (lda = row stride) or MN-major [K,M]
   const void* B = nullptr;  // bf16: K-major [N,K] or MN-major [K,N]
   void* D = nullptr;        // [M,N] bf16 (fp32 for EPI_F32), ldd = row stride in elements
-  void* D2 = nullptr;       // second output (EPI_GELU_DUAL), bf16 [M,N]
+  void* D2 = nullptr;       // second output (EPI_GELU_DUAL / EPI_GELU_GRAD), bf16 [M,N]
   const float* bias = nullptr;
   const void* aux = nullptr;  // bf16 [M,N]
   int M = 0, N = 0, K = 0;

@@ -193,7 +193,7 @@ class B200Engine:
         self._attention_fwd(lw, b, S)
         ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
         ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)
-        ops.linear_gelu_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])
+        ops.linear_gelu_grad_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])   # lw["z"] holds gelu'(pre-activation)
         ops.linear_fwd(lw["u"], w.wdown, w.bdown, h[i + 1], residual=lw["hmid"])
 
     def _forward(self, ids: torch.Tensor, ws: dict[str, Any]) -> None:
@@ -236,7 +236,7 @@ class B200Engine:
             # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
             ops.col_sum(dh, w.d_bdown)
             ops.linear_wgrad(dh, lw["u"], w.d_wdown)
-            ops.linear_dgrad(dh, w.wdown, ws["dz"], gelu_pre=lw["z"])
+            ops.linear_dgrad(dh, w.wdown, ws["dz"], mul=lw["z"])
             ops.col_sum(ws["dz"], w.d_bup)
             ops.linear_wgrad(ws["dz"], lw["ln2"], w.d_wup)
             ops.linear_dgrad(ws["dz"], w.wup, dln)

@@ -52,7 +52,7 @@ def add_launch_count(n: int) -> None:
 
 
 # --------------------------------------------------------------------------------- GEMM
-EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2, 3, 4, 5, 6
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
@@ -77,8 +77,19 @@ def linear_gelu_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
     return gemm(x, w, act, epi=EPI_GELU_DUAL, bias=bias, out2=pre)
 
 
-def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, gelu_pre: torch.Tensor | None = None) -> torch.Tensor:
-    """dx = dy @ w  (w stored [N,K] → consumed MN-major, no transpose); optional ``* gelu'(pre)``."""
+def linear_gelu_grad_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, dact: torch.Tensor,
+                         act: torch.Tensor) -> torch.Tensor:
+    """z = x @ w^T + bias ; act = gelu(z) ; dact = gelu'(z) — the derivative is what the backward needs, so it is saved
+    INSTEAD of z and the dgrad epilogue becomes a plain multiply (no erf / exp in the backward)."""
+    return gemm(x, w, act, epi=EPI_GELU_GRAD, bias=bias, out2=dact)
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, gelu_pre: torch.Tensor | None = None,
+                 mul: torch.Tensor | None = None) -> torch.Tensor:
+    """dx = dy @ w  (w stored [N,K] → consumed MN-major, no transpose); optional ``* gelu'(pre)`` (pre-activation given)
+    or ``* mul`` (saved derivative given)."""
+    if mul is not None:
+        return gemm(dy, w, dx, b_mn=True, epi=EPI_MUL, aux=mul)
     return gemm(dy, w, dx, b_mn=True, epi=EPI_DGELU if gelu_pre is not None else EPI_BF16, aux=gelu_pre)
 
 

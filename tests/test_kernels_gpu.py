@@ -219,3 +219,30 @@ def test_fused_optimizer_matches_torch_path(name):
     _close(fa.params, fb.params, 1e-5, 1e-6, f"{name} params")
     _close(oa.exp_avg_sq, ob.exp_avg_sq, 1e-5, 1e-8, f"{name} v")
     assert torch.equal(shadow, fa.params.to(torch.bfloat16))
+
+
+def test_gemm_gelu_with_saved_derivative_and_mul_epilogue():
+    """EPI_GELU_GRAD (act + gelu'(z) from one CDF/PDF evaluation) and EPI_MUL (dgrad * saved derivative) reproduce the
+    exact-erf GELU forward / backward."""
+    from photon_b200 import ops
+
+    torch.manual_seed(0)
+    T, K, N = 512, 256, 768
+    x = (torch.randn(T, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda") * 0.1
+    act = torch.empty(T, N, device="cuda", dtype=torch.bfloat16)
+    dact = torch.empty_like(act)
+    ops.linear_gelu_grad_fwd(x, w, b, dact, act)
+    z = (x.float() @ w.float().t() + b).requires_grad_(True)
+    ref = torch.nn.functional.gelu(z)
+    (gref,) = torch.autograd.grad(ref.sum(), z)
+    assert (act.float() - ref).abs().max().item() < 3e-2
+    assert (dact.float() - gref).abs().max().item() < 1.5e-2
+    dy = (torch.randn(T, N, device="cuda") * 0.3).to(torch.bfloat16)
+    w2 = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)          # [N_out, K_in] of the next layer
+    mul = torch.rand(T, K, device="cuda").to(torch.bfloat16)
+    dx = torch.empty(T, K, device="cuda", dtype=torch.bfloat16)
+    ops.linear_dgrad(dy, w2, dx, mul=mul)
+    rdx = (dy.float() @ w2.float()) * mul.float()
+    assert ((dx.float() - rdx).norm() / rdx.norm()).item() < 1e-2
