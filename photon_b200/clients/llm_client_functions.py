@@ -139,6 +139,7 @@ def llm_eval(trainer: Trainer | None, payload: Payload, eval_config: EvaluateCon
     if trainer.device.type == "cuda":
         torch.cuda.synchronize(trainer.device)
     metrics["client/eval_time"] = _now() - t0
+    t0 = _now()
     out = {}
     loss = 0.0
     for k, v in vals.items():
@@ -148,4 +149,8 @@ def llm_eval(trainer: Trainer | None, payload: Payload, eval_config: EvaluateCon
             loss = float(v)
     metrics.update(out)
     n_samples = int(st.eval_timestamp.sample)
+    metrics["client/eval_metrics_collection_time"] = _now() - t0
+    # the trainer is persistent here (the reference closes and rebuilds it around every evaluation,
+    # ref: llm_client_functions.py:341-351): the key is kept for dashboards that expect it
+    metrics["client/eval_trainer_closing_time"] = 0.0
     return loss, max(1, n_samples), metrics, trainer

@@ -72,6 +72,14 @@ def _grad_clip(train_cfg: Any) -> float | None:
     return float(gc["clipping_threshold"])
 
 
+def _with_profiler(t: Any) -> dict[str, Any]:
+    """``llm_config.callbacks`` plus the optional ``llm_config.profiler`` node (ref: trainer_utils.py:1456-1482)."""
+    cbs = dict(t.get("callbacks") or {})
+    if t.get("profiler"):
+        cbs["profiler"] = dict(t["profiler"])
+    return cbs
+
+
 def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", device: torch.device | None = None,
                        rank: int | None = None, world_size: int | None = None, process_group: Any = None,
                        grad_comm: Any = None, split_eval: bool = False, use_unigram_metrics: bool = False,
@@ -119,7 +127,7 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  train_loader=train_loader, eval_loaders=eval_loaders, global_train_batch_size=gbs,
                  device_train_microbatch_size=t.get("device_train_microbatch_size", "auto"),
                  device_eval_batch_size=eval_bs, precision=precision, max_duration=t.get("max_duration"),
-                 grad_clip_norm=_grad_clip(t), callbacks=build_callbacks(t.get("callbacks")), loggers=loggers,
+                 grad_clip_norm=_grad_clip(t), callbacks=build_callbacks(_with_profiler(t)), loggers=loggers,
                  save_folder=t.get("save_folder"), save_interval=t.get("save_interval"),
                  save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),
                  save_overwrite=bool(t.get("save_overwrite", False)), eval_interval=t.get("eval_interval"),

@@ -337,7 +337,57 @@ class OOMObserver(Callback):
         torch._C._cuda_attach_out_of_memory_observer(observer)
 
 
+class ProfilerCallback(Callback):
+    """``llm_config.profiler``: Composer's ``Profiler(schedule=cyclic_schedule(...), trace_handlers=[JSONTraceHandler])``
+    surface (ref: clients/trainer_utils.py:1456-1482) on top of ``torch.profiler``: per cycle ``skip_first`` (once),
+    ``wait``, ``warmup``, ``active`` batches, ``repeat`` cycles (0 = forever); every finished active window is exported
+    as a Chrome-trace JSON ``{folder}/rank{R}.{batch}.pt.trace.json``. CPU + CUDA activities; our kernels show up by
+    name (they are ordinary launches), and `PhaseTracer` spans can be correlated through NVTX."""
+
+    def __init__(self, schedule: dict[str, Any] | None = None, json_trace_handler: dict[str, Any] | None = None,
+                 torch_prof_record_shapes: bool = False, torch_prof_profile_memory: bool = False,
+                 torch_prof_with_stack: bool = False, torch_prof_with_flops: bool = False, **_ignored: Any) -> None:
+        sch = dict(schedule or {})
+        self.skip_first, self.wait = int(sch.get("skip_first", 0)), int(sch.get("wait", 0))
+        self.warmup, self.active, self.repeat = int(sch.get("warmup", 1)), int(sch.get("active", 4)), int(sch.get("repeat", 1))
+        h = dict(json_trace_handler or {})
+        self.folder = str(h.get("folder", "{run_name}/traces"))
+        self.opts = dict(record_shapes=torch_prof_record_shapes, profile_memory=torch_prof_profile_memory,
+                         with_stack=torch_prof_with_stack, with_flops=torch_prof_with_flops)
+        self.prof: Any = None
+        self.traces: list[Path] = []
+
+    def fit_start(self, tr: "Trainer") -> None:
+        from torch.profiler import ProfilerActivity, profile, schedule
+
+        out = Path(self.folder.format(run_name=tr.state.run_name))
+        if not out.is_absolute() and tr.save_folder:
+            out = Path(tr.save_folder).parent / out
+        out.mkdir(parents=True, exist_ok=True)
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if tr.device.type == "cuda" else [])
+
+        def on_ready(p: Any) -> None:
+            path = out / f"rank{tr.rank}.{tr.state.timestamp.batch}.pt.trace.json"
+            p.export_chrome_trace(str(path))
+            self.traces.append(path)
+
+        self.prof = profile(activities=acts, on_trace_ready=on_ready, **self.opts,
+                            schedule=schedule(skip_first=self.skip_first, wait=self.wait, warmup=self.warmup, active=self.active,
+                                              repeat=self.repeat))
+        self.prof.__enter__()
+
+    def batch_end(self, tr: "Trainer") -> None:
+        if self.prof is not None:
+            self.prof.step()
+
+    def fit_end(self, tr: "Trainer") -> None:
+        if self.prof is not None:
+            self.prof.__exit__(None, None, None)
+            self.prof = None
+
+
 _CALLBACKS.update({"memory_snapshot": MemorySnapshot, "oom_observer": OOMObserver})
+_CALLBACKS["profiler"] = ProfilerCallback
 
 
 def build_callbacks(cfg: dict[str, Any] | None) -> list[Callback]:

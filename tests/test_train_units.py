@@ -207,3 +207,28 @@ def test_sharded_optimizer_state_matches_replicated(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29547", str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_profiler_callback_exports_chrome_traces(tmp_path):
+    """llm_config.profiler → cyclic schedule + JSON trace handler (ref: clients/trainer_utils.py:1456-1482)."""
+    from photon_b200.models.mpt import MPTConfig
+    from photon_b200.train.callbacks import build_callbacks
+    from photon_b200.train.trainer import Trainer
+
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=1, max_seq_len=16, vocab_size=64, attn_impl="torch")
+    ids = torch.randint(0, 64, (2, 16))
+
+    class Loader:
+        def __iter__(self):
+            while True:
+                yield {"input_ids": ids}
+
+    cbs = build_callbacks({"profiler": {"schedule": {"skip_first": 1, "wait": 0, "warmup": 1, "active": 2, "repeat": 1},
+                                        "json_trace_handler": {"folder": str(tmp_path / "traces")}}})
+    tr = Trainer(cfg, optimizer_cfg=dict(name="sgd", lr=1e-2), scheduler_cfg=dict(name="constant_with_warmup", t_warmup="0ba"),
+                 train_loader=Loader(), global_train_batch_size=2, device_train_microbatch_size=2, precision="fp32", device="cpu",
+                 callbacks=cbs, kernels=dict(gemm="torch", attention="torch", norm="torch", loss="torch", optimizer="torch"))
+    tr.fit("6ba")
+    traces = list((tmp_path / "traces").glob("rank0.*.pt.trace.json"))
+    assert len(traces) == 1 and traces[0].stat().st_size > 1000
+    tr.close()
