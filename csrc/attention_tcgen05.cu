@@ -85,10 +85,10 @@ struct FwdSched {
   }
 };
 
-template <int DH, int NS>
+template <int DH, int NS, bool ALIBI>
 __global__ void __launch_bounds__((4 * NS + 2) * 32, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
-                float scale, int causal, const FwdSched sched) {
+                float scale, int causal, const FwdSched sched, const float* __restrict__ alibi_slopes) {
   using C = FwdCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -329,8 +329,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
       const int n_kv = causal ? qt + 1 : S / BKV;
       const uint32_t to = tl + C::COL_O + (it & 1) * DH;
       float m = -INFINITY, l = 0.f;                     // l = partial row sum over this thread's COLS columns
+      // ALiBi (attn_config.alibi): score += slope_h * (key - query) (<= 0 for visible keys), folded into the exponent FMA
+      const float slope2 = ALIBI ? alibi_slopes[h] * LOG2E : 0.f;
       auto tile = [&](int j, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
+        // key index of this thread's first column minus its query index (ALiBi distance of column 0 of the part)
+        const float dist0 = float(j * BKV + part * COLS - (qt * BQ + row));
         const uint32_t ts = tl + C::COL_S + (n & 1) * 128 + part * COLS;   // this thread's S columns; P goes over their head
         mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tc_fence_after();
@@ -355,17 +359,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
           if (DIAG && part * COLS + cc * 32 + t > row) v = -INFINITY;   // causal mask: columns beyond this row
           return v;
         };
+        // scaled (log2-domain) score of element t of chunk cc, ALiBi bias included
+        auto score = [&](const uint32_t (&r)[32], int cc, int t) -> float {
+          const float v = masked(r, cc, t) * sc;
+          return ALIBI ? fmaf(slope2, dist0 + float(cc * 32 + t), v) : v;
+        };
         auto exp_pass = [&](float m_ref) {
           rs0 = 0.f, rs1 = 0.f;
           sweep([&](int cc, const uint32_t (&r)[32]) {
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
             for (int t = 0; t < 32; t += 2) {
-              const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
-              cm0 = fmaxf(cm0, v0);
-              cm1 = fmaxf(cm1, v1);
-              const float p0 = exp2f(fmaf(v0, sc, -m_ref));
-              const float p1 = exp2f(fmaf(v1, sc, -m_ref));
+              float p0, p1;
+              if (ALIBI) {
+                const float y0 = score(r, cc, t), y1 = score(r, cc, t + 1);
+                cm0 = fmaxf(cm0, y0);
+                cm1 = fmaxf(cm1, y1);
+                p0 = exp2f(y0 - m_ref);
+                p1 = exp2f(y1 - m_ref);
+              } else {
+                const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
+                cm0 = fmaxf(cm0, v0);
+                cm1 = fmaxf(cm1, v1);
+                p0 = exp2f(fmaf(v0, sc, -m_ref));
+                p1 = exp2f(fmaf(v1, sc, -m_ref));
+              }
               rs0 += p0;
               rs1 += p1;
               pk[cc * 16 + (t >> 1)] = pack_bf16(p0, p1);
@@ -381,19 +399,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
             for (int t = 0; t < 32; t += 2) {
-              cm0 = fmaxf(cm0, masked(r, cc, t));
-              cm1 = fmaxf(cm1, masked(r, cc, t + 1));
+              cm0 = fmaxf(cm0, ALIBI ? score(r, cc, t) : masked(r, cc, t));
+              cm1 = fmaxf(cm1, ALIBI ? score(r, cc, t + 1) : masked(r, cc, t + 1));
             }
             mx = fmaxf(mx, fmaxf(cm0, cm1));
           });
         }
         // all parts of the row now learn the tile max -> identical decisions
         mx = row_max(mx, n & 1);
-        const bool bump = first || (mx * sc - m) > 8.0f;
+        const float mxs = ALIBI ? mx : mx * sc;   // the ALiBi path tracks scaled, biased scores
+        const bool bump = first || (mxs - m) > 8.0f;
         float alpha = 1.0f;
         const bool redo = __any_sync(0xffffffff, bump);
         if (redo) {
-          const float m_new = bump ? fmaxf(m, mx * sc) : m;
+          const float m_new = bump ? fmaxf(m, mxs) : m;
           alpha = bump ? exp2f(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
           exp_pass(m_new);
           m = m_new;
@@ -515,11 +534,11 @@ struct BwdCfg {
 // 320 threads: warps 0-7 = row threads (two per SMSP: warp w and w+4 own the same 32 query rows / TMEM lanes and
 // split the 128 key columns 64/64 - no cross-thread exchange is needed because lse and delta are per-row inputs),
 // warp 8 = TMA producer, warp 9 = MMA issuer (whole warp, elected lane) + TMEM allocator.
-template <int DH_>
+template <int DH_, bool ALIBI>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale,
-                int causal, const FwdSched sched, float* __restrict__ dq_acc, int dq_red) {
+                int causal, const FwdSched sched, float* __restrict__ dq_acc, int dq_red, const float* __restrict__ alibi_slopes) {
   using C = BwdCfg<DH_>;
   constexpr int DH = C::DH, NP = C::NP, NKV = C::NKV, NST = C::NST;
   extern __shared__ uint8_t smem_raw[];
@@ -828,9 +847,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         nx_lse = lse[g0];
         nx_dl = delta[g0];
       }
+      const float slope2 = ALIBI ? alibi_slopes[h] * LOG2E : 0.f;
       auto row_tile = [&](int t, auto diag_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
         const int qt = i0 + t;
+        // ALiBi distance (key - query) of this thread's first column; slope2 == 0 leaves the exponent untouched
+        const float bias0 = slope2 * float(jt * 128 + half * 64 - (qt * 128 + row)) - nx_lse * LOG2E;
         const float lse2 = nx_lse * LOG2E;   // this tile's row statistics were fetched one tile ahead
         const float dl = nx_dl;
         mbar_wait(sdp_full, n & 1);
@@ -849,8 +871,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const int c = half * 2 + cc;  // 32-column block of the row
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            float p0 = exp2f(fmaf(__uint_as_float(rs2[cc][e]), sc, -lse2));
-            float p1 = exp2f(fmaf(__uint_as_float(rs2[cc][e + 1]), sc, -lse2));
+            float p0, p1;
+            if (ALIBI) {   // score + slope * (key - query) - lse
+              p0 = exp2f(fmaf(__uint_as_float(rs2[cc][e]), sc, fmaf(slope2, float(cc * 32 + e), bias0)));
+              p1 = exp2f(fmaf(__uint_as_float(rs2[cc][e + 1]), sc, fmaf(slope2, float(cc * 32 + e + 1), bias0)));
+            } else {
+              p0 = exp2f(fmaf(__uint_as_float(rs2[cc][e]), sc, -lse2));
+              p1 = exp2f(fmaf(__uint_as_float(rs2[cc][e + 1]), sc, -lse2));
+            }
             if (DIAG) {
               if (c * 32 + e > row) p0 = 0.f;
               if (c * 32 + e + 1 > row) p1 = 0.f;
@@ -932,7 +960,7 @@ size_t g_dq_acc_bytes = 0;
 }  // namespace
 
 void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H, int dh, float scale, bool causal, int num_sms,
-                          cudaStream_t st) {
+                          cudaStream_t st, const float* alibi_slopes) {
   if (S % 128) throw std::runtime_error("photon_b200 attention: sequence length must be a multiple of 128");
   if (dh != 64 && dh != 128) throw std::runtime_error("photon_b200 attention: d_head must be 64 or 128");
   const int d = H * dh;
@@ -948,27 +976,25 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
     while (b2) { const int t = a % b2; a = b2; b2 = t; }
     sched.cyc_rounds = sched.n_qt / a;
   }
-  // NS = column parts per query row = softmax warps per SM sub-partition (PB_ATTN_NS=2|4 overrides for experiments)
-  static const int ns_env = [] { const char* e = std::getenv("PB_ATTN_NS"); return e ? std::atoi(e) : 0; }();
-  const int ns = (ns_env == 2 || ns_env == 4) ? ns_env : 2;   // measured: 407 us (NS=2) vs 432 us (NS=4) at b32 H12 S2048
-#define PB_FWD(DHV, NSV)                                                                                              \
+  // two column parts per query row = two softmax warps per SM sub-partition (four measured slower: 432 vs 407 us)
+#define PB_FWD(DHV, AL)                                                                                               \
   {                                                                                                                   \
-    static bool once = (set_smem(attn_fwd_kernel<DHV, NSV>, FwdCfg<DHV>::SMEM), true);                                 \
+    static bool once = (set_smem(attn_fwd_kernel<DHV, 2, AL>, FwdCfg<DHV>::SMEM), true);                               \
     (void)once;                                                                                                       \
-    attn_fwd_kernel<DHV, NSV><<<grid, (4 * NSV + 2) * 32, FwdCfg<DHV>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, \
-                                                                                 causal ? 1 : 0, sched);             \
+    attn_fwd_kernel<DHV, 2, AL><<<grid, 10 * 32, FwdCfg<DHV>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale,   \
+                                                                        causal ? 1 : 0, sched, alibi_slopes);         \
   }
-  if (dh == 64 && ns == 4) PB_FWD(64, 4)
-  else if (dh == 64) PB_FWD(64, 2)
-  else if (ns == 4) PB_FWD(128, 4)
-  else PB_FWD(128, 2)
+  if (dh == 64 && !alibi_slopes) PB_FWD(64, false)
+  else if (dh == 64) PB_FWD(64, true)
+  else if (!alibi_slopes) PB_FWD(128, false)
+  else PB_FWD(128, true)
 #undef PB_FWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention fwd launch: ") + cudaGetErrorString(e));
 }
 
 int attention_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B, int S, int H,
-                         int dh, float scale, bool causal, int num_sms, cudaStream_t st) {
+                         int dh, float scale, bool causal, int num_sms, cudaStream_t st, const float* alibi_slopes) {
   if (S % 128) throw std::runtime_error("photon_b200 attention: sequence length must be a multiple of 128");
   if (dh != 64 && dh != 128) throw std::runtime_error("photon_b200 attention backward: d_head must be 64 or 128");
   const int d = H * dh;
@@ -1000,22 +1026,69 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* dout, con
     sched.cyc_rounds = sched.n_qt / a;
   }
   static const int dq_red = [] { const char* e = std::getenv("PB_ATTN_DQ_RED"); return e ? std::atoi(e) : 0; }();
-  if (dh == 64) {
-    static bool once = (set_smem(attn_bwd_kernel<64>, BwdCfg<64>::SMEM), true);
-    (void)once;
-    attn_bwd_kernel<64><<<grid, 320, BwdCfg<64>::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale,
-                                                             causal ? 1 : 0, sched, g_dq_acc, dq_red);
-  } else {
-    static bool once = (set_smem(attn_bwd_kernel<128>, BwdCfg<128>::SMEM), true);
-    (void)once;
-    const int grid2 = 2 * sched.n_items < sms ? 2 * sched.n_items : sms;
-    attn_bwd_kernel<128><<<grid2, 320, BwdCfg<128>::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale,
-                                                                causal ? 1 : 0, sched, g_dq_acc, dq_red);
+#define PB_BWD(DHV, AL, GRID)                                                                                        \
+  {                                                                                                                   \
+    static bool once = (set_smem(attn_bwd_kernel<DHV, AL>, BwdCfg<DHV>::SMEM), true);                                  \
+    (void)once;                                                                                                       \
+    attn_bwd_kernel<DHV, AL><<<GRID, 320, BwdCfg<DHV>::SMEM, st>>>(tmQKV, tmDO, tmDQ, lse, delta, (__nv_bfloat16*)dqkv, S, H, scale, \
+                                                                  causal ? 1 : 0, sched, g_dq_acc, dq_red, alibi_slopes); \
   }
+  const int grid2 = 2 * sched.n_items < sms ? 2 * sched.n_items : sms;   // d_head 128: two passes per item
+  if (dh == 64 && !alibi_slopes) PB_BWD(64, false, grid)
+  else if (dh == 64) PB_BWD(64, true, grid)
+  else if (!alibi_slopes) PB_BWD(128, false, grid2)
+  else PB_BWD(128, true, grid2)
+#undef PB_BWD
   attn_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(g_dq_acc, (__nv_bfloat16*)dqkv, rows, d, scale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention bwd launch: ") + cudaGetErrorString(e));
   return 3;
+}
+
+// ---------------------------------------------------------------------------------------------- RoPE
+// In-place rotary embedding (rotate-half / GPT-NeoX convention) on the q and k thirds of a fused qkv buffer
+// [T, 3*H*dh] bf16; cos / sin: fp32 [S, dh/2]. inverse = 1 applies the transposed rotation (gradients of q, k).
+namespace {
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                                   long long T, int S, int H, int dh, int inverse) {
+  const int half = dh / 2, groups = half / 8;                 // 8 pairs (16 bytes of each half) per thread
+  const long long n = T * 2 * H * groups;                     // (token, q|k, head, group)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % groups);
+    long long r = i / groups;
+    const int h = int(r % H);
+    r /= H;
+    const int which = int(r % 2);
+    const long long t = r / 2;
+    const int pos = int(t % S);
+    __nv_bfloat16* base = qkv + t * (3LL * H * dh) + (long long)which * H * dh + h * dh + g * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(base);
+    const uint4 b = *reinterpret_cast<const uint4*>(base + half);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t oa[4], ob[4];
+    const float* c = cosT + (long long)pos * half + g * 8;
+    const float* sn = sinT + (long long)pos * half + g * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x1 = unpack_bf16(aw[k]), x2 = unpack_bf16(bw[k]);
+      const float c0 = c[2 * k], c1 = c[2 * k + 1];
+      const float s0 = inverse ? -sn[2 * k] : sn[2 * k], s1 = inverse ? -sn[2 * k + 1] : sn[2 * k + 1];
+      oa[k] = pack_bf16(x1.x * c0 - x2.x * s0, x1.y * c1 - x2.y * s1);
+      ob[k] = pack_bf16(x2.x * c0 + x1.x * s0, x2.y * c1 + x1.y * s1);
+    }
+    *reinterpret_cast<uint4*>(base) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<uint4*>(base + half) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+  }
+}
+}  // namespace
+
+void rope_launch(void* qkv, const float* cosT, const float* sinT, long long T, int S, int H, int dh, bool inverse, cudaStream_t st) {
+  if (dh % 16) throw std::runtime_error("photon_b200 rope: d_head must be a multiple of 16");
+  const long long n = T * 2 * H * (dh / 16);
+  const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 16));
+  rope_kernel<<<blocks, 256, 0, st>>>((__nv_bfloat16*)qkv, cosT, sinT, T, S, H, dh, inverse ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("rope launch: ") + cudaGetErrorString(e));
 }
 
 }  // namespace pb

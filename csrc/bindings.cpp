@@ -91,19 +91,25 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int e
 }
 
 // ---------------------------------------------------------------------------------- attention
-void attention_fwd(const Tensor& qkv, Tensor& out, Tensor& lse, int n_heads, double scale, bool causal) {
+void attention_fwd(const Tensor& qkv, Tensor& out, Tensor& lse, int n_heads, double scale, bool causal,
+                   const c10::optional<Tensor>& alibi_slopes) {
   check_bf16(qkv, "qkv");
   check_bf16(out, "out");
   check_f32(lse, "lse");
   TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous(), "qkv must be contiguous [B,S,3*d]");
   c10::cuda::CUDAGuard guard(qkv.device());
   const int B = int(qkv.size(0)), S = int(qkv.size(1)), d = int(qkv.size(2) / 3);
+  if (alibi_slopes.has_value()) {
+    check_f32(*alibi_slopes, "alibi_slopes");
+    TORCH_CHECK(alibi_slopes->numel() == n_heads, "alibi_slopes must have n_heads elements");
+  }
   pb::attention_fwd_launch(qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, S, n_heads, d / n_heads, float(scale), causal,
-                           at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv));
+                           at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv),
+                           alibi_slopes.has_value() ? alibi_slopes->data_ptr<float>() : nullptr);
   g_launches += 1;
 }
 void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, const Tensor& lse, Tensor& dqkv, Tensor& delta,
-                   int n_heads, double scale, bool causal) {
+                   int n_heads, double scale, bool causal, const c10::optional<Tensor>& alibi_slopes) {
   check_bf16(qkv, "qkv");
   check_bf16(out, "out");
   check_bf16(dout, "dout");
@@ -114,8 +120,21 @@ void attention_bwd(const Tensor& qkv, const Tensor& out, const Tensor& dout, con
   const int B = int(qkv.size(0)), S = int(qkv.size(1)), d = int(qkv.size(2) / 3);
   const int launched = pb::attention_bwd_launch(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), dqkv.data_ptr(),
                                                 delta.data_ptr<float>(), B, S, n_heads, d / n_heads, float(scale), causal,
-                                                at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv));
+                                                at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(qkv),
+                                                alibi_slopes.has_value() ? alibi_slopes->data_ptr<float>() : nullptr);
   g_launches += launched;
+}
+void rope(Tensor& qkv, const Tensor& cos_t, const Tensor& sin_t, int n_heads, bool inverse) {
+  check_bf16(qkv, "qkv");
+  check_f32(cos_t, "cos");
+  check_f32(sin_t, "sin");
+  TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous(), "qkv must be contiguous [B,S,3*d]");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  const int S = int(qkv.size(1)), d = int(qkv.size(2) / 3), dh = d / n_heads;
+  TORCH_CHECK(cos_t.is_contiguous() && sin_t.is_contiguous() && cos_t.size(0) >= S && cos_t.size(1) == dh / 2, "cos/sin must be [>=S, dh/2]");
+  pb::rope_launch(qkv.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), (long long)qkv.size(0) * S, S, n_heads, dh, inverse,
+                  stream_of(qkv));
+  g_launches += 1;
 }
 
 // ---------------------------------------------------------------------------------- fused ops
@@ -353,8 +372,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("d"), py::arg("a_mn") = 0, py::arg("b_mn") = 0, py::arg("epi") = 0,
         py::arg("bias") = py::none(), py::arg("aux") = py::none(), py::arg("d2") = py::none(), py::arg("accumulate") = false,
         py::arg("alpha") = 1.0, py::arg("cluster") = 0);
-  m.def("attention_fwd", &attention_fwd);
-  m.def("attention_bwd", &attention_bwd);
+  m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("out"), py::arg("lse"), py::arg("n_heads"), py::arg("scale"),
+        py::arg("causal"), py::arg("alibi_slopes") = py::none());
+  m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("dqkv"), py::arg("delta"),
+        py::arg("n_heads"), py::arg("scale"), py::arg("causal"), py::arg("alibi_slopes") = py::none());
+  m.def("rope", &rope);
   m.def("embed_fwd", &embed_fwd);
   m.def("embed_bwd", &embed_bwd);
   m.def("layernorm_fwd", &layernorm_fwd);

@@ -60,9 +60,9 @@ class B200Engine:
             raise RuntimeError("B200Engine needs a CUDA (sm_100a) device")
         if precision not in ("amp_bf16", "amp_fp8"):
             raise NotImplementedError(f"B200Engine computes in bf16 (got precision={precision}); use kernels.*=torch for fp32/fp16")
-        if cfg.alibi or cfg.rope or cfg.qk_ln or cfg.clip_qkv or cfg.no_bias or not cfg.learned_pos_emb:
-            raise NotImplementedError("B200Engine covers the shipped MPT configs (learned positions, biases, no qk_ln/clip_qkv); "
-                                      "set kernels.*=torch for ALiBi/RoPE variants")
+        if cfg.qk_ln or cfg.clip_qkv or cfg.no_bias:
+            raise NotImplementedError("B200Engine covers learned / ALiBi / RoPE positions with biases; "
+                                      "set kernels.*=torch for qk_ln, clip_qkv or no_bias variants")
         if frozen_layers or unfrozen_layers:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
         if precision == "amp_fp8":
@@ -92,6 +92,14 @@ class B200Engine:
             raise ValueError("shadow_storage must be a bf16 tensor with layout.total elements")
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.lm_head_chunk = int(lm_head_chunk)
+        # positional variants of the MPT attention block (ref: SURVEY §5.7): ALiBi slopes enter the attention kernels,
+        # RoPE rotates q / k in place after the QKV GEMM (and un-rotates their gradients)
+        from photon_b200.models.mpt import alibi_slopes, rope_tables
+
+        self.alibi = alibi_slopes(cfg.n_heads, cfg.alibi_bias_max).to(self.device, torch.float32).contiguous() if cfg.alibi else None
+        self.rope = tuple(t.contiguous() for t in rope_tables(cfg.max_seq_len, cfg.d_head, cfg.rope_theta, self.device)) if cfg.rope else None
+        if (self.alibi is not None or self.rope is not None) and kernels.get("attention", "auto") == "torch":
+            raise NotImplementedError("ALiBi / RoPE on the engine need kernels.attention=b200")
         # keep only the block inputs h[i]; every block's internals are recomputed right before its backward
         # (fsdp_config.activation_checkpointing, ref: conf/llm_config/mpt-1b.yaml:88): 16·T·d·L bytes of bf16 -> 16·T·d
         self.activation_checkpointing = bool(activation_checkpointing)
@@ -109,8 +117,9 @@ class B200Engine:
         v32 = lambda n: lay.view(P, "transformer." + n)  # noqa: E731
         vg = lambda n: lay.view(G, "transformer." + n)  # noqa: E731
         v16 = lambda n: lay.view(Sd, "transformer." + n)  # noqa: E731
-        self.wte16, self.wpe16 = v16("wte.weight"), v16("wpe.weight")
-        self.d_wte, self.d_wpe = vg("wte.weight"), vg("wpe.weight")
+        has_wpe = self.cfg.learned_pos_emb
+        self.wte16, self.wpe16 = v16("wte.weight"), (v16("wpe.weight") if has_wpe else None)
+        self.d_wte, self.d_wpe = vg("wte.weight"), (vg("wpe.weight") if has_wpe else None)
         self.gf, self.bf, self.d_gf, self.d_bf = v32("norm_f.weight"), v32("norm_f.bias"), vg("norm_f.weight"), vg("norm_f.bias")
         self.layers: list[_LayerW] = []
         for i in range(self.cfg.n_layers):
@@ -164,7 +173,8 @@ class B200Engine:
         c = self.cfg
         scale = 1.0 / math.sqrt(c.d_head)
         if self.attn_mode == "b200":
-            ops.attention_fwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model), lw["lse"], c.n_heads, scale, True)
+            ops.attention_fwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model), lw["lse"], c.n_heads, scale, True,
+                              self.alibi)
             return
         q, k, v = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).permute(2, 0, 3, 1, 4)
         o = F.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
@@ -176,7 +186,9 @@ class B200Engine:
         if self.attn_mode == "b200":
             ops.attention_bwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model),
                               ws["dattn"].view(b, S, c.d_model), lw["lse"], ws["dqkv"].view(b, S, 3 * c.d_model), ws["delta"],
-                              c.n_heads, scale, True)
+                              c.n_heads, scale, True, self.alibi)
+            if self.rope is not None:   # gradients w.r.t. the un-rotated q, k
+                ops.rope_(ws["dqkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads, inverse=True)
             return
         with torch.enable_grad():
             qkv = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).detach().requires_grad_(True)
@@ -190,6 +202,8 @@ class B200Engine:
         c, h, w, lw = self.cfg, ws["h"], self.layers[i], ws["layers"][i]
         ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
         ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
+        if self.rope is not None:
+            ops.rope_(lw["qkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads)
         self._attention_fwd(lw, b, S)
         ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
         ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)

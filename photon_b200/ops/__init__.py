@@ -193,10 +193,20 @@ def fused_optimizer_step(opt: Any, lr: float, grad_mult: torch.Tensor | float | 
 
 
 # ---------------------------------------------------------------------------- attention
-def attention_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, n_heads: int, scale: float, causal: bool = True) -> None:
-    ext().attention_fwd(qkv, out, lse, int(n_heads), float(scale), bool(causal))
+def attention_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, n_heads: int, scale: float, causal: bool = True,
+                  alibi_slopes: torch.Tensor | None = None) -> None:
+    """``alibi_slopes``: optional fp32 [n_heads]; adds ``slope_h * (key - query)`` to the scores (MPT ``attn_config.alibi``)."""
+    ext().attention_fwd(qkv, out, lse, int(n_heads), float(scale), bool(causal), alibi_slopes)
 
 
 def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor,
-                  delta: torch.Tensor, n_heads: int, scale: float, causal: bool = True) -> None:
-    ext().attention_bwd(qkv, out, dout, lse, dqkv, delta, int(n_heads), float(scale), bool(causal))
+                  delta: torch.Tensor, n_heads: int, scale: float, causal: bool = True,
+                  alibi_slopes: torch.Tensor | None = None) -> None:
+    ext().attention_bwd(qkv, out, dout, lse, dqkv, delta, int(n_heads), float(scale), bool(causal), alibi_slopes)
+
+
+def rope_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, inverse: bool = False) -> torch.Tensor:
+    """In-place rotary embedding (rotate-half) of the q and k thirds of ``qkv`` [B,S,3d]; ``inverse`` applies the
+    transposed rotation (what the gradients of q and k need)."""
+    ext().rope(qkv, cos, sin, int(n_heads), bool(inverse))
+    return qkv

@@ -105,3 +105,55 @@ def test_attention_persistent_many_items(B, S, H, causal, dh):
     ops.attention_fwd(qkv, out2, lse, H, scale, causal)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("B,S,H,dh", [(2, 512, 4, 64), (1, 1024, 3, 128)])
+def test_attention_alibi_fwd_bwd(B, S, H, dh):
+    """attn_config.alibi: score += slope_h * (key - query) inside both kernels, vs an explicit fp32 oracle."""
+    from photon_b200 import ops
+    from photon_b200.models.mpt import alibi_slopes
+
+    d = H * dh
+    qkv = torch.randn(B, S, 3 * d, device="cuda:0").to(torch.bfloat16)
+    dout = torch.randn(B, S, d, device="cuda:0").to(torch.bfloat16)
+    slopes = alibi_slopes(H, 8).to("cuda:0")
+    out = torch.empty(B, S, d, device="cuda:0", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, S, device="cuda:0", dtype=torch.float32)
+    scale = 1.0 / math.sqrt(dh)
+    ops.attention_fwd(qkv, out, lse, H, scale, True, slopes)
+    dqkv = torch.zeros_like(qkv)
+    delta = torch.empty_like(lse)
+    ops.attention_bwd(qkv, out, dout, lse, dqkv, delta, H, scale, True, slopes)
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    pos = torch.arange(S, device="cuda:0")
+    bias = slopes[:, None, None] * (pos[None, :] - pos[:, None]).clamp(max=0).float()[None]
+    att = (q @ k.transpose(-1, -2)) * scale + bias[None]
+    att = att.masked_fill(~torch.ones(S, S, dtype=torch.bool, device="cuda:0").tril(), float("-inf"))
+    ro = (torch.softmax(att, dim=-1) @ v).transpose(1, 2).reshape(B, S, d)
+    assert (out.float() - ro).abs().max().item() < 3e-2
+    assert (lse - torch.logsumexp(att, dim=-1)).abs().max().item() < 2e-2
+    ro.backward(dout.float())
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        a, b = dqkv[..., sl].float(), x.grad[..., sl]
+        assert ((a - b).norm() / b.norm()).item() < 3e-2, name
+
+
+def test_rope_kernel_matches_oracle_and_inverts():
+    from photon_b200 import ops
+    from photon_b200.models.mpt import apply_rope, rope_tables
+
+    B, S, H, dh = 2, 256, 4, 64
+    d = H * dh
+    qkv = torch.randn(B, S, 3 * d, device="cuda:0").to(torch.bfloat16)
+    cos, sin = rope_tables(S, dh, 10000.0, "cuda:0")
+    ref = qkv.float().view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)            # [3, B, H, S, dh]
+    rq, rk = apply_rope(ref[0], cos, sin), apply_rope(ref[1], cos, sin)
+    work = qkv.clone()
+    ops.rope_(work, cos.contiguous(), sin.contiguous(), H)
+    got = work.float().view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    assert (got[0] - rq).abs().max().item() < 3e-2 and (got[1] - rk).abs().max().item() < 3e-2
+    assert torch.equal(got[2], ref[2])                                        # v untouched
+    ops.rope_(work, cos.contiguous(), sin.contiguous(), H, inverse=True)      # rotation is orthogonal
+    assert (work.float() - qkv.float()).abs().max().item() < 6e-2

@@ -151,3 +151,30 @@ def test_engine_d_head_128_runs_on_own_attention():
     cos = torch.nn.functional.cosine_similarity(ref.flat.grads, eng.flat.grads, dim=0).item()
     rel = ((ref.flat.grads - eng.flat.grads).norm() / ref.flat.grads.norm()).item()
     assert cos > 0.995 and rel < 0.08, (cos, rel)
+
+
+@pytest.mark.parametrize("variant", ["alibi", "rope"])
+def test_engine_positional_variants_match_torch(variant):
+    """ALiBi / RoPE (no learned positions) run on the engine's own attention kernels and match the PyTorch model."""
+    from photon_b200.models.engine import B200Engine
+    from photon_b200.models.mpt import MPTConfig
+    from photon_b200.train.backend import TorchBackend
+
+    cfg = MPTConfig(d_model=256, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=2048, attn_impl="torch",
+                    learned_pos_emb=False, **{variant: True})
+    dev = torch.device("cuda", 0)
+    ref = TorchBackend(cfg, dev, "fp32", seed=3)
+    eng = B200Engine(cfg, dev, "amp_bf16", {"cuda_graph": False}, seed=5)
+    assert eng.attn_mode == "b200" and (eng.alibi is not None) == (variant == "alibi") and (eng.rope is not None) == (variant == "rope")
+    eng.flat.params.copy_(ref.flat.params)
+    eng.params_updated()
+    ids = torch.randint(0, cfg.vocab_size, (4, cfg.max_seq_len), device=dev)
+    denom = float(ids.shape[0] * (ids.shape[1] - 1))
+    ref.flat.zero_grad(), eng.flat.zero_grad()
+    l_ref, _ = ref.fwd_bwd(ids, denom)
+    l_eng, _ = eng.fwd_bwd(ids, denom)
+    torch.cuda.synchronize()
+    assert abs(float(l_ref) - float(l_eng)) / float(l_ref) < 5e-3, (float(l_ref), float(l_eng))
+    cos = torch.nn.functional.cosine_similarity(ref.flat.grads, eng.flat.grads, dim=0).item()
+    rel = ((ref.flat.grads - eng.flat.grads).norm() / ref.flat.grads.norm()).item()
+    assert cos > 0.995 and rel < 0.08, (cos, rel)
