@@ -60,9 +60,9 @@ class B200Engine:
             raise RuntimeError("B200Engine needs a CUDA (sm_100a) device")
         if precision not in ("amp_bf16", "amp_fp8"):
             raise NotImplementedError(f"B200Engine computes in bf16 (got precision={precision}); use kernels.*=torch for fp32/fp16")
-        if cfg.qk_ln or cfg.clip_qkv or cfg.no_bias:
-            raise NotImplementedError("B200Engine covers learned / ALiBi / RoPE positions with biases; "
-                                      "set kernels.*=torch for qk_ln, clip_qkv or no_bias variants")
+        if cfg.qk_ln:
+            raise NotImplementedError("B200Engine covers learned / ALiBi / RoPE positions, no_bias and clip_qkv; "
+                                      "set kernels.*=torch for qk_ln")
         if frozen_layers or unfrozen_layers:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
         if precision == "amp_fp8":
@@ -114,8 +114,11 @@ class B200Engine:
     # ------------------------------------------------------------------ binding
     def _bind(self) -> None:
         lay, P, G, Sd = self.flat.layout, self.flat.params, self.flat.grads, self.bf16_params
-        v32 = lambda n: lay.view(P, "transformer." + n)  # noqa: E731
-        vg = lambda n: lay.view(G, "transformer." + n)  # noqa: E731
+        have = set(lay.names)
+        # biases are absent under `no_bias`: every consumer below accepts None (GEMM without bias, LN without beta,
+        # no bias-gradient column sums)
+        v32 = lambda n: lay.view(P, "transformer." + n) if "transformer." + n in have else None  # noqa: E731
+        vg = lambda n: lay.view(G, "transformer." + n) if "transformer." + n in have else None  # noqa: E731
         v16 = lambda n: lay.view(Sd, "transformer." + n)  # noqa: E731
         has_wpe = self.cfg.learned_pos_emb
         self.wte16, self.wpe16 = v16("wte.weight"), (v16("wpe.weight") if has_wpe else None)
@@ -162,6 +165,8 @@ class B200Engine:
             ws["layers"].append({"ln1": bf(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d),
                                  "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": bf(T, d), "m2": f32(T), "r2": f32(T),
                                  "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
+            if c.clip_qkv:
+                ws["layers"][-1]["clipmask"] = torch.empty(T, 3 * d, dtype=torch.bool, device=dev)
         ws.update(lnf=bf(T, d), mf=f32(T), rf=f32(T), dlnf=bf(T, d), dh=bf(T, d), dhmid=bf(T, d), dln=bf(T, d),
                   dqkv=bf(T, 3 * d), dattn=bf(T, d), dz=bf(T, c.expansion_ratio * d), delta=f32(b, H, S),
                   logits=bf(min(self.lm_head_chunk, T), c.vocab_size))
@@ -202,6 +207,9 @@ class B200Engine:
         c, h, w, lw = self.cfg, ws["h"], self.layers[i], ws["layers"][i]
         ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
         ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
+        if c.clip_qkv:   # attn_config.clip_qkv: clamp the fused projection; remember where the gradient passes
+            torch.logical_and(lw["qkv"] > -c.clip_qkv, lw["qkv"] < c.clip_qkv, out=lw["clipmask"])
+            lw["qkv"].clamp_(-c.clip_qkv, c.clip_qkv)
         if self.rope is not None:
             ops.rope_(lw["qkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads)
         self._attention_fwd(lw, b, S)
@@ -248,19 +256,25 @@ class B200Engine:
             if self.activation_checkpointing and i < c.n_layers - 1:
                 self._block_fwd(i, ws, b, S)   # recompute (the shared buffers still hold the LAST block after the forward)
             # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
-            ops.col_sum(dh, w.d_bdown)
+            if w.d_bdown is not None:
+                ops.col_sum(dh, w.d_bdown)
             ops.linear_wgrad(dh, lw["u"], w.d_wdown)
             ops.linear_dgrad(dh, w.wdown, ws["dz"], mul=lw["z"])
-            ops.col_sum(ws["dz"], w.d_bup)
+            if w.d_bup is not None:
+                ops.col_sum(ws["dz"], w.d_bup)
             ops.linear_wgrad(ws["dz"], lw["ln2"], w.d_wup)
             ops.linear_dgrad(ws["dz"], w.wup, dln)
             ops.layernorm_bwd(dln, lw["hmid"], w.g2, lw["m2"], lw["r2"], dh, dhmid, w.d_g2, w.d_b2)
             # ---- attention: hmid = h[i] + out_proj(attn(qkv(ln1(h[i]))))
-            ops.col_sum(dhmid, w.d_bo)
+            if w.d_bo is not None:
+                ops.col_sum(dhmid, w.d_bo)
             ops.linear_wgrad(dhmid, lw["attn"], w.d_wo)
             ops.linear_dgrad(dhmid, w.wo, ws["dattn"])
             self._attention_bwd(lw, ws, b, S)
-            ops.col_sum(ws["dqkv"], w.d_bqkv)
+            if c.clip_qkv:
+                ws["dqkv"].mul_(lw["clipmask"])
+            if w.d_bqkv is not None:
+                ops.col_sum(ws["dqkv"], w.d_bqkv)
             ops.linear_wgrad(ws["dqkv"], lw["ln1"], w.d_wqkv)
             ops.linear_dgrad(ws["dqkv"], w.wqkv, dln)
             ops.layernorm_bwd(dln, h[i], w.g1, lw["m1"], lw["r1"], dhmid, dh, w.d_g1, w.d_b1)

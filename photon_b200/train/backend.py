@@ -145,8 +145,8 @@ def build_backend(model_cfg: MPTConfig, device: torch.device, precision: str, ke
         unsupported = []
         if precision not in ("amp_bf16", "amp_fp8"):
             unsupported.append(f"precision={precision}")
-        if model_cfg.qk_ln or model_cfg.clip_qkv or model_cfg.no_bias:
-            unsupported.append("attn/bias variant (qk_ln|clip_qkv|no_bias)")
+        if model_cfg.qk_ln:
+            unsupported.append("attn_config.qk_ln")
         if (model_cfg.alibi or model_cfg.rope) and kernels.get("attention", "auto") == "torch":
             unsupported.append("alibi/rope with kernels.attention=torch")
         if kw.get("frozen_layers") or kw.get("unfrozen_layers"):
