@@ -98,8 +98,6 @@ class B200Engine:
 
         self.alibi = alibi_slopes(cfg.n_heads, cfg.alibi_bias_max).to(self.device, torch.float32).contiguous() if cfg.alibi else None
         self.rope = tuple(t.contiguous() for t in rope_tables(cfg.max_seq_len, cfg.d_head, cfg.rope_theta, self.device)) if cfg.rope else None
-        if (self.alibi is not None or self.rope is not None) and kernels.get("attention", "auto") == "torch":
-            raise NotImplementedError("ALiBi / RoPE on the engine need kernels.attention=b200")
         # keep only the block inputs h[i]; every block's internals are recomputed right before its backward
         # (fsdp_config.activation_checkpointing, ref: conf/llm_config/mpt-1b.yaml:88): 16·T·d·L bytes of bf16 -> 16·T·d
         self.activation_checkpointing = bool(activation_checkpointing)
@@ -177,18 +175,28 @@ class B200Engine:
     def _attention_fwd(self, lw: dict[str, Any], b: int, S: int) -> None:
         c = self.cfg
         scale = 1.0 / math.sqrt(c.d_head)
-        if self.attn_mode == "b200":
+        if self.attn_mode == "b200" and S % 128 == 0:
             ops.attention_fwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model), lw["lse"], c.n_heads, scale, True,
                               self.alibi)
             return
+        # library attention: kernels.attention=torch, an unsupported d_head, or a sequence length that is not a multiple
+        # of the 128-row tiles (the shipped configs use 2048)
         q, k, v = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).permute(2, 0, 3, 1, 4)
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
+        o = F.scaled_dot_product_attention(q, k, v, scale=scale, **self._sdpa_mask(S, q.dtype))
         lw["attn"].view(b, S, c.n_heads, c.d_head).copy_(o.transpose(1, 2))
+
+    def _sdpa_mask(self, S: int, dtype: torch.dtype) -> dict[str, Any]:
+        if self.alibi is None:
+            return {"is_causal": True}
+        pos = torch.arange(S, device=self.device)
+        bias = self.alibi[:, None, None] * (pos[None, :] - pos[:, None]).clamp(max=0).float()[None]
+        keep = torch.ones(S, S, dtype=torch.bool, device=self.device).tril()
+        return {"attn_mask": bias.masked_fill(~keep, float("-inf")).to(dtype)[None]}
 
     def _attention_bwd(self, lw: dict[str, Any], ws: dict[str, Any], b: int, S: int) -> None:
         c = self.cfg
         scale = 1.0 / math.sqrt(c.d_head)
-        if self.attn_mode == "b200":
+        if self.attn_mode == "b200" and S % 128 == 0:
             ops.attention_bwd(lw["qkv"].view(b, S, 3 * c.d_model), lw["attn"].view(b, S, c.d_model),
                               ws["dattn"].view(b, S, c.d_model), lw["lse"], ws["dqkv"].view(b, S, 3 * c.d_model), ws["delta"],
                               c.n_heads, scale, True, self.alibi)
@@ -198,9 +206,11 @@ class B200Engine:
         with torch.enable_grad():
             qkv = lw["qkv"].view(b, S, 3, c.n_heads, c.d_head).detach().requires_grad_(True)
             q, k, v = qkv.permute(2, 0, 3, 1, 4)
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=True, scale=scale)
+            o = F.scaled_dot_product_attention(q, k, v, scale=scale, **self._sdpa_mask(S, q.dtype))
             (g,) = torch.autograd.grad(o, qkv, ws["dattn"].view(b, S, c.n_heads, c.d_head).transpose(1, 2))
         ws["dqkv"].view(b, S, 3, c.n_heads, c.d_head).copy_(g)
+        if self.rope is not None:
+            ops.rope_(ws["dqkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads, inverse=True)
 
     def _block_fwd(self, i: int, ws: dict[str, Any], b: int, S: int) -> None:
         """h[i] -> h[i+1]; the block internals land in ws["layers"][i] (also the recompute step under checkpointing)."""
@@ -294,7 +304,7 @@ class B200Engine:
         """Accumulate d(Σ token-loss · scale / denom) into ``flat.grads``; returns (loss_sum, n_tokens)."""
         b, S = ids.shape
         grad_scale = scale / denom
-        graphable = self.use_graph and self.attn_mode == "b200" and not self.collect_activation_stats
+        graphable = self.use_graph and self.attn_mode == "b200" and S % 128 == 0 and not self.collect_activation_stats
         if not graphable:
             n0 = ops.launch_count()
             self._fwd_bwd_eager(ids, grad_scale)

@@ -147,8 +147,6 @@ def build_backend(model_cfg: MPTConfig, device: torch.device, precision: str, ke
             unsupported.append(f"precision={precision}")
         if model_cfg.qk_ln:
             unsupported.append("attn_config.qk_ln")
-        if (model_cfg.alibi or model_cfg.rope) and kernels.get("attention", "auto") == "torch":
-            unsupported.append("alibi/rope with kernels.attention=torch")
         if kw.get("frozen_layers") or kw.get("unfrozen_layers"):
             unsupported.append("frozen/unfrozen layers")
         if unsupported:

@@ -179,3 +179,27 @@ def test_engine_positional_variants_match_torch(variant):
     cos = torch.nn.functional.cosine_similarity(ref.flat.grads, eng.flat.grads, dim=0).item()
     rel = ((ref.flat.grads - eng.flat.grads).norm() / ref.flat.grads.norm()).item()
     assert cos > 0.995 and rel < 0.08, (cos, rel)
+
+
+def test_engine_sequence_length_not_multiple_of_128_uses_library_attention():
+    """The tcgen05 attention kernels need S % 128 == 0; any other length runs attention through SDPA inside the same engine
+    step (everything else stays on our kernels) and still matches the PyTorch model."""
+    from photon_b200.models.engine import B200Engine
+    from photon_b200.models.mpt import MPTConfig
+    from photon_b200.train.backend import TorchBackend
+
+    cfg = MPTConfig(d_model=256, n_heads=4, n_layers=2, max_seq_len=200, vocab_size=2048, attn_impl="torch")
+    dev = torch.device("cuda", 0)
+    ref = TorchBackend(cfg, dev, "fp32", seed=3)
+    eng = B200Engine(cfg, dev, "amp_bf16", {}, seed=5)
+    eng.flat.params.copy_(ref.flat.params)
+    eng.params_updated()
+    ids = torch.randint(0, cfg.vocab_size, (4, 200), device=dev)
+    denom = float(4 * 199)
+    ref.flat.zero_grad(), eng.flat.zero_grad()
+    l_ref, _ = ref.fwd_bwd(ids, denom)
+    l_eng, _ = eng.fwd_bwd(ids, denom)
+    torch.cuda.synchronize()
+    assert abs(float(l_ref) - float(l_eng)) / float(l_ref) < 5e-3
+    rel = ((ref.flat.grads - eng.flat.grads).norm() / ref.flat.grads.norm()).item()
+    assert rel < 0.08, rel
