@@ -45,13 +45,21 @@ class NvlFedRound:
         self.n_local = len(self.arena.devices) if self.arena.single else 1
         self.has_shadow = bf16_shadow
         self._wsum = [0.0] * self.n_local
-        # server moment shards live outside the arena (never read by peers); full length keeps indexing trivial
+        # server moments live outside the arena (never read by peers) and exist ONLY for the shard a rank owns
+        # (8 B/param divided by the number of GPUs: what lets the multi-billion-parameter configs fit); the kernel keeps
+        # indexing by global element, so it is handed `shard_ptr - lo`
         self._m: list[torch.Tensor | None] = []
         self._v: list[torch.Tensor | None] = []
         for i in range(self.n_local):
             dev = torch.device("cuda", self.arena.devices[i])
-            self._m.append(torch.zeros(total, device=dev) if strategy.n_moments >= 1 else None)
-            self._v.append(torch.zeros(total, device=dev) if strategy.n_moments >= 2 else None)
+            lo, hi = self.shard_of(i)
+            self._m.append(torch.zeros(hi - lo, device=dev) if strategy.n_moments >= 1 else None)
+            self._v.append(torch.zeros(hi - lo, device=dev) if strategy.n_moments >= 2 else None)
+
+    def shard_of(self, local: int = 0) -> tuple[int, int]:
+        """[lo, hi) of the flat index space whose server state lives on local GPU ``local``."""
+        rank = local if self.arena.single else self.arena.rank
+        return self.arena.shard(self.total, rank)
 
     # ------------------------------------------------------------------ planes
     def _r(self, local: int) -> int | None:
@@ -75,11 +83,13 @@ class NvlFedRound:
                 ops.cast_bf16(g, self.global_shadow(i))
 
     def set_moments(self, m: torch.Tensor | None, v: torch.Tensor | None) -> None:
+        """Install full-length server moments (every rank keeps its own slice)."""
         for i in range(self.n_local):
+            lo, hi = self.shard_of(i)
             if m is not None and self._m[i] is not None:
-                self._m[i].copy_(m.to(self._m[i].device))
+                self._m[i].copy_(m[lo:hi].to(self._m[i].device))
             if v is not None and self._v[i] is not None:
-                self._v[i].copy_(v.to(self._v[i].device))
+                self._v[i].copy_(v[lo:hi].to(self._v[i].device))
 
     # ------------------------------------------------------------------ round protocol
     def begin_round(self) -> None:
@@ -107,7 +117,8 @@ class NvlFedRound:
             launches.append((rank, dev, lo, hi, i))
         for rank, dev, lo, hi, i in launches:
             ext.fed_round(ar.ctl_ptrs(), rank, dev, epoch, ar.ptrs("acc"), ar.ptrs("xg"), ar.ptrs("xs") if self.has_shadow else [],
-                          self._m[i].data_ptr() if self._m[i] is not None else 0, self._v[i].data_ptr() if self._v[i] is not None else 0,
+                          self._m[i].data_ptr() - 4 * lo if self._m[i] is not None else 0,
+                          self._v[i].data_ptr() - 4 * lo if self._v[i] is not None else 0,
                           lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
                           hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat))
 
@@ -127,7 +138,21 @@ class NvlFedRound:
         return {f"server/l2_norm_{n}": math.sqrt(max(float(s), 0.0)) for n, s in list(zip(names, sums.tolist()))[:keep]}
 
     def moments(self, local: int = 0) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        """This GPU's slices ``[lo, hi)`` of the server moments (see :meth:`shard_of`)."""
         return self._m[local], self._v[local]
+
+    def full_moments(self, local: int = 0) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        """Zero-padded full-length copies of this GPU's slices (sum them over ranks to stitch the state)."""
+        lo, hi = self.shard_of(local)
+        out = []
+        for t in (self._m[local], self._v[local]):
+            if t is None:
+                out.append(None)
+                continue
+            full = torch.zeros(self.total, dtype=t.dtype, device=t.device)
+            full[lo:hi] = t
+            out.append(full)
+        return out[0], out[1]
 
     def close(self) -> None:
         self.arena.close()

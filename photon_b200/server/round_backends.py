@@ -292,6 +292,7 @@ class NvlRoundBackend(RoundBackend):
         # keep the strategy object's state pointing at the device planes (checkpointing reads them)
         self.strategy.parameters = self.fed.global_params()
         self.strategy.layout = self.layout
+        # the strategy object only keeps this rank's slices; `moments()` below stitches the full state for checkpoints
         m, v = self.fed.moments()
         self.strategy.momentum_vector, self.strategy.second_momentum_vector = m, v
 
@@ -321,14 +322,9 @@ class NvlRoundBackend(RoundBackend):
         """Full-length server moments. Each rank only maintains its shard, so the shards are
         stitched with one all-reduce of zero-padded copies (checkpoint path, not the hot path)."""
         out = []
-        for t in self.fed.moments():
-            if t is None or self.world_size == 1 or not _dist_on(self.group):
-                out.append(t)
-                continue
-            lo, hi = self.fed.arena.shard(self.layout.total)
-            full = torch.zeros_like(t)
-            full[lo:hi] = t[lo:hi]
-            dist.all_reduce(full, group=self.group)
+        for full in self.fed.full_moments():
+            if full is not None and self.world_size > 1 and _dist_on(self.group):
+                dist.all_reduce(full, group=self.group)
             out.append(full)
         return out[0], out[1]
 
