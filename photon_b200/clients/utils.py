@@ -149,14 +149,13 @@ def post_process_client_result(trainer: Trainer, initial: torch.Tensor, fit_conf
     lay = st.flat.layout
     n_samples = max(1, int(steps_done) * int(fit_config.batch_size))  # ref: clients/utils.py:583
     metrics: dict[str, Any] = dict(st.train_metric_values)
+    # per-tensor pseudo-gradient norms with ONE host sync and no parameter-sized fp64 temporaries (the reference does one
+    # NumPy reduction per tensor on the CPU, ref: clients/utils.py:599-619): a multi-tensor norm over views of the delta
     delta = initial - st.flat.params
-    # per-tensor pseudo-gradient norms with ONE host sync (the reference does 148 NumPy reductions on the CPU,
-    # ref: clients/utils.py:599-619): segment sums of delta^2 via a cumulative sum over the flat buffer
-    sq = (delta.double() ** 2).cumsum(0)
-    offs = torch.tensor(lay.offsets, device=sq.device)
-    ends = offs + torch.tensor(lay.numels, device=sq.device) - 1
-    seg = sq[ends] - torch.where(offs > 0, sq[(offs - 1).clamp(min=0)], torch.zeros_like(sq[:1]))
-    vals = torch.cat([seg.clamp(min=0).sqrt(), seg.sum().clamp(min=0).sqrt()[None]]).tolist()
+    views = [lay.view(delta, i) for i in range(len(lay.names))]
+    per = torch.stack(torch._foreach_norm(views)).double()
+    vals = torch.cat([per, (per * per).sum().sqrt()[None]]).tolist()
+    del delta, views
     metrics["client/l2_norm_pseudo_gradient"] = vals[-1]
     for i in range(len(lay.names)):
         metrics[f"client/layer/{i}/l2_norm_of_pseudo_gradient"] = vals[i]

@@ -42,7 +42,8 @@ class _LayerW:
     """Per-block handles: bf16 weights (shadow plane), fp32 small params and fp32 grads."""
 
     __slots__ = ("wqkv", "bqkv", "wo", "bo", "wup", "bup", "wdown", "bdown", "g1", "b1", "g2", "b2",
-                 "d_wqkv", "d_bqkv", "d_wo", "d_bo", "d_wup", "d_bup", "d_wdown", "d_bdown", "d_g1", "d_b1", "d_g2", "d_b2")
+                 "d_wqkv", "d_bqkv", "d_wo", "d_bo", "d_wup", "d_bup", "d_wdown", "d_bdown", "d_g1", "d_b1", "d_g2", "d_b2",
+                 "qk_g", "qk_b", "d_qk_g", "d_qk_b")
 
 
 class B200Engine:
@@ -60,9 +61,6 @@ class B200Engine:
             raise RuntimeError("B200Engine needs a CUDA (sm_100a) device")
         if precision not in ("amp_bf16", "amp_fp8"):
             raise NotImplementedError(f"B200Engine computes in bf16 (got precision={precision}); use kernels.*=torch for fp32/fp16")
-        if cfg.qk_ln:
-            raise NotImplementedError("B200Engine covers learned / ALiBi / RoPE positions, no_bias and clip_qkv; "
-                                      "set kernels.*=torch for qk_ln")
         if frozen_layers or unfrozen_layers:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
         if precision == "amp_fp8":
@@ -136,6 +134,11 @@ class B200Engine:
             w.d_bqkv, w.d_bo, w.d_bup, w.d_bdown = (vg(p + "attn.Wqkv.bias"), vg(p + "attn.out_proj.bias"),
                                                     vg(p + "ffn.up_proj.bias"), vg(p + "ffn.down_proj.bias"))
             w.d_g1, w.d_b1, w.d_g2, w.d_b2 = vg(p + "norm_1.weight"), vg(p + "norm_1.bias"), vg(p + "norm_2.weight"), vg(p + "norm_2.bias")
+            # attn_config.qk_ln: LayerNorm over d_model on the query and key projections
+            w.qk_g = [v32(p + "attn.q_ln.weight"), v32(p + "attn.k_ln.weight")]
+            w.qk_b = [v32(p + "attn.q_ln.bias"), v32(p + "attn.k_ln.bias")]
+            w.d_qk_g = [vg(p + "attn.q_ln.weight"), vg(p + "attn.k_ln.weight")]
+            w.d_qk_b = [vg(p + "attn.q_ln.bias"), vg(p + "attn.k_ln.bias")]
             self.layers.append(w)
 
     def params_updated(self) -> None:
@@ -165,6 +168,10 @@ class B200Engine:
                                  "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
             if c.clip_qkv:
                 ws["layers"][-1]["clipmask"] = torch.empty(T, 3 * d, dtype=torch.bool, device=dev)
+            if c.qk_ln:   # pre-LayerNorm q / k (inputs of the two LN backward passes) and their row statistics
+                ws["layers"][-1].update(qk_pre=[bf(T, d), bf(T, d)], qk_m=[f32(T), f32(T)], qk_r=[f32(T), f32(T)])
+        if c.qk_ln:
+            ws.update(qk_tmp=bf(T, d), qk_tmp2=bf(T, d))
         ws.update(lnf=bf(T, d), mf=f32(T), rf=f32(T), dlnf=bf(T, d), dh=bf(T, d), dhmid=bf(T, d), dln=bf(T, d),
                   dqkv=bf(T, 3 * d), dattn=bf(T, d), dz=bf(T, c.expansion_ratio * d), delta=f32(b, H, S),
                   logits=bf(min(self.lm_head_chunk, T), c.vocab_size))
@@ -220,6 +227,12 @@ class B200Engine:
         if c.clip_qkv:   # attn_config.clip_qkv: clamp the fused projection; remember where the gradient passes
             torch.logical_and(lw["qkv"] > -c.clip_qkv, lw["qkv"] < c.clip_qkv, out=lw["clipmask"])
             lw["qkv"].clamp_(-c.clip_qkv, c.clip_qkv)
+        if c.qk_ln:   # the q / k thirds are strided inside the fused buffer: normalise contiguous copies
+            qkv3 = lw["qkv"].view(-1, 3, c.d_model)
+            for j in range(2):
+                lw["qk_pre"][j].copy_(qkv3[:, j])
+                ops.layernorm_fwd(lw["qk_pre"][j], w.qk_g[j], w.qk_b[j], ws["qk_tmp"], lw["qk_m"][j], lw["qk_r"][j], c.norm_eps)
+                qkv3[:, j].copy_(ws["qk_tmp"])
         if self.rope is not None:
             ops.rope_(lw["qkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads)
         self._attention_fwd(lw, b, S)
@@ -281,6 +294,13 @@ class B200Engine:
             ops.linear_wgrad(dhmid, lw["attn"], w.d_wo)
             ops.linear_dgrad(dhmid, w.wo, ws["dattn"])
             self._attention_bwd(lw, ws, b, S)
+            if c.qk_ln:
+                dqkv3 = ws["dqkv"].view(-1, 3, c.d_model)
+                for j in range(2):
+                    ws["qk_tmp"].copy_(dqkv3[:, j])
+                    ops.layernorm_bwd(ws["qk_tmp"], lw["qk_pre"][j], w.qk_g[j], lw["qk_m"][j], lw["qk_r"][j], None, ws["qk_tmp2"],
+                                      w.d_qk_g[j], w.d_qk_b[j])
+                    dqkv3[:, j].copy_(ws["qk_tmp2"])
             if c.clip_qkv:
                 ws["dqkv"].mul_(lw["clipmask"])
             if w.d_bqkv is not None:

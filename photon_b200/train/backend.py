@@ -145,8 +145,6 @@ def build_backend(model_cfg: MPTConfig, device: torch.device, precision: str, ke
         unsupported = []
         if precision not in ("amp_bf16", "amp_fp8"):
             unsupported.append(f"precision={precision}")
-        if model_cfg.qk_ln:
-            unsupported.append("attn_config.qk_ln")
         if kw.get("frozen_layers") or kw.get("unfrozen_layers"):
             unsupported.append("frozen/unfrozen layers")
         if unsupported:

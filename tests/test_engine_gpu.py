@@ -153,15 +153,15 @@ def test_engine_d_head_128_runs_on_own_attention():
     assert cos > 0.995 and rel < 0.08, (cos, rel)
 
 
-@pytest.mark.parametrize("variant", ["alibi", "rope", "no_bias", "clip_qkv"])
+@pytest.mark.parametrize("variant", ["alibi", "rope", "no_bias", "clip_qkv", "qk_ln"])
 def test_engine_positional_variants_match_torch(variant):
-    """ALiBi / RoPE (no learned positions), no_bias and clip_qkv run on the engine's own kernels and match the PyTorch model."""
+    """ALiBi / RoPE (no learned positions), no_bias, clip_qkv and qk_ln run on the engine's own kernels and match the PyTorch model."""
     from photon_b200.models.engine import B200Engine
     from photon_b200.models.mpt import MPTConfig
     from photon_b200.train.backend import TorchBackend
 
     extra = {"alibi": dict(alibi=True, learned_pos_emb=False), "rope": dict(rope=True, learned_pos_emb=False),
-             "no_bias": dict(no_bias=True), "clip_qkv": dict(clip_qkv=0.5)}[variant]
+             "no_bias": dict(no_bias=True), "clip_qkv": dict(clip_qkv=0.5), "qk_ln": dict(qk_ln=True)}[variant]
     cfg = MPTConfig(d_model=256, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=2048, attn_impl="torch", **extra)
     dev = torch.device("cuda", 0)
     ref = TorchBackend(cfg, dev, "fp32", seed=3)
