@@ -299,7 +299,7 @@ pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
 void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& acc_ptrs,
                const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi, int64_t total,
                int kind, double avg_scale, double lr, double mu, double eta, double beta1, double beta2, double tau, int64_t round_t,
-               bool sign_compat) {
+               bool sign_compat, int64_t acc_mc, int64_t xg_mc) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::CommCtl c = make_ctl(ctl_ptrs, rank);
   pb::FedRoundArgs a{};
@@ -317,17 +317,20 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
   a.inv_bc1 = float(1.0 / (1.0 - std::pow(beta1, t)));
   a.inv_bc2 = float(1.0 / (1.0 - std::pow(beta2, t)));
   a.sign = sign_compat ? 1.0f : -1.0f;
+  a.acc_mc = reinterpret_cast<const float*>(acc_mc);   // NVLS multicast addresses (0 = P2P loops)
+  a.xg_mc = reinterpret_cast<float*>(xg_mc);
   pb::fed_round_launch(a, c, uint32_t(epoch), at::cuda::getCurrentDeviceProperties()->multiProcessorCount,
                        at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += 1;
 }
 void ddp_allreduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& buf_ptrs, int64_t lo,
-                   int64_t hi, c10::optional<Tensor> out_norm) {
+                   int64_t hi, c10::optional<Tensor> out_norm, int64_t buf_mc) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::CommCtl c = make_ctl(ctl_ptrs, rank);
   pb::AllReduceArgs a{};
   for (int i = 0; i < c.n; ++i) a.buf[i] = reinterpret_cast<float*>(buf_ptrs[i]);
   a.lo = lo, a.hi = hi;
+  a.buf_mc = reinterpret_cast<float*>(buf_mc);
   pb::ddp_allreduce_launch(a, c, uint32_t(epoch), out_norm.has_value() ? out_norm->data_ptr<float>() : nullptr,
                            at::cuda::getCurrentDeviceProperties()->multiProcessorCount, at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += out_norm.has_value() ? 2 : 1;
@@ -335,7 +338,8 @@ void ddp_allreduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, i
 void ddp_zero_step(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& grad_ptrs,
                    const std::vector<int64_t>& param_ptrs, const std::vector<int64_t>& shadow_ptrs, Tensor m, Tensor v, int64_t lo, int64_t hi,
                    int64_t kind, bool first_step, double lr, double beta1, double beta2, double eps, double decay, double clip,
-                   double step_size, double inv_sqrt_bc2, double max_norm, double grad_mult, c10::optional<Tensor> out_norm) {
+                   double step_size, double inv_sqrt_bc2, double max_norm, double grad_mult, c10::optional<Tensor> out_norm,
+                   int64_t grads_mc, int64_t params_mc, int64_t shadow_mc) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::CommCtl c = make_ctl(ctl_ptrs, rank);
   pb::ZeroStepArgs a{};
@@ -351,6 +355,9 @@ void ddp_zero_step(const std::vector<int64_t>& ctl_ptrs, int rank, int device, i
   a.h.lr = float(lr), a.h.beta1 = float(beta1), a.h.beta2 = float(beta2), a.h.eps = float(eps), a.h.decay = float(decay);
   a.h.clip = float(clip), a.h.step_size = float(step_size), a.h.inv_sqrt_bc2 = float(inv_sqrt_bc2);
   a.max_norm = float(max_norm), a.grad_mult = float(grad_mult);
+  a.grads_mc = reinterpret_cast<const float*>(grads_mc);
+  a.params_mc = reinterpret_cast<float*>(params_mc);
+  a.shadow_mc = shadow_ptrs.empty() ? nullptr : reinterpret_cast<void*>(shadow_mc);
   pb::ddp_zero_step_launch(a, c, uint32_t(epoch), out_norm.has_value() ? out_norm->data_ptr<float>() : nullptr,
                            at::cuda::getCurrentDeviceProperties()->multiProcessorCount, at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += 1;
@@ -394,9 +401,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ipc_free", &ipc_free);
   m.def("enable_peer_access", &enable_peer_access);
   m.def("tensor_from_ptr", &tensor_from_ptr);
-  m.def("fed_round", &fed_round);
-  m.def("ddp_allreduce", &ddp_allreduce);
-  m.def("ddp_zero_step", &ddp_zero_step);
+  m.def("fed_round", &fed_round, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("acc_ptrs"),
+        py::arg("xg_ptrs"), py::arg("xs_ptrs"), py::arg("m_ptr"), py::arg("v_ptr"), py::arg("lo"), py::arg("hi"), py::arg("total"),
+        py::arg("kind"), py::arg("avg_scale"), py::arg("lr"), py::arg("mu"), py::arg("eta"), py::arg("beta1"), py::arg("beta2"),
+        py::arg("tau"), py::arg("round_t"), py::arg("sign_compat"), py::arg("acc_mc") = 0, py::arg("xg_mc") = 0);
+  m.def("ddp_allreduce", &ddp_allreduce, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("buf_ptrs"),
+        py::arg("lo"), py::arg("hi"), py::arg("out_norm") = py::none(), py::arg("buf_mc") = 0);
+  m.def("ddp_zero_step", &ddp_zero_step, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("grad_ptrs"),
+        py::arg("param_ptrs"), py::arg("shadow_ptrs"), py::arg("m"), py::arg("v"), py::arg("lo"), py::arg("hi"), py::arg("kind"),
+        py::arg("first_step"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"), py::arg("eps"), py::arg("decay"), py::arg("clip"),
+        py::arg("step_size"), py::arg("inv_sqrt_bc2"), py::arg("max_norm"), py::arg("grad_mult"), py::arg("out_norm") = py::none(),
+        py::arg("grads_mc") = 0, py::arg("params_mc") = 0, py::arg("shadow_mc") = 0);
   m.def("set_wsum", &set_wsum);
   m.def("ctl_sums_word_offset", &pb::ctl_sums_word_offset);
   m.def("launch_count", &launch_count);

@@ -102,10 +102,14 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
   for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4 && !skip;
        i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.acc_mc) {   // NVLS: the switch adds the N weighted client sums, one load per element
+      acc = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + i);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
-      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
-      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
+        const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
+        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      }
     }
     float av[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
     const float4 X = reinterpret_cast<const float4*>(a.x)[i];
@@ -160,8 +164,12 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
     if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     // R2 (a): push the updated fp32 slice into every rank's global plane over NVLink
     const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    if (a.xg_mc) {    // NVLS: one multicast store lands in every rank's global plane
+      mm_st_f4(reinterpret_cast<float4*>(a.xg_mc) + i, nx);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
+      for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
+    }
   }
   // norm by-products (this rank's shard): block reduce -> fp64 atomics in the local control page
   __shared__ float red[5][16];
@@ -215,15 +223,23 @@ __global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs 
   const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
   for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.buf_mc) {
+      acc = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.buf_mc) + i);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) {
-      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.buf[p]) + i);
-      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      for (int p = 0; p < c.n; ++p) {
+        const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.buf[p]) + i);
+        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      }
     }
     acc.x *= inv, acc.y *= inv, acc.z *= inv, acc.w *= inv;
     sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    if (a.buf_mc) {
+      mm_st_f4(reinterpret_cast<float4*>(a.buf_mc) + i, acc);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.buf[p]) + i, acc);
+      for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.buf[p]) + i, acc);
+    }
   }
   __shared__ float red[16];
   sq = warp_sum(sq);
@@ -260,10 +276,14 @@ __global__ void __launch_bounds__(512) ddp_zero_step_kernel(const ZeroStepArgs a
   float* gmine = a.grads[c.rank];
   for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.grads_mc) {
+      acc = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.grads_mc) + i);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) {
-      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.grads[p]) + i);
-      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      for (int p = 0; p < c.n; ++p) {
+        const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.grads[p]) + i);
+        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      }
     }
     acc.x *= inv, acc.y *= inv, acc.z *= inv, acc.w *= inv;
     sq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
@@ -340,10 +360,15 @@ __global__ void __launch_bounds__(512) ddp_zero_step_kernel(const ZeroStepArgs a
     const float4 np = make_float4(pp[0], pp[1], pp[2], pp[3]);
     uint2 nb;
     nb.x = pack_bf16(pp[0], pp[1]), nb.y = pack_bf16(pp[2], pp[3]);
+    if (a.params_mc) {
+      mm_st_f4(reinterpret_cast<float4*>(a.params_mc) + i, np);
+      if (a.shadow_mc) mm_st_u2(reinterpret_cast<uint2*>(a.shadow_mc) + i, nb);
+    } else {
 #pragma unroll 1
-    for (int p = 0; p < c.n; ++p) {
-      st_peer_f4(reinterpret_cast<float4*>(a.params[p]) + i, np);
-      if (a.shadow[p]) st_peer_u2(reinterpret_cast<uint2*>(a.shadow[p]) + i, nb);
+      for (int p = 0; p < c.n; ++p) {
+        st_peer_f4(reinterpret_cast<float4*>(a.params[p]) + i, np);
+        if (a.shadow[p]) st_peer_u2(reinterpret_cast<uint2*>(a.shadow[p]) + i, nb);
+      }
     }
   }
   if (grid_done(c)) peer_barrier_end(c, epoch);

@@ -29,11 +29,14 @@ struct FedRoundArgs {
   float avg_scale;              // scaling_fn(K)
   float lr, mu;                 // fedavg / nesterov / fedmom
   float eta, beta1, beta2, tau, inv_bc1, inv_bc2, sign;  // adam / yogi (sign=-1 descent, +1 reference compat)
+  const float* acc_mc;          // NVLS: multicast address of the acc planes (in-switch reduction), or nullptr
+  float* xg_mc;                 // NVLS: multicast address of the fp32 global planes (one store reaches every GPU), or nullptr
 };
 
 struct AllReduceArgs {
   float* buf[MAX_PEERS];
   long long lo, hi;
+  float* buf_mc;                // NVLS multicast address of the gradient planes, or nullptr
 };
 
 // N1 + K11 + K12 in one launch (ZeRO-style): reduce-scatter of the gradient planes, global-norm clipping, the local
@@ -48,6 +51,9 @@ struct ZeroStepArgs {
   OptimHyper h;
   float max_norm;               // <= 0: no clipping
   float grad_mult;              // 1 / loss scale
+  const float* grads_mc;        // NVLS multicast addresses (nullptr = P2P loops)
+  float* params_mc;
+  void* shadow_mc;
 };
 
 void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);

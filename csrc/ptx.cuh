@@ -376,6 +376,22 @@ __device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
                : "memory");
   return r;
 }
+// NVLS (NVLink SHARP): `p` is an address in a MULTICAST mapping bound to the same buffer on every GPU of the group.
+// ld_reduce returns the element-wise sum over all GPUs, computed inside the NVSwitch; st writes all GPUs at once.
+__device__ __forceinline__ float4 mm_ld_reduce_add_f4(const float4* p) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void mm_st_f4(float4* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mm_st_u2(uint2* p, uint2 v) {   // 8 bytes of packed bf16, moved as two 32-bit lanes
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
 __device__ __forceinline__ void st_peer_f4(float4* p, float4 v) {
   asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");

@@ -37,7 +37,8 @@ class NvlGradComm:
         if g.data_ptr() != ar.ptrs("grads")[ar.rank]:
             raise ValueError("NvlGradComm reduces its own arena plane; build FlatParams with grads_storage=comm.grads")
         lo, hi = ar.shard(self.total)
-        ops.ext().ddp_allreduce(ar.ctl_ptrs(), ar.rank, ar.devices[0], ar.next_epoch(), ar.ptrs("grads"), lo, hi, self.norm)
+        ops.ext().ddp_allreduce(ar.ctl_ptrs(), ar.rank, ar.devices[0], ar.next_epoch(), ar.ptrs("grads"), lo, hi, self.norm,
+                                ar.mc_ptr("grads"))
         return g
 
     def last_grad_norm(self) -> torch.Tensor:
@@ -94,7 +95,8 @@ class NvlZeroComm:
         ops.ext().ddp_zero_step(ar.ctl_ptrs(), ar.rank, ar.devices[0], ar.next_epoch(), ar.ptrs("grads"), ar.ptrs("params"), shadow,
                                 opt.exp_avg, opt.exp_avg_sq, lo, hi, h["kind"], h["first"], h["lr"], h["beta1"], h["beta2"], h["eps"],
                                 h["decay"], h["clip"], h["step_size"], h["inv_sqrt_bc2"],
-                                float(max_norm) if max_norm is not None else -1.0, float(inv_scale), self.norm)
+                                float(max_norm) if max_norm is not None else -1.0, float(inv_scale), self.norm,
+                                ar.mc_ptr("grads"), ar.mc_ptr("params"), ar.mc_ptr("shadow"))
         opt.lr = float(lr)
         opt.step_count += 1
         return self.norm[0]

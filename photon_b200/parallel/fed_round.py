@@ -120,7 +120,8 @@ class NvlFedRound:
                           self._m[i].data_ptr() - 4 * lo if self._m[i] is not None else 0,
                           self._v[i].data_ptr() - 4 * lo if self._v[i] is not None else 0,
                           lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
-                          hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat))
+                          hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat),
+                          ar.mc_ptr("acc"), ar.mc_ptr("xg"))
 
     def round_norms(self, group: Any = None) -> dict[str, float]:
         """Global L2 norms from the kernel's per-shard Σx² by-products (tiny host read; off the hot path)."""

@@ -10,12 +10,20 @@ once (bootstrap only — no NCCL call ever touches the planes).  Two modes:
 * ``single``: one process driving several local GPUs with peer access enabled
   (unit tests, notebooks).
 
+When the box exposes NVLink SHARP (NVLS) the distributed arena is allocated through
+``torch.distributed._symmetric_memory`` instead of CUDA IPC: besides the per-peer pointers it then
+has a MULTICAST mapping (``mc_ptr``) on which the kernels use ``multimem.ld_reduce`` (the sum over
+all GPUs is formed inside the NVSwitch) and ``multimem.st`` (one store reaches every GPU).
+``PB_NVLS=0`` forces the IPC / P2P path.
+
 Replaces the reference's host-side hand-off stack (POSIX shm / Ray plasma / S3;
 ref: photon/server/s3_utils.py:730-1115, photon/shm/utils.py) on the GPU path.
 """
 from __future__ import annotations
 
 from typing import Any
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -50,6 +58,8 @@ class SymmArena:
             off = _round_up(off + int(numel) * _DT[dt][1], _ALIGN)
         self.nbytes = off
         self.epoch = 0
+        self.mc_base = 0            # base of the NVLS multicast mapping of the arena (0 = not available)
+        self._symm: Any = None
         self._opened: list[int] = []
         if self.single:
             for a in self.devices:
@@ -60,6 +70,9 @@ class SymmArena:
             self._owned = list(self.base)
         else:
             dv = self.devices[0]
+            if self.world_size > 1 and self._try_nvls(dv, group):
+                self._owned = []
+                return
             mine = self.ext.ipc_alloc(self.nbytes, dv)
             self._owned = [mine]
             if self.world_size == 1:
@@ -76,6 +89,40 @@ class SymmArena:
                         self._opened.append(ptr)
                         self.base.append(ptr)
                 dist.barrier(group=group)
+
+    def _try_nvls(self, dv: int, group: Any) -> bool:
+        """Allocate the arena as torch symmetric memory with a multicast mapping; all ranks agree on the outcome."""
+        ok, t, hdl = 0, None, None
+        if os.environ.get("PB_NVLS", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                pg = group if group is not None else dist.group.WORLD
+                t = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=torch.device("cuda", dv))
+                t.zero_()
+                torch.cuda.synchronize(dv)
+                hdl = symm_mem.rendezvous(t, group=pg.group_name)
+                ok = int(bool(getattr(hdl, "multicast_ptr", 0)) and len(hdl.buffer_ptrs) == self.world_size)
+            except Exception as e:  # noqa: BLE001 - any failure means "use the IPC path"
+                print(f"[symm] NVLS arena unavailable ({type(e).__name__}: {str(e)[:120]}); using CUDA IPC + P2P", flush=True)
+                ok = 0
+        flag = torch.tensor([ok], device=torch.device("cuda", dv))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            return False
+        self._symm = (t, hdl)
+        self.base = [int(p) for p in hdl.buffer_ptrs]
+        self.mc_base = int(hdl.multicast_ptr)
+        dist.barrier(group=group)
+        return True
+
+    def mc_ptr(self, name: str) -> int:
+        """Multicast address of a plane, or 0 = use the P2P loops: no NVLS mapping, or fewer than ``PB_NVLS_MIN_WORLD``
+        (default 4) GPUs — with 2 GPUs one peer read per element beats the switch round trip (0.96 vs 1.9 ms for the
+        125M-parameter round), from 4 GPUs on the N-fold P2P traffic loses."""
+        if not self.mc_base or self.world_size < int(os.environ.get("PB_NVLS_MIN_WORLD", "4")):
+            return 0
+        return self.mc_base + self.offsets[name][0]
 
     # ------------------------------------------------------------------ views / pointers
     def _dev(self, rank: int | None) -> int:
@@ -127,3 +174,4 @@ class SymmArena:
             except Exception:  # noqa: BLE001
                 pass
         self._opened, self._owned = [], []
+        self._symm = None
