@@ -99,76 +99,97 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
 
   float s_pg = 0.f, s_a = 0.f, s_x = 0.f, s_m = 0.f, s_v = 0.f;
   const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
-  for (long long i = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi4 && !skip;
-       i += (long long)gridDim.x * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.acc_mc) {   // NVLS: the switch adds the N weighted client sums, one load per element
-      acc = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + i);
-    } else {
+  // one element (float4) of the shard: pseudo-gradient, server optimizer, norm partials, broadcast
+  auto process = [&](long long i, float4 acc) {
+      float av[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+      const float4 X = reinterpret_cast<const float4*>(a.x)[i];
+      float xv[4] = {X.x, X.y, X.z, X.w};
+      float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
+      if (a.kind >= 1) {
+        const float4 Mv = reinterpret_cast<const float4*>(a.m)[i];
+        mv[0] = Mv.x, mv[1] = Mv.y, mv[2] = Mv.z, mv[3] = Mv.w;
+      }
+      if (a.kind >= 3) {
+        const float4 Vv = reinterpret_cast<const float4*>(a.v)[i];
+        vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float pg = xv[k] - av[k];
+        s_pg += pg * pg;
+        s_a += av[k] * av[k];
+        switch (a.kind) {
+          case 0:  // FedAvg
+            xv[k] -= a.lr * pg;
+            break;
+          case 1:  // Nesterov (torch SGD form)
+            mv[k] = a.mu * mv[k] + pg;
+            xv[k] -= a.lr * (pg + a.mu * mv[k]);
+            break;
+          case 2: {  // FedMom
+            const float vn = xv[k] - a.lr * pg;
+            xv[k] = (1.f + a.mu) * vn - a.mu * mv[k];
+            mv[k] = vn;
+            break;
+          }
+          default: {  // 3 FedAdam, 4 FedYogi
+            mv[k] = a.beta1 * mv[k] + (1.f - a.beta1) * pg;
+            const float g2 = pg * pg;
+            if (a.kind == 3) {
+              vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g2;
+            } else {
+              const float d = g2 - vv[k];
+              vv[k] += (1.f - a.beta2) * g2 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+            }
+            const float step = a.eta * (mv[k] * a.inv_bc1) / (sqrtf(vv[k] * a.inv_bc2) + a.tau);
+            xv[k] += a.sign * step;
+            break;
+          }
+        }
+        s_x += xv[k] * xv[k];
+        s_m += mv[k] * mv[k];
+        s_v += vv[k] * vv[k];
+      }
+      if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      // R2 (a): push the updated fp32 slice into every rank's global plane over NVLink
+      const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
+      if (a.xg_mc) {    // NVLS: one multicast store lands in every rank's global plane
+        mm_st_f4(reinterpret_cast<float4*>(a.xg_mc) + i, nx);
+      } else {
+#pragma unroll 1
+        for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
+      }
+  };
+  const long long gs = (long long)gridDim.x * blockDim.x;
+  const long long i0 = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (!skip && a.acc_mc) {
+    // NVLS: the switch adds the N weighted client sums (one multimem.ld_reduce per element). The round trip through the
+    // switch is long, so four reductions per thread are kept in flight ahead of the arithmetic.
+    float4 pre[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * gs < hi4) pre[u] = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + i0 + u * gs);
+    for (long long i = i0; i < hi4; i += 4 * gs) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long idx = i + u * gs;
+        if (idx < hi4) {
+          const float4 acc = pre[u];
+          if (idx + 4 * gs < hi4) pre[u] = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + idx + 4 * gs);
+          process(idx, acc);
+        }
+      }
+    }
+  } else if (!skip) {
+    for (long long i = i0; i < hi4; i += gs) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
       for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
         const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
         acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
       }
-    }
-    float av[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
-    const float4 X = reinterpret_cast<const float4*>(a.x)[i];
-    float xv[4] = {X.x, X.y, X.z, X.w};
-    float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
-    if (a.kind >= 1) {
-      const float4 Mv = reinterpret_cast<const float4*>(a.m)[i];
-      mv[0] = Mv.x, mv[1] = Mv.y, mv[2] = Mv.z, mv[3] = Mv.w;
-    }
-    if (a.kind >= 3) {
-      const float4 Vv = reinterpret_cast<const float4*>(a.v)[i];
-      vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float pg = xv[k] - av[k];
-      s_pg += pg * pg;
-      s_a += av[k] * av[k];
-      switch (a.kind) {
-        case 0:  // FedAvg
-          xv[k] -= a.lr * pg;
-          break;
-        case 1:  // Nesterov (torch SGD form)
-          mv[k] = a.mu * mv[k] + pg;
-          xv[k] -= a.lr * (pg + a.mu * mv[k]);
-          break;
-        case 2: {  // FedMom
-          const float vn = xv[k] - a.lr * pg;
-          xv[k] = (1.f + a.mu) * vn - a.mu * mv[k];
-          mv[k] = vn;
-          break;
-        }
-        default: {  // 3 FedAdam, 4 FedYogi
-          mv[k] = a.beta1 * mv[k] + (1.f - a.beta1) * pg;
-          const float g2 = pg * pg;
-          if (a.kind == 3) {
-            vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g2;
-          } else {
-            const float d = g2 - vv[k];
-            vv[k] += (1.f - a.beta2) * g2 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-          }
-          const float step = a.eta * (mv[k] * a.inv_bc1) / (sqrtf(vv[k] * a.inv_bc2) + a.tau);
-          xv[k] += a.sign * step;
-          break;
-        }
-      }
-      s_x += xv[k] * xv[k];
-      s_m += mv[k] * mv[k];
-      s_v += vv[k] * vv[k];
-    }
-    if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
-    if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    // R2 (a): push the updated fp32 slice into every rank's global plane over NVLink
-    const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
-    if (a.xg_mc) {    // NVLS: one multicast store lands in every rank's global plane
-      mm_st_f4(reinterpret_cast<float4*>(a.xg_mc) + i, nx);
-    } else {
-#pragma unroll 1
-      for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
+      process(i, acc);
     }
   }
   // norm by-products (this rank's shard): block reduce -> fp64 atomics in the local control page

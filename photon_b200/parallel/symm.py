@@ -60,6 +60,7 @@ class SymmArena:
         self.epoch = 0
         self.mc_base = 0            # base of the NVLS multicast mapping of the arena (0 = not available)
         self._symm: Any = None
+        self._group: Any = None
         self._opened: list[int] = []
         if self.single:
             for a in self.devices:
@@ -111,6 +112,7 @@ class SymmArena:
         if int(flag.item()) != 1:
             return False
         self._symm = (t, hdl)
+        self._group = group
         self.base = [int(p) for p in hdl.buffer_ptrs]
         self.mc_base = int(hdl.multicast_ptr)
         dist.barrier(group=group)
@@ -163,6 +165,15 @@ class SymmArena:
         return lo, min(total, lo + per)
 
     def close(self) -> None:
+        if self._symm is not None:
+            # symmetric-memory arenas are not reference counted across ranks: nobody may free while a peer's kernel can still
+            # touch this rank's pages (flag polling in the end barrier, multicast stores) -> collective teardown
+            try:
+                torch.cuda.synchronize(self.devices[0])
+                if dist.is_initialized():
+                    dist.barrier(group=self._group)
+            except Exception:  # noqa: BLE001 - process group already gone at interpreter exit
+                pass
         for p in self._opened:
             try:
                 self.ext.ipc_close(p)

@@ -18,7 +18,7 @@ TINY = ["llm_config.model.d_model=256", "llm_config.model.n_heads=4", "llm_confi
         "fl.eval_period=null", "photon.resume_round=null"]
 
 
-def _torchrun(tmp_path, n, body, port):
+def _torchrun(tmp_path, n, body, port, env=None):
     if torch.cuda.device_count() < n:
         pytest.skip(f"needs >= {n} GPUs")
     script = tmp_path / "run.py"
@@ -28,7 +28,7 @@ def _torchrun(tmp_path, n, body, port):
                       f"TINY = {TINY!r}\n" + textwrap.dedent(body) + "\ndist.barrier(); dist.destroy_process_group()\n")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                           "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900,
-                         env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1", **(env or {})))
     assert out.returncode == 0 and "RESULT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-4000:]
 
 
@@ -85,3 +85,39 @@ def test_spmd_federation_nvl_and_two_gpus_per_client(tmp_path):
         assert torch.isfinite(finals['nvl2']).all()
         if rank == 0: print('RESULT_OK', rel)
     """, 29543)
+
+
+def test_nvls_multimem_paths_match_p2p(tmp_path):
+    """NVLS (multimem.ld_reduce / multimem.st on the multicast mapping of the arena) against the P2P loops of the same
+    kernels: federated round (FedAdam) and the fused ZeRO step. Skips itself when the box has no multicast support."""
+    _torchrun(tmp_path, 2, """
+        import os
+        from photon_b200.config import compose
+        from photon_b200.federation import FederationRuntime
+        from photon_b200.server_app import run_server
+        from photon_b200.centralised_train import run_centralised
+        rank = dist.get_rank(); dev = torch.device('cuda', rank)
+        res = {}
+        for mode in ('nvls', 'p2p'):
+            os.environ['PB_NVLS'] = '1' if mode == 'nvls' else '0'
+            cfg = compose(TINY + ['run_uuid=nv-' + mode, 'fl.n_total_clients=4', 'fl.n_clients_per_round=4', 'fl.n_rounds=2',
+                                  'fl.strategy_name=fedadam', 'fl.strategy_kwargs={eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}',
+                                  'dataset.train.root_local=synthetic://c', 'photon.comm_stack.shm=false', 'photon.comm_stack.nvl=true'])
+            rt = FederationRuntime(cfg, device=dev, rank=rank, world_size=2)
+            run_server(cfg, runtime=rt)
+            res[mode] = (rt.round_backend.global_params().clone(), bool(rt.round_backend.fed.arena.mc_ptr('acc')))
+            rt.close()
+            cfg = compose(TINY + ['run_uuid=nvz-' + mode, 'dataset/streams@dataset.train.streams=centralised', 'dataset.train.root_local=synthetic://7'])
+            tr = run_centralised(cfg, device=dev, rank=rank, world_size=2, duration='3ba', use_nvl_allreduce=True)
+            res['z' + mode] = (tr.state.flat.params.clone(), bool(tr.grad_comm.arena.mc_ptr('grads')))
+            tr.close()
+        if not res['nvls'][1]:
+            if rank == 0: print('RESULT_OK (no multicast on this box: nothing to compare)')
+        else:
+            assert res['znvls'][1] and not res['p2p'][1] and not res['zp2p'][1]
+            for a, b in (('nvls', 'p2p'), ('znvls', 'zp2p')):
+                rel = ((res[a][0] - res[b][0]).norm() / res[b][0].norm()).item()
+                # the switch adds the ranks in its own order: 1-ulp differences in the mean, amplified by the Adam-type steps
+                assert rel < 2e-3, (a, rel)
+            if rank == 0: print('RESULT_OK nvls == p2p')
+    """, 29545, env={"PB_NVLS_MIN_WORLD": "2"})
