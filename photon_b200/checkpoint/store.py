@@ -25,7 +25,6 @@ from typing import Any, Sequence
 import numpy as np
 import torch
 
-from photon_b200.strategy.constants import MOMENTUM_KEY, SECOND_MOMENTUM_KEY, SERVER_PARAMETERS_KEY
 from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file
 from photon_b200.utils.flat import FlatLayout
 

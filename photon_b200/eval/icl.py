@@ -16,7 +16,6 @@ loops that are out of scope of the training engine.  Datasets are jsonl files re
 from __future__ import annotations
 
 import json
-import math
 from pathlib import Path
 from typing import Any, Callable
 

@@ -17,7 +17,6 @@ import time
 from pathlib import Path
 from typing import Any
 
-import torch
 import torch.distributed as dist
 
 from photon_b200.checkpoint.store import CheckpointStore
