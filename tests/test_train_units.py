@@ -232,3 +232,15 @@ def test_profiler_callback_exports_chrome_traces(tmp_path):
     traces = list((tmp_path / "traces").glob("rank0.*.pt.trace.json"))
     assert len(traces) == 1 and traces[0].stat().st_size > 1000
     tr.close()
+
+
+def test_fsdp_config_selects_the_sharded_step():
+    """fsdp_config (YAML default) → fused ZeRO step / sharded optimizer; NO_SHARD or a deleted node → plain DDP."""
+    from photon_b200.config import compose
+    from photon_b200.parallel.ddp import wants_sharded_step
+
+    cfg = compose(["run_uuid=t"])
+    assert wants_sharded_step(cfg["llm_config"])                               # shipped YAML: FSDP FULL_SHARD
+    assert not wants_sharded_step(compose(["run_uuid=t", "~llm_config.fsdp_config"])["llm_config"])
+    assert not wants_sharded_step(compose(["run_uuid=t", "llm_config.fsdp_config.sharding_strategy=NO_SHARD"])["llm_config"])
+    assert wants_sharded_step(compose(["run_uuid=t", "llm_config.fsdp_config.sharding_strategy=SHARD_GRAD_OP"])["llm_config"])
