@@ -85,5 +85,10 @@ def ptxas_report() -> str:
     return "\n".join(p.read_text() for p in sorted(OBJ.glob("*.log")))
 
 
-if __name__ == "__main__":
+def main() -> None:
+    """Console entry point (``photon-build-kernels [--force]``)."""
     build(force="--force" in sys.argv)
+
+
+if __name__ == "__main__":
+    main()
