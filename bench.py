@@ -52,7 +52,8 @@ def reference_arm() -> None:
             import photon.server_app  # noqa: F401  (would need flwr)
         except Exception as e:  # noqa: BLE001
             why = f"baseline/_ref present but not importable: {type(e).__name__}: {e}"
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:   # one line per job, also under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
 class ClockSampler:
