@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from photon_b200.config import compose
+from conftest import free_port as _free_port  # noqa: E402
 
 TINY = ["llm_config.model.d_model=32", "llm_config.model.n_heads=2", "llm_config.model.n_layers=1", "llm_config.max_seq_len=16",
         "llm_config.global_train_batch_size=4", "llm_config.device_train_microbatch_size=2", "llm_config.device_eval_batch_size=4",
@@ -152,5 +153,5 @@ def test_two_rank_gloo_federation(tmp_path):
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600, env=env)
+                          "--master-port", str(_free_port()), str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -8,6 +8,7 @@ from pathlib import Path
 
 import pytest
 import torch
+from conftest import free_port as _free_port  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -27,7 +28,7 @@ def _torchrun(tmp_path, n, body, port, env=None):
                       "dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))\n"
                       f"TINY = {TINY!r}\n" + textwrap.dedent(body) + "\ndist.barrier(); dist.destroy_process_group()\n")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900,
+                          "--master-port", str(_free_port() if port else port), str(script)], capture_output=True, text=True, timeout=900,
                          env=dict(os.environ, MASTER_ADDR="127.0.0.1", **(env or {})))
     assert out.returncode == 0 and "RESULT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-4000:]
 

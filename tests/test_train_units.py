@@ -13,6 +13,7 @@ from photon_b200.train.optim import ADOPT, DecoupledAdamW, build_optimizer, clip
 from photon_b200.train.schedulers import build_scheduler
 from photon_b200.train.timestamp import Time, Timestamp
 from photon_b200.utils.flat import FlatLayout, FlatParams
+from conftest import free_port as _free_port  # noqa: E402
 
 
 def test_time_strings():
@@ -205,7 +206,7 @@ def test_sharded_optimizer_state_matches_replicated(tmp_path):
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29547", str(script)], capture_output=True, text=True, timeout=600, env=env)
+                          "--master-port", str(_free_port()), str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
