@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from photon_b200.clients import llm_config_functions as lcf
+from photon_b200.data.synthetic import TOKENIZER_VOCAB
 from photon_b200.data.streaming import build_text_loader
 from photon_b200.metrics.language import unigram_log_probs
 from photon_b200.models.mpt import MPTConfig
@@ -109,9 +110,10 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
             uni = unigram_log_probs(freq, mcfg.vocab_size)
         elif not allow_unigram_metrics_failures:
             raise RuntimeError("unigram metrics requested but no 1_gram.json found")
-    train_loader = None if no_data else build_text_loader(t["train_loader"], gbs // world_size, rank, world_size, seed)
+    syn_vocab = min(int(mcfg.vocab_size), TOKENIZER_VOCAB)   # synthetic streams stay inside the model's embedding table
+    train_loader = None if no_data else build_text_loader(t["train_loader"], gbs // world_size, rank, world_size, seed, syn_vocab)
     eval_bs = int(t.get("device_eval_batch_size", 1))
-    eval_loaders = {} if no_data else {lbl: build_text_loader(lc, eval_bs, rank, world_size, seed + 1) for lbl, lc in evals.items()}
+    eval_loaders = {} if no_data else {lbl: build_text_loader(lc, eval_bs, rank, world_size, seed + 1, syn_vocab) for lbl, lc in evals.items()}
     save_root = t.get("save_folder") or "."
     interval = t.get("console_log_interval", "1ba")
     loggers = build_loggers(t.get("loggers"), Path(str(save_root)).parent if t.get("save_folder") else ".", str(t["run_name"]),
@@ -145,8 +147,9 @@ def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, lo
     """Swap the per-client mutables on a live Trainer (loaders, save folder, run name, clocks)."""
     t, evals = _prepare_train_cfg(cfg, cid, split_eval, trainer.world_size, log_name)
     seed = int(t.get("seed", 17))
-    trainer.train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed)
-    trainer.eval_loaders = {lbl: build_text_loader(lc, trainer.device_eval_batch_size, trainer.rank, trainer.world_size, seed + 1)
+    syn_vocab = min(int(trainer.model_cfg.vocab_size), TOKENIZER_VOCAB)
+    trainer.train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed, syn_vocab)
+    trainer.eval_loaders = {lbl: build_text_loader(lc, trainer.device_eval_batch_size, trainer.rank, trainer.world_size, seed + 1, syn_vocab)
                             for lbl, lc in evals.items()}
     trainer._train_iter = None  # noqa: SLF001
     trainer.save_folder = t.get("save_folder")

@@ -53,7 +53,8 @@ class Stream:
         return p / self.split if self.split else p
 
 
-def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: int, allow_synthetic: bool) -> Any:
+def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: int, allow_synthetic: bool,
+                 synth_vocab: int | None = None) -> Any:
     d = st.directory()
     if d is not None and (d / INDEX_NAME).exists():
         return ShardReader(d, validate_hash=bool(st.validate_hash))
@@ -66,7 +67,8 @@ def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: i
     elif st.local:
         digits = "".join(ch for ch in Path(str(st.local)).name if ch.isdigit())
         sid = int(digits) if digits else idx
-    return SyntheticC4(seq_len=seq_len, seed=seed, stream_id=sid, num_samples=synth_samples)
+    kw = {"vocab_size": int(synth_vocab)} if synth_vocab else {}   # never emit ids the (possibly resized) model cannot embed
+    return SyntheticC4(seq_len=seq_len, seed=seed, stream_id=sid, num_samples=synth_samples, **kw)
 
 
 class StreamingTokenDataset:
@@ -81,14 +83,14 @@ class StreamingTokenDataset:
     def __init__(self, streams: Sequence[Stream | dict[str, Any]], seq_len: int = 2048, *, shuffle: bool = False,
                  shuffle_seed: int = 9176, epoch_size: int | None = None, rank: int = 0, world_size: int = 1,
                  synthetic_samples: int = 1 << 16, synthetic_seed: int = 17, allow_synthetic: bool = True,
-                 **_unused: Any) -> None:
+                 synthetic_vocab: int | None = None, **_unused: Any) -> None:
         self.streams = [s if isinstance(s, Stream) else Stream(**{k: v for k, v in s.items() if k in Stream.__annotations__})
                         for s in streams]
         if not self.streams:
             raise ValueError("need at least one stream")
         self.seq_len, self.shuffle, self.shuffle_seed = int(seq_len), bool(shuffle), int(shuffle_seed)
         self.rank, self.world_size, self.epoch_size = int(rank), int(world_size), epoch_size
-        self._sources = [_open_stream(s, self.seq_len, i, synthetic_samples, synthetic_seed, allow_synthetic)
+        self._sources = [_open_stream(s, self.seq_len, i, synthetic_samples, synthetic_seed, allow_synthetic, synthetic_vocab)
                          for i, s in enumerate(self.streams)]
         for src in self._sources:
             if getattr(src, "seq_len", self.seq_len) != self.seq_len:
@@ -230,7 +232,7 @@ class TokenLoader:
 
 
 def build_text_loader(loader_cfg: dict[str, Any], batch_size: int, rank: int = 0, world_size: int = 1,
-                      seed: int = 17) -> TokenLoader:
+                      seed: int = 17, vocab_size: int | None = None) -> TokenLoader:
     """``loader_cfg`` = ``llm_config.train_loader`` / ``eval_loader`` after the client-side
     stream surgery has replaced ``dataset.streams`` with a flat ``{name: Stream-dict}`` map
     (ref: photon/clients/llm_config_functions.py:239-529)."""
@@ -257,6 +259,7 @@ def build_text_loader(loader_cfg: dict[str, Any], batch_size: int, rank: int = 0
                                shuffle=bool(ds_cfg.pop("shuffle", False)),
                                shuffle_seed=int(ds_cfg.pop("shuffle_seed", 9176) or 9176),
                                epoch_size=ds_cfg.pop("epoch_size", None), rank=rank, world_size=world_size,
-                               synthetic_seed=seed, **{k: v for k, v in ds_cfg.items() if k in ("synthetic_samples", "allow_synthetic")})
+                               synthetic_seed=seed, synthetic_vocab=vocab_size,
+                               **{k: v for k, v in ds_cfg.items() if k in ("synthetic_samples", "allow_synthetic")})
     return TokenLoader(ds, batch_size=batch_size, drop_last=bool(loader_cfg.get("drop_last", True)),
                        num_workers=0 if nw in (None, "auto") else min(int(nw), 1))

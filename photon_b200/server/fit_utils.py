@@ -58,6 +58,8 @@ def fit_round(runtime: Any, server_round: int, sampled_clients: list[int]) -> di
     results = runtime.run_clients_fit(server_round, sampled_clients)
     all_results = runtime.gather_results(results)
     ok, failed = split_results(all_results)
+    for r in failed:   # say WHY before deciding whether the round survives (the reference only counts)
+        print(f"[server] round {server_round}: client {getattr(r, 'cid', '?')} failed: {r.status.message}", flush=True)
     ignore = check_failures(len(failed), int(runtime.cfg["fl"]["accept_failures_cnt"]), bool(runtime.cfg["fl"]["ignore_failed_rounds"]))
     if ignore or not ok:
         runtime.abort_round()
