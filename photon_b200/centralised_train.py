@@ -19,7 +19,7 @@ from photon_b200.clients.configs import CentralizedConfig
 from photon_b200.clients.trainer_utils import get_trainer_object, initialize_dist, pick_device
 from photon_b200.config import load_config
 from photon_b200.train.trainer import Trainer
-from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file
+from photon_b200.utils.core import dump_model_parameters_to_file, load_model_parameters_from_file, set_wte_parameters_to_trainer
 
 
 def _centralized_config(cfg: Any) -> CentralizedConfig:
@@ -33,12 +33,7 @@ def _centralized_config(cfg: Any) -> CentralizedConfig:
 
 def set_wte_parameters(trainer: Trainer, wte: np.ndarray) -> None:
     """Transplant only the token embedding (ref: photon/utils.py:585-599)."""
-    st = trainer.state
-    view = st.flat.layout.view(st.flat.params, "transformer.wte.weight")
-    if tuple(view.shape) != tuple(wte.shape):
-        raise ValueError(f"wte shape {wte.shape} != model {tuple(view.shape)}")
-    view.copy_(torch.from_numpy(np.asarray(wte, dtype=np.float32)).to(view.device))
-    st.backend.params_updated()
+    set_wte_parameters_to_trainer(trainer, wte)
 
 
 def dump_checkpoint_npz(trainer: Trainer, run_uuid: str, out_dir: str | Path = ".") -> Path:

@@ -16,11 +16,10 @@ from typing import Any
 
 import torch
 
-from photon_b200.clients import llm_config_functions as lcf
 from photon_b200.clients.configs import EvaluateConfig, FitConfig
 from photon_b200.clients.trainer_utils import get_trainer_object, load_trainer_checkpoint, reconfigure_trainer
 from photon_b200.clients.utils import (Payload, load_ignore_keys, manipulate_pre_training_params, payload_to_planes,
-                                       post_process_client_result)
+                                       post_process_client_result, set_initial_config_from_fit_config)
 from photon_b200.train.timestamp import Time
 from photon_b200.train.trainer import Trainer
 
@@ -51,13 +50,8 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
     else:
         train_cfg = reconfigure_trainer(trainer, cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval)
     # ---- per-client checkpoint policy: resume mid-round or skip an already finished round
-    skip_iteration, load_set = (False, False)
-    if not fc.reset_checkpoint:
-        skip_iteration, load_set = lcf.set_client_load_path(train_cfg, cid, server_steps + local_steps)
-        trainer.save_folder = train_cfg.get("save_folder")
-    else:
-        lcf.set_client_save_and_load_path(train_cfg, cid)
-        trainer.save_folder = train_cfg.get("save_folder")
+    skip_iteration, load_set, _ = set_initial_config_from_fit_config(fc, train_cfg, cid)
+    trainer.save_folder = train_cfg.get("save_folder")
     metrics["client/fit_init_time"] = _now() - t_start
 
     # ---- install the round's parameters (+ momenta / personalised / re-initialised layers)

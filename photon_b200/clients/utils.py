@@ -42,6 +42,34 @@ def load_ignore_keys(fit_config: FitConfig) -> list[str]:
     return keys
 
 
+def set_initial_config_from_fit_config(fit_config: FitConfig, llm_config: Any, cid: int | str | None
+                                       ) -> tuple[bool, bool, int | None]:
+    """Per-round, per-client config surgery before the trainer is (re)configured
+    (ref: clients/utils.py:177-254): choose the save folder / resume checkpoint (or decide the round was
+    already done), set the load/save ignore globs, apply ``resize_vocab``.
+
+    Returns ``(skip_iteration, checkpoint_exists, server_steps_cumulative)``."""
+    from photon_b200.clients import llm_config_functions as lcf
+    from photon_b200.train.timestamp import Time
+
+    local_steps = Time.parse(llm_config.get("local_steps", "1ba")).to_batches()
+    server_steps = fit_config.server_steps_cumulative
+    skip_iteration = checkpoint_exists = False
+    if not fit_config.reset_checkpoint:
+        if server_steps is None:
+            raise ValueError("Server steps cumulative is None and we want to reset a checkpoint.")
+        skip_iteration, checkpoint_exists = lcf.set_client_load_path(llm_config, cid, int(server_steps) + local_steps)
+    else:
+        lcf.set_client_save_and_load_path(llm_config, cid)
+    llm_config["load_ignore_keys"] = load_ignore_keys(fit_config)
+    if fit_config.reset_optimizer:
+        llm_config["save_ignore_keys"] = ["*optim*"]
+    model = llm_config.get("model")
+    if model is not None and "vocab_size" in model and fit_config.resize_vocab is not None:
+        model["vocab_size"] = int(fit_config.resize_vocab)
+    return skip_iteration, checkpoint_exists, server_steps
+
+
 # ------------------------------------------------------------------------ payload codecs
 def payload_to_planes(payload: Payload, layout: FlatLayout, device: torch.device, n_planes: int) -> list[torch.Tensor]:
     """→ ``n_planes`` flat fp32 tensors on ``device`` in ``layout`` order."""
@@ -137,6 +165,15 @@ def manipulate_pre_training_params(trainer: Trainer, payload: Payload, fit_confi
         randomize_layers(params, lay, trainer.model_cfg, rl, server_round=fit_config.server_round, cid=cid,
                          truly_random=fit_config.truly_random_init, base_seed=trainer.seed)
     return params, metrics
+
+
+def manipulate_pre_training_ndarrays(parameters: Sequence[np.ndarray], trainer: Trainer, fit_config: FitConfig,
+                                     client_state: ClientState, cid: int = 0) -> list[np.ndarray]:
+    """The reference's ndarray-in / ndarray-out form of ``manipulate_pre_training_params``
+    (ref: clients/utils.py:405-511): momenta are split off and installed into the optimizer, personalised /
+    randomly re-initialised layers are patched, and only the model's arrays come back."""
+    params, _ = manipulate_pre_training_params(trainer, list(parameters), fit_config, cid, client_state)
+    return trainer.state.flat.layout.to_ndarrays(params)
 
 
 # ------------------------------------------------------------------------- post-processing

@@ -108,6 +108,24 @@ UNIGRAM_METRIC_NAMES_AND_CLASSES = {
 BASE_METRICS = {c.name: c for c in (LanguageCrossEntropy, LanguagePerplexity, TokenAccuracy)}
 
 
+def create_wrapped_subclass(base_class: type, **kwargs: Any) -> type:
+    """A same-named subclass of ``base_class`` whose constructor has ``kwargs`` pre-bound, so a metric that needs
+    arguments (e.g. a custom unigram table) can sit in a name → class registry that instantiates with no arguments
+    (ref: photon/metrics/unigram_normalized_metrics.py:233-256). Call-time kwargs override the bound ones."""
+    def __init__(self: Any, **init_kwargs: Any) -> None:
+        base_class.__init__(self, **{**kwargs, **init_kwargs})
+
+    return type(base_class.__name__, (base_class,), {"__init__": __init__, "__module__": base_class.__module__,
+                                                    "__doc__": base_class.__doc__})
+
+
+def register_metric(cls: type, *, unigram: bool = False, **bound_kwargs: Any) -> type:
+    """Add a ``Metric`` subclass to the registry ``build_metrics`` instantiates from."""
+    wrapped = create_wrapped_subclass(cls, **bound_kwargs) if bound_kwargs else cls
+    (UNIGRAM_METRIC_NAMES_AND_CLASSES if unigram else BASE_METRICS)[getattr(cls, "name", cls.__name__)] = wrapped
+    return wrapped
+
+
 def build_metrics(use_unigram: bool = False) -> dict[str, Metric]:
     out = {n: c() for n, c in BASE_METRICS.items()}
     if use_unigram:

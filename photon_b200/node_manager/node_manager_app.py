@@ -128,12 +128,17 @@ class NodeManagerApp:
             self.close_workers()   # soft close then terminate; next attempt respawns (ref: node_manager_app.py:553-579)
         return None, err
 
+    def collaborative_fit(self, cid: int, task_cfg: dict[str, Any]) -> tuple[Any, str | None]:
+        """ALL workers of the node train ONE client together (one DDP / ZeRO group); on failure the client is
+        re-queued after the pool is torn down and respawned (ref: node_manager_app.py:405-592)."""
+        return self._with_retries(int(cid), "fit", task_cfg)
+
     def fit(self, configs: dict[int, dict[str, Any]]) -> list[FitRes]:
         """``configs``: cid → {"fit_config": wire dict, ...}. Clients run sequentially."""
         t0 = time.time()
         out: list[FitRes] = []
         for cid, task_cfg in configs.items():
-            msg, err = self._with_retries(int(cid), "fit", task_cfg)
+            msg, err = self.collaborative_fit(int(cid), task_cfg)
             if msg is None:
                 out.append(FitRes(Status(Code.FAILED, err or "failed"), None, 0, {}, int(cid)))
                 continue

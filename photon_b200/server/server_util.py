@@ -86,3 +86,6 @@ def fit_or_evaluate_ins(kind: str, server_round: int, client_ids: list[int], cli
     msg = Message(kind=kind, content=content, group_id=str(server_round))
     msg.per_client = {int(c): v for c, v in per_client_config.items()}  # type: ignore[attr-defined]
     return msg
+
+
+fit_or_evaluate_ins_recordset = fit_or_evaluate_ins  # reference name (ref: server_util.py:205-302); no RecordSet here

@@ -50,6 +50,36 @@ def aggregate_inplace(results: Iterable[tuple[torch.Tensor, float]],
     return sm.result(), sm.total, sm.count
 
 
+def aggregate_parameters(acc: torch.Tensor | None, cur: torch.Tensor, n_prev: float, n_cur: float) -> tuple[torch.Tensor, float]:
+    """One step of the running mean, functional form: ``acc ← acc·N_prev/N_new + cur·n/N_new``
+    (ref: photon/strategy/aggregation.py:19-87). ``acc`` is updated in place when given."""
+    if n_cur <= 0:
+        raise ValueError("client weight (num_examples) must be positive")
+    if acc is None:
+        return cur.detach().to(torch.float32).clone(), float(n_cur)
+    n_new = float(n_prev) + float(n_cur)
+    acc.mul_(float(n_prev) / n_new).add_(cur.to(acc.device, torch.float32), alpha=float(n_cur) / n_new)
+    return acc, n_new
+
+
+def aggregate_cumulative_average(fit_results: Iterable[Any], metrics_callback: Any = None) -> torch.Tensor | None:
+    """Lazy in-place weighted average over ``FitRes``-like objects (``.parameters`` flat tensor, ``.num_examples``);
+    only one client payload is alive at a time (ref: aggregation.py:121-150)."""
+    hook = None
+    if metrics_callback is not None:
+        hook = lambda flat, n: metrics_callback.per_client(flat, n)  # noqa: E731
+    mean, _, _ = aggregate_inplace(((r.parameters, r.num_examples) for r in fit_results), per_client_hook=hook)
+    return mean
+
+
+def parameters_to_ndarrays_gen(flat: torch.Tensor, layout: Any) -> Any:
+    """Yield one per-tensor ndarray VIEW at a time from a flat payload — the lazy per-layer decode of
+    ref aggregation.py:153-169, without the ``np.load`` of serialized bytes (payloads are never serialized here)."""
+    host = flat.detach().cpu() if flat.is_cuda else flat.detach()
+    for off, ne, shp in zip(layout.offsets, layout.numels, layout.shapes):
+        yield host[off:off + ne].view(shp).numpy()
+
+
 def naive_weighted_mean(results: list[tuple[torch.Tensor, float]]) -> torch.Tensor:
     """Textbook Σ n_k x_k / Σ n_k in float64 — the oracle for ``track_inplace_aggregation``
     (ref: photon/strategy/fedavg_eff.py:366-391 ``server/l2_norm_fedavg_gap``)."""

@@ -55,6 +55,79 @@ def parameters_checker(a: Sequence[np.ndarray], b: Sequence[np.ndarray], *, expe
         raise AssertionError(f"{what}: parameters are identical but were expected to change")
 
 
+# ------------------------------------------------------------ parameter get / set on a live trainer
+def _flat_of(trainer: Any) -> Any:
+    st = getattr(trainer, "state", trainer)
+    flat = getattr(st, "flat", None)
+    if flat is None:
+        raise TypeError("expected a photon_b200 Trainer (or its state) holding flat parameter storage")
+    return flat
+
+
+def get_trainable_params_dict(model_or_trainer: Any, *, sort_dict: bool = True,
+                              no_detach_and_clone: bool = False) -> dict[str, torch.Tensor]:
+    """name → tensor for every trainable parameter (ref: photon/utils.py:247-319).
+
+    The reference needs an FSDP ``summon_full_params`` + CPU offload here; our masters live in one flat
+    buffer that every rank holds in full, so this is a dictionary of views (``no_detach_and_clone``)
+    or of clones, already in sorted-name order.  A plain ``nn.Module`` is accepted too."""
+    if isinstance(model_or_trainer, torch.nn.Module):
+        items = [(clean_parameter_name(n), p) for n, p in model_or_trainer.named_parameters() if p.requires_grad]
+        if sort_dict:
+            items.sort(key=lambda kv: kv[0])
+        return {n: (p if no_detach_and_clone else p.detach().clone()) for n, p in items}
+    flat = _flat_of(model_or_trainer)
+    views = flat.layout.views(flat.params)
+    return {n: (v if no_detach_and_clone else v.detach().clone()) for n, v in zip(flat.layout.names, views)}
+
+
+def get_parameters_from_state(_config: Any, trainer: Any) -> list[np.ndarray]:
+    """The model as the reference's payload: one fp32 ndarray per tensor, sorted by name (ref: :227-244)."""
+    return _flat_of(trainer).to_ndarrays()
+
+
+def set_trainer_trainable_params_dict(trainer: Any, params: dict[str, Any]) -> None:
+    """Overwrite the named tensors (a subset is fine) and refresh the bf16 compute copy
+    (ref: photon/utils.py:390-478 — there a pickled rank-0 broadcast under FSDP)."""
+    flat = _flat_of(trainer)
+    with torch.no_grad():
+        for name, value in params.items():
+            view = flat.layout.view(flat.params, clean_parameter_name(name))
+            t = torch.as_tensor(value)
+            if tuple(t.shape) != tuple(view.shape):
+                raise ValueError(f"{name}: shape {tuple(t.shape)} != model {tuple(view.shape)}")
+            view.copy_(t.to(view.device, view.dtype))
+    backend = getattr(getattr(trainer, "state", trainer), "backend", None)
+    if backend is not None:
+        backend.params_updated()
+
+
+def set_trainer_params_from_ndarrays(arrays: Sequence[np.ndarray], trainer: Any, key_filter: str | None = None) -> None:
+    """Install a sorted-name payload; with ``key_filter`` the arrays correspond to the names containing it
+    (ref: photon/utils.py:481-540)."""
+    flat = _flat_of(trainer)
+    names = [n for n in flat.layout.names if key_filter is None or key_filter in n]
+    set_trainer_trainable_params_dict(trainer, construct_parameters_dict(names, list(arrays)))
+
+
+def get_wte_parameters_from_trainer(trainer: Any) -> np.ndarray:
+    """The (unique) token-embedding matrix (ref: photon/utils.py:543-582)."""
+    flat = _flat_of(trainer)
+    hits = [n for n in flat.layout.names if "wte" in n]
+    if len(hits) != 1:
+        raise ValueError("There are no WTE parameters" if not hits else "WTE parameters are not unique")
+    return flat.layout.view(flat.params, hits[0]).detach().cpu().numpy().copy()
+
+
+def set_wte_parameters_to_trainer(trainer: Any, wte_parameters: np.ndarray) -> None:
+    """Transplant only the token embedding (ref: photon/utils.py:585-599)."""
+    flat = _flat_of(trainer)
+    hits = [n for n in flat.layout.names if "wte" in n]
+    if len(hits) != 1:
+        raise ValueError("There are no WTE parameters" if not hits else "WTE parameters are not unique")
+    set_trainer_trainable_params_dict(trainer, {hits[0]: np.asarray(wte_parameters, dtype=np.float32)})
+
+
 # ------------------------------------------------------------------- model files (npz / npzc / bin)
 def dump_model_parameters_to_file(path: str | os.PathLike, arrays: Sequence[np.ndarray], compressed: bool = False) -> Path:
     """``np.savez(*arrays)`` → keys ``arr_0..arr_{n-1}`` in sorted-name order (ref: photon/utils.py:733-761)."""
@@ -92,6 +165,37 @@ def sum_of_squares(arrays: Sequence[np.ndarray | torch.Tensor]) -> float:
 
 def l2_norm(arrays: Sequence[np.ndarray | torch.Tensor]) -> float:
     return float(np.sqrt(sum_of_squares(arrays)))
+
+
+def l2_norm_of_momenta(optimizer_or_state: Any) -> tuple[float, float]:
+    """(‖exp_avg‖, ‖exp_avg_sq‖) of the local optimizer (ref: photon/utils.py:878-908). Accepts our flat
+    optimizer (``full_moments()``) or a torch-style ``{param: {"exp_avg", "exp_avg_sq"}}`` state dict."""
+    if hasattr(optimizer_or_state, "full_moments"):
+        m, v = optimizer_or_state.full_moments()
+        return float(m.double().norm()), float(v.double().norm())
+    vals = list(optimizer_or_state.values())
+    return l2_norm([s["exp_avg"] for s in vals]), l2_norm([s["exp_avg_sq"] for s in vals])
+
+
+def chunks_idx(list_of_stuff: Sequence[Any], n_chunks: int) -> Any:
+    """(start, end) of ``n_chunks`` near-equal contiguous chunks, longer ones first (ref: photon/utils.py:819-841)."""
+    d, r = divmod(len(list_of_stuff), n_chunks)
+    lo = 0
+    for i in range(n_chunks):
+        hi = lo + d + (1 if i < r else 0)
+        yield lo, hi
+        lo = hi
+
+
+def is_literal_for_ast(s: str) -> bool:
+    """True when ``ast.literal_eval`` accepts the string (ref: photon/utils.py:1066-1084)."""
+    import ast
+
+    try:
+        ast.literal_eval(s)
+    except (ValueError, SyntaxError):
+        return False
+    return True
 
 
 # ----------------------------------------------------------------------------- environment

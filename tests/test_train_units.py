@@ -245,3 +245,97 @@ def test_fsdp_config_selects_the_sharded_step():
     assert not wants_sharded_step(compose(["run_uuid=t", "~llm_config.fsdp_config"])["llm_config"])
     assert not wants_sharded_step(compose(["run_uuid=t", "llm_config.fsdp_config.sharding_strategy=NO_SHARD"])["llm_config"])
     assert wants_sharded_step(compose(["run_uuid=t", "llm_config.fsdp_config.sharding_strategy=SHARD_GRAD_OP"])["llm_config"])
+
+
+# ------------------------------------------------------------------ reference-named API surface
+def _tiny_trainer(tmp_path):
+    from photon_b200.train.trainer import Trainer
+
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=1, max_seq_len=16, vocab_size=64, attn_impl="torch")
+    ids = torch.randint(0, 64, (2, 16))
+
+    class Loader:
+        def __iter__(self):
+            while True:
+                yield {"input_ids": ids}
+
+    tr = Trainer(cfg, optimizer_cfg=dict(name="decoupled_adamw", lr=1e-3), scheduler_cfg=dict(name="constant_with_warmup", t_warmup="0ba"),
+                 train_loader=Loader(), global_train_batch_size=2, device_train_microbatch_size=2, precision="fp32", device="cpu",
+                 kernels=dict(gemm="torch", attention="torch", norm="torch", loss="torch", optimizer="torch"))
+    tr.fit("2ba")
+    return tr
+
+
+
+def test_param_side_channel_roundtrip(tmp_path):
+    """Sender/receiver halves of the parameter side channel over shm and npz files."""
+    import uuid
+
+    from photon_b200.messages import ParamHandle
+    from photon_b200.server.s3_utils import (release_remote_parameters, replace_parameters_in_recordset_with_remote,
+                                             replace_remote_with_parameters_in_recordset)
+    from photon_b200.utils.flat import FlatLayout
+
+    lay = FlatLayout.build([("b.weight", (3, 5)), ("a.bias", (7,)), ("c", ())], align=8, total_multiple=16)
+    flat = torch.arange(lay.total, dtype=torch.float32)
+    want = lay.to_ndarrays(flat)
+    for stack in ({"shm": True}, {"s3": True}):
+        h = replace_remote_with_parameters_in_recordset(ParamHandle("inline", flat), stack, endpoint_id=f"pbt{uuid.uuid4().hex[:8]}",
+                                                        layout=lay, root=tmp_path)
+        assert h.kind == ("shm" if "shm" in stack else "file") and not torch.is_tensor(h.data)
+        got = replace_parameters_in_recordset_with_remote(h)
+        assert all(np.array_equal(a, b) for a, b in zip(got.data, want))
+        back = replace_parameters_in_recordset_with_remote(h, layout=lay, as_flat=True).data
+        assert all(np.array_equal(a, b) for a, b in zip(lay.to_ndarrays(back), want))
+        release_remote_parameters(h)
+    assert replace_remote_with_parameters_in_recordset(ParamHandle("inline", flat), {"nvl": True}, endpoint_id="x").kind == "nvl"
+
+
+def test_reference_named_helpers(tmp_path):
+    from photon_b200.metrics.unigram_normalized_metrics import create_wrapped_subclass
+    from photon_b200.strategy import (FedAdam, FedAvgEfficient, aggregate_parameters, initialize_strategy,
+                                      parameters_to_ndarrays_gen)
+    from photon_b200.utils.core import (chunks_idx, get_parameters_from_state, get_trainable_params_dict,
+                                        get_wte_parameters_from_trainer, is_literal_for_ast, l2_norm_of_momenta,
+                                        set_trainer_params_from_ndarrays, set_wte_parameters_to_trainer)
+    from photon_b200.utils.flat import FlatLayout
+
+    # running mean, functional form == textbook weighted mean
+    xs, ws = [torch.randn(64) for _ in range(3)], [3.0, 1.0, 4.0]
+    acc, n = None, 0.0
+    for x, w in zip(xs, ws):
+        acc, n = aggregate_parameters(acc, x, n, w)
+    assert torch.allclose(acc, sum(x * w for x, w in zip(xs, ws)) / sum(ws), atol=1e-6) and n == 8.0
+    lay = FlatLayout.build([("w", (4, 4)), ("b", (4,))], align=8, total_multiple=16)
+    flat = torch.randn(lay.total)
+    assert [a.shape for a in parameters_to_ndarrays_gen(flat, lay)] == [(4,), (4, 4)]
+    # strategy initialisation: momenta required exactly when the strategy uses them
+    initialize_strategy(FedAvgEfficient(1.0), flat.clone(), layout=lay)
+    with pytest.raises(ValueError):
+        initialize_strategy(FedAdam(), flat.clone(), layout=lay)
+    st = FedAdam()
+    initialize_strategy(st, lay.to_ndarrays(flat), lay.to_ndarrays(torch.zeros(lay.total)), lay.to_ndarrays(torch.zeros(lay.total)), layout=lay)
+    assert torch.equal(lay.view(st.parameters, "w"), lay.view(flat, "w")) and st.second_momentum_vector is not None
+    # misc helpers
+    assert list(chunks_idx(list(range(10)), 3)) == [(0, 4), (4, 7), (7, 10)]
+    assert is_literal_for_ast("{'a': [1, 2]}") and not is_literal_for_ast("foo bar(")
+
+    class WithArg:
+        def __init__(self, k: int = 0) -> None:
+            self.k = k
+
+    sub = create_wrapped_subclass(WithArg, k=3)
+    assert sub.__name__ == "WithArg" and sub().k == 3 and sub(k=5).k == 5 and isinstance(sub(), WithArg)
+    # trainer parameter get / set by name
+    tr = _tiny_trainer(tmp_path)
+    arrays = get_parameters_from_state({}, tr)
+    names = list(get_trainable_params_dict(tr))
+    assert names == sorted(names) and len(arrays) == len(names)
+    wte = get_wte_parameters_from_trainer(tr)
+    set_wte_parameters_to_trainer(tr, wte * 0 + 0.5)
+    assert float(get_wte_parameters_from_trainer(tr).mean()) == 0.5
+    set_trainer_params_from_ndarrays(arrays, tr)
+    assert all(np.array_equal(a, b) for a, b in zip(get_parameters_from_state({}, tr), arrays))
+    m, v = l2_norm_of_momenta(tr.state.optimizer)
+    assert m >= 0.0 and v >= 0.0
+    tr.close()
