@@ -121,7 +121,12 @@ def llm_eval(trainer: Trainer | None, payload: Payload, eval_config: EvaluateCon
     t0 = _now()
     st = trainer.state
     before = st.flat.params.clone()
-    (params,) = payload_to_planes(payload, st.flat.layout, st.flat.params.device, 1)
+    lay = st.flat.layout
+    if torch.is_tensor(payload):   # with fl.aggregate_momenta the broadcast carries [params | exp_avg | exp_avg_sq]:
+        payload = payload.reshape(-1)[: lay.total]          # evaluation only needs the model plane
+    else:
+        payload = list(payload)[: len(lay.names)]
+    (params,) = payload_to_planes(payload, lay, st.flat.params.device, 1)
     st.flat.params.copy_(params)
     st.backend.params_updated()
     if not torch.equal(st.flat.params, params):

@@ -73,7 +73,9 @@ class FederationRuntime:
         self.trainer: Trainer | None = None
         self._opt_states: dict[int, tuple[torch.Tensor, torch.Tensor, int]] = {}
         self._local_params: dict[int, torch.Tensor] = {}   # personalised-layer memory per client
-        self.layout: FlatLayout | None = None
+        self.layout: FlatLayout | None = None        # exchange layout (3 planes with fl.aggregate_momenta)
+        self.model_layout: FlatLayout | None = None  # the trainer's parameter layout
+        self.aggregate_momenta = bool(cfg["fl"].get("aggregate_momenta", False))
         self.round_backend: RoundBackend | None = None
         self.fault_injection = dict(cfg["fl"].get("fault_injection") or {})
         self.timings: dict[str, float] = {}
@@ -103,7 +105,10 @@ class FederationRuntime:
                                              allow_unigram_metrics_failures=bool(fl["allow_unigram_metrics_failures"]),
                                              frozen_layers=fl.get("frozen_layers"), unfrozen_layers=fl.get("unfrozen_layers"),
                                              resize_vocab=fl.get("resize_vocab"), **kw)
-        self.layout = self.trainer.state.flat.layout
+        self.model_layout = self.trainer.state.flat.layout
+        # fl.aggregate_momenta (R3): the exchanged / aggregated / checkpointed vector is [params | exp_avg | exp_avg_sq];
+        # the strategy is oblivious to the structure, exactly like the reference's 3n-array payload
+        self.layout = self.model_layout.stacked(("", "exp_avg/", "exp_avg_sq/")) if self.aggregate_momenta else self.model_layout
         self.round_backend = build_round_backend(self.cfg, self.layout, self.strategy, self.device, rank=self.rank,
                                                  world_size=self.world_size, group=self.group)
 
@@ -113,9 +118,9 @@ class FederationRuntime:
         flat = torch.zeros(self.layout.total, dtype=torch.float32)
         if self.rank == 0:
             arrays, lay = get_initial_parameters(self.cfg)
-            if lay.names != self.layout.names:
+            if lay.names != self.model_layout.names:
                 raise AssertionError("initial-parameter layout differs from the trainer's")
-            self.layout.from_ndarrays(flat, arrays)
+            self.model_layout.from_ndarrays(flat[: self.model_layout.total], arrays)  # momenta planes start at zero
         return flat
 
     # ----------------------------------------------------------------------- sampling
@@ -160,14 +165,17 @@ class FederationRuntime:
                 if fc.personalized_layers and cid in self._local_params:
                     tr.state.flat.params.copy_(self._local_params[cid])
                 with tracer().span("client_fit", cat="client", device=True, cid=cid, server_round=server_round):
+                    shadow = rb.global_shadow()
                     payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
-                                                             shadow_payload=rb.global_shadow())
+                                                             shadow_payload=None if shadow is None else shadow[: self.model_layout.total])
                 if keep_opt and len(self.my_clients(sampled)) > 1:
                     self._opt_states[cid] = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
                 if fc.personalized_layers:
                     self._local_params[cid] = tr.state.flat.params.clone()
                 if self.is_leader:
-                    rb.add_client(payload if torch.is_tensor(payload) and payload.numel() == self.layout.total else tr.state.flat.params, n_samples)
+                    if not (torch.is_tensor(payload) and payload.numel() == self.layout.total):
+                        raise AssertionError("client payload does not match the exchange layout")
+                    rb.add_client(payload, n_samples)
                 results.append(FitRes(Status(Code.OK, ""), ParamHandle(kind=rb.name), n_samples if self.is_leader else 0, metrics, cid))
             except Exception as e:  # noqa: BLE001 - a failed client must not take the round down
                 results.append(FitRes(Status(Code.FAILED, repr(e)), None, 0, {}, cid))

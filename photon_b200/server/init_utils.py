@@ -51,8 +51,10 @@ def initialize_round(runtime: Any, store: CheckpointStore | None, history: Wandb
     runtime.server_steps_cumulative = 0
     params = runtime.initial_parameters()
     if runtime.rank == 0:
-        cent = get_centralized_run_parameters(runtime.cfg, runtime.layout)
-        params = cent if cent is not None else params
+        model_layout = getattr(runtime, "model_layout", None) or runtime.layout
+        cent = get_centralized_run_parameters(runtime.cfg, model_layout)
+        if cent is not None:
+            params[: model_layout.total] = cent  # any momenta planes stay zero
     broadcast_parameters_to_nodes(runtime, params)
     if store is not None and runtime.rank == 0:
         store.upload_server_checkpoint(str(runtime.cfg["run_uuid"]), 0, layout=runtime.layout, tensors=runtime.state_tensors(),

@@ -64,6 +64,18 @@ class FlatLayout:
     def views(self, flat: torch.Tensor) -> list[torch.Tensor]:
         return [self.view(flat, i) for i in range(len(self.names))]
 
+    def stacked(self, prefixes: Sequence[str]) -> "FlatLayout":
+        """This layout repeated once per prefix, plane after plane (``total`` elements each): the exchange layout
+        of ``fl.aggregate_momenta`` — ``[params | exp_avg | exp_avg_sq]`` (ref: photon/clients/utils.py:457-468,626-650).
+        The first prefix is normally ``""`` so plane 0 keeps the model's names."""
+        names, shapes, offsets, numels = [], [], [], []
+        for k, pre in enumerate(prefixes):
+            names += [pre + n for n in self.names]
+            shapes += list(self.shapes)
+            offsets += [o + k * self.total for o in self.offsets]
+            numels += list(self.numels)
+        return FlatLayout(tuple(names), tuple(shapes), tuple(offsets), tuple(numels), self.total * len(prefixes), self.align)
+
     def segment_table(self) -> torch.Tensor:
         """int64 [n,2] (offset, numel) — consumed by per-layer norm kernels."""
         return torch.tensor(list(zip(self.offsets, self.numels)), dtype=torch.int64)

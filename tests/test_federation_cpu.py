@@ -155,3 +155,33 @@ def test_two_rank_gloo_federation(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", str(_free_port()), str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("extra,check", [
+    (["fl.aggregate_momenta=true", "fl.reset_optimizer=false", "llm_config.optimizer.name=decoupled_adamw"], "momenta"),
+    (["fl.personalized_layers=[transformer.wpe.weight]"], "personalized"),
+    (["fl.random_layers=[transformer.blocks.0.ffn.up_proj.weight]", "fl.random_init_freq=1"], "random"),
+    (["fl.frozen_layers=[transformer.wpe.weight]", "fl.split_eval=true"], "frozen"),
+])
+def test_client_side_model_surgery_features(tmp_path, extra, check):
+    """SURVEY App. B features run end to end through the round loop (ref: clients/utils.py:405-652)."""
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server_app import run_server
+
+    cfg = _cfg(tmp_path, f"run_uuid=s-{check}", "fl.n_rounds=2", "fl.n_clients_per_round=2", *extra)
+    rt = FederationRuntime(cfg, device=torch.device("cpu"), rank=0, world_size=1)
+    h = run_server(cfg, runtime=rt)
+    fit = h.metrics_distributed_fit
+    assert [r for r, _ in fit["server/l2_norm_pseudo_gradient"]] == [1, 2]
+    assert all(np.isfinite(v) for _, v in fit["server/l2_norm_model"])
+    if check == "momenta":
+        # three planes travelled: [params | exp_avg | exp_avg_sq]; the aggregated Adam moments are non-zero after a round
+        total = rt.model_layout.total
+        g = rt.round_backend.global_params()
+        assert g.numel() == 3 * total == rt.layout.total and len(rt.layout.names) == 3 * len(rt.model_layout.names)
+        assert float(g[total:2 * total].abs().sum()) > 0 and float(g[2 * total:].min()) >= 0 and float(g[2 * total:].sum()) > 0
+        assert any("exp_avg" in k or "momentum" in k for k in fit if k.startswith("client/"))
+    if check == "frozen":
+        assert "transformer.wpe.weight" not in rt.layout.names
+        assert len(h.losses_distributed) >= 2
+    rt.close()

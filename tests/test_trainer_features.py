@@ -1,0 +1,154 @@
+"""CPU checks of Trainer behaviours the reference gets from Composer: ``auto`` microbatching with
+OOM halving, monitoring callbacks and loggers, fp16 loss scaling, freeze lists, the virtual-client work queue."""
+import json
+
+import pytest
+import torch
+
+from photon_b200.models.mpt import MPTConfig
+from photon_b200.train.callbacks import InMemoryLogger, JSONLLogger, build_callbacks
+from photon_b200.train.trainer import GradScaler, Trainer
+
+TORCH_KERNELS = dict(gemm="torch", attention="torch", norm="torch", loss="torch", optimizer="torch")
+
+
+class _Loader:
+    def __init__(self, batch: int, seq: int = 16, vocab: int = 64) -> None:
+        g = torch.Generator().manual_seed(5)
+        self.ids = torch.randint(0, vocab, (batch, seq), generator=g)
+
+    def __iter__(self):
+        while True:
+            yield {"input_ids": self.ids}
+
+
+def _trainer(batch: int = 8, **kw) -> Trainer:
+    cfg = MPTConfig(d_model=32, n_heads=2, n_layers=2, max_seq_len=16, vocab_size=64, attn_impl="torch")
+    base = dict(optimizer_cfg=dict(name="decoupled_adamw", lr=1e-3), scheduler_cfg=dict(name="constant_with_warmup", t_warmup="0ba"),
+                train_loader=_Loader(batch), global_train_batch_size=batch, device_train_microbatch_size=batch, precision="fp32",
+                device="cpu", kernels=TORCH_KERNELS)
+    base.update(kw)
+    return Trainer(cfg, **base)
+
+
+def test_auto_microbatch_halves_on_oom_and_matches_fixed_microbatch():
+    """``device_train_microbatch_size: auto`` starts at the device batch and halves on an OOM; the resulting
+    gradient equals the fixed-microbatch one because the loss is normalised by the batch's token count."""
+    auto = _trainer(device_train_microbatch_size="auto")
+    real = auto.state.backend.fwd_bwd
+    seen: list[int] = []
+
+    def flaky(ids, denom, scale=1.0):
+        seen.append(ids.shape[0])
+        if ids.shape[0] > 2:
+            raise RuntimeError("CUDA out of memory. Tried to allocate 20.00 GiB")
+        return real(ids, denom, scale)
+
+    auto.state.backend.fwd_bwd = flaky
+    auto.fit("1ba")
+    assert auto._auto_mb == 2 and seen[:2] == [8, 4] and seen[2:] == [2, 2, 2, 2]
+    fixed = _trainer(device_train_microbatch_size=2)
+    fixed.fit("1ba")
+    assert torch.allclose(auto.state.flat.params, fixed.state.flat.params, atol=1e-6)
+    whole = _trainer(device_train_microbatch_size=8)
+    whole.fit("1ba")
+    assert torch.allclose(whole.state.flat.params, fixed.state.flat.params, atol=1e-5)
+    # a non-OOM error is not swallowed
+    bad = _trainer(device_train_microbatch_size="auto")
+    bad.state.backend.fwd_bwd = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("shape mismatch"))
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        bad.fit("1ba")
+    for t in (auto, fixed, whole, bad):
+        t.close()
+
+
+def test_monitor_callbacks_and_loggers_emit_the_reference_keys(tmp_path):
+    cbs = build_callbacks({"speed_monitor": {"window_size": 2}, "lr_monitor": {}, "memory_monitor": {}, "runtime_estimator": {},
+                           "optimizer_monitor": {"interval": "1ba"}, "activation_monitor_full_model": {"interval": "2ba"},
+                           "not_a_callback": {}})
+    assert len(cbs) == 6  # unknown names are skipped with a notice, like llm-foundry's registry miss would be fatal there
+    mem, jl = InMemoryLogger(), JSONLLogger(tmp_path / "log.jsonl", flush_interval=1)
+    tr = _trainer(callbacks=cbs, loggers=[mem, jl], grad_clip_norm=1.0, max_duration="6ba")
+    tr.fit()
+    keys = set(mem.data)
+    for want in ("loss/train/total", "metrics/train/LanguageCrossEntropy", "throughput/batches_per_sec", "throughput/device/tokens_per_sec",
+                 "lr-DecoupledAdamW/group0", "time/remaining_estimate", "l2_norm/grad/global", "l2_norm/grad/clipped_from"):
+        assert any(k == want for k in keys), f"{want} not logged; have {sorted(keys)[:40]}"
+    assert any(k.startswith("activations/") for k in keys)
+    tr.close()
+    lines = [json.loads(x) for x in (tmp_path / "log.jsonl").read_text().splitlines()]
+    assert lines and lines[-1]["step"] == 6 and "loss/train/total" in lines[-1]
+
+
+def test_fp16_loss_scaler_skips_nonfinite_steps_and_backs_off():
+    sc = GradScaler(init=1024.0, growth_interval=2)
+    sc.update(True)
+    assert sc.scale == 512.0
+    sc.update(False), sc.update(False)
+    assert sc.scale == 1024.0
+    tr = _trainer(precision="amp_fp16", grad_clip_norm=1.0)
+    before = tr.state.flat.params.clone()
+    real = tr.state.backend.fwd_bwd
+
+    def poisoned(ids, denom, scale=1.0):
+        out = real(ids, denom, scale)
+        tr.state.flat.grads[0] = float("inf")
+        return out
+
+    tr.state.backend.fwd_bwd = poisoned
+    s0 = tr.scaler.scale
+    tr.fit("1ba")
+    assert torch.equal(tr.state.flat.params, before) and tr.scaler.scale == s0 / 2  # step skipped, scale halved
+    tr.state.backend.fwd_bwd = real
+    tr.fit("1ba")
+    assert not torch.equal(tr.state.flat.params, before)
+    tr.close()
+
+
+def test_freeze_lists_shrink_the_exchanged_layout():
+    full = _trainer()
+    names = list(full.state.flat.names)
+    frozen = [n for n in names if ".blocks.0." in n]
+    tr = _trainer(frozen_layers=frozen)
+    assert set(tr.state.flat.names) == set(names) - set(frozen)
+    only = _trainer(unfrozen_layers=["transformer.wte.weight"])
+    assert list(only.state.flat.names) == ["transformer.wte.weight"]
+    with pytest.raises(ValueError):
+        _trainer(frozen_layers=frozen, unfrozen_layers=["transformer.wte.weight"])
+    with pytest.raises(KeyError):
+        _trainer(frozen_layers=["transformer.nope"])
+    tr.fit("1ba")  # a partly frozen model still trains
+    for t in (full, tr, only):
+        t.close()
+
+
+def test_virtual_client_work_queue_hands_next_client_to_first_free_node():
+    """7 sampled clients on 3 nodes: first three dispatched at once, each reply frees that node for the next cid
+    (ref: server/server_util.py:145-202)."""
+    from photon_b200.server.server_util import ClientScheduler, static_assignment
+
+    log: list[tuple[int, int]] = []
+    running: dict[int, int] = {}
+    speed = {10: 1, 11: 3, 12: 2}  # polls a node needs per client
+    clock: dict[int, int] = {}
+
+    def dispatch(node: int, cid: int) -> None:
+        log.append((node, cid))
+        running[node], clock[node] = cid, speed[node]
+
+    def poll() -> list[tuple[int, int, str]]:
+        done = []
+        for node in list(running):
+            clock[node] -= 1
+            if clock[node] == 0:
+                done.append((node, running.pop(node), f"ok{node}"))
+        return done
+
+    got = list(ClientScheduler(range(7), [10, 11, 12], dispatch, poll))
+    assert sorted(c for _, c, _ in got) == list(range(7))
+    assert log[:3] == [(10, 0), (11, 1), (12, 2)]
+    per_node = {n: [c for m, c in log if m == n] for n in speed}
+    assert len(per_node[10]) > len(per_node[12]) >= len(per_node[11])  # the fast node takes more clients
+    assert all(r == f"ok{n}" for n, _, r in got)
+    sa = static_assignment(list(range(7)), [10, 11, 12])
+    assert sorted(c for v in sa.values() for c in v) == list(range(7)) and max(map(len, sa.values())) == 3
