@@ -48,7 +48,9 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
                                                 frozen_layers=fc.frozen_layers, unfrozen_layers=fc.unfrozen_layers,
                                                 resize_vocab=fc.resize_vocab, **(trainer_kwargs or {}))
     else:
-        train_cfg = reconfigure_trainer(trainer, cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval)
+        train_cfg = reconfigure_trainer(trainer, cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval,
+                                        use_unigram_metrics=fc.use_unigram_metrics,
+                                        allow_unigram_metrics_failures=fc.allow_unigram_metrics_failures)
     # ---- per-client checkpoint policy: resume mid-round or skip an already finished round
     skip_iteration, load_set, _ = set_initial_config_from_fit_config(fc, train_cfg, cid)
     trainer.save_folder = train_cfg.get("save_folder")
@@ -116,7 +118,8 @@ def llm_eval(trainer: Trainer | None, payload: Payload, eval_config: EvaluateCon
                                         frozen_layers=ec.frozen_layers, unfrozen_layers=ec.unfrozen_layers,
                                         resize_vocab=ec.resize_vocab, **(trainer_kwargs or {}))
     else:
-        reconfigure_trainer(trainer, cfg, None, log_name="_eval", split_eval=ec.split_eval)
+        reconfigure_trainer(trainer, cfg, None, log_name="_eval", split_eval=ec.split_eval, use_unigram_metrics=ec.use_unigram_metrics,
+                            allow_unigram_metrics_failures=ec.allow_unigram_metrics_failures)
     metrics["client/eval_init_time"] = _now() - t_start
     t0 = _now()
     st = trainer.state

@@ -143,9 +143,19 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
 
 
 def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, log_name: str = "", split_eval: bool = False,
-                        reset_timestamp: bool = False) -> Any:
-    """Swap the per-client mutables on a live Trainer (loaders, save folder, run name, clocks)."""
+                        reset_timestamp: bool = False, use_unigram_metrics: bool | None = None,
+                        allow_unigram_metrics_failures: bool = False) -> Any:
+    """Swap the per-client mutables on a live Trainer (loaders, save folder, run name, clocks, and — when
+    ``use_unigram_metrics`` — the unigram table of THIS client's streams; ref: trainer_utils.py:278-327,656-1114)."""
     t, evals = _prepare_train_cfg(cfg, cid, split_eval, trainer.world_size, log_name)
+    if use_unigram_metrics:
+        from photon_b200.utils.core import add_unigram_metrics
+
+        freq = lcf.get_stream_freq_dict_for_client(t, cid, allow_failures=allow_unigram_metrics_failures)
+        if freq is not None:
+            add_unigram_metrics(trainer, freq)
+        elif not allow_unigram_metrics_failures:
+            raise RuntimeError("unigram metrics requested but no 1_gram.json found")
     seed = int(t.get("seed", 17))
     syn_vocab = min(int(trainer.model_cfg.vocab_size), TOKENIZER_VOCAB)
     trainer.train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed, syn_vocab)

@@ -67,6 +67,6 @@ def fit_round(runtime: Any, server_round: int, sampled_clients: list[int]) -> di
     else:
         runtime.finish_round(server_round)
         metrics = handle_fit_replies(runtime, server_round, all_results)
-        metrics.update(runtime.round_backend.last_metrics)
+        metrics.update(runtime.round_backend.collect_metrics())
     metrics["server/fit_round_time"] = time.time() - t0
     return metrics

@@ -73,6 +73,40 @@ class RoundBackend:
     def moments(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
         return self.strategy.momentum_vector, self.strategy.second_momentum_vector
 
+    # -- server metric callback (noise scale): additive per-client statistics, reduced over ranks at collection time
+    def _cb_begin(self) -> None:
+        self._cb_sq: torch.Tensor | None = None
+        self._cb_n = 0
+
+    def _cb_add(self, params: torch.Tensor) -> None:
+        if self.strategy.metrics_callback is None:
+            return
+        d = (self.global_params().to(params.device)[: params.numel()] - params.reshape(-1)).float()
+        sq = torch.dot(d, d).double()       # stays on the device: no host sync inside the round
+        self._cb_sq = sq if self._cb_sq is None else self._cb_sq + sq
+        self._cb_n += 1
+
+    def _pg_sq(self) -> float | None:
+        return self.strategy.last_pg_sq
+
+    def collect_metrics(self) -> dict[str, Any]:
+        """Server-side metrics of the round that just finished (collective: every rank calls it)."""
+        cb = self.strategy.metrics_callback
+        if cb is None:
+            return self.last_metrics
+        stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if getattr(self, "_cb_sq", None) is not None:
+            stats[0], stats[1] = self._cb_sq.to(self.device), float(self._cb_n)
+        if self.world_size > 1 and _dist_on(self.group):
+            if dist.get_backend(self.group) != "nccl":
+                stats = stats.cpu()
+            dist.all_reduce(stats, group=self.group)
+        g_big = self._pg_sq()
+        if g_big is not None:
+            sum_sq, n = stats.tolist()
+            cb.round_end_from_stats(float(sum_sq), int(round(n)), float(g_big), self.last_metrics)
+        return self.last_metrics
+
     def close(self) -> None:
         pass
 
@@ -93,10 +127,15 @@ class _HostAccumulating(RoundBackend):
     def begin_round(self) -> None:
         self._acc: torch.Tensor | None = None
         self._w = 0.0
+        self._kept: list[tuple[torch.Tensor, float]] = []
+        self._cb_begin()
 
     def add_client(self, params: torch.Tensor, weight: float) -> None:
         if weight <= 0:
             raise ValueError("client weight must be positive")
+        self._cb_add(params)
+        if self.strategy.track_inplace:   # debug self-check: keep every client to form the textbook mean later
+            self._kept.append((params.detach().to("cpu", torch.float64), float(weight)))
         if self._acc is None:
             self._acc = params.detach().to(self.device, torch.float32) * float(weight)
         else:
@@ -105,6 +144,28 @@ class _HostAccumulating(RoundBackend):
 
     def global_params(self) -> torch.Tensor:
         return self._x_dev
+
+    def _fedavg_gap(self, avg: torch.Tensor | None, scale: float) -> dict[str, float]:
+        """``server/l2_norm_fedavg_gap``: distance between the transport's aggregate and the textbook float64
+        Σ n_k x_k / Σ n_k over ALL clients of the round (ref: fedavg_eff.py:366-391). Collective — every rank calls
+        it at the same point of ``finish_round``; ranks that do not hold ``avg`` pass None."""
+        if not self.strategy.track_inplace:
+            return {}
+        num = torch.zeros(self.layout.total, dtype=torch.float64)
+        den = torch.zeros(1, dtype=torch.float64)
+        for x, w in self._kept:
+            num += x * w
+            den += w
+        if self.world_size > 1 and _dist_on(self.group):
+            nccl = dist.get_backend(self.group) == "nccl"
+            num, den = (num.to(self.device), den.to(self.device)) if nccl else (num, den)
+            dist.all_reduce(num, group=self.group)
+            dist.all_reduce(den, group=self.group)
+        self._kept = []
+        if avg is None or float(den) <= 0:
+            return {}
+        naive = (num / den).to("cpu") * scale
+        return {"server/l2_norm_fedavg_gap": float((naive - avg.detach().to("cpu", torch.float64)).norm())}
 
 
 class CollectiveRoundBackend(_HostAccumulating):
@@ -127,7 +188,8 @@ class CollectiveRoundBackend(_HostAccumulating):
         s = self.strategy.scaling_factor()
         if s != 1.0:
             avg.mul_(s)
-        self.last_metrics = self.strategy.apply_server_update(avg, server_round)
+        gap = self._fedavg_gap(avg, s)
+        self.last_metrics = {**self.strategy.apply_server_update(avg, server_round), **gap}
         self._x_dev = self.strategy.parameters
         self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
 
@@ -175,6 +237,8 @@ class ShmRoundBackend(_HostAccumulating):
             infos = [mine]
         down = f"{self.uid}_down"
         down_meta: list[Any] = [None]
+        agg: torch.Tensor | None = None
+        agg_scale = 1.0
         if self.rank == 0:
             from photon_b200.strategy.aggregation import StreamingMean
 
@@ -191,8 +255,12 @@ class ShmRoundBackend(_HostAccumulating):
                 s = self.strategy.scaling_factor()
                 if s != 1.0:
                     avg.mul_(s)
+                agg, agg_scale = avg.clone() if self.strategy.track_inplace else None, s
                 self.last_metrics = self.strategy.apply_server_update(avg, server_round)
             down_meta[0] = self._put(down, self.strategy.parameters).to_literal()
+        gap = self._fedavg_gap(agg, agg_scale)
+        if gap:
+            self.last_metrics = {**self.last_metrics, **gap}
         if _dist_on(self.group):
             dist.broadcast_object_list(down_meta, src=0, group=self.group)
         arrays = self._get(down, ModelParametersMetadata.from_literal(down_meta[0]))
@@ -246,6 +314,8 @@ class FileRoundBackend(_HostAccumulating):
         else:
             infos = [rec]
         down = self.dir / "server" / "parameters.npz"
+        agg: torch.Tensor | None = None
+        agg_scale = 1.0
         if self.rank == 0:
             from photon_b200.strategy.aggregation import StreamingMean
 
@@ -261,8 +331,12 @@ class FileRoundBackend(_HostAccumulating):
                 s = self.strategy.scaling_factor()
                 if s != 1.0:
                     avg.mul_(s)
+                agg, agg_scale = avg.clone() if self.strategy.track_inplace else None, s
                 self.last_metrics = self.strategy.apply_server_update(avg, server_round)
             dump_model_parameters_to_file(down, self.layout.to_ndarrays(self.strategy.parameters))
+        gap = self._fedavg_gap(agg, agg_scale)
+        if gap:
+            self.last_metrics = {**self.last_metrics, **gap}
         if _dist_on(self.group):
             dist.barrier(group=self.group)
         host = torch.zeros(self.layout.total)
@@ -285,6 +359,9 @@ class NvlRoundBackend(RoundBackend):
 
         self.fed = NvlFedRound(layout.total, strategy, rank=rank, world_size=world_size, device=device, group=group)
         self.track_norms = track_norms
+        if strategy.track_inplace and rank == 0:
+            print("[round/nvl] track_inplace_aggregation is a host-transport self-check; the fused kernel never materialises "
+                  "the aggregate, so server/l2_norm_fedavg_gap is not reported on comm_stack.nvl")
 
     def set_global(self, params: torch.Tensor, momentum: torch.Tensor | None = None, second: torch.Tensor | None = None) -> None:
         self.fed.set_global(params)
@@ -298,19 +375,26 @@ class NvlRoundBackend(RoundBackend):
 
     def begin_round(self) -> None:
         self.fed.begin_round()
+        self._cb_begin()
 
     def add_client(self, params: torch.Tensor, weight: float) -> None:
+        self._cb_add(params)
         self.fed.add_client(params, weight)
 
     def finish_round(self, server_round: int) -> None:
         self.fed.finish_round(server_round)
         self.last_metrics = {}
 
+    def _pg_sq(self) -> float | None:
+        n = self.last_metrics.get("server/l2_norm_pseudo_gradient")
+        return None if n is None else float(n) ** 2
+
     def collect_metrics(self) -> dict[str, Any]:
-        """Norm by-products of the last round (host read; call outside timed regions)."""
-        if self.track_norms:
+        """Norm by-products of the last round's kernel (+ the noise-scale estimate): a tiny host read, done after
+        the round's device work instead of inside it."""
+        if self.track_norms or self.strategy.metrics_callback is not None:
             self.last_metrics = self.fed.round_norms(self.group)
-        return self.last_metrics
+        return super().collect_metrics()
 
     def global_params(self) -> torch.Tensor:
         return self.fed.global_params()

@@ -43,12 +43,18 @@ class FedSimpleNoiseScale(ServerMetricCallback):
         self._n += 1
 
     def round_end(self, fedavg_result: torch.Tensor | None, metrics: dict[str, Any]) -> None:
-        if fedavg_result is None or self._sum_sq == 0.0 or self._n < 2 or self._old is None:
+        if fedavg_result is None or self._old is None:
             return
         pg = self._old.to(fedavg_result.device) - fedavg_result
-        g_big = float(torch.dot(pg, pg))
-        g_small = self._sum_sq / self._n
-        b_small, b_big = 1, self._n
+        self.round_end_from_stats(self._sum_sq, self._n, float(torch.dot(pg, pg)), metrics)
+
+    def round_end_from_stats(self, sum_sq: float, n: int, g_big: float, metrics: dict[str, Any]) -> None:
+        """The same estimate from additive statistics — Σ_k ‖x − x_k‖², K and ‖x − x̄‖² — which is what the
+        distributed round transports have (each rank sees only its own clients; two scalars are all-reduced)."""
+        if sum_sq == 0.0 or n < 2:
+            return
+        g_small = sum_sq / n
+        b_small, b_big = 1, int(n)
         trace = (g_small - g_big) / (1.0 / b_small - 1.0 / b_big)
         sq = (b_big * g_big - b_small * g_small) / (b_big - b_small)
         self.counter += 1

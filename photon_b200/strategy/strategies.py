@@ -101,6 +101,7 @@ class ServerStrategy:
         self.momentum_vector: torch.Tensor | None = None
         self.second_momentum_vector: torch.Tensor | None = None
         self.layout: FlatLayout | None = None
+        self.last_pg_sq: float | None = None   # ‖x − x̄‖² of the last server update (kept when a metrics callback is set)
 
     # -- state ----------------------------------------------------------------------
     @property
@@ -173,6 +174,9 @@ class ServerStrategy:
         assert self.parameters is not None
         pg = server_opt_step(self.kind, self.parameters, avg, self.momentum_vector, self.second_momentum_vector,
                              self.hp, max(1, server_round), self.sign_compat)
+        if self.metrics_callback is not None:   # the round transports feed the noise-scale estimate from this
+            flat = pg.reshape(-1)
+            self.last_pg_sq = float(torch.dot(flat, flat))
         return self.norm_metrics(pg, avg) if self.track_norms else {}
 
     def norm_metrics(self, pg: torch.Tensor, avg: torch.Tensor) -> dict[str, Any]:

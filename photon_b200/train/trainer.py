@@ -33,8 +33,8 @@ from typing import Any, Iterable, Iterator
 import torch
 import torch.distributed as dist
 
-from photon_b200.metrics.language import Metric, build_metrics, sync_metrics
-from photon_b200.models.mpt import MPTConfig
+from photon_b200.metrics.language import Metric, build_metrics, sync_metrics, unigram_loss_sum
+from photon_b200.models.mpt import MPTConfig, shift_labels
 from photon_b200.train.backend import build_backend
 from photon_b200.train.callbacks import Callback, InMemoryLogger, Logger
 from photon_b200.train.optim import FlatOptimizer, build_optimizer, clip_coefficient
@@ -244,11 +244,15 @@ class Trainer:
                 st.flat.zero_grad()
                 loss_sum = torch.zeros((), device=self.device, dtype=torch.float32)
                 n_tok = torch.zeros((), device=self.device, dtype=torch.float32)
+                uni_logp = getattr(st.backend, "unigram_log_probs", None)
+                uni_sum = torch.zeros((), device=self.device, dtype=torch.float32) if uni_logp is not None else None
                 for lo in range(0, B, mb):
                     ids = self._to_device(ids_host[lo:lo + mb])
                     ls, n = st.backend.fwd_bwd(ids, n_tok_target, scale)
                     loss_sum += ls.float()
                     n_tok += n.float() if torch.is_tensor(n) else float(n)
+                    if uni_sum is not None:  # CE of the unigram model needs the targets only (K15: no second pass over logits)
+                        uni_sum += unigram_loss_sum(shift_labels(ids).view(-1), uni_logp).float()
                 break
             except RuntimeError as e:  # auto microbatch: halve on OOM (ref: SURVEY App. C)
                 if self._auto_mb is None or not _is_oom(e) or mb == 1:
@@ -267,7 +271,7 @@ class Trainer:
                                         self.grad_clip_norm, 1.0 / scale)
             if self.grad_clip_norm is not None:
                 self.log({"l2_norm/grad/clipped_from": gnorm})
-            self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok}
+            self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok, **({"unigram_loss_sum": uni_sum} if uni_sum is not None else {})}
             st.timestamp.advance_batch(samples=B * self.world_size, tokens=B * S * self.world_size)
             return
         # N1: ONE gradient all-reduce on the flat bucket (mean over ranks)
@@ -289,7 +293,7 @@ class Trainer:
             st.optimizer.step(st.scheduler(st.timestamp.batch), grad_mult)
             if not (st.optimizer.use_kernel and st.optimizer.bf16_shadow is not None):
                 st.backend.params_updated()
-        self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok}
+        self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok, **({"unigram_loss_sum": uni_sum} if uni_sum is not None else {})}
         st.timestamp.advance_batch(samples=B * self.world_size, tokens=B * S * self.world_size)
 
     def _grad_norm(self) -> torch.Tensor:
@@ -349,10 +353,11 @@ class Trainer:
         """D2H read of the step's loss (the only host sync in the step)."""
         stats = {k: float(v) for k, v in self.last_batch_stats.items()}
         if self.world_size > 1 and dist.is_initialized():
-            t = torch.tensor([stats["loss_sum"], stats["n_tokens"]], dtype=torch.float64,
+            keys = sorted(stats)
+            t = torch.tensor([stats[k] for k in keys], dtype=torch.float64,
                              device=self.device if dist.get_backend(self.process_group) == "nccl" else "cpu")
             dist.all_reduce(t, group=self.process_group)
-            stats = {"loss_sum": float(t[0]), "n_tokens": float(t[1])}
+            stats = dict(zip(keys, t.tolist()))
         for m in self.state.train_metrics.values():
             m.update(stats)
         loss = stats["loss_sum"] / max(stats["n_tokens"], 1.0)

@@ -250,7 +250,11 @@ def add_unigram_metrics(trainer: Any, unigram_freq: dict[int, int] | dict[str, i
 
     st = trainer.state
     logp = unigram_log_probs({int(k): int(v) for k, v in unigram_freq.items()}, trainer.model_cfg.vocab_size)
-    st.backend.unigram_log_probs = logp.to(st.flat.params.device)
+    cur = getattr(st.backend, "unigram_log_probs", None)
+    if cur is not None and cur.shape == logp.shape:
+        cur.copy_(logp)   # in place: a captured CUDA graph keeps reading this buffer
+    else:
+        st.backend.unigram_log_probs = logp.to(st.flat.params.device)
     st.train_metrics = build_metrics(True)
     st.eval_metrics = {lbl: build_metrics(True) for lbl in st.eval_metrics}
 

@@ -140,14 +140,17 @@ def test_two_rank_gloo_federation(tmp_path):
         from photon_b200.server_app import run_server
         dist.init_process_group("gloo")
         cfg = compose({TINY!r} + ["run_uuid=g2", "fl.n_rounds=2", "fl.eval_period=null", "photon.comm_stack.shm=false", "photon.comm_stack.ray=true",
-                                "llm_config.save_folder=null", "fl.n_clients_per_round=4"])
+                                "llm_config.save_folder=null", "fl.n_clients_per_round=4", "fl.use_noise_scale_metric=true",
+                                "fl.strategy_kwargs={{server_learning_rate: 1.0, server_momentum: 0.0, track_inplace_aggregation: true}}"])
         rt = FederationRuntime(cfg, device=torch.device("cpu"), rank=dist.get_rank(), world_size=2)
         h = run_server(cfg, runtime=rt)
         x = rt.round_backend.global_params().clone()
         ref = x.clone(); dist.broadcast(ref, src=0)
         assert torch.equal(x, ref)
         if dist.get_rank() == 0:
-            assert h.latest("server/n_aggregated_clients") is None or True
+            fit = h.metrics_distributed_fit
+            assert [v for _, v in fit["noise_scale/b_big"]] == [4, 4]          # per-client statistics reduced over both ranks
+            assert all(v < 1e-4 for _, v in fit["server/l2_norm_fedavg_gap"])   # transport aggregate == textbook mean
             print("OK", float(x.norm()))
         dist.destroy_process_group()
     """))
@@ -185,3 +188,37 @@ def test_client_side_model_surgery_features(tmp_path, extra, check):
         assert "transformer.wpe.weight" not in rt.layout.names
         assert len(h.losses_distributed) >= 2
     rt.close()
+
+
+_MATRIX = {
+    "noise_scale+unigram": ["fl.use_noise_scale_metric=true", "fl.use_unigram_metrics=true"],
+    "resize_vocab+eval_every_round": ["fl.resize_vocab=96", "fl.eval_period=1"],
+    "fedmom": ["fl.strategy_name=fedmom", "fl.strategy_kwargs={server_learning_rate: 1.0, server_momentum: 0.5}"],
+    "fedyogi": ["fl.strategy_name=fedyogi"],
+    "sqrt_scaling+gap_metric": ["fl.strategy_kwargs={server_learning_rate: 1.0, server_momentum: 0.0, scaling_fn: sqrt, track_inplace_aggregation: true}"],
+    "per_round_cleanup": ["photon.checkpoint=true", "cleanup_checkpoints_per_round=true"],
+    "rope+qk_ln+clip": ["++llm_config.model.attn_config.rope=true", "++llm_config.model.learned_pos_emb=false",
+                        "++llm_config.model.attn_config.qk_ln=true", "++llm_config.model.attn_config.clip_qkv=0.5"],
+    "alibi+no_bias": ["++llm_config.model.attn_config.alibi=true", "++llm_config.model.learned_pos_emb=false", "++llm_config.model.no_bias=true"],
+    "sqrt_cooldown+adamw": ["llm_config.scheduler.schedulers.lr.name=constant_with_sqrt_cooldown_with_warmup",
+                            "++llm_config.scheduler.schedulers.lr.t_cooldown=1ba", "~llm_config.scheduler.schedulers.lr.alpha_f",
+                            "llm_config.optimizer.name=decoupled_adamw"],
+    "keep_optimizer+reset_timestamp": ["fl.reset_optimizer=false", "fl.reset_timestamp=true", "llm_config.save_overwrite=true"],
+    "more_clients_than_nodes": ["fl.n_total_clients=8", "fl.n_clients_per_round=5"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(_MATRIX))
+def test_option_matrix_runs_two_clean_rounds(tmp_path, name):
+    """Every documented ``fl.*`` / ``llm_config.*`` switch combination runs two federated rounds without a client failure."""
+    from photon_b200.server_app import run_server
+
+    h = run_server(_cfg(tmp_path, "run_uuid=mx", "fl.n_rounds=2", *_MATRIX[name]))
+    fit = h.metrics_distributed_fit
+    assert [v for _, v in fit["server/n_failures"]] == [0, 0]
+    assert [r for r, _ in fit["server/l2_norm_pseudo_gradient"]] == [1, 2]
+    assert len(h.losses_distributed) == 3 and all(np.isfinite(v) for _, v in h.losses_distributed)
+    if "gap_metric" in name:
+        assert all(v < 1e-4 for _, v in fit["server/l2_norm_fedavg_gap"])
+    if "noise_scale" in name:
+        assert any(k.startswith("noise_scale/") for k in fit) and any("Unigram" in k for k in fit)
