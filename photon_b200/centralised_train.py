@@ -73,7 +73,17 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
         trainer.state.flat.load_ndarrays(arrays[: len(trainer.state.flat.names)])
         trainer.state.backend.params_updated()
     if cc.wte_parameters_path:
-        set_wte_parameters(trainer, load_model_parameters_from_file(cc.wte_parameters_path)[0])
+        # a FULL model file whose token embedding is transplanted on top of whatever was loaded above
+        # (ref: centralised_train.py:98-117); a one-array file holding just the embedding is accepted too
+        donor = load_model_parameters_from_file(cc.wte_parameters_path)
+        names = list(trainer.state.flat.names)
+        if len(donor) >= len(names):
+            wte = donor[names.index("transformer.wte.weight")]
+        elif len(donor) == 1:
+            wte = donor[0]
+        else:
+            raise ValueError(f"wte_parameters_path holds {len(donor)} arrays; expected a full model ({len(names)}) or the embedding alone")
+        set_wte_parameters(trainer, wte)
     if world_size > 1:  # identical start on every rank
         torch.distributed.broadcast(trainer.state.flat.params, src=0)
         trainer.state.backend.params_updated()

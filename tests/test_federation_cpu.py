@@ -222,3 +222,51 @@ def test_option_matrix_runs_two_clean_rounds(tmp_path, name):
         assert all(v < 1e-4 for _, v in fit["server/l2_norm_fedavg_gap"])
     if "noise_scale" in name:
         assert any(k.startswith("noise_scale/") for k in fit) and any("Unigram" in k for k in fit)
+
+
+def test_centralised_warm_starts_and_federation_restores(tmp_path, monkeypatch):
+    """``store_*_model`` → ``pretrained_model_path`` / ``wte_parameters_path`` / ``eval_only`` in a second centralised run,
+    ``photon.restore_cent_run_uuid`` seeding a federation, and ``photon.restore_run_uuid`` importing another run's round
+    (ref: centralised_train.py:98-166, server/init_utils.py:43-125, server/s3_utils.py:275-345)."""
+    from photon_b200.centralised_train import run_centralised
+    from photon_b200.checkpoint import CheckpointStore
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server_app import run_server
+    from photon_b200.utils.core import load_model_parameters_from_file
+
+    monkeypatch.chdir(tmp_path)
+    cen = [a for a in TINY if not a.startswith(("fl.", "llm_config.local_steps"))] + [f"photon.saving_path={tmp_path}", "llm_config.save_folder=null"]
+    a = run_centralised(compose(cen + ["run_uuid=cA", "centralized.store_init_model=true", "centralized.store_final_model=true"]),
+                        device=torch.device("cpu"), duration="3ba")
+    final = tmp_path / "cA-3-checkpoint.npz"
+    assert (tmp_path / "cA-0-checkpoint.npz").exists() and final.exists()
+    trained = load_model_parameters_from_file(final)
+    assert all(np.array_equal(x, y) for x, y in zip(trained, a.state.flat.to_ndarrays()))
+    a.close()
+    # eval-only run on the trained weights: no optimizer step, weights untouched
+    b = run_centralised(compose(cen + ["run_uuid=cB", f"pretrained_model_path={final}", "centralized.eval_only=true"]), device=torch.device("cpu"))
+    assert b.state.timestamp.batch == 0 and all(np.array_equal(x, y) for x, y in zip(trained, b.state.flat.to_ndarrays()))
+    assert "eval/LanguageCrossEntropy" in b.state.eval_metric_values
+    b.close()
+    # embedding transplant: everything fresh except wte, which comes from the donor file
+    c = run_centralised(compose(cen + ["run_uuid=cC", f"wte_parameters_path={final}", "centralized.eval_only=true", "llm_config.seed=99"]),
+                        device=torch.device("cpu"))
+    names = list(c.state.flat.names)
+    got = c.state.flat.to_ndarrays()
+    i = names.index("transformer.wte.weight")
+    assert np.array_equal(got[i], trained[i]) and not np.array_equal(got[i - 1], trained[i - 1])
+    c.close()
+    # a federation seeded from the centralised run starts at its weights (round-0 checkpoint proves it)
+    fed = _cfg(tmp_path, "run_uuid=fA", "photon.checkpoint=true", "fl.n_rounds=1", "photon.restore_cent_run_uuid=cA", "photon.restore_cent_run_batches=3")
+    run_server(fed)
+    store = CheckpointStore(tmp_path, "checkpoints")
+    r0 = load_model_parameters_from_file(store.round_dir("fA", 0) / "current_server_parameters.npz")
+    assert all(np.array_equal(x, y) for x, y in zip(r0, trained))
+    # a NEW run importing fA's last round continues from round 1 → runs only round 2
+    fed2 = _cfg(tmp_path, "run_uuid=fB", "photon.checkpoint=true", "fl.n_rounds=2", "photon.restore_run_uuid=fA", "photon.resume_round=-1")
+    h = run_server(fed2)
+    assert [r for r, _ in h.metrics_distributed_fit["server/l2_norm_pseudo_gradient"]][-1] == 2
+    assert store.obtain_sorted_rounds("fB", ["current_server_parameters", "current_momentum_vector"])[-2:] == [1, 2]
+    r1a = load_model_parameters_from_file(store.round_dir("fA", 1) / "current_server_parameters.npz")
+    r1b = load_model_parameters_from_file(store.round_dir("fB", 1) / "current_server_parameters.npz")
+    assert all(np.array_equal(x, y) for x, y in zip(r1a, r1b))
