@@ -10,14 +10,14 @@ from __future__ import annotations
 import contextlib
 from typing import Any, Iterator
 
-from photon_b200.messages import Code, EvaluateRes, FitRes, Message, Status
+from photon_b200.messages import Code, EvaluateRes, FitRes, Message, ParamHandle, Status
 from photon_b200.node_manager.node_manager_app import NodeManagerApp
 
 
 class ClientApp:
-    def __init__(self, cfg: Any, n_workers: int | None = None, node_id: int = 0) -> None:
+    def __init__(self, cfg: Any, n_workers: int | None = None, node_id: int = 0, devices: list[int] | None = None) -> None:
         self.cfg, self.node_id = cfg, node_id
-        self.nm = NodeManagerApp(cfg, n_workers=n_workers)
+        self.nm = NodeManagerApp(cfg, n_workers=n_workers, devices=devices)
         self.refresh_period = int(cfg["photon"].get("refresh_period", 50))
 
     @contextlib.contextmanager
@@ -31,7 +31,14 @@ class ClientApp:
 
     # ------------------------------------------------------------------------- handlers
     def set_parameters(self, msg: Message) -> Message:
-        self.nm.set_parameters(msg.content["parameters"])
+        """Broadcast sink: fetch the payload from the side channel (shm / npz object) when the message carries a
+        locator instead of the arrays, then publish it to this node's workers (ref: client_app.py:78-118)."""
+        payload = msg.content["parameters"]
+        if isinstance(payload, ParamHandle):
+            from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
+
+            payload = replace_parameters_in_recordset_with_remote(payload).data
+        self.nm.set_parameters(payload)
         return Message("query", {"broadcast": {"status": "OK"}}, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
 
     def train(self, msg: Message) -> Message:

@@ -51,6 +51,7 @@ class Centralized(_Strict):
 
 class Photon(_Strict):
     n_nodes: int = 1
+    topology: str = "spmd"   # spmd: one process per GPU + fused round transports; nodes: server → ClientApp → NodeManager → Workers
     refresh_period: int = 50
     checkpoint: bool = False
     restore_run_uuid: str | None = None
@@ -66,6 +67,13 @@ class Photon(_Strict):
     def _positive(cls, v: int) -> int:
         if v < 1:
             raise ValueError("must be >= 1")
+        return v
+
+    @field_validator("topology")
+    @classmethod
+    def _topology(cls, v: str) -> str:
+        if v not in ("spmd", "nodes"):
+            raise ValueError("photon.topology must be 'spmd' or 'nodes'")
         return v
 
 

@@ -68,7 +68,16 @@ def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: i
         digits = "".join(ch for ch in Path(str(st.local)).name if ch.isdigit())
         sid = int(digits) if digits else idx
     kw = {"vocab_size": int(synth_vocab)} if synth_vocab else {}   # never emit ids the (possibly resized) model cannot embed
-    return SyntheticC4(seq_len=seq_len, seed=seed, stream_id=sid, num_samples=synth_samples, **kw)
+    return SyntheticC4(seq_len=seq_len, seed=seed, stream_id=sid, num_samples=_synthetic_split_size(st.split, synth_samples), **kw)
+
+
+# a synthetic stand-in is as long as the split it replaces would be (documents of the truncated C4 splits; ref:
+# photon/dataset/constants/mc4.py:39-44,67-72) so that "evaluate on val_xxsmall" stays a seconds-long job
+_SYNTH_SPLIT_SAMPLES = {"val_xxsmall": 100, "val_xsmall": 3_000, "val_small": 10_000, "val": 1 << 14, "validation": 1 << 14}
+
+
+def _synthetic_split_size(split: str | None, default: int) -> int:
+    return min(default, _SYNTH_SPLIT_SAMPLES.get(str(split), default)) if split else default
 
 
 class StreamingTokenDataset:

@@ -34,7 +34,7 @@ from photon_b200.clients.trainer_utils import get_trainer_object, pick_device
 from photon_b200.clients.utils import get_initial_parameters
 from photon_b200.messages import ClientState, Code, EvaluateRes, FitRes, ParamHandle, Status
 from photon_b200.server.round_backends import RoundBackend, build_round_backend
-from photon_b200.server.server_util import static_assignment
+from photon_b200.server.server_util import spmd_node_ids, static_assignment
 from photon_b200.strategy.dispatcher import dispatch_strategy
 from photon_b200.train.trainer import Trainer
 from photon_b200.utils.flat import FlatLayout
@@ -122,6 +122,10 @@ class FederationRuntime:
                 raise AssertionError("initial-parameter layout differs from the trainer's")
             self.model_layout.from_ndarrays(flat[: self.model_layout.total], arrays)  # momenta planes start at zero
         return flat
+
+    def node_ids(self) -> list[int]:
+        """Logical nodes currently alive: one per client group of ranks (ref: Driver.get_node_ids)."""
+        return spmd_node_ids(self.group)[:: self.gpus_per_client]
 
     # ----------------------------------------------------------------------- sampling
     def sample_clients(self) -> list[int]:

@@ -38,11 +38,14 @@ from photon_b200.worker.worker import Worker
 
 class NodeManagerApp:
     def __init__(self, cfg: Any, n_workers: int | None = None, nm_uuid: str | None = None, max_retries: int = 2,
-                 poll_s: float = 0.1) -> None:
+                 poll_s: float = 0.1, devices: list[int] | None = None) -> None:
+        """``devices``: the GPUs this node owns (default: every visible one — the reference gives each node process its
+        own ``CUDA_VISIBLE_DEVICES``); one worker per device."""
         self.cfg_dict = to_container(cfg)
         self.nm_uuid = nm_uuid or f"nm-{uuid.uuid4().hex[:10]}"
         n_gpu = get_n_cuda_devices()
-        self.devices = list(range(n_gpu)) if n_gpu else None
+        self.devices = list(devices) if devices else (list(range(n_gpu)) if n_gpu else None)
+        n_gpu = len(self.devices) if self.devices else 0
         self.n_workers = int(n_workers or max(1, n_gpu))
         self.max_retries, self.poll_s = int(max_retries), float(poll_s)
         ctx = mp.get_context("spawn")

@@ -1,0 +1,167 @@
+"""Node-fleet runtime: the reference's process topology, in one box.
+
+``photon.topology: nodes`` runs the federation the way the reference deploys it:
+
+    server loop ──messages──▶ N × ClientApp ──▶ NodeManagerApp ──queues/shm──▶ one Worker process per device
+
+* the server owns no trainer: it holds the global model + strategy on the host, samples clients, and hands them to
+  nodes through the **work queue** (first ``n_nodes`` clients go out at once, every reply frees its node for the next
+  sampled client — virtual-client multiplexing; ref: photon/server/server_util.py:65-202);
+* every round starts with the **broadcast** QUERY to every node — one payload parked once on the parameter side
+  channel, one control message per node, acknowledged with ``{"broadcast": {"status": "OK"}}``
+  (ref: photon/server/broadcast_utils.py:60-201);
+* replies are folded into the running weighted sum **as they arrive** (streaming aggregation, one client payload alive
+  at a time; ref: photon/server/fit_utils.py:41-217, photon/strategy/aggregation.py:57-118);
+* all devices of a node collaborate on ONE client at a time (DDP / ZeRO over the node's workers), failed workers are
+  respawned and the client retried (ref: photon/node_manager/node_manager_app.py:405-592).
+
+The SPMD runtime (:mod:`photon_b200.federation`) is the fast path — one process per GPU and the fused NVLink round kernel.
+This one exists for parity with the reference's deployment shape (persistent worker processes that can be recycled every
+``photon.refresh_period`` rounds, host-side server) and as the oracle the SPMD path is compared against.
+"""
+from __future__ import annotations
+
+import time
+import uuid
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Any
+
+import torch
+
+from photon_b200.client_app import ClientApp
+from photon_b200.clients.utils import get_raw_model_parameters
+from photon_b200.federation import FederationRuntime
+from photon_b200.messages import Code, EvaluateRes, FitRes, Message, ParamHandle, Status
+from photon_b200.server.round_backends import CollectiveRoundBackend
+from photon_b200.server.s3_utils import release_remote_parameters, replace_remote_with_parameters_in_recordset
+from photon_b200.server.server_util import ClientScheduler, fit_or_evaluate_ins, wait_for_nodes_to_connect
+from photon_b200.utils.core import get_n_cuda_devices
+from photon_b200.utils.trace import tracer
+
+
+def split_devices(n_devices: int, n_nodes: int) -> list[list[int] | None]:
+    """Contiguous, near-equal device groups, one per node (``None`` = CPU node)."""
+    if n_devices <= 0:
+        return [None] * n_nodes
+    if n_nodes > n_devices:
+        raise ValueError(f"photon.n_nodes={n_nodes} exceeds the {n_devices} visible GPUs")
+    per, extra = divmod(n_devices, n_nodes)
+    out, lo = [], 0
+    for i in range(n_nodes):
+        hi = lo + per + (1 if i < extra else 0)
+        out.append(list(range(lo, hi)))
+        lo = hi
+    return out
+
+
+class NodeFleetRuntime(FederationRuntime):
+    """Same interface as :class:`FederationRuntime` (``run_server`` drives either), different plumbing."""
+
+    def __init__(self, cfg: Any, *, n_nodes: int | None = None, workers_per_node: int | None = None) -> None:
+        super().__init__(cfg, device=torch.device("cpu"), rank=0, world_size=1)
+        self.n_nodes = int(n_nodes or cfg["photon"].get("n_nodes", 1))
+        self.workers_per_node = workers_per_node
+        self.apps: list[ClientApp] = []
+        self._pool: ThreadPoolExecutor | None = None
+        self._uid = f"pb200_{uuid.uuid4().hex[:8]}"
+
+    # --------------------------------------------------------------------- bring-up
+    def build(self) -> None:
+        fl = self.cfg["fl"]
+        _, self.model_layout = get_raw_model_parameters(self.cfg)      # CPU model → names/shapes only (ref: node_manager_app.py:261-271)
+        self.layout = self.model_layout.stacked(("", "exp_avg/", "exp_avg_sq/")) if self.aggregate_momenta else self.model_layout
+        self.round_backend = CollectiveRoundBackend(self.layout, self.strategy, self.device)   # world 1 → plain host server
+        groups = split_devices(get_n_cuda_devices(), self.n_nodes)
+        for i, devs in enumerate(groups):
+            app = ClientApp(self.cfg, n_workers=self.workers_per_node or (len(devs) if devs else 1), node_id=i, devices=devs)
+            app.nm.create_and_start_workers()
+            self.apps.append(app)
+        self._pool = ThreadPoolExecutor(max_workers=self.n_nodes, thread_name_prefix="node")
+        wait_for_nodes_to_connect(self.n_nodes, self.node_ids, poll_s=0.05)
+        _ = fl
+
+    def node_ids(self) -> list[int]:
+        return [a.node_id for a in self.apps if a.nm.workers and all(w.is_alive() for w in a.nm.workers)]
+
+    # --------------------------------------------------------------------- broadcast (R2)
+    def broadcast_to_nodes(self) -> dict[str, Any]:
+        """One payload on the side channel, one QUERY per node, wait for every ack."""
+        assert self._pool is not None and self.round_backend is not None
+        t0 = time.time()
+        handle = replace_remote_with_parameters_in_recordset(
+            ParamHandle("inline", self.round_backend.global_params()), {"shm": True}, endpoint_id=f"{self._uid}_bcast", layout=self.layout)
+        try:
+            futs = [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": handle}, node_id=app.node_id))
+                    for app in self.apps]
+            acks = [f.result() for f in futs]
+        finally:
+            release_remote_parameters(handle)
+        bad = [a.error for a in acks if a.error or a.content != {"broadcast": {"status": "OK"}}]
+        if bad:
+            raise RuntimeError(f"broadcast not acknowledged by {len(bad)} node(s): {bad[:2]}")
+        return {"server/broadcast_time": time.time() - t0}
+
+    # ---------------------------------------------------------------------------- fit
+    def run_clients_fit(self, server_round: int, sampled: list[int]) -> list[FitRes]:
+        assert self._pool is not None and self.round_backend is not None
+        rb = self.round_backend
+        rb.begin_round()
+        self.timings.update(self.broadcast_to_nodes())
+        pending: dict[int, Future[Message]] = {}
+        by_id = {a.node_id: a for a in self.apps}
+
+        def dispatch(node: int, cid: int) -> None:
+            if self._should_fail(server_round, cid):
+                f: Future[Message] = Future()
+                f.set_result(Message("train", [FitRes(Status(Code.FAILED, f"fault injection: client {cid} dropped in round {server_round}"),
+                                                      None, 0, {}, cid)], node_id=node))
+                pending[node] = f
+                return
+            fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
+            msg = fit_or_evaluate_ins("train", server_round, [cid], self.client_states, self.server_steps_cumulative, {cid: fc.to_wire()})
+            msg.node_id = node
+            pending[node] = self._pool.submit(by_id[node].handle, msg)
+
+        def poll() -> list[tuple[int, int, Message]]:
+            done = [(n, f) for n, f in pending.items() if f.done()]
+            out = []
+            for n, f in done:
+                del pending[n]
+                rep = f.result()
+                cid = rep.content[0].cid if rep.content else -1
+                out.append((n, int(cid if cid is not None else -1), rep))
+            return out
+
+        results: list[FitRes] = []
+        t0 = time.time()
+        with tracer().span("fit_clients", cat="server", server_round=server_round):
+            for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps], dispatch, poll, poll_s=0.01):
+                for res in reply.content or [FitRes(Status(Code.FAILED, reply.error or "empty reply"), None, 0, {}, cid)]:
+                    if res.status.code == Code.OK and res.parameters is not None:
+                        flat = torch.zeros(self.layout.total, dtype=torch.float32)
+                        self.layout.from_ndarrays(flat, res.parameters.data)   # streaming: fold in, then drop the payload
+                        rb.add_client(flat, res.num_examples)
+                        res = FitRes(res.status, ParamHandle(kind=rb.name), res.num_examples, res.metrics, res.cid)
+                    results.append(res)
+        self.timings["node_training_time_s"] = time.time() - t0
+        return results
+
+    # ----------------------------------------------------------------------- evaluate
+    def run_clients_evaluate(self, server_round: int, sampled: list[int]) -> list[EvaluateRes]:
+        self.broadcast_to_nodes()
+        per = {int(cid): self.eval_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative).to_wire() for cid in sampled}
+        msg = fit_or_evaluate_ins("evaluate", server_round, list(per), self.client_states, self.server_steps_cumulative, per)
+        rep = self.apps[0].handle(msg)     # the reference evaluates on ONE node (client id 0, all streams concatenated)
+        res = rep.content
+        return [res] if isinstance(res, EvaluateRes) else [EvaluateRes(Status(Code.FAILED, rep.error or "no result"), 0.0, 0, {})]
+
+    # --------------------------------------------------------------------------- close
+    def close(self) -> None:
+        for app in self.apps:
+            app.nm.close()
+        self.apps = []
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        if self.round_backend is not None:
+            self.round_backend.close()

@@ -26,7 +26,7 @@ from photon_b200.federation import FederationRuntime
 from photon_b200.server.evaluate_utils import evaluate_round
 from photon_b200.server.fit_utils import fit_round
 from photon_b200.server.init_utils import initialize_round, resume_from_round, server_state_dict
-from photon_b200.server.server_util import spmd_node_ids, wait_for_nodes_to_connect
+from photon_b200.server.server_util import wait_for_nodes_to_connect
 from photon_b200.utils.core import wandb_init
 from photon_b200.utils.trace import tracer
 from photon_b200.wandb_history import WandbHistory
@@ -41,6 +41,10 @@ def _store_for(cfg: Any) -> CheckpointStore | None:
 
 def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int | None = None) -> WandbHistory:
     own = runtime is None
+    if runtime is None and str(cfg["photon"].get("topology", "spmd")) == "nodes":
+        from photon_b200.server.fleet import NodeFleetRuntime
+
+        runtime = NodeFleetRuntime(cfg)
     if runtime is None:
         device = pick_device(int(os.environ.get("LOCAL_RANK", "0")))
         rank, world = initialize_dist(device)
@@ -67,7 +71,7 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
     else:
         initialize_round(runtime, store, history)
 
-    wait_for_nodes_to_connect(runtime.n_nodes, lambda: spmd_node_ids(runtime.group)[:: runtime.gpus_per_client], poll_s=0.0)
+    wait_for_nodes_to_connect(runtime.n_nodes, runtime.node_ids, poll_s=0.0)
     eval_period = fl.get("eval_period")
     if eval_period and start_round == 0:
         loss, em = evaluate_round(runtime, 0)
@@ -78,11 +82,11 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
     total = int(fl["n_rounds"]) if n_rounds is None else start_round + n_rounds
     for server_round in range(start_round + 1, total + 1):
         t_round = time.time()
-        node_ids = spmd_node_ids(runtime.group)                    # health check (ref: server_app.py:285)
+        node_ids = runtime.node_ids()                              # health check (ref: server_app.py:285)
         sampled = runtime.sample_clients()
         with tracer().span("fit_round", cat="server", server_round=server_round, clients=str(sampled)):
             metrics = fit_round(runtime, server_round, sampled)
-        metrics["server/n_nodes"] = len(node_ids) // runtime.gpus_per_client
+        metrics["server/n_nodes"] = len(node_ids)
         if runtime.rank == 0:
             history.add_metrics_distributed_fit(server_round, metrics)
         if eval_period and server_round % int(eval_period) == 0:

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import pickle
 import sys
+import threading
 from dataclasses import asdict, dataclass, field
 from multiprocessing import shared_memory
 from typing import Any, Sequence
@@ -26,13 +27,20 @@ import numpy as np
 from photon_b200.shm import constants as C
 
 
+# The resource tracker keeps a SET of names per process tree: two threads attaching the same segment concurrently
+# would interleave register/register/unregister/unregister and the second unregister raises inside the tracker.
+# Attach + untrack (and open + unlink) therefore run under one process-wide lock.
+_TRACKER_LOCK = threading.RLock()
+
+
 def _open(name: str, create: bool = False, size: int = 0, untrack: bool = True) -> shared_memory.SharedMemory:
     kw: dict[str, Any] = {}
     if sys.version_info >= (3, 13):
         kw["track"] = False
-    shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0, **kw)
-    if sys.version_info < (3, 13) and untrack:
-        remove_shm_from_resource_tracker(shm)
+    with _TRACKER_LOCK:
+        shm = shared_memory.SharedMemory(name=name, create=create, size=size if create else 0, **kw)
+        if sys.version_info < (3, 13) and untrack:
+            remove_shm_from_resource_tracker(shm)
     return shm
 
 
@@ -57,15 +65,16 @@ def shm_exists(name: str) -> bool:
 
 
 def unlink_quietly(name: str) -> None:
-    try:
-        s = _open(name, untrack=False)  # stays registered so that unlink()'s unregister is balanced
-    except FileNotFoundError:
-        return
-    s.close()
-    try:
-        s.unlink()
-    except FileNotFoundError:
-        pass
+    with _TRACKER_LOCK:
+        try:
+            s = _open(name, untrack=False)  # stays registered so that unlink()'s unregister is balanced
+        except FileNotFoundError:
+            return
+        s.close()
+        try:
+            s.unlink()
+        except FileNotFoundError:
+            pass
 
 
 @dataclass

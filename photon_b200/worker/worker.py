@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import multiprocessing as mp
 import os
+import queue
 import time
 import traceback
 import uuid
@@ -93,7 +94,16 @@ class Worker(mp.get_context("spawn").Process):  # type: ignore[misc,name-defined
     # ------------------------------------------------------------------------- loop
     def run(self) -> None:
         os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 2) // max(1, self.n_workers))))
-        for task in iter(self.task_queue.get, None):
+        parent = os.getppid()
+        while True:
+            try:
+                task = self.task_queue.get(timeout=2.0)
+            except queue.Empty:
+                if os.getppid() != parent:   # the node manager is gone (killed server): do not linger as an orphan
+                    return
+                continue
+            if task is None:
+                return
             cid, kind = task
             try:
                 self.process_task(int(cid), kind)

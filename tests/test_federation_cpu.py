@@ -270,3 +270,30 @@ def test_centralised_warm_starts_and_federation_restores(tmp_path, monkeypatch):
     r1a = load_model_parameters_from_file(store.round_dir("fA", 1) / "current_server_parameters.npz")
     r1b = load_model_parameters_from_file(store.round_dir("fB", 1) / "current_server_parameters.npz")
     assert all(np.array_equal(x, y) for x, y in zip(r1a, r1b))
+
+
+def test_node_fleet_topology_matches_spmd_runtime(tmp_path):
+    """``photon.topology=nodes``: server → 2 ClientApps → NodeManagers → worker processes, work queue over 3 sampled
+    clients, broadcast over the shm side channel, streaming aggregation — and the same global model as the SPMD runtime."""
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server.fleet import NodeFleetRuntime, split_devices
+    from photon_b200.server_app import run_server
+
+    assert split_devices(8, 3) == [[0, 1, 2], [3, 4, 5], [6, 7]] and split_devices(0, 2) == [None, None]
+    common = ["fl.n_rounds=2", "fl.n_clients_per_round=3", "llm_config.save_folder=null", "fl.strategy_name=fedavg"]
+    cfg = _cfg(tmp_path / "a", "run_uuid=fleet", "photon.topology=nodes", "photon.n_nodes=2", *common)
+    rt = NodeFleetRuntime(cfg)
+    try:
+        h = run_server(cfg, runtime=rt)
+        fit = h.metrics_distributed_fit
+        assert [v for _, v in fit["server/n_failures"]] == [0, 0] and [v for _, v in fit["server/n_nodes"]] == [2, 2]
+        assert len(h.losses_distributed) == 3 and "node_training_time_s" in fit
+        x_nodes = rt.round_backend.global_params().clone()
+    finally:
+        rt.close()
+    cfg2 = _cfg(tmp_path / "b", "run_uuid=spmd", *common)
+    rt2 = FederationRuntime(cfg2, device=torch.device("cpu"), rank=0, world_size=1)
+    run_server(cfg2, runtime=rt2)
+    x_spmd = rt2.round_backend.global_params()
+    assert torch.allclose(x_nodes, x_spmd, atol=1e-5), float((x_nodes - x_spmd).abs().max())
+    rt2.close()
