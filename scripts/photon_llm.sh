@@ -16,5 +16,12 @@ if [ "$N_GPUS" -eq 0 ]; then  # CPU plumbing mode (ref README.md:82-84)
 else
   PHOTON_CONFIG="$PHOTON_CONFIG photon.comm_stack.shm=false photon.comm_stack.nvl=true"
 fi
-resolve $PHOTON_CONFIG
-launch photon_b200.server_app 2>&1 | tee "$PHOTON_SAVE_PATH/server.log"
+# TOPOLOGY=nodes: the reference's process shape — one host-side server driving N_NODES node managers, each with one
+# persistent worker process per GPU of its share (no torchrun); default spmd = one process per GPU + fused round kernels
+if [ "${TOPOLOGY:-spmd}" = "nodes" ]; then
+  resolve $PHOTON_CONFIG photon.topology=nodes photon.n_nodes="${N_NODES:-1}" photon.comm_stack.nvl=false photon.comm_stack.shm=true
+  python -m photon_b200.server_app 2>&1 | tee "$PHOTON_SAVE_PATH/server.log"
+else
+  resolve $PHOTON_CONFIG
+  launch photon_b200.server_app 2>&1 | tee "$PHOTON_SAVE_PATH/server.log"
+fi

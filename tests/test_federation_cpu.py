@@ -297,3 +297,18 @@ def test_node_fleet_topology_matches_spmd_runtime(tmp_path):
     x_spmd = rt2.round_backend.global_params()
     assert torch.allclose(x_nodes, x_spmd, atol=1e-5), float((x_nodes - x_spmd).abs().max())
     rt2.close()
+
+
+def test_node_fleet_two_workers_collaborate_on_one_client(tmp_path):
+    """All workers of a node train ONE client together (intra-client DDP over gloo here, NCCL/NVLink on GPUs)."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    cfg = _cfg(tmp_path, "run_uuid=f2", "photon.topology=nodes", "fl.n_rounds=1", "fl.n_clients_per_round=2", "llm_config.save_folder=null")
+    rt = NodeFleetRuntime(cfg, n_nodes=1, workers_per_node=2)
+    try:
+        h = run_server(cfg, runtime=rt)
+        assert h.metrics_distributed_fit["server/n_failures"] == [(1, 0)] and len(h.losses_distributed) == 2
+        assert len(rt.apps[0].nm.workers) == 2 and all(w.is_alive() for w in rt.apps[0].nm.workers)
+    finally:
+        rt.close()
