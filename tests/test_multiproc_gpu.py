@@ -72,19 +72,25 @@ def test_spmd_federation_nvl_and_two_gpus_per_client(tmp_path):
                                  ('nvl2', ['photon.comm_stack.shm=false', 'photon.comm_stack.nvl=true'], 2)):
             cfg = compose(TINY + ['run_uuid=fed-' + name, 'fl.n_total_clients=4', 'fl.n_clients_per_round=4', 'fl.n_rounds=2',
                                   'fl.strategy_name=fedadam', 'fl.strategy_kwargs={eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}',
-                                  'dataset.train.root_local=synthetic://c'] + extra)
+                                  'fl.use_noise_scale_metric=true', 'dataset.train.root_local=synthetic://c'] + extra)
             rt = FederationRuntime(cfg, device=dev, rank=rank, world_size=2, gpus_per_client=gpc)
             h = run_server(cfg, runtime=rt)
             x = rt.round_backend.global_params().clone()
             ref = x.clone(); dist.broadcast(ref, src=0)
             assert torch.equal(ref, x), name + ': ranks hold different global models'
             finals[name] = x
-            if rank == 0: assert h.latest('server/n_failures') == 0, (name, h.metrics_distributed_fit)
+            if rank == 0:
+                assert h.latest('server/n_failures') == 0, (name, h.metrics_distributed_fit)
+                fit = h.metrics_distributed_fit    # kernel by-product norms + the noise-scale estimate reach the history on every transport
+                assert len(fit['server/l2_norm_pseudo_gradient']) == 2 and fit['noise_scale/b_big'][-1][1] == 4, name
+                finals[name + '/pg'] = fit['server/l2_norm_pseudo_gradient'][-1][1]
             rt.close()
         rel = ((finals['nvl'] - finals['ray']).norm() / finals['ray'].norm()).item()
         assert rel < 1e-3, rel          # fused NVLink round == NCCL all-reduce baseline
         assert torch.isfinite(finals['nvl2']).all()
-        if rank == 0: print('RESULT_OK', rel)
+        if rank == 0:
+            assert abs(finals['nvl/pg'] - finals['ray/pg']) < 2e-2 * finals['ray/pg'], (finals['nvl/pg'], finals['ray/pg'])
+            print('RESULT_OK', rel)
     """, 29543)
 
 
