@@ -36,6 +36,27 @@ def set_wte_parameters(trainer: Trainer, wte: np.ndarray) -> None:
     set_wte_parameters_to_trainer(trainer, wte)
 
 
+def resume_centralised(trainer: Trainer, train_cfg: Any) -> Path | None:
+    """``llm_config.load_path`` (explicit, may contain ``{rank}``; ``load_ignore_keys`` globs honoured) or — Composer's
+    ``autoresume`` — the ``latest-rank{R}.pt`` of the run's own ``save_folder``. Autoresume defaults to ON when a save
+    folder is set and ``save_overwrite`` is off, like the reference (ref: clients/trainer_utils.py:437-450). Takes
+    precedence over ``pretrained_model_path`` because it restores optimizer, clock and data position too."""
+    load_path = train_cfg.get("load_path")
+    if load_path:
+        path = Path(str(load_path).format(rank=trainer.rank))
+        trainer.load_checkpoint(path, list(train_cfg.get("load_ignore_keys") or []))
+        return path
+    folder = trainer.save_folder
+    auto = bool(train_cfg.get("autoresume")) or (folder is not None and not trainer.save_overwrite)
+    if auto and folder is not None:
+        latest = Path(str(folder)) / f"latest-rank{trainer.rank}.pt"
+        if latest.exists():
+            trainer.load_checkpoint(latest)
+            print(f"[centralised_train] autoresume from {latest} at batch {trainer.state.timestamp.batch}")
+            return latest
+    return None
+
+
 def dump_checkpoint_npz(trainer: Trainer, run_uuid: str, out_dir: str | Path = ".") -> Path:
     """``{run_uuid}-{n_steps}-checkpoint.npz`` with arr_i in sorted-name order (ref: :139-166)."""
     st = trainer.state
@@ -64,7 +85,7 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
             from photon_b200.parallel.ddp import NcclGradComm
 
             grad_comm = NcclGradComm()
-    trainer, _ = get_trainer_object(cfg, cc.stream_id, log_name="_centralised", device=device, rank=rank, world_size=world_size,
+    trainer, train_cfg = get_trainer_object(cfg, cc.stream_id, log_name="_centralised", device=device, rank=rank, world_size=world_size,
                                     grad_comm=grad_comm, split_eval=cc.split_eval, use_unigram_metrics=cc.use_unigram_metrics,
                                     allow_unigram_metrics_failures=cc.allow_unigram_metrics_failures, frozen_layers=cc.frozen_layers,
                                     unfrozen_layers=cc.unfrozen_layers, resize_vocab=cc.resize_vocab)
@@ -84,6 +105,7 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
         else:
             raise ValueError(f"wte_parameters_path holds {len(donor)} arrays; expected a full model ({len(names)}) or the embedding alone")
         set_wte_parameters(trainer, wte)
+    resume_centralised(trainer, train_cfg)
     if world_size > 1:  # identical start on every rank
         torch.distributed.broadcast(trainer.state.flat.params, src=0)
         trainer.state.backend.params_updated()

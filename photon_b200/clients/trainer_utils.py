@@ -81,6 +81,30 @@ def _with_profiler(t: Any) -> dict[str, Any]:
     return cbs
 
 
+def apply_runtime_env(llm_cfg: Any) -> dict[str, str]:
+    """Process-level knobs of ``llm_config`` that must be in the environment before CUDA / the process group come up
+    (ref: trainer_utils.py:1278-1298): caching-allocator configuration (``max_split_size_mb``, ``expandable_segments``),
+    lazy CUDA module loading, python log level. Returns what was set."""
+    import logging
+
+    out: dict[str, str] = {}
+    alloc = []
+    if llm_cfg.get("max_split_size_mb") is not None:
+        alloc.append(f"max_split_size_mb:{int(llm_cfg['max_split_size_mb'])}")
+    if llm_cfg.get("expandable_segments"):
+        alloc.append("expandable_segments:True")
+    if alloc:
+        out["PYTORCH_CUDA_ALLOC_CONF"] = ",".join(alloc)
+    if llm_cfg.get("cuda_load_lazy"):
+        out["CUDA_MODULE_LOADING"] = "LAZY"
+    os.environ.update(out)
+    level = llm_cfg.get("python_log_level")
+    if level:
+        logging.getLogger("photon_b200").setLevel(str(level).upper())
+        out["python_log_level"] = str(level).upper()
+    return out
+
+
 def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", device: torch.device | None = None,
                        rank: int | None = None, world_size: int | None = None, process_group: Any = None,
                        grad_comm: Any = None, split_eval: bool = False, use_unigram_metrics: bool = False,
@@ -88,10 +112,13 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                        unfrozen_layers: list[str] | None = None, resize_vocab: int | None = None,
                        no_data: bool = False, backend: Any = None) -> tuple[Trainer, Any]:
     """Returns ``(trainer, train_cfg)``. ``cid=None`` = all streams (centralised / evaluation)."""
+    apply_runtime_env(cfg["llm_config"])
     device = device or pick_device(int(os.environ.get("LOCAL_RANK", "0")))
     if rank is None or world_size is None:
-        rank, world_size = initialize_dist(device)
+        rank, world_size = initialize_dist(device, timeout_s=float(cfg["llm_config"].get("dist_timeout") or 600.0))
     t, evals = _prepare_train_cfg(cfg, cid, split_eval, world_size, log_name)
+    if t.get("compile_config"):
+        print("[trainer] compile_config is ignored: the GPU step is an explicit kernel schedule replayed as a CUDA graph")
     if t.get("tp_config"):
         raise ValueError("tp_config must be null (TP is plumbing-only in the reference)")
     model_node = dict(t["model"])
@@ -128,7 +155,8 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
     tr = Trainer(mcfg, optimizer_cfg=dict(t["optimizer"]), scheduler_cfg=dict(t.get("scheduler") or {}),
                  train_loader=train_loader, eval_loaders=eval_loaders, global_train_batch_size=gbs,
                  device_train_microbatch_size=t.get("device_train_microbatch_size", "auto"),
-                 device_eval_batch_size=eval_bs, precision=precision, max_duration=t.get("max_duration"),
+                 device_eval_batch_size=eval_bs, device_eval_microbatch_size=t.get("device_eval_microbatch_size"),
+                 precision=precision, max_duration=t.get("max_duration"),
                  grad_clip_norm=_grad_clip(t), callbacks=build_callbacks(_with_profiler(t)), loggers=loggers,
                  save_folder=t.get("save_folder"), save_interval=t.get("save_interval"),
                  save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),

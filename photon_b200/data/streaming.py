@@ -177,6 +177,11 @@ class TokenLoader:
         self.dataset, self.batch_size, self.drop_last = dataset, int(batch_size), bool(drop_last)
         self.num_workers, self.prefetch = int(num_workers), int(prefetch)
         self.pin = torch.cuda.is_available() if pin_memory is None else pin_memory
+        # position of the CONSUMER (the trainer), not of the producer: the prefetch thread runs ahead of what has been
+        # trained on, so a checkpoint must not store the dataset's own cursor (mosaicml-streaming derives its
+        # ``state_dict`` from the number of samples the trainer has seen for the same reason)
+        self._live: tuple[int, int] | None = None   # (epoch, sample_in_epoch) at the start of the running iterator
+        self._handed_out = 0                         # batches the consumer has received from it
 
     def __len__(self) -> int:
         n = self.dataset.samples_per_epoch()
@@ -199,6 +204,20 @@ class TokenLoader:
             yield self._collate(rows)
 
     def __iter__(self) -> Iterator[dict[str, torch.Tensor]]:
+        self._live, self._handed_out = (self.dataset.epoch, self.dataset.sample_in_epoch), 0
+        it = self._iter_batches()
+        try:
+            for batch in it:
+                self._handed_out += 1
+                yield batch
+        finally:
+            it.close()   # stops and joins the prefetch thread before the cursor is rewound
+            # exhausted (the dataset already points at the next epoch) or abandoned: its own cursor is authoritative again
+            if self._live is not None and self.dataset.epoch == self._live[0]:
+                self.dataset.sample_in_epoch = self._live[1] + self._handed_out * self.batch_size   # drop what was only prefetched
+            self._live = None
+
+    def _iter_batches(self) -> Iterator[dict[str, torch.Tensor]]:
         if self.num_workers <= 0:
             yield from self._gen()
             return
@@ -232,12 +251,17 @@ class TokenLoader:
                 yield item
         finally:
             stop.set()
+            th.join(timeout=5.0)
 
     def state_dict(self) -> dict[str, int]:
-        return self.dataset.state_dict()
+        sd = self.dataset.state_dict()
+        if self._live is not None:
+            sd["epoch"], sd["sample_in_epoch"] = self._live[0], self._live[1] + self._handed_out * self.batch_size
+        return sd
 
     def load_state_dict(self, sd: dict[str, int]) -> None:
         self.dataset.load_state_dict(sd)
+        self._live = None
 
 
 def build_text_loader(loader_cfg: dict[str, Any], batch_size: int, rank: int = 0, world_size: int = 1,

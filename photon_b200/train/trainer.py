@@ -114,7 +114,8 @@ class Trainer:
                  seed: int = 17, run_name: str = "run", use_unigram_metrics: bool = False,
                  unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
-                 backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False) -> None:
+                 backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False,
+                 device_eval_microbatch_size: int | str | None = None) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -127,6 +128,8 @@ class Trainer:
         self.microbatch = device_train_microbatch_size
         self._auto_mb = self.device_batch if device_train_microbatch_size == "auto" else None
         self.device_eval_batch_size = device_eval_batch_size or self.device_batch
+        self.eval_microbatch: int | str | None = device_eval_microbatch_size
+        self._eval_mb_auto = device_eval_microbatch_size == "auto"
         self.grad_clip_norm = grad_clip_norm
         self.train_loader, self.eval_loaders = train_loader, dict(eval_loaders or {})
         self.callbacks, self.loggers = list(callbacks), list(loggers) or [InMemoryLogger()]
@@ -382,8 +385,7 @@ class Trainer:
                 if 0 <= limit <= i:
                     break
                 ids = self._to_device(batch["input_ids"])
-                stats = st.backend.eval_stats(ids)
-                stats = {k: float(v) for k, v in stats.items()}
+                stats = self._eval_batch_stats(ids)
                 for m in metrics.values():
                     m.update(stats)
                 st.eval_timestamp.advance_batch(samples=ids.shape[0] * self.world_size,
@@ -394,6 +396,27 @@ class Trainer:
         self._emit("eval_end")
         self._flush_logs()
         return vals
+
+    def _eval_batch_stats(self, ids: torch.Tensor) -> dict[str, float]:
+        """Sum-type statistics of one eval batch, computed in ``device_eval_microbatch_size`` slices (``auto`` halves the
+        slice on an out-of-memory error and remembers the size that worked — same policy as the train microbatch)."""
+        B = ids.shape[0]
+        while True:
+            mb = self.eval_microbatch
+            mb = B if mb in (None, "auto") else max(1, min(int(mb), B))
+            try:
+                total: dict[str, float] = {}
+                for lo in range(0, B, mb):
+                    for k, v in self.state.backend.eval_stats(ids[lo:lo + mb]).items():
+                        total[k] = total.get(k, 0.0) + float(v)
+                return total
+            except RuntimeError as e:
+                if not self._eval_mb_auto or not _is_oom(e) or mb == 1:
+                    raise
+                if self.device.type == "cuda":
+                    torch.cuda.empty_cache()
+                self.eval_microbatch = max(1, mb // 2)
+                print(f"[trainer] CUDA OOM at eval microbatch {mb}; retrying with {self.eval_microbatch}")
 
     # --------------------------------------------------------------- checkpoints
     def state_dict(self) -> dict[str, Any]:

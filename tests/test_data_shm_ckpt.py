@@ -178,3 +178,30 @@ def test_streaming_shm_cleanup_removes_only_our_segments():
     finally:
         other.close()
         other.unlink()
+
+
+def test_loader_state_tracks_the_consumer_not_the_prefetch_thread():
+    """With a prefetch thread the dataset cursor runs ahead of what was trained on; the checkpointed position must be the
+    consumer's, so a resumed loader continues with exactly the next unseen batch."""
+    from photon_b200.data.streaming import Stream, StreamingTokenDataset, TokenLoader
+
+    def make():
+        ds = StreamingTokenDataset([Stream(local="synthetic://7", name="s")], seq_len=8, shuffle=True, shuffle_seed=3, synthetic_samples=64)
+        return TokenLoader(ds, batch_size=4, num_workers=1, prefetch=4, pin_memory=False)
+
+    ref = [b["input_ids"].clone() for b in make()]
+    assert len(ref) == 16
+    a = make()
+    it = iter(a)
+    seen = [next(it)["input_ids"].clone() for _ in range(5)]
+    import time
+
+    time.sleep(0.3)  # let the prefetcher run ahead
+    sd = a.state_dict()
+    assert sd["sample_in_epoch"] == 20 and a.dataset.sample_in_epoch > 20
+    b = make()
+    b.load_state_dict(sd)
+    rest = [x["input_ids"] for x in b]
+    assert len(rest) == 11 and all(torch.equal(x, y) for x, y in zip(seen + rest, ref))
+    it.close()
+    assert a.dataset.sample_in_epoch == 20 and a.state_dict()["sample_in_epoch"] == 20   # abandoned iterator: prefetched samples are not lost

@@ -312,3 +312,23 @@ def test_node_fleet_two_workers_collaborate_on_one_client(tmp_path):
         assert len(rt.apps[0].nm.workers) == 2 and all(w.is_alive() for w in rt.apps[0].nm.workers)
     finally:
         rt.close()
+
+
+def test_centralised_autoresume_continues_from_latest_checkpoint(tmp_path, monkeypatch):
+    """A restarted centralised run picks up ``latest-rank0.pt`` (weights, optimizer, clock, data position) and only trains
+    the remaining batches; the result equals an uninterrupted run (ref: Composer autoresume, trainer_utils.py:437-450)."""
+    from photon_b200.centralised_train import run_centralised
+
+    monkeypatch.chdir(tmp_path)
+    cen = [a for a in TINY if not a.startswith(("fl.", "llm_config.local_steps"))] + [
+        f"photon.saving_path={tmp_path}", "llm_config.save_interval=1ba", "llm_config.scheduler.schedulers.lr.t_max=5ba"]
+    a = run_centralised(compose(cen + ["run_uuid=ar", f"llm_config.save_folder={tmp_path}/ar", "llm_config.max_duration=3ba"]), device=torch.device("cpu"))
+    assert a.state.timestamp.batch == 3
+    a.close()
+    b = run_centralised(compose(cen + ["run_uuid=ar", f"llm_config.save_folder={tmp_path}/ar", "llm_config.max_duration=5ba"]), device=torch.device("cpu"))
+    assert b.state.timestamp.batch == 5 and b.fit_start_batch == 3      # resumed at 3, trained 2
+    resumed = b.state.flat.params.clone()
+    b.close()
+    c = run_centralised(compose(cen + ["run_uuid=one", f"llm_config.save_folder={tmp_path}/one", "llm_config.max_duration=5ba"]), device=torch.device("cpu"))
+    assert torch.allclose(resumed, c.state.flat.params, atol=1e-6), float((resumed - c.state.flat.params).abs().max())
+    c.close()

@@ -152,3 +152,40 @@ def test_virtual_client_work_queue_hands_next_client_to_first_free_node():
     assert all(r == f"ok{n}" for n, _, r in got)
     sa = static_assignment(list(range(7)), [10, 11, 12])
     assert sorted(c for v in sa.values() for c in v) == list(range(7)) and max(map(len, sa.values())) == 3
+
+
+def test_eval_microbatch_auto_and_runtime_env(monkeypatch):
+    """``device_eval_microbatch_size`` (int | auto) slices eval batches without changing the metrics; allocator / lazy-loading
+    knobs of ``llm_config`` land in the environment (ref: trainer_utils.py:1278-1298)."""
+    from photon_b200.clients.trainer_utils import apply_runtime_env
+
+    ev = {"eval": _Loader(8)}
+    whole = _trainer(eval_loaders=ev, eval_subset_num_batches=2)
+    want = whole.eval()
+    sliced = _trainer(eval_loaders=ev, eval_subset_num_batches=2, device_eval_microbatch_size=3)
+    got = sliced.eval()
+    assert want.keys() == got.keys() and all(abs(want[k] - got[k]) < 1e-5 * max(1.0, abs(want[k])) for k in want)
+    auto = _trainer(eval_loaders=ev, eval_subset_num_batches=2, device_eval_microbatch_size="auto")
+    real = auto.state.backend.eval_stats
+    seen = []
+
+    def flaky(ids):
+        seen.append(ids.shape[0])
+        if ids.shape[0] > 2:
+            raise RuntimeError("CUDA out of memory.")
+        return real(ids)
+
+    auto.state.backend.eval_stats = flaky
+    got = auto.eval()
+    assert auto.eval_microbatch == 2 and seen[:2] == [8, 4] and all(abs(want[k] - got[k]) < 1e-5 * max(1.0, abs(want[k])) for k in want)
+    for t in (whole, sliced, auto):
+        t.close()
+    for k in ("PYTORCH_CUDA_ALLOC_CONF", "CUDA_MODULE_LOADING"):
+        monkeypatch.delenv(k, raising=False)
+    out = apply_runtime_env({"max_split_size_mb": 512, "expandable_segments": True, "cuda_load_lazy": True, "python_log_level": "debug"})
+    assert out["PYTORCH_CUDA_ALLOC_CONF"] == "max_split_size_mb:512,expandable_segments:True" and out["CUDA_MODULE_LOADING"] == "LAZY"
+    import os
+
+    assert os.environ["PYTORCH_CUDA_ALLOC_CONF"] == out["PYTORCH_CUDA_ALLOC_CONF"]
+    monkeypatch.delenv("PYTORCH_CUDA_ALLOC_CONF"), monkeypatch.delenv("CUDA_MODULE_LOADING")
+    assert apply_runtime_env({}) == {}
