@@ -55,6 +55,13 @@ def test_federated_rounds_checkpoint_and_resume(tmp_path):
     rt = FederationRuntime(cfg2, device=torch.device("cpu"), rank=0, world_size=1)
     rt.replay_sampling(2)
     assert [rt.sample_clients(), rt.sample_clients()] == expect[2:]
+    # and the resumed federation is bit-identical to one that never stopped (server moments, client clocks, data positions)
+    cfg3 = _cfg(tmp_path / "straight", "run_uuid=r1", "photon.checkpoint=true", "fl.n_rounds=4", "fl.strategy_name=fedadam",
+                "fl.strategy_kwargs={eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}")
+    run_server(cfg3)
+    a = np.load(store.round_dir("r1", 4) / "current_server_parameters.npz")
+    b = np.load(CheckpointStore(tmp_path / "straight", "checkpoints").round_dir("r1", 4) / "current_server_parameters.npz")
+    assert all(np.array_equal(a[k], b[k]) for k in a.files)
 
 
 def test_fault_injection_accept_and_ignore(tmp_path):
