@@ -67,7 +67,6 @@ class NodeFleetRuntime(FederationRuntime):
 
     # --------------------------------------------------------------------- bring-up
     def build(self) -> None:
-        fl = self.cfg["fl"]
         _, self.model_layout = get_raw_model_parameters(self.cfg)      # CPU model → names/shapes only (ref: node_manager_app.py:261-271)
         self.layout = self.model_layout.stacked(("", "exp_avg/", "exp_avg_sq/")) if self.aggregate_momenta else self.model_layout
         self.round_backend = CollectiveRoundBackend(self.layout, self.strategy, self.device)   # world 1 → plain host server
@@ -77,8 +76,7 @@ class NodeFleetRuntime(FederationRuntime):
             app.nm.create_and_start_workers()
             self.apps.append(app)
         self._pool = ThreadPoolExecutor(max_workers=self.n_nodes, thread_name_prefix="node")
-        wait_for_nodes_to_connect(self.n_nodes, self.node_ids, poll_s=0.05)
-        _ = fl
+        wait_for_nodes_to_connect(self.n_nodes, self.node_ids, poll_s=0.05, timeout_s=300.0)
 
     def node_ids(self) -> list[int]:
         return [a.node_id for a in self.apps if a.nm.workers and all(w.is_alive() for w in a.nm.workers)]
