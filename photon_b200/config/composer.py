@@ -434,5 +434,17 @@ def compose(overrides: Iterable[str] = (), config_name: str = "base",
     if validate:
         from photon_b200.config.schema import validate_config
 
-        validate_config(cfg)
+        model = validate_config(cfg)
+        # keys the schema knows but the YAML tree does not spell out (e.g. a reference user's own conf/ directory, which has no
+        # ``photon.comm_stack.nvl`` / ``photon.topology`` / ``kernels``) are materialised with their defaults, so the dumped
+        # config.yaml is complete and downstream code never has to guess
+        _fill_defaults(cfg, model.model_dump(mode="json", exclude={"llm_config", "dataset", "eval_gauntlet_config", "icl_tasks_config"}))
     return cfg
+
+
+def _fill_defaults(node: Any, defaults: dict[str, Any]) -> None:
+    for k, v in defaults.items():
+        if k not in node:
+            node[k] = ConfigNode(v) if isinstance(v, dict) else v
+        elif isinstance(v, dict) and isinstance(node[k], dict):
+            _fill_defaults(node[k], v)

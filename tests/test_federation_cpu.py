@@ -339,3 +339,25 @@ def test_centralised_autoresume_continues_from_latest_checkpoint(tmp_path, monke
     c = run_centralised(compose(cen + ["run_uuid=one", f"llm_config.save_folder={tmp_path}/one", "llm_config.max_duration=5ba"]), device=torch.device("cpu"))
     assert torch.allclose(resumed, c.state.flat.params, atol=1e-6), float((resumed - c.state.flat.params).abs().max())
     c.close()
+
+
+@pytest.mark.skipif(not Path("/root/reference/photon/conf/base.yaml").exists(), reason="reference tree not mounted")
+def test_runs_from_the_reference_yaml_tree(tmp_path):
+    """A user of the reference can point this framework at THEIR config directory: the composer resolves the reference's
+    defaults lists / interpolations / schema, and both entry points run from it (keys that only exist here take defaults)."""
+    from photon_b200.centralised_train import run_centralised
+    from photon_b200.server_app import run_server
+
+    ref = "/root/reference/photon/conf"
+    for size, d, opt in (("mpt-125m", 768, "adopt"), ("mpt-1b", 2048, "decoupled_adamw"), ("mpt-3b", 2560, "decoupled_adamw"), ("mpt-7b", 4096, "decoupled_adamw")):
+        c = compose([f"llm_config={size}"], config_dir=ref)
+        assert c.llm_config.model.d_model == d and c.llm_config.optimizer.name == opt and c.photon.comm_stack.nvl is False
+    cfg = compose(TINY + [f"photon.saving_path={tmp_path}", f"llm_config.save_folder={tmp_path}/clients", "run_uuid=refconf", "fl.n_rounds=1",
+                          "photon.checkpoint=true"], config_dir=ref)
+    h = run_server(cfg)
+    assert h.metrics_distributed_fit["server/n_failures"] == [(1, 0)] and len(h.losses_distributed) == 2
+    cen = [a for a in TINY if not a.startswith(("fl.", "llm_config.local_steps"))]
+    tr = run_centralised(compose(cen + [f"photon.saving_path={tmp_path}", "llm_config.save_folder=null", "run_uuid=refcen",
+                                        "llm_config.max_duration=2ba"], config_dir=ref), device=torch.device("cpu"))
+    assert tr.state.timestamp.batch == 2
+    tr.close()
