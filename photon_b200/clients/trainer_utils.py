@@ -167,7 +167,22 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend,
                  shard_optimizer_state=shard_state,
                  activation_checkpointing=bool(fsdp) and bool(dict(fsdp).get("activation_checkpointing", False)))
+    tr.icl_suite = build_icl_suite(cfg, mcfg.max_seq_len)
     return tr, t
+
+
+def build_icl_suite(cfg: Any, max_seq_len: int) -> Any:
+    """``icl_tasks_config`` (+ ``eval_gauntlet_config``) → a callable the Trainer runs at every ``eval()``
+    (ref: centralised_train.py:120-136 and llm-foundry ``build_evaluators`` / ``EvalGauntlet``). None when no task is listed."""
+    tasks = ((cfg.get("icl_tasks_config") or {}).get("icl_tasks")) or []
+    if not tasks:
+        return None
+    from photon_b200.dataset.utils import build_tokenizer
+    from photon_b200.eval.icl import run_icl_suite
+
+    tok_cfg = dict((cfg["llm_config"].get("tokenizer") or {}))
+    tokenizer = build_tokenizer(str(tok_cfg.get("name", "EleutherAI/gpt-neox-20b")))
+    return lambda logits_fn: run_icl_suite(logits_fn, tokenizer, cfg, max_seq_len)
 
 
 def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, log_name: str = "", split_eval: bool = False,

@@ -376,6 +376,15 @@ class B200Engine:
             out["unigram_loss_sum"] = st[3]
         return out
 
+    @torch.no_grad()
+    def logits(self, ids: torch.Tensor) -> torch.Tensor:
+        """``[B,S] → [B,S,V]`` for the in-context-learning evaluator. ICL prompts are ragged single sequences scored a
+        handful of tokens at a time — nothing like the fixed ``[b, 2048]`` schedule the kernel workspace is laid out for — so
+        this runs the torch module that shares the fp32 master weights (bf16 autocast, SDPA); it is an evaluation utility,
+        not part of the training step."""
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return self.model(ids.to(self.device))
+
     def train_mode(self, on: bool = True) -> None:
         self.model.train(on)
 

@@ -121,6 +121,12 @@ class TorchBackend:
             out["unigram_loss_sum"] = unigram_loss_sum(tf, self.unigram_log_probs)
         return out
 
+    @torch.no_grad()
+    def logits(self, ids: torch.Tensor) -> torch.Tensor:
+        """``[B,S] → [B,S,V]`` next-token logits (the in-context-learning evaluator's view of the model)."""
+        with autocast_ctx(self.device, self.precision):
+            return self.model(ids.to(self.device))
+
     def params_updated(self) -> None:
         pass
 

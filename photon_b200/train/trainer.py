@@ -146,6 +146,8 @@ class Trainer:
         self.fit_start_batch, self.fit_end_batch = 0, None
         self.closed = False
         self.last_batch_stats: dict[str, float] = {}
+        self.icl_suite: Any = None              # callable(logits_fn) -> metrics; set by get_trainer_object from icl_tasks_config
+        self.last_icl_metrics: dict[str, float] = {}
 
         seq = self.model_cfg.max_seq_len
         self.max_duration = Time.parse(max_duration) if max_duration is not None else None
@@ -393,6 +395,11 @@ class Trainer:
             sync_metrics(metrics, self.process_group)
         vals = st.eval_metric_values
         self.log({f"metrics/{k}": v for k, v in vals.items()})
+        if self.icl_suite is not None:   # llm-foundry's ICL evaluators + EvalGauntlet run as part of every trainer.eval()
+            icl = {k: v for k, v in self.icl_suite(st.backend.logits).items() if isinstance(v, (int, float))} if self.rank == 0 else {}
+            self.last_icl_metrics = icl
+            self.log({(k if k.startswith("icl/") else f"metrics/icl/{k}"): float(v) for k, v in icl.items()})
+            vals = {**vals, **{(k if k.startswith("icl/") else f"icl/{k}"): float(v) for k, v in icl.items()}}
         self._emit("eval_end")
         self._flush_logs()
         return vals

@@ -35,3 +35,34 @@ def test_gauntlet_aggregation():
                                      {"name": "b", "benchmarks": [{"name": "t2", "num_fewshot": 5, "random_baseline": 0.0}]}]})
     out = g.aggregate({"t1/0-shot/accuracy": 0.625, "t2/5-shot/accuracy": 0.3})
     assert math.isclose(out["icl/metrics/eval_gauntlet/a"], 0.5) and math.isclose(out["icl/metrics/eval_gauntlet/core"], 0.4)
+
+
+def test_icl_suite_runs_inside_trainer_eval(tmp_path):
+    """``icl_tasks_config`` + ``eval_gauntlet_config`` → evaluated at every ``trainer.eval()`` of the centralised entry point
+    (``eval_only``), logged as ``metrics/icl/*`` and ``icl/metrics/eval_gauntlet/*`` (ref: centralised_train.py:120-136)."""
+    from photon_b200.centralised_train import run_centralised
+    from photon_b200.config import compose
+
+    (tmp_path / "lm.jsonl").write_text("\n".join(json.dumps(r) for r in [{"context": "ab", "continuation": "c"}, {"context": "xy", "continuation": "z"}]))
+    (tmp_path / "mc.jsonl").write_text(json.dumps({"query": "q", "choices": ["a", "b", "c", "d"], "gold": 2}))
+    tiny = ["llm_config.model.d_model=32", "llm_config.model.n_heads=2", "llm_config.model.n_layers=1", "llm_config.max_seq_len=32",
+            "llm_config.global_train_batch_size=2", "llm_config.device_train_microbatch_size=2", "llm_config.device_eval_batch_size=2",
+            "llm_config.precision=fp32", "llm_config.model.attn_config.attn_impl=torch", "llm_config.eval_subset_num_batches=1",
+            "llm_config.log_to_console=false", "~llm_config.loggers.wandb", "~llm_config.loggers.tensorboard", "~llm_config.callbacks",
+            "llm_config.save_folder=null", f"photon.saving_path={tmp_path}", "run_uuid=icl", "centralized.eval_only=true"]
+    icl = ("icl_tasks_config={root_dir: " + str(tmp_path) + ", icl_tasks: ["
+           "{label: lm, dataset_uri: lm.jsonl, icl_task_type: language_modeling, num_fewshot: [0, 1]}, "
+           "{label: mc, dataset_uri: mc.jsonl, icl_task_type: multiple_choice}, "
+           "{label: gone, dataset_uri: missing.jsonl, icl_task_type: multiple_choice}]}")
+    gauntlet = ("eval_gauntlet_config={eval_gauntlet: {weighting: EQUAL, subtract_random_baseline: true, rescale_accuracy: true, "
+                "averages: {core_average: [reasoning]}, categories: [{name: reasoning, benchmarks: ["
+                "{name: mc, num_fewshot: 0, random_baseline: 0.25}, {name: lm, num_fewshot: 1, random_baseline: 0.0}]}]}}")
+    tr = run_centralised(compose(tiny + [icl, gauntlet]), device=torch.device("cpu"))
+    m = tr.last_icl_metrics
+    assert set(m) >= {"lm/0-shot/accuracy", "lm/1-shot/accuracy", "mc/0-shot/accuracy", "icl/metrics/eval_gauntlet/reasoning",
+                      "icl/metrics/eval_gauntlet/core_average"} and not any(k.startswith("gone") for k in m)
+    want = ((m["mc/0-shot/accuracy"] - 0.25) / 0.75 + m["lm/1-shot/accuracy"]) / 2
+    assert math.isclose(m["icl/metrics/eval_gauntlet/reasoning"], want, abs_tol=1e-9)
+    logged = tr.loggers[0].data
+    assert "metrics/icl/mc/0-shot/accuracy" in logged and "icl/metrics/eval_gauntlet/core_average" in logged
+    tr.close()
