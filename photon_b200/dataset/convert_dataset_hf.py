@@ -23,20 +23,29 @@ from photon_b200.dataset.utils import UnigramCounter, build_tokenizer, concat_to
 
 
 def convert_split(docs: Any, tokenizer: Any, out_dirs: list[Path], seq_len: int, total_samples: int | None,
-                  compression: str | None = "zlib", shard_samples: int = 8192, eos_text: str = "<|endoftext|>") -> list[int]:
+                  compression: str | None = "zlib", shard_samples: int = 8192, eos_text: str = "<|endoftext|>",
+                  bos_text: str = "", no_wrap: bool = False, only_client: int | None = None) -> list[int]:
     """Write samples into ``len(out_dirs)`` contiguous partitions. When ``total_samples`` is unknown the
-    samples are first counted into memory-light temporary order: we buffer and cut at the end."""
+    samples are first counted into memory-light temporary order: we buffer and cut at the end. ``only_client`` writes
+    just that partition (its samples are the same ones a full conversion would give it)."""
     n_clients = len(out_dirs)
-    samples = list(concat_tokens(docs, tokenizer, seq_len, eos_text=eos_text)) if total_samples is None else None
-    it = iter(samples) if samples is not None else concat_tokens(docs, tokenizer, seq_len, eos_text=eos_text)
+    kw = dict(eos_text=eos_text, bos_text=bos_text, no_wrap=no_wrap)
+    samples = list(concat_tokens(docs, tokenizer, seq_len, **kw)) if total_samples is None else None
+    it = iter(samples) if samples is not None else concat_tokens(docs, tokenizer, seq_len, **kw)
     total = len(samples) if samples is not None else int(total_samples)
     per = total // n_clients
     written = []
     for c, d in enumerate(out_dirs):
+        quota = per if c < n_clients - 1 else total - per * (n_clients - 1)
+        if only_client is not None and c != only_client:
+            for _ in range(quota):     # consume this partition's samples so the next one starts where it should
+                next(it, None)
+            written.append(0)
+            continue
         counter = UnigramCounter()
         n = 0
         with ShardWriter(d, seq_len=seq_len, shard_samples=shard_samples, compression=compression) as w:
-            for _ in range(per if c < n_clients - 1 else total - per * (n_clients - 1)):
+            for _ in range(quota):
                 try:
                     s = next(it)
                 except StopIteration:
@@ -50,30 +59,56 @@ def convert_split(docs: Any, tokenizer: Any, out_dirs: list[Path], seq_len: int,
 
 
 def main(argv: list[str] | None = None) -> dict[str, list[int]]:
+    """CLI with the reference's flag surface (ref: photon/dataset/convert_dataset_hf.py:93-140). ``--path`` / ``--name`` select
+    an HF dataset when it is cached locally; ``--source`` takes a local text/jsonl file or directory (or ``synthetic://N``)."""
+    import json
+    import shutil
+
     ap = argparse.ArgumentParser(description="Convert a text corpus into per-client token shards")
     ap.add_argument("--dataset", default="c4_en", choices=sorted(DATASETS_CONSTANTS))
+    ap.add_argument("--path", default=None, help="HF dataset path (reference flag); default: the table entry of --dataset")
+    ap.add_argument("--name", default=None, help='HF dataset config name, e.g. "en" (reference flag; selects c4_<name> when --dataset is not given)')
     ap.add_argument("--splits", nargs="+", default=["train_small", "val_xxsmall"])
-    ap.add_argument("--source", default=None, help="text/jsonl file or dir, HF dataset name, or synthetic://N (default: the HF path of --dataset)")
+    ap.add_argument("--source", default=None, help="text/jsonl file or dir, HF dataset name, or synthetic://N (default: --path / the HF path of --dataset)")
     ap.add_argument("--out_root", required=True)
+    ap.add_argument("--remote_path", default=None, help="mirror the converted tree here as well (the object-store upload of the reference)")
     ap.add_argument("--num_clients", type=int, default=8)
+    ap.add_argument("--client", type=int, default=None, help="only write this client's partition (the others are skipped, not re-numbered)")
     ap.add_argument("--concat_tokens", type=int, default=2048)
     ap.add_argument("--tokenizer", default="EleutherAI/gpt-neox-20b")
+    ap.add_argument("--tokenizer_kwargs", default=None, help="JSON dict forwarded to the tokenizer constructor")
+    ap.add_argument("--bos_text", default=None)
     ap.add_argument("--eos_text", default="<|endoftext|>")
-    ap.add_argument("--compression", default="zlib", choices=["zlib", "none"])
+    ap.add_argument("--pad_text", default=None, help="accepted for flag parity; packed samples are never padded")
+    ap.add_argument("--no_wrap", action="store_true", help="drop the tail of a document that does not fill the current sample instead of carrying it over")
+    ap.add_argument("--num_workers", type=int, default=None, help="accepted for flag parity; conversion is a single streaming pass")
+    ap.add_argument("--compression", default="zlib", choices=["zlib", "zstd", "none"])
     args = ap.parse_args(argv)
+    if args.name and f"c4_{args.name}" in DATASETS_CONSTANTS and args.dataset == "c4_en":
+        args.dataset = f"c4_{args.name}"
+    if args.compression == "zstd":
+        try:
+            import zstandard  # noqa: F401
+        except ImportError:
+            print("[convert] zstd is not importable here; writing zlib shards (the reader picks the codec from index.json)")
+        args.compression = "zlib"
     consts = DATASETS_CONSTANTS[args.dataset]
-    tok = build_tokenizer(args.tokenizer)
+    tok = build_tokenizer(args.tokenizer, **(json.loads(args.tokenizer_kwargs) if args.tokenizer_kwargs else {}))
     lang = args.dataset.split("_", 1)[1]
     root = Path(args.out_root) / f"c{args.num_clients}" / lang
     out: dict[str, list[int]] = {}
     for fs in args.splits:
         sc = consts.splits[fs]
-        src = args.source or sc.path
+        src = args.source or args.path or sc.path
         docs = iter_text_source(src, split=sc.split, limit=sc.truncated_samples)
         dirs = [root / f"client_{i}" / fs for i in range(args.num_clients)]
-        out[fs] = convert_split(docs, tok, dirs, args.concat_tokens, None, None if args.compression == "none" else "zlib", eos_text=args.eos_text)
+        out[fs] = convert_split(docs, tok, dirs, args.concat_tokens, None, None if args.compression == "none" else "zlib",
+                                eos_text=args.eos_text, bos_text=args.bos_text or "", no_wrap=args.no_wrap, only_client=args.client)
         print(f"[convert] {args.dataset}/{fs}: {out[fs]} samples per client -> {root}")
     tok.save_pretrained(str(Path(args.out_root) / "tokenizer"))
+    if args.remote_path:
+        shutil.copytree(args.out_root, args.remote_path, dirs_exist_ok=True)
+        print(f"[convert] mirrored {args.out_root} -> {args.remote_path}")
     return out
 
 

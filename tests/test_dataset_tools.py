@@ -38,6 +38,22 @@ def test_converter_contiguous_partitions_and_unigram(tmp_path):
     assert len(re64) == counts[1] // 2 and re64[0]["tokens"].shape == (64,)
 
 
+def test_converter_reference_flags_single_client_and_mirror(tmp_path):
+    """``--client k`` writes exactly the partition a full conversion gives client k; ``--remote_path`` mirrors the tree;
+    ``--compression zstd`` / ``--num_workers`` / ``--pad_text`` are accepted like in the reference CLI."""
+    common = ["--source", "synthetic://200", "--num_clients", "4", "--concat_tokens", "32", "--splits", "train_small", "--bos_text", "", "--num_workers", "2",
+              "--pad_text", "<s>", "--tokenizer_kwargs", "{}"]
+    full = convert_main(common + ["--out_root", str(tmp_path / "full"), "--compression", "zstd"])["train_small"]
+    one = convert_main(common + ["--out_root", str(tmp_path / "one"), "--client", "2", "--compression", "none", "--remote_path", str(tmp_path / "mirror")])["train_small"]
+    assert one[2] == full[2] and one[0] == one[1] == one[3] == 0
+    a = ShardReader(tmp_path / "full" / "c4" / "en" / "client_2" / "train_small")
+    b = ShardReader(tmp_path / "mirror" / "c4" / "en" / "client_2" / "train_small")
+    assert len(a) == len(b) and all((a[i] == b[i]).all() for i in range(len(a)))
+    assert not (tmp_path / "one" / "c4" / "en" / "client_0" / "train_small" / "index.json").exists()
+    wrapped = convert_main(common + ["--out_root", str(tmp_path / "nw"), "--no_wrap"])["train_small"]
+    assert sum(wrapped) <= sum(full)          # tails of documents are dropped instead of carried over
+
+
 def test_stream_partitioner(tmp_path):
     entries = [{"client_streams": {f"stream_{i}": {"local": f"c8/en/client_{i}"}}} for i in range(8)]
     two = partition_stream_list(entries, 2)
