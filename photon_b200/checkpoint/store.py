@@ -101,8 +101,7 @@ class CheckpointStore:
     def download_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
                                    state_keys: Sequence[str]) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
         d = self.round_dir(run_uuid, server_round)
-        with open(d / STATE_FILE, "rb") as f:
-            state = pickle.load(f)  # noqa: S301 - our own checkpoint
+        state = load_server_state(d / STATE_FILE)
         tensors: dict[str, torch.Tensor] = {}
         for key in state_keys:
             arrays = load_model_parameters_from_file(d / f"{key}.npz")
@@ -177,6 +176,41 @@ class CheckpointStore:
             self.delete_clients_checkpoints(run_uuid, keep_latest=True)
         else:
             shutil.rmtree(self.bucket / run_uuid, ignore_errors=True)
+
+
+class _Foreign:
+    """Stand-in for a class this process cannot import while unpickling (attributes land in ``__dict__``)."""
+
+    def __setstate__(self, state: Any) -> None:
+        self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    def find_class(self, module: str, name: str) -> Any:
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            return type(name, (_Foreign,), {"__module__": module})
+
+
+def load_server_state(path: str | Path) -> dict[str, Any]:
+    """``state.bin`` of either framework. The reference pickles the same five fields (``server_round``, ``history``,
+    ``time_offset``, ``client_state`` as a literal string, ``server_steps_cumulative``; ref: s3_utils.py:374-389) but its
+    ``history`` is a Flower ``History`` subclass this process cannot import: it is read through a tolerant unpickler and its
+    five metric stores are copied into our :class:`WandbHistory`, so a federation started with the reference resumes here."""
+    from photon_b200.wandb_history import History, WandbHistory
+
+    with open(path, "rb") as f:
+        state = _TolerantUnpickler(f).load()  # noqa: S301 - a checkpoint the user points us at
+    hist = state.get("history")
+    if hist is not None and not isinstance(hist, History):
+        mine = WandbHistory(False)
+        for attr in ("losses_distributed", "losses_centralized", "metrics_distributed_fit", "metrics_distributed", "metrics_centralized"):
+            val = getattr(hist, attr, None)
+            if val is not None:
+                setattr(mine, attr, type(getattr(mine, attr))(val))
+        state["history"] = mine
+    return state
 
 
 def load_pretrained_model_from_path(path: str | Path) -> list[np.ndarray]:

@@ -18,7 +18,21 @@ def main(argv: list[str] | None = None) -> Path:
     save_path = os.environ.get("PHOTON_SAVE_PATH")
     if not save_path:
         raise SystemExit("PHOTON_SAVE_PATH must be set (ref: photon/hydra_resolver.py:33)")
-    cfg = compose(argv)
+    # Hydra's own flags: ``--config-dir/--config-path/-cd/-cp DIR`` (e.g. a reference checkout's photon/conf) and
+    # ``--config-name/-cn NAME``; ``PHOTON_CONFIG_DIR`` does the same for launch scripts
+    config_dir: str | None = os.environ.get("PHOTON_CONFIG_DIR") or None
+    config_name = "base"
+    rest: list[str] = []
+    it = iter(argv)
+    for a in it:
+        key, _, val = a.partition("=")
+        if key in ("--config-dir", "--config-path", "-cd", "-cp"):
+            config_dir = val or next(it)
+        elif key in ("--config-name", "-cn"):
+            config_name = (val or next(it)).removesuffix(".yaml")
+        else:
+            rest.append(a)
+    cfg = compose(rest, config_name=config_name, config_dir=config_dir)
     out = Path(save_path) / "config.yaml"
     save_yaml(cfg, out)
     print(f"[hydra_resolver] wrote {out}")

@@ -78,3 +78,21 @@ def test_resolver_cli_roundtrip(tmp_path, monkeypatch):
     assert cfg.run_uuid == "cli" and cfg.fl.strategy_kwargs.eta == 0.1
     save_yaml(cfg, tmp_path / "again.yaml")
     assert load_config(tmp_path / "again.yaml") == cfg
+
+
+def test_resolver_takes_hydra_config_dir_flags(tmp_path, monkeypatch):
+    """``--config-dir`` / ``-cn`` (or ``PHOTON_CONFIG_DIR``) point the resolver at another tree — here a copy of ours with one
+    value changed — the way a reference user would point it at their ``photon/conf``."""
+    import shutil
+
+    from photon_b200 import hydra_resolver
+    from photon_b200.config.composer import DEFAULT_CONFIG_DIR
+
+    mine = tmp_path / "conf"
+    shutil.copytree(DEFAULT_CONFIG_DIR, mine)
+    (mine / "base.yaml").write_text((mine / "base.yaml").read_text().replace("seed: 1337", "seed: 4242"))
+    monkeypatch.setenv("PHOTON_SAVE_PATH", str(tmp_path))
+    assert load_config(hydra_resolver.main(["--config-dir", str(mine), "--config-name=base", "run_uuid=x"])).seed == 4242
+    assert load_config(hydra_resolver.main(["run_uuid=x"])).seed == 1337
+    monkeypatch.setenv("PHOTON_CONFIG_DIR", str(mine))
+    assert load_config(hydra_resolver.main(["run_uuid=x"])).seed == 4242

@@ -205,3 +205,39 @@ def test_loader_state_tracks_the_consumer_not_the_prefetch_thread():
     assert len(rest) == 11 and all(torch.equal(x, y) for x, y in zip(seen + rest, ref))
     it.close()
     assert a.dataset.sample_in_epoch == 20 and a.state_dict()["sample_in_epoch"] == 20   # abandoned iterator: prefetched samples are not lost
+
+
+def test_state_bin_written_by_the_reference_is_readable(tmp_path, monkeypatch):
+    """The reference pickles a Flower ``History`` subclass into ``state.bin``; neither ``flwr`` nor ``photon`` is importable
+    here, so the loader must read it without those classes and hand back our own history object."""
+    import importlib
+    import pickle
+    import sys
+
+    from photon_b200.checkpoint.store import load_server_state
+    from photon_b200.messages import decode_client_states
+    from photon_b200.wandb_history import WandbHistory
+
+    pkg = tmp_path / "fakeflwr_pkg"
+    pkg.mkdir()
+    (pkg / "fakeflwr_history.py").write_text(
+        "class History:\n"
+        "    def __init__(self):\n"
+        "        self.losses_distributed, self.losses_centralized = [(0, 11.0), (1, 10.5)], []\n"
+        "        self.metrics_distributed_fit, self.metrics_distributed, self.metrics_centralized = {'server/n_failures': [(1, 0)]}, {}, {'t': [(1, 2.0)]}\n"
+        "class WandbHistory(History):\n"
+        "    def __init__(self):\n"
+        "        super().__init__()\n"
+        "        self.use_wandb = False\n")
+    monkeypatch.syspath_prepend(str(pkg))
+    mod = importlib.import_module("fakeflwr_history")
+    blob = pickle.dumps({"server_round": 1, "history": mod.WandbHistory(), "time_offset": 3.5, "server_steps_cumulative": 4,
+                         "client_state": "{0: {'local_steps_cumulative': 4, 'local_timestamp': {}, 'steps_done': 0}}"})
+    del sys.modules["fakeflwr_history"]
+    monkeypatch.setattr(sys, "path", [p for p in sys.path if p != str(pkg)])
+    importlib.invalidate_caches()
+    (tmp_path / "state.bin").write_bytes(blob)
+    st = load_server_state(tmp_path / "state.bin")
+    assert isinstance(st["history"], WandbHistory) and st["history"].losses_distributed == [(0, 11.0), (1, 10.5)]
+    assert st["history"].latest("server/n_failures") == 0 and st["server_steps_cumulative"] == 4 and st["time_offset"] == 3.5
+    assert decode_client_states(st["client_state"])[0].local_steps_cumulative == 4
