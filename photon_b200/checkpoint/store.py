@@ -139,6 +139,15 @@ class CheckpointStore:
         self.copy_old_checkpoints_to_new_run(str(src), str(dst), rnd, state_keys=state_keys,
                                              copy_client_checkpoints=bool(ph.get("copy_client_checkpoints", True)),
                                              client_ids=range(int(cfg["fl"]["n_total_clients"])))
+        # client checkpoints normally live under llm_config.save_folder, whose path carries the run id
+        # (``…/{run_uuid}/clients/client_{cid}/``): bring the old run's over so optimizer state / data position survive
+        sf = (cfg.get("llm_config") or {}).get("save_folder")
+        if bool(ph.get("copy_client_checkpoints", True)) and sf and str(dst) in str(sf):
+            old_sf = Path(str(sf).replace(str(dst), str(src)))
+            for cid in range(int(cfg["fl"]["n_total_clients"])):
+                s_dir = old_sf / f"client_{cid}"
+                if s_dir.is_dir():
+                    shutil.copytree(s_dir, Path(str(sf)) / f"client_{cid}", dirs_exist_ok=True, symlinks=True)
         ph["resume_round"] = rnd
         return rnd
 

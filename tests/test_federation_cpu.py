@@ -361,3 +361,21 @@ def test_runs_from_the_reference_yaml_tree(tmp_path):
                                         "llm_config.max_duration=2ba"], config_dir=ref), device=torch.device("cpu"))
     assert tr.state.timestamp.batch == 2
     tr.close()
+
+
+def test_restore_run_brings_client_checkpoints_along(tmp_path):
+    """``photon.restore_run_uuid`` + ``copy_client_checkpoints``: the new run finds the old run's per-client checkpoints under its
+    own save folder, so clients keep optimizer state and data position (ref: server/s3_utils.py:1478-1608)."""
+    from photon_b200.server_app import run_server
+
+    def cfg_for(uuid, *extra):
+        return compose(TINY + [f"photon.saving_path={tmp_path}", f"llm_config.save_folder={tmp_path}/{uuid}/clients", "llm_config.save_interval=2ba",
+                               f"run_uuid={uuid}", "photon.checkpoint=true", "fl.reset_optimizer=false", *extra])
+
+    run_server(cfg_for("old", "fl.n_rounds=1"))
+    old = sorted(p.relative_to(tmp_path / "old").as_posix() for p in (tmp_path / "old" / "clients").rglob("ep*-rank0.pt"))
+    assert old, "the first run wrote no client checkpoints"
+    h = run_server(cfg_for("new", "fl.n_rounds=2", "photon.restore_run_uuid=old", "photon.resume_round=-1"))
+    new = sorted(p.relative_to(tmp_path / "new").as_posix() for p in (tmp_path / "new" / "clients").rglob("ep*-rank0.pt"))
+    assert set(old) <= set(new)
+    assert [r for r, _ in h.metrics_distributed_fit["server/n_failures"]][-1] == 2
