@@ -7,11 +7,11 @@ The on-disk layout is our own, sized for fast sequential reads into pinned
 host memory: a directory holding
 
 * ``index.json`` — ``{"version", "format": "pb200-tokens", "seq_len",
-  "dtype": "int32", "compression": null|"zlib", "shards": [{"basename",
+  "dtype": "int32", "compression": null|"zlib"|"zstd", "shards": [{"basename",
   "samples", "raw_bytes", "zip_bytes", "sha1"}...]}``
 * ``shard.00000.tok[.z]`` — a C-contiguous ``[samples, seq_len]`` int32 matrix.
 
-(zstd is not importable in this image; zlib is the optional codec.)
+(zstd — the reference's MDS default — comes from pyarrow's bundled codec; zlib needs nothing.)
 """
 from __future__ import annotations
 
@@ -28,13 +28,32 @@ INDEX_NAME = "index.json"
 FORMAT = "pb200-tokens"
 
 
+def _zstd() -> Any:
+    """zstd through pyarrow's bundled codec (the ``zstandard`` module is not installed here); None if unavailable."""
+    try:
+        import pyarrow as pa
+
+        return pa.Codec("zstd", compression_level=3) if pa.Codec.is_available("zstd") else None
+    except ImportError:
+        return None
+
+
+def _zstd_decompress(blob: bytes, raw_bytes: int) -> bytes:
+    codec = _zstd()
+    if codec is None:
+        raise RuntimeError("this shard is zstd-compressed and no zstd codec is importable")
+    return codec.decompress(blob, decompressed_size=raw_bytes, asbytes=True)
+
+
 class ShardWriter:
     """Accumulates fixed-length int32 samples and cuts a shard every ``shard_samples``."""
 
     def __init__(self, out_dir: str | os.PathLike, seq_len: int, shard_samples: int = 8192,
                  compression: str | None = None) -> None:
-        if compression not in (None, "zlib"):
-            raise ValueError("compression must be null or 'zlib'")
+        if compression not in (None, "zlib", "zstd"):
+            raise ValueError("compression must be null, 'zlib' or 'zstd'")
+        if compression == "zstd" and _zstd() is None:
+            raise RuntimeError("zstd shards need pyarrow's codec (no zstandard module in this image)")
         self.out = Path(out_dir)
         self.out.mkdir(parents=True, exist_ok=True)
         self.seq_len, self.shard_samples, self.compression = int(seq_len), int(shard_samples), compression
@@ -62,6 +81,8 @@ class ShardWriter:
         payload = raw
         if self.compression == "zlib":
             payload, base = zlib.compress(raw, 3), base + ".z"
+        elif self.compression == "zstd":
+            payload, base = _zstd().compress(raw, asbytes=True), base + ".zstd"
         (self.out / base).write_bytes(payload)
         self._shards.append({"basename": base, "samples": int(mat.shape[0]), "raw_bytes": len(raw),
                              "zip_bytes": len(payload), "sha1": hashlib.sha1(raw).hexdigest()})  # noqa: S324
@@ -105,8 +126,10 @@ class ShardReader:
         if i not in self._cache:
             meta = self.index["shards"][i]
             path = self.dir / meta["basename"]
-            if self.index.get("compression") == "zlib":
-                raw = zlib.decompress(path.read_bytes())
+            codec = self.index.get("compression")
+            if codec in ("zlib", "zstd"):
+                blob = path.read_bytes()
+                raw = zlib.decompress(blob) if codec == "zlib" else _zstd_decompress(blob, int(meta["raw_bytes"]))
                 mat = np.frombuffer(raw, dtype=np.int32).reshape(meta["samples"], self.seq_len)
             else:
                 mat = np.memmap(path, dtype=np.int32, mode="r", shape=(meta["samples"], self.seq_len))

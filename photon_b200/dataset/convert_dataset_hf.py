@@ -87,11 +87,11 @@ def main(argv: list[str] | None = None) -> dict[str, list[int]]:
     if args.name and f"c4_{args.name}" in DATASETS_CONSTANTS and args.dataset == "c4_en":
         args.dataset = f"c4_{args.name}"
     if args.compression == "zstd":
-        try:
-            import zstandard  # noqa: F401
-        except ImportError:
-            print("[convert] zstd is not importable here; writing zlib shards (the reader picks the codec from index.json)")
-        args.compression = "zlib"
+        from photon_b200.data.shards import _zstd
+
+        if _zstd() is None:
+            print("[convert] no zstd codec importable here; writing zlib shards (the reader picks the codec from index.json)")
+            args.compression = "zlib"
     consts = DATASETS_CONSTANTS[args.dataset]
     tok = build_tokenizer(args.tokenizer, **(json.loads(args.tokenizer_kwargs) if args.tokenizer_kwargs else {}))
     lang = args.dataset.split("_", 1)[1]
@@ -102,7 +102,7 @@ def main(argv: list[str] | None = None) -> dict[str, list[int]]:
         src = args.source or args.path or sc.path
         docs = iter_text_source(src, split=sc.split, limit=sc.truncated_samples)
         dirs = [root / f"client_{i}" / fs for i in range(args.num_clients)]
-        out[fs] = convert_split(docs, tok, dirs, args.concat_tokens, None, None if args.compression == "none" else "zlib",
+        out[fs] = convert_split(docs, tok, dirs, args.concat_tokens, None, None if args.compression == "none" else args.compression,
                                 eos_text=args.eos_text, bos_text=args.bos_text or "", no_wrap=args.no_wrap, only_client=args.client)
         print(f"[convert] {args.dataset}/{fs}: {out[fs]} samples per client -> {root}")
     tok.save_pretrained(str(Path(args.out_root) / "tokenizer"))

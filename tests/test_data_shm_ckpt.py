@@ -15,7 +15,7 @@ from photon_b200.utils.core import dump_model_parameters_to_file, load_model_par
 from photon_b200.utils.flat import FlatLayout
 
 
-@pytest.mark.parametrize("comp", [None, "zlib"])
+@pytest.mark.parametrize("comp", [None, "zlib", "zstd"])
 def test_shard_roundtrip(tmp_path, comp):
     rows = [np.arange(i, i + 16, dtype=np.int32) for i in range(37)]
     with ShardWriter(tmp_path / "s", seq_len=16, shard_samples=10, compression=comp) as w:
