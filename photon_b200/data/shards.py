@@ -145,3 +145,112 @@ class ShardReader:
             raise IndexError(idx)
         s = int(np.searchsorted(self._starts, idx, side="right") - 1)
         return np.asarray(self._shard(s)[idx - int(self._starts[s])])
+
+
+class MDSReader:
+    """Read-only access to token datasets written by mosaicml-streaming's ``MDSWriter`` (the reference's on-disk format:
+    ``MDSWriter(columns={"tokens": "ndarray:int32"}, compression="zstd")``, ref: photon/dataset/convert_dataset_hf.py:234-363),
+    so datasets converted for the reference can be trained on without re-tokenising.
+
+    Layout handled (streaming ``format: mds``, index ``version: 2``): ``index.json`` lists shards with ``raw_data`` /
+    ``zip_data`` basenames, ``samples``, ``column_names`` / ``column_encodings`` / ``column_sizes`` and ``compression``.
+    A raw shard is ``uint32 n | uint32 offsets[n+1] | json config | samples``; offsets are absolute byte positions; a sample
+    is ``uint32 size`` per variable-size column followed by the column payloads; an ``ndarray:<dtype>`` payload is a short
+    shape header followed by the C-order data, so the tokens are the trailing ``4·n`` bytes and the header is cross-checked
+    against ``n``. Only the token column is decoded. Compressed shards (``.zstd``) go through pyarrow's codec.
+
+    NB: implemented from the format description — there is no mosaicml-streaming install or MDS sample in this environment;
+    the unit test builds shards following the same description.
+    """
+
+    def __init__(self, directory: str | os.PathLike, column: str = "tokens", seq_len: int | None = None, validate_hash: bool = False) -> None:
+        self.dir = Path(directory)
+        self.index = json.loads((self.dir / INDEX_NAME).read_text())
+        shards = self.index.get("shards") or []
+        if not shards or any(sh.get("format") != "mds" for sh in shards):
+            raise ValueError(f"{self.dir}: not an MDS index")
+        self.column = column
+        self._meta = shards
+        counts = [int(sh["samples"]) for sh in shards]
+        self._starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self._cache: dict[int, tuple[bytes, np.ndarray]] = {}
+        self.validate_hash = validate_hash
+        self.seq_len = int(seq_len) if seq_len else int(self[0].shape[0])
+
+    def __len__(self) -> int:
+        return int(self._starts[-1])
+
+    def _load(self, i: int) -> tuple[bytes, np.ndarray]:
+        if i not in self._cache:
+            sh = self._meta[i]
+            raw_name, zip_info = sh["raw_data"]["basename"], sh.get("zip_data")
+            if (self.dir / raw_name).exists():
+                blob = (self.dir / raw_name).read_bytes()
+            elif zip_info and (self.dir / zip_info["basename"]).exists():
+                codec = str(sh.get("compression") or "").split(":")[0]
+                z = (self.dir / zip_info["basename"]).read_bytes()
+                if codec == "zstd":
+                    blob = _zstd_decompress(z, int(sh["raw_data"]["bytes"]))
+                elif codec in ("zlib", "gz"):
+                    blob = zlib.decompress(z, 15 + 32)
+                else:
+                    raise ValueError(f"{self.dir}: unsupported MDS compression {sh.get('compression')!r}")
+            else:
+                raise FileNotFoundError(f"{self.dir}: neither {raw_name} nor its compressed form is present")
+            n = int(np.frombuffer(blob, np.uint32, 1)[0])
+            if n != int(sh["samples"]):
+                raise OSError(f"{self.dir / raw_name}: header says {n} samples, index says {sh['samples']}")
+            offsets = np.frombuffer(blob, np.uint32, n + 1, offset=4)
+            if len(self._cache) > 4:
+                self._cache.pop(next(iter(self._cache)))
+            self._cache[i] = (blob, offsets)
+        return self._cache[i]
+
+    def _decode(self, sample: bytes, sh: dict[str, Any]) -> np.ndarray:
+        names, encs, sizes = sh["column_names"], sh["column_encodings"], sh["column_sizes"]
+        pos, lens = 0, []
+        for sz in sizes:
+            if sz:
+                lens.append(int(sz))
+            else:
+                lens.append(int(np.frombuffer(sample, np.uint32, 1, offset=pos)[0]))
+                pos += 4
+        for name, enc, ln in zip(names, encs, lens):
+            if name != self.column:
+                pos += ln
+                continue
+            payload = sample[pos:pos + ln]
+            kind, _, rest = enc.partition(":")
+            if kind != "ndarray":
+                raise ValueError(f"column {name!r} has encoding {enc!r}; expected ndarray:int32")
+            dtype = np.dtype(rest.split(":")[0] or "int32")
+            # shape header: 1 byte (rank / width code) + rank × {1,2,4,8}-byte dims; rank is 1 for token rows
+            for width in (0, 1, 2, 4, 8):
+                h = 0 if width == 0 else 1 + width
+                body = ln - h
+                if body < 0 or body % dtype.itemsize:
+                    continue
+                n = body // dtype.itemsize
+                if width and int.from_bytes(payload[1:h], "little") != n:
+                    continue
+                if width == 0 and ":" not in rest:      # no explicit shape in the encoding → a header must be present
+                    continue
+                return np.frombuffer(payload, dtype, n, offset=h).astype(np.int32, copy=False)
+            raise ValueError(f"cannot locate the token payload in a {ln}-byte {enc} column")
+        raise KeyError(f"column {self.column!r} not in {names}")
+
+    def __getitem__(self, idx: int) -> np.ndarray:
+        if not 0 <= idx < len(self):
+            raise IndexError(idx)
+        s = int(np.searchsorted(self._starts, idx, side="right") - 1)
+        blob, offsets = self._load(s)
+        j = idx - int(self._starts[s])
+        return self._decode(blob[int(offsets[j]):int(offsets[j + 1])], self._meta[s])
+
+
+def open_shard_dir(directory: str | os.PathLike, validate_hash: bool = False) -> Any:
+    """:class:`ShardReader` for our own format, :class:`MDSReader` for a mosaicml-streaming directory."""
+    index = json.loads((Path(directory) / INDEX_NAME).read_text())
+    if index.get("format") == FORMAT:
+        return ShardReader(directory, validate_hash=validate_hash)
+    return MDSReader(directory, validate_hash=validate_hash)

@@ -24,7 +24,7 @@ from typing import Any, Iterator, Sequence
 import numpy as np
 import torch
 
-from photon_b200.data.shards import INDEX_NAME, ShardReader
+from photon_b200.data.shards import INDEX_NAME, ShardReader, open_shard_dir
 from photon_b200.data.synthetic import SyntheticC4
 
 SYNTH_PREFIX = "synthetic://"
@@ -57,7 +57,7 @@ def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: i
                  synth_vocab: int | None = None) -> Any:
     d = st.directory()
     if d is not None and (d / INDEX_NAME).exists():
-        return ShardReader(d, validate_hash=bool(st.validate_hash))
+        return open_shard_dir(d, validate_hash=bool(st.validate_hash))   # our shards, or an MDS directory written for the reference
     if d is not None and not allow_synthetic:
         raise FileNotFoundError(f"stream '{st.name}': {d} has no {INDEX_NAME} (and remote fetch is unavailable offline)")
     sid = idx

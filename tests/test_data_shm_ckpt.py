@@ -241,3 +241,52 @@ def test_state_bin_written_by_the_reference_is_readable(tmp_path, monkeypatch):
     assert isinstance(st["history"], WandbHistory) and st["history"].losses_distributed == [(0, 11.0), (1, 10.5)]
     assert st["history"].latest("server/n_failures") == 0 and st["server_steps_cumulative"] == 4 and st["time_offset"] == 3.5
     assert decode_client_states(st["client_state"])[0].local_steps_cumulative == 4
+
+
+def _write_mds(directory, rows, shard_samples, compression=None):
+    """mosaicml-streaming's MDS layout for ``columns={"tokens": "ndarray:int32"}`` (see MDSReader's docstring)."""
+    import json as _json
+
+    import pyarrow as pa
+
+    directory.mkdir(parents=True)
+    cols = {"column_encodings": ["ndarray:int32"], "column_names": ["tokens"], "column_sizes": [None]}
+    config = _json.dumps({**cols, "compression": compression, "format": "mds", "hashes": [], "size_limit": 1 << 26}, sort_keys=True).encode()
+    shards = []
+    for k in range(0, len(rows), shard_samples):
+        samples = []
+        for r in rows[k:k + shard_samples]:
+            payload = bytes([(1 << 4) | 1]) + int(r.size).to_bytes(2, "little") + r.astype(np.int32).tobytes()   # rank-1, uint16 dim, data
+            samples.append(np.uint32(len(payload)).tobytes() + payload)
+        n = np.uint32(len(samples))
+        offsets = np.array([0] + [len(x) for x in samples]).cumsum().astype(np.uint32)
+        offsets += 4 + offsets.nbytes + len(config)
+        raw = n.tobytes() + offsets.tobytes() + config + b"".join(samples)
+        base = f"shard.{len(shards):05d}.mds"
+        meta = {**cols, "compression": compression, "format": "mds", "hashes": [], "samples": len(samples), "size_limit": 1 << 26, "version": 2,
+                "raw_data": {"basename": base, "bytes": len(raw), "hashes": {}}, "zip_data": None}
+        if compression:
+            z = pa.Codec("zstd").compress(raw, asbytes=True)
+            (directory / (base + ".zstd")).write_bytes(z)
+            meta["zip_data"] = {"basename": base + ".zstd", "bytes": len(z), "hashes": {}}
+        else:
+            (directory / base).write_bytes(raw)
+        shards.append(meta)
+    (directory / "index.json").write_text(_json.dumps({"shards": shards, "version": 2}))
+
+
+@pytest.mark.parametrize("compression", [None, "zstd"])
+def test_mds_directories_written_for_the_reference_are_readable(tmp_path, compression):
+    from photon_b200.data.shards import MDSReader, open_shard_dir
+    from photon_b200.data.streaming import Stream, StreamingTokenDataset, TokenLoader
+
+    rng = np.random.default_rng(0)
+    rows = [rng.integers(0, 50000, 32).astype(np.int32) for _ in range(25)]
+    _write_mds(tmp_path / "c8" / "en" / "client_0" / "train", rows, shard_samples=10, compression=compression)
+    r = open_shard_dir(tmp_path / "c8" / "en" / "client_0" / "train")
+    assert isinstance(r, MDSReader) and len(r) == 25 and r.seq_len == 32
+    assert all(np.array_equal(r[i], rows[i]) for i in (0, 9, 10, 24))
+    ds = StreamingTokenDataset([Stream(local=str(tmp_path / "c8" / "en" / "client_0"), split="train", name="s")], seq_len=32, shuffle=False,
+                               allow_synthetic=False)
+    batches = [b["input_ids"] for b in TokenLoader(ds, batch_size=5, pin_memory=False)]
+    assert len(batches) == 5 and torch.equal(batches[0][0], torch.from_numpy(rows[0].astype(np.int64)))
