@@ -1,0 +1,153 @@
+"""Property tests (hypothesis) for the pieces whose correctness is combinatorial rather than numerical: flat layouts,
+shard bounds, streaming aggregation, the override grammar, time strings, device splitting, the running-mean update."""
+import math
+
+import numpy as np
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from photon_b200.config.composer import ConfigNode, apply_overrides, parse_value
+from photon_b200.server.fleet import split_devices
+from photon_b200.strategy.aggregation import StreamingMean, aggregate_parameters, naive_weighted_mean
+from photon_b200.train.timestamp import Time
+from photon_b200.train.trainer import shard_bounds
+from photon_b200.utils.core import chunks_idx
+from photon_b200.utils.flat import FlatLayout
+
+names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz._0123456789", min_size=1, max_size=12)
+shapes = st.lists(st.integers(1, 7), min_size=0, max_size=3).map(tuple)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.dictionaries(names, shapes, min_size=1, max_size=12), st.sampled_from([1, 4, 64, 256]))
+def test_flat_layout_is_sorted_aligned_disjoint_and_roundtrips(named, align):
+    lay = FlatLayout.build(named.items(), align=align, total_multiple=align)
+    assert list(lay.names) == sorted(named) and lay.n_params == sum(int(np.prod(s)) if s else 1 for s in named.values())
+    spans = sorted(zip(lay.offsets, lay.numels))
+    assert all(o % align == 0 for o, _ in spans) and all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:]))
+    assert spans[-1][0] + spans[-1][1] <= lay.total and lay.total % align == 0
+    flat = torch.arange(lay.total, dtype=torch.float32)
+    back = torch.full((lay.total,), -1.0)
+    lay.from_ndarrays(back, lay.to_ndarrays(flat))
+    for i in range(len(lay.names)):
+        assert torch.equal(lay.view(back, i), lay.view(flat, i))
+    stacked = lay.stacked(("", "m/", "v/"))
+    assert stacked.total == 3 * lay.total and len(stacked.names) == 3 * len(lay.names)
+    assert torch.equal(stacked.view(torch.arange(stacked.total, dtype=torch.float32), "v/" + lay.names[0]).reshape(-1)[:1],
+                       torch.tensor([2.0 * lay.total + lay.offsets[0]]))
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 1 << 22), st.integers(1, 8), st.sampled_from([1, 4, 256]))
+def test_shard_bounds_tile_the_index_space(total, world, align):
+    b = shard_bounds(total, world, align)
+    assert len(b) == world and b[0][0] == 0 and b[-1][1] == total
+    assert all(lo <= hi for lo, hi in b) and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    assert all(lo % align == 0 for lo, _ in b[1:] if lo < total)
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 2 ** 31 - 1), st.floats(0.5, 1e4)), min_size=1, max_size=9))
+def test_streaming_mean_matches_textbook_mean(clients):
+    xs = [(torch.randn(257, generator=torch.Generator().manual_seed(seed)), w) for seed, w in clients]
+    sm, acc, n = StreamingMean(), None, 0.0
+    for x, w in xs:
+        sm.add(x, w)
+        acc, n = aggregate_parameters(acc, x, n, w)
+    want = naive_weighted_mean(xs)
+    assert torch.allclose(sm.result(), want, atol=1e-5) and torch.allclose(acc, want, atol=1e-5)
+    assert math.isclose(sm.total, sum(w for _, w in xs), rel_tol=1e-9) and math.isclose(n, sm.total, rel_tol=1e-9)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(0, 64), st.integers(1, 9))
+def test_chunks_and_device_groups_partition_exactly(n, k):
+    spans = list(chunks_idx(list(range(n)), k))
+    assert len(spans) == k and spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    if n >= k:
+        groups = split_devices(n, k)
+        assert sorted(d for g in groups for d in g) == list(range(n)) and max(map(len, groups)) - min(map(len, groups)) <= 1
+
+
+scalars = st.one_of(st.integers(-10 ** 6, 10 ** 6), st.booleans(), st.none(), st.floats(allow_nan=False, allow_infinity=False, width=32),
+                    st.text(alphabet="abcxyz_-/", min_size=1, max_size=8))
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.tuples(st.lists(st.sampled_from(["a", "b", "c", "d"]), min_size=1, max_size=3).map(".".join), scalars), min_size=1, max_size=6))
+def test_override_grammar_add_set_delete_roundtrip(assignments):
+    """``++k=v`` always lands, a later ``k=v`` overrides it, ``~k`` removes it, values keep their YAML type."""
+    cfg = ConfigNode({})
+    final = {}
+    for key, val in assignments:
+        text = "null" if val is None else ("true" if val is True else "false" if val is False else repr(val) if isinstance(val, float) else str(val))
+        # a key cannot be both a leaf and a parent: skip assignments that would contradict an earlier one
+        if any(k != key and (k.startswith(key + ".") or key.startswith(k + ".")) for k in final):
+            continue
+        apply_overrides(cfg, _ov("++" + key + "=" + text))
+        final[key] = parse_value(text)
+    for key, want in final.items():
+        node = cfg
+        for part in key.split("."):
+            node = node[part]
+        assert node == want or (isinstance(want, float) and math.isclose(node, want, rel_tol=1e-6))
+    for key in list(final):
+        apply_overrides(cfg, _ov("~" + key))
+        node, ok = cfg, True
+        for part in key.split("."):
+            if part not in node:
+                ok = False
+                break
+            node = node[part]
+        assert not ok
+
+
+def _ov(text):
+    from photon_b200.config.composer import DEFAULT_CONFIG_DIR, split_overrides
+
+    return split_overrides(DEFAULT_CONFIG_DIR, [text])[1]
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(0, 10 ** 6), st.sampled_from(["ba", "ep", "sp", "tok"]))
+def test_time_strings_roundtrip(value, unit):
+    t = Time.parse(f"{value}{unit}")
+    assert t.value == value and t.unit == unit and Time.parse(str(t)) == t
+    if unit == "ba":
+        assert t.to_batches() == value
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 12), st.lists(st.integers(1, 4), min_size=1, max_size=5), st.integers(0, 2 ** 16))
+def test_work_queue_dispatches_every_client_exactly_once(n_clients, speeds, seed):
+    """Whatever the node speeds and reply order, each sampled client runs exactly once, never two at a time on a node."""
+    import random
+
+    from photon_b200.server.server_util import ClientScheduler
+
+    rng = random.Random(seed)
+    nodes = list(range(100, 100 + len(speeds)))
+    speed = dict(zip(nodes, speeds))
+    running: dict[int, list[int]] = {}
+    dispatched: list[int] = []
+
+    def dispatch(node, cid):
+        assert node not in running, "node was handed a second client while busy"
+        running[node] = [cid, speed[node] + rng.randint(0, 2)]
+        dispatched.append(cid)
+
+    def poll():
+        done = []
+        for node in list(running):
+            running[node][1] -= 1
+            if running[node][1] <= 0:
+                done.append((node, running.pop(node)[0], None))
+        rng.shuffle(done)
+        return done
+
+    clients = rng.sample(range(1000), n_clients)
+    got = [cid for _, cid, _ in ClientScheduler(clients, nodes, dispatch, poll)]
+    assert sorted(got) == sorted(clients) == sorted(dispatched) and not running
+    assert dispatched[: min(len(nodes), n_clients)] == clients[: min(len(nodes), n_clients)]   # first wave in sampling order
