@@ -65,11 +65,14 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
         if runtime.world_size > 1:
             dist.barrier(group=runtime.group)
         resume = store.interpret_resume_round(run_uuid, ph.get("resume_round"), runtime.strategy.state_keys)
+    t_bcast = time.time()
     if resume is not None and resume > 0:
         history, time_offset = resume_from_round(runtime, store, run_uuid, resume)
         start_round = resume
     else:
         initialize_round(runtime, store, history)
+    if runtime.rank == 0:   # same keys as the reference's dashboards (ref: server_app.py:271-274)
+        history.add_metrics_centralized(start_round + 1, {"server/broadcast_pre_time": time.time() - t_bcast})
 
     wait_for_nodes_to_connect(runtime.n_nodes, runtime.node_ids, poll_s=0.0)
     eval_period = fl.get("eval_period")
@@ -82,7 +85,9 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
     total = int(fl["n_rounds"]) if n_rounds is None else start_round + n_rounds
     for server_round in range(start_round + 1, total + 1):
         t_round = time.time()
+        t_chk = time.time()
         node_ids = runtime.node_ids()                              # health check (ref: server_app.py:285)
+        first_check = time.time() - t_chk
         sampled = runtime.sample_clients()
         with tracer().span("fit_round", cat="server", server_round=server_round, clients=str(sampled)):
             metrics = fit_round(runtime, server_round, sampled)
@@ -101,8 +106,14 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
                                                state=server_state_dict(runtime, history, time_offset + time.time() - t_zero))
                 if cfg.get("cleanup_checkpoints_per_round"):
                     store.cleanup_checkpoints(run_uuid, per_round=True)
+        t_chk = time.time()
+        n_after = len(runtime.node_ids())                          # second liveness check after the round's broadcast (ref: :346)
         if runtime.rank == 0:
-            history.add_metrics_centralized(server_round, {"server/round_time": time.time() - t_round})
+            history.add_metrics_centralized(server_round, {
+                "server/round_time": time.time() - t_round, "server/first_check_nm_time": first_check,
+                "server/second_check_nm_time": time.time() - t_chk, "server/n_nodes_after_round": n_after,
+                # reduce + server optimizer + broadcast of the round (the reference times only its broadcast here)
+                "server/broadcast_post_time": float(runtime.timings.get("aggregate_broadcast_host_s", runtime.timings.get("server/broadcast_time", 0.0)))})
     if store is not None and cfg.get("cleanup_checkpoints") and runtime.rank == 0:
         store.cleanup_checkpoints(run_uuid)
     if wandb_run is not None:
