@@ -156,6 +156,11 @@ def manipulate_pre_training_params(trainer: Trainer, payload: Payload, fit_confi
     params = planes[0].clone() if torch.is_tensor(payload) and planes[0].data_ptr() == payload.data_ptr() else planes[0]
     metrics: dict[str, float] = {}
     pers = list(fit_config.personalized_layers or [])
+    # key filter (ref: photon/utils.py:640-670): only tensors whose name contains ``fl.set_trainer_key_to_filter`` are taken
+    # from the server. The flat payload always carries every tensor, so the filtered-out ones simply keep the client's local
+    # values — the same thing a reference client sees when those tensors never travel. ("transformer" matches all of MPT.)
+    if fit_config.set_trainer_params_filter_keys and fit_config.set_trainer_key_to_filter:
+        pers += [n for n in lay.names if fit_config.set_trainer_key_to_filter not in n]
     if fit_config.aggregate_momenta:
         metrics.update(set_optimizer_state(trainer, planes[1], planes[2], client_state.local_steps_cumulative, pers))
     if pers and client_state.local_steps_cumulative > 0:

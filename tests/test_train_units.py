@@ -339,3 +339,26 @@ def test_reference_named_helpers(tmp_path):
     m, v = l2_norm_of_momenta(tr.state.optimizer)
     assert m >= 0.0 and v >= 0.0
     tr.close()
+
+
+def test_key_filter_keeps_local_values_for_unmatched_tensors(tmp_path):
+    """``fl.set_trainer_key_to_filter``: tensors whose name lacks the key are not taken from the server payload."""
+    from photon_b200.clients.utils import manipulate_pre_training_params
+    from photon_b200.messages import ClientState
+
+    tr = _tiny_trainer(tmp_path)
+    lay = tr.state.flat.layout
+    local = tr.state.flat.params.clone()
+    server = torch.full_like(local, 7.0)
+    from photon_b200.clients.configs import get_photon_fit_config_fn
+    from photon_b200.config import compose
+
+    fc = get_photon_fit_config_fn(compose(["run_uuid=kf", "fl.set_trainer_key_to_filter=blocks"]))(2, 0, {0: ClientState(local_steps_cumulative=2)}, 2)
+    assert fc.set_trainer_params_filter_keys and fc.set_trainer_key_to_filter == "blocks"
+    got, _ = manipulate_pre_training_params(tr, server.clone(), fc, 0, ClientState(local_steps_cumulative=2))
+    for i, n in enumerate(lay.names):
+        want = server if "blocks" in n else local
+        assert torch.equal(lay.view(got, i), lay.view(want, i)), n
+    first, _ = manipulate_pre_training_params(tr, server.clone(), fc, 0, ClientState(local_steps_cumulative=0))
+    assert torch.equal(first, server)      # very first round: nothing local to keep yet
+    tr.close()
