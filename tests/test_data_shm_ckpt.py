@@ -196,7 +196,9 @@ def test_loader_state_tracks_the_consumer_not_the_prefetch_thread():
     seen = [next(it)["input_ids"].clone() for _ in range(5)]
     import time
 
-    time.sleep(0.3)  # let the prefetcher run ahead
+    t0 = time.time()
+    while a.dataset.sample_in_epoch <= 20 and time.time() - t0 < 10:   # let the prefetcher run ahead
+        time.sleep(0.02)
     sd = a.state_dict()
     assert sd["sample_in_epoch"] == 20 and a.dataset.sample_in_epoch > 20
     b = make()
