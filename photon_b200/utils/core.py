@@ -107,7 +107,24 @@ def set_trainer_params_from_ndarrays(arrays: Sequence[np.ndarray], trainer: Any,
     (ref: photon/utils.py:481-540)."""
     flat = _flat_of(trainer)
     names = [n for n in flat.layout.names if key_filter is None or key_filter in n]
-    set_trainer_trainable_params_dict(trainer, construct_parameters_dict(names, list(arrays)))
+    arrays = list(arrays)
+    try:
+        set_trainer_trainable_params_dict(trainer, construct_parameters_dict(names, arrays))
+    except ValueError as sorted_err:
+        # the reference's fallback for payloads written in MODEL DEFINITION order instead of sorted-name order
+        # (ref: photon/utils.py:515-540); only taken when the sorted interpretation does not even fit the shapes
+        model = getattr(getattr(getattr(trainer, "state", trainer), "backend", None), "model", None)
+        if model is None:
+            raise
+        unsorted = [clean_parameter_name(n) for n, p in model.named_parameters() if p.requires_grad]
+        unsorted = [n for n in unsorted if key_filter is None or key_filter in n]
+        if unsorted == names or len(unsorted) != len(arrays):
+            raise
+        try:
+            set_trainer_trainable_params_dict(trainer, construct_parameters_dict(unsorted, arrays))
+        except ValueError:
+            raise sorted_err from None
+        print("[params] payload did not fit the sorted-name layout; installed it in model-definition order")
 
 
 def get_wte_parameters_from_trainer(trainer: Any) -> np.ndarray:

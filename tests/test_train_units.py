@@ -362,3 +362,22 @@ def test_key_filter_keeps_local_values_for_unmatched_tensors(tmp_path):
     first, _ = manipulate_pre_training_params(tr, server.clone(), fc, 0, ClientState(local_steps_cumulative=0))
     assert torch.equal(first, server)      # very first round: nothing local to keep yet
     tr.close()
+
+
+def test_param_install_falls_back_to_definition_order(tmp_path):
+    """A payload in model-definition order (not sorted-name order) is still installed when the sorted reading does not fit the
+    shapes — the reference's ordered→unordered retry (ref: photon/utils.py:515-540); garbage still raises."""
+    from photon_b200.utils.core import get_trainable_params_dict, set_trainer_params_from_ndarrays
+
+    tr = _tiny_trainer(tmp_path)
+    model = tr.state.backend.model
+    defn = [(n, p.detach().clone()) for n, p in model.named_parameters() if p.requires_grad]
+    assert [n for n, _ in defn] != sorted(n for n, _ in defn)
+    payload = [(p * 0 + i).numpy() for i, (_, p) in enumerate(defn)]        # tensor k of the definition order is filled with k
+    set_trainer_params_from_ndarrays(payload, tr)
+    got = get_trainable_params_dict(tr)
+    for i, (n, _) in enumerate(defn):
+        assert float(got[n].mean()) == float(i), n
+    with pytest.raises(ValueError):
+        set_trainer_params_from_ndarrays([np.zeros((3, 3), np.float32)] * len(defn), tr)
+    tr.close()
