@@ -379,3 +379,24 @@ def test_restore_run_brings_client_checkpoints_along(tmp_path):
     new = sorted(p.relative_to(tmp_path / "new").as_posix() for p in (tmp_path / "new" / "clients").rglob("ep*-rank0.pt"))
     assert set(old) <= set(new)
     assert [r for r, _ in h.metrics_distributed_fit["server/n_failures"]][-1] == 2
+
+
+def test_round_lost_by_a_server_crash_is_rebuilt_from_client_checkpoints(tmp_path):
+    """The server dies after the clients finished round 2 but before the round was checkpointed. On restart round 2 runs again;
+    every client finds its ``ba == target`` checkpoint, skips training and returns those weights, so the rebuilt round equals
+    the lost one bit for bit (ref: llm_config_functions.py:724-761 skip/resume, llm_client_functions.py:163,207)."""
+    import shutil
+
+    from photon_b200.checkpoint import CheckpointStore
+    from photon_b200.server_app import run_server
+
+    base = ["run_uuid=mid", "photon.checkpoint=true", "fl.n_clients_per_round=4", "fl.n_rounds=2", "llm_config.save_num_checkpoints_to_keep=-1"]
+    run_server(_cfg(tmp_path, *base))
+    store = CheckpointStore(tmp_path, "checkpoints")
+    with np.load(store.round_dir("mid", 2) / "current_server_parameters.npz") as z:
+        want = [z[k] for k in z.files]
+    shutil.rmtree(store.round_dir("mid", 2))
+    h = run_server(_cfg(tmp_path, *base, "photon.resume_round=-1"))
+    with np.load(store.round_dir("mid", 2) / "current_server_parameters.npz") as z:
+        assert all(np.array_equal(a, z[k]) for a, k in zip(want, z.files))
+    assert h.metrics_distributed_fit["client/fit_time"][-1][1] < 0.05      # nobody trained: the weights came from the checkpoints
