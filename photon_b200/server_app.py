@@ -95,17 +95,19 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
         if runtime.rank == 0:
             history.add_metrics_distributed_fit(server_round, metrics)
         if eval_period and server_round % int(eval_period) == 0:
-            loss, em = evaluate_round(runtime, server_round)
+            with tracer().span("evaluate_round", cat="server", server_round=server_round):
+                loss, em = evaluate_round(runtime, server_round)
             if runtime.rank == 0 and loss is not None:
                 history.add_loss_distributed(server_round, loss)
                 history.add_metrics_distributed(server_round, em)
         if store is not None:
             tensors = runtime.state_tensors()                      # collective when moments are sharded
             if runtime.rank == 0:
-                store.upload_server_checkpoint(run_uuid, server_round, layout=runtime.layout, tensors=tensors,
-                                               state=server_state_dict(runtime, history, time_offset + time.time() - t_zero))
-                if cfg.get("cleanup_checkpoints_per_round"):
-                    store.cleanup_checkpoints(run_uuid, per_round=True)
+                with tracer().span("server_checkpoint", cat="server", server_round=server_round):
+                    store.upload_server_checkpoint(run_uuid, server_round, layout=runtime.layout, tensors=tensors,
+                                                   state=server_state_dict(runtime, history, time_offset + time.time() - t_zero))
+                    if cfg.get("cleanup_checkpoints_per_round"):
+                        store.cleanup_checkpoints(run_uuid, per_round=True)
         t_chk = time.time()
         n_after = len(runtime.node_ids())                          # second liveness check after the round's broadcast (ref: :346)
         if runtime.rank == 0:
