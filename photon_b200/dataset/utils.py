@@ -21,6 +21,9 @@ class ByteTokenizer:
     def encode(self, text: str) -> list[int]:
         return [b + 1 for b in text.encode("utf-8")]
 
+    def decode(self, ids: Iterable[int]) -> str:
+        return bytes(int(i) - 1 for i in ids if 0 < int(i) <= 256).decode("utf-8", errors="replace")
+
     def save_pretrained(self, path: str | Path) -> None:
         Path(path).mkdir(parents=True, exist_ok=True)
         (Path(path) / "tokenizer_config.json").write_text(json.dumps({"tokenizer_class": "ByteTokenizer", "vocab_size": 257}))

@@ -9,9 +9,13 @@ self-contained implementation of the two task types that dominate those tables:
 * ``multiple_choice``     — pick the choice with the highest length-normalised log-likelihood;
   ``schema`` tasks are scored the same way with the context varying instead of the continuation.
 
-``generation_task_with_answers`` (free generation) is reported as unsupported — it needs sampling
-loops that are out of scope of the training engine.  Datasets are jsonl files resolved against
-``icl_tasks_config.root_dir`` (there is no network, so missing files yield ``skipped``).
+* ``generation_task_with_answers`` — greedy decoding (one ``logits_fn`` call per new token, no KV cache: this is an
+  evaluation utility, not a serving path) until ``max_new_tokens`` or an ``early_stopping_criteria`` string; exact match
+  against any of the ``answer`` / ``aliases`` after llm-foundry's normalisation (lower-case, punctuation and articles
+  stripped) unless ``do_normalization: false``; with a ``cot_delimiter`` only the text after it counts.
+
+Datasets are jsonl files resolved against ``icl_tasks_config.root_dir`` (there is no network, so missing files yield
+``skipped``).
 """
 from __future__ import annotations
 
@@ -22,7 +26,8 @@ from typing import Any, Callable
 import torch
 
 TASK_DEFAULTS = {"num_fewshot": [0], "continuation_delimiter": " ", "example_delimiter": "\n", "prompt_string": "",
-                 "question_prelimiter": "", "batch_size": 4}
+                 "question_prelimiter": "", "batch_size": 4, "max_new_tokens": 64, "early_stopping_criteria": [],
+                 "cot_delimiter": "", "do_normalization": True}
 
 
 def expand_task(task: dict[str, Any]) -> dict[str, Any]:
@@ -33,6 +38,15 @@ def expand_task(task: dict[str, Any]) -> dict[str, Any]:
     if "label" not in t or "dataset_uri" not in t or "icl_task_type" not in t:
         raise ValueError(f"ICL task needs label/dataset_uri/icl_task_type: {task}")
     return t
+
+
+def _normalize_answer(text: str) -> str:
+    """llm-foundry's exact-match normalisation: lower-case, drop punctuation and articles, squeeze whitespace."""
+    import re
+    import string
+
+    text = "".join(ch for ch in text.lower() if ch not in set(string.punctuation))
+    return " ".join(re.sub(r"\b(a|an|the)\b", " ", text).split())
 
 
 def _rows(path: Path) -> list[dict[str, Any]]:
@@ -70,21 +84,48 @@ class ICLEvaluator:
         lp = logp[pos].cpu()
         return float(lp[torch.arange(n), tgt].sum()), bool((lp.argmax(-1) == tgt).all())
 
+    @torch.no_grad()
+    def _generate(self, ctx: list[int], max_new_tokens: int, stops: list[str]) -> str:
+        """Greedy continuation of ``ctx`` as text, cut at the first stop string."""
+        ids, new = list(ctx), []
+        eos = getattr(self.tok, "eos_token_id", None)
+        for _ in range(max_new_tokens):
+            window = ids[-self.max_seq_len:]
+            nxt = int(self.logits_fn(torch.tensor([window], dtype=torch.long))[0, -1].float().argmax())
+            if eos is not None and nxt == eos:
+                break
+            ids.append(nxt), new.append(nxt)
+            text = self.tok.decode(new)
+            hit = [text.index(s) for s in stops if s and s in text]
+            if hit:
+                return text[: min(hit)]
+        return self.tok.decode(new)
+
     def evaluate_task(self, task: dict[str, Any]) -> dict[str, float | str]:
         t = expand_task(task)
         path = self.root / t["dataset_uri"]
         if not path.exists():
             return {"status": "skipped (dataset missing offline)"}
         kind = t["icl_task_type"]
-        if kind not in ("language_modeling", "multiple_choice", "schema"):
+        if kind not in ("language_modeling", "multiple_choice", "schema", "generation_task_with_answers"):
             return {"status": f"unsupported task type {kind}"}
+        if kind == "generation_task_with_answers" and not hasattr(self.tok, "decode"):
+            return {"status": "generation tasks need a tokenizer with decode()"}
         rows = _rows(path)
         out: dict[str, float | str] = {}
         for k in t["num_fewshot"]:
             correct = 0
             for i, r in enumerate(rows):
                 prefix = self._fewshot_prefix(rows, i, k, t)
-                if kind == "language_modeling":
+                if kind == "generation_task_with_answers":
+                    ctx = self._enc(prefix + t["question_prelimiter"] + r["context"] + t["continuation_delimiter"].rstrip())
+                    text = self._generate(ctx, int(t["max_new_tokens"]), list(t["early_stopping_criteria"] or []))
+                    if t["cot_delimiter"] and t["cot_delimiter"] in text:
+                        text = text.split(t["cot_delimiter"])[-1]
+                    golds = [str(r["answer"])] + [str(a) for a in r.get("aliases", [])]
+                    norm = _normalize_answer if t["do_normalization"] else (lambda x: x.strip())
+                    correct += int(any(norm(text).startswith(norm(g)) for g in golds if norm(g)))
+                elif kind == "language_modeling":
                     ctx = self._enc(prefix + t["question_prelimiter"] + r["context"] + t["continuation_delimiter"].rstrip())
                     _, em = self._continuation_stats(ctx, self._enc(" " + r["continuation"].lstrip()))
                     correct += int(em)

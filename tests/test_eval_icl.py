@@ -66,3 +66,20 @@ def test_icl_suite_runs_inside_trainer_eval(tmp_path):
     logged = tr.loggers[0].data
     assert "metrics/icl/mc/0-shot/accuracy" in logged and "icl/metrics/eval_gauntlet/core_average" in logged
     tr.close()
+
+
+def test_icl_generation_task_greedy_decode_with_stops_and_cot(tmp_path):
+    """The +1 'model' continues 'a' with 'bcdefg…': generation stops at the stop string, answers are normalised, aliases count,
+    and with a chain-of-thought delimiter only the text after it is compared."""
+    tok = ByteTokenizer()
+    rows = [{"context": "a", "answer": "BCD"}, {"context": "a", "answer": "zz", "aliases": ["b c d".replace(" ", "")]}, {"context": "k", "answer": "nope"}]
+    (tmp_path / "gen.jsonl").write_text("\n".join(json.dumps(r) for r in rows))
+    ev = ICLEvaluator(_fake_logits, tok, 64, str(tmp_path))
+    task = {"label": "gen", "dataset_uri": "gen.jsonl", "icl_task_type": "generation_task_with_answers", "num_fewshot": [0],
+            "continuation_delimiter": "", "early_stopping_criteria": ["e"], "max_new_tokens": 8}
+    assert math.isclose(ev.evaluate_task(task)["gen/0-shot/accuracy"], 2 / 3)
+    assert ev._generate(tok.encode("a"), 8, ["e"]) == "bcd" and ev._generate(tok.encode("a"), 3, []) == "bcd"   # noqa: SLF001
+    (tmp_path / "cot.jsonl").write_text(json.dumps({"context": "a", "answer": "fg"}))
+    cot = {"label": "cot", "dataset_uri": "cot.jsonl", "icl_task_type": "generation_task_with_answers", "continuation_delimiter": "",
+           "cot_delimiter": "e", "early_stopping_criteria": ["h"], "max_new_tokens": 10, "do_normalization": False}
+    assert ev.evaluate_task(cot)["cot/0-shot/accuracy"] == 1.0
