@@ -1,0 +1,5 @@
+"""``FedAdam`` under the reference's module path (ref: photon/strategy/fedadam.py:291-318). All five server optimizers share one
+implementation — ``photon_b200.strategy.strategies`` (host / oracle path) and ``csrc/comm.cu`` (fused NVLink round kernel)."""
+from photon_b200.strategy.strategies import FedAdam, server_opt_step  # noqa: F401
+
+__all__ = ["FedAdam"]
