@@ -1,4 +1,5 @@
 import os
+from pathlib import Path
 
 import pytest
 
@@ -96,3 +97,25 @@ def test_resolver_takes_hydra_config_dir_flags(tmp_path, monkeypatch):
     assert load_config(hydra_resolver.main(["run_uuid=x"])).seed == 1337
     monkeypatch.setenv("PHOTON_CONFIG_DIR", str(mine))
     assert load_config(hydra_resolver.main(["run_uuid=x"])).seed == 4242
+
+
+def test_photon_import_alias_resolves_to_the_same_modules(tmp_path, monkeypatch):
+    """Code written against the reference's package name keeps working: ``photon.X`` IS ``photon_b200.X``."""
+    import subprocess
+    import sys
+
+    import photon.strategy.fedadam as alias
+    from photon.utils import get_parameters_from_state  # noqa: F401
+
+    import photon_b200.strategy.strategies as real
+
+    assert alias.FedAdam is real.FedAdam
+    import photon.clients.utils as a
+    import photon_b200.clients.utils as b
+
+    assert a is b
+    with pytest.raises(ModuleNotFoundError):
+        import photon.does_not_exist  # noqa: F401
+    out = subprocess.run([sys.executable, "-m", "photon.hydra_resolver", "run_uuid=alias"], capture_output=True, text=True,
+                         env={**__import__("os").environ, "PHOTON_SAVE_PATH": str(tmp_path)}, cwd=str(Path(__file__).resolve().parents[1]))
+    assert out.returncode == 0 and (tmp_path / "config.yaml").exists(), out.stderr[-500:]
