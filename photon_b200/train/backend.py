@@ -78,6 +78,11 @@ class TorchBackend:
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
         self.flat = FlatParams(self.model, device=self.device, params_storage=params_storage, grads_storage=grads_storage)
         self.bf16_params = shadow_storage   # only kept so a fused NVLink step has a plane to write (autocast casts on the fly)
+        self.fp8_layers: list[str] = []
+        if precision == "amp_fp8":          # E4M3 forward / E5M2 backward GEMM operands with delayed scaling, bf16 elsewhere
+            from photon_b200.train.fp8 import enable_fp8
+
+            self.fp8_layers = enable_fp8(self.model)
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.collect_activation_stats = False
         self.activation_stats: dict[str, float] = {}

@@ -439,9 +439,18 @@ class Trainer:
                 "callbacks": {type(c).__name__: c.state_dict() for c in self.callbacks},
                 "run_name": st.run_name,
                 "scaler": {"scale": self.scaler.scale} if self.scaler else None,
+                "fp8": self._fp8_state(),
             },
             "rng": {"torch": torch.get_rng_state(), "seed": self.seed},
         }
+
+    def _fp8_state(self) -> dict[str, Any] | None:
+        """amax histories / scales of an ``amp_fp8`` run (the delayed-scaling recipe resumes with the scales it stopped with)."""
+        if not getattr(self.state.backend, "fp8_layers", None):
+            return None
+        from photon_b200.train.fp8 import fp8_state_dict
+
+        return fp8_state_dict(self.state.backend.model)
 
     def checkpoint_name(self) -> str:
         ts = self.state.timestamp
@@ -496,6 +505,10 @@ class Trainer:
                 self._train_iter = None
         if self.scaler and s.get("scaler") and not ignored("scaler"):
             self.scaler.scale = float(s["scaler"]["scale"])
+        if s.get("fp8") and getattr(st.backend, "fp8_layers", None) and not ignored("fp8"):
+            from photon_b200.train.fp8 import load_fp8_state_dict
+
+            load_fp8_state_dict(st.backend.model, s["fp8"])
         if not ignored("rng") and "rng" in ck and "torch" in ck["rng"]:
             torch.set_rng_state(ck["rng"]["torch"])
 

