@@ -146,6 +146,8 @@ def main() -> None:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     if N_CLIENTS % world:
         raise SystemExit("--gpus must divide 8")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py measures the sm_100a engine: it needs a CUDA (B200) device and does not fall back to the CPU")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
