@@ -221,8 +221,14 @@ class MDSReader:
                 continue
             payload = sample[pos:pos + ln]
             kind, _, rest = enc.partition(":")
+            if kind == "bytes":
+                # older llm-foundry converters store ``np.int64`` token ids as raw bytes (read back with
+                # ``np.frombuffer(sample["tokens"], dtype=np.int64)``); accept int32 too when the length only fits that
+                want = getattr(self, "seq_len", None)
+                dt = np.dtype(np.int64) if (ln % 8 == 0 and (want is None or ln == 8 * want)) else np.dtype(np.int32)
+                return np.frombuffer(payload, dt).astype(np.int32)
             if kind != "ndarray":
-                raise ValueError(f"column {name!r} has encoding {enc!r}; expected ndarray:int32")
+                raise ValueError(f"column {name!r} has encoding {enc!r}; expected ndarray:<dtype> or bytes")
             dtype = np.dtype(rest.split(":")[0] or "int32")
             # shape header: 1 byte (rank / width code) + rank × {1,2,4,8}-byte dims; rank is 1 for token rows
             for width in (0, 1, 2, 4, 8):

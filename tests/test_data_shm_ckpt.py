@@ -245,6 +245,27 @@ def test_state_bin_written_by_the_reference_is_readable(tmp_path, monkeypatch):
     assert decode_client_states(st["client_state"])[0].local_steps_cumulative == 4
 
 
+def test_mds_bytes_column_of_older_converters(tmp_path):
+    """``columns={"tokens": "bytes"}`` with int64 ids (older llm-foundry ``ConcatTokensDataset``)."""
+    import json as _json
+
+    from photon_b200.data.shards import MDSReader
+
+    rows = [np.arange(i, i + 16, dtype=np.int64) for i in range(3)]
+    cols = {"column_encodings": ["bytes"], "column_names": ["tokens"], "column_sizes": [None]}
+    config = _json.dumps({**cols, "format": "mds"}).encode()
+    samples = [np.uint32(r.nbytes).tobytes() + r.tobytes() for r in rows]
+    offsets = np.array([0] + [len(x) for x in samples]).cumsum().astype(np.uint32)
+    offsets += 4 + offsets.nbytes + len(config)
+    d = tmp_path / "old"
+    d.mkdir()
+    (d / "shard.00000.mds").write_bytes(np.uint32(3).tobytes() + offsets.tobytes() + config + b"".join(samples))
+    (d / "index.json").write_text(_json.dumps({"version": 2, "shards": [{**cols, "compression": None, "format": "mds", "samples": 3, "version": 2,
+                                                                        "raw_data": {"basename": "shard.00000.mds", "bytes": 0, "hashes": {}}, "zip_data": None}]}))
+    r = MDSReader(d)
+    assert r.seq_len == 16 and np.array_equal(r[2], rows[2].astype(np.int32)) and r[0].dtype == np.int32
+
+
 def _write_mds(directory, rows, shard_samples, compression=None):
     """mosaicml-streaming's MDS layout for ``columns={"tokens": "ndarray:int32"}`` (see MDSReader's docstring)."""
     import json as _json
