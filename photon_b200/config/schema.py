@@ -51,6 +51,7 @@ class Centralized(_Strict):
 
 class Photon(_Strict):
     n_nodes: int = 1
+    task_timeout_s: float | None = None   # node manager: presume the workers hung after this long without a result (null = wait forever)
     topology: str = "spmd"   # spmd: one process per GPU + fused round transports; nodes: server → ClientApp → NodeManager → Workers
     refresh_period: int = 50
     checkpoint: bool = False

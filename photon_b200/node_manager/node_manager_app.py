@@ -48,6 +48,10 @@ class NodeManagerApp:
         n_gpu = len(self.devices) if self.devices else 0
         self.n_workers = int(n_workers or max(1, n_gpu))
         self.max_retries, self.poll_s = int(max_retries), float(poll_s)
+        # a worker that neither answers nor dies (a wedged collective, a stuck filesystem) is treated like a dead one after
+        # ``photon.task_timeout_s``: the pool is torn down, respawned and the client retried. null = wait forever (reference).
+        tmo = (self.cfg_dict.get("photon") or {}).get("task_timeout_s")
+        self.task_timeout_s = float(tmo) if tmo else None
         ctx = mp.get_context("spawn")
         self.task_queue: Any = ctx.Queue()
         self.result_queue: Any = ctx.Queue()
@@ -109,12 +113,15 @@ class NodeManagerApp:
         for _ in self.workers:
             self.task_queue.put((cid, kind))
         got: list[Any] = []
+        t0 = time.time()
         while len(got) < self.n_workers:
             try:
                 msg = self.result_queue.get(timeout=self.poll_s)
             except queue.Empty:
                 if any(not w.is_alive() for w in self.workers):
                     return None, "a worker died while running the task"
+                if self.task_timeout_s is not None and time.time() - t0 > self.task_timeout_s:
+                    return None, f"no result after {self.task_timeout_s:.0f}s (photon.task_timeout_s): workers presumed hung"
                 continue
             if msg.n_samples < 0:
                 return None, msg.error or "worker reported failure"
@@ -125,7 +132,7 @@ class NodeManagerApp:
     def _with_retries(self, cid: int, kind: str, task_cfg: dict[str, Any]) -> tuple[Any, str | None]:
         err: str | None = None
         for attempt in range(self.max_retries + 1):
-            msg, err = self._run_client(cid, kind, task_cfg if attempt == 0 else {k: v for k, v in task_cfg.items() if k != "inject_failure"})
+            msg, err = self._run_client(cid, kind, task_cfg if attempt == 0 else {k: v for k, v in task_cfg.items() if k not in ("inject_failure", "inject_hang")})
             if msg is not None:
                 return msg, None
             self.close_workers()   # soft close then terminate; next attempt respawns (ref: node_manager_app.py:553-579)

@@ -84,6 +84,8 @@ class Worker(mp.get_context("spawn").Process):  # type: ignore[misc,name-defined
         task_cfg = all_cfg[str(cid)]
         if task_cfg.get("inject_failure") and self.worker_rank == 0:
             raise RuntimeError(f"fault injection: worker failure on client {cid}")
+        if task_cfg.get("inject_hang") and self.worker_rank == 0:     # fault injection: alive, silent, never finishing
+            time.sleep(3600)
         with env_patcher(self.worker_rank, self.n_workers, int(task_cfg["MASTER_PORT"]), self.devices):
             n, _ = (self.fit_action if kind == "fit" else self.evaluate_action)(cid, task_cfg)
         for h in self._keep[:-2]:

@@ -134,6 +134,11 @@ def test_node_manager_workers_over_shm(tmp_path):
         # a failing worker is reported, the pool is rebuilt and the retry succeeds
         res2 = app.nm.fit({1: {"fit_config": fn(1, 1, states, 0).to_wire(), "inject_failure": True}})
         assert res2[0].status.code == Code.OK and all(w.is_alive() for w in app.nm.workers)
+        # a worker that hangs (alive, silent) is caught by photon.task_timeout_s: pool torn down, respawned, client retried
+        app.nm.task_timeout_s = 15.0   # must exceed a respawn + one tiny fit (worker start-up imports torch)
+        old_pids = [w.pid for w in app.nm.workers]
+        res3 = app.nm.fit({2: {"fit_config": fn(1, 2, states, 0).to_wire(), "inject_hang": True}})
+        assert res3[0].status.code == Code.OK and [w.pid for w in app.nm.workers] != old_pids
 
 
 def test_two_rank_gloo_federation(tmp_path):
