@@ -149,6 +149,15 @@ class FederationRuntime:
     def run_clients_fit(self, server_round: int, sampled: list[int]) -> list[FitRes]:
         assert self.trainer is not None and self.round_backend is not None
         rb, tr = self.round_backend, self.trainer
+        period = int(self.cfg["photon"].get("refresh_period", 0) or 0)
+        if period and server_round > 1 and server_round % period == 0:
+            # the reference recycles its worker PROCESSES here to shed leaked memory (ref: client_app.py:175-177); a rank of
+            # the SPMD job cannot restart itself, so it drops what can be dropped: python garbage and the allocator's cache
+            import gc
+
+            gc.collect()
+            if self.device.type == "cuda":
+                torch.cuda.empty_cache()
         rb.begin_round()
         results: list[FitRes] = []
         keep_opt = not bool(self.cfg["fl"]["reset_optimizer"])
