@@ -237,10 +237,17 @@ def get_stream_freq_dict_for_client(train_cfg: Any, cid: int | str | None, split
                                     allow_failures: bool = False, cache_dir: str = "/tmp") -> dict[str, int] | None:
     """Merge ``{stream}/{split}/1_gram.json`` over the client's streams; synthetic streams use
     the generator's exact distribution. Cached as ``{cache_dir}/{cid}_freq_dict.json``."""
-    cache = Path(cache_dir) / f"{cid}_freq_dict.json"
+    streams = (train_cfg["train_loader"]["dataset"].get("streams") or {})
+    vocab = int((train_cfg.get("model") or {}).get("vocab_size", 0) or 0)
+    # the reference keys this cache by client id only (``/tmp/{cid}_freq_dict.json``), so a second experiment on the same box
+    # silently reuses the first one's table; here the key also covers WHAT was counted
+    import hashlib
+
+    sig = hashlib.sha1(json.dumps([sorted((n, str((s or {}).get("local")), str((s or {}).get("split") or split)) for n, s in streams.items()),
+                                   vocab]).encode()).hexdigest()[:10]  # noqa: S324
+    cache = Path(cache_dir) / f"{cid}_{sig}_freq_dict.json"
     if cache.exists():
         return json.loads(cache.read_text())
-    streams = (train_cfg["train_loader"]["dataset"].get("streams") or {})
     dicts = []
     for name, st in streams.items():
         local = (st or {}).get("local")
@@ -249,7 +256,10 @@ def get_stream_freq_dict_for_client(train_cfg: Any, cid: int | str | None, split
         if path is not None and path.exists():
             dicts.append(json.loads(path.read_text()))
         elif local is None or str(local).startswith("synthetic://") or not Path(str(local)).exists():
-            p = SyntheticC4().unigram_probabilities()
+            from photon_b200.data.synthetic import TOKENIZER_VOCAB
+
+            # the stand-in stream is generated inside the model's vocabulary (see build_text_loader): count the same thing
+            p = SyntheticC4(vocab_size=min(vocab, TOKENIZER_VOCAB) if vocab else TOKENIZER_VOCAB).unigram_probabilities()
             dicts.append({str(i): int(round(x * 1e9)) for i, x in enumerate(p) if x > 0})
         elif not allow_failures:
             raise FileNotFoundError(f"1_gram.json missing for stream '{name}' at {path}")
