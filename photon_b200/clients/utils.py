@@ -256,11 +256,14 @@ def pseudo_gradient_norm(initial: torch.Tensor, final: torch.Tensor) -> float:
     return float(math.sqrt(float(((initial - final).double() ** 2).sum())))
 
 
-def streaming_shms_clean_up(prefixes: Sequence[str] = ("photon_", "pb200_")) -> int:
-    """Unlink stale POSIX shared-memory segments left by crashed workers / loaders and collect
-    garbage (ref: clients/utils.py:655-673, which leans on streaming's stale-shm sweep)."""
+def streaming_shms_clean_up(prefixes: Sequence[str] = ("photon_", "pb200_", "nm-"), min_age_s: float = 0.0) -> int:
+    """Unlink stale POSIX shared-memory segments left by crashed node managers / workers / loaders and collect garbage
+    (ref: clients/utils.py:655-673, which leans on streaming's stale-shm sweep). ``min_age_s`` spares segments younger
+    than that (another federation may be starting on the same box): ``python -m photon_b200.clients.utils 3600`` removes
+    what has not been touched for an hour."""
     import gc
     import os
+    import time as _time
 
     removed = 0
     try:
@@ -269,9 +272,22 @@ def streaming_shms_clean_up(prefixes: Sequence[str] = ("photon_", "pb200_")) -> 
         names = []
     from photon_b200.shm.utils import unlink_quietly
 
+    now = _time.time()
     for n in names:
-        if n.startswith(tuple(prefixes)):
-            unlink_quietly(n)
-            removed += 1
+        if not n.startswith(tuple(prefixes)):
+            continue
+        try:
+            if min_age_s and now - os.stat(os.path.join("/dev/shm", n)).st_mtime < min_age_s:
+                continue
+        except OSError:
+            continue
+        unlink_quietly(n)
+        removed += 1
     gc.collect()
     return removed
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(f"[shm] removed {streaming_shms_clean_up(min_age_s=float(sys.argv[1]) if len(sys.argv) > 1 else 600.0)} stale segment(s)")

@@ -93,6 +93,15 @@ class Worker(mp.get_context("spawn").Process):  # type: ignore[misc,name-defined
         self._keep = self._keep[-2:]
         self.result_queue.put(WorkerResultMessage(n_samples=int(n), delta=time.time() - t0, worker_uuid=self.worker_uuid, cid=cid))
 
+    def _sweep_orphaned_segments(self) -> None:
+        from photon_b200.shm.utils import close_all_shms, unlink_quietly
+
+        close_all_shms(self.worker_uuid)
+        unlink_quietly(self.worker_uuid + C.W_PARAMS_SHM + "_meta")
+        if self.worker_rank == 0:
+            close_all_shms(self.nm_uuid)
+            unlink_quietly(self.nm_uuid + C.NM_PARAMS_SHM + "_meta")
+
     # ------------------------------------------------------------------------- loop
     def run(self) -> None:
         os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 2) // max(1, self.n_workers))))
@@ -101,7 +110,8 @@ class Worker(mp.get_context("spawn").Process):  # type: ignore[misc,name-defined
             try:
                 task = self.task_queue.get(timeout=2.0)
             except queue.Empty:
-                if os.getppid() != parent:   # the node manager is gone (killed server): do not linger as an orphan
+                if os.getppid() != parent:   # the node manager is gone (killed server): do not linger as an orphan,
+                    self._sweep_orphaned_segments()   # and do not leave its /dev/shm segments (nor ours) behind
                     return
                 continue
             if task is None:

@@ -405,3 +405,47 @@ def test_round_lost_by_a_server_crash_is_rebuilt_from_client_checkpoints(tmp_pat
     with np.load(store.round_dir("mid", 2) / "current_server_parameters.npz") as z:
         assert all(np.array_equal(a, z[k]) for a, k in zip(want, z.files))
     assert h.metrics_distributed_fit["client/fit_time"][-1][1] < 0.05      # nobody trained: the weights came from the checkpoints
+
+
+def test_killed_server_leaves_no_orphan_workers_and_no_shm_segments(tmp_path):
+    """SIGKILL the node-topology server mid-run: its worker processes notice the missing parent, exit on their own and take the
+    node manager's /dev/shm segments with them (the reference leaks both)."""
+    import signal
+    import time
+
+    script = tmp_path / "srv.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})
+        if __name__ == "__main__":
+            from photon_b200.config import compose
+            from photon_b200.server.fleet import NodeFleetRuntime
+            from photon_b200.server_app import run_server
+            cfg = compose({TINY!r} + ["run_uuid=orphan", "photon.topology=nodes", "photon.n_nodes=1", "fl.n_rounds=100000", "fl.eval_period=null",
+                                    "llm_config.save_folder=null", "photon.saving_path={tmp_path}"])
+            rt = NodeFleetRuntime(cfg)
+            rt.build()
+            print("NM", rt.apps[0].nm.nm_uuid, " ".join(str(w.pid) for w in rt.apps[0].nm.workers), flush=True)
+            run_server(cfg, runtime=rt)
+    """))
+    proc = subprocess.Popen([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    try:
+        line = ""
+        t0 = time.time()
+        while not line.startswith("NM ") and time.time() - t0 < 120:
+            line = proc.stdout.readline()
+        assert line.startswith("NM "), "server did not come up"
+        _, nm_uuid, *pids = line.split()
+        time.sleep(3.0)                                     # a few rounds in
+        assert any(n.startswith(nm_uuid) for n in os.listdir("/dev/shm"))
+        proc.send_signal(signal.SIGKILL)
+        proc.wait(timeout=30)
+        deadline = time.time() + 60
+        alive = lambda pid: Path(f"/proc/{pid}").exists() and "zombie" not in Path(f"/proc/{pid}/status").read_text().lower()  # noqa: E731
+        while time.time() < deadline and (any(alive(p) for p in pids) or any(n.startswith(nm_uuid) for n in os.listdir("/dev/shm"))):
+            time.sleep(0.5)
+        assert not any(alive(p) for p in pids), "worker processes outlived the killed server"
+        assert not [n for n in os.listdir("/dev/shm") if n.startswith(nm_uuid)], "node-manager segments were left in /dev/shm"
+    finally:
+        if proc.poll() is None:
+            proc.kill()
