@@ -151,3 +151,65 @@ def test_work_queue_dispatches_every_client_exactly_once(n_clients, speeds, seed
     got = [cid for _, cid, _ in ClientScheduler(clients, nodes, dispatch, poll)]
     assert sorted(got) == sorted(clients) == sorted(dispatched) and not running
     assert dispatched[: min(len(nodes), n_clients)] == clients[: min(len(nodes), n_clients)]   # first wave in sampling order
+
+
+arrays = st.lists(st.tuples(st.lists(st.integers(1, 5), min_size=0, max_size=3), st.sampled_from(["float32", "float16", "int32", "int64"])), min_size=1, max_size=6)
+
+
+@settings(max_examples=40, deadline=None)
+@given(arrays, st.integers(0, 2 ** 16))
+def test_shm_metadata_codec_and_segment_roundtrip(specs, seed):
+    """Any mix of shapes / dtypes survives metadata → literal string → metadata and a trip through one flat POSIX segment."""
+    import uuid
+
+    from photon_b200.shm.utils import ModelParametersMetadata, get_parameters_shm, set_parameters_shm, unlink_quietly
+
+    rng = np.random.default_rng(seed)
+    arrs = [(rng.standard_normal(tuple(shp)) * 100).astype(dt) for shp, dt in specs]
+    meta = ModelParametersMetadata.from_ndarrays(arrs)
+    again = ModelParametersMetadata.from_literal(meta.to_literal())
+    assert again == meta and all(lo % 64 == 0 and hi - lo == a.nbytes for (lo, hi), a in zip(meta.array_bounds, arrs))
+    assert all(a[1] <= b[0] for a, b in zip(meta.array_bounds, meta.array_bounds[1:]))
+    name = f"pbt_prop_{uuid.uuid4().hex[:10]}"
+    shm, _ = set_parameters_shm(name, arrs)
+    try:
+        h, views = get_parameters_shm(name, again, copy=True)
+        h.close()
+        assert all(v.dtype == a.dtype and v.shape == a.shape and np.array_equal(v, a) for v, a in zip(views, arrs))
+    finally:
+        shm.close()
+        unlink_quietly(name)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.lists(st.integers(0, 30), min_size=0, max_size=8, unique=True), st.sampled_from([None, -1, -2, 0, 3, 7]))
+def test_resume_round_resolution(rounds, want):
+    """``photon.resume_round``: None → fresh start; negative → counted from the newest COMPLETE round; k → must be complete."""
+    import tempfile
+
+    from photon_b200.checkpoint import CheckpointStore
+
+    with tempfile.TemporaryDirectory() as tmp:
+        store = CheckpointStore(tmp, "b")
+        keys = ["current_server_parameters"]
+        for r in rounds:
+            d = store.round_dir("u", r)
+            d.mkdir(parents=True)
+            (d / "current_server_parameters.npz").write_bytes(b"x")
+            if r % 5 != 4:                       # rounds ≡ 4 (mod 5) are left incomplete: no state.bin
+                (d / "state.bin").write_bytes(b"x")
+        complete = sorted(r for r in rounds if r % 5 != 4)
+        assert store.obtain_sorted_rounds("u", keys) == complete
+        if want is None:
+            assert store.interpret_resume_round("u", None, keys) is None
+        elif want < 0:
+            got = store.interpret_resume_round("u", want, keys)
+            assert got == (complete[want] if len(complete) >= -want else None)
+        elif want in complete:
+            assert store.interpret_resume_round("u", want, keys) == want
+        else:
+            try:
+                store.interpret_resume_round("u", want, keys)
+                raise AssertionError("an incomplete / missing round must not resolve")
+            except FileNotFoundError:
+                pass
