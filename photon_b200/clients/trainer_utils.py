@@ -64,13 +64,16 @@ def _prepare_train_cfg(cfg: Any, cid: int | str | None, split_eval: bool, n_devi
     return t, evals
 
 
-def _grad_clip(train_cfg: Any) -> float | None:
+def _grad_clip(train_cfg: Any, kind: str = "norm") -> float | None:
+    """``algorithms.gradient_clipping`` → threshold for ``kind`` (``norm``: global L2, the reference's setting; ``value``:
+    element-wise clamp — Composer's two non-adaptive types). None when the algorithm is absent or of the other kind."""
     gc = ((train_cfg.get("algorithms") or {}).get("gradient_clipping") or None)
     if not gc:
         return None
-    if gc.get("clipping_type", "norm") != "norm":
-        raise NotImplementedError("only clipping_type=norm is supported")
-    return float(gc["clipping_threshold"])
+    have = str(gc.get("clipping_type", "norm"))
+    if have not in ("norm", "value"):
+        raise NotImplementedError(f"gradient_clipping.clipping_type={have!r}: norm and value are supported (adaptive is not)")
+    return float(gc["clipping_threshold"]) if have == kind else None
 
 
 def _with_profiler(t: Any) -> dict[str, Any]:
@@ -157,7 +160,7 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  device_train_microbatch_size=t.get("device_train_microbatch_size", "auto"),
                  device_eval_batch_size=eval_bs, device_eval_microbatch_size=t.get("device_eval_microbatch_size"),
                  precision=precision, max_duration=t.get("max_duration"),
-                 grad_clip_norm=_grad_clip(t), callbacks=build_callbacks(_with_profiler(t)), loggers=loggers,
+                 grad_clip_norm=_grad_clip(t), grad_clip_value=_grad_clip(t, "value"), callbacks=build_callbacks(_with_profiler(t)), loggers=loggers,
                  save_folder=t.get("save_folder"), save_interval=t.get("save_interval"),
                  save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),
                  save_overwrite=bool(t.get("save_overwrite", False)), eval_interval=t.get("eval_interval"),

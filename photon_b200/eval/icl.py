@@ -142,6 +142,7 @@ class ICLEvaluator:
                             scores.append(self._continuation_stats(self._enc(prefix + opt), cont)[0] / max(1, len(cont)))
                     correct += int(int(torch.tensor(scores).argmax()) == int(r["gold"]))
             out[f"{t['label']}/{k}-shot/accuracy"] = correct / max(1, len(rows))
+            out[f"{t['label']}/{k}-shot/n_samples"] = float(len(rows))
         return out
 
 
@@ -151,17 +152,27 @@ class EvalGauntlet:
 
     def __init__(self, cfg: dict[str, Any]) -> None:
         self.cfg = cfg
-        if cfg.get("weighting", "EQUAL") != "EQUAL":
-            raise NotImplementedError("only EQUAL weighting is implemented")
+        if cfg.get("weighting", "EQUAL") not in ("EQUAL", "SAMPLE_SZ", "LOG_SAMPLE_SZ"):
+            raise ValueError(f"unknown eval_gauntlet weighting {cfg.get('weighting')!r} (EQUAL | SAMPLE_SZ | LOG_SAMPLE_SZ)")
+
+    def _weight(self, n_samples: float) -> float:
+        """llm-foundry's benchmark weights inside a category: equal, by sample count, or by log2 of it (at least 1)."""
+        import math
+
+        mode = self.cfg.get("weighting", "EQUAL")
+        if mode == "EQUAL" or n_samples <= 0:
+            return 1.0
+        return float(n_samples) if mode == "SAMPLE_SZ" else max(math.log2(n_samples), 1.0)
 
     def aggregate(self, metrics: dict[str, float]) -> dict[str, float]:
         out: dict[str, float] = {}
         for cat in self.cfg.get("categories", []):
-            vals = []
+            vals, wts = [], []
             for b in cat["benchmarks"]:
                 key = f"{b['name']}/{b['num_fewshot']}-shot/accuracy"
                 if key not in metrics:
                     continue
+                wts.append(self._weight(float(metrics.get(f"{b['name']}/{b['num_fewshot']}-shot/n_samples", 0.0))))
                 acc, base = float(metrics[key]), float(b.get("random_baseline", 0.0))
                 if self.cfg.get("subtract_random_baseline", True):
                     acc -= base
@@ -169,7 +180,7 @@ class EvalGauntlet:
                     acc /= (1.0 - base)
                 vals.append(acc)
             if vals:
-                out[f"icl/metrics/eval_gauntlet/{cat['name']}"] = sum(vals) / len(vals)
+                out[f"icl/metrics/eval_gauntlet/{cat['name']}"] = sum(v * w for v, w in zip(vals, wts)) / sum(wts)
         for name, cats in (self.cfg.get("averages") or {}).items():
             vs = [out[f"icl/metrics/eval_gauntlet/{c}"] for c in cats if f"icl/metrics/eval_gauntlet/{c}" in out]
             if vs:

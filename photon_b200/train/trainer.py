@@ -115,7 +115,7 @@ class Trainer:
                  unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
                  backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False,
-                 device_eval_microbatch_size: int | str | None = None) -> None:
+                 device_eval_microbatch_size: int | str | None = None, grad_clip_value: float | None = None) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -131,6 +131,7 @@ class Trainer:
         self.eval_microbatch: int | str | None = device_eval_microbatch_size
         self._eval_mb_auto = device_eval_microbatch_size == "auto"
         self.grad_clip_norm = grad_clip_norm
+        self.grad_clip_value = float(grad_clip_value) if grad_clip_value is not None else None   # element-wise clamp (clipping_type: value)
         self.train_loader, self.eval_loaders = train_loader, dict(eval_loaders or {})
         self.callbacks, self.loggers = list(callbacks), list(loggers) or [InMemoryLogger()]
         self.save_folder, self.save_overwrite = save_folder, save_overwrite
@@ -167,7 +168,8 @@ class Trainer:
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
         shard_kw: dict[str, Any] = {}
-        self.fused_comm_step = bool(getattr(grad_comm, "fused_step", False)) and self.world_size > 1 and self.scaler is None
+        self.fused_comm_step = (bool(getattr(grad_comm, "fused_step", False)) and self.world_size > 1 and self.scaler is None
+                                and grad_clip_value is None)   # the fused NVLink step clips by norm only
         if self.fused_comm_step:
             # reduce-scatter + clip + optimizer + all-gather in one NVLink kernel: moments sharded like the arena
             shard_kw = dict(shard=grad_comm.shard(), shard_bounds=grad_comm.shard_bounds(), group=process_group)
@@ -282,6 +284,9 @@ class Trainer:
         # N1: ONE gradient all-reduce on the flat bucket (mean over ranks)
         if self.world_size > 1:
             self._allreduce_grads()
+        if self.grad_clip_value is not None:
+            lim = self.grad_clip_value * scale
+            st.flat.grads.clamp_(-lim, lim)
         self._emit("after_backward")
 
         grad_mult: torch.Tensor | float | None = None

@@ -83,3 +83,16 @@ def test_icl_generation_task_greedy_decode_with_stops_and_cot(tmp_path):
     cot = {"label": "cot", "dataset_uri": "cot.jsonl", "icl_task_type": "generation_task_with_answers", "continuation_delimiter": "",
            "cot_delimiter": "e", "early_stopping_criteria": ["h"], "max_new_tokens": 10, "do_normalization": False}
     assert ev.evaluate_task(cot)["cot/0-shot/accuracy"] == 1.0
+
+
+def test_gauntlet_sample_size_weightings():
+    cats = [{"name": "a", "benchmarks": [{"name": "t1", "num_fewshot": 0, "random_baseline": 0.0}, {"name": "t2", "num_fewshot": 0, "random_baseline": 0.0}]}]
+    m = {"t1/0-shot/accuracy": 1.0, "t1/0-shot/n_samples": 1024.0, "t2/0-shot/accuracy": 0.0, "t2/0-shot/n_samples": 4.0}
+    mk = lambda w: EvalGauntlet({"weighting": w, "subtract_random_baseline": False, "rescale_accuracy": False, "categories": cats}).aggregate(m)  # noqa: E731
+    assert math.isclose(mk("EQUAL")["icl/metrics/eval_gauntlet/a"], 0.5)
+    assert math.isclose(mk("SAMPLE_SZ")["icl/metrics/eval_gauntlet/a"], 1024 / 1028)
+    assert math.isclose(mk("LOG_SAMPLE_SZ")["icl/metrics/eval_gauntlet/a"], 10 / 12)
+    import pytest
+
+    with pytest.raises(ValueError):
+        EvalGauntlet({"weighting": "BOGUS"})

@@ -233,3 +233,21 @@ def test_amp_fp8_scales_travel_with_the_checkpoint(tmp_path):
     b.load_checkpoint(tmp_path / "latest-rank0.pt")
     assert fp8_state_dict(b.state.backend.model) == want and torch.equal(a.state.flat.params, b.state.flat.params)
     a.close(), b.close()
+
+
+def test_gradient_clipping_by_value(tmp_path):
+    """``algorithms.gradient_clipping.clipping_type: value`` clamps every gradient element before the optimizer sees it."""
+    from photon_b200.clients.trainer_utils import _grad_clip
+
+    assert _grad_clip({"algorithms": {"gradient_clipping": {"clipping_type": "value", "clipping_threshold": 0.5}}}, "value") == 0.5
+    assert _grad_clip({"algorithms": {"gradient_clipping": {"clipping_type": "value", "clipping_threshold": 0.5}}}) is None
+    assert _grad_clip({"algorithms": {"gradient_clipping": {"clipping_type": "norm", "clipping_threshold": 1.0}}}) == 1.0
+    with pytest.raises(NotImplementedError):
+        _grad_clip({"algorithms": {"gradient_clipping": {"clipping_type": "adaptive", "clipping_threshold": 0.01}}})
+    free, clipped = _trainer(optimizer_cfg=dict(name="sgd", lr=1.0)), _trainer(optimizer_cfg=dict(name="sgd", lr=1.0), grad_clip_value=1e-4)
+    start = free.state.flat.params.clone()
+    free.fit("1ba"), clipped.fit("1ba")
+    assert float(free.state.flat.grads.abs().max()) > 1e-4
+    assert float(clipped.state.flat.grads.abs().max()) <= 1e-4 + 1e-12
+    assert float((clipped.state.flat.params - start).abs().max()) <= 1.01e-4          # SGD, lr 1: the step IS the clamped gradient (fp32 rounding of p - g)
+    free.close(), clipped.close()
