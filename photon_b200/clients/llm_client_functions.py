@@ -54,6 +54,7 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
     # ---- per-client checkpoint policy: resume mid-round or skip an already finished round
     skip_iteration, load_set, _ = set_initial_config_from_fit_config(fc, train_cfg, cid)
     trainer.save_folder = train_cfg.get("save_folder")
+    trainer.save_ignore_keys = list(train_cfg.get("save_ignore_keys") or [])   # reset_optimizer → client checkpoints carry no optimizer state
     metrics["client/fit_init_time"] = _now() - t_start
 
     # ---- install the round's parameters (+ momenta / personalised / re-initialised layers)

@@ -163,7 +163,9 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  grad_clip_norm=_grad_clip(t), grad_clip_value=_grad_clip(t, "value"), callbacks=build_callbacks(_with_profiler(t)), loggers=loggers,
                  save_folder=t.get("save_folder"), save_interval=t.get("save_interval"),
                  save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),
-                 save_overwrite=bool(t.get("save_overwrite", False)), eval_interval=t.get("eval_interval"),
+                 save_overwrite=bool(t.get("save_overwrite", False)), save_filename=t.get("save_filename"),
+                 save_latest_filename=t.get("save_latest_filename"), save_weights_only=bool(t.get("save_weights_only", False)),
+                 save_ignore_keys=t.get("save_ignore_keys"), eval_interval=t.get("eval_interval"),
                  eval_subset_num_batches=int(t.get("eval_subset_num_batches", -1)), device=device, rank=rank,
                  world_size=world_size, process_group=process_group, grad_comm=grad_comm, kernels=kernels, seed=seed,
                  run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,

@@ -115,7 +115,9 @@ class Trainer:
                  unigram_log_probs: torch.Tensor | None = None, frozen_layers: list[str] | None = None,
                  unfrozen_layers: list[str] | None = None, metric_sync_interval: int = 1,
                  backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False,
-                 device_eval_microbatch_size: int | str | None = None, grad_clip_value: float | None = None) -> None:
+                 device_eval_microbatch_size: int | str | None = None, grad_clip_value: float | None = None,
+                 save_filename: str | None = None, save_latest_filename: str | None = None, save_weights_only: bool = False,
+                 save_ignore_keys: Iterable[str] | None = None) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -136,6 +138,9 @@ class Trainer:
         self.callbacks, self.loggers = list(callbacks), list(loggers) or [InMemoryLogger()]
         self.save_folder, self.save_overwrite = save_folder, save_overwrite
         self.save_keep = int(save_num_checkpoints_to_keep)
+        self.save_filename = save_filename or "ep{epoch}-ba{batch}-rank{rank}.pt"     # the per-client resume logic parses this default
+        self.save_latest_filename = save_latest_filename or "latest-rank{rank}.pt"
+        self.save_weights_only, self.save_ignore_keys = bool(save_weights_only), list(save_ignore_keys or [])
         self.eval_subset_num_batches = int(eval_subset_num_batches)
         self.metric_sync_interval = max(1, int(metric_sync_interval))
         self.grad_comm = grad_comm
@@ -459,7 +464,21 @@ class Trainer:
 
     def checkpoint_name(self) -> str:
         ts = self.state.timestamp
-        return f"ep{ts.epoch}-ba{ts.batch}-rank{self.rank}.pt"
+        return self.save_filename.format(epoch=ts.epoch, batch=ts.batch, rank=self.rank, run_name=self.state.run_name)
+
+    def _pruned_state_dict(self) -> dict[str, Any]:
+        """``state_dict()`` minus what ``save_weights_only`` / ``save_ignore_keys`` (Composer glob paths such as ``*optim*`` or
+        ``state/dataset_state``) exclude — e.g. the reference drops optimizer state from client checkpoints when
+        ``fl.reset_optimizer`` (ref: clients/utils.py:229-238)."""
+        sd = self.state_dict()
+        if self.save_weights_only:
+            return {"state": {"model": sd["state"]["model"], "run_name": sd["state"]["run_name"]}}
+        for key in list(sd["state"]):
+            if any(fnmatch.fnmatch(key, pat) or fnmatch.fnmatch("state/" + key, pat) for pat in self.save_ignore_keys):
+                del sd["state"][key]
+        if any(fnmatch.fnmatch("rng", pat) for pat in self.save_ignore_keys):
+            sd.pop("rng", None)
+        return sd
 
     def save_checkpoint(self, folder: str | None = None) -> Path:
         folder_p = Path(folder or self.save_folder or ".")
@@ -468,9 +487,9 @@ class Trainer:
         if path.exists() and not self.save_overwrite:
             raise FileExistsError(path)
         tmp = path.with_suffix(".pt.tmp")
-        torch.save(self.state_dict(), tmp)
+        torch.save(self._pruned_state_dict(), tmp)
         os.replace(tmp, path)
-        latest = folder_p / f"latest-rank{self.rank}.pt"
+        latest = folder_p / self.save_latest_filename.format(rank=self.rank, run_name=self.state.run_name)
         if latest.is_symlink() or latest.exists():
             latest.unlink()
         latest.symlink_to(path.name)
@@ -501,7 +520,7 @@ class Trainer:
             sd = s["optimizers"].get(type(st.optimizer).__name__)
             if sd is not None:
                 st.optimizer.load_state_dict(sd)
-        if not ignored("timestamp"):
+        if not ignored("timestamp") and "timestamp" in s:     # absent from weights-only / pruned checkpoints
             st.timestamp.load_state_dict(s["timestamp"])
         if not ignored("dataset_state") and hasattr(self.train_loader, "load_state_dict"):
             ds = (s.get("dataset_state") or {}).get("train")

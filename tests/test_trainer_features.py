@@ -251,3 +251,23 @@ def test_gradient_clipping_by_value(tmp_path):
     assert float(clipped.state.flat.grads.abs().max()) <= 1e-4 + 1e-12
     assert float((clipped.state.flat.params - start).abs().max()) <= 1.01e-4          # SGD, lr 1: the step IS the clamped gradient (fp32 rounding of p - g)
     free.close(), clipped.close()
+
+
+def test_checkpoint_pruning_and_filename_templates(tmp_path):
+    """``save_ignore_keys`` / ``save_weights_only`` / ``save_filename`` / ``save_latest_filename`` (Composer's checkpoint knobs)."""
+    a = _trainer(save_folder=str(tmp_path / "a"), save_interval="1ba", save_ignore_keys=["*optim*", "state/dataset_state"],
+                 save_filename="{run_name}-e{epoch}-b{batch}-r{rank}.pt", save_latest_filename="newest-r{rank}.pt", run_name="job")
+    a.fit("1ba")
+    path = tmp_path / "a" / "job-e0-b1-r0.pt"
+    assert path.exists() and (tmp_path / "a" / "newest-r0.pt").resolve() == path.resolve()
+    ck = torch.load(path, weights_only=False)
+    assert "optimizers" not in ck["state"] and "dataset_state" not in ck["state"] and "model" in ck["state"] and "timestamp" in ck["state"]
+    w = _trainer(save_folder=str(tmp_path / "w"), save_interval="1ba", save_weights_only=True)
+    w.fit("1ba")
+    ck = torch.load(tmp_path / "w" / "ep0-ba1-rank0.pt", weights_only=False)
+    assert set(ck["state"]) == {"model", "run_name"} and "rng" not in ck
+    b = _trainer()
+    b.load_checkpoint(tmp_path / "w" / "latest-rank0.pt")          # weights-only files load (no clock, no optimizer)
+    assert torch.equal(b.state.flat.params, w.state.flat.params) and b.state.timestamp.batch == 0
+    for t in (a, w, b):
+        t.close()
