@@ -44,7 +44,9 @@ def resume_centralised(trainer: Trainer, train_cfg: Any) -> Path | None:
     load_path = train_cfg.get("load_path")
     if load_path:
         path = Path(str(load_path).format(rank=trainer.rank))
-        trainer.load_checkpoint(path, list(train_cfg.get("load_ignore_keys") or []))
+        from photon_b200.clients.trainer_utils import load_kwargs_from_config
+
+        trainer.load_checkpoint(path, **load_kwargs_from_config(train_cfg))
         return path
     folder = trainer.save_folder
     auto = bool(train_cfg.get("autoresume")) or (folder is not None and not trainer.save_overwrite)

@@ -165,7 +165,8 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  save_num_checkpoints_to_keep=int(t.get("save_num_checkpoints_to_keep", -1)),
                  save_overwrite=bool(t.get("save_overwrite", False)), save_filename=t.get("save_filename"),
                  save_latest_filename=t.get("save_latest_filename"), save_weights_only=bool(t.get("save_weights_only", False)),
-                 save_ignore_keys=t.get("save_ignore_keys"), eval_interval=t.get("eval_interval"),
+                 save_ignore_keys=t.get("save_ignore_keys"), train_subset_num_batches=int(t.get("train_subset_num_batches", -1) or -1),
+                 eval_interval=t.get("eval_interval"),
                  eval_subset_num_batches=int(t.get("eval_subset_num_batches", -1)), device=device, rank=rank,
                  world_size=world_size, process_group=process_group, grad_comm=grad_comm, kernels=kernels, seed=seed,
                  run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,
@@ -222,6 +223,12 @@ def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, lo
 def load_trainer_checkpoint(trainer: Trainer, load_path: str, ignore_keys: list[str] | None = None) -> None:
     """``load_path`` may contain ``{rank}`` (ref: trainer_utils.py:229-275)."""
     trainer.load_checkpoint(load_path.format(rank=trainer.rank), ignore_keys or [])
+
+
+def load_kwargs_from_config(train_cfg: Any) -> dict[str, Any]:
+    """``load_weights_only`` / ``load_strict_model_weights`` / ``load_ignore_keys`` of ``llm_config`` as ``load_checkpoint`` kwargs."""
+    return dict(ignore_keys=list(train_cfg.get("load_ignore_keys") or []), weights_only=bool(train_cfg.get("load_weights_only", False)),
+                strict_model_weights=bool(train_cfg.get("load_strict_model_weights", False)))
 
 
 def trainer_clean_up(trainer: Trainer) -> None:

@@ -117,7 +117,7 @@ class Trainer:
                  backend: Any = None, shard_optimizer_state: bool = False, activation_checkpointing: bool = False,
                  device_eval_microbatch_size: int | str | None = None, grad_clip_value: float | None = None,
                  save_filename: str | None = None, save_latest_filename: str | None = None, save_weights_only: bool = False,
-                 save_ignore_keys: Iterable[str] | None = None) -> None:
+                 save_ignore_keys: Iterable[str] | None = None, train_subset_num_batches: int = -1) -> None:
         self.model_cfg = model_cfg if isinstance(model_cfg, MPTConfig) else MPTConfig.from_model_cfg(model_cfg)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -142,6 +142,7 @@ class Trainer:
         self.save_latest_filename = save_latest_filename or "latest-rank{rank}.pt"
         self.save_weights_only, self.save_ignore_keys = bool(save_weights_only), list(save_ignore_keys or [])
         self.eval_subset_num_batches = int(eval_subset_num_batches)
+        self.train_subset_num_batches = int(train_subset_num_batches if train_subset_num_batches is not None else -1)
         self.metric_sync_interval = max(1, int(metric_sync_interval))
         self.grad_comm = grad_comm
         self.seed = seed
@@ -229,9 +230,14 @@ class Trainer:
         while True:
             if self._train_iter is None:
                 self._train_iter = iter(self.train_loader)
+            limit = self.train_subset_num_batches
             try:
+                if limit >= 0 and self.state.timestamp.batch_in_epoch >= limit:
+                    raise StopIteration       # train_subset_num_batches: the epoch ends early
                 return next(self._train_iter)
             except StopIteration:
+                if hasattr(self._train_iter, "close"):
+                    self._train_iter.close()
                 self._train_iter = None
                 self.state.timestamp.advance_epoch()
 
@@ -501,9 +507,16 @@ class Trainer:
                     old.unlink()
         return path
 
-    def load_checkpoint(self, path: str | os.PathLike, ignore_keys: Iterable[str] = ()) -> None:
+    def load_checkpoint(self, path: str | os.PathLike, ignore_keys: Iterable[str] = (), *, weights_only: bool = False,
+                        strict_model_weights: bool = False) -> None:
+        """``weights_only`` = Composer's ``load_weights_only`` (model tensors, nothing else); ``strict_model_weights`` refuses a
+        checkpoint whose tensor names do not match the model's exactly (otherwise names in common are loaded)."""
         ck = torch.load(path, map_location="cpu", weights_only=False)
-        pats = list(ignore_keys)
+        pats = list(ignore_keys) + (["optimizers", "timestamp", "dataset_state", "scaler", "fp8", "rng", "callbacks"] if weights_only else [])
+        if strict_model_weights:
+            have, want = set(ck["state"].get("model", {})), set(self.state.flat.layout.names)
+            if have != want:
+                raise KeyError(f"checkpoint / model tensor names differ: missing {sorted(want - have)[:3]}, unexpected {sorted(have - want)[:3]}")
 
         def ignored(key: str) -> bool:
             return any(fnmatch.fnmatch(key, p) or fnmatch.fnmatch("state/" + key, p) for p in pats)

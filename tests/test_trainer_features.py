@@ -271,3 +271,22 @@ def test_checkpoint_pruning_and_filename_templates(tmp_path):
     assert torch.equal(b.state.flat.params, w.state.flat.params) and b.state.timestamp.batch == 0
     for t in (a, w, b):
         t.close()
+
+
+def test_load_weights_only_strict_names_and_train_subset(tmp_path):
+    a = _trainer(save_folder=str(tmp_path), save_interval="2ba")
+    a.fit("2ba")
+    b = _trainer()
+    b.load_checkpoint(tmp_path / "latest-rank0.pt", weights_only=True, strict_model_weights=True)
+    assert torch.equal(b.state.flat.params, a.state.flat.params) and b.state.timestamp.batch == 0
+    assert float(b.state.optimizer.exp_avg.abs().sum()) == 0.0                       # optimizer state was not taken
+    c = _trainer(frozen_layers=["transformer.wpe.weight"])
+    with pytest.raises(KeyError):
+        c.load_checkpoint(tmp_path / "latest-rank0.pt", strict_model_weights=True)    # names differ (one tensor is frozen here)
+    c.load_checkpoint(tmp_path / "latest-rank0.pt", weights_only=True)               # non-strict: the common tensors load
+    d = _trainer(train_subset_num_batches=3)
+    d.fit("7ba")
+    ts = d.state.timestamp
+    assert ts.batch == 7 and ts.epoch == 2 and ts.batch_in_epoch == 1                 # epochs of 3 batches: 3 + 3 + 1
+    for t in (a, b, c, d):
+        t.close()
