@@ -65,6 +65,27 @@ class ConsoleLogger(Logger):
         print(f"{self.prefix}[ba={step}] {body}", flush=True)
 
 
+class ProgressBarLogger(Logger):
+    """``progress_bar: true`` — one tqdm bar per run showing the batch counter and the running loss (Composer's
+    ``ProgressBarLogger``); needs nothing but a terminal."""
+
+    def __init__(self, total: int | None = None, desc: str = "train") -> None:
+        from tqdm import tqdm
+
+        self.bar = tqdm(total=total, desc=desc, unit="ba", dynamic_ncols=True, leave=True)
+        self._last = 0
+
+    def log_metrics(self, metrics: dict[str, float], step: int) -> None:
+        if step > self._last:
+            self.bar.update(step - self._last)
+            self._last = step
+        if "loss/train/total" in metrics:
+            self.bar.set_postfix(loss=f"{float(metrics['loss/train/total']):.4f}", refresh=False)
+
+    def close(self) -> None:
+        self.bar.close()
+
+
 class JSONLLogger(Logger):
     """File sink (one JSON object per call). Stands in for the TensorBoard event file
     when ``tensorboard`` is not importable; path mirrors ``<save>/tensorboard/<run>``."""
@@ -132,12 +153,14 @@ class WandBLogger(Logger):
 
 
 def build_loggers(cfg: dict[str, Any] | None, save_root: str | Path, run_name: str, console_interval: int = 1,
-                  log_to_console: bool = True, rank: int = 0) -> list[Logger]:
+                  log_to_console: bool = True, rank: int = 0, progress_bar: bool = False, total_batches: int | None = None) -> list[Logger]:
     out: list[Logger] = [InMemoryLogger()]
     if rank != 0:
         return out
     if log_to_console:
         out.append(ConsoleLogger(console_interval, prefix=f"{run_name} "))
+    if progress_bar:
+        out.append(ProgressBarLogger(total_batches, desc=run_name))
     for name, sub in (cfg or {}).items():
         sub = dict(sub or {})
         if name == "tensorboard":
