@@ -126,6 +126,26 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
     return history
 
 
+def dump_history(history: WandbHistory, path: str | os.PathLike) -> Path:
+    """The run's round-level metrics as plain JSON next to ``config.yaml`` (the reference only has them in wandb or inside the
+    pickled ``state.bin``): ``{store: {key: [[round, value], …]}}`` for the five History stores."""
+    import json
+
+    def plain(v: Any) -> Any:
+        try:
+            return float(v) if not isinstance(v, (str, bool, int)) else v
+        except (TypeError, ValueError):
+            return str(v)
+
+    out = {"losses_distributed": [[r, plain(v)] for r, v in history.losses_distributed],
+           "losses_centralized": [[r, plain(v)] for r, v in history.losses_centralized]}
+    for name in ("metrics_distributed_fit", "metrics_distributed", "metrics_centralized"):
+        out[name] = {k: [[r, plain(v)] for r, v in vals] for k, vals in getattr(history, name).items()}
+    p = Path(path)
+    p.write_text(json.dumps(out, indent=1))
+    return p
+
+
 def main() -> None:
     save_path = os.environ.get("PHOTON_SAVE_PATH")
     if not save_path:
@@ -133,6 +153,7 @@ def main() -> None:
     cfg = load_config(Path(save_path) / "config.yaml")
     hist = run_server(cfg)
     if int(os.environ.get("RANK", "0")) == 0:
+        dump_history(hist, Path(save_path) / "history.json")
         last = {k: v[-1][1] for k, v in hist.metrics_distributed_fit.items() if "/layer/" not in k}
         print("[server] done. last round fit metrics:", {k: (round(v, 5) if isinstance(v, float) else v) for k, v in last.items()})
 

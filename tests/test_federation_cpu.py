@@ -449,3 +449,14 @@ def test_killed_server_leaves_no_orphan_workers_and_no_shm_segments(tmp_path):
     finally:
         if proc.poll() is None:
             proc.kill()
+
+
+def test_history_json_dump(tmp_path):
+    import json
+
+    from photon_b200.server_app import dump_history, run_server
+
+    h = run_server(_cfg(tmp_path, "run_uuid=hj", "fl.n_rounds=1"))
+    rec = json.loads(dump_history(h, tmp_path / "history.json").read_text())
+    assert rec["losses_distributed"][0][0] == 0 and rec["metrics_distributed_fit"]["server/n_failures"] == [[1, 0.0]]
+    assert "server/round_time" in rec["metrics_centralized"] and "server/broadcast_pre_time" in rec["metrics_centralized"]
