@@ -125,6 +125,18 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
     return trainer
 
 
+def dump_metrics(trainer: Trainer, path: str | os.PathLike) -> Path:
+    """Everything the run logged (``{key: [[batch, value], …]}`` from the in-memory logger) + the final clock, as plain JSON."""
+    import json
+
+    mem = next((lg for lg in trainer.loggers if hasattr(lg, "data")), None)
+    out = {"timestamp": {k: v for k, v in trainer.state.timestamp.state_dict().items() if isinstance(v, (int, float))},
+           "metrics": {k: [[int(s), float(v)] for s, v in vals] for k, vals in (mem.data if mem is not None else {}).items()}}
+    p = Path(path)
+    p.write_text(json.dumps(out, indent=1))
+    return p
+
+
 def main() -> None:
     save_path = os.environ.get("PHOTON_SAVE_PATH")
     if not save_path:
@@ -132,6 +144,7 @@ def main() -> None:
     cfg = load_config(Path(save_path) / "config.yaml")
     tr = run_centralised(cfg)
     if tr.rank == 0:
+        dump_metrics(tr, Path(save_path) / "centralised_metrics.json")
         print("[centralised_train] done:", tr.state.timestamp, tr.state.train_metric_values)
     tr.close()
 

@@ -339,6 +339,12 @@ def test_centralised_autoresume_continues_from_latest_checkpoint(tmp_path, monke
     a.close()
     b = run_centralised(compose(cen + ["run_uuid=ar", f"llm_config.save_folder={tmp_path}/ar", "llm_config.max_duration=5ba"]), device=torch.device("cpu"))
     assert b.state.timestamp.batch == 5 and b.fit_start_batch == 3      # resumed at 3, trained 2
+    import json
+
+    from photon_b200.centralised_train import dump_metrics
+
+    rec = json.loads(dump_metrics(b, tmp_path / "m.json").read_text())
+    assert rec["timestamp"]["batch"] == 5 and [s for s, _ in rec["metrics"]["loss/train/total"]] == [4, 5]
     resumed = b.state.flat.params.clone()
     b.close()
     c = run_centralised(compose(cen + ["run_uuid=one", f"llm_config.save_folder={tmp_path}/one", "llm_config.max_duration=5ba"]), device=torch.device("cpu"))
