@@ -148,7 +148,8 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
     interval = t.get("console_log_interval", "1ba")
     loggers = build_loggers(t.get("loggers"), Path(str(save_root)).parent if t.get("save_folder") else ".", str(t["run_name"]),
                             console_interval=Time.parse(interval).to_batches(), log_to_console=bool(t.get("log_to_console", True)), rank=rank,
-                            progress_bar=bool(t.get("progress_bar", False)))
+                            progress_bar=bool(t.get("progress_bar", False)),
+                            total_batches=(Time.parse(t["max_duration"]).to_batches() if str(t.get("max_duration", "")).endswith("ba") else None))
     kernels = dict(cfg.get("kernels") or {})
     if mcfg.attn_impl == "torch" and device.type == "cuda" and kernels.get("attention", "auto") == "auto":
         kernels["attention"] = "torch"
