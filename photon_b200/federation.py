@@ -83,6 +83,11 @@ class FederationRuntime:
     # --------------------------------------------------------------------- bring-up
     def build(self) -> None:
         """Create the persistent Trainer (also fixes the flat layout) and the round transport."""
+        want = int(self.cfg["photon"].get("n_nodes", 1) or 1)
+        if want not in (1, self.n_nodes) and self.rank == 0:
+            # the reference waits for photon.n_nodes Flower nodes; here the job's ranks ARE the nodes
+            print(f"[federation] photon.n_nodes={want} but this job has {self.n_nodes} node(s) "
+                  f"({self.world_size} rank(s) / {self.gpus_per_client} GPU(s) per client): using {self.n_nodes}", flush=True)
         kw: dict[str, Any] = dict(device=self.device, rank=self.rank % self.gpus_per_client, world_size=self.gpus_per_client,
                                   process_group=self.client_group)
         if self.gpus_per_client > 1 and self.device.type == "cuda":
