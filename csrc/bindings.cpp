@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "comm.h"
+#include "fp8_ops.h"
 #include "fused_ops.h"
 #include "gemm_tcgen05.h"
 #include "attention_tcgen05.h"
@@ -87,6 +88,137 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int e
   g.num_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   g.cluster = cluster;
   pb::gemm_bf16_launch(g, stream_of(a));
+  g_launches += 1;
+}
+
+// fp8 operands (1-byte tensors: torch.uint8 or float8 storage). `meta` = float32 [3, n_roles] = (scale, scale_inv, amax) rows.
+inline bool is_byte(const Tensor& t) {
+  return t.scalar_type() == at::kByte || t.scalar_type() == at::kFloat8_e4m3fn || t.scalar_type() == at::kFloat8_e5m2;
+}
+void gemm_fp8(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, int epi, int a_fmt, int b_fmt, const Tensor& meta, int role_a,
+              int role_b, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& aux, c10::optional<Tensor> d2, bool accumulate,
+              double alpha, int cluster, c10::optional<Tensor> d8, int role_out) {
+  check_cuda(a, "a");
+  check_cuda(b, "b");
+  check_cuda(d, "d");
+  TORCH_CHECK(is_byte(a) && is_byte(b), "gemm_fp8 operands must be 1-byte tensors");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && d.dim() == 2, "gemm operands must be 2-D");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1, "gemm operands must have unit inner stride");
+  check_f32(meta, "meta");
+  TORCH_CHECK(meta.dim() == 2 && meta.size(0) == 3 && meta.is_contiguous(), "meta must be contiguous float32 [3, n_roles]");
+  const int64_t nr = meta.size(1);
+  TORCH_CHECK(role_a >= 0 && role_a < nr && role_b >= 0 && role_b < nr, "role index out of range");
+  c10::cuda::CUDAGuard guard(a.device());
+  pb::GemmArgs g;
+  g.fp8 = 1, g.a_fmt = a_fmt, g.b_fmt = b_fmt;
+  g.M = int(a_mn ? a.size(1) : a.size(0));
+  g.K = int(a_mn ? a.size(0) : a.size(1));
+  g.N = int(b_mn ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == g.K, "gemm: K mismatch between a and b");
+  TORCH_CHECK(d.size(0) == g.M && d.size(1) == g.N, "gemm: output shape mismatch");
+  g.A = a.data_ptr(), g.B = b.data_ptr(), g.D = d.data_ptr();
+  g.lda = a.stride(0), g.ldb = b.stride(0), g.ldd = d.stride(0);
+  g.a_mn = a_mn, g.b_mn = b_mn, g.epi = epi, g.accumulate = accumulate ? 1 : 0, g.alpha = float(alpha);
+  const float* m = meta.data_ptr<float>();
+  g.sinv_a = m + nr + role_a, g.sinv_b = m + nr + role_b;
+  if (epi == pb::EPI_F32) {
+    TORCH_CHECK(d.scalar_type() == at::kFloat, "EPI_F32 needs a float32 output");
+  } else {
+    TORCH_CHECK(d.scalar_type() == at::kBFloat16, "bf16 epilogues need a bfloat16 output");
+  }
+  if (bias.has_value()) {
+    check_f32(*bias, "bias");
+    TORCH_CHECK(bias->numel() == g.N, "bias length must equal N");
+    g.bias = bias->data_ptr<float>();
+  }
+  if (aux.has_value()) {
+    check_bf16(*aux, "aux");
+    TORCH_CHECK(aux->size(0) == g.M && aux->size(1) == g.N && aux->stride(1) == 1, "aux must be [M,N]");
+    g.aux = aux->data_ptr(), g.ld_aux = aux->stride(0);
+  }
+  if (d2.has_value()) {
+    check_bf16(*d2, "d2");
+    TORCH_CHECK(d2->size(0) == g.M && d2->size(1) == g.N && d2->stride(1) == 1, "d2 must be [M,N]");
+    g.D2 = d2->data_ptr(), g.ldd2 = d2->stride(0);
+  }
+  if (d8.has_value()) {
+    TORCH_CHECK(is_byte(*d8) && d8->size(0) == g.M && d8->size(1) == g.N && d8->stride(1) == 1, "d8 must be a 1-byte [M,N] tensor");
+    TORCH_CHECK(role_out >= 0 && role_out < nr, "role_out out of range");
+    g.D8 = d8->data_ptr(), g.ldd8 = d8->stride(0);
+    g.out_scale = m + role_out;
+    g.out_amax = const_cast<float*>(m) + 2 * nr + role_out;
+  }
+  g.num_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  g.cluster = cluster;
+  pb::gemm_launch(g, stream_of(a));
+  g_launches += 1;
+}
+void layernorm_fwd_q8(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta, Tensor& y8, Tensor& mean, Tensor& rstd,
+                      double eps, Tensor& meta, int role) {
+  check_bf16(x, "x");
+  check_f32(gamma, "gamma");
+  check_f32(meta, "meta");
+  TORCH_CHECK(x.is_contiguous() && y8.is_contiguous() && is_byte(y8) && y8.numel() == x.numel(), "layernorm_fwd_q8: y8 must be a contiguous 1-byte tensor shaped like x");
+  const int64_t nr = meta.size(1);
+  TORCH_CHECK(meta.dim() == 2 && meta.size(0) == 3 && role >= 0 && role < nr, "bad meta / role");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int d = int(x.size(-1));
+  float* m = meta.data_ptr<float>();
+  pb::layernorm_fwd_q8(x.data_ptr(), gamma.data_ptr<float>(), beta.has_value() ? beta->data_ptr<float>() : nullptr, y8.data_ptr(),
+                       mean.data_ptr<float>(), rstd.data_ptr<float>(), x.numel() / d, d, float(eps), m + role, m + 2 * nr + role, stream_of(x));
+  g_launches += 1;
+}
+// out_sum[j] += sum_t dy[t,j] and / or y8 = fp8(dy * scale[role]) with amax[role] updated — one read of dy
+void colsum_quant(const Tensor& dy, c10::optional<Tensor> out_sum, c10::optional<Tensor> y8, int fmt, c10::optional<Tensor> meta, int role) {
+  check_bf16(dy, "dy");
+  TORCH_CHECK(dy.dim() == 2 && dy.stride(1) == 1, "colsum_quant expects [T,N] with unit inner stride");
+  c10::cuda::CUDAGuard guard(dy.device());
+  const float* scale = nullptr;
+  float* amax = nullptr;
+  void* y = nullptr;
+  long long ld8 = 0;
+  if (y8.has_value()) {
+    TORCH_CHECK(meta.has_value(), "quantising needs the meta tensor");
+    check_f32(*meta, "meta");
+    const int64_t nr = meta->size(1);
+    TORCH_CHECK(meta->dim() == 2 && meta->size(0) == 3 && role >= 0 && role < nr, "bad meta / role");
+    TORCH_CHECK(is_byte(*y8) && y8->dim() == 2 && y8->size(0) == dy.size(0) && y8->size(1) == dy.size(1) && y8->stride(1) == 1 &&
+                    y8->stride(0) % 8 == 0, "y8 must be a 1-byte [T,N] tensor");
+    scale = meta->data_ptr<float>() + role;
+    amax = meta->data_ptr<float>() + 2 * nr + role;
+    y = y8->data_ptr(), ld8 = y8->stride(0);
+  }
+  if (out_sum.has_value()) check_f32(*out_sum, "out_sum");
+  pb::colsum_quant(dy.data_ptr(), dy.stride(0), out_sum.has_value() ? out_sum->data_ptr<float>() : nullptr, y, ld8, fmt, scale, amax,
+                   dy.size(0), int(dy.size(1)), stream_of(dy));
+  g_launches += 1;
+}
+void fp8_quantize_segments(const Tensor& src, Tensor& dst8, const Tensor& seg, Tensor& meta, int role0) {
+  check_bf16(src, "src");
+  check_cuda(seg, "seg");
+  check_f32(meta, "meta");
+  TORCH_CHECK(seg.scalar_type() == at::kLong && seg.dim() == 2 && seg.size(1) == 2 && seg.is_contiguous(), "seg must be int64 [n,2] on the device");
+  TORCH_CHECK(is_byte(dst8) && dst8.numel() >= src.numel(), "dst8 must be a 1-byte tensor at least as long as src");
+  const int64_t nr = meta.size(1);
+  const int n = int(seg.size(0));
+  TORCH_CHECK(role0 >= 0 && role0 + n <= nr, "roles out of range");
+  c10::cuda::CUDAGuard guard(src.device());
+  float* m = meta.data_ptr<float>();
+  pb::quantize_segments(src.data_ptr(), dst8.data_ptr(), reinterpret_cast<const long long*>(seg.data_ptr<int64_t>()), n, m + role0,
+                        m + nr + role0, m + 2 * nr + role0, stream_of(src));
+  g_launches += 2;
+}
+void fp8_update_scales(Tensor& meta, Tensor& hist, const Tensor& fmax, Tensor& pos, int n, double margin_mult) {
+  check_f32(meta, "meta");
+  check_f32(hist, "hist");
+  check_f32(fmax, "fmax");
+  TORCH_CHECK(pos.scalar_type() == at::kInt && pos.is_cuda(), "pos must be an int32 device tensor");
+  const int64_t nr = meta.size(1);
+  TORCH_CHECK(n <= nr && hist.dim() == 2 && hist.size(0) >= n && fmax.numel() >= n && hist.is_contiguous(), "bad history / fmax shapes");
+  c10::cuda::CUDAGuard guard(meta.device());
+  float* m = meta.data_ptr<float>();
+  pb::update_scales(m, m + nr, m + 2 * nr, hist.data_ptr<float>(), fmax.data_ptr<float>(), pos.data_ptr<int>(), n, int(hist.size(1)),
+                    float(margin_mult), stream_of(meta));
   g_launches += 1;
 }
 
@@ -379,6 +511,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("d"), py::arg("a_mn") = 0, py::arg("b_mn") = 0, py::arg("epi") = 0,
         py::arg("bias") = py::none(), py::arg("aux") = py::none(), py::arg("d2") = py::none(), py::arg("accumulate") = false,
         py::arg("alpha") = 1.0, py::arg("cluster") = 0);
+  m.def("gemm_fp8", &gemm_fp8, py::arg("a"), py::arg("b"), py::arg("d"), py::arg("a_mn"), py::arg("b_mn"), py::arg("epi"), py::arg("a_fmt"),
+        py::arg("b_fmt"), py::arg("meta"), py::arg("role_a"), py::arg("role_b"), py::arg("bias") = py::none(), py::arg("aux") = py::none(),
+        py::arg("d2") = py::none(), py::arg("accumulate") = false, py::arg("alpha") = 1.0, py::arg("cluster") = 0,
+        py::arg("d8") = py::none(), py::arg("role_out") = -1);
+  m.def("layernorm_fwd_q8", &layernorm_fwd_q8);
+  m.def("colsum_quant", &colsum_quant, py::arg("dy"), py::arg("out_sum") = py::none(), py::arg("y8") = py::none(), py::arg("fmt") = 1,
+        py::arg("meta") = py::none(), py::arg("role") = -1);
+  m.def("fp8_quantize_segments", &fp8_quantize_segments);
+  m.def("fp8_update_scales", &fp8_update_scales);
   m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("out"), py::arg("lse"), py::arg("n_heads"), py::arg("scale"),
         py::arg("causal"), py::arg("alibi_slopes") = py::none());
   m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("out"), py::arg("dout"), py::arg("lse"), py::arg("dqkv"), py::arg("delta"),
@@ -425,4 +566,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("EPI_F32") = int(pb::EPI_F32);
   m.attr("EPI_GELU_GRAD") = int(pb::EPI_GELU_GRAD);
   m.attr("EPI_MUL") = int(pb::EPI_MUL);
+  m.attr("EPI_GELU_GRAD_Q8") = int(pb::EPI_GELU_GRAD_Q8);
 }

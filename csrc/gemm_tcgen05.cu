@@ -23,8 +23,11 @@ namespace pb {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int A_STAGE = BM * BK * 2;  // 16 KiB
+constexpr int BM = 128, BN = 256;
+// A stage holds 128 BYTES of K per row for either operand type: 64 bf16 (4 UMMA k-steps of 16) or 128 fp8 (4 k-steps of 32),
+// so the shared-memory plan, the TMA box bytes and the descriptor arithmetic are the same for kind::f16 and kind::f8f6f4.
+constexpr int ROW_BYTES = 128;
+constexpr int A_STAGE = BM * ROW_BYTES;  // 16 KiB
 constexpr int EPI_BUF = 128 * 128;    // 128 rows x 128 B (one swizzle atom wide)
 constexpr int NUM_THREADS = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue (two groups of four)
 constexpr int TMEM_COLS = 512;
@@ -34,7 +37,7 @@ constexpr int TMEM_COLS = 512;
 // staging): ~2500 instead of ~1500 tensor-core clocks of loads in flight per SM.
 template <int EPI, int CL>
 struct Cfg {
-  static constexpr int B_STAGE = (BN / CL) * BK * 2;   // 32 KiB (CL=1) / 16 KiB (CL=2)
+  static constexpr int B_STAGE = (BN / CL) * ROW_BYTES;   // 32 KiB (CL=1) / 16 KiB (CL=2)
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
   static constexpr int STORES = (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD) ? 2 : 1;   // staging buffers consumed per epilogue chunk
   // two epilogue groups (even / odd column chunks of a tile), two staging buffers each: the exact-erf GELU epilogues
@@ -56,6 +59,16 @@ struct Params {
   int accumulate;               // EPI_F32: reduce-add into D instead of overwrite
   float alpha;                  // scale applied to the accumulator before the epilogue
   int splits, kb_per_split;     // split-K (EPI_F32 + accumulate): work item = (tile, k-range)
+  // fp8 (kind::f8f6f4) operands: element formats (0 = E4M3, 1 = E5M2) and the per-tensor de-scales, read from device memory
+  // (delayed scaling keeps them on the device so the whole step stays CUDA-graph capturable)
+  int a_fmt, b_fmt;
+  const float* sinv_a;
+  const float* sinv_b;
+  // EPI_GELU_GRAD_Q8: the activation leaves as E4M3 (scaled by *out_scale, amax recorded) for the next fp8 GEMM
+  uint8_t* d8;
+  long long ld_d8;
+  const float* out_scale;
+  float* out_amax;
 };
 
 // CL = 1: one CTA per 128x256 tile (tcgen05 cta_group::1).
@@ -64,12 +77,16 @@ struct Params {
 //         256 N rows), the tensor cores of both SMs read both halves, each SM accumulates its 128 rows in its own TMEM.
 //         Per SM this halves the B traffic through shared memory (the 1-CTA form is smem-bandwidth bound: 96 B/clk of
 //         MMA operand reads + 96 B/clk of TMA writes against a 128 B/clk port) and needs 32 instead of 48 KiB per stage.
-template <int A_MN, int B_MN, int EPI, int CL>
+template <int A_MN, int B_MN, int EPI, int CL, int F8>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const Params p) {
   using C = Cfg<EPI, CL>;
   constexpr int STAGES = C::STAGES, B_STAGE = C::B_STAGE, STAGE_BYTES = C::STAGE_BYTES, EPI_BUFS = C::EPI_BUFS;
+  constexpr int BK = F8 ? 128 : 64;            // K elements per stage (128 bytes per row)
+  constexpr int UK = F8 ? 32 : 16;             // K elements per tcgen05.mma
+  constexpr int MNC = F8 ? 128 : 64;           // MN elements in one 128-byte row of an MN-major tile
+  constexpr int CHUNK = BK * ROW_BYTES;        // bytes of one MN-major chunk: BK k-rows of 128 bytes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -88,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmD);
-    if (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD) prefetch_tmap(&tmD2);
+    if (EPI == EPI_GELU_DUAL || EPI == EPI_GELU_GRAD || EPI == EPI_GELU_GRAD_Q8) prefetch_tmap(&tmD2);
   }
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
   if (warp == 1 && lane == 0) {
@@ -139,15 +156,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (crank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d_2sm(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
+              for (int j = 0; j < BM / MNC; ++j)
+                tma_load_2d_2sm(a_dst + j * CHUNK, &tmA, &full[stage], m_blk * BM + j * MNC, kb * BK);
             } else {
               tma_load_2d_2sm(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j)
-                tma_load_2d_2sm(b_dst + j * (BK * 128), &tmB, &full[stage], n_blk * BN + (crank * (BN / 128) + j) * 64, kb * BK);
+              for (int j = 0; j < BN / 2 / MNC; ++j)
+                tma_load_2d_2sm(b_dst + j * CHUNK, &tmB, &full[stage], n_blk * BN + (crank * (BN / 2 / MNC) + j) * MNC, kb * BK);
             } else {
               tma_load_2d_2sm(b_dst, &tmB, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2));
             }
@@ -164,15 +181,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* b_dst = sB + stage * B_STAGE;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a_dst + j * (BK * 128), &tmA, &full[stage], m_blk * BM + j * 64, kb * BK);
+            for (int j = 0; j < BM / MNC; ++j)
+              tma_load_2d(a_dst + j * CHUNK, &tmA, &full[stage], m_blk * BM + j * MNC, kb * BK);
           } else {
             tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * (BK * 128), &tmB, &full[stage], n_blk * BN + j * 64, kb * BK);
+            for (int j = 0; j < BN / MNC; ++j)
+              tma_load_2d(b_dst + j * CHUNK, &tmB, &full[stage], n_blk * BN + j * MNC, kb * BK);
           } else {
             tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_blk * BN);
           }
@@ -188,7 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // The whole warp walks the loop (waits included) so every operand is warp-uniform; one elected lane issues the
     // tcgen05 instructions. (`if (lane == 0)` around the loop costs a ~20-instruction elect/broadcast round trip per MMA.)
     if (crank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
+      const uint32_t idesc = F8 ? make_idesc_f8(BM * CL, BN, A_MN, B_MN, p.a_fmt, p.b_fmt) : make_idesc_bf16(BM * CL, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -204,16 +221,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
           const uint32_t b_base = smem_u32(sB + stage * B_STAGE);
-          const uint32_t ad0 = smem_desc_lo(a_base, A_MN ? BK * 128 : 16);
-          const uint32_t bd0 = smem_desc_lo(b_base, B_MN ? BK * 128 : 16);
+          const uint32_t ad0 = smem_desc_lo(a_base, A_MN ? CHUNK : 16);
+          const uint32_t bd0 = smem_desc_lo(b_base, B_MN ? CHUNK : 16);
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // k-step inside the stage: UK rows of 128 B (MN-major) or UK elements of 2 B (K-major), in 16-byte descriptor units
-            const uint32_t adesc = ad0 + uint32_t(A_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
-            const uint32_t bdesc = bd0 + uint32_t(B_MN ? (k * UK * 128) >> 4 : (k * UK * 2) >> 4);
+          for (int k = 0; k < 4; ++k) {   // BK / UK = 4 for both operand types
+            // k-step inside the stage: UK rows of 128 B (MN-major) or 32 bytes of K (K-major), in 16-byte descriptor units
+            const uint32_t adesc = ad0 + uint32_t(A_MN ? (k * UK * 128) >> 4 : (k * 32) >> 4);
+            const uint32_t bdesc = bd0 + uint32_t(B_MN ? (k * UK * 128) >> 4 : (k * 32) >> 4);
             if (elect_one()) {
-              if (CL > 1) tc_mma_f16_ss_2sm_lo(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else tc_mma_f16_ss_lo(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (F8) {
+                if (CL > 1) tc_mma_f8_ss_2sm_lo(d_tmem, adesc, bdesc, idesc, accum);
+                else tc_mma_f8_ss_lo(d_tmem, adesc, bdesc, idesc, accum);
+              } else {
+                if (CL > 1) tc_mma_f16_ss_2sm_lo(d_tmem, adesc, bdesc, idesc, accum);
+                else tc_mma_f16_ss_lo(d_tmem, adesc, bdesc, idesc, accum);
+              }
             }
           }
           if (elect_one()) {
@@ -251,6 +274,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t swz = (row_in_tile & 7);
+    // fp8 operands: fold the per-tensor de-scales (device scalars written by the quantising producers) into alpha
+    float alpha = p.alpha;
+    if (F8) alpha *= (p.sinv_a ? __ldg(p.sinv_a) : 1.0f) * (p.sinv_b ? __ldg(p.sinv_b) : 1.0f);
+    const float q8_scale = (EPI == EPI_GELU_GRAD_Q8 && p.out_scale) ? __ldg(p.out_scale) : 1.0f;
+    float q8_amax = 0.f;
     for (int w = w0; w < num_work; w += wstride) {
       const int tile = w % num_tiles;
       const int m_blk = (p.m_fastest ? tile % tiles_mu : tile / p.tiles_n) * CL + crank;
@@ -279,12 +307,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_32x32(taddr, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
           if (CW == 64) {
             tmem_ld_32x32(taddr + 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[(CW == 64 ? 32 : 0) + j] = __uint_as_float(r[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) v[(CW == 64 ? 32 : 0) + j] = __uint_as_float(r[j]) * alpha;
           }
         }
         if (EPI != EPI_F32 && p.bias != nullptr) {
@@ -348,6 +376,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(buf1 + row_in_tile * 128 + ((j ^ swz) << 4)) = o;   // gelu'(z)
             }
           }
+          if (EPI == EPI_GELU_GRAD_Q8) {
+            // gelu'(z) -> v (staged + TMA-stored as bf16 below, through tmD2); gelu(z) -> E4M3 straight to global memory:
+            // each thread owns 64 consecutive bytes of one output row (two full 32-byte sectors)
+            uint32_t q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a4[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float c, pd;
+                const float z = v[4 * j + t];
+                gelu_cdf_pdf(z, c, pd);
+                v[4 * j + t] = fmaf(z, pd, c);
+                a4[t] = z * c;
+                if (row_ok && col0 + 4 * j + t < p.N) q8_amax = fmaxf(q8_amax, fabsf(a4[t]));
+              }
+              q[j] = pack_e4m3x4(a4[0] * q8_scale, a4[1] * q8_scale, a4[2] * q8_scale, a4[3] * q8_scale);
+            }
+            if (row_ok) {
+              uint8_t* drow = p.d8 + row * p.ld_d8 + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + 16 * j < p.N) *reinterpret_cast<uint4*>(drow + 16 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+            }
+          }
           if (EPI == EPI_GELU_DUAL) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -376,6 +429,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (issuer) {
           if (EPI == EPI_F32 && (p.accumulate || p.splits > 1)) {
             tma_reduce_add_2d(&tmD, buf0, col0, m_blk * BM);
+          } else if (EPI == EPI_GELU_GRAD_Q8) {
+            tma_store_2d(&tmD2, buf0, col0, m_blk * BM);
           } else {
             tma_store_2d(&tmD, buf0, col0, m_blk * BM);
           }
@@ -394,6 +449,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (acc == 0) acc_phase ^= 1;
     }
     if (issuer) tma_wait_all<0>();
+    if (EPI == EPI_GELU_GRAD_Q8 && p.out_amax) {
+      q8_amax = warp_max_f(q8_amax);
+      if (lane == 0 && q8_amax > 0.f) atomic_max_pos_f32(p.out_amax, q8_amax);
+    }
   }
 
   tc_fence_before();
@@ -443,10 +502,10 @@ CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint6
   return m;
 }
 
-template <int A_MN, int B_MN, int EPI, int CL>
+template <int A_MN, int B_MN, int EPI, int CL, int F8>
 static void launch_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
                       const Params& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<A_MN, B_MN, EPI, CL>;
+  auto kern = gemm_kernel<A_MN, B_MN, EPI, CL, F8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<EPI, CL>::SMEM_BYTES);
@@ -469,35 +528,48 @@ static void launch_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm launch: ") + cudaGetErrorString(e));
 }
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, int F8>
 static void launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
                         const Params& p, int grid, int cluster, cudaStream_t stream) {
-  if (cluster == 2) launch_cl<A_MN, B_MN, EPI, 2>(ta, tb, td, td2, p, grid, stream);
-  else launch_cl<A_MN, B_MN, EPI, 1>(ta, tb, td, td2, p, grid, stream);
+  if (cluster == 2) launch_cl<A_MN, B_MN, EPI, 2, F8>(ta, tb, td, td2, p, grid, stream);
+  else launch_cl<A_MN, B_MN, EPI, 1, F8>(ta, tb, td, td2, p, grid, stream);
 }
 
-void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
+// Operands are bf16 (kind::f16) or, with g.fp8, 8-bit floats (kind::f8f6f4: E4M3 / E5M2 chosen per operand, fp32 accumulate,
+// per-tensor de-scales applied in the epilogue). Everything else — pipeline, tile shape, epilogues — is shared.
+void gemm_launch(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return;
   if (g.N % 8) throw std::runtime_error("photon_b200 gemm: N must be a multiple of 8");
   const bool f32 = g.epi == EPI_F32;
-  // A: K-major -> dims {K, M}, box {64, 128};  MN-major -> dims {M, K}, box {64(M), 64(K)}
-  CUtensorMap ta = g.a_mn ? make_tmap_2d(g.A, 2, false, g.M, g.K, g.lda * 2, 64, BK)
-                          : make_tmap_2d(g.A, 2, false, g.K, g.M, g.lda * 2, BK, BM);
-  // 2-CTA clusters (B tile multicast: each CTA fetches half of the N rows) whenever there are >= 2 M tiles
+  const int eb = g.fp8 ? 1 : 2;                 // operand element bytes
+  const int BKE = ROW_BYTES / eb;               // K elements per stage
+  const int MNC = ROW_BYTES / eb;               // MN elements per 128-byte row of an MN-major tile
+  // A: K-major -> dims {K, M}, box {128 B of K, 128 rows};  MN-major -> dims {M, K}, box {128 B of M, BKE k-rows}
+  CUtensorMap ta = g.a_mn ? make_tmap_2d(g.A, eb, false, g.M, g.K, g.lda * eb, MNC, BKE)
+                          : make_tmap_2d(g.A, eb, false, g.K, g.M, g.lda * eb, BKE, BM);
+  // 2-CTA clusters (each CTA stages half of the B tile) whenever there are >= 2 M tiles
   const int cluster = (g.cluster > 0 ? g.cluster : ((g.M + BM - 1) / BM >= 2 ? 2 : 1));
-  CUtensorMap tb = g.b_mn ? make_tmap_2d(g.B, 2, false, g.N, g.K, g.ldb * 2, 64, BK)
-                          : make_tmap_2d(g.B, 2, false, g.K, g.N, g.ldb * 2, BK, BN / cluster);
-  CUtensorMap td = f32 ? make_tmap_2d(g.D, 4, true, g.N, g.M, g.ldd * 4, 32, BM)
-                       : make_tmap_2d(g.D, 2, false, g.N, g.M, g.ldd * 2, 64, BM);
-  CUtensorMap td2 = td;
-  if (g.epi == EPI_GELU_DUAL || g.epi == EPI_GELU_GRAD) {
+  CUtensorMap tb = g.b_mn ? make_tmap_2d(g.B, eb, false, g.N, g.K, g.ldb * eb, MNC, BKE)
+                          : make_tmap_2d(g.B, eb, false, g.K, g.N, g.ldb * eb, BKE, BN / cluster);
+  const bool two_out = g.epi == EPI_GELU_DUAL || g.epi == EPI_GELU_GRAD || g.epi == EPI_GELU_GRAD_Q8;
+  CUtensorMap td2{};
+  if (two_out) {
     if (!g.D2) throw std::runtime_error("photon_b200 gemm: the two-output GELU epilogues need the second output");
     td2 = make_tmap_2d(g.D2, 2, false, g.N, g.M, g.ldd2 * 2, 64, BM);
   }
+  CUtensorMap td;
+  if (g.epi == EPI_GELU_GRAD_Q8) {
+    if (!g.fp8 || !g.D8 || (g.ldd8 % 16) || (reinterpret_cast<uintptr_t>(g.D8) & 15))
+      throw std::runtime_error("photon_b200 gemm: the fp8-output epilogue needs fp8 operands and a 16-byte aligned fp8 output");
+    td = td2;   // the primary output leaves by direct stores
+  } else {
+    td = f32 ? make_tmap_2d(g.D, 4, true, g.N, g.M, g.ldd * 4, 32, BM) : make_tmap_2d(g.D, 2, false, g.N, g.M, g.ldd * 2, 64, BM);
+  }
+  if (!two_out) td2 = td;
   if ((g.epi == EPI_RESIDUAL || g.epi == EPI_DGELU || g.epi == EPI_MUL) && (!g.aux || (g.ld_aux % 8) || (reinterpret_cast<uintptr_t>(g.aux) & 15)))
     throw std::runtime_error("photon_b200 gemm: aux operand missing or not 16-byte aligned");
   if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) throw std::runtime_error("photon_b200 gemm: bias must be 16-byte aligned");
-  Params p;
+  Params p{};
   p.M = g.M, p.N = g.N, p.K = g.K;
   p.tiles_m = (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
@@ -508,9 +580,16 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   p.ld_aux = g.ld_aux;
   p.accumulate = g.accumulate;
   p.alpha = g.alpha;
-  int sms = g.num_sms > 0 ? g.num_sms : 148;
+  p.a_fmt = g.a_fmt, p.b_fmt = g.b_fmt, p.sinv_a = g.sinv_a, p.sinv_b = g.sinv_b;
+  p.d8 = reinterpret_cast<uint8_t*>(g.D8), p.ld_d8 = g.ldd8, p.out_scale = g.out_scale, p.out_amax = g.out_amax;
+  int sms = g.num_sms;
+  if (sms <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   const int tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int num_kb = (g.K + BKE - 1) / BKE;
   p.splits = 1;
   if (f32 && g.accumulate && tiles < sms && num_kb >= 16) {
     // few output tiles, long K (weight gradients): split K across CTAs, partials meet in the fp32
@@ -529,26 +608,39 @@ void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) {
   const int work_units = ((p.tiles_m + cluster - 1) / cluster) * p.tiles_n * p.splits;
   int grid = work_units * cluster < sms ? work_units * cluster : (sms / cluster) * cluster;
 
-#define PB_CASE(AM, BMJ, E)                                            \
-  if (g.a_mn == AM && g.b_mn == BMJ && g.epi == E) {                   \
-    launch_inst<AM, BMJ, E>(ta, tb, td, td2, p, grid, cluster, stream); \
-    return;                                                            \
+#define PB_CASE(AM, BMJ, E, F)                                              \
+  if (g.a_mn == AM && g.b_mn == BMJ && g.epi == E && int(g.fp8) == F) {     \
+    launch_inst<AM, BMJ, E, F>(ta, tb, td, td2, p, grid, cluster, stream);  \
+    return;                                                                 \
   }
-  PB_CASE(0, 0, EPI_BF16)
-  PB_CASE(0, 0, EPI_RESIDUAL)
-  PB_CASE(0, 0, EPI_GELU_DUAL)
-  PB_CASE(0, 0, EPI_F32)
-  PB_CASE(0, 1, EPI_BF16)
-  PB_CASE(0, 1, EPI_DGELU)
-  PB_CASE(0, 1, EPI_MUL)
-  PB_CASE(0, 0, EPI_GELU_GRAD)
-  PB_CASE(0, 1, EPI_F32)
-  PB_CASE(1, 1, EPI_F32)
-  PB_CASE(1, 1, EPI_BF16)
-  PB_CASE(1, 0, EPI_F32)
-  PB_CASE(1, 0, EPI_BF16)
+  PB_CASE(0, 0, EPI_BF16, 0)
+  PB_CASE(0, 0, EPI_RESIDUAL, 0)
+  PB_CASE(0, 0, EPI_GELU_DUAL, 0)
+  PB_CASE(0, 0, EPI_F32, 0)
+  PB_CASE(0, 1, EPI_BF16, 0)
+  PB_CASE(0, 1, EPI_DGELU, 0)
+  PB_CASE(0, 1, EPI_MUL, 0)
+  PB_CASE(0, 0, EPI_GELU_GRAD, 0)
+  PB_CASE(0, 1, EPI_F32, 0)
+  PB_CASE(1, 1, EPI_F32, 0)
+  PB_CASE(1, 1, EPI_BF16, 0)
+  PB_CASE(1, 0, EPI_F32, 0)
+  PB_CASE(1, 0, EPI_BF16, 0)
+  // fp8 operands: forward (K-major x K-major), dgrad (dY K-major x W MN-major), wgrad (both MN-major)
+  PB_CASE(0, 0, EPI_BF16, 1)
+  PB_CASE(0, 0, EPI_RESIDUAL, 1)
+  PB_CASE(0, 0, EPI_GELU_GRAD, 1)
+  PB_CASE(0, 0, EPI_GELU_GRAD_Q8, 1)
+  PB_CASE(0, 0, EPI_F32, 1)
+  PB_CASE(0, 1, EPI_BF16, 1)
+  PB_CASE(0, 1, EPI_MUL, 1)
+  PB_CASE(0, 1, EPI_F32, 1)
+  PB_CASE(1, 1, EPI_F32, 1)
+  PB_CASE(1, 1, EPI_BF16, 1)
 #undef PB_CASE
-  throw std::runtime_error("photon_b200 gemm: unsupported (a_major, b_major, epilogue) combination");
+  throw std::runtime_error("photon_b200 gemm: unsupported (a_major, b_major, epilogue, operand type) combination");
 }
+
+void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream) { gemm_launch(g, stream); }
 
 }  // namespace pb

@@ -14,6 +14,7 @@ enum Epilogue : int {
   EPI_F32 = 4,        // D (fp32) = acc*alpha   or  D += acc*alpha   (accumulate, TMA reduce-add)
   EPI_GELU_GRAD = 5,  // z = acc*alpha + bias;  D = bf16(gelu(z));  D2 = bf16(gelu'(z))  — the backward then needs no erf/exp
   EPI_MUL = 6,        // D = bf16((acc*alpha + bias) * aux)
+  EPI_GELU_GRAD_Q8 = 7,  // fp8 operands only: z = acc*alpha + bias;  D8 = e4m3(gelu(z) * *out_scale) (+ amax);  D2 = bf16(gelu'(z))
 };
 
 struct GemmArgs {
@@ -31,9 +32,19 @@ struct GemmArgs {
   float alpha = 1.0f;
   int num_sms = 0;
   int cluster = 0;   // 0 = auto (2-CTA clusters with B multicast when >= 2 M tiles), 1 or 2 to force
+  // ---- fp8 operands (tcgen05.mma kind::f8f6f4): A and B hold 1-byte elements, lda / ldb count elements (= bytes)
+  int fp8 = 0;
+  int a_fmt = 0, b_fmt = 0;           // 0 = E4M3, 1 = E5M2
+  const float* sinv_a = nullptr;      // device scalars: 1 / quantisation scale of A and of B (multiplied into alpha)
+  const float* sinv_b = nullptr;
+  void* D8 = nullptr;                 // EPI_GELU_GRAD_Q8: E4M3 output [M,N], ldd8 = row stride in bytes
+  long long ldd8 = 0;
+  const float* out_scale = nullptr;   // device scalar: quantisation scale applied to the E4M3 output
+  float* out_amax = nullptr;          // device scalar: running max |output| before scaling (bit pattern of a non-negative float)
 };
 
-void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream);
+void gemm_launch(const GemmArgs& g, cudaStream_t stream);
+void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream);   // same entry (kept for callers that predate fp8)
 
 CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint64_t inner, uint64_t outer,
                          uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);

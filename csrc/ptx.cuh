@@ -231,6 +231,27 @@ __device__ __forceinline__ void tc_mma_f16_ss_2sm_lo(uint32_t d_tmem, uint32_t a
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
       : "memory");
 }
+// fp8 operands (E4M3 / E5M2 picked per operand by the instruction descriptor), fp32 accumulate: 32 K-elements per instruction
+__device__ __forceinline__ void tc_mma_f8_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_ss_2sm_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
@@ -316,6 +337,41 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (uint32_t(b_mn_major) << 16) // B major
          | (uint32_t(N >> 3) << 17)     // N / 8
          | (uint32_t(M >> 4) << 24);    // M / 16
+}
+
+// Instruction descriptor for kind::f8f6f4 (A/B 8-bit floats, D fp32). fmt: 0 = E4M3, 1 = E5M2. MN-major operands are legal for
+// the 8-bit formats (not for the 4/6-bit ones).
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+  return (1u << 4)                      // D format  = F32
+         | (uint32_t(a_fmt) << 7)       // A format
+         | (uint32_t(b_fmt) << 10)      // B format
+         | (uint32_t(a_mn_major) << 15) // A major
+         | (uint32_t(b_mn_major) << 16) // B major
+         | (uint32_t(N >> 3) << 17)     // N / 8
+         | (uint32_t(M >> 4) << 24);    // M / 16
+}
+
+// ---------------------------------------------------------------- fp8 packing (saturating, round-to-nearest-even)
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));   // first source -> upper byte
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return uint32_t(lo) | (uint32_t(hi) << 16);
+}
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return uint32_t(lo) | (uint32_t(hi) << 16);
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffff, v, o));
+  return v;
+}
+// running maximum of NON-NEGATIVE floats: their bit patterns order like unsigned integers
+__device__ __forceinline__ void atomic_max_pos_f32(float* p, float v) {
+  if (__float_as_uint(v) > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(reinterpret_cast<unsigned int*>(p), __float_as_uint(v));
 }
 
 // ---------------------------------------------------------------- misc math / packing

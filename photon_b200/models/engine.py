@@ -63,13 +63,13 @@ class B200Engine:
             raise NotImplementedError(f"B200Engine computes in bf16 (got precision={precision}); use kernels.*=torch for fp32/fp16")
         if frozen_layers or unfrozen_layers:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
-        if precision == "amp_fp8":
-            # the reference only sketches fp8 (TransformerEngine line commented out, scripts/centralised_training.sh:91);
-            # here the config is accepted and computed in bf16 until the block-scaled kind::f8f6f4 GEMM lands
-            print("[engine] precision=amp_fp8: GEMMs run in bf16 on this build (fp8 tensor-core path not enabled)", flush=True)
         ops.ext()  # fail loudly if the extension is missing
         self.precision = precision
         kernels = dict(kernels or {})
+        # amp_fp8 (ref: scripts/centralised_training.sh:91, Composer amp_fp8 -> TransformerEngine): the four GEMMs of every block
+        # and their dgrad / wgrad run on tcgen05.mma kind::f8f6f4 (E4M3 activations / weights, E5M2 gradients, per-tensor
+        # scaling, fp32 accumulation); LayerNorm, attention, residuals, LM head, loss and optimizer stay bf16 / fp32
+        self.fp8 = precision == "amp_fp8"
         self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
         # kernels.cuda_graph: the ~330 launches of one microbatch are captured once per (batch, seq, loss scaling) and
         # replayed (the schedule is static: preallocated workspace, TMA descriptors baked into the launches)
@@ -105,6 +105,8 @@ class B200Engine:
         self._ws: dict[tuple[int, int], dict[str, Any]] = {}
         self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._bind()
+        if self.fp8:
+            self._init_fp8(int(kernels.get("fp8_amax_history_len", 16)), int(kernels.get("fp8_margin", 0)))
         self.params_updated()
 
     # ------------------------------------------------------------------ binding
@@ -147,6 +149,58 @@ class B200Engine:
         themselves (the Trainer skips this call in that case)."""
         ops.cast_bf16(self.flat.params, self.bf16_params)
 
+    # ---------------------------------------------------------------------- fp8
+    _DYN_ROLES = ("x_ln1", "x_attn", "x_ln2", "x_u", "g_dqkv", "g_dhmid", "g_dz", "g_dh")   # per block: 4 × E4M3, 4 × E5M2
+    _W_ROLES = ("wqkv", "wo", "wup", "wdown")
+
+    def _init_fp8(self, history_len: int, margin: int) -> None:
+        """Device-resident scaling state: ``meta`` = [3, n_roles] (scale, 1/scale, running amax). Roles [0, 8L) are activations
+        and gradients (delayed scaling: amax history → next scale, ``ops.fp8_update_scales``); roles [8L, 12L) are the weight
+        matrices (current scaling, re-quantised from the bf16 shadow at the start of every microbatch — two passes over
+        ≤ 2 bytes/param, so whoever wrote the shadow (optimizer, round broadcast, ZeRO step) needs no hook)."""
+        L, lay, dev = self.cfg.n_layers, self.flat.layout, self.device
+        self._n_dyn = len(self._DYN_ROLES) * L
+        n_roles = self._n_dyn + len(self._W_ROLES) * L
+        self.fp8_meta = torch.zeros(3, n_roles, dtype=torch.float32, device=dev)
+        self.fp8_meta[:2] = 1.0
+        self.fp8_hist = torch.zeros(self._n_dyn, max(1, history_len), dtype=torch.float32, device=dev)
+        self.fp8_fmax = torch.tensor([ops.FP8_MAX[0 if j < 4 else 1] for _ in range(L) for j in range(8)], dtype=torch.float32, device=dev)
+        self.fp8_pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.fp8_margin_mult = float(2.0 ** margin)
+        self.w8 = torch.zeros(lay.total, dtype=torch.uint8, device=dev)      # E4M3 weights at the flat layout's offsets
+        seg, self.w8_views = [], []
+        for i in range(L):
+            views = {}
+            for key, name in zip(self._W_ROLES, ("attn.Wqkv.weight", "attn.out_proj.weight", "ffn.up_proj.weight", "ffn.down_proj.weight")):
+                j = lay.index(f"transformer.blocks.{i}.{name}")
+                seg.append((lay.offsets[j], lay.numels[j]))
+                views[key] = lay.view(self.w8, j)
+            self.w8_views.append(views)
+        self.w8_seg = torch.tensor(seg, dtype=torch.int64, device=dev)
+        self._fp8_calibrated = False
+
+    def _role(self, name: str, layer: int) -> int:
+        if name in self._DYN_ROLES:
+            return layer * len(self._DYN_ROLES) + self._DYN_ROLES.index(name)
+        return self._n_dyn + layer * len(self._W_ROLES) + self._W_ROLES.index(name)
+
+    def _fp8_prologue(self, train: bool) -> None:
+        """Start of a microbatch: roll the delayed scales (training only) and re-quantise the weights from the shadow."""
+        if train:
+            ops.fp8_update_scales(self.fp8_meta, self.fp8_hist, self.fp8_fmax, self.fp8_pos, self._n_dyn, self.fp8_margin_mult)
+        ops.fp8_quantize_segments(self.bf16_params, self.w8, self.w8_seg, self.fp8_meta, self._n_dyn)
+
+    def fp8_state_dict(self) -> dict[str, Any] | None:
+        """Scales / amax histories, checkpointed next to the optimizer so a resumed run casts with the scales it stopped with."""
+        if not self.fp8:
+            return None
+        return {"meta": self.fp8_meta.cpu(), "hist": self.fp8_hist.cpu(), "pos": self.fp8_pos.cpu(), "calibrated": self._fp8_calibrated}
+
+    def load_fp8_state_dict(self, sd: dict[str, Any]) -> None:
+        if self.fp8 and sd and "meta" in sd and tuple(sd["meta"].shape) == tuple(self.fp8_meta.shape):
+            self.fp8_meta.copy_(sd["meta"]), self.fp8_hist.copy_(sd["hist"]), self.fp8_pos.copy_(sd["pos"])
+            self._fp8_calibrated = bool(sd.get("calibrated", True))
+
     # ---------------------------------------------------------------- workspace
     def _workspace(self, b: int, S: int) -> dict[str, Any]:
         key = (b, S)
@@ -163,9 +217,15 @@ class B200Engine:
             if self.activation_checkpointing and i > 0:
                 ws["layers"].append(ws["layers"][0])  # ONE set of block internals shared by all layers
                 continue
-            ws["layers"].append({"ln1": bf(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d),
-                                 "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": bf(T, d), "m2": f32(T), "r2": f32(T),
-                                 "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
+            if self.fp8:   # the GEMM inputs exist only as E4M3 (1 byte): 7·T·d instead of 12·T·d bytes of saved activations
+                u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)  # noqa: E731
+                ws["layers"].append({"ln1": u8(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d), "attn8": u8(T, d),
+                                     "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": u8(T, d), "m2": f32(T), "r2": f32(T),
+                                     "z": bf(T, c.expansion_ratio * d), "u": u8(T, c.expansion_ratio * d)})
+            else:
+                ws["layers"].append({"ln1": bf(T, d), "m1": f32(T), "r1": f32(T), "qkv": bf(T, 3 * d), "attn": bf(T, d),
+                                     "lse": f32(b, H, S), "hmid": bf(T, d), "ln2": bf(T, d), "m2": f32(T), "r2": f32(T),
+                                     "z": bf(T, c.expansion_ratio * d), "u": bf(T, c.expansion_ratio * d)})
             if c.clip_qkv:
                 ws["layers"][-1]["clipmask"] = torch.empty(T, 3 * d, dtype=torch.bool, device=dev)
             if c.qk_ln:   # pre-LayerNorm q / k (inputs of the two LN backward passes) and their row statistics
@@ -175,6 +235,8 @@ class B200Engine:
         ws.update(lnf=bf(T, d), mf=f32(T), rf=f32(T), dlnf=bf(T, d), dh=bf(T, d), dhmid=bf(T, d), dln=bf(T, d),
                   dqkv=bf(T, 3 * d), dattn=bf(T, d), dz=bf(T, c.expansion_ratio * d), delta=f32(b, H, S),
                   logits=bf(min(self.lm_head_chunk, T), c.vocab_size))
+        if self.fp8:   # E5M2 copy of the gradient currently flowing backward (one buffer, viewed at the width in use)
+            ws["g8"] = torch.empty(T * max(c.expansion_ratio, 3) * d, dtype=torch.uint8, device=dev)
         self._ws[key] = ws
         return ws
 
@@ -222,8 +284,13 @@ class B200Engine:
     def _block_fwd(self, i: int, ws: dict[str, Any], b: int, S: int) -> None:
         """h[i] -> h[i+1]; the block internals land in ws["layers"][i] (also the recompute step under checkpointing)."""
         c, h, w, lw = self.cfg, ws["h"], self.layers[i], ws["layers"][i]
-        ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
-        ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
+        if self.fp8:
+            M, w8, R = self.fp8_meta, self.w8_views[i], self._role
+            ops.layernorm_fwd_q8(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps, M, R("x_ln1", i))
+            ops.gemm_fp8(lw["ln1"], w8["wqkv"], lw["qkv"], M, R("x_ln1", i), R("wqkv", i), bias=w.bqkv)
+        else:
+            ops.layernorm_fwd(h[i], w.g1, w.b1, lw["ln1"], lw["m1"], lw["r1"], c.norm_eps)
+            ops.linear_fwd(lw["ln1"], w.wqkv, w.bqkv, lw["qkv"])
         if c.clip_qkv:   # attn_config.clip_qkv: clamp the fused projection; remember where the gradient passes
             torch.logical_and(lw["qkv"] > -c.clip_qkv, lw["qkv"] < c.clip_qkv, out=lw["clipmask"])
             lw["qkv"].clamp_(-c.clip_qkv, c.clip_qkv)
@@ -236,6 +303,15 @@ class B200Engine:
         if self.rope is not None:
             ops.rope_(lw["qkv"].view(b, S, 3 * c.d_model), self.rope[0], self.rope[1], c.n_heads)
         self._attention_fwd(lw, b, S)
+        if self.fp8:
+            ops.colsum_quant(lw["attn"], None, lw["attn8"], ops.E4M3, M, R("x_attn", i))
+            ops.gemm_fp8(lw["attn8"], w8["wo"], lw["hmid"], M, R("x_attn", i), R("wo", i), epi=ops.EPI_RESIDUAL, bias=w.bo, aux=h[i])
+            ops.layernorm_fwd_q8(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps, M, R("x_ln2", i))
+            # gelu(z) leaves the epilogue as E4M3 (the down-projection's operand), gelu'(z) as bf16 (the dgrad multiplier)
+            ops.gemm_fp8(lw["ln2"], w8["wup"], lw["z"], M, R("x_ln2", i), R("wup", i), epi=ops.EPI_GELU_GRAD_Q8, bias=w.bup, out2=lw["z"],
+                         out8=lw["u"], role_out=R("x_u", i))
+            ops.gemm_fp8(lw["u"], w8["wdown"], h[i + 1], M, R("x_u", i), R("wdown", i), epi=ops.EPI_RESIDUAL, bias=w.bdown, aux=lw["hmid"])
+            return
         ops.linear_fwd(lw["attn"], w.wo, w.bo, lw["hmid"], residual=h[i])
         ops.layernorm_fwd(lw["hmid"], w.g2, w.b2, lw["ln2"], lw["m2"], lw["r2"], c.norm_eps)
         ops.linear_gelu_grad_fwd(lw["ln2"], w.wup, w.bup, lw["z"], lw["u"])   # lw["z"] holds gelu'(pre-activation)
@@ -268,6 +344,25 @@ class B200Engine:
                 ops.linear_wgrad(logits, ws["lnf"][lo:hi], self.d_wte, accumulate=True)
 
     # ----------------------------------------------------------------- backward
+    def _linear_bwd(self, i: int, ws: dict[str, Any], dy: torch.Tensor, g_role: str, x: torch.Tensor, x_role: str, w_role: str,
+                    w16: torch.Tensor, dw: torch.Tensor, db: torch.Tensor | None, dx: torch.Tensor, mul: torch.Tensor | None = None) -> None:
+        """Backward of ``y = x @ w^T + b``: db += colsum(dy); dw += dy^T x; dx = dy w (optionally ``* mul``).
+        fp8: the column-sum pass also emits the E5M2 copy of ``dy`` both GEMMs read; ``x`` is the saved E4M3 input."""
+        if not self.fp8:
+            if db is not None:
+                ops.col_sum(dy, db)
+            ops.linear_wgrad(dy, x, dw)
+            ops.linear_dgrad(dy, w16, dx, mul=mul)
+            return
+        M, R = self.fp8_meta, self._role
+        T, n = dy.shape
+        dy8 = ws["g8"][: T * n].view(T, n)
+        ops.colsum_quant(dy, db, dy8, ops.E5M2, M, R(g_role, i))
+        ops.gemm_fp8(dy8, x, dw, M, R(g_role, i), R(x_role, i), a_mn=True, b_mn=True, epi=ops.EPI_F32, a_fmt=ops.E5M2, b_fmt=ops.E4M3,
+                     accumulate=True)
+        ops.gemm_fp8(dy8, self.w8_views[i][w_role], dx, M, R(g_role, i), R(w_role, i), b_mn=True, epi=ops.EPI_MUL if mul is not None else ops.EPI_BF16,
+                     a_fmt=ops.E5M2, b_fmt=ops.E4M3, aux=mul)
+
     def _backward(self, ids: torch.Tensor, ws: dict[str, Any]) -> None:
         c = self.cfg
         b, S = ids.shape
@@ -279,20 +374,11 @@ class B200Engine:
             if self.activation_checkpointing and i < c.n_layers - 1:
                 self._block_fwd(i, ws, b, S)   # recompute (the shared buffers still hold the LAST block after the forward)
             # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
-            if w.d_bdown is not None:
-                ops.col_sum(dh, w.d_bdown)
-            ops.linear_wgrad(dh, lw["u"], w.d_wdown)
-            ops.linear_dgrad(dh, w.wdown, ws["dz"], mul=lw["z"])
-            if w.d_bup is not None:
-                ops.col_sum(ws["dz"], w.d_bup)
-            ops.linear_wgrad(ws["dz"], lw["ln2"], w.d_wup)
-            ops.linear_dgrad(ws["dz"], w.wup, dln)
+            self._linear_bwd(i, ws, dh, "g_dh", lw["u"], "x_u", "wdown", w.wdown, w.d_wdown, w.d_bdown, ws["dz"], mul=lw["z"])
+            self._linear_bwd(i, ws, ws["dz"], "g_dz", lw["ln2"], "x_ln2", "wup", w.wup, w.d_wup, w.d_bup, dln)
             ops.layernorm_bwd(dln, lw["hmid"], w.g2, lw["m2"], lw["r2"], dh, dhmid, w.d_g2, w.d_b2)
             # ---- attention: hmid = h[i] + out_proj(attn(qkv(ln1(h[i]))))
-            if w.d_bo is not None:
-                ops.col_sum(dhmid, w.d_bo)
-            ops.linear_wgrad(dhmid, lw["attn"], w.d_wo)
-            ops.linear_dgrad(dhmid, w.wo, ws["dattn"])
+            self._linear_bwd(i, ws, dhmid, "g_dhmid", lw["attn8"] if self.fp8 else lw["attn"], "x_attn", "wo", w.wo, w.d_wo, w.d_bo, ws["dattn"])
             self._attention_bwd(lw, ws, b, S)
             if c.qk_ln:
                 dqkv3 = ws["dqkv"].view(-1, 3, c.d_model)
@@ -303,10 +389,7 @@ class B200Engine:
                     dqkv3[:, j].copy_(ws["qk_tmp2"])
             if c.clip_qkv:
                 ws["dqkv"].mul_(lw["clipmask"])
-            if w.d_bqkv is not None:
-                ops.col_sum(ws["dqkv"], w.d_bqkv)
-            ops.linear_wgrad(ws["dqkv"], lw["ln1"], w.d_wqkv)
-            ops.linear_dgrad(ws["dqkv"], w.wqkv, dln)
+            self._linear_bwd(i, ws, ws["dqkv"], "g_dqkv", lw["ln1"], "x_ln1", "wqkv", w.wqkv, w.d_wqkv, w.d_bqkv, dln)
             ops.layernorm_bwd(dln, h[i], w.g1, lw["m1"], lw["r1"], dhmid, dh, w.d_g1, w.d_b1)
         ops.embed_bwd(ids.reshape(-1), dh, self.d_wte, self.d_wpe, S)
 
@@ -316,6 +399,8 @@ class B200Engine:
         ws = self._workspace(b, S)
         targets = shift_labels(ids).reshape(-1)
         self._stats.zero_()
+        if self.fp8:
+            self._fp8_prologue(train=True)
         self._forward(ids, ws)
         self._head(ws, targets, grad_scale, train=True)
         self._backward(ids, ws)
@@ -324,6 +409,13 @@ class B200Engine:
         """Accumulate d(Σ token-loss · scale / denom) into ``flat.grads``; returns (loss_sum, n_tokens)."""
         b, S = ids.shape
         grad_scale = scale / denom
+        if self.fp8 and not self._fp8_calibrated:
+            # delayed scaling has no history yet: one discarded pass at scale 1 records every role's amax (gradients would
+            # underflow E5M2 unscaled), the next prologue turns them into scales
+            saved = self.flat.grads.clone()
+            self._fwd_bwd_eager(ids, grad_scale)
+            self.flat.grads.copy_(saved)
+            self._fp8_calibrated = True
         graphable = self.use_graph and self.attn_mode == "b200" and S % 128 == 0 and not self.collect_activation_stats
         if not graphable:
             n0 = ops.launch_count()
@@ -368,6 +460,8 @@ class B200Engine:
         ws = self._workspace(b, S)
         targets = shift_labels(ids).reshape(-1)
         self._stats.zero_()
+        if self.fp8:
+            self._fp8_prologue(train=False)
         self._forward(ids, ws)
         self._head(ws, targets, 0.0, train=False)
         st = self._stats.clone()

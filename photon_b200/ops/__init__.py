@@ -52,7 +52,9 @@ def add_launch_count(n: int) -> None:
 
 
 # --------------------------------------------------------------------------------- GEMM
-EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2, 3, 4, 5, 6
+EPI_BF16, EPI_RESIDUAL, EPI_GELU_DUAL, EPI_DGELU, EPI_F32, EPI_GELU_GRAD, EPI_MUL, EPI_GELU_GRAD_Q8 = 0, 1, 2, 3, 4, 5, 6, 7
+E4M3, E5M2 = 0, 1          # operand formats of the kind::f8f6f4 GEMMs
+FP8_MAX = (448.0, 57344.0)
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
@@ -96,6 +98,44 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, gelu_pre: 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, accumulate: bool = True, alpha: float = 1.0) -> torch.Tensor:
     """dw[N,K] (+)= dy^T @ x in fp32 (both operands consumed MN-major; TMA reduce-add when accumulating)."""
     return gemm(dy, x, dw, a_mn=True, b_mn=True, epi=EPI_F32, accumulate=accumulate, alpha=alpha)
+
+
+# ------------------------------------------------------------------------------ fp8 GEMM
+def gemm_fp8(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, meta: torch.Tensor, role_a: int, role_b: int, *,
+             a_mn: bool = False, b_mn: bool = False, epi: int = EPI_BF16, a_fmt: int = E4M3, b_fmt: int = E4M3,
+             bias: torch.Tensor | None = None, aux: torch.Tensor | None = None, out2: torch.Tensor | None = None,
+             accumulate: bool = False, alpha: float = 1.0, cluster: int = 0, out8: torch.Tensor | None = None,
+             role_out: int = -1) -> torch.Tensor:
+    """``out = epilogue(alpha / (scale[role_a] * scale[role_b]) * A8 @ B8^T)`` — 1-byte operands (E4M3 / E5M2 per operand) on
+    ``tcgen05.mma kind::f8f6f4``, fp32 accumulation. ``meta`` = float32 ``[3, n_roles]`` (scale, 1/scale, amax) on the device;
+    the de-scales are read by the kernel, so nothing here touches the host. ``EPI_GELU_GRAD_Q8`` writes ``out8`` (E4M3,
+    scaled by ``scale[role_out]``, amax recorded) and ``out2`` = gelu'; ``out`` is then unused (pass ``out2``)."""
+    ext().gemm_fp8(a, b, out, int(a_mn), int(b_mn), int(epi), int(a_fmt), int(b_fmt), meta, int(role_a), int(role_b), bias, aux, out2,
+                   bool(accumulate), float(alpha), int(cluster), out8, int(role_out))
+    return out
+
+
+def layernorm_fwd_q8(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, y8: torch.Tensor, mean: torch.Tensor,
+                     rstd: torch.Tensor, eps: float, meta: torch.Tensor, role: int) -> torch.Tensor:
+    """LayerNorm whose only output is the E4M3 tensor the next GEMM reads (scaled by ``scale[role]``, ``amax[role]`` updated)."""
+    ext().layernorm_fwd_q8(x, gamma, beta, y8, mean, rstd, float(eps), meta, int(role))
+    return y8
+
+
+def colsum_quant(dy: torch.Tensor, out_sum: torch.Tensor | None, y8: torch.Tensor | None, fmt: int = E5M2,
+                 meta: torch.Tensor | None = None, role: int = -1) -> None:
+    """One read of ``dy`` [T,N]: ``out_sum[j] += Σ_t dy[t,j]`` (bias gradient) and ``y8 = fp8(dy * scale[role])``."""
+    ext().colsum_quant(dy, out_sum, y8, int(fmt), meta, int(role))
+
+
+def fp8_quantize_segments(src_bf16: torch.Tensor, dst8: torch.Tensor, seg: torch.Tensor, meta: torch.Tensor, role0: int) -> None:
+    """Per-tensor current scaling of ``seg`` = int64 [n,2] (offset, numel) slices of a flat bf16 plane → E4M3 in ``dst8``."""
+    ext().fp8_quantize_segments(src_bf16, dst8, seg, meta, int(role0))
+
+
+def fp8_update_scales(meta: torch.Tensor, hist: torch.Tensor, fmax: torch.Tensor, pos: torch.Tensor, n: int, margin_mult: float = 1.0) -> None:
+    """Delayed scaling for roles [0, n): amax → history ring → scale for the next cast; amax reset."""
+    ext().fp8_update_scales(meta, hist, fmax, pos, int(n), float(margin_mult))
 
 
 # ---------------------------------------------------------------------------- fused ops

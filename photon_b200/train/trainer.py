@@ -462,6 +462,8 @@ class Trainer:
 
     def _fp8_state(self) -> dict[str, Any] | None:
         """amax histories / scales of an ``amp_fp8`` run (the delayed-scaling recipe resumes with the scales it stopped with)."""
+        if hasattr(self.state.backend, "fp8_state_dict"):      # the sm_100a engine keeps its scales on the device
+            return self.state.backend.fp8_state_dict()
         if not getattr(self.state.backend, "fp8_layers", None):
             return None
         from photon_b200.train.fp8 import fp8_state_dict
@@ -542,10 +544,13 @@ class Trainer:
                 self._train_iter = None
         if self.scaler and s.get("scaler") and not ignored("scaler"):
             self.scaler.scale = float(s["scaler"]["scale"])
-        if s.get("fp8") and getattr(st.backend, "fp8_layers", None) and not ignored("fp8"):
-            from photon_b200.train.fp8 import load_fp8_state_dict
+        if s.get("fp8") and not ignored("fp8"):
+            if hasattr(st.backend, "load_fp8_state_dict"):
+                st.backend.load_fp8_state_dict(s["fp8"])
+            elif getattr(st.backend, "fp8_layers", None):
+                from photon_b200.train.fp8 import load_fp8_state_dict
 
-            load_fp8_state_dict(st.backend.model, s["fp8"])
+                load_fp8_state_dict(st.backend.model, s["fp8"])
         if not ignored("rng") and "rng" in ck and "torch" in ck["rng"]:
             torch.set_rng_state(ck["rng"]["torch"])
 

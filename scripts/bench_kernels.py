@@ -36,7 +36,10 @@ def main():
     pk = measured_peaks()
     rows = []
     T = 32768
-    shapes = [("qkv fwd", T, 2304, 768, 0, 0), ("out fwd", T, 768, 768, 0, 0), ("up fwd", T, 3072, 768, 0, 0),
+    d1 = 2048   # MPT-1B geometry (BASELINE config #4)
+    shapes = [("1b qkv fwd", 16384, 3 * d1, d1, 0, 0), ("1b up fwd", 16384, 4 * d1, d1, 0, 0), ("1b down fwd", 16384, d1, 4 * d1, 0, 0),
+              ("1b up dgrad", 16384, d1, 4 * d1, 0, 1), ("1b up wgrad", 4 * d1, d1, 16384, 1, 1),
+              ("qkv fwd", T, 2304, 768, 0, 0), ("out fwd", T, 768, 768, 0, 0), ("up fwd", T, 3072, 768, 0, 0),
               ("down fwd", T, 768, 3072, 0, 0), ("up dgrad", T, 768, 3072, 0, 1), ("up wgrad", 3072, 768, T, 1, 1),
               ("lmhead fwd", 8192, 50368, 768, 0, 0), ("lmhead dgrad", 8192, 768, 50368, 0, 1), ("lmhead wgrad", 50368, 768, 8192, 1, 1),
               ("square 8192", 8192, 8192, 8192, 0, 0)]
@@ -53,8 +56,15 @@ def main():
         else:
             cub = timeit(lambda: torch.matmul(A, Bt))
         fl = 2.0 * M * N * K
+        # same shape on kind::f8f6f4 (E4M3 x E4M3 forward, E5M2 x E4M3 backward; operands pre-quantised, de-scale in the epilogue)
+        a8 = (a.float().clamp(-400, 400)).to(torch.float8_e5m2 if (amn or bmn) else torch.float8_e4m3fn).view(torch.uint8)
+        b8 = (b.float().clamp(-400, 400)).to(torch.float8_e4m3fn).view(torch.uint8)
+        meta = torch.ones(3, 2, device=dev)
+        fp8 = timeit(lambda: ops.gemm_fp8(a8, b8, out, meta, 0, 1, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16,
+                                          a_fmt=ops.E5M2 if (amn or bmn) else ops.E4M3, b_fmt=ops.E4M3))
         rows.append(dict(op=name, M=M, N=N, K=K, ours_ms=ours, cublas_ms=cub, ours_tflops=fl / ours / 1e9, cublas_tflops=fl / cub / 1e9,
-                         frac_of_measured_peak=fl / ours / 1e-3 / pk["bf16_flops"]))
+                         frac_of_measured_peak=fl / ours / 1e-3 / pk["bf16_flops"], fp8_ms=fp8, fp8_tflops=fl / fp8 / 1e9,
+                         fp8_speedup_vs_bf16=ours / fp8))
         print(rows[-1], flush=True)
     # memory-bound kernels
     d = 768
