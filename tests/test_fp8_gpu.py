@@ -61,7 +61,7 @@ def test_gemm_fp8_dgrad_mn_major_weight(cluster):
     """dX = dY(E5M2, K-major) · W(E4M3, stored [N,K], consumed MN-major) — the 8-bit formats allow MN-major operands."""
     from photon_b200 import ops
 
-    T, N, K = 640, 1088, 520
+    T, N, K = 640, 1088, 528
     dy, w = torch.randn(T, N, device=_dev()) * 1e-3, torch.randn(N, K, device=_dev()) * 0.05
     sg, sw = 57344.0 / dy.abs().max().item(), 448.0 / w.abs().max().item()
     dy8, dyd = _q(dy, E5M2, sg)
@@ -81,7 +81,7 @@ def test_gemm_fp8_wgrad_both_mn_major_splitk(cluster):
     """dW += dY^T(E5M2) · X(E4M3): both operands consumed MN-major from their [T, ·] storage, fp32 TMA reduce-add, split-K."""
     from photon_b200 import ops
 
-    T, N, K = 4352, 640, 520
+    T, N, K = 4352, 640, 528
     dy, x = torch.randn(T, N, device=_dev()) * 1e-3, torch.randn(T, K, device=_dev())
     sg, sx = 57344.0 / dy.abs().max().item(), 448.0 / x.abs().max().item()
     dy8, dyd = _q(dy, E5M2, sg)
@@ -207,29 +207,49 @@ def _make(precision, graph):
     return B200Engine(cfg, device=_dev(), precision=precision, kernels={"cuda_graph": graph}, seed=3)
 
 
+def _torch_grads(precision, params, ids):
+    """Gradients of the stock-PyTorch backend (``amp_fp8`` = the quantise/de-quantise emulation of train/fp8.py: the recipe oracle)."""
+    from photon_b200.models.mpt import MPTConfig
+    from photon_b200.train.backend import TorchBackend
+
+    cfg = MPTConfig(d_model=256, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=2048)
+    be = TorchBackend(cfg, device=_dev(), precision=precision, seed=3)
+    be.flat.params.copy_(params)
+    be.flat.zero_grad()
+    be.fwd_bwd(ids, 4.0 * 255)
+    return be.flat.grads.clone()
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_engine_amp_fp8_tracks_bf16(graph):
-    """Same weights, same batch: the fp8 engine's loss and gradients follow the bf16 engine's (cosine > 0.98 per tensor on the
-    large matrices), through eager launches and through CUDA-graph replay; scales move off their initial value."""
+    """Same weights, same batch: the fp8 engine's loss follows the bf16 engine's and its gradients are as close to the bf16
+    gradients as the recipe allows — per large tensor, cosine(ours fp8, ours bf16) is no worse than what the PyTorch emulation of
+    the same recipe achieves against PyTorch bf16 (minus a small margin) — through eager launches and CUDA-graph replay."""
     e8, e16 = _make("amp_fp8", graph), _make("amp_bf16", graph)
     assert e8.fp8 and not e16.fp8
     e8.flat.params.copy_(e16.flat.params)
     e8.params_updated()
     ids = torch.randint(0, 2048, (4, 256), device=_dev())
-    for e in (e8, e16):
-        e.flat.zero_grad()
+    o8, o16 = _torch_grads("amp_fp8", e16.flat.params, ids), _torch_grads("amp_bf16", e16.flat.params, ids)
     for _ in range(2):           # second call replays the graph (when enabled) and uses rolled scales
+        for e in (e8, e16):
+            e.flat.zero_grad()
         l8, n8 = e8.fwd_bwd(ids, 4.0 * 255)
         l16, n16 = e16.fwd_bwd(ids, 4.0 * 255)
     assert float(n8) == float(n16)
     assert abs(float(l8) - float(l16)) / float(l16) < 2e-2
     lay = e8.flat.layout
+
+    def cos(x, y, i):
+        a, b = lay.view(x, i).flatten().double(), lay.view(y, i).flatten().double()
+        return float((a @ b) / (a.norm() * b.norm()))
+
     for i, name in enumerate(lay.names):
         if lay.numels[i] < 256 * 256:
             continue
-        a, b = lay.view(e8.flat.grads, i).flatten().double(), lay.view(e16.flat.grads, i).flatten().double()
-        cos = float((a @ b) / (a.norm() * b.norm()))
-        assert cos > 0.98, (name, cos)
+        assert cos(e16.flat.grads, o16, i) > 0.99, (name, "bf16 engine vs torch bf16")
+        ours, oracle = cos(e8.flat.grads, e16.flat.grads, i), cos(o8, o16, i)
+        assert ours > 0.95 and ours > oracle - 0.015, (name, ours, oracle)
     assert float((e8.fp8_meta[0, : e8._n_dyn] != 1.0).float().mean()) == 1.0     # every activation / gradient role got a scale
     sd = e8.fp8_state_dict()
     e8.load_fp8_state_dict(sd)
