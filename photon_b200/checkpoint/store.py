@@ -133,7 +133,8 @@ class CheckpointStore:
         src, dst = ph.get("restore_run_uuid"), cfg.get("run_uuid")
         if not src or not dst:
             raise ValueError("import_checkpoints needs both run_uuid and photon.restore_run_uuid")
-        rnd = self.interpret_resume_round(str(src), ph.get("resume_round", -1), state_keys)
+        want = ph.get("resume_round", -1)
+        rnd = self.interpret_resume_round(str(src), -1 if want is None else want, state_keys)   # restoring a run with no round named = its newest
         if rnd is None or self.obtain_sorted_rounds(str(dst), state_keys):
             return None
         self.copy_old_checkpoints_to_new_run(str(src), str(dst), rnd, state_keys=state_keys,
@@ -142,8 +143,8 @@ class CheckpointStore:
         # client checkpoints normally live under llm_config.save_folder, whose path carries the run id
         # (``…/{run_uuid}/clients/client_{cid}/``): bring the old run's over so optimizer state / data position survive
         sf = (cfg.get("llm_config") or {}).get("save_folder")
-        if bool(ph.get("copy_client_checkpoints", True)) and sf and str(dst) in str(sf):
-            old_sf = Path(str(sf).replace(str(dst), str(src)))
+        if bool(ph.get("copy_client_checkpoints", True)) and sf and str(dst) in Path(str(sf)).parts:
+            old_sf = Path(*[str(src) if part == str(dst) else part for part in Path(str(sf)).parts])   # whole path components only
             for cid in range(int(cfg["fl"]["n_total_clients"])):
                 s_dir = old_sf / f"client_{cid}"
                 if s_dir.is_dir():

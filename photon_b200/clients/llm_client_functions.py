@@ -57,24 +57,31 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
     trainer.save_ignore_keys = list(train_cfg.get("save_ignore_keys") or [])   # reset_optimizer → client checkpoints carry no optimizer state
     metrics["client/fit_init_time"] = _now() - t_start
 
-    # ---- install the round's parameters (+ momenta / personalised / re-initialised layers)
+    # ---- client checkpoint FIRST (optimizer moments, data position, and the model it holds), THEN the round's parameters on
+    # top — the reference's order (ref: llm_client_functions.py:126-168). Only a client that already finished this round
+    # (skip_iteration) keeps the checkpoint's model: it IS the round's result. Loading after the install would overwrite the
+    # freshly broadcast global model with the client's stale weights and silently bypass the aggregation.
     t0 = _now()
     st = trainer.state
+    if load_set and train_cfg.get("load_path"):
+        load_trainer_checkpoint(trainer, str(train_cfg["load_path"]), load_ignore_keys(fc))
     if fc.reset_optimizer and not fc.aggregate_momenta:
         st.optimizer.reset_state()
     params, m = manipulate_pre_training_params(trainer, payload, fc, cid, state)
     metrics.update(m)
-    st.flat.params.copy_(params)
-    if shadow_payload is not None and getattr(st.backend, "bf16_params", None) is not None:
-        st.backend.bf16_params.copy_(shadow_payload)  # bf16 cast already produced by the round broadcast kernel
-    else:
-        st.backend.params_updated()
+    if not skip_iteration:
+        st.flat.params.copy_(params)
+        if shadow_payload is not None and getattr(st.backend, "bf16_params", None) is not None:
+            st.backend.bf16_params.copy_(shadow_payload)  # bf16 cast already produced by the round broadcast kernel
+        else:
+            st.backend.params_updated()
     initial = params if params.data_ptr() != st.flat.params.data_ptr() else params.clone()
-    if load_set and train_cfg.get("load_path"):
-        load_trainer_checkpoint(trainer, str(train_cfg["load_path"]), load_ignore_keys(fc))
-    # LR schedule continuity: the local clock starts at the federation's cumulative step count
-    if not fc.reset_timestamp:
-        st.timestamp.batch = max(st.timestamp.batch, server_steps) if load_set else server_steps
+    # LR schedule continuity: the local clock starts at the federation's cumulative step count (a checkpoint written in the
+    # middle of the round restarts the round from the global model, like the reference)
+    if skip_iteration:
+        pass
+    elif not fc.reset_timestamp:
+        st.timestamp.batch = server_steps
     else:
         st.timestamp.reset()
     metrics["client/fit_set_parameters_time"] = _now() - t0

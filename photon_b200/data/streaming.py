@@ -14,6 +14,7 @@ directory does not exist while ``allow_synthetic``) is backed by
 from __future__ import annotations
 
 import os
+import sys
 import queue
 import zlib
 import threading
@@ -53,13 +54,23 @@ class Stream:
         return p / self.split if self.split else p
 
 
+_WARNED_SYNTH: set[str] = set()
+
+
 def _open_stream(st: Stream, seq_len: int, idx: int, synth_samples: int, seed: int, allow_synthetic: bool,
                  synth_vocab: int | None = None) -> Any:
     d = st.directory()
     if d is not None and (d / INDEX_NAME).exists():
         return open_shard_dir(d, validate_hash=bool(st.validate_hash))   # our shards, or an MDS directory written for the reference
-    if d is not None and not allow_synthetic:
-        raise FileNotFoundError(f"stream '{st.name}': {d} has no {INDEX_NAME} (and remote fetch is unavailable offline)")
+    strict = os.environ.get("PHOTON_STRICT_DATA", "").lower() in ("1", "true", "yes")   # the launch scripts export it for real runs
+    if d is not None and (strict or not allow_synthetic):
+        raise FileNotFoundError(f"stream '{st.name}': {d} has no {INDEX_NAME} (and remote fetch is unavailable offline); "
+                                "use local: synthetic://<name> for synthetic tokens")
+    if d is not None and str(d) not in _WARNED_SYNTH:
+        # a typo or an unmounted dataset must not train on synthetic tokens unnoticed
+        _WARNED_SYNTH.add(str(d))
+        print(f"[streaming] WARNING: stream '{st.name}': {d} has no {INDEX_NAME} -> SYNTHETIC C4-shaped tokens are used instead. "
+              "Set dataset.<split>.allow_synthetic=false or PHOTON_STRICT_DATA=1 to make this an error.", file=sys.stderr, flush=True)
     sid = idx
     if st.local and str(st.local).startswith(SYNTH_PREFIX):
         tail = str(st.local)[len(SYNTH_PREFIX):]

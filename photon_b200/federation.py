@@ -71,7 +71,7 @@ class FederationRuntime:
         self.fit_config_fn = get_photon_fit_config_fn(cfg)
         self.eval_config_fn = get_photon_evaluate_config_fn(cfg)
         self.trainer: Trainer | None = None
-        self._opt_states: dict[int, tuple[torch.Tensor, torch.Tensor, int]] = {}
+        self._opt_states: dict[int, tuple[torch.Tensor, torch.Tensor, int]] = {}   # cid -> (exp_avg, exp_avg_sq, step) of its last fit HERE
         self._local_params: dict[int, torch.Tensor] = {}   # personalised-layer memory per client
         self.layout: FlatLayout | None = None        # exchange layout (3 planes with fl.aggregate_momenta)
         self.model_layout: FlatLayout | None = None  # the trainer's parameter layout
@@ -166,6 +166,10 @@ class FederationRuntime:
         rb.begin_round()
         results: list[FitRes] = []
         keep_opt = not bool(self.cfg["fl"]["reset_optimizer"])
+        mine = set(self.my_clients(sampled))
+        for cid in sampled:     # every rank sees the same sample: a client another node trains this round leaves stale moments here
+            if cid not in mine:
+                self._opt_states.pop(cid, None)
         t_fit = 0.0
         for cid in self.my_clients(sampled):
             t0 = time.time()
@@ -174,7 +178,10 @@ class FederationRuntime:
                     raise RuntimeError(f"fault injection: client {cid} dropped in round {server_round}")
                 fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
                 opt = tr.state.optimizer
-                if keep_opt and cid in self._opt_states:   # multiplexed clients keep their own moments
+                if keep_opt and cid in self._opt_states:
+                    # the client's own moments from ITS last participation (entries are dropped above as soon as the client
+                    # trains elsewhere, so what is found here is never older than that); a client checkpoint, when present,
+                    # is loaded on top by llm_fit. Keyed by client id, whatever the client-to-node mapping of the round.
                     m, v, step = self._opt_states[cid]
                     opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)  # per-rank planes (a slice when the state is sharded)
                     opt.step_count = step
@@ -186,7 +193,7 @@ class FederationRuntime:
                     shadow = rb.global_shadow()
                     payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
                                                              shadow_payload=None if shadow is None else shadow[: self.model_layout.total])
-                if keep_opt and len(self.my_clients(sampled)) > 1:
+                if keep_opt:   # always (also when the node hosts one client): behaviour must not depend on the topology
                     self._opt_states[cid] = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
                 if fc.personalized_layers:
                     self._local_params[cid] = tr.state.flat.params.clone()

@@ -227,8 +227,10 @@ class Trainer:
     def _next_batch(self) -> dict[str, torch.Tensor]:
         if self.train_loader is None:
             raise RuntimeError("Trainer has no train_loader")
+        empty_epochs = 0
         while True:
-            if self._train_iter is None:
+            fresh = self._train_iter is None
+            if fresh:
                 self._train_iter = iter(self.train_loader)
             limit = self.train_subset_num_batches
             try:
@@ -240,6 +242,10 @@ class Trainer:
                     self._train_iter.close()
                 self._train_iter = None
                 self.state.timestamp.advance_epoch()
+                empty_epochs = empty_epochs + 1 if fresh else 0
+                if empty_epochs >= 2:   # a whole epoch without a single batch (dataset < one batch with drop_last, subset of 0)
+                    raise RuntimeError("the train loader yields no batches per epoch (dataset smaller than one batch with drop_last, "
+                                       "or train_subset_num_batches=0): nothing to train on")
 
     def _agree_min(self, v: int) -> int:
         if self.world_size > 1 and dist.is_initialized():

@@ -10,6 +10,8 @@ export SAVE_PATH=${SAVE_PATH:-"$PROJECT_PATH/runs"}
 export PHOTON_SAVE_PATH=${PHOTON_SAVE_PATH:-"$SAVE_PATH/$RUN_UUID"}
 export DATASET_CACHE_DIR=${DATASET_CACHE_DIR:-"$PROJECT_PATH/data"}
 export MASTER_ADDR=127.0.0.1
+# real runs must not fall back to synthetic tokens when a dataset path is wrong (PHOTON_STRICT_DATA=0 to allow, e.g. smoke runs)
+export PHOTON_STRICT_DATA=${PHOTON_STRICT_DATA:-1}
 mkdir -p "$PHOTON_SAVE_PATH"
 if command -v nvidia-smi >/dev/null 2>&1; then N_GPUS=${N_GPUS:-$(nvidia-smi -L | wc -l)}; else N_GPUS=${N_GPUS:-0}; fi
 export APPOINTED_CUDA_DEVICE=${APPOINTED_CUDA_DEVICE:-$(seq -s, 0 $((N_GPUS > 0 ? N_GPUS - 1 : 0)))}

@@ -466,3 +466,35 @@ def test_history_json_dump(tmp_path):
     rec = json.loads(dump_history(h, tmp_path / "history.json").read_text())
     assert rec["losses_distributed"][0][0] == 0 and rec["metrics_distributed_fit"]["server/n_failures"] == [[1, 0.0]]
     assert "server/round_time" in rec["metrics_centralized"] and "server/broadcast_pre_time" in rec["metrics_centralized"]
+
+
+def test_round_two_trains_from_the_broadcast_global_not_the_client_checkpoint(tmp_path, monkeypatch):
+    """With client checkpoints on (save_folder set, reset_checkpoint=false) the client's checkpoint is loaded BEFORE the round's
+    parameters are installed: right before ``fit()`` in every round the trainer holds exactly the broadcast global model, not the
+    client's own stale weights (ref order: photon/clients/llm_client_functions.py:126-168)."""
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server.broadcast_utils import broadcast_parameters_to_nodes
+    from photon_b200.train.trainer import Trainer
+
+    cfg = _cfg(tmp_path, "run_uuid=order", "fl.n_total_clients=2", "fl.n_clients_per_round=2", "fl.strategy_name=fedavg")
+    rt = FederationRuntime(cfg, device=torch.device("cpu"), rank=0, world_size=1)
+    rt.build()
+    broadcast_parameters_to_nodes(rt, rt.initial_parameters())
+    seen = []
+    real_fit = Trainer.fit
+
+    def spy(self, *a, **k):
+        seen.append(bool(torch.equal(self.state.flat.params, rt.round_backend.global_params()[: self.state.flat.layout.total])))
+        return real_fit(self, *a, **k)
+
+    monkeypatch.setattr(Trainer, "fit", spy)
+    for rnd in (1, 2, 3):
+        res = rt.run_clients_fit(rnd, [0, 1])
+        assert all(r.status.code == 0 for r in res), [r.status.message for r in res]
+        for r in res:
+            rt.client_states[r.cid] = rt.client_states[r.cid]
+        rt.finish_round(rnd)
+        rt.server_steps_cumulative += 2
+    assert len(seen) == 6 and all(seen), seen
+    assert list((tmp_path / "clients").rglob("*.pt")), "client checkpoints were expected on disk"
+    rt.close()
