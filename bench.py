@@ -1,32 +1,33 @@
 #!/usr/bin/env python
-"""Headline benchmark: tokens/sec of one federated round of MPT-125M, 8 clients, on N B200s.
+"""Headline benchmark of photon_b200 — one script for every BASELINE.json config.
 
-    python bench.py --gpus 1 --steps 4 --warmup 3
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --gpus 1 --steps 4 --warmup 3                       # config #2 (default): MPT-125M, 8 federated clients
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W [--mode fed|ddp|fed4x2] [--model mpt-1b --server fedadam --precision amp_fp8]
 
-Config = ``fed_125m_example``: 8 clients per round, local batch 32 × S 2048,
-ADOPT lr 6e-4, cosine schedule, FedAvg (Nesterov η=1 μ=0), ``reset_optimizer=false``, amp_bf16,
-random-init MPT-125M, synthetic C4-shaped tokens.  The 8 clients are spread over the N GPUs
-(8/N per GPU, time-multiplexed on the node's persistent Trainer) → total work per round is
-fixed → ``"scaling": "strong"``.  One "step" = every client advances one local optimizer step
-(8 × 32 × 2048 tokens); the timed region is ONE full round of K local steps per client **plus
-the round's aggregate + server optimizer + broadcast** (the fused NVLink kernel).
+``--mode fed``  (configs #2 / #4)  ``fed_125m_example``: 8 clients per round spread over the N GPUs (8/N per GPU, time-multiplexed on the
+    node's persistent Trainer), local batch 32 × 2048, ADOPT (125M) / DecoupledAdamW (1B+), FedAvg ≡ Nesterov η=1 μ=0 or FedAdam;
+    one "step" = every client advances one local optimizer step (8 × 32 × 2048 tokens); the timed region is ONE full round of K
+    local steps per client PLUS the round's aggregate + server optimizer + broadcast (the fused NVLink kernel).
+``--mode ddp``  (config #3)  ``cen_125m_example``: centralised training, global batch 256 over the N GPUs, DecoupledAdamW, no clipping,
+    DDP with the fused NVLink all-reduce on the flat gradient bucket; one step = one optimizer step (256 × 2048 tokens).
+``--mode fed4x2`` (config #5)  4 clients × 2 GPUs: DDP inside every client (fused all-reduce), federated round across the clients.
 
-Two measurements of the same work:
-* ``value``      — device time (CUDA events on the launching stream, max over ranks);
-* ``e2e.value``  — wall clock around the public API call ``FederationRuntime.run_clients_fit``
-                   + ``finish_round`` (every step copies its inputs H2D from pinned host memory and
-                   reads the loss back D2H — that is how the Trainer works; bytes are counted).
+Total work per step is fixed in every mode → ``"scaling": "strong"``.  Two measurements of the same work:
+* ``value``      device time (CUDA events on the launching stream, max over ranks; per-rank min/max printed as ``rank_dev_ms``);
+* ``e2e.value``  wall clock around the public API call (``FederationRuntime.run_clients_fit`` + ``finish_round`` / ``Trainer.fit``):
+                 every step copies its inputs H2D from pinned host memory and reads the loss back D2H (bytes counted).
 
-``--impl reference`` must run the UNMODIFIED reference from ``baseline/_ref``; it cannot be
-installed offline here (DESIGN.md §Reference arm) so that arm prints ``unavailable``.
-``--impl torch`` runs the reference-EQUIVALENT stock path (PyTorch ops + SDPA + host shm round)
-for our own A/B numbers.
+In the same invocation the reference-EQUIVALENT arm is measured too (``torch_arm``: stock PyTorch ops — cuBLAS, SDPA, ATen LN/GELU/CE,
+torch optimizer — with the reference's communication pattern: per-parameter NCCL all-reduce for DDP, host shared-memory round for the
+federation), same K, same batch, microbatch ``auto`` (32 unless it runs out of memory); ``vs_torch_arm`` = ours ÷ that.
+``--impl reference`` must run the UNMODIFIED reference from ``baseline/_ref``; it cannot be installed offline here, so
+that arm prints ``unavailable``.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -40,11 +41,15 @@ sys.path.insert(0, str(ROOT))
 N_CLIENTS = 8
 LOCAL_BATCH = 32
 SEQ = 2048
+DDP_GLOBAL_BATCH = 256
+MODEL_NAMES = {"mpt-125m": "MPT-125M", "mpt-1b": "MPT-1B", "mpt-3b": "MPT-3B", "mpt-7b": "MPT-7B"}
 
 
 def reference_arm() -> None:
-    why = ("reference needs poetry-core build backend + flwr/composer/llm-foundry/streaming/ray/hydra (git/URL deps) — "
-           "none in the image or /opt/wheelhouse, no network; pip install --no-index fails (see DESIGN.md)")
+    why = ("reference not installable offline: `pip install --no-index --no-build-isolation --find-links /opt/wheelhouse [--no-deps] "
+           "--target baseline/_ref` fails with ModuleNotFoundError: poetry (build backend poetry-core absent from image and wheelhouse); "
+           "its runtime deps flwr/composer/llm-foundry/streaming (git forks), ray, hydra, omegaconf, torchmetrics are absent too "
+           "(DESIGN.md §0); the same-box stand-in is the `torch_arm` key of the default run")
     ref = ROOT / "baseline" / "_ref" / "photon"
     if ref.exists():
         try:
@@ -75,10 +80,6 @@ class ClockSampler:
                 self.proc = None
         return self
 
-    def mark(self) -> None:
-        """Timed region starts now: drop what was sampled while idle."""
-        self._t0 = time.time()
-
     def stop(self) -> None:
         if self.proc is None:
             return
@@ -101,26 +102,218 @@ class ClockSampler:
                 "note": "median over samples with power draw > 300 W (under load)"}
 
 
-def build_cfg(impl: str, steps: int, model: str, attention: str, microbatch: int = LOCAL_BATCH, server: str = "fedavg"):
+# ------------------------------------------------------------------------------------------------------------------ configs
+def _common_overrides(args, impl: str) -> list[str]:
+    ov = [f"llm_config={args.model}", "run_uuid=bench", f"llm_config.precision={args.precision}", "llm_config.log_to_console=false",
+          "~llm_config.loggers.wandb", "~llm_config.loggers.tensorboard", "llm_config.save_folder=null", "llm_config.save_interval=1000000ba",
+          "llm_config.eval_interval=1000000ba", "~llm_config.callbacks", "photon.checkpoint=false",
+          "++llm_config.metric_sync_interval=1",    # the loss is read back EVERY step: that D2H is part of the e2e number
+          "dataset.train.root_local=synthetic://c4", "dataset.val.root_local=synthetic://c4"]
+    if impl == "ours":
+        ov += [f"kernels.attention={args.attention}"]
+    else:   # reference-equivalent stock path
+        ov += ["kernels.gemm=torch", "kernels.attention=torch", "kernels.norm=torch", "kernels.loss=torch", "kernels.optimizer=torch"]
+    return ov
+
+
+def fed_cfg(args, impl: str, steps: int, n_clients: int, microbatch):
     from photon_b200.config import compose
 
-    ov = [f"llm_config={model}", "run_uuid=bench", f"fl.n_total_clients={N_CLIENTS}", f"fl.n_clients_per_round={N_CLIENTS}",
-          "fl.strategy_name=NESTOROV", "fl.strategy_kwargs.server_learning_rate=1.0", "fl.strategy_kwargs.server_momentum=0.0",
-          "fl.reset_optimizer=false", "fl.eval_period=null", f"llm_config.global_train_batch_size={LOCAL_BATCH}",
-          f"llm_config.device_train_microbatch_size={microbatch}", f"llm_config.local_steps={steps}ba",
-          "llm_config.max_duration=40960ba", "llm_config.scheduler.schedulers.lr.t_max=40960ba",
-          "llm_config.scheduler.schedulers.lr.t_warmup=800ba", "llm_config.precision=amp_bf16", "llm_config.log_to_console=false",
-          "~llm_config.loggers.wandb", "~llm_config.loggers.tensorboard", "llm_config.save_folder=null", "llm_config.save_interval=1000000ba",
-          "llm_config.eval_interval=1000000ba", "~llm_config.callbacks", "photon.checkpoint=false", "photon.comm_stack.shm=false",
-          "dataset.train.root_local=synthetic://c4", "dataset.val.root_local=synthetic://c4"]
-    if server == "fedadam":   # BASELINE config #4 flavour
+    ov = _common_overrides(args, impl) + [
+        f"fl.n_total_clients={n_clients}", f"fl.n_clients_per_round={n_clients}", "fl.strategy_name=NESTOROV",
+        "fl.strategy_kwargs.server_learning_rate=1.0", "fl.strategy_kwargs.server_momentum=0.0", "fl.reset_optimizer=false",
+        "fl.eval_period=null", f"llm_config.global_train_batch_size={LOCAL_BATCH}", f"llm_config.device_train_microbatch_size={microbatch}",
+        f"llm_config.local_steps={steps}ba", "llm_config.max_duration=40960ba", "llm_config.scheduler.schedulers.lr.t_max=40960ba",
+        "llm_config.scheduler.schedulers.lr.t_warmup=800ba", "photon.comm_stack.shm=false"]
+    if args.mode == "fed4x2":
+        ov += ["~llm_config.fsdp_config"]      # plain DDP inside the client (the launch scripts' choice, ref: cen_125m_example.sh:87)
+    if args.server == "fedadam":   # BASELINE config #4 flavour
         ov += ["fl.strategy_name=fedadam", "fl.strategy_kwargs={eta: 0.1, beta_1: 0.9, beta_2: 0.95, tau: 1.0e-9}", "fl.reset_optimizer=true"]
-    if impl == "ours":
-        ov += ["photon.comm_stack.nvl=true", f"kernels.attention={attention}"]
-    else:  # reference-equivalent stock path: torch ops + SDPA/FA2 attention + host shm round
-        ov += ["photon.comm_stack.shm=true", "kernels.gemm=torch", "kernels.attention=torch", "kernels.norm=torch",
-               "kernels.loss=torch", "kernels.optimizer=torch", "llm_config.device_train_microbatch_size=8"]
+    ov += ["photon.comm_stack.nvl=true"] if impl == "ours" else ["photon.comm_stack.shm=true"]
     return compose(ov)
+
+
+def ddp_cfg(args, impl: str, microbatch):
+    from photon_b200.config import compose
+
+    ov = _common_overrides(args, impl) + [
+        f"llm_config.global_train_batch_size={DDP_GLOBAL_BATCH}", f"llm_config.device_train_microbatch_size={microbatch}",
+        "llm_config.scheduler.schedulers.lr.name=constant_with_sqrt_cooldown_with_warmup", "llm_config.scheduler.schedulers.lr.t_warmup=100ba",
+        "++llm_config.scheduler.schedulers.lr.t_cooldown=240ba", "llm_config.scheduler.schedulers.lr.t_max=5120ba",
+        "llm_config.max_duration=5120ba", "~llm_config.algorithms.gradient_clipping", "~llm_config.fsdp_config",
+        "llm_config.optimizer={name: decoupled_adamw, lr: 6.0e-4, betas: [0.9, 0.95], eps: 1.0e-8, weight_decay: 0.0}",
+        "dataset/streams@dataset.train.streams=centralised", "centralized.store_init_model=false", "centralized.store_final_model=false"]
+    return compose(ov)
+
+
+# ------------------------------------------------------------------------------------------------------------------ arms
+class Env:
+    """Process-wide state shared by the arms of one invocation."""
+
+    def __init__(self, args) -> None:
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torchrun --nproc-per-node {args.gpus}")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py measures the sm_100a engine: it needs a CUDA (B200) device and does not fall back to the CPU")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.dev)
+        from photon_b200.utils.hw import L2_BYTES
+
+        self.flush = torch.empty(max(2 * L2_BYTES, 1 << 28), dtype=torch.uint8, device=self.dev)
+
+    def sync(self) -> None:
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, vals: list[float]) -> tuple[list[float], list[float]]:
+        """(max over ranks, min over ranks) of each value."""
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        lo = t.clone()
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN)
+        return [float(x) for x in t.tolist()], [float(x) for x in lo.tolist()]
+
+    def timed(self, fn):
+        """(device ms, result) of ``fn`` bracketed by barrier + synchronize on both sides, L2 flushed before."""
+        torch = self.torch
+        self.flush.zero_()
+        self.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.sync()
+        return e0.elapsed_time(e1), out
+
+    def walled(self, fn):
+        self.flush.zero_()
+        self.sync()
+        t0 = time.perf_counter()
+        out = fn()
+        self.sync()
+        return time.perf_counter() - t0, out
+
+
+def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
+    """Configs #2 / #4 / #5: one federated round of K local steps per client + the round exchange."""
+    torch = env.torch
+    from photon_b200 import ops
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server.broadcast_utils import broadcast_parameters_to_nodes
+    from photon_b200.utils.hw import NVLINK_PEER_GBS, measured_peaks
+
+    gpc = 2 if args.mode == "fed4x2" else 1
+    n_clients = 4 if args.mode == "fed4x2" else N_CLIENTS
+    if env.world % gpc or n_clients % (env.world // gpc):
+        raise SystemExit(f"--mode {args.mode}: --gpus must be a multiple of {gpc} dividing {n_clients * gpc}")
+    default_mb = LOCAL_BATCH // gpc if args.model == "mpt-125m" else 8
+    mb = args.microbatch or (default_mb if impl == "ours" else "auto")
+    rt = FederationRuntime(fed_cfg(args, impl, W, n_clients, mb), device=env.dev, rank=env.rank, world_size=env.world, gpus_per_client=gpc)
+    rt.build()
+    broadcast_parameters_to_nodes(rt, rt.initial_parameters())
+    sampled = list(range(n_clients))
+
+    def one_round(server_round: int) -> list:
+        res = rt.run_clients_fit(server_round, sampled)       # K local steps on each of this rank's clients
+        rt.finish_round(server_round)                         # aggregate + server optimizer + broadcast
+        return res
+
+    one_round(1)                                              # warm-up: a W-step round (workspaces, kernels, arena, CUDA graphs)
+    env.sync()
+    rt.cfg["llm_config"]["local_steps"] = f"{K}ba"
+    if impl == "ours":
+        ops.reset_launch_count()
+    clk = ClockSampler(env.local, enabled=(env.rank == 0)).start()
+    dev_ms, res = env.timed(lambda: one_round(2))
+    launches = ops.launch_count() if impl == "ours" else 0
+    failed = [r for r in res if r.status.code != 0]
+    if failed:
+        raise SystemExit(f"bench round had failed clients: {failed[0].status.message}")
+    e2e_s, _ = env.walled(lambda: one_round(3))
+    clk.stop()
+    # the round exchange alone (aggregate + server optimizer + broadcast), device-timed on a freshly filled accumulator
+    rt.round_backend.begin_round()
+    if rt.is_leader:
+        rt.round_backend.add_client(rt.trainer.state.flat.params, 1.0)
+    agg_ms, _ = env.timed(lambda: rt.finish_round(4))
+    (dev_max, e2e_max, agg_max), (dev_min, _, agg_min) = env.reduce([dev_ms, e2e_s, agg_ms])
+    total = rt.layout.total
+    n_srv = {"fedavg": 0, "fedadam": 2}[args.server]
+    if env.world == 1:      # HBM roofline: read the client sum + x (+ moments), write x fp32 + bf16 (+ moments)
+        roof_ms = total * (4 + 4 + 4 + 2 + 8 * n_srv) / measured_peaks()["hbm_bytes_per_s"] * 1e3
+    else:                   # NVLink roofline: (N-1)/N of the fp32 plane in (reduce) and out again (fp32 + bf16 broadcast), per direction
+        roof_ms = total * ((env.world - 1) / env.world) * (4 + 4 + 2) / (NVLINK_PEER_GBS * 1e9) * 1e3
+    mcfg = rt.trainer.model_cfg
+    out = dict(dev_ms=dev_max, dev_ms_min=dev_min, e2e_s=e2e_max, agg_ms=agg_max, agg_ms_min=agg_min, agg_roofline_ms=roof_ms,
+               launches=int(launches), clocks=clk.summary(), tokens=n_clients * K * LOCAL_BATCH * SEQ,
+               flops_per_token=float(mcfg.flops_per_token(SEQ)), optimizer=str(rt.cfg["llm_config"]["optimizer"]["name"]),
+               comm_stack=rt.round_backend.name, microbatch=int(getattr(rt.trainer, "_auto_mb", None) or rt.trainer.microbatch),
+               clients_per_node=n_clients // rt.n_nodes, gpus_per_client=gpc, n_clients=n_clients,
+               h2d=(n_clients // rt.n_nodes) * (LOCAL_BATCH // gpc) * SEQ * 8, d2h=(n_clients // rt.n_nodes) * 2 * 8)
+    rt.close()
+    return out
+
+
+def run_ddp(env: Env, args, impl: str, K: int, W: int) -> dict:
+    """Config #3: centralised DDP — K optimizer steps of global batch 256 through ``run_centralised`` / ``Trainer.fit``."""
+    torch = env.torch
+    from photon_b200 import ops
+    from photon_b200.centralised_train import run_centralised
+    from photon_b200.parallel.ddp import NcclPerTensorGradComm
+    from photon_b200.utils.hw import NVLINK_PEER_GBS
+
+    if DDP_GLOBAL_BATCH % env.world:
+        raise SystemExit("--gpus must divide 256")
+    per_gpu = DDP_GLOBAL_BATCH // env.world
+    mb = args.microbatch or (min(LOCAL_BATCH, per_gpu) if impl == "ours" else "auto")
+    cfg = ddp_cfg(args, impl, mb)
+    kw = {}
+    if impl != "ours" and env.world > 1:
+        kw["grad_comm"] = NcclPerTensorGradComm()     # the reference's FORCED_SYNC: one NCCL all-reduce per parameter tensor
+    tr = run_centralised(cfg, device=env.dev, rank=env.rank, world_size=env.world, duration=f"{W}ba", **kw)
+    env.sync()
+    if impl == "ours":
+        ops.reset_launch_count()
+    clk = ClockSampler(env.local, enabled=(env.rank == 0)).start()
+    dev_ms, _ = env.timed(lambda: tr.fit(duration=f"{K}ba"))
+    launches = ops.launch_count() if impl == "ours" else 0
+    e2e_s, _ = env.walled(lambda: tr.fit(duration=f"{K}ba"))
+    clk.stop()
+    # the gradient all-reduce alone on the live bucket
+    ar_ms = 0.0
+    if env.world > 1:
+        g = tr.state.flat.grads
+        for _ in range(3):
+            tr._allreduce_grads()  # noqa: SLF001
+        ts = []
+        for _ in range(5):
+            t, _ = env.timed(tr._allreduce_grads)  # noqa: SLF001
+            ts.append(t)
+        ar_ms = sorted(ts)[len(ts) // 2]
+        g.zero_()
+    (dev_max, e2e_max, ar_max), (dev_min, _, _) = env.reduce([dev_ms, e2e_s, ar_ms])
+    total = tr.state.flat.layout.total
+    roof_ms = total * 4 * 2 * ((env.world - 1) / env.world) / (NVLINK_PEER_GBS * 1e9) * 1e3 if env.world > 1 else 0.0
+    out = dict(dev_ms=dev_max, dev_ms_min=dev_min, e2e_s=e2e_max, agg_ms=ar_max, agg_ms_min=ar_max, agg_roofline_ms=roof_ms, launches=int(launches),
+               clocks=clk.summary(), tokens=K * DDP_GLOBAL_BATCH * SEQ, flops_per_token=float(tr.model_cfg.flops_per_token(SEQ)),
+               optimizer="decoupled_adamw", comm_stack=type(tr.grad_comm).__name__ if tr.grad_comm is not None else "none",
+               microbatch=int(getattr(tr, "_auto_mb", None) or tr.microbatch), clients_per_node=1, gpus_per_client=env.world, n_clients=1,
+               h2d=per_gpu * SEQ * 8, d2h=2 * 8)
+    gc_ = tr.grad_comm
+    tr.close()
+    if gc_ is not None:
+        gc_.close()
+    return out
 
 
 def main() -> None:
@@ -129,136 +322,76 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch"])
+    ap.add_argument("--mode", default="fed", choices=["fed", "ddp", "fed4x2"])
     ap.add_argument("--model", default="mpt-125m")
+    ap.add_argument("--precision", default="amp_bf16", choices=["amp_bf16", "amp_fp8"])
     ap.add_argument("--attention", default="b200", choices=["b200", "torch"])
-    ap.add_argument("--microbatch", type=int, default=0, help="device microbatch (0 = 32 for mpt-125m, 8 otherwise)")
+    ap.add_argument("--microbatch", type=int, default=0, help="device microbatch (0 = 32 for mpt-125m, 8 otherwise; torch arm: auto)")
     ap.add_argument("--server", default="fedavg", choices=["fedavg", "fedadam"])
+    ap.add_argument("--torch-arm", default="auto", choices=["auto", "on", "off"],
+                    help="also measure the reference-equivalent stock-PyTorch arm in this invocation (auto = yes for mpt-125m)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm()
         return
-
-    import torch
-    import torch.distributed as dist
-
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
-    if N_CLIENTS % world:
-        raise SystemExit("--gpus must divide 8")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py measures the sm_100a engine: it needs a CUDA (B200) device and does not fall back to the CPU")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-
-    from photon_b200 import ops
-    from photon_b200.federation import FederationRuntime
-    from photon_b200.server.broadcast_utils import broadcast_parameters_to_nodes
-    from photon_b200.utils.hw import L2_BYTES, measured_peaks
+    env = Env(args)
+    from photon_b200.utils.hw import measured_peaks
 
     K, W = args.steps, max(args.warmup, 3)
-    sampled = list(range(N_CLIENTS))
-
-    def make_runtime(local_steps: int) -> FederationRuntime:
-        mb = args.microbatch or (LOCAL_BATCH if args.model == "mpt-125m" else 8)
-        rt = FederationRuntime(build_cfg(args.impl, local_steps, args.model, args.attention, mb, args.server), device=dev, rank=rank, world_size=world)
-        rt.build()
-        broadcast_parameters_to_nodes(rt, rt.initial_parameters())
-        return rt
-
-    def sync() -> None:
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def one_round(rt: FederationRuntime, server_round: int) -> list:
-        res = rt.run_clients_fit(server_round, sampled)       # K local steps on each of this rank's clients
-        rt.finish_round(server_round)                         # fused aggregate + server-opt + broadcast
-        return res
-
-    # ---- warm-up: a W-step round (also allocates workspaces, loads kernels, opens the arena)
-    rt = make_runtime(W)
-    one_round(rt, 1)
-    sync()
-    rt.cfg["llm_config"]["local_steps"] = f"{K}ba"
-    flush = torch.empty(max(2 * L2_BYTES, 1 << 28), dtype=torch.uint8, device=dev)
-
-    tokens = N_CLIENTS * K * LOCAL_BATCH * SEQ
-    # ---- (1) device-timed round
-    flush.zero_()
-    sync()
-    if args.impl == "ours":
-        ops.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local, enabled=(rank == 0)).start()
-    sync()
-    clk.mark()
-    ev0.record()
-    res = one_round(rt, 2)
-    ev1.record()
-    sync()
-    dev_ms = ev0.elapsed_time(ev1)
-    launches = ops.launch_count() if args.impl == "ours" else 0
-    failed = [r for r in res if r.status.code != 0]
-    if failed:
-        raise SystemExit(f"bench round had failed clients: {failed[0].status.message}")
-    # ---- (2) end-to-end wall clock through the same public API
-    flush.zero_()
-    sync()
-    t0 = time.perf_counter()
-    one_round(rt, 3)
-    sync()
-    e2e_s = time.perf_counter() - t0
-    clk.stop()   # sampled across both timed rounds
-    # ---- (3) aggregate + broadcast alone (round hot path), device-timed
-    rt.round_backend.begin_round()
-    rt.round_backend.add_client(rt.trainer.state.flat.params, 1.0)
-    sync()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    rt.finish_round(4)
-    a1.record()
-    sync()
-    agg_ms = a0.elapsed_time(a1)
-
-    t = torch.tensor([dev_ms, e2e_s, agg_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, agg_ms = (float(x) for x in t.tolist())
-    if rank == 0:
-        clients_per_gpu = N_CLIENTS // world
-        h2d = clients_per_gpu * LOCAL_BATCH * SEQ * 8            # int64 token ids per step per GPU
-        d2h = clients_per_gpu * 2 * 8                            # (loss_sum, n_tokens) float64 scalars
-        value = tokens / (dev_ms / 1e3)
-        mcfg = rt.trainer.model_cfg
+    run = run_ddp if args.mode == "ddp" else run_fed
+    r = run(env, args, args.impl, K, W)
+    torch_arm = None
+    want_torch = args.impl == "ours" and (args.torch_arm == "on" or (args.torch_arm == "auto" and args.model == "mpt-125m"))
+    if want_torch:
+        gc.collect()
+        env.torch.cuda.empty_cache()
+        try:
+            t = run(env, args, "torch", K, W)
+            torch_arm = {"value": t["tokens"] / (t["dev_ms"] / 1e3), "ms_per_step": t["dev_ms"] / K, "e2e_value": t["tokens"] / t["e2e_s"],
+                         "exchange_ms": t["agg_ms"], "microbatch": t["microbatch"], "comm_stack": t["comm_stack"],
+                         "what": "stock PyTorch ops (cuBLAS, SDPA, ATen, torch optimizer) + the reference's communication pattern, same K and batch"}
+        except Exception as e:  # noqa: BLE001 - the stand-in arm must never take the headline down
+            torch_arm = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if env.rank == 0:
+        world = env.world
+        value = r["tokens"] / (r["dev_ms"] / 1e3)
         peak = measured_peaks()
+        model = MODEL_NAMES.get(args.model, args.model)
+        metric = {"fed": f"tokens/sec (whole box, device-timed, max over ranks) {model} 8-client fed round",
+                  "ddp": f"tokens/sec (whole box, device-timed, max over ranks) {model} centralised_train DDP global batch 256",
+                  "fed4x2": f"tokens/sec (whole box, device-timed, max over ranks) {model} 4 clients x 2 GPUs fed round"}[args.mode]
+        par = {"fed": f"fed{N_CLIENTS}clients_on_{world}gpu", "ddp": f"dp{world}", "fed4x2": f"fed4clients_x_dp2_on_{world}gpu"}[args.mode]
+        exch = "round_aggregate_broadcast_ms" if args.mode != "ddp" else "allreduce_ms"
         out = {
-            "metric": "tokens/sec (whole box, device-timed, max over ranks) "
-                      + {"mpt-125m": "MPT-125M", "mpt-1b": "MPT-1B", "mpt-3b": "MPT-3B", "mpt-7b": "MPT-7B"}.get(args.model, args.model)
-                      + " 8-client fed round",
-            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic C4-shaped tokens, random-init weights", "impl": args.impl,
-            "config": {"model": args.model, "global_batch": N_CLIENTS * LOCAL_BATCH, "seq_len": SEQ,
-                       "parallelism": f"fed{N_CLIENTS}clients_on_{world}gpu", "clients_per_gpu": clients_per_gpu,
-                       "local_steps_per_round": K, "local_batch": LOCAL_BATCH, "optimizer": str(rt.cfg["llm_config"]["optimizer"]["name"]), "server": "fedavg(nesterov lr=1 mu=0)" if args.server == "fedavg" else "fedadam",
-                       "comm_stack": rt.round_backend.name, "attention": args.attention if args.impl == "ours" else "sdpa",
+            "metric": metric, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": r["dev_ms"] / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp8 GEMMs (E4M3/E5M2, fp32 accumulate) + bf16" if args.precision == "amp_fp8" else "bf16",
+            "data": "synthetic C4-shaped tokens, random-init weights", "impl": args.impl,
+            "config": {"model": args.model, "mode": args.mode, "global_batch": DDP_GLOBAL_BATCH if args.mode == "ddp" else r["n_clients"] * LOCAL_BATCH,
+                       "seq_len": SEQ, "parallelism": par, "clients_per_gpu_group": r["clients_per_node"], "gpus_per_client": r["gpus_per_client"],
+                       "local_steps_per_round": K if args.mode != "ddp" else None, "local_batch": LOCAL_BATCH if args.mode != "ddp" else None,
+                       "microbatch": r["microbatch"], "precision": args.precision, "optimizer": r["optimizer"],
+                       "server": None if args.mode == "ddp" else ("fedavg(nesterov lr=1 mu=0)" if args.server == "fedavg" else "fedadam"),
+                       "comm_stack": r["comm_stack"], "attention": args.attention if args.impl == "ours" else "sdpa",
                        "l2_flush": "256 MiB memset before each timed region; per-step activations (~19 GB) exceed L2",
-                       "timed_region": "one full round: K local steps x 8 clients + aggregate + server-opt + broadcast"},
-            "round_aggregate_broadcast_ms": agg_ms,
-            "mfu_of_measured_bf16_peak": value / world * mcfg.flops_per_token(SEQ) / peak["bf16_flops"],
-            "clocks": clk.summary(),
-            "e2e": {"value": tokens / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "FederationRuntime.run_clients_fit + finish_round (wall clock)"},
-            "gpu_launches": int(launches),
+                       "timed_region": "K optimizer steps" if args.mode == "ddp" else "one full round: K local steps x clients + aggregate + server-opt + broadcast"},
+            exch: r["agg_ms"], exch.replace("_ms", "_roofline_ms"): r["agg_roofline_ms"],
+            exch.replace("_ms", "_roofline_fraction"): (r["agg_roofline_ms"] / r["agg_ms"]) if r["agg_ms"] > 0 else None,
+            "rank_dev_ms": {"min": r["dev_ms_min"], "max": r["dev_ms"], "spread_pct": 100.0 * (r["dev_ms"] - r["dev_ms_min"]) / r["dev_ms"]},
+            "mfu_of_measured_bf16_peak": value / world * r["flops_per_token"] / peak["bf16_flops"],
+            "clocks": r["clocks"],
+            "e2e": {"value": r["tokens"] / r["e2e_s"], "unit": "tokens/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "api": "Trainer.fit via run_centralised (wall clock)" if args.mode == "ddp" else "FederationRuntime.run_clients_fit + finish_round (wall clock)"},
+            "gpu_launches": r["launches"],
         }
+        if torch_arm is not None:
+            out["torch_arm"] = torch_arm
+            if "value" in torch_arm:
+                out["vs_torch_arm"] = value / torch_arm["value"]
+                out["e2e_vs_torch_arm"] = out["e2e"]["value"] / torch_arm["e2e_value"]
         print(json.dumps(out))
-    rt.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

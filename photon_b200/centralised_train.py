@@ -67,13 +67,14 @@ def dump_checkpoint_npz(trainer: Trainer, run_uuid: str, out_dir: str | Path = "
 
 
 def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int | None = None, world_size: int | None = None,
-                    duration: str | None = None, use_nvl_allreduce: bool | None = None) -> Trainer:
+                    duration: str | None = None, use_nvl_allreduce: bool | None = None, grad_comm: Any = None) -> Trainer:
+    """``grad_comm``: an explicit gradient communicator (e.g. ``NcclPerTensorGradComm`` for baseline measurements); default =
+    the fused NVLink kernels on a GPU box, one flat NCCL all-reduce otherwise."""
     cc = _centralized_config(cfg)
     device = device or pick_device(int(os.environ.get("LOCAL_RANK", "0")))
     if rank is None or world_size is None:
         rank, world_size = initialize_dist(device)
-    grad_comm = None
-    if world_size > 1:
+    if world_size > 1 and grad_comm is None:
         if use_nvl_allreduce is None:
             use_nvl_allreduce = device.type == "cuda" and not all(
                 (cfg.get("kernels") or {}).get(k, "auto") == "torch" for k in ("gemm", "optimizer"))

@@ -174,6 +174,9 @@ def get_trainer_object(cfg: Any, cid: int | str | None, *, log_name: str = "", d
                  run_name=str(t["run_name"]), use_unigram_metrics=uni is not None, unigram_log_probs=uni,
                  frozen_layers=frozen_layers, unfrozen_layers=unfrozen_layers, backend=backend,
                  shard_optimizer_state=shard_state,
+                 # host read-back of the loss: every `metric_sync_interval` batches (default: whenever the console logs) — between
+                 # two reads the step path has no host synchronisation at all
+                 metric_sync_interval=int(t.get("metric_sync_interval") or max(1, Time.parse(interval).to_batches())),
                  activation_checkpointing=bool(fsdp) and bool(dict(fsdp).get("activation_checkpointing", False)))
     tr.icl_suite = build_icl_suite(cfg, mcfg.max_seq_len)
     return tr, t

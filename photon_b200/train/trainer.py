@@ -171,6 +171,8 @@ class Trainer:
                                       params_storage=getattr(grad_comm, "params", None),
                                       shadow_storage=getattr(grad_comm, "shadow", None),
                                       activation_checkpointing=activation_checkpointing)
+        if hasattr(grad_comm, "bind_layout"):
+            grad_comm.bind_layout(be.flat.layout)
         shadow = getattr(be, "bf16_params", None)
         use_kernel = (kernels or {}).get("optimizer", "auto") != "torch" and self.device.type == "cuda"
         shard_kw: dict[str, Any] = {}
