@@ -419,11 +419,14 @@ Tensor tensor_from_ptr(int64_t ptr, int64_t numel, const std::string& dtype, int
   return torch::from_blob(reinterpret_cast<void*>(ptr), {numel}, [](void*) {}, opts);
 }
 
+std::atomic<long long> g_comm_timeout_ms{120000};   // bound on every cross-GPU spin inside the NVLink kernels (0 = forever)
+
 pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
   TORCH_CHECK(ctl_ptrs.size() >= 1 && ctl_ptrs.size() <= pb::MAX_PEERS, "1..8 peers supported");
   pb::CommCtl c{};
   c.n = int(ctl_ptrs.size());
   c.rank = rank;
+  c.timeout_ns = static_cast<unsigned long long>(g_comm_timeout_ms.load()) * 1000000ull;
   for (int i = 0; i < c.n; ++i) c.ctl[i] = reinterpret_cast<uint32_t*>(ctl_ptrs[i]);
   return c;
 }
@@ -431,7 +434,7 @@ pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
 void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& acc_ptrs,
                const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi, int64_t total,
                int kind, double avg_scale, double lr, double mu, double eta, double beta1, double beta2, double tau, int64_t round_t,
-               bool sign_compat, int64_t acc_mc, int64_t xg_mc) {
+               bool sign_compat, int64_t acc_mc, int64_t xg_mc, const c10::optional<Tensor>& seg_bounds, c10::optional<Tensor> seg_sums) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::CommCtl c = make_ctl(ctl_ptrs, rank);
   pb::FedRoundArgs a{};
@@ -451,6 +454,15 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
   a.sign = sign_compat ? 1.0f : -1.0f;
   a.acc_mc = reinterpret_cast<const float*>(acc_mc);   // NVLS multicast addresses (0 = P2P loops)
   a.xg_mc = reinterpret_cast<float*>(xg_mc);
+  if (seg_bounds.has_value() && seg_sums.has_value()) {
+    TORCH_CHECK(seg_bounds->is_cuda() && seg_bounds->scalar_type() == at::kLong && seg_bounds->is_contiguous() && seg_bounds->numel() >= 2,
+                "seg_bounds must be a contiguous int64 device tensor with n_seg + 1 entries");
+    a.n_seg = int(seg_bounds->numel()) - 1;
+    TORCH_CHECK(seg_sums->is_cuda() && seg_sums->scalar_type() == at::kDouble && seg_sums->is_contiguous() && seg_sums->numel() == 5 * a.n_seg,
+                "seg_sums must be a contiguous float64 device tensor [5, n_seg]");
+    a.seg_bounds = reinterpret_cast<const long long*>(seg_bounds->data_ptr<int64_t>());
+    a.seg_sums = seg_sums->data_ptr<double>();
+  }
   pb::fed_round_launch(a, c, uint32_t(epoch), at::cuda::getCurrentDeviceProperties()->multiProcessorCount,
                        at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += 1;
@@ -545,7 +557,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fed_round", &fed_round, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("acc_ptrs"),
         py::arg("xg_ptrs"), py::arg("xs_ptrs"), py::arg("m_ptr"), py::arg("v_ptr"), py::arg("lo"), py::arg("hi"), py::arg("total"),
         py::arg("kind"), py::arg("avg_scale"), py::arg("lr"), py::arg("mu"), py::arg("eta"), py::arg("beta1"), py::arg("beta2"),
-        py::arg("tau"), py::arg("round_t"), py::arg("sign_compat"), py::arg("acc_mc") = 0, py::arg("xg_mc") = 0);
+        py::arg("tau"), py::arg("round_t"), py::arg("sign_compat"), py::arg("acc_mc") = 0, py::arg("xg_mc") = 0,
+        py::arg("seg_bounds") = py::none(), py::arg("seg_sums") = py::none());
+  m.def("set_comm_timeout_ms", [](long long ms) { g_comm_timeout_ms = ms < 0 ? 0 : ms; });
+  m.def("comm_timeout_ms", []() { return g_comm_timeout_ms.load(); });
+  m.def("ctl_status_word_offset", &pb::ctl_status_word_offset);
   m.def("ddp_allreduce", &ddp_allreduce, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("buf_ptrs"),
         py::arg("lo"), py::arg("hi"), py::arg("out_norm") = py::none(), py::arg("buf_mc") = 0);
   m.def("ddp_zero_step", &ddp_zero_step, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("grad_ptrs"),

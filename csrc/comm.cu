@@ -36,30 +36,60 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   [0,8)   start flags (slot r written by rank r)      [8,16)  end flags
 //   [16]    local "go" flag (block 0 -> other blocks)   [17]    local done-block counter   [24,32) mid-kernel flags
 //   [32,34) float wsum (this rank's sum of client weights)   [64..) double sq_parts[8], double sums[8]
-constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_GO2 = 18, CP_MID = 24, CP_WSUM = 32, CP_SQPARTS = 64, CP_SUMS = 96;
+constexpr int CP_START = 0, CP_END = 8, CP_GO = 16, CP_DONE = 17, CP_GO2 = 18, CP_ABORT = 19, CP_STATUS = 20, CP_MID = 24, CP_WSUM = 32,
+              CP_SQPARTS = 64, CP_SUMS = 96;
 
-__device__ __forceinline__ void grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= epoch; false when `timeout_ns` (0 = wait forever) expires first
+__device__ __forceinline__ bool wait_flag_sys(const uint32_t* flag, uint32_t epoch, unsigned long long timeout_ns) {
+  if (ld_acquire_sys(flag) >= epoch) return true;
+  const unsigned long long t0 = now_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < epoch) {
+    if (timeout_ns && (++spins & 1023u) == 0 && now_ns() - t0 > timeout_ns) return false;
+  }
+  return true;
+}
+
+// Start-of-kernel rendezvous of all ranks. Returns false on EVERY block of this rank when a peer did not show up within
+// c.timeout_ns: nothing has been touched yet, the kernel returns immediately (a clean abort), the missing peers are
+// recorded as a sticky bit mask in this rank's control page (CP_STATUS) for the host watchdog, and CP_ABORT holds the epoch.
+// A dead rank therefore turns into an aborted round on the survivors instead of an endless spin.
+__device__ __forceinline__ bool grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
   uint32_t* mine = c.ctl[c.rank];
+  __shared__ uint32_t s_abort;
   if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
     if (threadIdx.x < c.n) {
       st_release_sys(c.ctl[threadIdx.x] + CP_START + c.rank, epoch);                 // tell peer t "rank is here"
-      while (ld_acquire_sys(mine + CP_START + threadIdx.x) < epoch) {                 // wait for peer t
+      if (!wait_flag_sys(mine + CP_START + threadIdx.x, epoch, c.timeout_ns)) {       // wait for peer t
+        atomicOr(mine + CP_STATUS, 1u << threadIdx.x);
+        atomicOr(&s_abort, 1u);
       }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (s_abort) mine[CP_ABORT] = epoch;
       __threadfence();
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mine + CP_GO), "r"(epoch) : "memory");
     }
-  } else {
-    if (threadIdx.x == 0) {
-      uint32_t v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + CP_GO) : "memory");
-      } while (v < epoch);
-    }
     __syncthreads();
+    return s_abort == 0;
   }
+  if (threadIdx.x == 0) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + CP_GO) : "memory");
+    } while (v < epoch);
+    s_abort = (*reinterpret_cast<volatile uint32_t*>(mine + CP_ABORT) == epoch) ? 1u : 0u;
+  }
+  __syncthreads();
+  return s_abort == 0;
 }
 
 // returns true in the LAST block to finish (after all blocks' peer stores were fenced)
@@ -81,15 +111,23 @@ __device__ __forceinline__ void peer_barrier_end(const CommCtl& c, uint32_t epoc
   __threadfence_system();
   if (threadIdx.x < c.n) {
     st_release_sys(c.ctl[threadIdx.x] + CP_END + c.rank, epoch);
-    while (ld_acquire_sys(mine + CP_END + threadIdx.x) < epoch) {
-    }
+    // a peer that vanished INSIDE the kernel cannot be waited for: record it (bit 8+t = "left mid-kernel") and leave
+    if (!wait_flag_sys(mine + CP_END + threadIdx.x, epoch, c.timeout_ns)) atomicOr(mine + CP_STATUS, 0x100u << threadIdx.x);
   }
   __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------ R1 + R2
+// Work decomposition: the shard is cut into UNITS of 256 floats (64 float4 = two coalesced 512-byte warp accesses); every
+// warp owns a CONTIGUOUS run of units. Tensor boundaries of the flat layout are multiples of 256 floats, so a unit never
+// straddles two tensors and a warp walks the tensor table monotonically: the five squared-norm partials (pseudo-gradient,
+// fedavg result, new model, momentum, second momentum) are kept per tensor in registers and flushed with one warp reduction
+// + five fp64 atomics when the warp crosses into the next tensor — the reference's `server/layer/{i}/l2_norm_*` metrics
+// (ref: photon/strategy/fedadam.py:333-381) come out of the same single pass as the update itself.
+constexpr int UNIT4 = 64;   // float4 per unit
+
 __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, const CommCtl c, const uint32_t epoch) {
-  grid_peer_barrier_start(c, epoch);
+  if (!grid_peer_barrier_start(c, epoch)) return;
 
   // total client weight = sum over ranks (each rank published its own before the launch)
   float wtot = 0.f;
@@ -97,27 +135,32 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
   const bool skip = !(wtot > 0.f);  // no successful client anywhere -> keep the model (ignore_failed_rounds)
   const float inv = skip ? 0.f : a.avg_scale / wtot;
 
-  float s_pg = 0.f, s_a = 0.f, s_x = 0.f, s_m = 0.f, s_v = 0.f;
-  const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
-  // one element (float4) of the shard: pseudo-gradient, server optimizer, norm partials, broadcast
-  auto process = [&](long long i, float4 acc) {
+  const int lane = threadIdx.x & 31;
+  float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // Σpg², Σa², Σx², Σm², Σv² of the tensor the warp is in
+  __nv_bfloat16* xs_mine = reinterpret_cast<__nv_bfloat16*>(a.xs[c.rank]);
+  const bool local_only = (c.n == 1);
+
+  auto load_acc = [&](long long i) -> float4 {
+    if (local_only) return __ldcs(reinterpret_cast<const float4*>(a.acc[0]) + i);     // plain streaming load: nobody else wrote it
+    if (a.acc_mc) return mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + i);   // NVLS: the switch adds the N planes
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
+      const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
+      acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+    }
+    return acc;
+  };
+  // one float4 of the shard: pseudo-gradient, server optimizer, norm partials, broadcast (fp32 to all, bf16 locally)
+  auto process = [&](long long i, float4 acc, float4 X, float4 Mv, float4 Vv) {
       float av[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
-      const float4 X = reinterpret_cast<const float4*>(a.x)[i];
       float xv[4] = {X.x, X.y, X.z, X.w};
-      float mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
-      if (a.kind >= 1) {
-        const float4 Mv = reinterpret_cast<const float4*>(a.m)[i];
-        mv[0] = Mv.x, mv[1] = Mv.y, mv[2] = Mv.z, mv[3] = Mv.w;
-      }
-      if (a.kind >= 3) {
-        const float4 Vv = reinterpret_cast<const float4*>(a.v)[i];
-        vv[0] = Vv.x, vv[1] = Vv.y, vv[2] = Vv.z, vv[3] = Vv.w;
-      }
+      float mv[4] = {Mv.x, Mv.y, Mv.z, Mv.w}, vv[4] = {Vv.x, Vv.y, Vv.z, Vv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float pg = xv[k] - av[k];
-        s_pg += pg * pg;
-        s_a += av[k] * av[k];
+        s5[0] += pg * pg;
+        s5[1] += av[k] * av[k];
         switch (a.kind) {
           case 0:  // FedAvg
             xv[k] -= a.lr * pg;
@@ -146,69 +189,85 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
             break;
           }
         }
-        s_x += xv[k] * xv[k];
-        s_m += mv[k] * mv[k];
-        s_v += vv[k] * vv[k];
+        s5[2] += xv[k] * xv[k];
+        s5[3] += mv[k] * mv[k];
+        s5[4] += vv[k] * vv[k];
       }
       if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
       if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
       // R2 (a): push the updated fp32 slice into every rank's global plane over NVLink
       const float4 nx = make_float4(xv[0], xv[1], xv[2], xv[3]);
-      if (a.xg_mc) {    // NVLS: one multicast store lands in every rank's global plane
+      if (local_only) {
+        reinterpret_cast<float4*>(a.xg[0])[i] = nx;
+      } else if (a.xg_mc) {    // NVLS: one multicast store lands in every rank's global plane
         mm_st_f4(reinterpret_cast<float4*>(a.xg_mc) + i, nx);
       } else {
 #pragma unroll 1
         for (int p = 0; p < c.n; ++p) st_peer_f4(reinterpret_cast<float4*>(a.xg[p]) + i, nx);
       }
+      // R2 (b) for the OWN shard: the bf16 compute copy straight from registers (no second pass over this slice)
+      if (xs_mine) {
+        uint2 o;
+        o.x = pack_bf16(xv[0], xv[1]), o.y = pack_bf16(xv[2], xv[3]);
+        reinterpret_cast<uint2*>(xs_mine)[i] = o;
+      }
   };
-  const long long gs = (long long)gridDim.x * blockDim.x;
-  const long long i0 = lo4 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (!skip && a.acc_mc) {
-    // NVLS: the switch adds the N weighted client sums (one multimem.ld_reduce per element). The round trip through the
-    // switch is long, so four reductions per thread are kept in flight ahead of the arithmetic.
-    float4 pre[4];
+  int seg = 0;
+  auto flush = [&]() {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (i0 + u * gs < hi4) pre[u] = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + i0 + u * gs);
-    for (long long i = i0; i < hi4; i += 4 * gs) {
+    for (int j = 0; j < 5; ++j) {
+      const float t = warp_sum(s5[j]);
+      if (lane == 0 && t != 0.f && a.seg_sums) atomicAdd(a.seg_sums + (long long)j * a.n_seg + seg, double(t));
+      s5[j] = 0.f;
+    }
+  };
+  if (!skip) {
+    const long long u_lo = a.lo / (4 * UNIT4), u_hi = (a.hi + 4 * UNIT4 - 1) / (4 * UNIT4);   // shard bounds are unit-aligned
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long per = (u_hi - u_lo + n_warps - 1) / n_warps;
+    const long long ub = u_lo + gw * per, ue = (ub + per < u_hi) ? ub + per : u_hi;
+    const long long hi4 = a.hi / 4;
+    if (ub < ue && a.seg_bounds) {   // binary search: first tensor whose end is beyond this warp's first unit
+      int l = 0, r = a.n_seg - 1;
+      while (l < r) {
+        const int mid = (l + r) >> 1;
+        if (a.seg_bounds[mid + 1] > ub) r = mid;
+        else l = mid + 1;
+      }
+      seg = l;
+    }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long u = ub; u < ue; u += 2) {   // two units per trip: four 16-byte loads per plane per thread in flight
+      float4 A[4], X[4], M[4], V[4];
+      long long idx[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long idx = i + u * gs;
-        if (idx < hi4) {
-          const float4 acc = pre[u];
-          if (idx + 4 * gs < hi4) pre[u] = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.acc_mc) + idx + 4 * gs);
-          process(idx, acc);
+      for (int k = 0; k < 4; ++k) {
+        idx[k] = (u + (k >> 1)) * UNIT4 + (k & 1) * 32 + lane;
+        const bool ok = (u + (k >> 1)) < ue && idx[k] < hi4;
+        if (!ok) idx[k] = -1;
+        A[k] = ok ? load_acc(idx[k]) : z4;
+        X[k] = ok ? reinterpret_cast<const float4*>(a.x)[idx[k]] : z4;
+        M[k] = (ok && a.kind >= 1) ? reinterpret_cast<const float4*>(a.m)[idx[k]] : z4;
+        V[k] = (ok && a.kind >= 3) ? reinterpret_cast<const float4*>(a.v)[idx[k]] : z4;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((k & 1) == 0 && a.seg_bounds && (u + (k >> 1)) < ue) {   // entering a unit: did the warp cross into the next tensor?
+          const long long unit = u + (k >> 1);
+          if (unit >= a.seg_bounds[seg + 1]) {
+            flush();
+            while (seg + 1 < a.n_seg && unit >= a.seg_bounds[seg + 1]) ++seg;
+          }
         }
+        if (idx[k] >= 0) process(idx[k], A[k], X[k], M[k], V[k]);
       }
     }
-  } else if (!skip) {
-    for (long long i = i0; i < hi4; i += gs) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-      for (int p = 0; p < c.n; ++p) {  // fixed order -> bitwise reproducible across runs
-        const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.acc[p]) + i);
-        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
-      }
-      process(i, acc);
-    }
-  }
-  // norm by-products (this rank's shard): block reduce -> fp64 atomics in the local control page
-  __shared__ float red[5][16];
-  float vals[5] = {s_pg, s_a, s_x, s_m, s_v};
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    vals[j] = warp_sum(vals[j]);
-    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = vals[j];
-  }
-  __syncthreads();
-  if (threadIdx.x < 5) {
-    float t = 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
-    atomicAdd(reinterpret_cast<double*>(c.ctl[c.rank] + CP_SUMS) + threadIdx.x, double(t));
+    flush();
   }
   // every rank's slice has landed everywhere once the end barrier completes; the last block runs it and then
-  // releases the whole grid into R2 (b): the bf16 compute copy is cast LOCALLY from the received fp32 plane
-  // (halves the NVLink bytes of the broadcast compared with also pushing the bf16 copy to 7 peers)
+  // releases the whole grid into R2 (b) for the slices OWNED BY PEERS: the bf16 compute copy is cast LOCALLY from the received
+  // fp32 plane (halves the NVLink bytes of the broadcast compared with also pushing the bf16 copy to 7 peers)
   uint32_t* mine = c.ctl[c.rank];
   if (grid_done(c)) {
     peer_barrier_end(c, epoch);
@@ -217,8 +276,7 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mine + CP_GO2), "r"(epoch) : "memory");
     }
   }
-  void* xs = a.xs[c.rank];
-  if (xs != nullptr && !skip) {
+  if (xs_mine != nullptr && !skip && !local_only) {
     if (threadIdx.x == 0) {
       uint32_t v;
       do {
@@ -227,18 +285,20 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
     }
     __syncthreads();
     const float4* src = reinterpret_cast<const float4*>(a.xg[c.rank]);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.total / 4; i += (long long)gridDim.x * blockDim.x) {
+    const long long lo4 = a.lo / 4, n_own = a.hi / 4 - lo4, n_rest = a.total / 4 - n_own;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_rest; j += (long long)gridDim.x * blockDim.x) {
+      const long long i = j < lo4 ? j : j + n_own;   // skip the own shard
       const float4 v = ld_peer_f4(src + i);  // written by peers during this launch: bypass the non-coherent path
       uint2 o;
       o.x = pack_bf16(v.x, v.y), o.y = pack_bf16(v.z, v.w);
-      reinterpret_cast<uint2*>(xs)[i] = o;
+      reinterpret_cast<uint2*>(xs_mine)[i] = o;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ N1
 __global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs a, const CommCtl c, const uint32_t epoch) {
-  grid_peer_barrier_start(c, epoch);
+  if (!grid_peer_barrier_start(c, epoch)) return;
   const float inv = 1.0f / c.n;
   float sq = 0.f;
   const long long lo4 = a.lo / 4, hi4 = a.hi / 4;
@@ -289,7 +349,7 @@ __global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs 
 // plane and publishes the shard's squared norm to every rank. Mid barrier. Phase 2: clip coefficient from the global norm,
 // local optimizer on the shard of (p, m, v), new fp32 masters and bf16 casts pushed into every rank's planes.
 __global__ void __launch_bounds__(512) ddp_zero_step_kernel(const ZeroStepArgs a, const CommCtl c, const uint32_t epoch, float* out_norm) {
-  grid_peer_barrier_start(c, epoch);
+  if (!grid_peer_barrier_start(c, epoch)) return;
   uint32_t* mine = c.ctl[c.rank];
   const float inv = a.grad_mult / c.n;
   float sq = 0.f;
@@ -332,8 +392,7 @@ __global__ void __launch_bounds__(512) ddp_zero_step_kernel(const ZeroStepArgs a
     __threadfence_system();
     if (threadIdx.x < c.n) {
       st_release_sys(c.ctl[threadIdx.x] + CP_MID + c.rank, epoch);
-      while (ld_acquire_sys(mine + CP_MID + threadIdx.x) < epoch) {
-      }
+      if (!wait_flag_sys(mine + CP_MID + threadIdx.x, epoch, c.timeout_ns)) atomicOr(mine + CP_STATUS, 0x100u << threadIdx.x);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -413,9 +472,10 @@ __global__ void set_wsum_kernel(uint32_t* ctl, float w, int zero_sums) {
 }  // namespace
 
 int ctl_sums_word_offset() { return CP_SUMS; }
+int ctl_status_word_offset() { return CP_STATUS; }
 
 void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st) {
-  if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("fed_round: shard bounds must be multiples of 4");
+  if ((a.lo % 256) || (a.hi % 4)) throw std::runtime_error("fed_round: the shard must start on a 256-element boundary and end on a multiple of 4");
   fed_round_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("fed_round launch: ") + cudaGetErrorString(e));

@@ -14,6 +14,7 @@ struct CommCtl {
   uint32_t* ctl[MAX_PEERS];  // control page of every rank (peer-mapped)
   int n;
   int rank;
+  unsigned long long timeout_ns;  // bound on every cross-GPU spin (0 = wait forever); see CP_STATUS / CP_ABORT in comm.cu
 };
 
 struct FedRoundArgs {
@@ -31,6 +32,11 @@ struct FedRoundArgs {
   float eta, beta1, beta2, tau, inv_bc1, inv_bc2, sign;  // adam / yogi (sign=-1 descent, +1 reference compat)
   const float* acc_mc;          // NVLS: multicast address of the acc planes (in-switch reduction), or nullptr
   float* xg_mc;                 // NVLS: multicast address of the fp32 global planes (one store reaches every GPU), or nullptr
+  // per-tensor squared-norm by-products: seg_bounds[0..n_seg] = tensor boundaries in units of 256 floats (ascending, the last
+  // entry >= total/256), seg_sums = double[5][n_seg] (pg, fedavg result, model, momentum, second momentum); both may be null
+  const long long* seg_bounds;
+  int n_seg;
+  double* seg_sums;
 };
 
 struct AllReduceArgs {
@@ -61,5 +67,6 @@ void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, i
 void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
 void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st);
 int ctl_sums_word_offset();
+int ctl_status_word_offset();   // sticky word: bit t = peer t missed a start barrier, bit 8+t = peer t vanished mid-kernel
 
 }  // namespace pb

@@ -34,10 +34,17 @@ _KIND = {"fedavg": 0, "nesterov": 1, "fedmom": 2, "fedadam": 3, "fedyogi": 4}
 class NvlFedRound:
     def __init__(self, total: int, strategy: ServerStrategy, *, rank: int = 0, world_size: int = 1,
                  device: torch.device | int | None = None, group: Any = None, devices: list[int] | None = None,
-                 bf16_shadow: bool = True) -> None:
-        if total % 4:
-            raise ValueError("flat length must be a multiple of 4")
+                 bf16_shadow: bool = True, layout: Any = None) -> None:
+        """``layout``: the exchange :class:`FlatLayout` — its tensor boundaries become the kernel's segment table, so the round
+        also yields the per-tensor norms (``server/layer/{i}/l2_norm_*``). Without it the whole plane is one segment."""
+        if total % 256:
+            raise ValueError("flat length must be a multiple of 256 (FlatLayout pads to 4096)")
         self.total, self.strategy = int(total), strategy
+        offs = list(layout.offsets) if layout is not None else [0]
+        if any(o % 256 for o in offs) or (layout is not None and layout.total != total):
+            raise ValueError("layout offsets must be multiples of 256 elements and cover `total`")
+        self.n_seg = len(offs)
+        self._seg_bounds_host = [o // 256 for o in offs] + [total // 256]
         planes = {"acc": (total, torch.float32), "xg": (total, torch.float32)}
         if bf16_shadow:
             planes["xs"] = (total, torch.bfloat16)
@@ -50,9 +57,14 @@ class NvlFedRound:
         # indexing by global element, so it is handed `shard_ptr - lo`
         self._m: list[torch.Tensor | None] = []
         self._v: list[torch.Tensor | None] = []
+        self._seg_bounds: list[torch.Tensor] = []
+        self._seg_sums: list[torch.Tensor] = []
+        self.last_status = 0
         for i in range(self.n_local):
             dev = torch.device("cuda", self.arena.devices[i])
             lo, hi = self.shard_of(i)
+            self._seg_bounds.append(torch.tensor(self._seg_bounds_host, dtype=torch.int64, device=dev))
+            self._seg_sums.append(torch.zeros(5, self.n_seg, dtype=torch.float64, device=dev))
             self._m.append(torch.zeros(hi - lo, device=dev) if strategy.n_moments >= 1 else None)
             self._v.append(torch.zeros(hi - lo, device=dev) if strategy.n_moments >= 2 else None)
 
@@ -116,27 +128,58 @@ class NvlFedRound:
             ext.set_wsum(ar.ctl_ptrs()[rank], dev, self._wsum[i], True)
             launches.append((rank, dev, lo, hi, i))
         for rank, dev, lo, hi, i in launches:
+            self._seg_sums[i].zero_()
             ext.fed_round(ar.ctl_ptrs(), rank, dev, epoch, ar.ptrs("acc"), ar.ptrs("xg"), ar.ptrs("xs") if self.has_shadow else [],
                           self._m[i].data_ptr() - 4 * lo if self._m[i] is not None else 0,
                           self._v[i].data_ptr() - 4 * lo if self._v[i] is not None else 0,
                           lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
                           hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat),
-                          ar.mc_ptr("acc"), ar.mc_ptr("xg"))
+                          ar.mc_ptr("acc"), ar.mc_ptr("xg"), self._seg_bounds[i], self._seg_sums[i])
 
-    def round_norms(self, group: Any = None) -> dict[str, float]:
-        """Global L2 norms from the kernel's per-shard Σx² by-products (tiny host read; off the hot path)."""
-        sums = torch.zeros(5, dtype=torch.float64)
+    def check_status(self) -> int:
+        """Sticky status word of the local control page(s) after the round kernel (one 4-byte read, synchronising): 0 = every
+        peer took part; bit t = peer t never reached the start barrier within the time-out → the kernel ABORTED without
+        touching anything (accumulators, model and moments are as before the launch); bit 8+t = peer t vanished mid-kernel."""
+        off = ops.ext().ctl_status_word_offset()
+        st = 0
         for i in range(self.n_local):
-            sums += self.arena.ctl_sums(self._r(i))[:5].cpu()
+            st |= int(self.arena.ctl_words(self._r(i))[off].item()) & 0xFFFF
+        self.last_status = st
+        return st
+
+    def clear_status(self) -> None:
+        off = ops.ext().ctl_status_word_offset()
+        for i in range(self.n_local):
+            self.arena.ctl_words(self._r(i))[off] = 0
+
+    def segment_sq_sums(self, group: Any = None) -> torch.Tensor:
+        """float64 [5, n_seg] on the host: per-tensor Σpg², Σa², Σx², Σm², Σv² of the last round, summed over all ranks' shards
+        (tiny: off the hot path, called when the metrics are collected)."""
+        sums = torch.zeros(5, self.n_seg, dtype=torch.float64)
+        for i in range(self.n_local):
+            sums += self._seg_sums[i].cpu()
         if not self.arena.single and self.arena.world_size > 1:
             import torch.distributed as dist
 
             t = sums.to(torch.device("cuda", self.arena.devices[0]))
             dist.all_reduce(t, group=group)
             sums = t.cpu()
-        names = ["pseudo_gradient", "fedavg_result", "model", "momentum_vector", "second_momentum_vector"]
-        keep = 3 + self.strategy.n_moments
-        return {f"server/l2_norm_{n}": math.sqrt(max(float(s), 0.0)) for n, s in list(zip(names, sums.tolist()))[:keep]}
+        return sums
+
+    def round_norms(self, group: Any = None, per_layer: bool = True) -> dict[str, float]:
+        """The reference's server norm metrics from the kernel's by-products: ``server/l2_norm_{pseudo_gradient,fedavg_result,
+        model,momentum_vector,second_momentum_vector}`` and, per tensor of the layout, ``server/layer/{i}/l2_norm_*``
+        (ref: photon/strategy/fedadam.py:333-381)."""
+        sums = self.segment_sq_sums(group)
+        names = ["pseudo_gradient", "fedavg_result", "model", "momentum_vector", "second_momentum_vector"][: 3 + self.strategy.n_moments]
+        out: dict[str, float] = {}
+        for j, n in enumerate(names):
+            row = sums[j].tolist()
+            out[f"server/l2_norm_{n}"] = math.sqrt(max(sum(row), 0.0))
+            if per_layer and self.n_seg > 1:
+                for i, q in enumerate(row):
+                    out[f"server/layer/{i}/l2_norm_{n}"] = math.sqrt(max(q, 0.0))
+        return out
 
     def moments(self, local: int = 0) -> tuple[torch.Tensor | None, torch.Tensor | None]:
         """This GPU's slices ``[lo, hi)`` of the server moments (see :meth:`shard_of`)."""

@@ -158,9 +158,10 @@ class SymmArena:
         return self.epoch
 
     def shard(self, total: int, rank: int | None = None) -> tuple[int, int]:
-        """Contiguous [lo,hi) slice of a flat index space owned by ``rank`` (multiples of 4)."""
+        """Contiguous [lo,hi) slice of a flat index space owned by ``rank``; shards start on 256-element boundaries (the
+        unit of the round kernel's per-tensor bookkeeping, and the alignment of every tensor in a FlatLayout)."""
         r = self.rank if rank is None else rank
-        per = _round_up(-(-total // self.world_size), 4)
+        per = _round_up(-(-total // self.world_size), 256)
         lo = min(total, r * per)
         return lo, min(total, lo + per)
 

@@ -357,7 +357,7 @@ class NvlRoundBackend(RoundBackend):
         super().__init__(layout, strategy, device, rank=rank, world_size=world_size, group=group)
         from photon_b200.parallel.fed_round import NvlFedRound
 
-        self.fed = NvlFedRound(layout.total, strategy, rank=rank, world_size=world_size, device=device, group=group)
+        self.fed = NvlFedRound(layout.total, strategy, rank=rank, world_size=world_size, device=device, group=group, layout=layout)
         self.track_norms = track_norms
         if strategy.track_inplace and rank == 0:
             print("[round/nvl] track_inplace_aggregation is a host-transport self-check; the fused kernel never materialises "

@@ -1,4 +1,4 @@
-"""Fused NVLink kernels across >= 2 GPUs (single process, peer access): federated round (all five server
+"""Fused NVLink kernels on 1..8 GPUs (single process, peer access): federated round (all five server
 optimizers) and the DDP all-reduce vs PyTorch references."""
 import math
 
@@ -8,49 +8,77 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs >= {n} GPUs")
+    return n
+
+
 def _need2():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    return min(torch.cuda.device_count(), 4)
+    return _need(2) and min(torch.cuda.device_count(), 4)
 
 
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
 @pytest.mark.parametrize("kind", ["fedavg", "nesterov", "fedmom", "fedadam", "fedyogi"])
-def test_fed_round_multi_gpu_matches_oracle(kind):
-    n = _need2()
+def test_fed_round_matches_oracle(kind, n):
+    """The fused round kernel on n GPUs of one process (n = 1: plain loads, bf16 cast from registers, no second pass)."""
+    _need(n)
     from photon_b200.parallel.fed_round import NvlFedRound
     from photon_b200.strategy.strategies import FedAdam, FedAvgEfficient, FedMom, FedNesterov, FedYogi, server_opt_step
+    from photon_b200.utils.flat import FlatLayout
 
     mk = {"fedavg": lambda: FedAvgEfficient(0.7), "nesterov": lambda: FedNesterov(0.7, 0.9), "fedmom": lambda: FedMom(0.5, 0.8),
-          "fedadam": lambda: FedAdam(tau=5e-2), "fedyogi": lambda: FedYogi()}[kind]
-    # tau: Adam-type steps are eta*pg/(|pg|+tau) in round 1 - a 1-ulp difference in the fp32 mean is amplified by eta/tau near pg = 0
+          "fedadam": lambda: FedAdam(tau=1e-3), "fedyogi": lambda: FedYogi()}[kind]
     strat, ref = mk(), mk()
-    total = 1 << 20
+    # an uneven tensor table (tensors smaller and larger than a shard, one crossing every shard boundary)
+    lay = FlatLayout.build([("a", (300, 1000)), ("b", (7,)), ("c", (513, 512)), ("d", (1 << 18,)), ("e", (1000, 200))])
+    total = lay.total
     torch.manual_seed(0)
-    x0 = torch.randn(total)
-    fed = NvlFedRound(total, strat, devices=list(range(n)))
+    x0 = torch.zeros(total)
+    for i in range(len(lay.names)):
+        lay.view(x0, i).normal_()
+    fed = NvlFedRound(total, strat, devices=list(range(n)), layout=lay)
     fed.set_global(x0)
-    ref.initialize(x0.clone())
+    ref.initialize(x0.clone(), layout=lay)
     for rnd in range(1, 4):
         fed.begin_round()
         clients, weights = [], []
         for g in range(n):
             for c in range(2):  # two multiplexed clients per GPU
-                p = (ref.parameters + 0.05 * torch.randn(total)).contiguous()
+                p = ref.parameters.clone()
+                for i in range(len(lay.names)):
+                    lay.view(p, i).add_(0.05 * torch.randn(lay.shapes[i]))
                 w = float(10 * (g + 1) + c)
                 fed.add_client(p.to(f"cuda:{g}"), w, local=g)
                 clients.append(p), weights.append(w)
         fed.finish_round(rnd)
         for g in range(n):
             torch.cuda.synchronize(g)
-        avg = sum(p.double() * w for p, w in zip(clients, weights)) / sum(weights)
-        server_opt_step(ref.kind, ref.parameters, avg.float(), ref.momentum_vector, ref.second_momentum_vector, ref.hp, rnd)
+        assert fed.check_status() == 0
+        avg = (sum(p.double() * w for p, w in zip(clients, weights)) / sum(weights)).float()
+        x_before = ref.parameters.clone()
+        pg = server_opt_step(ref.kind, ref.parameters, avg, ref.momentum_vector, ref.second_momentum_vector, ref.hp, rnd)
+        # Adam-type steps are eta * m_hat / (sqrt(v_hat) + tau): where |pg| is within a few tau of zero a 1-ulp difference of the fp32
+        # mean moves the step by up to eta/tau ulps. Those elements are compared against that bound, everything else tightly.
+        tight = torch.ones(total, dtype=torch.bool) if kind not in ("fedadam", "fedyogi") else (x_before - avg).abs() > 20 * ref.hp["tau"]
+        assert float(tight.float().mean()) > 0.5
         for g in range(n):  # every GPU must hold the same new global model (fp32 + bf16 cast)
             got = fed.global_params(g).cpu()
-            bad = ((got - ref.parameters).abs() > 2e-5 + 2e-4 * ref.parameters.abs()).float().mean().item()
-            assert bad < 1e-4, (kind, rnd, g, bad, (got - ref.parameters).abs().max())  # adaptive steps amplify 1-ulp pg differences
+            torch.testing.assert_close(got[tight], ref.parameters[tight], rtol=2e-5, atol=2e-6)
+            torch.testing.assert_close(got[~tight], ref.parameters[~tight], rtol=0, atol=ref.hp.get("eta", 0.0) / ref.hp.get("tau", 1.0) * 4e-7 + 1e-6)
             assert torch.equal(fed.global_shadow(g).cpu(), got.to(torch.bfloat16))
+        # server moments (each GPU keeps its shard): stitched they equal the oracle's planes
+        for j, plane in enumerate((ref.momentum_vector, ref.second_momentum_vector)):
+            if plane is None:
+                continue
+            full = sum(fed.full_moments(g)[j].cpu() for g in range(n))
+            torch.testing.assert_close(full, plane, rtol=1e-4, atol=1e-6)
+        # norm by-products of the same pass: global AND per tensor (the reference's server/layer/{i}/... metrics)
+        want = ref.norm_metrics(pg, avg)
         norms = fed.round_norms()
-        assert math.isclose(norms["server/l2_norm_model"], float(ref.parameters.double().norm()), rel_tol=1e-3)
+        assert set(want) == set(norms), sorted(set(want) ^ set(norms))[:5]
+        for k, v in want.items():
+            assert math.isclose(norms[k], v, rel_tol=1e-4, abs_tol=1e-6), (k, norms[k], v)
     fed.close()
 
 
@@ -60,7 +88,7 @@ def test_fed_round_failed_client_and_empty_round():
     from photon_b200.strategy.strategies import FedAvgEfficient
 
     total = 1 << 16
-    fed = NvlFedRound(total, FedAvgEfficient(1.0), devices=list(range(n)))
+    fed = NvlFedRound(total, FedAvgEfficient(1.0), devices=list(range(n)))   # no layout: the whole plane is one segment
     x0 = torch.randn(total)
     fed.set_global(x0)
     fed.begin_round()
