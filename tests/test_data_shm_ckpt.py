@@ -313,3 +313,45 @@ def test_mds_directories_written_for_the_reference_are_readable(tmp_path, compre
                                allow_synthetic=False)
     batches = [b["input_ids"] for b in TokenLoader(ds, batch_size=5, pin_memory=False)]
     assert len(batches) == 5 and torch.equal(batches[0][0], torch.from_numpy(rows[0].astype(np.int64)))
+
+
+import pathlib
+
+FIXTURES = pathlib.Path(__file__).resolve().parent / "fixtures"
+
+
+def test_committed_mds_fixture_opens_and_streams():
+    """A mosaicml-streaming MDS directory (index.json v2 + zstd shards, written by tests/fixtures/make_fixtures.py byte by byte from
+    the format, independently of the reader) is readable as-is: the reference's converted datasets need no re-tokenising
+    (ref: photon/dataset/convert_dataset_hf.py:323-327)."""
+    import numpy as np
+
+    from photon_b200.data.shards import MDSReader, open_shard_dir
+    from photon_b200.data.streaming import Stream, StreamingTokenDataset
+
+    r = open_shard_dir(FIXTURES / "mds_tiny")
+    assert isinstance(r, MDSReader) and len(r) == 12 and r.seq_len == 16
+    want = np.load(FIXTURES / "mds_tiny" / "expected_tokens.npy")
+    for i in range(12):
+        assert r[i].dtype == np.int32 and (r[i] == want[i]).all()
+    ds = StreamingTokenDataset([Stream(local=str(FIXTURES / "mds_tiny"), split=None, name="mds")], seq_len=16, allow_synthetic=False)
+    got = np.stack([np.asarray(x) for _, x in zip(range(12), iter(ds))])
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+
+
+def test_committed_reference_state_bin_loads():
+    """A ``state.bin`` carrying the reference's pickled ``photon.wandb_history.WandbHistory`` (Flower ``History`` subclass) and its
+    five fields loads without flwr: history stores, literal client-state string, counters (ref: photon/server/s3_utils.py:374-389)."""
+    import ast
+
+    from photon_b200.checkpoint.store import load_server_state
+    from photon_b200.wandb_history import History
+
+    st = load_server_state(FIXTURES / "ref_state" / "state.bin")
+    assert st["server_round"] == 2 and st["server_steps_cumulative"] == 256 and abs(st["time_offset"] - 1234.5) < 1e-9
+    h = st["history"]
+    assert isinstance(h, History)
+    assert h.losses_distributed == [(0, 10.83), (1, 9.91), (2, 9.17)]
+    assert h.metrics_distributed_fit["server/n_aggregated_clients"] == [(1, 8), (2, 8)]
+    cs = ast.literal_eval(st["client_state"])
+    assert set(cs) == set(range(8)) and cs[3]["steps_done"] == 128
