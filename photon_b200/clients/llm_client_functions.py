@@ -100,9 +100,7 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
         remaining = max(0, target - st.timestamp.batch)
         if remaining:
             trainer.fit(duration=f"{remaining}ba")
-        steps_done = local_steps
-        if trainer.device.type == "cuda":
-            torch.cuda.synchronize(trainer.device)
+        steps_done = local_steps       # (no device synchronise here: the last batch of fit() read its loss back, which already waited)
     metrics["client/fit_time"] = _now() - t0
 
     t0 = _now()

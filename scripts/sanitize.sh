@@ -1,9 +1,18 @@
 #!/usr/bin/env bash
-# compute-sanitizer passes over the kernel numerics tests at CI-sized shapes.
-# usage (on a GPU box): scripts/sanitize.sh [memcheck|racecheck|synccheck|initcheck]
+# compute-sanitizer passes over the kernel numerics tests at CI-sized shapes: fused ops, GEMM (bf16 + fp8), the fp8
+# producers, attention fwd/bwd, and the NVLink kernels (fed_round / ddp_allreduce / ddp_zero_step run on one GPU with n = 1, plus the
+# single-process multi-GPU tests when the box has peers).
+# usage (on a GPU box): scripts/sanitize.sh [memcheck|racecheck|synccheck|initcheck|all]
 set -uo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."; mkdir -p gpurun_out
-TOOL=${1:-memcheck}
-compute-sanitizer --tool "$TOOL" --error-exitcode 3 --print-limit 20 \
-  python -m pytest tests/test_kernels_gpu.py -x -q -k "layernorm or cross_entropy or embedding or colsum or optimizer or gemm_kk_bias" \
-  2>&1 | tail -40 | tee "gpurun_out/sanitizer_$TOOL.log"
+TOOLS=${1:-memcheck}
+[ "$TOOLS" = all ] && TOOLS="memcheck racecheck synccheck initcheck"
+SEL='layernorm or cross_entropy or embedding or colsum or optimizer or gemm_kk_bias or gemm_fp8_forward or gemm_fp8_wgrad or gelu_epilogue or weight_segments or test_attention_fwd or test_attention_bwd or fed_round_matches_oracle or allreduce'
+rc=0
+for TOOL in $TOOLS; do
+  compute-sanitizer --tool "$TOOL" --error-exitcode 3 --print-limit 20 \
+    python -m pytest tests/test_kernels_gpu.py tests/test_fp8_gpu.py tests/test_attention_gpu.py tests/test_multigpu.py -x -q -k "$SEL" \
+    2>&1 | tail -25 | tee "gpurun_out/sanitizer_$TOOL.log"
+  [ "${PIPESTATUS[0]}" -ne 0 ] && rc=1
+done
+exit $rc

@@ -20,8 +20,8 @@ def _close(got, ref, rtol, atol, what=""):
     got, ref = got.float(), ref.float()
     err = (got - ref).abs()
     tol = atol + rtol * ref.abs()
-    bad = (err > tol).float().mean().item()
-    assert bad < 1e-3, f"{what}: {bad*100:.3f}% elements out of tolerance, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+    bad = int((err > tol).sum().item())     # every element, no "fraction may be wrong" allowance
+    assert bad == 0, f"{what}: {bad} of {err.numel()} elements out of tolerance, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 768), (384, 768, 3072), (1024, 2304, 768), (200, 328, 136)])
@@ -134,8 +134,8 @@ def test_layernorm_fwd_bwd():
         dg, db = torch.zeros(d, device=_dev()), torch.zeros(d, device=_dev())
         ops.layernorm_bwd(dy, x, g, mean, rstd, dres, dx, dg, db)
         _close(dx, xf.grad + dres.float(), 2e-2, 3e-2, f"ln bwd dx d={d}")
-        _close(dg, gf.grad, 2e-2, 0.3, f"ln dgamma d={d}")
-        _close(db, bf.grad, 2e-2, 0.3, f"ln dbeta d={d}")
+        _close(dg, gf.grad, 2e-3, 2e-2, f"ln dgamma d={d}")     # fp32 column sums of the same bf16 inputs: only mean / rstd rounding differs
+        _close(db, bf.grad, 2e-3, 2e-2, f"ln dbeta d={d}")
 
 
 def test_cross_entropy_loss_and_grad():
