@@ -65,7 +65,9 @@ def test_fed_round_matches_oracle(kind, n):
         for g in range(n):  # every GPU must hold the same new global model (fp32 + bf16 cast)
             got = fed.global_params(g).cpu()
             torch.testing.assert_close(got[tight], ref.parameters[tight], rtol=2e-5, atol=2e-6)
-            torch.testing.assert_close(got[~tight], ref.parameters[~tight], rtol=0, atol=ref.hp.get("eta", 0.0) / ref.hp.get("tau", 1.0) * 4e-7 + 1e-6)
+            # near pg = 0: |d step / d pg| <= eta / tau, and the fp32 weighted mean carries ~1e-7 * (1 + |x|) of rounding noise
+            bound = ref.hp.get("eta", 0.0) / ref.hp.get("tau", 1.0) * 1e-6 * (1.0 + ref.parameters[~tight].abs()) + 1e-6
+            assert bool(((got[~tight] - ref.parameters[~tight]).abs() <= bound).all())
             assert torch.equal(fed.global_shadow(g).cpu(), got.to(torch.bfloat16))
         # server moments (each GPU keeps its shard): stitched they equal the oracle's planes
         for j, plane in enumerate((ref.momentum_vector, ref.second_momentum_vector)):
