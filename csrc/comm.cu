@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
   const float inv = skip ? 0.f : a.avg_scale / wtot;
 
   const int lane = threadIdx.x & 31;
-  float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // Σpg², Σa², Σx², Σm², Σv² of the tensor the warp is in
+  float s_pg = 0.f, s_a = 0.f, s_x = 0.f, s_m = 0.f, s_v = 0.f;   // Σpg², Σa², Σx², Σm², Σv² of the tensor the warp is in
   __nv_bfloat16* xs_mine = reinterpret_cast<__nv_bfloat16*>(a.xs[c.rank]);
   const bool local_only = (c.n == 1);
 
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float pg = xv[k] - av[k];
-        s5[0] += pg * pg;
-        s5[1] += av[k] * av[k];
+        s_pg += pg * pg;
+        s_a += av[k] * av[k];
         switch (a.kind) {
           case 0:  // FedAvg
             xv[k] -= a.lr * pg;
@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
             break;
           }
         }
-        s5[2] += xv[k] * xv[k];
-        s5[3] += mv[k] * mv[k];
-        s5[4] += vv[k] * vv[k];
+        s_x += xv[k] * xv[k];
+        s_m += mv[k] * mv[k];
+        s_v += vv[k] * vv[k];
       }
       if (a.kind >= 1) reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
       if (a.kind >= 3) reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
@@ -214,19 +214,27 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
   };
   int seg = 0;
   auto flush = [&]() {
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float t = warp_sum(s5[j]);
-      if (lane == 0 && t != 0.f && a.seg_sums) atomicAdd(a.seg_sums + (long long)j * a.n_seg + seg, double(t));
-      s5[j] = 0.f;
+    const float t0 = warp_sum(s_pg), t1 = warp_sum(s_a), t2 = warp_sum(s_x), t3 = warp_sum(s_m), t4 = warp_sum(s_v);
+    if (lane == 0 && a.seg_sums) {
+      double* d = a.seg_sums + seg;
+      if (t0 != 0.f) atomicAdd(d, double(t0));
+      if (t1 != 0.f) atomicAdd(d + a.n_seg, double(t1));
+      if (t2 != 0.f) atomicAdd(d + 2 * a.n_seg, double(t2));
+      if (t3 != 0.f) atomicAdd(d + 3 * a.n_seg, double(t3));
+      if (t4 != 0.f) atomicAdd(d + 4 * a.n_seg, double(t4));
     }
+    s_pg = s_a = s_x = s_m = s_v = 0.f;
   };
   if (!skip) {
     const long long u_lo = a.lo / (4 * UNIT4), u_hi = (a.hi + 4 * UNIT4 - 1) / (4 * UNIT4);   // shard bounds are unit-aligned
-    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long per = (u_hi - u_lo + n_warps - 1) / n_warps;
-    const long long ub = u_lo + gw * per, ue = (ub + per < u_hi) ? ub + per : u_hi;
+    // every BLOCK owns a contiguous run of units; inside it the warps take neighbouring unit pairs (warp w: pairs w, w + W, ...),
+    // so at any moment a block streams one dense ~32 KiB window per plane (DRAM-page friendly) while every warp still walks
+    // the unit space monotonically (what the per-tensor bookkeeping needs)
+    const long long W = blockDim.x >> 5;
+    long long per = (u_hi - u_lo + gridDim.x - 1) / gridDim.x;
+    per = (per + 1) & ~1ll;                                      // even: pairs never straddle two blocks
+    const long long bb = u_lo + blockIdx.x * per, ue = (bb + per < u_hi) ? bb + per : u_hi;
+    const long long ub = bb + 2 * (threadIdx.x >> 5);
     const long long hi4 = a.hi / 4;
     if (ub < ue && a.seg_bounds) {   // binary search: first tensor whose end is beyond this warp's first unit
       int l = 0, r = a.n_seg - 1;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
       seg = l;
     }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long u = ub; u < ue; u += 2) {   // two units per trip: four 16-byte loads per plane per thread in flight
+    for (long long u = ub; u < ue; u += 2 * W) {   // two units per trip: four 16-byte loads per plane per thread in flight
       float4 A[4], X[4], M[4], V[4];
       long long idx[4];
 #pragma unroll
