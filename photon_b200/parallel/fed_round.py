@@ -60,6 +60,7 @@ class NvlFedRound:
         self._seg_bounds: list[torch.Tensor] = []
         self._seg_sums: list[torch.Tensor] = []
         self.last_status = 0
+        self._orphans: dict[int, tuple[torch.Tensor | None, torch.Tensor | None]] = {}   # server moments of adopted (dead ranks') shards
         for i in range(self.n_local):
             dev = torch.device("cuda", self.arena.devices[i])
             lo, hi = self.shard_of(i)
@@ -115,26 +116,58 @@ class NvlFedRound:
         ops.axpby_(self.acc(local), params, 1.0, float(weight))
         self._wsum[local] += float(weight)
 
-    def finish_round(self, server_round: int) -> None:
-        """Launch the fused reduce + server-opt + broadcast kernel on every local GPU."""
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
+        """Launch the fused reduce + server-opt + broadcast kernel on every local GPU.
+
+        ``alive``: the ranks taking part (default: all). After a rank died the survivors run the SAME kernel over the subset —
+        control pages, planes and the reduction simply leave the dead peer out (P2P path; the multicast mapping still includes
+        it) — and the slice of the index space the dead rank owned is ADOPTED by a survivor in an extra launch (its server
+        moments restart from zero there: that state lived in the dead process)."""
         st, hp, ext, ar = self.strategy, self.strategy.hp, ops.ext(), self.arena
-        epoch = ar.next_epoch()
         kind = _KIND[st.kind]
-        launches = []
+        world = ar.world_size
+        ranks = list(range(world)) if alive is None else sorted(int(r) for r in alive)
+        degraded = len(ranks) < world
+        if degraded and ar.single:
+            raise NotImplementedError("masked rounds are a multi-process feature")
         for i in range(self.n_local):
             rank = i if ar.single else ar.rank
-            dev = ar.devices[i if ar.single else 0]
-            lo, hi = ar.shard(self.total, rank)
-            ext.set_wsum(ar.ctl_ptrs()[rank], dev, self._wsum[i], True)
-            launches.append((rank, dev, lo, hi, i))
-        for rank, dev, lo, hi, i in launches:
+            ext.set_wsum(ar.ctl_ptrs()[rank], ar.devices[i if ar.single else 0], self._wsum[i], True)
             self._seg_sums[i].zero_()
-            ext.fed_round(ar.ctl_ptrs(), rank, dev, epoch, ar.ptrs("acc"), ar.ptrs("xg"), ar.ptrs("xs") if self.has_shadow else [],
-                          self._m[i].data_ptr() - 4 * lo if self._m[i] is not None else 0,
-                          self._v[i].data_ptr() - 4 * lo if self._v[i] is not None else 0,
+        sub = (lambda xs: [xs[r] for r in ranks]) if degraded else (lambda xs: xs)
+        acc_mc, xg_mc = (0, 0) if degraded else (ar.mc_ptr("acc"), ar.mc_ptr("xg"))
+        shadow = ar.ptrs("xs") if self.has_shadow else []
+
+        def launch(i: int, rank: int, lo: int, hi: int, m: torch.Tensor | None, v: torch.Tensor | None, epoch: int) -> None:
+            ext.fed_round(sub(ar.ctl_ptrs()), ranks.index(rank), ar.devices[i if ar.single else 0], epoch, sub(ar.ptrs("acc")), sub(ar.ptrs("xg")),
+                          sub(shadow) if shadow else [], m.data_ptr() - 4 * lo if m is not None else 0, v.data_ptr() - 4 * lo if v is not None else 0,
                           lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
                           hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat),
-                          ar.mc_ptr("acc"), ar.mc_ptr("xg"), self._seg_bounds[i], self._seg_sums[i])
+                          acc_mc, xg_mc, self._seg_bounds[i], self._seg_sums[i])
+
+        epoch = ar.next_epoch()
+        for i in range(self.n_local):      # every participant updates the shard it owns
+            rank = i if ar.single else ar.rank
+            lo, hi = ar.shard(self.total, rank)
+            launch(i, rank, lo, hi, self._m[i], self._v[i], epoch)
+        if degraded:                        # orphaned shards, one launch each: every survivor takes part, the adopter does the work
+            for d in [r for r in range(world) if r not in ranks]:
+                adopter = ranks[d % len(ranks)]
+                lo, hi = ar.shard(self.total, d)
+                epoch = ar.next_epoch()
+                if ar.rank == adopter:
+                    m, v = self._orphan_moments(d, hi - lo)
+                    launch(0, ar.rank, lo, hi, m, v, epoch)
+                else:
+                    launch(0, ar.rank, lo, lo, None, None, epoch)
+
+    def _orphan_moments(self, dead_rank: int, n: int) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        if dead_rank not in self._orphans:
+            dev = torch.device("cuda", self.arena.devices[0])
+            print(f"[round/nvl] adopting the server shard of dead rank {dead_rank}: its moments restart from zero", flush=True)
+            self._orphans[dead_rank] = (torch.zeros(n, device=dev) if self.strategy.n_moments >= 1 else None,
+                                        torch.zeros(n, device=dev) if self.strategy.n_moments >= 2 else None)
+        return self._orphans[dead_rank]
 
     def check_status(self) -> int:
         """Sticky status word of the local control page(s) after the round kernel (one 4-byte read, synchronising): 0 = every
@@ -152,12 +185,14 @@ class NvlFedRound:
         for i in range(self.n_local):
             self.arena.ctl_words(self._r(i))[off] = 0
 
-    def segment_sq_sums(self, group: Any = None) -> torch.Tensor:
+    def segment_sq_sums(self, group: Any = None, ctl: Any = None) -> torch.Tensor:
         """float64 [5, n_seg] on the host: per-tensor Σpg², Σa², Σx², Σm², Σv² of the last round, summed over all ranks' shards
         (tiny: off the hot path, called when the metrics are collected)."""
         sums = torch.zeros(5, self.n_seg, dtype=torch.float64)
         for i in range(self.n_local):
             sums += self._seg_sums[i].cpu()
+        if ctl is not None:
+            return ctl.sum_tensor("segsq", sums)         # host control plane: survives dead peers
         if not self.arena.single and self.arena.world_size > 1:
             import torch.distributed as dist
 
@@ -166,11 +201,11 @@ class NvlFedRound:
             sums = t.cpu()
         return sums
 
-    def round_norms(self, group: Any = None, per_layer: bool = True) -> dict[str, float]:
+    def round_norms(self, group: Any = None, per_layer: bool = True, ctl: Any = None) -> dict[str, float]:
         """The reference's server norm metrics from the kernel's by-products: ``server/l2_norm_{pseudo_gradient,fedavg_result,
         model,momentum_vector,second_momentum_vector}`` and, per tensor of the layout, ``server/layer/{i}/l2_norm_*``
         (ref: photon/strategy/fedadam.py:333-381)."""
-        sums = self.segment_sq_sums(group)
+        sums = self.segment_sq_sums(group, ctl)
         names = ["pseudo_gradient", "fedavg_result", "model", "momentum_vector", "second_momentum_vector"][: 3 + self.strategy.n_moments]
         out: dict[str, float] = {}
         for j, n in enumerate(names):

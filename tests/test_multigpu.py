@@ -77,6 +77,12 @@ def test_fed_round_matches_oracle(kind, n):
             torch.testing.assert_close(full, plane, rtol=1e-4, atol=1e-6)
         # norm by-products of the same pass: global AND per tensor (the reference's server/layer/{i}/... metrics)
         want = ref.norm_metrics(pg, avg)
+        # every round is compared as ONE step from identical state: adopt the kernel's state so that the (bounded) differences
+        # near pg = 0 do not compound through the adaptive optimizers' history
+        ref.parameters.copy_(fed.global_params(0).cpu())
+        for j, name in enumerate(("momentum_vector", "second_momentum_vector")):
+            if getattr(ref, name) is not None:
+                getattr(ref, name).copy_(sum(fed.full_moments(g)[j].cpu() for g in range(n)))
         norms = fed.round_norms()
         assert set(want) == set(norms), sorted(set(want) ^ set(norms))[:5]
         for k, v in want.items():
