@@ -62,6 +62,12 @@ class Photon(_Strict):
     resume_round: int | None = -1
     saving_path: str | None = None
     comm_stack: CommStack = Field(default_factory=CommStack)
+    # SPMD host control plane (photon_b200/server/control.py): liveness, shared work queue, time-bounded metadata exchange
+    control_plane: str = "store"          # store | none
+    scheduling: str = "dynamic"           # dynamic = shared work queue (a free GPU takes the next client) | static = client i -> node i mod n
+    liveness_timeout_s: float = 20.0      # a rank whose heartbeat is older than this is dead
+    progress_timeout_s: float = 900.0     # a rank whose main thread made no progress for this long stops its heartbeat (hung = dead)
+    kernel_peer_timeout_s: float = 120.0  # bound on every cross-GPU spin inside the NVLink kernels (aborted round instead of a hang)
 
     @field_validator("n_nodes", "refresh_period")
     @classmethod

@@ -79,6 +79,11 @@ class FederationRuntime:
         self.round_backend: RoundBackend | None = None
         self.fault_injection = dict(cfg["fl"].get("fault_injection") or {})
         self.timings: dict[str, float] = {}
+        # host control plane (liveness, shared work queue, time-bounded metadata exchange); None on a single rank
+        self.ctl: Any = None
+        self.alive_ranks: list[int] = list(range(self.world_size))
+        self.scheduling = str(cfg["photon"].get("scheduling", "dynamic") or "dynamic").lower()
+        self.assignment: dict[int, int] = {}        # cid -> node that trained it in the last round (diagnostics / tests)
 
     # --------------------------------------------------------------------- bring-up
     def build(self) -> None:
@@ -116,6 +121,26 @@ class FederationRuntime:
         self.layout = self.model_layout.stacked(("", "exp_avg/", "exp_avg_sq/")) if self.aggregate_momenta else self.model_layout
         self.round_backend = build_round_backend(self.cfg, self.layout, self.strategy, self.device, rank=self.rank,
                                                  world_size=self.world_size, group=self.group)
+        from photon_b200.server.control import build_control_plane
+
+        self.ctl = build_control_plane(self.cfg, self.rank, self.world_size)
+        self.round_backend.ctl = self.ctl
+        if self.ctl is not None:
+            from photon_b200.train.callbacks import Callback
+
+            ctl = self.ctl
+
+            class _Progress(Callback):     # every finished batch is a sign of life of this rank's main thread
+                def batch_end(self, trainer: Any) -> None:
+                    ctl.tick()
+
+            self.trainer.callbacks.append(_Progress())
+        if self.ctl is not None and self.device.type == "cuda":
+            from photon_b200 import ops
+
+            # the in-kernel spins give up after this long: a peer that died after the host-side liveness check turns into an
+            # aborted (and then repeated, masked) round instead of a hang
+            ops.ext().set_comm_timeout_ms(int(1000 * float(self.cfg["photon"].get("kernel_peer_timeout_s", 120.0) or 120.0)))
 
     def initial_parameters(self) -> torch.Tensor:
         """Rank 0's freshly initialised (or pretrained) model as a flat tensor."""
@@ -129,8 +154,13 @@ class FederationRuntime:
         return flat
 
     def node_ids(self) -> list[int]:
-        """Logical nodes currently alive: one per client group of ranks (ref: Driver.get_node_ids)."""
-        return spmd_node_ids(self.group)[:: self.gpus_per_client]
+        """Logical nodes currently alive: one per client group of ranks (ref: Driver.get_node_ids). With the control plane this
+        is a real liveness check (heartbeats); a client group counts as alive only while ALL its ranks are."""
+        if self.ctl is None:
+            return spmd_node_ids(self.group)[:: self.gpus_per_client]
+        alive = set(self.ctl.alive())
+        g = self.gpus_per_client
+        return [n for n in range(self.n_nodes) if all(r in alive for r in range(n * g, (n + 1) * g))]
 
     # ----------------------------------------------------------------------- sampling
     def sample_clients(self) -> list[int]:
@@ -144,12 +174,55 @@ class FederationRuntime:
             self.sample_clients()
 
     def my_clients(self, sampled: list[int]) -> list[int]:
-        return static_assignment(sampled, list(range(self.n_nodes)))[self.node_id]
+        """Static queue of this node: client i -> living node i mod n (what the work queue converges to with equally fast nodes)."""
+        nodes = self.node_ids() if self.ctl is not None else list(range(self.n_nodes))
+        return static_assignment(sampled, nodes).get(self.node_id, [])
+
+    def _client_queue(self, server_round: int, sampled: list[int]) -> Any:
+        """The clients this node trains in this round, one at a time. ``photon.scheduling=dynamic`` (default with a control plane):
+        a shared atomic counter — whenever this node is free it takes the NEXT sampled client, so a fast GPU ends up with more
+        clients than a slow one (the reference's reply-frees-the-node work queue, ref: photon/server/server_util.py:163-202).
+        ``static``: the precomputed queue (reproducible client-to-node mapping)."""
+        if self.ctl is None or self.scheduling == "static":
+            yield from self.my_clients(sampled)
+            return
+        q = self.ctl.open_queue(f"fit/{server_round}")
+        while True:
+            idx = self.ctl.next_index(q) if self.is_leader else 0
+            if self.gpus_per_client > 1:     # the leader's pick is the whole client group's pick
+                t = torch.tensor([idx], dtype=torch.int64, device=self.device if dist.get_backend(self.client_group) == "nccl" else "cpu")
+                dist.broadcast(t, src=self.node_id * self.gpus_per_client, group=self.client_group)
+                idx = int(t.item())
+            if idx >= len(sampled):
+                return
+            yield sampled[idx]
 
     # -------------------------------------------------------------------------- fit
     def _should_fail(self, server_round: int, cid: int) -> bool:
+        """``fl.fault_injection: {round, cid, kind}`` — ``kind: exception`` (default) fails the client, ``kill`` SIGKILLs the whole
+        rank while it trains the client (a dead node), ``hang`` blocks it forever (a hung node: its heartbeat goes stale after
+        ``photon.progress_timeout_s``)."""
         fi = self.fault_injection
-        return bool(fi) and int(fi.get("round", -1)) == server_round and int(fi.get("cid", -1)) == cid
+        if not (bool(fi) and int(fi.get("round", -1)) == server_round):
+            return False
+        # target: a client id (``cid``) and / or whatever client a given rank is training (``rank``)
+        if ("cid" in fi and int(fi["cid"]) != cid) or ("rank" in fi and int(fi["rank"]) != self.rank) or not ({"cid", "rank"} & set(fi)):
+            return False
+        kind = str(fi.get("kind", "exception"))
+        if kind == "slow":      # a straggler: the client takes `seconds` longer (work-queue rebalancing tests)
+            time.sleep(float(fi.get("seconds", 1.0)))
+            return False
+        if kind == "kill":
+            import os
+            import signal
+
+            print(f"[fault-injection] rank {self.rank}: SIGKILL while training client {cid} in round {server_round}", flush=True)
+            os.kill(os.getpid(), signal.SIGKILL)
+        if kind == "hang":
+            print(f"[fault-injection] rank {self.rank}: hanging while training client {cid} in round {server_round}", flush=True)
+            while True:
+                time.sleep(3600.0)
+        return True
 
     def run_clients_fit(self, server_round: int, sampled: list[int]) -> list[FitRes]:
         assert self.trainer is not None and self.round_backend is not None
@@ -166,12 +239,10 @@ class FederationRuntime:
         rb.begin_round()
         results: list[FitRes] = []
         keep_opt = not bool(self.cfg["fl"]["reset_optimizer"])
-        mine = set(self.my_clients(sampled))
-        for cid in sampled:     # every rank sees the same sample: a client another node trains this round leaves stale moments here
-            if cid not in mine:
-                self._opt_states.pop(cid, None)
         t_fit = 0.0
-        for cid in self.my_clients(sampled):
+        self._trained_here: list[int] = []
+        for cid in self._client_queue(server_round, sampled):
+            self._trained_here.append(cid)
             t0 = time.time()
             try:
                 if self._should_fail(server_round, cid):
@@ -179,8 +250,8 @@ class FederationRuntime:
                 fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
                 opt = tr.state.optimizer
                 if keep_opt and cid in self._opt_states:
-                    # the client's own moments from ITS last participation (entries are dropped above as soon as the client
-                    # trains elsewhere, so what is found here is never older than that); a client checkpoint, when present,
+                    # the client's own moments from ITS last participation (entries are dropped in gather_results as soon as the
+                    # client trains elsewhere, so what is found here is never older than that); a client checkpoint, when present,
                     # is loaded on top by llm_fit. Keyed by client id, whatever the client-to-node mapping of the round.
                     m, v, step = self._opt_states[cid]
                     opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)  # per-rank planes (a slice when the state is sharded)
@@ -208,20 +279,57 @@ class FederationRuntime:
         self.timings["node_training_time_s"] = t_fit
         return results
 
-    def gather_results(self, results: list[FitRes]) -> list[FitRes]:
-        """Control-plane gather (metadata only — parameters never travel here)."""
+    def gather_results(self, results: list[FitRes], sampled: list[int] | None = None) -> list[FitRes]:
+        """Control-plane gather (metadata only — parameters never travel here). With the host control plane this is also where a
+        dead rank is discovered: it never answers, rank 0 rules it out, and every sampled client nobody reported on becomes a
+        FAILED result (counted against ``fl.accept_failures_cnt`` like any other client failure)."""
         mine = [r for r in results if self.is_leader or r.status.code != Code.OK]
-        if self.world_size == 1 or not dist.is_initialized():
-            return mine
-        box: list[Any] = [None] * self.world_size
-        dist.all_gather_object(box, mine, group=self.group)
-        return [r for part in box for r in part]
+        if self.ctl is not None:
+            parts = self.ctl.gather("fit_results", (self.node_id, mine))
+            self.alive_ranks = sorted(parts)
+            out = [r for rk in sorted(parts) for r in parts[rk][1]]
+            self.assignment = {int(r.cid): int(parts[rk][0]) for rk in sorted(parts) for r in parts[rk][1] if r.status.code == Code.OK}
+            if sampled is not None:
+                seen = {int(r.cid) for r in out}
+                for cid in sampled:
+                    if int(cid) not in seen:
+                        out.append(FitRes(Status(Code.FAILED, "the node training this client stopped responding (marked dead)"), None, 0, {}, cid))
+        elif self.world_size == 1 or not dist.is_initialized():
+            out = mine
+        else:
+            box: list[Any] = [None] * self.world_size
+            dist.all_gather_object(box, mine, group=self.group)
+            out = [r for part in box for r in part]
+        # clients another node trained this round leave stale optimizer moments here
+        here = set(getattr(self, "_trained_here", []))
+        for r in out:
+            if r.status.code == Code.OK and int(r.cid) not in here:
+                self._opt_states.pop(int(r.cid), None)
+        return out
 
     def finish_round(self, server_round: int) -> None:
+        """Aggregate + server optimizer + broadcast over the ranks that are alive. If the fused kernel reports that a participant
+        never reached its start barrier (it died after the host-side check) nothing was modified: the rank is ruled out and the
+        round is run again over the survivors."""
         assert self.round_backend is not None
         t0 = time.time()
         with tracer().span("aggregate_server_opt_broadcast", cat="round", device=True, server_round=server_round, transport=self.round_backend.name):
-            self.round_backend.finish_round(server_round)
+            for attempt in range(max(1, self.world_size)):
+                alive = list(self.alive_ranks)
+                self.round_backend.finish_round(server_round, alive=alive if len(alive) < self.world_size else None)
+                if self.ctl is None:
+                    break
+                st = self.round_backend.status()
+                verdict = self.ctl.gather(f"round_status/{server_round}/{attempt}", int(st))
+                lost = {alive[t] for stv in verdict.values() for t in range(len(alive)) if (int(stv) >> t) & 1 or (int(stv) >> (8 + t)) & 1}
+                lost |= set(alive) - set(verdict)
+                if any((int(stv) >> 8) & 0xFF for stv in verdict.values()):
+                    raise RuntimeError("a peer vanished INSIDE the round kernel: the global model may be torn; resume from the last server checkpoint")
+                if not lost:
+                    break
+                self.ctl.mark_dead(lost)
+                self.alive_ranks = [r for r in alive if r not in lost]
+                print(f"[federation] round {server_round}: rank(s) {sorted(lost)} did not reach the round kernel; repeating over {self.alive_ranks}", flush=True)
         self.timings["aggregate_broadcast_host_s"] = time.time() - t0
 
     def abort_round(self) -> None:
@@ -243,6 +351,9 @@ class FederationRuntime:
         return self._gather_eval(out)
 
     def _gather_eval(self, mine: list[EvaluateRes]) -> list[EvaluateRes]:
+        if self.ctl is not None:
+            parts = self.ctl.gather("eval_results", mine if self.is_leader else [])
+            return [r for rk in sorted(parts) for r in parts[rk]]
         if self.world_size == 1 or not dist.is_initialized():
             return mine
         box: list[Any] = [None] * self.world_size
@@ -259,5 +370,9 @@ class FederationRuntime:
     def close(self) -> None:
         if self.trainer is not None:
             self.trainer.close()
+        if self.ctl is not None:
+            self.ctl.close()
         if self.round_backend is not None:
+            if self.ctl is not None and self.ctl.dead:
+                return   # arena teardown is collective over the original group; with a dead peer the process just exits
             self.round_backend.close()

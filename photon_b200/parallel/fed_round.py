@@ -233,5 +233,13 @@ class NvlFedRound:
             out.append(full)
         return out[0], out[1]
 
+    def add_orphans(self, full: torch.Tensor, which: int) -> torch.Tensor:
+        """Add the moments of the shards this rank adopted from dead ranks into a zero-padded full-length plane."""
+        for d, mv in self._orphans.items():
+            if mv[which] is not None:
+                lo, hi = self.arena.shard(self.total, d)
+                full[lo:hi] = mv[which]
+        return full
+
     def close(self) -> None:
         self.arena.close()

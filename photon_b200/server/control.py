@@ -34,7 +34,8 @@ class ServerLostError(RuntimeError):
 
 class ControlPlane:
     def __init__(self, rank: int, world_size: int, *, host: str | None = None, port: int | None = None, heartbeat_s: float = 0.5,
-                 liveness_timeout_s: float = 20.0, exchange_timeout_s: float = 7200.0, namespace: str = "photon") -> None:
+                 liveness_timeout_s: float = 20.0, exchange_timeout_s: float = 7200.0, progress_timeout_s: float = 900.0,
+                 namespace: str = "photon") -> None:
         from torch.distributed import TCPStore
 
         self.rank, self.world_size = int(rank), int(world_size)
@@ -44,6 +45,10 @@ class ControlPlane:
         self.store = TCPStore(host, port, world_size=None, is_master=(self.rank == 0), timeout=timedelta(seconds=60), wait_for_workers=False,
                               multi_tenant=True)
         self.ns = namespace
+        # a rank whose MAIN thread made no progress for this long stops refreshing its heartbeat: a hung worker (stuck kernel,
+        # dead-locked loader) then looks exactly like a dead one (ref: the node manager's per-task time-out)
+        self.progress_timeout_s = float(progress_timeout_s)
+        self._last_tick = time.time()
         self.dead: set[int] = set()
         self._seq: dict[str, int] = {}
         self._stop = threading.Event()
@@ -65,8 +70,14 @@ class ControlPlane:
     def _beat(self) -> None:
         self.store.set(self._k(f"hb/{self.rank}"), repr(time.time()).encode())
 
+    def tick(self) -> None:
+        """Progress mark of the main thread (every training batch, every control-plane call)."""
+        self._last_tick = time.time()
+
     def _heartbeat_loop(self) -> None:
         while not self._stop.wait(self.heartbeat_s):
+            if time.time() - self._last_tick > self.progress_timeout_s:
+                continue    # hung: let the heartbeat go stale
             try:
                 self._beat()
             except Exception:  # noqa: BLE001 - the store went away (rank 0 died): nothing left to tell
@@ -101,12 +112,14 @@ class ControlPlane:
 
     def next_index(self, queue: str) -> int:
         """Atomically take the next work item index of ``queue`` (0, 1, 2, ... across ALL ranks)."""
+        self.tick()
         return int(self.store.add(self._k(queue), 1)) - 1
 
     # ------------------------------------------------------------------ exchanges
     def _wait_key(self, key: str, owner: int, deadline: float) -> bool:
         """True when ``key`` exists; False when its owner died (or the exchange timed out) first."""
         while True:
+            self.tick()      # waiting for a peer IS this rank's progress
             if self.store.check([key]):
                 return True
             if owner in self.dead or self._age(owner) > self.liveness_timeout_s or time.time() > deadline:
@@ -116,6 +129,7 @@ class ControlPlane:
     def gather(self, tag: str, obj: Any) -> dict[int, Any]:
         """Every living rank contributes ``obj``; returns ``{rank: obj}`` for the ranks rank 0 ruled in (identical on every survivor).
         Ranks that died before contributing are added to :attr:`dead`."""
+        self.tick()
         key = self._k(self._next_seq(f"x/{tag}"))
         self.store.set(f"{key}/{self.rank}", pickle.dumps(obj))
         deadline = time.time() + self.exchange_timeout_s
@@ -159,6 +173,8 @@ class ControlPlane:
 
     def close(self) -> None:
         self._stop.set()
+        self._thread.join(timeout=2.0)
+        self.store = None   # drop the client connection (rank 0: the server socket goes with the last reference)
 
 
 def build_control_plane(cfg: Any, rank: int, world_size: int) -> ControlPlane | None:
@@ -168,4 +184,5 @@ def build_control_plane(cfg: Any, rank: int, world_size: int) -> ControlPlane | 
     if world_size <= 1 or mode in ("none", "off", "false"):
         return None
     return ControlPlane(rank, world_size, liveness_timeout_s=float(ph.get("liveness_timeout_s", 20.0) or 20.0),
+                        progress_timeout_s=float(ph.get("progress_timeout_s", 900.0) or 900.0),
                         namespace=f"photon/{cfg.get('run_uuid', 'run')}")

@@ -56,7 +56,7 @@ def fit_round(runtime: Any, server_round: int, sampled_clients: list[int]) -> di
     (``server/fit_round_time`` included; ref: fit_utils.py:291-389)."""
     t0 = time.time()
     results = runtime.run_clients_fit(server_round, sampled_clients)
-    all_results = runtime.gather_results(results)
+    all_results = runtime.gather_results(results, sampled_clients)
     ok, failed = split_results(all_results)
     for r in failed:   # say WHY before deciding whether the round survives (the reference only counts)
         print(f"[server] round {server_round}: client {getattr(r, 'cid', '?')} failed: {r.status.message}", flush=True)

@@ -51,6 +51,49 @@ class RoundBackend:
         self.rank, self.world_size, self.group = rank, world_size, group
         self.last_metrics: dict[str, Any] = {}
         self.timings: dict[str, float] = {}
+        # host control plane (photon_b200.server.control): when set, the tiny metadata exchanges of a round go through it instead
+        # of torch.distributed collectives, so they keep working (over the survivors) after a rank died
+        self.ctl: Any = None
+
+    # -- metadata exchange: control plane when present, torch.distributed otherwise ---------------------------------------
+    def _gather_objects(self, tag: str, obj: Any) -> list[Any]:
+        """One object per LIVING rank, in rank order."""
+        if self.ctl is not None:
+            parts = self.ctl.gather(f"rb/{tag}", obj)
+            return [parts[r] for r in sorted(parts)]
+        if _dist_on(self.group):
+            box: list[Any] = [None] * self.world_size
+            dist.all_gather_object(box, obj, group=self.group)
+            return box
+        return [obj]
+
+    def _bcast_object(self, tag: str, obj: Any) -> Any:
+        if self.ctl is not None:
+            return self.ctl.broadcast(f"rb/{tag}", obj, src=0)
+        if _dist_on(self.group):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            return box[0]
+        return obj
+
+    def _barrier(self, tag: str) -> None:
+        if self.ctl is not None:
+            self.ctl.barrier(f"rb/{tag}")
+        elif _dist_on(self.group):
+            dist.barrier(group=self.group)
+
+    def _sum_small(self, tag: str, t: torch.Tensor) -> torch.Tensor:
+        if self.ctl is not None:
+            return self.ctl.sum_tensor(f"rb/{tag}", t)
+        if self.world_size > 1 and _dist_on(self.group):
+            if dist.get_backend(self.group) != "nccl":
+                t = t.cpu()
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def status(self) -> int:
+        """Non-zero when the last ``finish_round`` could not include every participant (bit mask; nvl only)."""
+        return 0
 
     def set_global(self, params: torch.Tensor, momentum: torch.Tensor | None = None, second: torch.Tensor | None = None) -> None:
         raise NotImplementedError
@@ -61,7 +104,8 @@ class RoundBackend:
     def add_client(self, params: torch.Tensor, weight: float) -> None:
         raise NotImplementedError
 
-    def finish_round(self, server_round: int) -> None:
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
+        """``alive``: the ranks taking part when some died (None = all)."""
         raise NotImplementedError
 
     def global_params(self) -> torch.Tensor:
@@ -97,10 +141,7 @@ class RoundBackend:
         stats = torch.zeros(2, dtype=torch.float64, device=self.device)
         if getattr(self, "_cb_sq", None) is not None:
             stats[0], stats[1] = self._cb_sq.to(self.device), float(self._cb_n)
-        if self.world_size > 1 and _dist_on(self.group):
-            if dist.get_backend(self.group) != "nccl":
-                stats = stats.cpu()
-            dist.all_reduce(stats, group=self.group)
+        stats = self._sum_small("cbstats", stats)
         g_big = self._pg_sq()
         if g_big is not None:
             sum_sq, n = stats.tolist()
@@ -173,7 +214,10 @@ class CollectiveRoundBackend(_HostAccumulating):
 
     name = "ray"
 
-    def finish_round(self, server_round: int) -> None:
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
+        if alive is not None and len(alive) < self.world_size:
+            raise RuntimeError("comm_stack.ray all-reduces over the job's process group and cannot leave a dead rank out; "
+                               "use comm_stack.nvl (GPU) or comm_stack.shm (host) for fault-tolerant rounds")
         t0 = time.perf_counter()
         acc = self._acc if self._acc is not None else torch.zeros(self.layout.total, device=self.device)
         w = torch.tensor([self._w], dtype=torch.float64, device=acc.device if _dist_on(self.group) and dist.get_backend(self.group) == "nccl" else "cpu")
@@ -208,6 +252,7 @@ class ShmRoundBackend(_HostAccumulating):
             dist.broadcast_object_list(box, src=0, group=self.group)
             self.uid = box[0]
         self._handles: list[Any] = []
+        self._n = 0
 
     @property
     def server_device(self) -> torch.device:
@@ -224,17 +269,14 @@ class ShmRoundBackend(_HostAccumulating):
         shm.close()
         return views
 
-    def finish_round(self, server_round: int) -> None:
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
         t0 = time.perf_counter()
+        self._n += 1
         up = f"{self.uid}_r{self.rank}_up"
         have = self._acc is not None and self._w > 0
         meta = self._put(up, self._acc / self._w) if have else None
-        infos: list[Any] = [None] * self.world_size
         mine = (up, meta.to_literal() if meta else None, self._w)
-        if _dist_on(self.group):
-            dist.all_gather_object(infos, mine, group=self.group)
-        else:
-            infos = [mine]
+        infos = self._gather_objects(f"shm_up/{self._n}", mine)     # only the living ranks answer (parameters travel through POSIX shm)
         down = f"{self.uid}_down"
         down_meta: list[Any] = [None]
         agg: torch.Tensor | None = None
@@ -261,14 +303,12 @@ class ShmRoundBackend(_HostAccumulating):
         gap = self._fedavg_gap(agg, agg_scale)
         if gap:
             self.last_metrics = {**self.last_metrics, **gap}
-        if _dist_on(self.group):
-            dist.broadcast_object_list(down_meta, src=0, group=self.group)
+        down_meta[0] = self._bcast_object(f"shm_down/{self._n}", down_meta[0])
         arrays = self._get(down, ModelParametersMetadata.from_literal(down_meta[0]))
         host = torch.zeros(self.layout.total)
         self.layout.from_ndarrays(host, arrays)
         self._x_dev = host.to(self.device)  # H2D
-        if _dist_on(self.group):
-            dist.barrier(group=self.group)
+        self._barrier(f"shm_done/{self._n}")
         for h in self._handles:
             h.close()
         self._handles = []
@@ -301,18 +341,15 @@ class FileRoundBackend(_HostAccumulating):
                 time.sleep(0.05 * (attempt + 1))
         return load_model_parameters_from_file(path)
 
-    def finish_round(self, server_round: int) -> None:
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
         t0 = time.perf_counter()
         have = self._acc is not None and self._w > 0
         mine = self.dir / f"client-rank{self.rank}" / "parameters.npz"
         if have:
             dump_model_parameters_to_file(mine, self.layout.to_ndarrays(self._acc / self._w))
-        infos: list[Any] = [None] * self.world_size
+        self._n = getattr(self, "_n", 0) + 1
         rec = (str(mine) if have else None, self._w)
-        if _dist_on(self.group):
-            dist.all_gather_object(infos, rec, group=self.group)
-        else:
-            infos = [rec]
+        infos = self._gather_objects(f"s3_up/{self._n}", rec)
         down = self.dir / "server" / "parameters.npz"
         agg: torch.Tensor | None = None
         agg_scale = 1.0
@@ -337,13 +374,11 @@ class FileRoundBackend(_HostAccumulating):
         gap = self._fedavg_gap(agg, agg_scale)
         if gap:
             self.last_metrics = {**self.last_metrics, **gap}
-        if _dist_on(self.group):
-            dist.barrier(group=self.group)
+        self._barrier(f"s3_written/{self._n}")
         host = torch.zeros(self.layout.total)
         self.layout.from_ndarrays(host, self._load(down))
         self._x_dev = host.to(self.device)
-        if _dist_on(self.group):
-            dist.barrier(group=self.group)
+        self._barrier(f"s3_read/{self._n}")
         self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
 
 
@@ -381,9 +416,17 @@ class NvlRoundBackend(RoundBackend):
         self._cb_add(params)
         self.fed.add_client(params, weight)
 
-    def finish_round(self, server_round: int) -> None:
-        self.fed.finish_round(server_round)
+    def finish_round(self, server_round: int, alive: list[int] | None = None) -> None:
+        self.fed.finish_round(server_round, alive=alive)
         self.last_metrics = {}
+
+    def status(self) -> int:
+        """Sticky status of the round kernel (synchronises): 0 = every participant took part; bit t = participant t (index into the
+        ``alive`` list of the launch) missed the start barrier -> the kernel ABORTED and nothing was modified; bit 8+t = left mid-kernel."""
+        st = self.fed.check_status()
+        if st:
+            self.fed.clear_status()
+        return st
 
     def _pg_sq(self) -> float | None:
         n = self.last_metrics.get("server/l2_norm_pseudo_gradient")
@@ -393,7 +436,7 @@ class NvlRoundBackend(RoundBackend):
         """Norm by-products of the last round's kernel (+ the noise-scale estimate): a tiny host read, done after
         the round's device work instead of inside it."""
         if self.track_norms or self.strategy.metrics_callback is not None:
-            self.last_metrics = self.fed.round_norms(self.group)
+            self.last_metrics = self.fed.round_norms(self.group, ctl=self.ctl)
         return super().collect_metrics()
 
     def global_params(self) -> torch.Tensor:
@@ -406,8 +449,13 @@ class NvlRoundBackend(RoundBackend):
         """Full-length server moments. Each rank only maintains its shard, so the shards are
         stitched with one all-reduce of zero-padded copies (checkpoint path, not the hot path)."""
         out = []
-        for full in self.fed.full_moments():
-            if full is not None and self.world_size > 1 and _dist_on(self.group):
+        degraded = self.ctl is not None and bool(self.ctl.dead)
+        for j, full in enumerate(self.fed.full_moments()):
+            if full is not None and degraded:      # survivors only, through the host control plane (adopted shards included)
+                full = self.fed.add_orphans(full, j)
+                parts = self.ctl.gather(f"rb/moments/{j}", full.cpu())
+                full = sum(parts[r] for r in sorted(parts)).to(self.device)
+            elif full is not None and self.world_size > 1 and _dist_on(self.group):
                 dist.all_reduce(full, group=self.group)
             out.append(full)
         return out[0], out[1]

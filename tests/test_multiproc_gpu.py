@@ -128,3 +128,42 @@ def test_nvls_multimem_paths_match_p2p(tmp_path):
                 assert rel < 2e-3, (a, rel)
             if rank == 0: print('RESULT_OK nvls == p2p')
     """, 29545, env={"PB_NVLS_MIN_WORLD": "2"})
+
+
+@pytest.mark.parametrize("kind", ["kill"])
+def test_rank_killed_mid_round_nvl_round_completes_over_survivors(tmp_path, kind):
+    """2 GPUs, comm_stack.nvl: rank 1 is SIGKILLed while it trains in round 2. Rank 0 rules it out (heartbeat), runs the fused round
+    kernel over the survivors (subset control pages, P2P path, the dead rank's server shard adopted), counts the lost clients as
+    failures and finishes round 3 alone. Started with photon_b200.launch (torchrun would kill the survivor too)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = tmp_path / "run.py"
+    script.write_text("import os, sys, math, torch, torch.distributed as dist\n" f"sys.path.insert(0, {str(ROOT)!r})\n" f"TINY = {TINY!r}\n" + textwrap.dedent(f"""
+        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+        from photon_b200.config import compose
+        from photon_b200.federation import FederationRuntime
+        from photon_b200.server_app import run_server
+        rank = dist.get_rank(); dev = torch.device('cuda', rank)
+        cfg = compose(TINY + ['run_uuid=ftgpu', 'fl.n_total_clients=4', 'fl.n_clients_per_round=4', 'fl.n_rounds=3', 'fl.accept_failures_cnt=4',
+                              'fl.strategy_name=fedadam', 'fl.strategy_kwargs={{eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}}',
+                              'dataset.train.root_local=synthetic://c', 'photon.comm_stack.shm=false', 'photon.comm_stack.nvl=true',
+                              'photon.liveness_timeout_s=3', 'photon.kernel_peer_timeout_s=5',
+                              'fl.fault_injection={{round: 2, rank: 1, kind: {kind}}}'])
+        rt = FederationRuntime(cfg, device=dev, rank=rank, world_size=2)
+        h = run_server(cfg, runtime=rt)
+        if rank == 0:
+            fit = h.metrics_distributed_fit
+            fails = dict(fit['server/n_failures'])
+            assert fails[1] == 0 and fails[2] >= 1 and fails[3] == 0, fails
+            assert 'server/round_ignored' not in fit
+            assert [r for r, _ in fit['server/l2_norm_pseudo_gradient']] == [1, 2, 3]
+            assert dict(fit['server/n_nodes'])[3] == 1 and rt.alive_ranks == [0]
+            x = rt.round_backend.global_params()
+            assert bool(torch.isfinite(x).all()) and torch.equal(rt.round_backend.global_shadow(), x.to(torch.bfloat16))
+            print('RESULT_OK survivors', rt.alive_ranks)
+        os._exit(0)
+    """))
+    out = subprocess.run([sys.executable, "-m", "photon_b200.launch", "--nproc", "2", "--master-port", str(_free_port()), str(script)],
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), cwd=str(ROOT))
+    assert out.returncode == 0 and "RESULT_OK survivors [0]" in out.stdout, out.stdout[-3000:] + out.stderr[-4000:]
