@@ -1,4 +1,5 @@
 import json
+from pathlib import Path
 import math
 
 import torch
@@ -96,3 +97,44 @@ def test_gauntlet_sample_size_weightings():
 
     with pytest.raises(ValueError):
         EvalGauntlet({"weighting": "BOGUS"})
+
+
+def test_lighteval_task_list_runner_scores_local_datasets(tmp_path):
+    """The reference's ``conf/lighteval/*.txt`` lists run offline against local jsonl datasets: multiple-choice by length-normalised
+    log-likelihood, generative by normalised exact match, ifeval reported as skipped, missing datasets never silently scored."""
+    import json
+
+    import torch
+
+    from photon_b200.eval.lighteval_runner import parse_task_list, run_task_list
+
+    conf = Path(__file__).resolve().parents[1] / "photon_b200" / "conf" / "lighteval"
+    entries = parse_task_list(conf / "smollm2_instruct.txt")
+    assert entries[0] == {"suite": "extended", "task": "ifeval", "num_fewshot": 0, "truncate_fewshot": False}
+    assert {"hellaswag", "arc", "piqa", "gsm8k"} <= {e["task"] for e in entries}
+
+    class Tok:       # bytes-as-tokens tokenizer (deterministic, invertible)
+        eos_token_id = None
+
+        def encode(self, text):
+            return list(text.encode())
+
+        def decode(self, ids):
+            return bytes(ids).decode(errors="ignore")
+
+    def logits_fn(ids):   # a "model" that always continues with the byte after the current one in "abcdefgh..." order
+        B, S = ids.shape
+        out = torch.full((B, S, 256), -10.0)
+        out[torch.arange(B)[:, None], torch.arange(S)[None, :], (ids + 1) % 256] = 10.0
+        return out
+
+    (tmp_path / "piqa.jsonl").write_text("\n".join(json.dumps(r) for r in [
+        {"query": "a", "choices": ["bcd", "zzz"], "gold": 0}, {"query": "x", "choices": ["qqq", "yz{"], "gold": 1}]))
+    (tmp_path / "trivia_qa.jsonl").write_text(json.dumps({"context": "ab", "answer": "cde", "aliases": []}))
+    tasks = tmp_path / "tasks.txt"
+    tasks.write_text("custom|piqa|0|1\ncustom|trivia_qa|0|1\ncustom|hellaswag|0|1\nextended|ifeval|0|0\n")
+    res = run_task_list(tasks, logits_fn, Tok(), 64, tmp_path)
+    assert res["custom|piqa|0"]["acc_norm"] == 1.0 and res["custom|piqa|0"]["n_samples"] == 2.0
+    assert "status" in res["custom|hellaswag|0"] and "skipped" in res["custom|hellaswag|0"]["status"]      # no local dataset
+    assert "skipped" in res["extended|ifeval|0"]["status"]
+    assert res["all"]["n_tasks_scored"] >= 1
