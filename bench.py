@@ -241,12 +241,18 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
         raise SystemExit(f"bench round had failed clients: {failed[0].status.message}")
     e2e_s, _ = env.walled(lambda: one_round(3))
     clk.stop()
-    # the round exchange alone (aggregate + server optimizer + broadcast), device-timed on a freshly filled accumulator
-    rt.round_backend.begin_round()
-    if rt.is_leader:
-        rt.round_backend.add_client(rt.trainer.state.flat.params, 1.0)
-    agg_ms, _ = env.timed(lambda: rt.finish_round(4))
-    (dev_max, e2e_max, agg_max), (dev_min, _, agg_min) = env.reduce([dev_ms, e2e_s, agg_ms])
+    # the round exchange alone (aggregate + server optimizer + broadcast) on a freshly filled accumulator: device time of the
+    # transport's launch, and wall clock of the whole public call (adds the host-side status agreement of the control plane)
+    def fill() -> None:
+        rt.round_backend.begin_round()
+        if rt.is_leader:
+            rt.round_backend.add_client(rt.trainer.state.flat.params, 1.0)
+
+    fill()
+    agg_ms, _ = env.timed(lambda: rt.round_backend.finish_round(4))
+    fill()
+    agg_host_s, _ = env.walled(lambda: rt.finish_round(5))
+    (dev_max, e2e_max, agg_max, agg_host_max), (dev_min, _, agg_min, _) = env.reduce([dev_ms, e2e_s, agg_ms, agg_host_s])
     total = rt.layout.total
     n_srv = {"fedavg": 0, "fedadam": 2}[args.server]
     if env.world == 1:      # HBM roofline: read the client sum + x (+ moments), write x fp32 + bf16 (+ moments)
@@ -255,7 +261,7 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
         roof_ms = total * ((env.world - 1) / env.world) * (4 + 4 + 2) / (NVLINK_PEER_GBS * 1e9) * 1e3
     mcfg = rt.trainer.model_cfg
     out = dict(dev_ms=dev_max, dev_ms_min=dev_min, e2e_s=e2e_max, agg_ms=agg_max, agg_ms_min=agg_min, agg_roofline_ms=roof_ms,
-               launches=int(launches), clocks=clk.summary(), tokens=n_clients * K * LOCAL_BATCH * SEQ,
+               agg_host_ms=agg_host_max * 1e3, launches=int(launches), clocks=clk.summary(), tokens=n_clients * K * LOCAL_BATCH * SEQ,
                flops_per_token=float(mcfg.flops_per_token(SEQ)), optimizer=str(rt.cfg["llm_config"]["optimizer"]["name"]),
                comm_stack=rt.round_backend.name, microbatch=int(getattr(rt.trainer, "_auto_mb", None) or rt.trainer.microbatch),
                clients_per_node=n_clients // rt.n_nodes, gpus_per_client=gpc, n_clients=n_clients,
@@ -377,6 +383,7 @@ def main() -> None:
                        "timed_region": "K optimizer steps" if args.mode == "ddp" else "one full round: K local steps x clients + aggregate + server-opt + broadcast"},
             exch: r["agg_ms"], exch.replace("_ms", "_roofline_ms"): r["agg_roofline_ms"],
             exch.replace("_ms", "_roofline_fraction"): (r["agg_roofline_ms"] / r["agg_ms"]) if r["agg_ms"] > 0 else None,
+            **({"round_exchange_wall_ms_incl_host_agreement": r["agg_host_ms"]} if "agg_host_ms" in r else {}),
             "rank_dev_ms": {"min": r["dev_ms_min"], "max": r["dev_ms"], "spread_pct": 100.0 * (r["dev_ms"] - r["dev_ms_min"]) / r["dev_ms"]},
             "mfu_of_measured_bf16_peak": value / world * r["flops_per_token"] / peak["bf16_flops"],
             "clocks": r["clocks"],
