@@ -153,6 +153,34 @@ void gemm_fp8(const Tensor& a, const Tensor& b, Tensor& d, int a_mn, int b_mn, i
   pb::gemm_launch(g, stream_of(a));
   g_launches += 1;
 }
+// block-scaled MXFP8: quantise a bf16 matrix (rows padded to `rblk` 128-row blocks in the scale array) / multiply
+std::vector<Tensor> mx_quantize(const Tensor& x, int64_t rblk) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) % 128 == 0, "mx_quantize expects [R,K] with K a multiple of 128");
+  const int64_t R = x.size(0), K = x.size(1);
+  if (rblk <= 0) rblk = (R + 127) / 128;
+  TORCH_CHECK(rblk * 128 >= R, "rblk too small");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto q = torch::empty({R, K}, x.options().dtype(at::kByte));
+  auto sf = torch::zeros({K / 128, rblk, 512}, x.options().dtype(at::kByte));
+  pb::mx_quantize(x.data_ptr(), x.stride(0), q.data_ptr(), sf.data_ptr(), R, int(K), int(rblk), stream_of(x));
+  g_launches += 1;
+  return {q, sf};
+}
+void gemm_mxfp8(const Tensor& a8, const Tensor& b8, Tensor& d, const Tensor& sfa, const Tensor& sfb, const c10::optional<Tensor>& bias) {
+  TORCH_CHECK(is_byte(a8) && is_byte(b8) && a8.is_contiguous() && b8.is_contiguous(), "gemm_mxfp8 operands must be contiguous 1-byte matrices");
+  check_bf16(d, "d");
+  const int M = int(a8.size(0)), K = int(a8.size(1)), N = int(b8.size(0));
+  TORCH_CHECK(b8.size(1) == K && d.size(0) == M && d.size(1) == N && d.stride(1) == 1, "gemm_mxfp8: shape mismatch");
+  TORCH_CHECK(sfa.is_contiguous() && sfa.numel() == int64_t(K / 128) * ((M + 127) / 128) * 512, "sfa must be [K/128][ceil(M/128)][512]");
+  TORCH_CHECK(sfb.is_contiguous() && sfb.numel() == int64_t(K / 128) * (2 * ((N + 255) / 256)) * 512, "sfb must be [K/128][2*ceil(N/256)][512]");
+  if (bias.has_value()) check_f32(*bias, "bias");
+  c10::cuda::CUDAGuard guard(a8.device());
+  pb::gemm_mxfp8_launch(a8.data_ptr(), b8.data_ptr(), d.data_ptr(), sfa.data_ptr(), sfb.data_ptr(),
+                        bias.has_value() ? bias->data_ptr<float>() : nullptr, M, N, K, d.stride(0),
+                        at::cuda::getCurrentDeviceProperties()->multiProcessorCount, stream_of(a8));
+  g_launches += 1;
+}
 void layernorm_fwd_q8(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta, Tensor& y8, Tensor& mean, Tensor& rstd,
                       double eps, Tensor& meta, int role) {
   check_bf16(x, "x");
@@ -528,6 +556,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("d2") = py::none(), py::arg("accumulate") = false, py::arg("alpha") = 1.0, py::arg("cluster") = 0,
         py::arg("d8") = py::none(), py::arg("role_out") = -1);
   m.def("layernorm_fwd_q8", &layernorm_fwd_q8);
+  m.def("mx_quantize", &mx_quantize, py::arg("x"), py::arg("rblk") = 0);
+  m.def("gemm_mxfp8", &gemm_mxfp8, py::arg("a8"), py::arg("b8"), py::arg("d"), py::arg("sfa"), py::arg("sfb"), py::arg("bias") = py::none());
   m.def("colsum_quant", &colsum_quant, py::arg("dy"), py::arg("out_sum") = py::none(), py::arg("y8") = py::none(), py::arg("fmt") = 1,
         py::arg("meta") = py::none(), py::arg("role") = -1);
   m.def("fp8_quantize_segments", &fp8_quantize_segments);

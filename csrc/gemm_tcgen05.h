@@ -46,6 +46,13 @@ struct GemmArgs {
 void gemm_launch(const GemmArgs& g, cudaStream_t stream);
 void gemm_bf16_launch(const GemmArgs& g, cudaStream_t stream);   // same entry (kept for callers that predate fp8)
 
+// ---- block-scaled MXFP8 (gemm_mxfp8.cu): E4M3 elements + one E8M0 scale per 32 K-elements of every row, scales applied in the tensor core
+// x [R,K] bf16 -> q8 [R,K] E4M3, sf [K/128][rblk][512] scale atoms (rblk >= ceil(R/128); rows beyond R must be pre-zeroed)
+void mx_quantize(const void* x_bf16, long long ld, void* q8, void* sf, long long R, int K, int rblk, cudaStream_t st);
+// D[M,N] bf16 = (A.*SFA)[M,K] (B.*SFB)[N,K]^T (+ bias); sfa [K/128][ceil(M/128)][512], sfb [K/128][2*ceil(N/256)][512]
+void gemm_mxfp8_launch(const void* A, const void* B, void* D, const void* sfa, const void* sfb, const float* bias, int M, int N, int K,
+                       long long ldd, int num_sms, cudaStream_t stream);
+
 CUtensorMap make_tmap_2d(const void* ptr, int elem_bytes, bool is_float32, uint64_t inner, uint64_t outer,
                          uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer);
 

@@ -115,6 +115,21 @@ def gemm_fp8(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, meta: torch.Te
     return out
 
 
+def mx_quantize(x: torch.Tensor, row_blocks: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    """bf16 ``[R,K]`` → (E4M3 ``[R,K]`` uint8, E8M0 scale atoms ``[K/128, row_blocks, 512]`` uint8): OCP MXFP8, one power-of-two scale
+    per 32 consecutive K elements of a row, stored in the layout ``tcgen05.mma ... block_scale`` reads from TMEM."""
+    q, sf = ext().mx_quantize(x, int(row_blocks))
+    return q, sf
+
+
+def gemm_mxfp8(a8: torch.Tensor, b8: torch.Tensor, out: torch.Tensor, sfa: torch.Tensor, sfb: torch.Tensor,
+               bias: torch.Tensor | None = None) -> torch.Tensor:
+    """``out[M,N] = (A ⊙ SFA) @ (B ⊙ SFB)^T (+ bias)`` with the block scales applied inside the tensor core
+    (``tcgen05.mma kind::mxf8f6f4.block_scale``). ``sfb`` needs ``2·ceil(N/256)`` row blocks (``mx_quantize(w, 2 * ceil(N/256))``)."""
+    ext().gemm_mxfp8(a8, b8, out, sfa, sfb, bias)
+    return out
+
+
 def layernorm_fwd_q8(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, y8: torch.Tensor, mean: torch.Tensor,
                      rstd: torch.Tensor, eps: float, meta: torch.Tensor, role: int) -> torch.Tensor:
     """LayerNorm whose only output is the E4M3 tensor the next GEMM reads (scaled by ``scale[role]``, ``amax[role]`` updated)."""
