@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -482,6 +483,10 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
   a.sign = sign_compat ? 1.0f : -1.0f;
   a.acc_mc = reinterpret_cast<const float*>(acc_mc);   // NVLS multicast addresses (0 = P2P loops)
   a.xg_mc = reinterpret_cast<float*>(xg_mc);
+  {
+    static const int walk = [] { const char* e = std::getenv("PB_ROUND_WALK"); return e ? std::atoi(e) : 0; }();
+    a.walk = walk;
+  }
   if (seg_bounds.has_value() && seg_sums.has_value()) {
     TORCH_CHECK(seg_bounds->is_cuda() && seg_bounds->scalar_type() == at::kLong && seg_bounds->is_contiguous() && seg_bounds->numel() >= 2,
                 "seg_bounds must be a contiguous int64 device tensor with n_seg + 1 entries");

@@ -227,14 +227,25 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
   };
   if (!skip) {
     const long long u_lo = a.lo / (4 * UNIT4), u_hi = (a.hi + 4 * UNIT4 - 1) / (4 * UNIT4);   // shard bounds are unit-aligned
-    // every BLOCK owns a contiguous run of units; inside it the warps take neighbouring unit pairs (warp w: pairs w, w + W, ...),
-    // so at any moment a block streams one dense ~32 KiB window per plane (DRAM-page friendly) while every warp still walks
-    // the unit space monotonically (what the per-tensor bookkeeping needs)
+    // two walks over the units (a.walk, PB_ROUND_WALK): 0 = grid-stride, 1 = every BLOCK owns a contiguous run with its warps on
+    // neighbouring unit pairs (a dense ~32 KiB window per block). Both keep every warp monotonic in the unit space, which is what
+    // the per-tensor bookkeeping needs.
     const long long W = blockDim.x >> 5;
-    long long per = (u_hi - u_lo + gridDim.x - 1) / gridDim.x;
-    per = (per + 1) & ~1ll;                                      // even: pairs never straddle two blocks
-    const long long bb = u_lo + blockIdx.x * per, ue = (bb + per < u_hi) ? bb + per : u_hi;
-    const long long ub = bb + 2 * (threadIdx.x >> 5);
+    long long ub, ue, ustep;
+    if (a.walk == 0) {
+      // grid-stride over unit PAIRS: at any moment the whole grid streams one dense window (2 KiB per warp, ~2.4 MiB per trip);
+      // every warp still walks the unit space monotonically
+      ub = u_lo + 2 * ((long long)blockIdx.x * W + (threadIdx.x >> 5));
+      ue = u_hi;
+      ustep = 2 * W * gridDim.x;
+    } else {
+      long long per = (u_hi - u_lo + gridDim.x - 1) / gridDim.x;
+      per = (per + 1) & ~1ll;                                      // even: pairs never straddle two blocks
+      const long long bb = u_lo + blockIdx.x * per;
+      ue = (bb + per < u_hi) ? bb + per : u_hi;
+      ub = bb + 2 * (threadIdx.x >> 5);
+      ustep = 2 * W;
+    }
     const long long hi4 = a.hi / 4;
     if (ub < ue && a.seg_bounds) {   // binary search: first tensor whose end is beyond this warp's first unit
       int l = 0, r = a.n_seg - 1;
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, co
       seg = l;
     }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long u = ub; u < ue; u += 2 * W) {   // two units per trip: four 16-byte loads per plane per thread in flight
+    for (long long u = ub; u < ue; u += ustep) {   // two units per trip: four 16-byte loads per plane per thread in flight
       float4 A[4], X[4], M[4], V[4];
       long long idx[4];
 #pragma unroll

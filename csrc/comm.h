@@ -37,6 +37,7 @@ struct FedRoundArgs {
   const long long* seg_bounds;
   int n_seg;
   double* seg_sums;
+  int walk;                     // 0 = grid-stride over unit pairs, 1 = block-contiguous runs (tuning knob PB_ROUND_WALK)
 };
 
 struct AllReduceArgs {

@@ -67,6 +67,8 @@ def test_fed_round_matches_oracle(kind, n):
             torch.testing.assert_close(got[tight], ref.parameters[tight], rtol=2e-5, atol=2e-6)
             # near pg = 0: |d step / d pg| <= eta / tau, and the fp32 weighted mean carries ~1e-7 * (1 + |x|) of rounding noise
             bound = ref.hp.get("eta", 0.0) / ref.hp.get("tau", 1.0) * 1e-6 * (1.0 + ref.parameters[~tight].abs()) + 1e-6
+            if kind == "fedyogi":   # v += (1-b2) pg^2 sign(pg^2 - v) is discontinuous: a 1-ulp pg flips the sign where pg^2 ~ v -> v moves by 2 (1-b2) pg^2
+                bound = bound + 2.0 * ref.hp["eta"] * (1.0 - ref.hp["beta2"])
             assert bool(((got[~tight] - ref.parameters[~tight]).abs() <= bound).all())
             assert torch.equal(fed.global_shadow(g).cpu(), got.to(torch.bfloat16))
         # server moments (each GPU keeps its shard): stitched they equal the oracle's planes
