@@ -62,9 +62,14 @@ def main():
         meta = torch.ones(3, 2, device=dev)
         fp8 = timeit(lambda: ops.gemm_fp8(a8, b8, out, meta, 0, 1, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16,
                                           a_fmt=ops.E5M2 if (amn or bmn) else ops.E4M3, b_fmt=ops.E4M3))
+        mx = None
+        if not amn and not bmn and K % 128 == 0:      # block-scaled MXFP8 (forward layout: both operands K-major)
+            aq, asf = ops.mx_quantize(a)
+            bq, bsf = ops.mx_quantize(b, 2 * ((N + 255) // 256))
+            mx = timeit(lambda: ops.gemm_mxfp8(aq, bq, out, asf, bsf))
         rows.append(dict(op=name, M=M, N=N, K=K, ours_ms=ours, cublas_ms=cub, ours_tflops=fl / ours / 1e9, cublas_tflops=fl / cub / 1e9,
                          frac_of_measured_peak=fl / ours / 1e-3 / pk["bf16_flops"], fp8_ms=fp8, fp8_tflops=fl / fp8 / 1e9,
-                         fp8_speedup_vs_bf16=ours / fp8))
+                         fp8_speedup_vs_bf16=ours / fp8, **({"mxfp8_ms": mx, "mxfp8_tflops": fl / mx / 1e9} if mx else {})))
         print(rows[-1], flush=True)
     # memory-bound kernels
     d = 768

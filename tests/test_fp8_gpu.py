@@ -279,3 +279,37 @@ def test_trainer_amp_fp8_loss_goes_down():
     assert loss[-1] < 0.6 * loss[0], loss
     assert tr.state_dict()["state"]["fp8"]["meta"].shape[0] == 3
     tr.close()
+
+
+def _mx_dequant(q, sf, R):
+    """E4M3 data x E8M0 scale atoms [K/128][rblk][512] -> fp32 (the layout ops.mx_quantize documents)."""
+    G = q.shape[1] // 32
+    r = torch.arange(R, device=q.device)[:, None].expand(R, G)
+    g = torch.arange(G, device=q.device)[None, :].expand(R, G)
+    s = sf[g // 4, r // 128, (r % 32) * 16 + ((r // 32) % 4) * 4 + (g % 4)]
+    return q.view(E4M3).float() * torch.exp2(s.float() - 127).repeat_interleave(32, dim=1)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (640, 776, 1152), (2048, 2304, 768)])
+def test_gemm_mxfp8_block_scaled(M, N, K):
+    """OCP MXFP8 (one E8M0 scale per 32 K-elements of every row of A and B, applied inside tcgen05.mma ... block_scale):
+    quantiser and GEMM against the de-quantise-then-multiply oracle; rows of wildly different magnitude keep their precision."""
+    from photon_b200 import ops
+
+    x = (torch.randn(M, K, device=_dev()) * torch.exp(2 * torch.randn(M, 1, device=_dev()))).bfloat16()   # per-row magnitudes over ~4 decades
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    xq, xsf = ops.mx_quantize(x)
+    wq, wsf = ops.mx_quantize(w, 2 * ((N + 255) // 256))
+    # the quantiser itself: power-of-two scale = 2^(floor(log2 amax) - 8) per 32-block, saturating E4M3 cast
+    blocks = x.float().view(M, K // 32, 32)
+    amax = blocks.abs().amax(-1)
+    e = torch.where(amax > 0, torch.floor(torch.log2(amax)) - 8, torch.full_like(amax, -127.0))
+    want_q = (blocks * torch.exp2(-e)[..., None]).clamp(-448, 448).to(E4M3).view(M, K)
+    assert (xq.view(E4M3).float() != want_q.float()).float().mean().item() < 1e-4
+    bias = torch.randn(N, device=_dev())
+    out = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    ops.gemm_mxfp8(xq, wq, out, xsf, wsf, bias)
+    ref = _mx_dequant(xq, xsf, M) @ _mx_dequant(wq, wsf, N).t() + bias
+    _close(out, ref, 1e-2, 1e-2 * ref.abs().max().item() / 8, "mxfp8 gemm")
+    full = x.float() @ w.float().t() + bias
+    assert ((out.float() - full).norm() / full.norm()).item() < 0.06       # MXFP8 quantisation noise, not kernel error
