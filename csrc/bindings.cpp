@@ -463,7 +463,8 @@ pb::CommCtl make_ctl(const std::vector<int64_t>& ctl_ptrs, int rank) {
 void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& acc_ptrs,
                const std::vector<int64_t>& xg_ptrs, const std::vector<int64_t>& xs_ptrs, int64_t m_ptr, int64_t v_ptr, int64_t lo, int64_t hi, int64_t total,
                int kind, double avg_scale, double lr, double mu, double eta, double beta1, double beta2, double tau, int64_t round_t,
-               bool sign_compat, int64_t acc_mc, int64_t xg_mc, const c10::optional<Tensor>& seg_bounds, c10::optional<Tensor> seg_sums) {
+               bool sign_compat, int64_t acc_mc, int64_t xg_mc, const c10::optional<Tensor>& seg_bounds, c10::optional<Tensor> seg_sums,
+               double wsum, bool zero_seg_sums) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   pb::CommCtl c = make_ctl(ctl_ptrs, rank);
   pb::FedRoundArgs a{};
@@ -483,6 +484,9 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
   a.sign = sign_compat ? 1.0f : -1.0f;
   a.acc_mc = reinterpret_cast<const float*>(acc_mc);   // NVLS multicast addresses (0 = P2P loops)
   a.xg_mc = reinterpret_cast<float*>(xg_mc);
+  a.publish_wsum = wsum >= 0.0 ? 1 : 0;        // negative = the page was filled by set_wsum before (legacy callers)
+  a.wsum = float(wsum >= 0.0 ? wsum : 0.0);
+  a.zero_seg_sums = zero_seg_sums ? 1 : 0;
   {
     static const int walk = [] { const char* e = std::getenv("PB_ROUND_WALK"); return e ? std::atoi(e) : 0; }();
     a.walk = walk;
@@ -593,7 +597,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("xg_ptrs"), py::arg("xs_ptrs"), py::arg("m_ptr"), py::arg("v_ptr"), py::arg("lo"), py::arg("hi"), py::arg("total"),
         py::arg("kind"), py::arg("avg_scale"), py::arg("lr"), py::arg("mu"), py::arg("eta"), py::arg("beta1"), py::arg("beta2"),
         py::arg("tau"), py::arg("round_t"), py::arg("sign_compat"), py::arg("acc_mc") = 0, py::arg("xg_mc") = 0,
-        py::arg("seg_bounds") = py::none(), py::arg("seg_sums") = py::none());
+        py::arg("seg_bounds") = py::none(), py::arg("seg_sums") = py::none(), py::arg("wsum") = -1.0, py::arg("zero_seg_sums") = false);
   m.def("set_comm_timeout_ms", [](long long ms) { g_comm_timeout_ms = ms < 0 ? 0 : ms; });
   m.def("comm_timeout_ms", []() { return g_comm_timeout_ms.load(); });
   m.def("ctl_status_word_offset", &pb::ctl_status_word_offset);

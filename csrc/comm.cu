@@ -59,13 +59,18 @@ __device__ __forceinline__ bool wait_flag_sys(const uint32_t* flag, uint32_t epo
 // c.timeout_ns: nothing has been touched yet, the kernel returns immediately (a clean abort), the missing peers are
 // recorded as a sticky bit mask in this rank's control page (CP_STATUS) for the host watchdog, and CP_ABORT holds the epoch.
 // A dead rank therefore turns into an aborted round on the survivors instead of an endless spin.
-__device__ __forceinline__ bool grid_peer_barrier_start(const CommCtl& c, uint32_t epoch) {
+__device__ __forceinline__ bool grid_peer_barrier_start(const CommCtl& c, uint32_t epoch, const float* publish_wsum = nullptr,
+                                                        double* zero_buf = nullptr, int zero_n = 0) {
   uint32_t* mine = c.ctl[c.rank];
   __shared__ uint32_t s_abort;
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) s_abort = 0;
+    // work that must be ordered before the grid starts / before peers read this rank's page: zero the per-tensor accumulators,
+    // publish this rank's client-weight sum (saves two tiny launches per round)
+    for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_buf[i] = 0.0;
     __syncthreads();
     if (threadIdx.x < c.n) {
+      if (publish_wsum) mine[CP_WSUM] = __float_as_uint(*publish_wsum);   // released by the flag store below (same thread)
       st_release_sys(c.ctl[threadIdx.x] + CP_START + c.rank, epoch);                 // tell peer t "rank is here"
       if (!wait_flag_sys(mine + CP_START + threadIdx.x, epoch, c.timeout_ns)) {       // wait for peer t
         atomicOr(mine + CP_STATUS, 1u << threadIdx.x);
@@ -127,7 +132,9 @@ __device__ __forceinline__ void peer_barrier_end(const CommCtl& c, uint32_t epoc
 constexpr int UNIT4 = 64;   // float4 per unit
 
 __global__ void __launch_bounds__(512) fed_round_kernel(const FedRoundArgs a, const CommCtl c, const uint32_t epoch) {
-  if (!grid_peer_barrier_start(c, epoch)) return;
+  if (!grid_peer_barrier_start(c, epoch, a.publish_wsum ? &a.wsum : nullptr, a.zero_seg_sums ? a.seg_sums : nullptr,
+                               a.zero_seg_sums && a.seg_sums ? 5 * a.n_seg : 0))
+    return;
 
   // total client weight = sum over ranks (each rank published its own before the launch)
   float wtot = 0.f;

@@ -37,6 +37,9 @@ struct FedRoundArgs {
   const long long* seg_bounds;
   int n_seg;
   double* seg_sums;
+  float wsum;                   // this rank's sum of client weights, published to its control page by the kernel when publish_wsum
+  int publish_wsum;
+  int zero_seg_sums;            // zero seg_sums inside the kernel (first launch of a round)
   int walk;                     // 0 = grid-stride over unit pairs, 1 = block-contiguous runs (tuning knob PB_ROUND_WALK)
 };
 

@@ -130,20 +130,18 @@ class NvlFedRound:
         degraded = len(ranks) < world
         if degraded and ar.single:
             raise NotImplementedError("masked rounds are a multi-process feature")
-        for i in range(self.n_local):
-            rank = i if ar.single else ar.rank
-            ext.set_wsum(ar.ctl_ptrs()[rank], ar.devices[i if ar.single else 0], self._wsum[i], True)
-            self._seg_sums[i].zero_()
         sub = (lambda xs: [xs[r] for r in ranks]) if degraded else (lambda xs: xs)
         acc_mc, xg_mc = (0, 0) if degraded else (ar.mc_ptr("acc"), ar.mc_ptr("xg"))
         shadow = ar.ptrs("xs") if self.has_shadow else []
 
-        def launch(i: int, rank: int, lo: int, hi: int, m: torch.Tensor | None, v: torch.Tensor | None, epoch: int) -> None:
+        def launch(i: int, rank: int, lo: int, hi: int, m: torch.Tensor | None, v: torch.Tensor | None, epoch: int, first: bool = True) -> None:
+            # ONE launch per round and GPU: the kernel itself publishes this rank's client-weight sum and zeroes the per-tensor
+            # accumulators before its start barrier
             ext.fed_round(sub(ar.ctl_ptrs()), ranks.index(rank), ar.devices[i if ar.single else 0], epoch, sub(ar.ptrs("acc")), sub(ar.ptrs("xg")),
                           sub(shadow) if shadow else [], m.data_ptr() - 4 * lo if m is not None else 0, v.data_ptr() - 4 * lo if v is not None else 0,
                           lo, hi, self.total, kind, st.scaling_factor(), hp.get("lr", 1.0), hp.get("mu", 0.0), hp.get("eta", 0.0),
                           hp.get("beta1", 0.9), hp.get("beta2", 0.99), hp.get("tau", 1e-3), int(server_round), bool(st.sign_compat),
-                          acc_mc, xg_mc, self._seg_bounds[i], self._seg_sums[i])
+                          acc_mc, xg_mc, self._seg_bounds[i], self._seg_sums[i], float(self._wsum[i]), bool(first))
 
         epoch = ar.next_epoch()
         for i in range(self.n_local):      # every participant updates the shard it owns
@@ -157,9 +155,9 @@ class NvlFedRound:
                 epoch = ar.next_epoch()
                 if ar.rank == adopter:
                     m, v = self._orphan_moments(d, hi - lo)
-                    launch(0, ar.rank, lo, hi, m, v, epoch)
+                    launch(0, ar.rank, lo, hi, m, v, epoch, first=False)
                 else:
-                    launch(0, ar.rank, lo, lo, None, None, epoch)
+                    launch(0, ar.rank, lo, lo, None, None, epoch, first=False)
 
     def _orphan_moments(self, dead_rank: int, n: int) -> tuple[torch.Tensor | None, torch.Tensor | None]:
         if dead_rank not in self._orphans:
