@@ -254,7 +254,7 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
     agg_host_s, _ = env.walled(lambda: rt.finish_round(5))
     (dev_max, e2e_max, agg_max, agg_host_max), (dev_min, _, agg_min, _) = env.reduce([dev_ms, e2e_s, agg_ms, agg_host_s])
     total = rt.layout.total
-    n_srv = {"fedavg": 0, "fedadam": 2}[args.server]
+    n_srv = int(rt.strategy.n_moments)     # server moment planes the kernel reads and writes (Nesterov: 1 even with mu = 0, FedAdam: 2)
     if env.world == 1:      # HBM roofline: read the client sum + x (+ moments), write x fp32 + bf16 (+ moments)
         roof_ms = total * (4 + 4 + 4 + 2 + 8 * n_srv) / measured_peaks()["hbm_bytes_per_s"] * 1e3
     else:                   # NVLink roofline: (N-1)/N of the fp32 plane in (reduce) and out again (fp32 + bf16 broadcast), per direction
