@@ -24,6 +24,8 @@ PICKS = [
     ("gemm_tcgen05.cu.o", r"gemm_kernel<0, 0, 7, 2, 1>", "gemm_fp8_fwd_gelu_q8_2cta"),
     ("gemm_tcgen05.cu.o", r"gemm_kernel<0, 1, 6, 2, 1>", "gemm_fp8_dgrad_mul_2cta"),
     ("gemm_tcgen05.cu.o", r"gemm_kernel<1, 1, 4, 2, 1>", "gemm_fp8_wgrad_f32_2cta"),
+    ("gemm_mxfp8.cu.o", r"gemm_mx_kernel", "gemm_mxfp8_block_scaled"),
+    ("gemm_mxfp8.cu.o", r"mx_quantize_kernel", "mx_quantize"),
     ("attention_tcgen05.cu.o", r"attn_fwd_kernel<64", "attention_fwd_d64"),
     ("attention_tcgen05.cu.o", r"attn_bwd_kernel<64", "attention_bwd_d64"),
     ("attention_tcgen05.cu.o", r"attn_fwd_kernel<128", "attention_fwd_d128"),
@@ -35,7 +37,7 @@ PICKS = [
     ("fused_ops.cu.o", r"optim_kernel", "fused_optimizer"),
     ("fused_ops.cu.o", r"ce_kernel", "cross_entropy"),
 ]
-KEY = re.compile(r"\b(UTC[A-Z]*MMA(?:\.[A-Z0-9_]+)*|UTMA[A-Z]+(?:\.[A-Z0-9_]+)*|LDTM(?:\.[A-Z0-9_x]+)*|STTM(?:\.[A-Z0-9_x]+)*|UTCBAR(?:\.[A-Z0-9_]+)*|"
+KEY = re.compile(r"\b(UTC[A-Z]*MMA(?:\.[A-Z0-9_]+)*|UTMA[A-Z]+(?:\.[A-Z0-9_]+)*|LDTM(?:\.[A-Z0-9_x]+)*|STTM(?:\.[A-Z0-9_x]+)*|UTCBAR(?:\.[A-Z0-9_]+)*|UTCCP(?:\.[A-Z0-9_x]+)*|UBLKCP(?:\.[A-Z0-9_]+)*|"
                  r"[A-Z]*MULTIMEM[A-Z.0-9_]*|LDGMC[A-Z.0-9_]*|REDG?MC[A-Z.0-9_]*|STGMC[A-Z.0-9_]*|HMMA[.A-Z0-9_]*|F2FP[.A-Z0-9_]*)")
 
 
