@@ -341,14 +341,30 @@ def main() -> None:
         reference_arm()
         return
     env = Env(args)
-    from photon_b200.utils.hw import measured_peaks
-
     K, W = args.steps, max(args.warmup, 3)
     run = run_ddp if args.mode == "ddp" else run_fed
+    t_ours = time.time()
     r = run(env, args, args.impl, K, W)
+    t_ours = time.time() - t_ours
+
+    def emit(torch_arm) -> None:
+        if env.rank == 0:
+            print(json.dumps(result_line(env, args, r, K, W, torch_arm)), flush=True)
+
     torch_arm = None
     want_torch = args.impl == "ours" and (args.torch_arm == "on" or (args.torch_arm == "auto" and args.model == "mpt-125m"))
     if want_torch:
+        # The stand-in arm must never cost the headline: if it hangs (e.g. one rank failing while the others sit in a collective)
+        # a watchdog prints OUR line without it and ends every rank.
+        import threading
+
+        def bail() -> None:
+            emit({"error": "the stock-PyTorch arm did not finish within its time limit; headline printed without it"})
+            os._exit(0)
+
+        dog = threading.Timer(max(300.0, 12.0 * t_ours), bail)
+        dog.daemon = True
+        dog.start()
         gc.collect()
         env.torch.cuda.empty_cache()
         try:
@@ -358,7 +374,16 @@ def main() -> None:
                          "what": "stock PyTorch ops (cuBLAS, SDPA, ATen, torch optimizer) + the reference's communication pattern, same K and batch"}
         except Exception as e:  # noqa: BLE001 - the stand-in arm must never take the headline down
             torch_arm = {"error": f"{type(e).__name__}: {e}"[:300]}
-    if env.rank == 0:
+        dog.cancel()
+    emit(torch_arm)
+    if env.world > 1:
+        env.dist.destroy_process_group()
+
+
+def result_line(env, args, r: dict, K: int, W: int, torch_arm) -> dict:
+    from photon_b200.utils.hw import measured_peaks
+
+    if True:
         world = env.world
         value = r["tokens"] / (r["dev_ms"] / 1e3)
         peak = measured_peaks()
@@ -396,9 +421,7 @@ def main() -> None:
             if "value" in torch_arm:
                 out["vs_torch_arm"] = value / torch_arm["value"]
                 out["e2e_vs_torch_arm"] = out["e2e"]["value"] / torch_arm["e2e_value"]
-        print(json.dumps(out))
-    if env.world > 1:
-        env.dist.destroy_process_group()
+        return out
 
 
 if __name__ == "__main__":

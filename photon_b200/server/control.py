@@ -33,6 +33,8 @@ class ServerLostError(RuntimeError):
 
 
 class ControlPlane:
+    _instances = 0     # every rank creates its control planes in the same order: the count makes key spaces of successive runtimes disjoint
+
     def __init__(self, rank: int, world_size: int, *, host: str | None = None, port: int | None = None, heartbeat_s: float = 0.5,
                  liveness_timeout_s: float = 20.0, exchange_timeout_s: float = 7200.0, progress_timeout_s: float = 900.0,
                  namespace: str = "photon") -> None:
@@ -44,7 +46,8 @@ class ControlPlane:
         port = int(port or os.environ.get("PHOTON_CONTROL_PORT") or (int(os.environ.get("MASTER_PORT", "29500")) + 101))
         self.store = TCPStore(host, port, world_size=None, is_master=(self.rank == 0), timeout=timedelta(seconds=60), wait_for_workers=False,
                               multi_tenant=True)
-        self.ns = namespace
+        ControlPlane._instances += 1
+        self.ns = f"{namespace}/{ControlPlane._instances}"    # a later runtime in the same job must never read this one's keys
         # a rank whose MAIN thread made no progress for this long stops refreshing its heartbeat: a hung worker (stuck kernel,
         # dead-locked loader) then looks exactly like a dead one (ref: the node manager's per-task time-out)
         self.progress_timeout_s = float(progress_timeout_s)
