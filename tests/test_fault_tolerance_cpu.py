@@ -78,3 +78,63 @@ def test_rank_lost_mid_round_the_federation_goes_on(tmp_path, kind):
         os._exit(0)      # no collective teardown: a peer is gone
     """)
     assert out.returncode == 0 and "OK survivors [0, 1]" in out.stdout, out.stdout[-2500:] + out.stderr[-3500:]
+
+
+def test_control_plane_unit_gather_queue_and_dead_rank_in_one_process():
+    """Three control planes (threads standing in for ranks) over one TCPStore: work-queue indices are unique and dense, ``gather`` is
+    identical on every participant, a participant whose heartbeat stops is ruled out by rank 0 and everybody adopts that verdict."""
+    import threading
+    import time
+
+    import torch
+
+    from photon_b200.server.control import ControlPlane
+
+    port = _free_port()
+    planes = [None] * 3
+
+    def make(r):
+        planes[r] = ControlPlane(r, 3, host="127.0.0.1", port=port, heartbeat_s=0.1, liveness_timeout_s=1.0, namespace="unit")
+
+    ts = [threading.Thread(target=make, args=(r,)) for r in range(3)]
+    [t.start() for t in ts], [t.join() for t in ts]
+    assert all(p is not None for p in planes) and planes[0].alive() == [0, 1, 2]
+    # work queue: every index exactly once
+    q = [p.open_queue("round1") for p in planes]
+    assert len(set(q)) == 1
+    got = []
+    lock = threading.Lock()
+
+    def pull(p):
+        while True:
+            i = p.next_index(q[0])
+            if i >= 10:
+                return
+            with lock:
+                got.append(i)
+
+    ts = [threading.Thread(target=pull, args=(p,)) for p in planes]
+    [t.start() for t in ts], [t.join() for t in ts]
+    assert sorted(got) == list(range(10))
+    # gather / sum: same answer everywhere
+    out = [None] * 3
+
+    def ex(r):
+        out[r] = (planes[r].gather("g", {"rank": r}), planes[r].sum_tensor("s", torch.tensor([float(r + 1)])))
+
+    ts = [threading.Thread(target=ex, args=(r,)) for r in range(3)]
+    [t.start() for t in ts], [t.join() for t in ts]
+    assert all(sorted(o[0]) == [0, 1, 2] and float(o[1]) == 6.0 for o in out)
+    # rank 2 "dies": its heartbeat stops; the next exchange completes over ranks 0 and 1 and both know why
+    planes[2]._stop.set()
+    time.sleep(1.3)
+
+    def ex2(r):
+        out[r] = planes[r].gather("after", r)
+
+    ts = [threading.Thread(target=ex2, args=(r,)) for r in (0, 1)]
+    [t.start() for t in ts], [t.join() for t in ts]
+    assert sorted(out[0]) == [0, 1] and out[0] == out[1]
+    assert planes[0].dead == {2} and planes[1].dead == {2} and planes[1].alive() == [0, 1]
+    for p in planes:
+        p.close()
