@@ -37,7 +37,7 @@ class ControlPlane:
 
     def __init__(self, rank: int, world_size: int, *, host: str | None = None, port: int | None = None, heartbeat_s: float = 0.5,
                  liveness_timeout_s: float = 20.0, exchange_timeout_s: float = 7200.0, progress_timeout_s: float = 900.0,
-                 namespace: str = "photon") -> None:
+                 namespace: str = "photon", instance: int | None = None) -> None:
         from torch.distributed import TCPStore
 
         self.rank, self.world_size = int(rank), int(world_size)
@@ -47,7 +47,9 @@ class ControlPlane:
         self.store = TCPStore(host, port, world_size=None, is_master=(self.rank == 0), timeout=timedelta(seconds=60), wait_for_workers=False,
                               multi_tenant=True)
         ControlPlane._instances += 1
-        self.ns = f"{namespace}/{ControlPlane._instances}"    # a later runtime in the same job must never read this one's keys
+        # a later runtime in the same job must never read this one's keys (``instance``: explicit id when several "ranks" live in
+        # one process, e.g. unit tests)
+        self.ns = f"{namespace}/{ControlPlane._instances if instance is None else instance}"
         # a rank whose MAIN thread made no progress for this long stops refreshing its heartbeat: a hung worker (stuck kernel,
         # dead-locked loader) then looks exactly like a dead one (ref: the node manager's per-task time-out)
         self.progress_timeout_s = float(progress_timeout_s)

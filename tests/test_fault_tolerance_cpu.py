@@ -94,7 +94,7 @@ def test_control_plane_unit_gather_queue_and_dead_rank_in_one_process():
     planes = [None] * 3
 
     def make(r):
-        planes[r] = ControlPlane(r, 3, host="127.0.0.1", port=port, heartbeat_s=0.1, liveness_timeout_s=1.0, namespace="unit")
+        planes[r] = ControlPlane(r, 3, host="127.0.0.1", port=port, heartbeat_s=0.1, liveness_timeout_s=1.0, namespace="unit", instance=1)
 
     ts = [threading.Thread(target=make, args=(r,)) for r in range(3)]
     [t.start() for t in ts], [t.join() for t in ts]
