@@ -25,7 +25,7 @@ def make_batches(n, b, S, vocab, seed):
     return out
 
 
-def run(kernels, batches, steps):
+def run(kernels, batches, steps, precision="amp_bf16", lr=6e-4):
     cfg = MPTConfig()   # MPT-125M
     dev = torch.device("cuda", 0)
 
@@ -36,9 +36,9 @@ def run(kernels, batches, steps):
                 yield {"input_ids": batches[i % len(batches)].pin_memory()}
                 i += 1
 
-    tr = Trainer(cfg, optimizer_cfg=dict(name="adopt", lr=6e-4, betas=[0.9, 0.9999], eps=1e-6, weight_decay=0.0),
+    tr = Trainer(cfg, optimizer_cfg=dict(name="adopt", lr=lr, betas=[0.9, 0.9999], eps=1e-6, weight_decay=0.0),
                  scheduler_cfg=dict(name="cosine_with_warmup", t_warmup="10ba", t_max=f"{steps}ba", alpha_f=0.1), train_loader=Loader(),
-                 global_train_batch_size=16, device_train_microbatch_size=16, precision="amp_bf16", max_duration=f"{steps}ba",
+                 global_train_batch_size=16, device_train_microbatch_size=16, precision=precision, max_duration=f"{steps}ba",
                  grad_clip_norm=1.0, device=dev, kernels=kernels, seed=17)
     tr.fit(f"{steps}ba")
     losses = [float(v) for _, v in tr.loggers[0].data["loss/train/total"]]
@@ -47,7 +47,26 @@ def run(kernels, batches, steps):
     return kind, losses
 
 
+def fp8_parity():
+    """amp_fp8 engine (tcgen05 kind::f8f6f4 GEMMs) vs the bf16 engine: 60 steps from the same weights on the same data, at a
+    learning rate high enough for the loss to move (3e-3): the two curves must fall together."""
+    steps = 60
+    batches = make_batches(steps, 16, 2048, 50368, seed=5)
+    res = {}
+    for name, prec in (("engine_bf16", "amp_bf16"), ("engine_fp8", "amp_fp8")):
+        kind, losses = run({}, batches, steps, precision=prec, lr=3e-3)
+        res[name] = {"backend": kind, "precision": prec, "loss_first": losses[0], "loss_step10": losses[9], "loss_step20": losses[19],
+                     "loss_step30": losses[29], "loss_step45": losses[44], "loss_last": losses[-1]}
+        print(name, json.dumps(res[name]), flush=True)
+    gap = max(abs(res["engine_fp8"][k] - res["engine_bf16"][k]) for k in res["engine_bf16"] if k.startswith("loss"))
+    fell = res["engine_bf16"]["loss_first"] - res["engine_bf16"]["loss_last"]
+    print(json.dumps({"max_loss_gap_fp8_vs_bf16": gap, "bf16_loss_drop": fell, "ok": bool(gap < 0.05 + 0.05 * fell and res["engine_fp8"]["loss_last"] < res["engine_fp8"]["loss_first"])}))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fp8":
+        fp8_parity()
+        return
     steps = 60
     batches = make_batches(steps, 16, 2048, 50368, seed=5)
     res = {}
