@@ -497,25 +497,33 @@ __global__ void set_wsum_kernel(uint32_t* ctl, float w, int zero_sums) {
 
 }  // namespace
 
+static int sm_count(int num_sms) {   // one CTA per SM (co-residency is what makes the in-kernel spins deadlock-free)
+  if (num_sms > 0) return num_sms;
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
 int ctl_sums_word_offset() { return CP_SUMS; }
 int ctl_status_word_offset() { return CP_STATUS; }
 
 void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st) {
   if ((a.lo % 256) || (a.hi % 4)) throw std::runtime_error("fed_round: the shard must start on a 256-element boundary and end on a multiple of 4");
-  fed_round_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch);
+  fed_round_kernel<<<sm_count(num_sms), 512, 0, st>>>(a, c, epoch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("fed_round launch: ") + cudaGetErrorString(e));
 }
 void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st) {
   if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("ddp_allreduce: shard bounds must be multiples of 4");
-  ddp_allreduce_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch);
+  ddp_allreduce_kernel<<<sm_count(num_sms), 512, 0, st>>>(a, c, epoch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_allreduce launch: ") + cudaGetErrorString(e));
   if (out_norm) allreduce_norm_finalize_kernel<<<1, 1, 0, st>>>(c.ctl[c.rank], c.n, out_norm);
 }
 void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st) {
   if ((a.lo % 4) || (a.hi % 4)) throw std::runtime_error("ddp_zero_step: shard bounds must be multiples of 4");
-  ddp_zero_step_kernel<<<num_sms > 0 ? num_sms : 148, 512, 0, st>>>(a, c, epoch, out_norm);
+  ddp_zero_step_kernel<<<sm_count(num_sms), 512, 0, st>>>(a, c, epoch, out_norm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_zero_step launch: ") + cudaGetErrorString(e));
 }

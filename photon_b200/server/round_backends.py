@@ -18,7 +18,7 @@ model reaches the clients — the four ``photon.comm_stack`` options.
 
 All share one interface: ``begin_round`` → ``add_client`` × k → ``finish_round`` →
 ``global_params`` / ``global_shadow`` and produce the same model within fp32 tolerance
-(``tests/test_round_backends.py``).
+(``tests/test_federation_cpu.py::test_transports_agree``; nvl vs ray on GPUs: ``tests/test_multiproc_gpu.py``).
 """
 from __future__ import annotations
 
