@@ -48,7 +48,8 @@ def main():
         b = torch.randn((K, N) if bmn else (N, K), device=dev).to(torch.bfloat16) * 0.05
         f32 = amn and bmn
         out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-        ours = timeit(lambda: ops.gemm(a, b, out, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16))
+        # weight gradients are timed the way the engine issues them: accumulating into the fp32 bucket (split-K + TMA reduce-add)
+        ours = timeit(lambda: ops.gemm(a, b, out, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16, accumulate=bool(f32)))
         A = a.t() if amn else a
         Bt = b if bmn else b.t()
         if f32:
@@ -61,7 +62,7 @@ def main():
         b8 = (b.float().clamp(-400, 400)).to(torch.float8_e4m3fn).view(torch.uint8)
         meta = torch.ones(3, 2, device=dev)
         fp8 = timeit(lambda: ops.gemm_fp8(a8, b8, out, meta, 0, 1, a_mn=bool(amn), b_mn=bool(bmn), epi=ops.EPI_F32 if f32 else ops.EPI_BF16,
-                                          a_fmt=ops.E5M2 if (amn or bmn) else ops.E4M3, b_fmt=ops.E4M3))
+                                          a_fmt=ops.E5M2 if (amn or bmn) else ops.E4M3, b_fmt=ops.E4M3, accumulate=bool(f32)))
         mx = None
         if not amn and not bmn and K % 128 == 0:      # block-scaled MXFP8 (forward layout: both operands K-major)
             aq, asf = ops.mx_quantize(a)
