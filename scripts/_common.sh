@@ -15,8 +15,12 @@ export PHOTON_STRICT_DATA=${PHOTON_STRICT_DATA:-1}
 mkdir -p "$PHOTON_SAVE_PATH"
 if command -v nvidia-smi >/dev/null 2>&1; then N_GPUS=${N_GPUS:-$(nvidia-smi -L | wc -l)}; else N_GPUS=${N_GPUS:-0}; fi
 export APPOINTED_CUDA_DEVICE=${APPOINTED_CUDA_DEVICE:-$(seq -s, 0 $((N_GPUS > 0 ? N_GPUS - 1 : 0)))}
-launch() { # launch <module> : torchrun on GPUs, plain python on CPU
-  if [ "$N_GPUS" -gt 1 ]; then
+launch() { # launch <module> : one rank per GPU, plain python on CPU
+  # PHOTON_FAULT_TOLERANT=1 (default for the federated entry points): ranks started by photon_b200.launch, which — unlike torchrun —
+  # leaves the survivors alone when a rank dies; the control plane then rules the dead rank out and the federation goes on
+  if [ "$N_GPUS" -gt 1 ] && [ "${PHOTON_FAULT_TOLERANT:-1}" = "1" ] && [ "$1" != "photon_b200.centralised_train" ]; then
+    python -m photon_b200.launch --nproc "$N_GPUS" --master-addr 127.0.0.1 --master-port "${MASTER_PORT:-29500}" -m "$1"
+  elif [ "$N_GPUS" -gt 1 ]; then
     python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N_GPUS" --master-addr 127.0.0.1 --master-port "${MASTER_PORT:-29500}" -m "$1"
   else
     python -m "$1"
