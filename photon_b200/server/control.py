@@ -136,13 +136,13 @@ class ControlPlane:
                     return False
             time.sleep(0.00005 if waited < 0.005 else 0.002)   # peers normally arrive within microseconds of each other
 
-    def gather(self, tag: str, obj: Any) -> dict[int, Any]:
+    def gather(self, tag: str, obj: Any, timeout_s: float | None = None) -> dict[int, Any]:
         """Every living rank contributes ``obj``; returns ``{rank: obj}`` for the ranks rank 0 ruled in (identical on every survivor).
         Ranks that died before contributing are added to :attr:`dead`."""
         self.tick()
         key = self._k(self._next_seq(f"x/{tag}"))
         self.store.set(f"{key}/{self.rank}", pickle.dumps(obj))
-        deadline = time.time() + self.exchange_timeout_s
+        deadline = time.time() + (self.exchange_timeout_s if timeout_s is None else float(timeout_s))
         if self.rank == 0:
             included = []
             for r in range(self.world_size):
@@ -150,6 +150,8 @@ class ControlPlane:
                     continue
                 if self._wait_key(f"{key}/{r}", r, deadline):
                     included.append(r)
+                elif timeout_s is not None and self._age(r) < self.liveness_timeout_s:
+                    continue     # a short, best-effort exchange (shutdown): late is not dead
                 else:
                     self.dead.add(r)
                     print(f"[control] rank {r} stopped responding (heartbeat age {self._age(r):.1f} s): marked dead", flush=True)
@@ -182,8 +184,16 @@ class ControlPlane:
         return got[src]
 
     def close(self) -> None:
+        if self.store is None:
+            return
+        try:            # leave together: nobody's heartbeat should find the store gone (rank 0 hosts it and goes last)
+            self.gather("bar/close", None, timeout_s=5.0)
+        except Exception:  # noqa: BLE001
+            pass
         self._stop.set()
         self._thread.join(timeout=2.0)
+        if self.rank == 0:
+            time.sleep(2.0 * self.heartbeat_s)
         self.store = None   # drop the client connection (rank 0: the server socket goes with the last reference)
 
 

@@ -136,5 +136,5 @@ def test_control_plane_unit_gather_queue_and_dead_rank_in_one_process():
     [t.start() for t in ts], [t.join() for t in ts]
     assert sorted(out[0]) == [0, 1] and out[0] == out[1]
     assert planes[0].dead == {2} and planes[1].dead == {2} and planes[1].alive() == [0, 1]
-    for p in planes:
-        p.close()
+    ts = [threading.Thread(target=p.close) for p in planes]
+    [t.start() for t in ts], [t.join() for t in ts]
