@@ -223,8 +223,12 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
     broadcast_parameters_to_nodes(rt, rt.initial_parameters())
     sampled = list(range(n_clients))
 
+    mid = {"ev": None}
+
     def one_round(server_round: int) -> list:
         res = rt.run_clients_fit(server_round, sampled)       # K local steps on each of this rank's clients
+        mid["ev"] = torch.cuda.Event(enable_timing=True)      # this rank's own compute ends here; the round kernel then waits for the slowest peer
+        mid["ev"].record()
         rt.finish_round(server_round)                         # aggregate + server optimizer + broadcast
         return res
 
@@ -234,7 +238,14 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
     if impl == "ours":
         ops.reset_launch_count()
     clk = ClockSampler(env.local, enabled=(env.rank == 0)).start()
-    dev_ms, res = env.timed(lambda: one_round(2))
+    env.flush.zero_()
+    env.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = one_round(2)
+    e1.record()
+    env.sync()
+    dev_ms, own_ms = e0.elapsed_time(e1), e0.elapsed_time(mid["ev"])     # whole round / this rank's local training only
     launches = ops.launch_count() if impl == "ours" else 0
     failed = [r for r in res if r.status.code != 0]
     if failed:
@@ -252,7 +263,7 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
     agg_ms, _ = env.timed(lambda: rt.round_backend.finish_round(4))
     fill()
     agg_host_s, _ = env.walled(lambda: rt.finish_round(5))
-    (dev_max, e2e_max, agg_max, agg_host_max), (dev_min, _, agg_min, _) = env.reduce([dev_ms, e2e_s, agg_ms, agg_host_s])
+    (dev_max, e2e_max, agg_max, agg_host_max, own_max), (dev_min, _, agg_min, _, own_min) = env.reduce([dev_ms, e2e_s, agg_ms, agg_host_s, own_ms])
     total = rt.layout.total
     n_srv = int(rt.strategy.n_moments)     # server moment planes the kernel reads and writes (Nesterov: 1 even with mu = 0, FedAdam: 2)
     if env.world == 1:      # HBM roofline: read the client sum + x (+ moments), write x fp32 + bf16 (+ moments)
@@ -261,7 +272,7 @@ def run_fed(env: Env, args, impl: str, K: int, W: int) -> dict:
         roof_ms = total * ((env.world - 1) / env.world) * (4 + 4 + 2) / (NVLINK_PEER_GBS * 1e9) * 1e3
     mcfg = rt.trainer.model_cfg
     out = dict(dev_ms=dev_max, dev_ms_min=dev_min, e2e_s=e2e_max, agg_ms=agg_max, agg_ms_min=agg_min, agg_roofline_ms=roof_ms,
-               agg_host_ms=agg_host_max * 1e3, launches=int(launches), clocks=clk.summary(), tokens=n_clients * K * LOCAL_BATCH * SEQ,
+               agg_host_ms=agg_host_max * 1e3, own_ms_min=own_min, own_ms_max=own_max, launches=int(launches), clocks=clk.summary(), tokens=n_clients * K * LOCAL_BATCH * SEQ,
                flops_per_token=float(mcfg.flops_per_token(SEQ)), optimizer=str(rt.cfg["llm_config"]["optimizer"]["name"]),
                comm_stack=rt.round_backend.name, microbatch=int(getattr(rt.trainer, "_auto_mb", None) or rt.trainer.microbatch),
                clients_per_node=n_clients // rt.n_nodes, gpus_per_client=gpc, n_clients=n_clients,
@@ -410,6 +421,10 @@ def result_line(env, args, r: dict, K: int, W: int, torch_arm) -> dict:
             exch.replace("_ms", "_roofline_fraction"): (r["agg_roofline_ms"] / r["agg_ms"]) if r["agg_ms"] > 0 else None,
             **({"round_exchange_wall_ms_incl_host_agreement": r["agg_host_ms"]} if "agg_host_ms" in r else {}),
             "rank_dev_ms": {"min": r["dev_ms_min"], "max": r["dev_ms"], "spread_pct": 100.0 * (r["dev_ms"] - r["dev_ms_min"]) / r["dev_ms"]},
+            **({"rank_local_training_ms": {"min": r["own_ms_min"], "max": r["own_ms_max"],
+                                           "straggler_pct": 100.0 * (r["own_ms_max"] - r["own_ms_min"]) / r["own_ms_max"],
+                                           "note": "device time of each rank's own K local steps (before the round kernel's start barrier makes everyone wait for the slowest)"}}
+               if "own_ms_max" in r else {}),
             "mfu_of_measured_bf16_peak": value / world * r["flops_per_token"] / peak["bf16_flops"],
             "clocks": r["clocks"],
             "e2e": {"value": r["tokens"] / r["e2e_s"], "unit": "tokens/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
