@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -483,6 +484,103 @@ __global__ void __launch_bounds__(256) ce_kernel(__nv_bfloat16* __restrict__ log
   }
 }
 
+// Same contract, ONE read of the logits: the whole row (V bf16 = 100 KB for the GPT-NeoX vocabulary) is pulled into shared
+// memory by bulk async copies (cp.async.bulk on an mbarrier), both passes run out of shared memory and only the gradient goes back
+// to HBM — 2 instead of 3 row transfers per row. Two CTAs fit on an SM, so one row's copy overlaps the other's arithmetic.
+__global__ void __launch_bounds__(512) ce_smem_kernel(__nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ targets,
+                                                       int V, float grad_scale, int write_grad, double* __restrict__ stats,
+                                                       float* __restrict__ row_lse, const float* __restrict__ unigram_logp) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];
+  uint4* srow = reinterpret_cast<uint4*>(ce_smem);
+  __shared__ uint64_t bar;
+  __shared__ float sm[16], ss[16];
+  __shared__ int si[16];
+  __shared__ float bm, bs;
+  const long long row = blockIdx.x;
+  __nv_bfloat16* lr = logits + row * ld;
+  const long long tgt = targets[row];
+  const bool valid = tgt >= 0 && tgt < V;
+  const int vec = V / 8;
+  const uint32_t bytes = uint32_t(V) * 2u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(&bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {   // bulk copies of <= 32 KiB, all counted on the one barrier
+      const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ce_smem + off)),
+                   "l"(reinterpret_cast<uint64_t>(reinterpret_cast<const uint8_t*>(lr) + off)), "r"(n), "r"(smem_u32(&bar))
+                   : "memory");
+    }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  float m = -INFINITY, s = 0.f;
+  int am = 0;
+  for (int i = threadIdx.x; i < vec; i += blockDim.x) {
+    float f[8];
+    unpack8(srow[i], f);
+    float cm = f[0];
+    int ci = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (f[k] > cm) cm = f[k], ci = k;
+    if (cm > m) {
+      s *= __expf(m - cm);
+      m = cm;
+      am = i * 8 + ci;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += __expf(f[k] - m);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffff, m, o), os = __shfl_xor_sync(0xffffffff, s, o);
+    const int oi = __shfl_xor_sync(0xffffffff, am, o);
+    const float nm = fmaxf(m, om);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
+    if (om > m || (om == m && oi < am)) am = oi;
+    m = nm;
+  }
+  if (lane == 0) sm[w] = m, ss[w] = s, si[w] = am;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm[0], S = ss[0];
+    int I = si[0];
+    for (int i = 1; i < nw; ++i) {
+      const float nm = fmaxf(M, sm[i]);
+      S = (M == -INFINITY ? 0.f : S * __expf(M - nm)) + (sm[i] == -INFINITY ? 0.f : ss[i] * __expf(sm[i] - nm));
+      if (sm[i] > M || (sm[i] == M && si[i] < I)) I = si[i];
+      M = nm;
+    }
+    bm = M, bs = S;
+    const float lse = M + __logf(S);
+    if (row_lse) row_lse[row] = lse;
+    if (valid) {
+      const float lt = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ce_smem)[tgt]);
+      atomicAdd(stats + 0, double(lse - lt));
+      atomicAdd(stats + 1, 1.0);
+      if (I == tgt) atomicAdd(stats + 2, 1.0);
+      if (unigram_logp) atomicAdd(stats + 3, double(-unigram_logp[tgt]));
+    }
+  }
+  __syncthreads();
+  if (!write_grad) return;
+  const float M = bm, inv = grad_scale / bs;
+  for (int i = threadIdx.x; i < vec; i += blockDim.x) {
+    float f[8];
+    unpack8(srow[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float g = valid ? __expf(f[k] - M) * inv : 0.f;
+      if (valid && i * 8 + k == tgt) g -= grad_scale;
+      f[k] = g;
+    }
+    reinterpret_cast<uint4*>(lr)[i] = pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------ flat helpers
 __global__ void sqnorm_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
   __shared__ float sh[32];
@@ -636,6 +734,21 @@ void layernorm_bwd(const void* dy, const void* x, const float* gamma, const floa
 void cross_entropy(void* logits, long long ld, const int64_t* targets, long long rows, int V, float grad_scale, bool write_grad,
                    double* stats, float* row_lse, const float* unigram_logp, cudaStream_t st) {
   if (V % 8) throw std::runtime_error("cross_entropy: V must be a multiple of 8");
+  const size_t row_bytes = size_t(V) * 2;
+  static const bool smem_path = [] { const char* e = std::getenv("PB_CE_SMEM"); return !(e && e[0] == '0'); }();
+  if (smem_path && row_bytes <= 200 * 1024 && (ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    // the row lives in shared memory between the two passes: one HBM read of the logits instead of two
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(ce_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cross_entropy smem attr: ") + cudaGetErrorString(e));
+      configured = true;
+    }
+    ce_smem_kernel<<<int(rows), 512, row_bytes, st>>>((__nv_bfloat16*)logits, ld, targets, V, grad_scale, write_grad ? 1 : 0, stats, row_lse,
+                                                      unigram_logp);
+    PB_CHECK_LAUNCH("cross_entropy");
+    return;
+  }
   ce_kernel<<<int(rows), 256, 0, st>>>((__nv_bfloat16*)logits, ld, targets, V, grad_scale, write_grad ? 1 : 0, stats, row_lse,
                                        unigram_logp);
   PB_CHECK_LAUNCH("cross_entropy");
