@@ -416,7 +416,8 @@ class Trainer:
                     m.update(stats)
                 st.eval_timestamp.advance_batch(samples=ids.shape[0] * self.world_size,
                                                 tokens=ids.numel() * self.world_size)
-            sync_metrics(metrics, self.process_group)
+            if self.world_size > 1:     # the Trainer's OWN data-parallel group; a 1-rank trainer inside a bigger job must not
+                sync_metrics(metrics, self.process_group)      # all-reduce over the job's WORLD group (the other ranks are not evaluating)
         vals = st.eval_metric_values
         self.log({f"metrics/{k}": v for k, v in vals.items()})
         if self.icl_suite is not None:   # llm-foundry's ICL evaluators + EvalGauntlet run as part of every trainer.eval()

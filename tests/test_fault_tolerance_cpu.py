@@ -138,3 +138,26 @@ def test_control_plane_unit_gather_queue_and_dead_rank_in_one_process():
     assert planes[0].dead == {2} and planes[1].dead == {2} and planes[1].alive() == [0, 1]
     ts = [threading.Thread(target=p.close) for p in planes]
     [t.start() for t in ts], [t.join() for t in ts]
+
+
+def test_two_ranks_with_federated_eval_and_server_checkpoints(tmp_path):
+    """A 2-rank federation WITH evaluation rounds and server checkpoints: node 0 evaluates alone (its 1-rank Trainer must not
+    all-reduce its metrics over the job's WORLD group — the other rank is not evaluating), FedAdam moments are checkpointed."""
+    out = _launch(tmp_path, 2, f"""
+        from photon_b200.config import compose
+        from photon_b200.federation import FederationRuntime
+        from photon_b200.server_app import run_server
+        dist.init_process_group("gloo")
+        cfg = compose({TINY!r} + ["run_uuid=ev", "fl.n_rounds=2", "fl.n_total_clients=4", "fl.n_clients_per_round=4", "fl.eval_period=1",
+                                "llm_config.device_eval_batch_size=4", "llm_config.eval_subset_num_batches=1", "photon.checkpoint=true",
+                                "photon.saving_path={tmp_path}", "fl.strategy_name=fedadam",
+                                "fl.strategy_kwargs={{eta: 0.01, beta_1: 0.9, beta_2: 0.99, tau: 0.001}}"])
+        rt = FederationRuntime(cfg, device=torch.device("cpu"), rank=dist.get_rank(), world_size=2)
+        h = run_server(cfg, runtime=rt)
+        if dist.get_rank() == 0:
+            assert len(h.losses_distributed) == 3, h.losses_distributed        # rounds 0, 1, 2
+            print("OK eval", [round(v, 3) for _, v in h.losses_distributed])
+    """)
+    assert out.returncode == 0 and "OK eval" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    rounds = sorted(p.name for p in tmp_path.glob("*/ev/server/*") if p.is_dir())
+    assert rounds == ["0", "1", "2"], rounds
