@@ -61,17 +61,75 @@ class CheckpointStore:
 
     # -- upload -----------------------------------------------------------------------
     def upload_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
-                                 tensors: dict[str, torch.Tensor], state: dict[str, Any]) -> Path:
-        """Write one round: state.bin + one npz per strategy state key (ref: s3_utils.py:480-548)."""
+                                 tensors: dict[str, torch.Tensor], state: dict[str, Any], background: bool = False) -> Path:
+        """Write one round: state.bin + one npz per strategy state key (ref: s3_utils.py:480-548).
+
+        ``background=True``: the device → host copy of the planes and the pickling of ``state`` (whose history keeps growing)
+        happen NOW, so the snapshot is the round's; the file writes (0.5 GB of npz per plane for MPT-125M, seconds for the larger
+        models — the reference stalls its round loop on them, plus the S3 upload) run on a writer thread in submission order.
+        :meth:`wait` blocks until everything submitted is on disk (and re-raises a writer error)."""
         d = self.round_dir(run_uuid, server_round)
-        d.mkdir(parents=True, exist_ok=True)
-        for key, flat in tensors.items():
-            dump_model_parameters_to_file(d / f"{key}.npz", layout.to_ndarrays(flat))
-        tmp = d / (STATE_FILE + ".tmp")
-        with open(tmp, "wb") as f:
-            pickle.dump({"server_round": int(server_round), **state}, f)
-        tmp.replace(d / STATE_FILE)  # state.bin last: its presence marks the round complete
+        arrays = {key: layout.to_ndarrays(flat) for key, flat in tensors.items()}
+        blob = pickle.dumps({"server_round": int(server_round), **state})
+
+        def write() -> None:
+            d.mkdir(parents=True, exist_ok=True)
+            for key, arrs in arrays.items():
+                dump_model_parameters_to_file(d / f"{key}.npz", arrs)
+            tmp = d / (STATE_FILE + ".tmp")
+            tmp.write_bytes(blob)
+            tmp.replace(d / STATE_FILE)  # state.bin last: its presence marks the round complete
+
+        if background:
+            self.submit(write)
+        else:
+            write()
         return d
+
+    # -- background writer ------------------------------------------------------------
+    def submit(self, fn: Any) -> None:
+        """Run ``fn()`` on the store's single writer thread, after everything submitted before it (at most 2 jobs queue up: a
+        slow disk eventually back-pressures the round loop instead of piling snapshots up in host memory)."""
+        import queue
+        import threading
+
+        if getattr(self, "_q", None) is None:
+            self._q: Any = queue.Queue(maxsize=2)
+            self._err: BaseException | None = None
+
+            def loop() -> None:
+                while True:
+                    job = self._q.get()
+                    try:
+                        if job is None:
+                            return
+                        if self._err is None:
+                            job()
+                    except BaseException as e:  # noqa: BLE001 - surfaced by wait()
+                        self._err = e
+                    finally:
+                        self._q.task_done()
+
+            self._thread = threading.Thread(target=loop, name="photon-ckpt-writer", daemon=True)
+            self._thread.start()
+            import atexit
+
+            atexit.register(self._drain_quietly)    # also when the run ends with an exception: finish what was snapshotted
+        self._q.put(fn)
+
+    def _drain_quietly(self) -> None:
+        try:
+            self.wait()
+        except Exception as e:  # noqa: BLE001
+            print(f"[checkpoint] {e}: {e.__cause__}", flush=True)
+
+    def wait(self) -> None:
+        """Block until every submitted write is on disk; raise what the writer thread raised, if anything."""
+        if getattr(self, "_q", None) is not None:
+            self._q.join()
+            if self._err is not None:
+                err, self._err = self._err, None
+                raise RuntimeError("background checkpoint write failed") from err
 
     # -- discovery ----------------------------------------------------------------------
     def obtain_sorted_rounds(self, run_uuid: str, state_keys: Sequence[str]) -> list[int]:

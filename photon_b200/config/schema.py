@@ -63,6 +63,7 @@ class Photon(_Strict):
     saving_path: str | None = None
     comm_stack: CommStack = Field(default_factory=CommStack)
     # SPMD host control plane (photon_b200/server/control.py): liveness, shared work queue, time-bounded metadata exchange
+    async_checkpoint: bool = True         # server checkpoints: snapshot at the round boundary, write on a background thread
     control_plane: str = "store"          # store | none
     scheduling: str = "dynamic"           # dynamic = shared work queue (a free GPU takes the next client) | static = client i -> node i mod n
     liveness_timeout_s: float = 20.0      # a rank whose heartbeat is older than this is dead

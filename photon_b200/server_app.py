@@ -104,10 +104,14 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
             tensors = runtime.state_tensors()                      # collective when moments are sharded
             if runtime.rank == 0:
                 with tracer().span("server_checkpoint", cat="server", server_round=server_round):
-                    store.upload_server_checkpoint(run_uuid, server_round, layout=runtime.layout, tensors=tensors,
+                    bg = bool(ph.get("async_checkpoint", True))    # snapshot now, write on the store's writer thread
+                    store.upload_server_checkpoint(run_uuid, server_round, layout=runtime.layout, tensors=tensors, background=bg,
                                                    state=server_state_dict(runtime, history, time_offset + time.time() - t_zero))
                     if cfg.get("cleanup_checkpoints_per_round"):
-                        store.cleanup_checkpoints(run_uuid, per_round=True)
+                        if bg:
+                            store.submit(lambda: store.cleanup_checkpoints(run_uuid, per_round=True))   # after the write it follows
+                        else:
+                            store.cleanup_checkpoints(run_uuid, per_round=True)
         t_chk = time.time()
         n_after = len(runtime.node_ids())                          # second liveness check after the round's broadcast (ref: :346)
         if runtime.rank == 0:
@@ -116,6 +120,8 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
                 "server/second_check_nm_time": time.time() - t_chk, "server/n_nodes_after_round": n_after,
                 # reduce + server optimizer + broadcast of the round (the reference times only its broadcast here)
                 "server/broadcast_post_time": float(runtime.timings.get("aggregate_broadcast_host_s", runtime.timings.get("server/broadcast_time", 0.0)))})
+    if store is not None and runtime.rank == 0:
+        store.wait()                                               # every round's checkpoint is on disk before the run reports done
     if store is not None and cfg.get("cleanup_checkpoints") and runtime.rank == 0:
         store.cleanup_checkpoints(run_uuid)
     if wandb_run is not None:

@@ -355,3 +355,35 @@ def test_committed_reference_state_bin_loads():
     assert h.metrics_distributed_fit["server/n_aggregated_clients"] == [(1, 8), (2, 8)]
     cs = ast.literal_eval(st["client_state"])
     assert set(cs) == set(range(8)) and cs[3]["steps_done"] == 128
+
+
+def test_background_checkpoint_writer_snapshots_now_and_writes_in_order(tmp_path):
+    """``background=True``: the planes and the state are captured at the call (later mutations do not leak into the file), writes
+    land in submission order, ``wait()`` makes them visible and re-raises a writer error."""
+    import numpy as np
+    import torch
+
+    from photon_b200.checkpoint.store import CheckpointStore, load_server_state
+    from photon_b200.utils.flat import FlatLayout
+
+    lay = FlatLayout.build([("a", (300,)), ("b", (5, 7))])
+    store = CheckpointStore(tmp_path, "bucket")
+    flat = torch.arange(lay.total, dtype=torch.float32)
+    hist = {"rounds": [1]}
+    for r in (1, 2, 3):
+        store.upload_server_checkpoint("run", r, layout=lay, tensors={"current_server_parameters": flat}, background=True,
+                                       state={"client_state": "{}", "server_steps_cumulative": r, "seen_rounds": hist})
+        flat += 1000.0            # the next round's update happens while the writer is still busy
+        hist["rounds"].append(r + 1)
+    store.wait()
+    assert store.obtain_sorted_rounds("run", ["current_server_parameters"]) == [1, 2, 3]
+    for r in (1, 2, 3):
+        with np.load(store.round_dir("run", r) / "current_server_parameters.npz") as z:
+            assert float(z["arr_0"][1]) == 1.0 + 1000.0 * (r - 1)         # the value AT round r, not the final one
+        st = load_server_state(store.round_dir("run", r) / "state.bin")
+        assert st["server_steps_cumulative"] == r and st["seen_rounds"]["rounds"] == list(range(1, r + 1))
+    store.submit(lambda: (_ for _ in ()).throw(OSError("disk full")))
+    import pytest
+
+    with pytest.raises(RuntimeError, match="background checkpoint write failed"):
+        store.wait()
