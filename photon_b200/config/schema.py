@@ -63,6 +63,8 @@ class Photon(_Strict):
     saving_path: str | None = None
     comm_stack: CommStack = Field(default_factory=CommStack)
     # SPMD host control plane (photon_b200/server/control.py): liveness, shared work queue, time-bounded metadata exchange
+    client_state_cache_device_gb: float = 16.0   # per-client optimizer moments kept between participations: on the GPU up to this,
+    client_state_cache_host_gb: float = 64.0     # then in pinned host memory up to this, then the least recently used client is dropped
     async_checkpoint: bool = True         # server checkpoints: snapshot at the round boundary, write on a background thread
     control_plane: str = "store"          # store | none
     scheduling: str = "dynamic"           # dynamic = shared work queue (a free GPU takes the next client) | static = client i -> node i mod n

@@ -41,6 +41,65 @@ from photon_b200.utils.flat import FlatLayout
 from photon_b200.utils.trace import tracer
 
 
+class ClientStateCache:
+    """Per-client optimizer moments between a client's participations on this rank (``fl.reset_optimizer=false``), bounded.
+
+    The reference keeps this state in client checkpoints on disk; holding it in memory saves the round trip but must not grow with
+    ``n_total_clients``: entries live on the DEVICE up to ``device_bytes``, older ones are spilled to (pinned) HOST memory up to
+    ``host_bytes``, and beyond that the least recently used client is dropped — it then restarts from a fresh optimizer state (or
+    from its client checkpoint when there is one), exactly like a client this rank has never seen."""
+
+    def __init__(self, device_bytes: int, host_bytes: int) -> None:
+        from collections import OrderedDict
+
+        self.device_bytes, self.host_bytes = int(device_bytes), int(host_bytes)
+        self._d: "OrderedDict[int, tuple[torch.Tensor, torch.Tensor, int]]" = OrderedDict()   # least recently used first
+
+    @staticmethod
+    def _nbytes(e: tuple[torch.Tensor, torch.Tensor, int]) -> int:
+        return e[0].numel() * e[0].element_size() + e[1].numel() * e[1].element_size()
+
+    def _usage(self) -> tuple[int, int]:
+        dev = sum(self._nbytes(e) for e in self._d.values() if e[0].device.type != "cpu")
+        host = sum(self._nbytes(e) for e in self._d.values() if e[0].device.type == "cpu")
+        return dev, host
+
+    def __contains__(self, cid: int) -> bool:
+        return int(cid) in self._d
+
+    def __len__(self) -> int:
+        return len(self._d)
+
+    def pop(self, cid: int, default: Any = None) -> Any:
+        return self._d.pop(int(cid), default)
+
+    def get(self, cid: int) -> tuple[torch.Tensor, torch.Tensor, int]:
+        e = self._d[int(cid)]
+        self._d.move_to_end(int(cid))
+        return e
+
+    def put(self, cid: int, m: torch.Tensor, v: torch.Tensor, step: int) -> None:
+        self._d.pop(int(cid), None)
+        self._d[int(cid)] = (m, v, int(step))
+        dev, host = self._usage()
+        for k in list(self._d):                       # oldest first: device -> host
+            if dev <= self.device_bytes:
+                break
+            e = self._d[k]
+            if e[0].device.type == "cpu" or k == int(cid):
+                continue
+            pin = torch.cuda.is_available()
+            self._d[k] = (e[0].to("cpu", non_blocking=False).pin_memory() if pin else e[0].cpu(),
+                          e[1].to("cpu", non_blocking=False).pin_memory() if pin else e[1].cpu(), e[2])
+            dev -= self._nbytes(e)
+            host += self._nbytes(e)
+        for k in list(self._d):                       # oldest first: host -> gone
+            if host <= self.host_bytes:
+                break
+            if self._d[k][0].device.type == "cpu" and k != int(cid):
+                host -= self._nbytes(self._d.pop(k))
+
+
 class FederationRuntime:
     def __init__(self, cfg: Any, *, device: torch.device | None = None, rank: int | None = None,
                  world_size: int | None = None, group: Any = None, gpus_per_client: int = 1) -> None:
@@ -71,7 +130,10 @@ class FederationRuntime:
         self.fit_config_fn = get_photon_fit_config_fn(cfg)
         self.eval_config_fn = get_photon_evaluate_config_fn(cfg)
         self.trainer: Trainer | None = None
-        self._opt_states: dict[int, tuple[torch.Tensor, torch.Tensor, int]] = {}   # cid -> (exp_avg, exp_avg_sq, step) of its last fit HERE
+        # cid -> (exp_avg, exp_avg_sq, step) of its last fit HERE; bounded (device, then pinned host, then least-recently-used out)
+        ph = cfg["photon"]
+        self._opt_states = ClientStateCache(int(float(ph.get("client_state_cache_device_gb", 16.0) or 0.0) * (1 << 30)),
+                                            int(float(ph.get("client_state_cache_host_gb", 64.0) or 0.0) * (1 << 30)))
         self._local_params: dict[int, torch.Tensor] = {}   # personalised-layer memory per client
         self.layout: FlatLayout | None = None        # exchange layout (3 planes with fl.aggregate_momenta)
         self.model_layout: FlatLayout | None = None  # the trainer's parameter layout
@@ -253,8 +315,8 @@ class FederationRuntime:
                     # the client's own moments from ITS last participation (entries are dropped in gather_results as soon as the
                     # client trains elsewhere, so what is found here is never older than that); a client checkpoint, when present,
                     # is loaded on top by llm_fit. Keyed by client id, whatever the client-to-node mapping of the round.
-                    m, v, step = self._opt_states[cid]
-                    opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)  # per-rank planes (a slice when the state is sharded)
+                    m, v, step = self._opt_states.get(cid)
+                    opt.exp_avg.copy_(m), opt.exp_avg_sq.copy_(v)  # per-rank planes (a slice when the state is sharded); H2D when spilled
                     opt.step_count = step
                 elif keep_opt:
                     opt.reset_state()
@@ -265,7 +327,7 @@ class FederationRuntime:
                     payload, n_samples, metrics, _ = llm_fit(tr, rb.global_params(), fc, self.cfg, cid,
                                                              shadow_payload=None if shadow is None else shadow[: self.model_layout.total])
                 if keep_opt:   # always (also when the node hosts one client): behaviour must not depend on the topology
-                    self._opt_states[cid] = (opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
+                    self._opt_states.put(cid, opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_count)
                 if fc.personalized_layers:
                     self._local_params[cid] = tr.state.flat.params.clone()
                 if self.is_leader:

@@ -498,3 +498,20 @@ def test_round_two_trains_from_the_broadcast_global_not_the_client_checkpoint(tm
     assert len(seen) == 6 and all(seen), seen
     assert list((tmp_path / "clients").rglob("*.pt")), "client checkpoints were expected on disk"
     rt.close()
+
+
+def test_client_state_cache_is_bounded_lru():
+    """Per-client optimizer moments kept between participations never grow with the number of clients: device budget, then host
+    budget, then the least recently used client is dropped (it restarts from a fresh state, like an unseen client)."""
+    from photon_b200.federation import ClientStateCache
+
+    one = 2 * 256 * 4                                     # bytes of one entry (two fp32 planes of 256 elements)
+    c = ClientStateCache(device_bytes=0, host_bytes=3 * one)      # CPU box: everything counts as host
+    for cid in range(5):
+        c.put(cid, torch.full((256,), float(cid)), torch.zeros(256), cid)
+    assert len(c) == 3 and 0 not in c and 1 not in c and 4 in c
+    m, _, step = c.get(2)                                  # touching 2 makes it the most recent
+    assert float(m[0]) == 2.0 and step == 2
+    c.put(5, torch.ones(256), torch.ones(256), 5)
+    assert 3 not in c and 2 in c and 5 in c               # 3 was the least recently used
+    assert c.pop(2)[2] == 2 and 2 not in c
