@@ -85,7 +85,20 @@ struct FwdSched {
   }
 };
 
-template <int DH, int NS, bool ALIBI>
+// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, a degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, far below the bf16 rounding of P) and n added into the exponent field. The forward softmax is
+// bound by the 16 exp2 / clk / SM of the MUFU pipe while the FMA pipe idles: every POLY-th pair of a row goes this way.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.0f);                        // masked (-inf) scores end as 2^-126 ~ 0
+  const float r = x + 12582912.0f;              // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(f, 0.05517132207751274f, 0.24261054396629333f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+template <int DH, int NS, bool ALIBI, int POLY>
 __global__ void __launch_bounds__((4 * NS + 2) * 32, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int S, int H,
                 float scale, int causal, const FwdSched sched, const float* __restrict__ alibi_slopes) {
@@ -370,19 +383,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
             for (int t = 0; t < 32; t += 2) {
-              float p0, p1;
+              float p0, p1, x0, x1;
               if (ALIBI) {
                 const float y0 = score(r, cc, t), y1 = score(r, cc, t + 1);
                 cm0 = fmaxf(cm0, y0);
                 cm1 = fmaxf(cm1, y1);
-                p0 = exp2f(y0 - m_ref);
-                p1 = exp2f(y1 - m_ref);
+                x0 = y0 - m_ref, x1 = y1 - m_ref;
               } else {
                 const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
                 cm0 = fmaxf(cm0, v0);
                 cm1 = fmaxf(cm1, v1);
-                p0 = exp2f(fmaf(v0, sc, -m_ref));
-                p1 = exp2f(fmaf(v1, sc, -m_ref));
+                x0 = fmaf(v0, sc, -m_ref), x1 = fmaf(v1, sc, -m_ref);
+              }
+              if (POLY > 0 && (t >> 1) % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) {
+                p0 = exp2_fma(x0), p1 = exp2_fma(x1);
+              } else {
+                p0 = exp2f(x0), p1 = exp2f(x1);
               }
               rs0 += p0;
               rs1 += p1;
@@ -954,6 +970,10 @@ void set_smem(K kern, int bytes) {
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention smem attr: ") + cudaGetErrorString(e));
 }
 
+#ifndef PB_ATTN_POLY_DEFAULT
+#define PB_ATTN_POLY_DEFAULT 0
+#endif
+
 float* g_dq_acc = nullptr;
 size_t g_dq_acc_bytes = 0;
 
@@ -977,17 +997,28 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
     sched.cyc_rounds = sched.n_qt / a;
   }
   // two column parts per query row = two softmax warps per SM sub-partition (four measured slower: 432 vs 407 us)
-#define PB_FWD(DHV, AL)                                                                                               \
+  // PB_ATTN_POLY = 4: every 4th pair of exponentials on the FMA pipe (default 0 = all on MUFU). Measured (profiles/attn_exp2_poly.txt):
+  // 1/4 -> 0.419 ms, 1/3 -> 0.420, 1/2 -> 0.453 against 0.408 ms with none: the softmax warps are bound by issue slots and
+  // fixed-latency dependencies (two warps per scheduler), not by MUFU throughput, so the ~9 extra instructions per element cost
+  // more than the MUFU cycles they free. Kept as a switch for parts with a different MUFU : FMA ratio.
+  static const int poly = [] { const char* e = std::getenv("PB_ATTN_POLY"); return e ? std::atoi(e) : PB_ATTN_POLY_DEFAULT; }();
+#define PB_FWD(DHV, AL, PL)                                                                                           \
   {                                                                                                                   \
-    static bool once = (set_smem(attn_fwd_kernel<DHV, 2, AL>, FwdCfg<DHV>::SMEM), true);                               \
+    static bool once = (set_smem(attn_fwd_kernel<DHV, 2, AL, PL>, FwdCfg<DHV>::SMEM), true);                           \
     (void)once;                                                                                                       \
-    attn_fwd_kernel<DHV, 2, AL><<<grid, 10 * 32, FwdCfg<DHV>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale,   \
-                                                                        causal ? 1 : 0, sched, alibi_slopes);         \
+    attn_fwd_kernel<DHV, 2, AL, PL><<<grid, 10 * 32, FwdCfg<DHV>::SMEM, st>>>(tm, (__nv_bfloat16*)out, lse, S, H, scale, \
+                                                                            causal ? 1 : 0, sched, alibi_slopes);     \
   }
-  if (dh == 64 && !alibi_slopes) PB_FWD(64, false)
-  else if (dh == 64) PB_FWD(64, true)
-  else if (!alibi_slopes) PB_FWD(128, false)
-  else PB_FWD(128, true)
+#define PB_FWD_P(DHV, AL)                                                                                             \
+  {                                                                                                                   \
+    if (poly == 4) PB_FWD(DHV, AL, 4)                                                                                 \
+    else PB_FWD(DHV, AL, 0)                                                                                           \
+  }
+  if (dh == 64 && !alibi_slopes) PB_FWD_P(64, false)
+  else if (dh == 64) PB_FWD_P(64, true)
+  else if (!alibi_slopes) PB_FWD_P(128, false)
+  else PB_FWD_P(128, true)
+#undef PB_FWD_P
 #undef PB_FWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("attention fwd launch: ") + cudaGetErrorString(e));

@@ -504,6 +504,36 @@ void fed_round(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64
                        at::cuda::getCurrentCUDAStream(device).stream());
   g_launches += 1;
 }
+// ZeRO-3: accumulate the mean over ranks of slice `rank` of the unit's staging planes into `dst` (see comm.cu)
+void zero3_reduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& stage_ptrs,
+                  int64_t stage_mc, c10::optional<Tensor> dst, int64_t per) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  pb::CommCtl c = make_ctl(ctl_ptrs, rank);
+  pb::ShardReduceArgs a{};
+  TORCH_CHECK(per % 4 == 0 && per >= 0, "slice length must be a multiple of 4");
+  if (per > 0) {
+    TORCH_CHECK(dst.has_value() && dst->scalar_type() == at::kFloat && dst->numel() >= per && dst->is_contiguous(), "dst: fp32, >= per");
+    TORCH_CHECK(int(stage_ptrs.size()) == c.n, "one staging plane per rank");
+    for (int i = 0; i < c.n; ++i) a.stage[i] = reinterpret_cast<const float*>(stage_ptrs[i]);
+    a.dst = dst->data_ptr<float>();
+  }
+  a.stage_mc = reinterpret_cast<const float*>(stage_mc);
+  a.per = per;
+  a.scale = 1.0f / float(c.n);
+  pb::zero3_reduce_launch(a, c, uint32_t(epoch), at::cuda::getCurrentDeviceProperties()->multiProcessorCount,
+                          at::cuda::getCurrentCUDAStream(device).stream());
+  g_launches += 1;
+}
+
+// device-to-device copy between (possibly peer-mapped) raw addresses on the current stream: the copy engines pull a parameter
+// slice from its owner over NVLink without occupying an SM
+void memcpy_async(int64_t dst, int64_t src, int64_t nbytes, int device) {
+  c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+  cudaError_t e = cudaMemcpyAsync(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), size_t(nbytes), cudaMemcpyDefault,
+                                  at::cuda::getCurrentCUDAStream(device).stream());
+  TORCH_CHECK(e == cudaSuccess, "memcpy_async: ", cudaGetErrorString(e));
+}
+
 void ddp_allreduce(const std::vector<int64_t>& ctl_ptrs, int rank, int device, int64_t epoch, const std::vector<int64_t>& buf_ptrs, int64_t lo,
                    int64_t hi, c10::optional<Tensor> out_norm, int64_t buf_mc) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
@@ -603,6 +633,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ctl_status_word_offset", &pb::ctl_status_word_offset);
   m.def("ddp_allreduce", &ddp_allreduce, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("buf_ptrs"),
         py::arg("lo"), py::arg("hi"), py::arg("out_norm") = py::none(), py::arg("buf_mc") = 0);
+  m.def("zero3_reduce", &zero3_reduce, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("stage_ptrs"),
+        py::arg("stage_mc"), py::arg("dst"), py::arg("per"));
+  m.def("memcpy_async", &memcpy_async);
   m.def("ddp_zero_step", &ddp_zero_step, py::arg("ctl_ptrs"), py::arg("rank"), py::arg("device"), py::arg("epoch"), py::arg("grad_ptrs"),
         py::arg("param_ptrs"), py::arg("shadow_ptrs"), py::arg("m"), py::arg("v"), py::arg("lo"), py::arg("hi"), py::arg("kind"),
         py::arg("first_step"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"), py::arg("eps"), py::arg("decay"), py::arg("clip"),

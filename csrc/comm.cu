@@ -370,6 +370,35 @@ __global__ void __launch_bounds__(512) ddp_allreduce_kernel(const AllReduceArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------ ZeRO-3 gradient reduce-scatter
+// One UNIT (a transformer block, or the embeddings + final norm) of the flat gradient: every rank has just written the unit's
+// gradient of its own microbatch into its staging plane (n slices of `per` floats); rank r owns slice r and accumulates the
+// mean over ranks into its persistent fp32 gradient shard. Start barrier: every rank's staging plane is complete; end barrier:
+// every rank has finished reading, so the plane may be overwritten by the next unit of the same parity.
+__global__ void __launch_bounds__(512) zero3_reduce_kernel(const ShardReduceArgs a, const CommCtl c, const uint32_t epoch) {
+  if (!grid_peer_barrier_start(c, epoch)) return;
+  const long long off4 = (long long)c.rank * (a.per / 4), n4 = a.per / 4;
+  float4* dst = reinterpret_cast<float4*>(a.dst);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.stage_mc) {
+      acc = mm_ld_reduce_add_f4(reinterpret_cast<const float4*>(a.stage_mc) + off4 + i);
+    } else if (c.n == 1) {
+      acc = reinterpret_cast<const float4*>(a.stage[0])[i];
+    } else {
+#pragma unroll 1
+      for (int p = 0; p < c.n; ++p) {
+        const float4 t = ld_peer_f4(reinterpret_cast<const float4*>(a.stage[p]) + off4 + i);
+        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+      }
+    }
+    float4 d = dst[i];
+    d.x = fmaf(acc.x, a.scale, d.x), d.y = fmaf(acc.y, a.scale, d.y), d.z = fmaf(acc.z, a.scale, d.z), d.w = fmaf(acc.w, a.scale, d.w);
+    dst[i] = d;
+  }
+  if (grid_done(c)) peer_barrier_end(c, epoch);
+}
+
 // ------------------------------------------------------------------------------------------ N1 + K11 + K12
 // Phase 1: every rank sums its shard of all gradient planes over NVLink (mean folded in), keeps the result in its own
 // plane and publishes the shard's squared norm to every rank. Mid barrier. Phase 2: clip coefficient from the global norm,
@@ -527,6 +556,14 @@ void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoc
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("ddp_zero_step launch: ") + cudaGetErrorString(e));
 }
+void zero3_reduce_launch(const ShardReduceArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st) {
+  // a pure barrier (per == 0) needs one block; the reduction is bandwidth bound well below a full grid
+  const int grid = a.per == 0 ? 1 : sm_count(num_sms);
+  zero3_reduce_kernel<<<grid, 512, 0, st>>>(a, c, epoch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("zero3_reduce launch: ") + cudaGetErrorString(e));
+}
+
 void set_wsum(uint32_t* ctl, float w, bool zero_sums, cudaStream_t st) { set_wsum_kernel<<<1, 1, 0, st>>>(ctl, w, zero_sums ? 1 : 0); }
 
 }  // namespace pb

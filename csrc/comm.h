@@ -66,6 +66,16 @@ struct ZeroStepArgs {
   void* shadow_mc;
 };
 
+// ZeRO-3 (full parameter sharding): reduce-scatter of ONE unit's gradient staging planes into the owner's gradient shard.
+struct ShardReduceArgs {
+  const float* stage[MAX_PEERS];  // per-rank staging plane of the unit: n slices of `per` floats (slice r belongs to rank r)
+  const float* stage_mc;          // NVLS multicast address of the staging planes, or nullptr
+  float* dst;                     // this rank's slice of the persistent fp32 gradient shard (per floats), accumulated into
+  long long per;                  // slice length, multiple of 4 (0 = barrier only)
+  float scale;                    // 1 / n (mean over ranks)
+};
+void zero3_reduce_launch(const ShardReduceArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st);
+
 void ddp_zero_step_launch(const ZeroStepArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
 void fed_round_launch(const FedRoundArgs& a, const CommCtl& c, uint32_t epoch, int num_sms, cudaStream_t st);
 void ddp_allreduce_launch(const AllReduceArgs& a, const CommCtl& c, uint32_t epoch, float* out_norm, int num_sms, cudaStream_t st);
