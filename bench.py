@@ -140,9 +140,16 @@ def ddp_cfg(args, impl: str, microbatch):
         f"llm_config.global_train_batch_size={DDP_GLOBAL_BATCH}", f"llm_config.device_train_microbatch_size={microbatch}",
         "llm_config.scheduler.schedulers.lr.name=constant_with_sqrt_cooldown_with_warmup", "llm_config.scheduler.schedulers.lr.t_warmup=100ba",
         "++llm_config.scheduler.schedulers.lr.t_cooldown=240ba", "llm_config.scheduler.schedulers.lr.t_max=5120ba",
-        "llm_config.max_duration=5120ba", "~llm_config.algorithms.gradient_clipping", "~llm_config.fsdp_config",
+        "llm_config.max_duration=5120ba", "~llm_config.algorithms.gradient_clipping",
         "llm_config.optimizer={name: decoupled_adamw, lr: 6.0e-4, betas: [0.9, 0.95], eps: 1.0e-8, weight_decay: 0.0}",
         "dataset/streams@dataset.train.streams=centralised", "centralized.store_init_model=false", "centralized.store_final_model=false"]
+    # plain DDP is the launch scripts' choice for the small models (ref: cen_125m_example.sh:87 deletes fsdp_config); the 7B config
+    # keeps its fsdp_config (FULL_SHARD + activation checkpointing, ref: mpt-7b.yaml:85-91) -> full parameter sharding here
+    sharding = args.sharding if args.sharding != "auto" else ("zero3" if args.model == "mpt-7b" else "none")
+    if sharding == "none" or impl != "ours":
+        ov += ["~llm_config.fsdp_config"]
+    else:
+        ov += [f"kernels.param_sharding={sharding}"]
     return compose(ov)
 
 
@@ -308,7 +315,7 @@ def run_ddp(env: Env, args, impl: str, K: int, W: int) -> dict:
     clk.stop()
     # the gradient all-reduce alone on the live bucket
     ar_ms = 0.0
-    if env.world > 1:
+    if env.world > 1 and not getattr(tr.state.flat, "is_sharded", False):   # (fully sharded: reduced per block inside the backward)
         g = tr.state.flat.grads
         for _ in range(3):
             tr._allreduce_grads()  # noqa: SLF001
@@ -326,6 +333,9 @@ def run_ddp(env: Env, args, impl: str, K: int, W: int) -> dict:
                optimizer="decoupled_adamw", comm_stack=type(tr.grad_comm).__name__ if tr.grad_comm is not None else "none",
                microbatch=int(getattr(tr, "_auto_mb", None) or tr.microbatch), clients_per_node=1, gpus_per_client=env.world, n_clients=1,
                h2d=per_gpu * SEQ * 8, d2h=2 * 8)
+    free_b, total_b = torch.cuda.mem_get_info(env.dev)
+    out["gpu_mem_used_gb"] = round((total_b - free_b) / 2**30, 1)     # whole device, arena planes included (after the run)
+    out["torch_peak_alloc_gb"] = round(torch.cuda.max_memory_allocated(env.dev) / 2**30, 1)
     gc_ = tr.grad_comm
     tr.close()
     if gc_ is not None:
@@ -345,9 +355,16 @@ def main() -> None:
     ap.add_argument("--attention", default="b200", choices=["b200", "torch"])
     ap.add_argument("--microbatch", type=int, default=0, help="device microbatch (0 = 32 for mpt-125m, 8 otherwise; torch arm: auto)")
     ap.add_argument("--server", default="fedavg", choices=["fedavg", "fedadam"])
+    ap.add_argument("--sharding", default="auto", choices=["auto", "none", "zero1", "zero3"],
+                    help="ddp mode: none = replicated DDP, zero1 = fused sharded-optimizer step, zero3 = full parameter sharding "
+                         "(auto = zero3 for mpt-7b, none otherwise)")
+    ap.add_argument("--global-batch", type=int, default=0, help="ddp mode: sequences per optimizer step (default 256, BASELINE config #3)")
     ap.add_argument("--torch-arm", default="auto", choices=["auto", "on", "off"],
                     help="also measure the reference-equivalent stock-PyTorch arm in this invocation (auto = yes for mpt-125m)")
     args = ap.parse_args()
+    if args.global_batch:
+        global DDP_GLOBAL_BATCH
+        DDP_GLOBAL_BATCH = int(args.global_batch)
     if args.impl == "reference":
         reference_arm()
         return
@@ -400,7 +417,7 @@ def result_line(env, args, r: dict, K: int, W: int, torch_arm) -> dict:
         peak = measured_peaks()
         model = MODEL_NAMES.get(args.model, args.model)
         metric = {"fed": f"tokens/sec (whole box, device-timed, max over ranks) {model} 8-client fed round",
-                  "ddp": f"tokens/sec (whole box, device-timed, max over ranks) {model} centralised_train DDP global batch 256",
+                  "ddp": f"tokens/sec (whole box, device-timed, max over ranks) {model} centralised_train DDP global batch {DDP_GLOBAL_BATCH}",
                   "fed4x2": f"tokens/sec (whole box, device-timed, max over ranks) {model} 4 clients x 2 GPUs fed round"}[args.mode]
         par = {"fed": f"fed{N_CLIENTS}clients_on_{world}gpu", "ddp": f"dp{world}", "fed4x2": f"fed4clients_x_dp2_on_{world}gpu"}[args.mode]
         exch = "round_aggregate_broadcast_ms" if args.mode != "ddp" else "allreduce_ms"
@@ -431,6 +448,9 @@ def result_line(env, args, r: dict, K: int, W: int, torch_arm) -> dict:
                     "api": "Trainer.fit via run_centralised (wall clock)" if args.mode == "ddp" else "FederationRuntime.run_clients_fit + finish_round (wall clock)"},
             "gpu_launches": r["launches"],
         }
+        if "gpu_mem_used_gb" in r:
+            out["memory"] = {"gpu_mem_used_gb": r["gpu_mem_used_gb"], "torch_peak_alloc_gb": r["torch_peak_alloc_gb"],
+                             "note": "device memory in use after the run (arena planes included) / peak of the torch allocator"}
         if torch_arm is not None:
             out["torch_arm"] = torch_arm
             if "value" in torch_arm:

@@ -79,11 +79,20 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
             use_nvl_allreduce = device.type == "cuda" and not all(
                 (cfg.get("kernels") or {}).get(k, "auto") == "torch" for k in ("gemm", "optimizer"))
         if use_nvl_allreduce:
-            from photon_b200.parallel.ddp import build_nvl_comm, wants_sharded_step
+            from photon_b200.parallel.ddp import build_nvl_comm, wants_full_sharding, wants_sharded_step
             from photon_b200.utils.flat import layout_for_model_cfg
 
-            total = layout_for_model_cfg(cfg["llm_config"]["model"], cc.frozen_layers, cc.unfrozen_layers).total
-            grad_comm = build_nvl_comm(total, sharded=wants_sharded_step(cfg["llm_config"]), rank=rank, world_size=world_size, device=device)
+            lay = layout_for_model_cfg(cfg["llm_config"]["model"], cc.frozen_layers, cc.unfrozen_layers)
+            if wants_full_sharding(cfg, lay.n_params, device) and not (cc.frozen_layers or cc.unfrozen_layers):
+                from photon_b200.parallel.zero3 import NvlZero3Comm
+
+                # fsdp_config FULL_SHARD on a model whose replicated state would crowd the GPU: parameters, gradients and
+                # optimizer state all live as 1/world shards (ZeRO-3); smaller models keep the faster fused ZeRO-1 step
+                grad_comm = NvlZero3Comm(lay, int(cfg["llm_config"]["model"]["n_layers"]), rank=rank, world_size=world_size, device=device)
+                print(f"[centralised_train] full parameter sharding over {world_size} GPUs "
+                      f"({lay.n_params / 1e9:.2f} B parameters, {16 * grad_comm.plan.shard_len / 2**30:.1f} GiB of state per GPU)", flush=True)
+            else:
+                grad_comm = build_nvl_comm(lay.total, sharded=wants_sharded_step(cfg["llm_config"]), rank=rank, world_size=world_size, device=device)
         else:
             from photon_b200.parallel.ddp import NcclGradComm
 
@@ -109,7 +118,8 @@ def run_centralised(cfg: Any, *, device: torch.device | None = None, rank: int |
             raise ValueError(f"wte_parameters_path holds {len(donor)} arrays; expected a full model ({len(names)}) or the embedding alone")
         set_wte_parameters(trainer, wte)
     resume_centralised(trainer, train_cfg)
-    if world_size > 1:  # identical start on every rank
+    if world_size > 1 and not getattr(trainer.state.flat, "is_sharded", False):  # identical start on every rank
+        # (fully sharded runs: every rank initialises from the same seed / loads the same file and keeps only its slices)
         torch.distributed.broadcast(trainer.state.flat.params, src=0)
         trainer.state.backend.params_updated()
     run_uuid = str(cfg["run_uuid"])

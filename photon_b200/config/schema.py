@@ -189,6 +189,16 @@ class Kernels(_Strict):
     loss: str = "auto"        # fused cross-entropy
     optimizer: str = "auto"   # fused flat-buffer ADOPT / DecoupledAdamW
     cuda_graph: bool = True
+    # sharding inside a client / a centralised run when fsdp_config asks for it: zero1 = optimizer state only (one fused NVLink
+    # step), zero3 = parameters + gradients + state (parallel/zero3.py), auto = zero3 only when the model would crowd the GPU
+    param_sharding: str = "auto"
+
+    @field_validator("param_sharding")
+    @classmethod
+    def _sharding(cls, v: str) -> str:
+        if v not in ("auto", "zero1", "zero3"):
+            raise ValueError("must be one of auto|zero1|zero3")
+        return v
 
     @field_validator("gemm", "attention", "norm", "loss", "optimizer")
     @classmethod

@@ -54,7 +54,10 @@ class B200Engine:
                  unfrozen_layers: list[str] | None = None, unigram_log_probs: torch.Tensor | None = None,
                  lm_head_chunk: int = 18944, grads_storage: torch.Tensor | None = None,
                  activation_checkpointing: bool = False, params_storage: torch.Tensor | None = None,
-                 shadow_storage: torch.Tensor | None = None) -> None:
+                 shadow_storage: torch.Tensor | None = None, zero3: Any = None) -> None:
+        """``zero3``: a :class:`photon_b200.parallel.zero3.NvlZero3Comm` — full parameter sharding: this rank keeps 1/world of the
+        masters / gradients / bf16 weights, block weights are pulled into two rotating buffers one block ahead of the compute
+        stream and every block's gradient is reduce-scattered right after its backward (ref: fsdp_config FULL_SHARD)."""
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -65,6 +68,9 @@ class B200Engine:
             raise NotImplementedError("frozen/unfrozen layers run on the torch backend (kernels.*=torch)")
         ops.ext()  # fail loudly if the extension is missing
         self.precision = precision
+        self.zero3 = zero3
+        if zero3 is not None and precision != "amp_bf16":
+            raise NotImplementedError("full parameter sharding runs in amp_bf16 (the fp8 weight copies are quantised from a resident bf16 plane)")
         kernels = dict(kernels or {})
         # amp_fp8 (ref: scripts/centralised_training.sh:91, Composer amp_fp8 -> TransformerEngine): the four GEMMs of every block
         # and their dgrad / wgrad run on tcgen05.mma kind::f8f6f4 (E4M3 activations / weights, E5M2 gradients, per-tensor
@@ -73,7 +79,8 @@ class B200Engine:
         self.attn_mode = "torch" if kernels.get("attention", "auto") == "torch" else "b200"
         # kernels.cuda_graph: the ~330 launches of one microbatch are captured once per (batch, seq, loss scaling) and
         # replayed (the schedule is static: preallocated workspace, TMA descriptors baked into the launches)
-        self.use_graph = bool(kernels.get("cuda_graph", True))
+        # (not under full sharding: the per-block gathers / reductions carry host-side epochs and events)
+        self.use_graph = bool(kernels.get("cuda_graph", True)) and zero3 is None
         self._graphs: dict[tuple, Any] = {}
         if self.attn_mode == "b200" and cfg.d_head not in (64, 128):
             # the tcgen05 attention kernels cover d_head 64 and 128 (every shipped MPT config); anything else uses the
@@ -82,12 +89,25 @@ class B200Engine:
             self.attn_mode = "torch"
         self.model = MPTForCausalLM(cfg, device=self.device, seed=seed)
         self.frozen = apply_freeze(self.model, frozen_layers, unfrozen_layers)
-        self.flat = FlatParams(self.model, device=self.device, params_storage=params_storage, grads_storage=grads_storage)
-        # bf16 compute copy; lives in a symmetric arena plane when a fused NVLink step writes it from peer GPUs
-        self.bf16_params = shadow_storage if shadow_storage is not None else torch.zeros(
-            self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
-        if self.bf16_params.numel() != self.flat.layout.total or self.bf16_params.dtype != torch.bfloat16:
-            raise ValueError("shadow_storage must be a bf16 tensor with layout.total elements")
+        if zero3 is not None:
+            from photon_b200.parallel.zero3 import ShardedFlat
+
+            # same initial weights as an unsharded engine with this seed: materialise once, keep the shard, drop the rest
+            init = FlatParams(self.model, device=self.device, with_grad=False)
+            if init.layout.total != zero3.plan.layout.total or init.layout.names != zero3.plan.layout.names:
+                raise ValueError("the ZeRO-3 communicator was planned for a different parameter layout")
+            zero3.load_full_params(init.params)
+            del init
+            self.model = None
+            self.flat = ShardedFlat(zero3)
+            self.bf16_params = zero3.w16        # this rank's shard of the bf16 weights (what the optimizer kernel writes)
+        else:
+            self.flat = FlatParams(self.model, device=self.device, params_storage=params_storage, grads_storage=grads_storage)
+            # bf16 compute copy; lives in a symmetric arena plane when a fused NVLink step writes it from peer GPUs
+            self.bf16_params = shadow_storage if shadow_storage is not None else torch.zeros(
+                self.flat.layout.total, dtype=torch.bfloat16, device=self.device)
+            if self.bf16_params.numel() != self.flat.layout.total or self.bf16_params.dtype != torch.bfloat16:
+                raise ValueError("shadow_storage must be a bf16 tensor with layout.total elements")
         self.unigram_log_probs = unigram_log_probs.to(self.device) if unigram_log_probs is not None else None
         self.lm_head_chunk = int(lm_head_chunk)
         # positional variants of the MPT attention block (ref: SURVEY §5.7): ALiBi slopes enter the attention kernels,
@@ -118,6 +138,13 @@ class B200Engine:
         v32 = lambda n: lay.view(P, "transformer." + n) if "transformer." + n in have else None  # noqa: E731
         vg = lambda n: lay.view(G, "transformer." + n) if "transformer." + n in have else None  # noqa: E731
         v16 = lambda n: lay.view(Sd, "transformer." + n)  # noqa: E731
+        if self.zero3 is not None:
+            # weights: views into the two rotating block buffers (block i -> buffer i % 2) / the resident embedding buffer;
+            # 1-D fp32 parameters: the packed resident buffer; gradients: the block's staging plane (reduced after its backward)
+            z = self.zero3
+            v32 = lambda n: z.small("transformer." + n) if "transformer." + n in have else None  # noqa: E731
+            vg = lambda n: z.grad("transformer." + n) if "transformer." + n in have else None  # noqa: E731
+            v16 = lambda n: z.weight("transformer." + n)  # noqa: E731
         has_wpe = self.cfg.learned_pos_emb
         self.wte16, self.wpe16 = v16("wte.weight"), (v16("wpe.weight") if has_wpe else None)
         self.d_wte, self.d_wpe = vg("wte.weight"), (vg("wpe.weight") if has_wpe else None)
@@ -147,6 +174,11 @@ class B200Engine:
         """Re-cast the bf16 compute shadow from the fp32 masters. Only needed after host-side
         parameter loads: the fused optimizer and the round-broadcast kernels write the shadow
         themselves (the Trainer skips this call in that case)."""
+        if self.zero3 is not None:
+            self.zero3.before_param_write()
+            ops.cast_bf16(self.flat.params, self.bf16_params)
+            self.zero3.params_changed()
+            return
         ops.cast_bf16(self.flat.params, self.bf16_params)
 
     # ---------------------------------------------------------------------- fp8
@@ -321,8 +353,14 @@ class B200Engine:
         c = self.cfg
         b, S = ids.shape
         h = ws["h"]
+        z = self.zero3
+        if z is not None:
+            z.ensure_resident()
         ops.embed_fwd(ids.reshape(-1), self.wte16, self.wpe16, h[0], S)
         for i in range(c.n_layers):
+            if z is not None:
+                z.acquire(i)          # block i's weights are in buffer i % 2 (stream-ordered wait) ...
+                z.prefetch(i + 1)     # ... and block i+1 streams into the other one while block i computes
             self._block_fwd(i, ws, b, S)
             if self.collect_activation_stats:
                 x = h[i + 1][:S].float()
@@ -368,9 +406,14 @@ class B200Engine:
         b, S = ids.shape
         h = ws["h"]
         dh, dhmid, dln = ws["dh"], ws["dhmid"], ws["dln"]
+        z = self.zero3
         ops.layernorm_bwd(ws["dlnf"], h[c.n_layers], self.gf, ws["mf"], ws["rf"], None, dh, self.d_gf, self.d_bf)
         for i in range(c.n_layers - 1, -1, -1):
             w, lw = self.layers[i], ws["layers"][i]
+            if z is not None:
+                z.acquire(i)
+                z.prefetch(i - 1)
+                z.zero_stage(i)       # this microbatch's gradient of block i (the shard accumulates over microbatches)
             if self.activation_checkpointing and i < c.n_layers - 1:
                 self._block_fwd(i, ws, b, S)   # recompute (the shared buffers still hold the LAST block after the forward)
             # ---- FFN: h[i+1] = hmid + down(gelu(up(ln2(hmid))))
@@ -391,7 +434,11 @@ class B200Engine:
                 ws["dqkv"].mul_(lw["clipmask"])
             self._linear_bwd(i, ws, ws["dqkv"], "g_dqkv", lw["ln1"], "x_ln1", "wqkv", w.wqkv, w.d_wqkv, w.d_bqkv, dln)
             ops.layernorm_bwd(dln, h[i], w.g1, lw["m1"], lw["r1"], dhmid, dh, w.d_g1, w.d_b1)
+            if z is not None:
+                z.reduce(i)           # reduce-scatter: every rank adds the mean of ITS slice into its gradient shard
         ops.embed_bwd(ids.reshape(-1), dh, self.d_wte, self.d_wpe, S)
+        if z is not None:
+            z.reduce(z.plan.rest)
 
     # ---------------------------------------------------------------- protocol
     def _fwd_bwd_eager(self, ids: torch.Tensor, grad_scale: float) -> None:
@@ -401,6 +448,8 @@ class B200Engine:
         self._stats.zero_()
         if self.fp8:
             self._fp8_prologue(train=True)
+        if self.zero3 is not None:
+            self.zero3.zero_stage(self.zero3.plan.rest)   # embeddings + final norm collect gradients over the whole backward
         self._forward(ids, ws)
         self._head(ws, targets, grad_scale, train=True)
         self._backward(ids, ws)
@@ -476,11 +525,15 @@ class B200Engine:
         handful of tokens at a time — nothing like the fixed ``[b, 2048]`` schedule the kernel workspace is laid out for — so
         this runs the torch module that shares the fp32 master weights (bf16 autocast, SDPA); it is an evaluation utility,
         not part of the training step."""
+        if self.model is None:
+            raise NotImplementedError("in-context-learning evaluation needs the whole model on one GPU; under full parameter "
+                                      "sharding evaluate the run's checkpoint with an unsharded trainer")
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return self.model(ids.to(self.device))
 
     def train_mode(self, on: bool = True) -> None:
-        self.model.train(on)
+        if self.model is not None:
+            self.model.train(on)
 
     def close(self) -> None:
         self._graphs.clear()

@@ -153,6 +153,29 @@ def wants_sharded_step(llm_cfg: Any) -> bool:
     return bool(fsdp) and str(dict(fsdp).get("sharding_strategy", "FULL_SHARD")).upper() != "NO_SHARD"
 
 
+def wants_full_sharding(cfg: Any, n_params: int, device: Any = None) -> bool:
+    """``kernels.param_sharding``: ``zero3`` / ``zero1`` force a scheme; ``auto`` (default) shards parameters and gradients too
+    (ZeRO-3, :mod:`photon_b200.parallel.zero3`) when ``fsdp_config.sharding_strategy`` is FULL_SHARD AND the replicated training
+    state (18 B/param) would take more than 40 % of the GPU — MPT-7B on 180 GB, not MPT-125M..3B, for which the fused ZeRO-1 step
+    (one kernel, CUDA-graphed microbatches) is faster and memory is not a concern."""
+    llm = cfg["llm_config"]
+    mode = str((cfg.get("kernels") or {}).get("param_sharding", "auto") or "auto").lower()
+    if mode in ("zero3", "full", "full_shard"):
+        return True
+    fsdp = (llm or {}).get("fsdp_config") or None
+    if mode != "auto" or not fsdp or str(dict(fsdp).get("sharding_strategy", "FULL_SHARD")).upper() != "FULL_SHARD":
+        return False
+    cap = 180 * 2**30
+    try:
+        import torch as _t
+
+        if device is not None and _t.device(device).type == "cuda" and _t.cuda.is_available():
+            cap = _t.cuda.get_device_properties(device).total_memory
+    except Exception:  # noqa: BLE001
+        pass
+    return 18 * int(n_params) > 0.4 * cap
+
+
 def build_nvl_comm(total: int, *, sharded: bool, rank: int, world_size: int, device: torch.device | int | None = None,
                    group: Any = None) -> Any:
     """Intra-client gradient communicator on NVLink: the fused ZeRO step when the config asks for sharding

@@ -161,8 +161,11 @@ def build_backend(model_cfg: MPTConfig, device: torch.device, precision: str, ke
         if unsupported:
             print(f"[backend] {', '.join(unsupported)} not covered by the sm_100a engine -> stock PyTorch backend "
                   "(explicit, logged; set kernels.*=torch to silence)", flush=True)
+            kw.pop("zero3", None)
             return TorchBackend(model_cfg, device=device, precision=precision, **kw)
         from photon_b200.models.engine import B200Engine
 
         return B200Engine(model_cfg, device=device, precision=precision, kernels=kernels, **kw)
+    if kw.pop("zero3", None) is not None:
+        raise RuntimeError("full parameter sharding (NvlZero3Comm) needs the sm_100a engine on a CUDA device")
     return TorchBackend(model_cfg, device=device, precision=precision, **kw)

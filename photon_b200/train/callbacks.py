@@ -272,6 +272,11 @@ class OptimizerMonitor(Callback):
         if tr.state.timestamp.batch % self.interval:
             return
         flat, opt = tr.state.flat, tr.state.optimizer
+        if getattr(flat, "is_sharded", False):      # every plane is this rank's shard: the norms span all ranks
+            gn = flat.comm.grad_norm
+            tr.log({"l2_norm/grad/global": float(gn(flat.grads)), "l2_norm/param/global": float(gn(flat.params)),
+                    "l2_norm/moment/global": float(gn(opt.exp_avg)), "l2_norm/second_moment_sqrt/global": float(gn(opt.exp_avg_sq.sqrt()))})
+            return
         m = {"l2_norm/grad/global": float(flat.grads.norm()), "l2_norm/param/global": float(flat.params.norm()),
              "l2_norm/moment/global": float(opt.exp_avg.norm()),
              "l2_norm/second_moment_sqrt/global": float(opt.exp_avg_sq.sqrt().norm())}

@@ -170,7 +170,8 @@ class Trainer:
                                       grads_storage=getattr(grad_comm, "grads", None),
                                       params_storage=getattr(grad_comm, "params", None),
                                       shadow_storage=getattr(grad_comm, "shadow", None),
-                                      activation_checkpointing=activation_checkpointing)
+                                      activation_checkpointing=activation_checkpointing,
+                                      **({"zero3": grad_comm} if getattr(grad_comm, "zero3", False) else {}))
         if hasattr(grad_comm, "bind_layout"):
             grad_comm.bind_layout(be.flat.layout)
         shadow = getattr(be, "bf16_params", None)
@@ -181,7 +182,8 @@ class Trainer:
         if self.fused_comm_step:
             # reduce-scatter + clip + optimizer + all-gather in one NVLink kernel: moments sharded like the arena
             shard_kw = dict(shard=grad_comm.shard(), shard_bounds=grad_comm.shard_bounds(), group=process_group)
-        elif shard_optimizer_state and self.world_size > 1:
+        elif shard_optimizer_state and self.world_size > 1 and not getattr(be.flat, "is_sharded", False):
+            # (under full parameter sharding the optimizer already sees nothing but this rank's shard)
             # ZeRO-style state sharding inside the client (the reference's fsdp_config FULL_SHARD / SHARD_GRAD_OP)
             bounds = shard_bounds(be.flat.params.numel(), self.world_size)
             shard_kw = dict(shard=bounds[self.rank], shard_bounds=bounds, group=process_group)
@@ -319,7 +321,12 @@ class Trainer:
             grad_mult = coef / scale if scale != 1.0 else coef
             self.log({"l2_norm/grad/clipped_from": gnorm})  # device scalar; floated lazily below
         if not skip:
+            z3 = self.grad_comm if getattr(self.grad_comm, "zero3", False) else None
+            if z3 is not None:
+                z3.before_param_write()       # peers have finished pulling this step's weights from this rank's shard
             st.optimizer.step(st.scheduler(st.timestamp.batch), grad_mult)
+            if z3 is not None:
+                z3.params_changed()           # every shard is new before anybody pulls for the next step
             if not (st.optimizer.use_kernel and st.optimizer.bf16_shadow is not None):
                 st.backend.params_updated()
         self.last_batch_stats = {"loss_sum": loss_sum, "n_tokens": n_tok, **({"unigram_loss_sum": uni_sum} if uni_sum is not None else {})}
@@ -327,6 +334,8 @@ class Trainer:
 
     def _grad_norm(self) -> torch.Tensor:
         g = self.state.flat.grads
+        if hasattr(self.grad_comm, "grad_norm"):     # sharded gradients: the norm spans every rank's shard
+            return self.grad_comm.grad_norm(g)
         if g.is_cuda and self.state.optimizer.use_kernel:
             from photon_b200 import ops
 
@@ -456,7 +465,8 @@ class Trainer:
         names = st.flat.layout.names
         return {
             "state": {
-                "model": {n: st.flat.layout.view(st.flat.params, i).detach().cpu().clone() for i, n in enumerate(names)},
+                "model": (lambda full: {n: st.flat.layout.view(full, i).detach().cpu().clone() for i, n in enumerate(names)})(
+                    st.flat.full_params()),
                 "optimizers": {type(st.optimizer).__name__: st.optimizer.state_dict()},
                 "schedulers": {"lr": {"last_batch": st.timestamp.batch}},
                 "timestamp": st.timestamp.state_dict(),
@@ -536,9 +546,12 @@ class Trainer:
         st = self.state
         if not ignored("model"):
             with torch.no_grad():
+                full = st.flat.full_params()      # the buffer itself, or a gathered copy under full parameter sharding
                 for i, n in enumerate(st.flat.layout.names):
                     if n in s["model"]:
-                        st.flat.layout.view(st.flat.params, i).copy_(s["model"][n])
+                        st.flat.layout.view(full, i).copy_(s["model"][n])
+                if getattr(st.flat, "is_sharded", False):
+                    st.flat.load_full_params(full)
             st.backend.params_updated()
         if not ignored("optimizers") and s.get("optimizers"):
             sd = s["optimizers"].get(type(st.optimizer).__name__)

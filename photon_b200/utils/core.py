@@ -77,7 +77,7 @@ def get_trainable_params_dict(model_or_trainer: Any, *, sort_dict: bool = True,
             items.sort(key=lambda kv: kv[0])
         return {n: (p if no_detach_and_clone else p.detach().clone()) for n, p in items}
     flat = _flat_of(model_or_trainer)
-    views = flat.layout.views(flat.params)
+    views = flat.layout.views(flat.full_params())      # assembled from the owners when the parameters are fully sharded
     return {n: (v if no_detach_and_clone else v.detach().clone()) for n, v in zip(flat.layout.names, views)}
 
 
@@ -90,13 +90,16 @@ def set_trainer_trainable_params_dict(trainer: Any, params: dict[str, Any]) -> N
     """Overwrite the named tensors (a subset is fine) and refresh the bf16 compute copy
     (ref: photon/utils.py:390-478 — there a pickled rank-0 broadcast under FSDP)."""
     flat = _flat_of(trainer)
+    full = flat.full_params()
     with torch.no_grad():
         for name, value in params.items():
-            view = flat.layout.view(flat.params, clean_parameter_name(name))
+            view = flat.layout.view(full, clean_parameter_name(name))
             t = torch.as_tensor(value)
             if tuple(t.shape) != tuple(view.shape):
                 raise ValueError(f"{name}: shape {tuple(t.shape)} != model {tuple(view.shape)}")
             view.copy_(t.to(view.device, view.dtype))
+    if flat.is_sharded:
+        flat.load_full_params(full)
     backend = getattr(getattr(trainer, "state", trainer), "backend", None)
     if backend is not None:
         backend.params_updated()
@@ -133,7 +136,7 @@ def get_wte_parameters_from_trainer(trainer: Any) -> np.ndarray:
     hits = [n for n in flat.layout.names if "wte" in n]
     if len(hits) != 1:
         raise ValueError("There are no WTE parameters" if not hits else "WTE parameters are not unique")
-    return flat.layout.view(flat.params, hits[0]).detach().cpu().numpy().copy()
+    return flat.layout.view(flat.full_params(), hits[0]).detach().cpu().numpy().copy()
 
 
 def set_wte_parameters_to_trainer(trainer: Any, wte_parameters: np.ndarray) -> None:

@@ -104,6 +104,8 @@ class FlatParams:
     """Owns the flat fp32 master buffer (+ grad buffer) of a model and re-points the
     module's ``Parameter.data`` / ``.grad`` at views of them."""
 
+    is_sharded = False      # photon_b200.parallel.zero3.ShardedFlat: ``params`` / ``grads`` are one rank's shard
+
     def __init__(self, model: nn.Module, align: int = 256, with_grad: bool = True,
                  device: torch.device | str | None = None, params_storage: torch.Tensor | None = None,
                  grads_storage: torch.Tensor | None = None) -> None:
@@ -140,6 +142,13 @@ class FlatParams:
             for i, (_, p) in enumerate(self._named):  # autograd may have replaced .grad
                 if p.grad is None or p.grad.data_ptr() != self.layout.view(self.grads, i).data_ptr():
                     p.grad = self.layout.view(self.grads, i)
+
+    def full_params(self) -> torch.Tensor:
+        """The whole fp32 vector (the buffer itself here; assembled from the owners under full sharding)."""
+        return self.params
+
+    def load_full_params(self, full: torch.Tensor) -> None:
+        self.params.copy_(full.to(self.params.device, torch.float32))
 
     def to_ndarrays(self) -> list[np.ndarray]:
         return self.layout.to_ndarrays(self.params)
