@@ -1,8 +1,10 @@
 """Server checkpoint store: layout, upload/download, resume-round resolution, restore
 from another run, cleanup (the role of ref photon/server/s3_utils.py:215-727,1261-1641).
 
-"Bucket" = a directory (``{saving_path}/{bucket_name}``) because there is no object store
-offline; the key layout is the reference's::
+"Bucket" = a directory (``{saving_path}/{bucket_name}``) that is the working copy; when an S3 endpoint is configured
+(``S3_ENDPOINT_URL`` / ``s3_comm_config.backend_kwargs.endpoint_url`` + ``AWS_*`` credentials → :mod:`photon_b200.utils.objstore`)
+every round is also uploaded under the same keys, rounds that exist only remotely are found and fetched on resume, and clean-up
+deletes both copies. The key layout is the reference's::
 
     {bucket}/{run_uuid}/server/{round}/state.bin
     {bucket}/{run_uuid}/server/{round}/current_server_parameters.npz      arr_i, sorted-name order
@@ -32,9 +34,23 @@ STATE_FILE = "state.bin"
 
 
 class CheckpointStore:
-    def __init__(self, root: str | Path, bucket_name: str = "checkpoints") -> None:
+    def __init__(self, root: str | Path, bucket_name: str = "checkpoints", remote: Any = None) -> None:
         self.bucket = Path(root) / bucket_name
         self.bucket.mkdir(parents=True, exist_ok=True)
+        self.remote = remote        # photon_b200.utils.objstore.ObjectStore or None
+
+    def _key(self, path: Path) -> str:
+        return path.relative_to(self.bucket).as_posix()
+
+    def _push(self, path: Path) -> None:
+        if self.remote is not None:
+            self.remote.upload(self._key(path), path)
+
+    def _ensure_local(self, path: Path) -> Path:
+        """Fetch ``path`` from the object store when this host does not have it (resume on another machine)."""
+        if not path.exists() and self.remote is not None and self.remote.exists(self._key(path)):
+            self.remote.download(self._key(path), path)
+        return path
 
     # -- key helpers ------------------------------------------------------------------
     def server_dir(self, run_uuid: str) -> Path:
@@ -48,9 +64,11 @@ class CheckpointStore:
 
     def list_objects(self, prefix: str | Path = "") -> list[str]:
         base = self.bucket / prefix
-        if not base.exists():
-            return []
-        return sorted(str(p.relative_to(self.bucket)) for p in base.rglob("*") if p.is_file())
+        local = {str(p.relative_to(self.bucket)) for p in base.rglob("*") if p.is_file()} if base.exists() else set()
+        if self.remote is not None:
+            pre = Path(prefix).as_posix() if str(prefix) else ""
+            local |= set(self.remote.list(pre + "/" if pre else ""))
+        return sorted(local)
 
     def delete_object(self, key: str | Path) -> None:
         p = self.bucket / key
@@ -58,6 +76,10 @@ class CheckpointStore:
             shutil.rmtree(p, ignore_errors=True)
         elif p.exists():
             p.unlink()
+        if self.remote is not None:
+            k = Path(key).as_posix()
+            self.remote.delete(k)
+            self.remote.delete_prefix(k + "/")
 
     # -- upload -----------------------------------------------------------------------
     def upload_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
@@ -76,9 +98,11 @@ class CheckpointStore:
             d.mkdir(parents=True, exist_ok=True)
             for key, arrs in arrays.items():
                 dump_model_parameters_to_file(d / f"{key}.npz", arrs)
+                self._push(d / f"{key}.npz")
             tmp = d / (STATE_FILE + ".tmp")
             tmp.write_bytes(blob)
-            tmp.replace(d / STATE_FILE)  # state.bin last: its presence marks the round complete
+            tmp.replace(d / STATE_FILE)  # state.bin last: its presence marks the round complete (locally and in the object store)
+            self._push(d / STATE_FILE)
 
         if background:
             self.submit(write)
@@ -135,11 +159,20 @@ class CheckpointStore:
     def obtain_sorted_rounds(self, run_uuid: str, state_keys: Sequence[str]) -> list[int]:
         """Rounds that are COMPLETE: state.bin + every state-key file present (ref: s3_utils.py:1261-1318)."""
         base = self.server_dir(run_uuid)
-        out = []
+        out = set()
         if base.exists():
             for p in base.iterdir():
                 if p.is_dir() and p.name.isdigit() and (p / STATE_FILE).exists() and all((p / f"{k}.npz").exists() for k in state_keys):
-                    out.append(int(p.name))
+                    out.add(int(p.name))
+        if self.remote is not None:     # rounds another host uploaded
+            have: dict[int, set[str]] = {}
+            pre = f"{run_uuid}/server/"
+            for k in self.remote.list(pre):
+                parts = k[len(pre):].split("/")
+                if len(parts) == 2 and parts[0].isdigit():
+                    have.setdefault(int(parts[0]), set()).add(parts[1])
+            want = {STATE_FILE, *(f"{k}.npz" for k in state_keys)}
+            out |= {r for r, files in have.items() if want <= files}
         return sorted(out)
 
     def interpret_resume_round(self, run_uuid: str, resume_round: int | None, state_keys: Sequence[str]) -> int | None:
@@ -159,10 +192,10 @@ class CheckpointStore:
     def download_server_checkpoint(self, run_uuid: str, server_round: int, *, layout: FlatLayout,
                                    state_keys: Sequence[str]) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
         d = self.round_dir(run_uuid, server_round)
-        state = load_server_state(d / STATE_FILE)
+        state = load_server_state(self._ensure_local(d / STATE_FILE))
         tensors: dict[str, torch.Tensor] = {}
         for key in state_keys:
-            arrays = load_model_parameters_from_file(d / f"{key}.npz")
+            arrays = load_model_parameters_from_file(self._ensure_local(d / f"{key}.npz"))
             flat = torch.zeros(layout.total, dtype=torch.float32)
             layout.from_ndarrays(flat, arrays)
             tensors[key] = flat
@@ -174,8 +207,10 @@ class CheckpointStore:
         src, dst = self.round_dir(old_uuid, server_round), self.round_dir(new_uuid, server_round)
         dst.mkdir(parents=True, exist_ok=True)
         for key in state_keys:  # includes the second momentum (the reference forgets it)
-            shutil.copy2(src / f"{key}.npz", dst / f"{key}.npz")
-        shutil.copy2(src / STATE_FILE, dst / STATE_FILE)
+            shutil.copy2(self._ensure_local(src / f"{key}.npz"), dst / f"{key}.npz")
+            self._push(dst / f"{key}.npz")
+        shutil.copy2(self._ensure_local(src / STATE_FILE), dst / STATE_FILE)
+        self._push(dst / STATE_FILE)
         if copy_client_checkpoints:
             for cid in client_ids:
                 s = self.client_dir(old_uuid, cid)
@@ -219,14 +254,24 @@ class CheckpointStore:
     # -- cleanup ------------------------------------------------------------------------
     def delete_rounds(self, run_uuid: str, keep_last: int = 0) -> None:
         base = self.server_dir(run_uuid)
-        if not base.exists():
-            return
-        rounds = sorted(int(p.name) for p in base.iterdir() if p.is_dir() and p.name.isdigit())
+        rounds = sorted(int(p.name) for p in base.iterdir() if p.is_dir() and p.name.isdigit()) if base.exists() else []
         complete = [r for r in rounds if (base / str(r) / STATE_FILE).exists()]
+        remote_rounds: set[int] = set()
+        if self.remote is not None:
+            pre = f"{run_uuid}/server/"
+            for k in self.remote.list(pre):
+                head = k[len(pre):].split("/")[0]
+                if head.isdigit():
+                    remote_rounds.add(int(head))
+                    if k.endswith("/" + STATE_FILE) and int(head) not in complete:
+                        complete.append(int(head))
+            complete.sort()
         keep = set(complete[-keep_last:]) if keep_last else set()
-        for r in rounds:
+        for r in sorted(set(rounds) | remote_rounds):
             if r not in keep:
                 shutil.rmtree(base / str(r), ignore_errors=True)
+                if r in remote_rounds:
+                    self.remote.delete_prefix(f"{run_uuid}/server/{r}/")
 
     def delete_clients_checkpoints(self, run_uuid: str, keep_latest: bool = False) -> None:
         base = self.bucket / run_uuid
@@ -244,6 +289,8 @@ class CheckpointStore:
             self.delete_clients_checkpoints(run_uuid, keep_latest=True)
         else:
             shutil.rmtree(self.bucket / run_uuid, ignore_errors=True)
+            if self.remote is not None:
+                self.remote.delete_prefix(f"{run_uuid}/")
 
 
 class _Foreign:
@@ -282,7 +329,18 @@ def load_server_state(path: str | Path) -> dict[str, Any]:
 
 
 def load_pretrained_model_from_path(path: str | Path) -> list[np.ndarray]:
-    """npz / npzc / bin, local path (``s3://`` is rejected offline) (ref: s3_utils.py:1192-1231)."""
+    """npz / npzc / bin from a local path or ``s3://bucket/key`` (needs ``S3_ENDPOINT_URL`` + ``AWS_*`` credentials in the
+    environment, like the reference's downloader) (ref: s3_utils.py:1192-1231)."""
     if str(path).startswith("s3://"):
-        raise RuntimeError("s3:// objects are unreachable in this environment; copy the file locally")
+        import tempfile
+
+        from photon_b200.utils.objstore import remote_store_from_cfg
+
+        bucket, _, key = str(path)[len("s3://"):].partition("/")
+        store = remote_store_from_cfg({"s3_comm_config": {"bucket_name": bucket}})
+        if store is None or not key:
+            raise RuntimeError(f"{path}: set S3_ENDPOINT_URL and AWS_ACCESS_KEY_ID / AWS_SECRET_ACCESS_KEY to read from an object store, "
+                               "or copy the file locally")
+        with tempfile.TemporaryDirectory() as td:
+            return load_model_parameters_from_file(store.download(key, Path(td) / Path(key).name))
     return load_model_parameters_from_file(path)

@@ -11,9 +11,10 @@ model reaches the clients — the four ``photon.comm_stack`` options.
 ``shm``    Reference-equivalent HOST path (ref: photon/server/s3_utils.py:865-903,
            photon/strategy/aggregation.py:57-75): D2H → per-tensor ndarrays → POSIX shm →
            rank-0 streaming mean + server optimizer on the CPU → shm → H2D.
-``s3``     Same as ``shm`` but through ``.npz`` objects in a directory (object-store stand-in),
-           layout ``{root}/{run_uuid}/server/comm_stack/{endpoint}/parameters.npz``
-           (ref: s3_utils.py:812-864).
+``s3``     Same as ``shm`` but through ``.npz`` objects, layout
+           ``{bucket}/{run_uuid}/server/comm_stack/{endpoint}/parameters.npz`` (ref: s3_utils.py:812-864): in an S3
+           bucket when an endpoint is configured (own SigV4 REST client, utils/objstore.py — works across hosts),
+           in a directory otherwise.
 =========  ================================================================================
 
 All share one interface: ``begin_round`` → ``add_client`` × k → ``finish_round`` →
@@ -319,15 +320,30 @@ class ShmRoundBackend(_HostAccumulating):
 
 
 class FileRoundBackend(_HostAccumulating):
-    """``comm_stack.s3``: npz objects under ``{root}/{run_uuid}/server/comm_stack/…``."""
+    """``comm_stack.s3``: npz objects under ``{bucket}/{run_uuid}/server/comm_stack/…`` (ref: photon/server/s3_utils.py:812-864).
+    With ``remote`` (an :class:`photon_b200.utils.objstore.ObjectStore`, i.e. a configured S3 endpoint) every object travels
+    through the store — ranks on different hosts need no shared file system; without it the bucket is a directory."""
 
     name = "s3"
 
-    def __init__(self, *a: Any, root: str | os.PathLike = "./checkpoints", run_uuid: str = "run", num_attempts: int = 3, **kw: Any) -> None:
+    def __init__(self, *a: Any, root: str | os.PathLike = "./checkpoints", run_uuid: str = "run", num_attempts: int = 3,
+                 remote: Any = None, **kw: Any) -> None:
         super().__init__(*a, **kw)
-        self.dir = Path(root) / run_uuid / "server" / "comm_stack"
+        self.bucket_dir = Path(root)
+        self.dir = self.bucket_dir / run_uuid / "server" / "comm_stack"
         self.dir.mkdir(parents=True, exist_ok=True)
         self.num_attempts = int(num_attempts)
+        self.remote = remote
+
+    def _publish(self, path: Path) -> None:
+        if self.remote is not None:
+            self.remote.upload(path.relative_to(self.bucket_dir).as_posix(), path)
+
+    def _fetch(self, path: Path, mine: bool = False) -> Path:
+        """Make ``path`` local: objects written by OTHER ranks always come from the store (a stale local copy must not win)."""
+        if self.remote is not None and not mine:
+            self.remote.download(path.relative_to(self.bucket_dir).as_posix(), path)
+        return path
 
     @property
     def server_device(self) -> torch.device:
@@ -347,6 +363,7 @@ class FileRoundBackend(_HostAccumulating):
         mine = self.dir / f"client-rank{self.rank}" / "parameters.npz"
         if have:
             dump_model_parameters_to_file(mine, self.layout.to_ndarrays(self._acc / self._w))
+            self._publish(mine)
         self._n = getattr(self, "_n", 0) + 1
         rec = (str(mine) if have else None, self._w)
         infos = self._gather_objects(f"s3_up/{self._n}", rec)
@@ -361,7 +378,7 @@ class FileRoundBackend(_HostAccumulating):
                 if path is None or w <= 0:
                     continue
                 host = torch.zeros(self.layout.total)
-                self.layout.from_ndarrays(host, self._load(Path(path)))
+                self.layout.from_ndarrays(host, self._load(self._fetch(Path(path), mine=(Path(path) == mine))))
                 sm.add(host, w)
             if sm.result() is not None:
                 avg = sm.result()
@@ -371,12 +388,13 @@ class FileRoundBackend(_HostAccumulating):
                 agg, agg_scale = avg.clone() if self.strategy.track_inplace else None, s
                 self.last_metrics = self.strategy.apply_server_update(avg, server_round)
             dump_model_parameters_to_file(down, self.layout.to_ndarrays(self.strategy.parameters))
+            self._publish(down)
         gap = self._fedavg_gap(agg, agg_scale)
         if gap:
             self.last_metrics = {**self.last_metrics, **gap}
         self._barrier(f"s3_written/{self._n}")
         host = torch.zeros(self.layout.total)
-        self.layout.from_ndarrays(host, self._load(down))
+        self.layout.from_ndarrays(host, self._load(self._fetch(down, mine=(self.rank == 0))))
         self._x_dev = host.to(self.device)
         self._barrier(f"s3_read/{self._n}")
         self.timings["aggregate_broadcast_s"] = time.perf_counter() - t0
@@ -477,6 +495,9 @@ def build_round_backend(cfg: Any, layout: FlatLayout, strategy: ServerStrategy, 
         return CollectiveRoundBackend(layout, strategy, device, **common)
     if active == "s3":
         root = cfg["photon"].get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
+        from photon_b200.utils.objstore import remote_store_from_cfg
+
         return FileRoundBackend(layout, strategy, device, root=Path(root) / str(cfg["s3_comm_config"]["bucket_name"]),
-                                run_uuid=str(cfg["run_uuid"]), num_attempts=int(cfg["s3_comm_config"].get("num_attempts", 3)), **common)
+                                run_uuid=str(cfg["run_uuid"]), num_attempts=int(cfg["s3_comm_config"].get("num_attempts", 3)),
+                                remote=remote_store_from_cfg(cfg), **common)
     return ShmRoundBackend(layout, strategy, device, run_uuid=str(cfg["run_uuid"]), **common)

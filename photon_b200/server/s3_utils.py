@@ -136,7 +136,9 @@ def _store(cfg: Any) -> CheckpointStore:
     import os
 
     root = cfg["photon"].get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
-    return CheckpointStore(root, str(cfg["s3_comm_config"]["bucket_name"]))
+    from photon_b200.utils.objstore import remote_store_from_cfg
+
+    return CheckpointStore(root, str(cfg["s3_comm_config"]["bucket_name"]), remote=remote_store_from_cfg(cfg))
 
 
 def interpret_resume_round(cfg: Any, state_keys: Sequence[str]) -> int | None:

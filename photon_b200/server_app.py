@@ -36,7 +36,9 @@ def _store_for(cfg: Any) -> CheckpointStore | None:
     if not (cfg["photon"]["checkpoint"] or cfg["photon"]["comm_stack"].get("s3")):
         return None
     root = cfg["photon"].get("saving_path") or os.environ.get("PHOTON_SAVE_PATH", ".")
-    return CheckpointStore(root, str(cfg["s3_comm_config"]["bucket_name"]))
+    from photon_b200.utils.objstore import remote_store_from_cfg
+
+    return CheckpointStore(root, str(cfg["s3_comm_config"]["bucket_name"]), remote=remote_store_from_cfg(cfg))
 
 
 def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int | None = None) -> WandbHistory:
