@@ -315,7 +315,8 @@ def run_ddp(env: Env, args, impl: str, K: int, W: int) -> dict:
     clk.stop()
     # the gradient all-reduce alone on the live bucket
     ar_ms = 0.0
-    if env.world > 1 and not getattr(tr.state.flat, "is_sharded", False):   # (fully sharded: reduced per block inside the backward)
+    # (fully sharded: reduced per block inside the backward; fused ZeRO-1 step: the reduction is part of the step kernel)
+    if env.world > 1 and not getattr(tr.state.flat, "is_sharded", False) and not getattr(tr, "fused_comm_step", False):
         g = tr.state.flat.grads
         for _ in range(3):
             tr._allreduce_grads()  # noqa: SLF001
