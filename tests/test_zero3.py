@@ -173,12 +173,14 @@ def test_sharded_trainer_steps_and_checkpoints_like_the_plain_one(tmp_path):
 
 
 @pytest.mark.gpu
-def test_two_ranks_fully_sharded_match_ddp(tmp_path):
-    """torchrun, 2 GPUs: ``kernels.param_sharding=zero3`` (per-block copy-engine gathers + fused reduce-scatter kernel) ends on the
-    same parameters as plain DDP with the fused all-reduce; every rank holds half of every plane."""
+@pytest.mark.parametrize("n", [2, 4])
+def test_ranks_fully_sharded_match_ddp(tmp_path, n):
+    """torchrun, n GPUs: ``kernels.param_sharding=zero3`` (per-block copy-engine gathers + fused reduce-scatter kernel: P2P loads at
+    n = 2, in-switch ``multimem.ld_reduce`` from n = 4 when NVLS is up) ends on the same parameters as plain DDP with the fused
+    all-reduce; every rank holds 1/n of every plane."""
     from test_multiproc_gpu import _torchrun
 
-    _torchrun(tmp_path, 2, """
+    _torchrun(tmp_path, n, """
         from photon_b200.config import compose
         from photon_b200.centralised_train import run_centralised
         rank = dist.get_rank(); dev = torch.device('cuda', rank)
@@ -186,19 +188,21 @@ def test_two_ranks_fully_sharded_match_ddp(tmp_path):
         for name, extra, cls in (('zero3', ['kernels.param_sharding=zero3'], 'NvlZero3Comm'), ('ddp', ['~llm_config.fsdp_config'], 'NvlGradComm')):
             cfg = compose(TINY + ['run_uuid=z3', 'dataset/streams@dataset.train.streams=centralised', 'dataset.train.root_local=synthetic://7',
                                   'llm_config.model.n_layers=3'] + extra)
-            tr = run_centralised(cfg, device=dev, rank=rank, world_size=2, duration='3ba')
+            W = dist.get_world_size()
+            tr = run_centralised(cfg, device=dev, rank=rank, world_size=W, duration='3ba')
             assert type(tr.grad_comm).__name__ == cls, (name, type(tr.grad_comm).__name__)
             x = tr.state.flat.full_params().clone()
             if name == 'zero3':
                 pl = tr.grad_comm.plan
-                assert tr.state.flat.params.numel() == pl.shard_len and 2 * pl.shard_len < 1.01 * pl.layout.total + 2 * 256 * len(pl.units)
+                assert tr.state.flat.params.numel() == pl.shard_len and W * pl.shard_len < 1.01 * pl.layout.total + W * 256 * len(pl.units)
+                print('nvls' if tr.grad_comm.arena.mc_ptr('gs0') else 'p2p', flush=True)
                 assert tr.state.optimizer.exp_avg.numel() == pl.shard_len
             ref = x.clone(); dist.broadcast(ref, src=0)
             assert torch.equal(ref, x), name + ': ranks assembled different models'
             outs[name] = x; outs[name + '_loss'] = tr.loggers[0].data['loss/train/total'][-1][1]
             tr.close()
         rel = ((outs['zero3'] - outs['ddp']).norm() / outs['ddp'].norm()).item()
-        assert rel < 1e-3, rel
+        assert rel < 2e-3, rel
         assert abs(outs['zero3_loss'] - outs['ddp_loss']) < 5e-3, (outs['zero3_loss'], outs['ddp_loss'])
         if rank == 0: print('RESULT_OK', rel)
     """, 29547)
