@@ -20,6 +20,13 @@ class ClientApp:
         self.nm = NodeManagerApp(cfg, n_workers=n_workers, devices=devices)
         self.refresh_period = int(cfg["photon"].get("refresh_period", 50))
 
+    def alive(self) -> bool:
+        """Every worker process of this node is up (what makes the node show up in ``node_ids()``)."""
+        return bool(self.nm.workers) and all(w.is_alive() for w in self.nm.workers)
+
+    def shutdown(self) -> None:
+        self.nm.close()
+
     @contextlib.contextmanager
     def lifespan(self) -> Iterator["ClientApp"]:
         """Workers live as long as the app (the reference's ``--persist-client`` fork feature)."""

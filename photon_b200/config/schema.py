@@ -49,8 +49,19 @@ class Centralized(_Strict):
     reset_timestamp: bool = False
 
 
+class Fleet(_Strict):
+    """Cross-host nodes of ``photon.topology=nodes`` (photon_b200/server/grpc_fleet.py): the server listens on ``address`` and waits
+    for ``n_remote_nodes`` machines running ``python -m photon_b200.node --server host:port``."""
+
+    address: str | None = None            # host:port the fleet link binds (null = every interface, an ephemeral port — printed at start)
+    n_remote_nodes: int = 0
+    liveness_timeout_s: float = 30.0      # a node that has not polled for this long is gone (its client goes to another node)
+    connect_timeout_s: float = 600.0      # how long the server waits for the remote nodes to register
+
+
 class Photon(_Strict):
-    n_nodes: int = 1
+    n_nodes: int = 1                      # in-process nodes of topology=nodes (0 = the server machine trains nothing itself)
+    fleet: Fleet = Field(default_factory=Fleet)
     task_timeout_s: float | None = None   # node manager: presume the workers hung after this long without a result (null = wait forever)
     topology: str = "spmd"   # spmd: one process per GPU + fused round transports; nodes: server → ClientApp → NodeManager → Workers
     refresh_period: int = 50
@@ -72,11 +83,18 @@ class Photon(_Strict):
     progress_timeout_s: float = 900.0     # a rank whose main thread made no progress for this long stops its heartbeat (hung = dead)
     kernel_peer_timeout_s: float = 120.0  # bound on every cross-GPU spin inside the NVLink kernels (aborted round instead of a hang)
 
-    @field_validator("n_nodes", "refresh_period")
+    @field_validator("refresh_period")
     @classmethod
     def _positive(cls, v: int) -> int:
         if v < 1:
             raise ValueError("must be >= 1")
+        return v
+
+    @field_validator("n_nodes")
+    @classmethod
+    def _non_negative(cls, v: int) -> int:
+        if v < 0:
+            raise ValueError("must be >= 0")
         return v
 
     @field_validator("topology")

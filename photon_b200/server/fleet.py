@@ -16,6 +16,11 @@
   respawned and the client retried (ref: photon/node_manager/node_manager_app.py:405-592).
 
 The SPMD runtime (:mod:`photon_b200.federation`) is the fast path — one process per GPU and the fused NVLink round kernel.
+Nodes on OTHER machines join through the gRPC fleet link (``photon.fleet.address`` + ``photon.fleet.n_remote_nodes``,
+:mod:`photon_b200.server.grpc_fleet`; start ``python -m photon_b200.node --server host:port`` on each machine): they are scheduled
+through the same work queue as the in-process ones, get their parameters through the S3 bucket (or inline in the gRPC message
+when no object store is configured) and drop out of ``node_ids()`` when they stop polling.
+
 This one exists for parity with the reference's deployment shape (persistent worker processes that can be recycled every
 ``photon.refresh_period`` rounds, host-side server) and as the oracle the SPMD path is compared against.
 """
@@ -59,9 +64,14 @@ class NodeFleetRuntime(FederationRuntime):
 
     def __init__(self, cfg: Any, *, n_nodes: int | None = None, workers_per_node: int | None = None) -> None:
         super().__init__(cfg, device=torch.device("cpu"), rank=0, world_size=1)
-        self.n_nodes = int(n_nodes or cfg["photon"].get("n_nodes", 1))
+        self.n_nodes = int(n_nodes if n_nodes is not None else cfg["photon"].get("n_nodes", 1))     # in-process nodes
         self.workers_per_node = workers_per_node
-        self.apps: list[ClientApp] = []
+        self.apps: list[Any] = []            # in-process ClientApp objects and RemoteNode handles (same ``handle`` / ``alive`` interface)
+        fleet = dict(cfg["photon"].get("fleet") or {})
+        self.fleet_address = fleet.get("address") or None
+        self.n_remote_nodes = int(fleet.get("n_remote_nodes", 0) or 0)
+        self.fleet_liveness_s = float(fleet.get("liveness_timeout_s", 30.0) or 30.0)
+        self.link: Any = None
         self._pool: ThreadPoolExecutor | None = None
         self._uid = f"pb200_{uuid.uuid4().hex[:8]}"
 
@@ -70,30 +80,67 @@ class NodeFleetRuntime(FederationRuntime):
         _, self.model_layout = get_raw_model_parameters(self.cfg)      # CPU model → names/shapes only (ref: node_manager_app.py:261-271)
         self.layout = self.model_layout.stacked(("", "exp_avg/", "exp_avg_sq/")) if self.aggregate_momenta else self.model_layout
         self.round_backend = CollectiveRoundBackend(self.layout, self.strategy, self.device)   # world 1 → plain host server
-        groups = split_devices(get_n_cuda_devices(), self.n_nodes)
+        groups = split_devices(get_n_cuda_devices(), self.n_nodes) if self.n_nodes > 0 else []
         for i, devs in enumerate(groups):
             app = ClientApp(self.cfg, n_workers=self.workers_per_node or (len(devs) if devs else 1), node_id=i, devices=devs)
             app.nm.create_and_start_workers()
             self.apps.append(app)
-        self._pool = ThreadPoolExecutor(max_workers=self.n_nodes, thread_name_prefix="node")
-        wait_for_nodes_to_connect(self.n_nodes, self.node_ids, poll_s=0.05, timeout_s=300.0)
+        if self.n_remote_nodes > 0:
+            import os
+
+            fleet = dict(self.cfg["photon"].get("fleet") or {})
+            from photon_b200.server.grpc_fleet import FleetLink
+
+            tls = (os.environ.get("PHOTON_FLEET_TLS_KEY"), os.environ.get("PHOTON_FLEET_TLS_CERT"))
+            self.link = FleetLink(self.fleet_address or "0.0.0.0:0", cfg=self.cfg, token=os.environ.get("PHOTON_FLEET_TOKEN"),
+                                  liveness_timeout_s=self.fleet_liveness_s, tls=tls if all(tls) else None)
+            print(f"[fleet] link listening on port {self.link.port}; waiting for {self.n_remote_nodes} remote node(s)", flush=True)
+            self.apps += self.link.wait_for_nodes(self.n_remote_nodes, timeout_s=float(fleet.get("connect_timeout_s", 600.0) or 600.0))
+        if not self.apps:
+            raise ValueError("photon.topology=nodes needs photon.n_nodes >= 1 or photon.fleet.n_remote_nodes >= 1")
+        self.n_nodes = len(self.apps)        # what the round loop waits for / reports: in-process + remote
+        self._pool = ThreadPoolExecutor(max_workers=len(self.apps), thread_name_prefix="node")
+        wait_for_nodes_to_connect(len(self.apps), self.node_ids, poll_s=0.05, timeout_s=300.0)
 
     def node_ids(self) -> list[int]:
-        return [a.node_id for a in self.apps if a.nm.workers and all(w.is_alive() for w in a.nm.workers)]
+        return [a.node_id for a in self.apps if a.alive()]
 
     # --------------------------------------------------------------------- broadcast (R2)
     def broadcast_to_nodes(self) -> dict[str, Any]:
         """One payload on the side channel, one QUERY per node, wait for every ack."""
         assert self._pool is not None and self.round_backend is not None
         t0 = time.time()
-        handle = replace_remote_with_parameters_in_recordset(
-            ParamHandle("inline", self.round_backend.global_params()), {"shm": True}, endpoint_id=f"{self._uid}_bcast", layout=self.layout)
+        local = [a for a in self.apps if not getattr(a, "remote", False)]
+        remote = [a for a in self.apps if getattr(a, "remote", False) and a.alive()]
+        handles: list[ParamHandle] = []
         try:
-            futs = [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": handle}, node_id=app.node_id))
-                    for app in self.apps]
+            futs = []
+            if local:       # one POSIX segment for every node of this machine
+                h = replace_remote_with_parameters_in_recordset(
+                    ParamHandle("inline", self.round_backend.global_params()), {"shm": True}, endpoint_id=f"{self._uid}_bcast", layout=self.layout)
+                handles.append(h)
+                futs += [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": h}, node_id=app.node_id))
+                         for app in local]
+            if remote:      # one object in the bucket for every other machine (or, without a store, the arrays in the message)
+                from photon_b200.utils.objstore import remote_store_from_cfg
+
+                store = remote_store_from_cfg(self.cfg)
+                inline = ParamHandle("inline", self.round_backend.global_params())
+                if store is not None:
+                    h = replace_remote_with_parameters_in_recordset(
+                        inline, "s3", endpoint_id="server", layout=self.layout, store=store, bucket=str(self.cfg["s3_comm_config"]["bucket_name"]),
+                        folder_name=f"{self.cfg['run_uuid']}/server/comm_stack")
+                    handles.append(h)
+                else:
+                    from photon_b200.server.s3_utils import _as_arrays
+
+                    h = ParamHandle("inline", _as_arrays(inline.data, self.layout))
+                futs += [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": h}, node_id=app.node_id))
+                         for app in remote]
             acks = [f.result() for f in futs]
         finally:
-            release_remote_parameters(handle)
+            for h in handles:
+                release_remote_parameters(h)
         bad = [a.error for a in acks if a.error or a.content != {"broadcast": {"status": "OK"}}]
         if bad:
             raise RuntimeError(f"broadcast not acknowledged by {len(bad)} node(s): {bad[:2]}")
@@ -133,10 +180,17 @@ class NodeFleetRuntime(FederationRuntime):
         results: list[FitRes] = []
         t0 = time.time()
         with tracer().span("fit_clients", cat="server", server_round=server_round):
-            for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps], dispatch, poll, poll_s=0.01):
+            for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps if a.alive()], dispatch, poll, poll_s=0.01,
+                                                     is_alive=lambda n: by_id[n].alive()):
                 for res in reply.content or [FitRes(Status(Code.FAILED, reply.error or "empty reply"), None, 0, {}, cid)]:
                     if res.status.code == Code.OK and res.parameters is not None:
                         flat = torch.zeros(self.layout.total, dtype=torch.float32)
+                        if res.parameters.kind != "inline":     # a remote node parked its result in the bucket
+                            from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
+
+                            parked = res.parameters
+                            res.parameters = replace_parameters_in_recordset_with_remote(parked)
+                            release_remote_parameters(parked)
                         self.layout.from_ndarrays(flat, res.parameters.data)   # streaming: fold in, then drop the payload
                         rb.add_client(flat, res.num_examples)
                         res = FitRes(res.status, ParamHandle(kind=rb.name), res.num_examples, res.metrics, res.cid)
@@ -149,15 +203,19 @@ class NodeFleetRuntime(FederationRuntime):
         self.broadcast_to_nodes()
         per = {int(cid): self.eval_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative).to_wire() for cid in sampled}
         msg = fit_or_evaluate_ins("evaluate", server_round, list(per), self.client_states, self.server_steps_cumulative, per)
-        rep = self.apps[0].handle(msg)     # the reference evaluates on ONE node (client id 0, all streams concatenated)
+        first = next((a for a in self.apps if a.alive()), self.apps[0])
+        rep = first.handle(msg)     # the reference evaluates on ONE node (client id 0, all streams concatenated)
         res = rep.content
         return [res] if isinstance(res, EvaluateRes) else [EvaluateRes(Status(Code.FAILED, rep.error or "no result"), 0.0, 0, {})]
 
     # --------------------------------------------------------------------------- close
     def close(self) -> None:
         for app in self.apps:
-            app.nm.close()
+            app.shutdown()
         self.apps = []
+        if self.link is not None:
+            self.link.close()
+            self.link = None
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None

@@ -1,0 +1,307 @@
+"""Cross-host node fleet over gRPC: the reference's SuperLink ↔ SuperNode link.
+
+The reference deploys one Flower SuperLink next to the server app and one SuperNode per machine; nodes CONNECT to the link and
+pull their work from it, so only the server needs a reachable address (ref: scripts/photon_llm.sh launch order, photon/client_app.py,
+photon/server_app.py:285,346 — ``driver.get_node_ids()`` is whoever is connected right now). Same shape here, on ``grpcio`` with
+generic (bytes-in / bytes-out) method handlers — no generated stubs:
+
+* :class:`FleetLink` (server process): ``Register`` hands a node its id AND the run's composed config (a node needs nothing but
+  the server's address), ``Pull`` is a long poll for the node's next :class:`~photon_b200.messages.Message`, ``Push`` returns the
+  reply, ``Beat`` is the heartbeat of a node that is busy training. Every call refreshes the node's liveness; a node silent for ``liveness_timeout_s`` drops out of ``node_ids()`` and whatever
+  it was running comes back as a FAILED result, which the round loop already knows how to handle (``accept_failures_cnt``,
+  re-queue on another node).
+* :class:`RemoteNode`: the server-side stand-in with the ``handle(msg) -> Message`` interface of an in-process
+  :class:`~photon_b200.client_app.ClientApp` — :class:`~photon_b200.server.fleet.NodeFleetRuntime` schedules local and remote
+  nodes through the same work queue.
+* :func:`serve_node` (node process, ``python -m photon_b200.node``): registers, builds its ``ClientApp`` (node manager + one
+  worker per local GPU, DDP / ZeRO inside the node), then pull → handle → push until the server says ``shutdown``.
+
+Parameters never ride inside a control message when an object store is configured (``S3_ENDPOINT_URL`` …): both directions park
+them in the bucket and send the key (``ParamHandle("s3", key)``), like the reference's ``comm_stack.s3``. Without a store they
+travel inline in the gRPC message (pickled ndarrays; fine up to the 2 GiB gRPC frame, i.e. models up to ≈ 500 M parameters).
+
+Messages are pickled: the link is for a trusted cluster (as the reference's pickled payloads are). ``PHOTON_FLEET_TOKEN`` — when set
+on both sides — is checked on every call; TLS: pass ``tls=(key, cert)`` / ``tls_ca`` (env ``PHOTON_FLEET_TLS_KEY`` / ``_CERT`` / ``_CA``).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import queue
+import threading
+import time
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Any
+
+from photon_b200.messages import Code, EvaluateRes, FitRes, Message, ParamHandle, Status
+
+SERVICE = "photon.Fleet"
+_MAX_MSG = 2**31 - 1
+_OPTS = [("grpc.max_send_message_length", _MAX_MSG), ("grpc.max_receive_message_length", _MAX_MSG),
+         ("grpc.keepalive_time_ms", 30000), ("grpc.keepalive_permit_without_calls", 1)]
+
+
+def _ser(obj: Any) -> bytes:
+    return pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+
+
+def _de(data: bytes) -> Any:
+    return pickle.loads(data)  # noqa: S301 - trusted cluster link (see module docstring)
+
+
+def _failed(msg: Message, why: str) -> Message:
+    bad: Any = None
+    if msg.kind == "train":
+        cids = list(getattr(msg, "per_client", {}) or [None])
+        bad = [FitRes(Status(Code.FAILED, why), None, 0, {}, c) for c in cids]
+    elif msg.kind == "evaluate":
+        bad = EvaluateRes(Status(Code.FAILED, why), 0.0, 0, {})
+    return Message(msg.kind, bad, node_id=msg.node_id, error=why, reply_to=msg.msg_id)
+
+
+class _Slot:
+    def __init__(self, node_id: int, info: dict[str, Any]) -> None:
+        self.node_id, self.info = node_id, info
+        self.outbox: "queue.Queue[Message]" = queue.Queue()
+        self.pending: dict[int, tuple[Message, Future]] = {}
+        self.last_seen = time.time()
+        self.lock = threading.Lock()
+        self.gone = False
+
+
+class RemoteNode:
+    """Server-side handle of a connected node (``ClientApp`` interface)."""
+
+    def __init__(self, link: "FleetLink", slot: _Slot) -> None:
+        self._link, self._slot = link, slot
+        self.node_id = slot.node_id
+        self.remote = True
+
+    def alive(self) -> bool:
+        return not self._slot.gone and time.time() - self._slot.last_seen < self._link.liveness_timeout_s
+
+    def handle(self, msg: Message) -> Message:
+        """Send ``msg`` to the node and wait for its reply; a node that stops polling turns into a FAILED reply."""
+        s = self._slot
+        fut: Future = Future()
+        with s.lock:
+            msg.msg_id = self._link.next_msg_id()
+            msg.node_id = self.node_id
+            s.pending[msg.msg_id] = (msg, fut)
+        s.outbox.put(msg)
+        while True:
+            try:
+                return fut.result(timeout=1.0)
+            except TimeoutError:
+                if not self.alive():
+                    with s.lock:
+                        s.pending.pop(msg.msg_id, None)
+                    return _failed(msg, f"node {self.node_id} stopped responding ({time.time() - s.last_seen:.0f} s since its last call)")
+
+    def shutdown(self) -> None:
+        if self.alive():
+            self._slot.outbox.put(Message("shutdown", None, node_id=self.node_id))
+
+
+class FleetLink:
+    def __init__(self, address: str = "0.0.0.0:0", *, cfg: Any = None, token: str | None = None, liveness_timeout_s: float = 30.0,
+                 tls: tuple[str, str] | None = None) -> None:
+        import grpc
+
+        self.cfg, self.token, self.liveness_timeout_s = cfg, token, float(liveness_timeout_s)
+        self._slots: dict[int, _Slot] = {}
+        self._lock = threading.Lock()
+        self._msg_id = 0
+        self._server = grpc.server(ThreadPoolExecutor(max_workers=64, thread_name_prefix="fleet-link"), options=_OPTS)
+        ident = lambda b: b  # noqa: E731 - payloads are already bytes
+        handlers = {name: grpc.unary_unary_rpc_method_handler(getattr(self, "_" + name.lower()), request_deserializer=ident, response_serializer=ident)
+                    for name in ("Register", "Pull", "Push", "Beat")}
+        self._server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(SERVICE, handlers),))
+        if tls is not None:
+            key, cert = (open(p, "rb").read() for p in tls)
+            self.port = self._server.add_secure_port(address, grpc.ssl_server_credentials([(key, cert)]))
+        else:
+            self.port = self._server.add_insecure_port(address)
+        if not self.port:
+            raise RuntimeError(f"fleet link could not bind {address}")
+        self._server.start()
+
+    # ------------------------------------------------------------------ rpc handlers
+    def _auth(self, context: Any) -> None:
+        import grpc
+
+        if self.token and dict(context.invocation_metadata()).get("x-photon-token") != self.token:
+            context.abort(grpc.StatusCode.UNAUTHENTICATED, "bad fleet token")
+
+    def _slot(self, node_id: int, context: Any) -> _Slot:
+        import grpc
+
+        s = self._slots.get(int(node_id))
+        if s is None or s.gone:
+            context.abort(grpc.StatusCode.NOT_FOUND, f"node {node_id} is not registered")
+        s.last_seen = time.time()
+        return s
+
+    def _register(self, request: bytes, context: Any) -> bytes:
+        self._auth(context)
+        info = _de(request)
+        with self._lock:
+            node_id = max(list(self._slots) + [int(info.get("first_id", 1000)) - 1]) + 1
+            self._slots[node_id] = _Slot(node_id, info)
+        print(f"[fleet] node {node_id} registered: {info.get('host')} devices={info.get('devices')} workers={info.get('n_workers')}", flush=True)
+        return _ser({"node_id": node_id, "cfg": self.cfg, "liveness_timeout_s": self.liveness_timeout_s})
+
+    def _beat(self, request: bytes, context: Any) -> bytes:
+        """Heartbeat of a node that is busy training (it does not poll while it works)."""
+        self._auth(context)
+        self._slot(_de(request)["node_id"], context)
+        return _ser(True)
+
+    def _pull(self, request: bytes, context: Any) -> bytes:
+        self._auth(context)
+        req = _de(request)
+        s = self._slot(req["node_id"], context)
+        try:
+            msg = s.outbox.get(timeout=float(req.get("wait_s", 2.0)))
+        except queue.Empty:
+            return _ser(None)
+        s.last_seen = time.time()
+        return _ser(msg)
+
+    def _push(self, request: bytes, context: Any) -> bytes:
+        self._auth(context)
+        req = _de(request)
+        s = self._slot(req["node_id"], context)
+        reply: Message = req["reply"]
+        with s.lock:
+            entry = s.pending.pop(int(reply.reply_to) if reply.reply_to is not None else -1, None)
+        if entry is not None:
+            entry[1].set_result(reply)
+        return _ser(True)
+
+    # ------------------------------------------------------------------ server API
+    def next_msg_id(self) -> int:
+        with self._lock:
+            self._msg_id += 1
+            return self._msg_id
+
+    def nodes(self) -> list[RemoteNode]:
+        return [RemoteNode(self, s) for s in self._slots.values() if not s.gone]
+
+    def wait_for_nodes(self, n: int, timeout_s: float = 600.0, poll_s: float = 0.1) -> list[RemoteNode]:
+        """Block until ``n`` nodes have registered (ref: photon/server/server_util.py ``wait_for_nodes_to_connect``)."""
+        t0 = time.time()
+        while len(self._slots) < n:
+            if time.time() - t0 > timeout_s:
+                raise TimeoutError(f"{len(self._slots)} of {n} remote nodes connected to the fleet link within {timeout_s:.0f} s")
+            time.sleep(poll_s)
+        return self.nodes()
+
+    def close(self, grace_s: float = 2.0) -> None:
+        for n in self.nodes():
+            n.shutdown()
+        t0 = time.time()
+        while time.time() - t0 < grace_s and any(not s.outbox.empty() for s in self._slots.values()):
+            time.sleep(0.05)
+        for s in self._slots.values():
+            s.gone = True
+        self._server.stop(grace=grace_s)
+
+
+# ---------------------------------------------------------------------------------------------------------------- node side
+def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
+    """Node → server parameters through the object store when there is one (key in the message instead of the arrays)."""
+    from photon_b200.utils.objstore import remote_store_from_cfg
+
+    store = remote_store_from_cfg(cfg)
+    if store is None or reply.kind != "train" or not isinstance(reply.content, list):
+        return reply
+    import tempfile
+    from pathlib import Path
+
+    from photon_b200.utils.core import dump_model_parameters_to_file
+
+    for res in reply.content:
+        if isinstance(res, FitRes) and res.parameters is not None and res.parameters.kind == "inline":
+            key = f"{cfg['run_uuid']}/server/comm_stack/node-{node_id}/client_{res.cid}.npz"
+            with tempfile.TemporaryDirectory() as td:
+                p = dump_model_parameters_to_file(Path(td) / "p.npz", list(res.parameters.data))
+                store.upload(key, p)
+            res.parameters = ParamHandle("s3", key, {"bucket": str(cfg["s3_comm_config"]["bucket_name"])})
+    return reply
+
+
+def serve_node(server_address: str, *, n_workers: int | None = None, devices: list[int] | None = None, token: str | None = None,
+               tls_ca: str | None = None, first_id: int = 1000, max_idle_s: float | None = None) -> int:
+    """Run one node until the server shuts the fleet down (or is unreachable for ``max_idle_s``). Returns the node id."""
+    import socket
+
+    import grpc
+
+    token = token if token is not None else os.environ.get("PHOTON_FLEET_TOKEN")
+    tls_ca = tls_ca or os.environ.get("PHOTON_FLEET_TLS_CA")
+    channel = (grpc.secure_channel(server_address, grpc.ssl_channel_credentials(open(tls_ca, "rb").read()), options=_OPTS) if tls_ca
+               else grpc.insecure_channel(server_address, options=_OPTS))
+    md = (("x-photon-token", token),) if token else ()
+    ident = lambda b: b  # noqa: E731
+    call = {name: channel.unary_unary(f"/{SERVICE}/{name}", request_serializer=ident, response_deserializer=ident)
+            for name in ("Register", "Pull", "Push", "Beat")}
+    t0 = time.time()
+    while True:     # the server may come up after its nodes (the reference starts the supernodes in any order)
+        try:
+            reg = _de(call["Register"](_ser({"host": socket.gethostname(), "pid": os.getpid(), "n_workers": n_workers, "devices": devices, "first_id": first_id}),
+                                       metadata=md, timeout=30.0))
+            break
+        except grpc.RpcError as e:
+            if e.code() == grpc.StatusCode.UNAUTHENTICATED or time.time() - t0 > (max_idle_s or 600.0):
+                raise
+            time.sleep(1.0)
+    node_id, cfg = int(reg["node_id"]), reg["cfg"]
+    from photon_b200.client_app import ClientApp
+
+    app = ClientApp(cfg, n_workers=n_workers, node_id=node_id, devices=devices)
+    app.nm.create_and_start_workers()
+    print(f"[node {node_id}] connected to {server_address}; {len(app.nm.workers)} worker(s)", flush=True)
+    last_ok = time.time()
+    stop = threading.Event()
+
+    def heartbeat() -> None:     # a training task takes minutes; the link must keep hearing from this node meanwhile
+        period = max(0.2, float(reg.get("liveness_timeout_s", 30.0)) / 4.0)
+        while not stop.wait(period):
+            try:
+                call["Beat"](_ser({"node_id": node_id}), metadata=md, timeout=10.0)
+            except grpc.RpcError:
+                pass
+
+    threading.Thread(target=heartbeat, name="photon-node-heartbeat", daemon=True).start()
+    try:
+        while True:
+            try:
+                msg = _de(call["Pull"](_ser({"node_id": node_id, "wait_s": 2.0}), metadata=md, timeout=30.0))
+                last_ok = time.time()
+            except grpc.RpcError as e:
+                if e.code() == grpc.StatusCode.NOT_FOUND or (max_idle_s is not None and time.time() - last_ok > max_idle_s):
+                    print(f"[node {node_id}] lost the fleet link ({e.code().name}); leaving", flush=True)
+                    break
+                time.sleep(0.5)
+                continue
+            if msg is None:
+                continue
+            if msg.kind == "shutdown":
+                break
+            reply = app.handle(msg)
+            reply.reply_to = msg.msg_id
+            reply = _park_results(reply, cfg, node_id)
+            for attempt in range(5):
+                try:
+                    call["Push"](_ser({"node_id": node_id, "reply": reply}), metadata=md, timeout=3600.0)
+                    break
+                except grpc.RpcError:
+                    if attempt == 4:
+                        raise
+                    time.sleep(1.0 + attempt)
+    finally:
+        stop.set()
+        app.nm.close()
+        channel.close()
+    return node_id

@@ -9,7 +9,9 @@ Here the message field is a ``ParamHandle`` and the places are
 ``nvl``       the symmetric NVLink arena — nothing to move; the fused round kernel reads/writes the planes
 ``inline``    same process (SPMD runtime, tests): the flat tensor / ndarray list itself
 ``shm``       one flat POSIX segment named ``endpoint_id`` + ``ModelParametersMetadata`` (node manager path)
-``file``      ``{root}/{folder_name}/{endpoint_id}/{file_name}.npz`` — the object-store stand-in (no S3 offline)
+``file``      ``{root}/{folder_name}/{endpoint_id}/{file_name}.npz`` — a directory standing in for the bucket
+``s3``        key of an npz object in the configured S3 bucket (``utils/objstore.py``); the way parameters reach nodes on
+              OTHER hosts (``server/grpc_fleet.py``)
 ============  ==========================================================================================
 
 ``replace_remote_with_parameters_in_recordset`` (sender) and ``replace_parameters_in_recordset_with_remote``
@@ -58,8 +60,16 @@ def _as_arrays(data: Any, layout: FlatLayout | None) -> list[np.ndarray]:
 def replace_remote_with_parameters_in_recordset(handle: ParamHandle, comm_stack: Any, *, endpoint_id: str,
                                                 layout: FlatLayout | None = None, root: str | Path | None = None,
                                                 folder_name: str = "comm_stack", file_name: str = "parameters",
-                                                num_attempts: int = 3) -> ParamHandle:
-    """SENDER: move an inline payload onto the side channel and return the locator handle."""
+                                                num_attempts: int = 3, store: Any = None, bucket: str | None = None) -> ParamHandle:
+    """SENDER: move an inline payload onto the side channel and return the locator handle. ``store`` (an object store) +
+    ``comm_stack="s3"``: the payload becomes the object ``{folder_name}/{endpoint_id}/{file_name}.npz`` of the bucket."""
+    if store is not None and comm_stack == "s3" and handle.kind == "inline":
+        import tempfile
+
+        key = f"{folder_name}/{endpoint_id}/{file_name}.npz"
+        with tempfile.TemporaryDirectory() as td:
+            store.upload(key, dump_model_parameters_to_file(Path(td) / "p.npz", _as_arrays(handle.data, layout)))
+        return ParamHandle("s3", key, {"bucket": bucket, "endpoint_id": endpoint_id})
     kind = _comm_kind(comm_stack)
     if handle.kind != "inline" or kind in ("inline", "nvl"):
         return handle if kind != "nvl" else ParamHandle("nvl", None, dict(handle.meta))
@@ -93,6 +103,16 @@ def replace_parameters_in_recordset_with_remote(handle: ParamHandle, *, layout: 
         shm, views = get_parameters_shm(str(handle.data), meta, copy=True)
         shm.close()
         arrays = [v.astype(np.float32, copy=False) for v in views]
+    elif handle.kind == "s3":
+        import tempfile
+
+        from photon_b200.utils.objstore import remote_store_from_cfg
+
+        store = remote_store_from_cfg({"s3_comm_config": {"bucket_name": handle.meta.get("bucket") or "checkpoints", "num_attempts": num_attempts}})
+        if store is None:
+            raise RuntimeError(f"parameters were parked in an object store ({handle.data}) but this process has no S3_ENDPOINT_URL / AWS_* settings")
+        with tempfile.TemporaryDirectory() as td:
+            arrays = load_model_parameters_from_file(store.download(str(handle.data), Path(td) / "p.npz"))
     elif handle.kind == "file":
         last: Exception | None = None
         for attempt in range(max(1, num_attempts)):
@@ -129,6 +149,12 @@ def release_remote_parameters(handle: ParamHandle) -> None:
         unlink_quietly(str(handle.data))
     elif handle.kind == "file":
         Path(str(handle.data)).unlink(missing_ok=True)
+    elif handle.kind == "s3":
+        from photon_b200.utils.objstore import remote_store_from_cfg
+
+        store = remote_store_from_cfg({"s3_comm_config": {"bucket_name": handle.meta.get("bucket") or "checkpoints"}})
+        if store is not None:
+            store.delete(str(handle.data))
 
 
 # ------------------------------------------------------------------ checkpoint API, reference-style free functions

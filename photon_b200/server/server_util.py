@@ -57,11 +57,15 @@ class ClientScheduler:
 
     def __init__(self, sampled_clients: Iterable[int], node_ids: Iterable[int],
                  dispatch: Callable[[int, int], None], poll: Callable[[], list[tuple[int, int, Any]]],
-                 poll_s: float = 0.0) -> None:
+                 poll_s: float = 0.0, is_alive: Callable[[int], bool] | None = None) -> None:
+        """``is_alive(node_id)``: a node that is gone when its reply comes back (a remote node that stopped polling, a node whose
+        workers died) leaves the rotation and the client it held goes to the next free node (ref: the node manager re-queues the
+        client of a dead worker, photon/node_manager/node_manager_app.py:553-579; Flower drops silent nodes from ``get_node_ids``)."""
         self.queue = deque(sampled_clients)
         self.free = deque(node_ids)
-        self.dispatch, self.poll, self.poll_s = dispatch, poll, poll_s
+        self.dispatch, self.poll, self.poll_s, self.is_alive = dispatch, poll, poll_s, is_alive
         self.in_flight: dict[int, int] = {}
+        self.lost: list[int] = []
 
     def __iter__(self) -> Iterator[tuple[int, int, Any]]:
         while self.queue or self.in_flight:
@@ -70,9 +74,16 @@ class ClientScheduler:
                 self.in_flight[node] = cid
                 self.dispatch(node, cid)
             for node, cid, reply in self.poll():
-                self.in_flight.pop(node, None)
+                held = self.in_flight.pop(node, None)
+                if self.is_alive is not None and not self.is_alive(node):
+                    self.lost.append(node)
+                    if held is not None:
+                        self.queue.appendleft(held)
+                    continue
                 self.free.append(node)
                 yield node, cid, reply
+            if self.queue and not self.free and not self.in_flight:
+                raise RuntimeError(f"every node of the fleet is gone ({len(self.lost)} lost); {len(self.queue)} sampled client(s) were not trained")
             if self.poll_s:
                 time.sleep(self.poll_s)
 

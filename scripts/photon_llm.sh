@@ -18,7 +18,14 @@ else
 fi
 # TOPOLOGY=nodes: the reference's process shape — one host-side server driving N_NODES node managers, each with one
 # persistent worker process per GPU of its share (no torchrun); default spmd = one process per GPU + fused round kernels
+# + REMOTE_NODES=k FLEET_ADDRESS=host:port: k more machines join over gRPC — on each of them run
+#   PHOTON_FLEET_TOKEN=... python -m photon_b200.node --server host:port      (scripts/photon_node.sh)
+# (parameters go through the S3 bucket when S3_ENDPOINT_URL + AWS_* are set on every machine, inline in the messages otherwise;
+#  N_NODES=0 = the server machine trains nothing itself)
 if [ "${TOPOLOGY:-spmd}" = "nodes" ]; then
+  if [ "${REMOTE_NODES:-0}" -gt 0 ]; then
+    PHOTON_CONFIG="$PHOTON_CONFIG photon.fleet.n_remote_nodes=$REMOTE_NODES photon.fleet.address=${FLEET_ADDRESS:-0.0.0.0:9092}"
+  fi
   resolve $PHOTON_CONFIG photon.topology=nodes photon.n_nodes="${N_NODES:-1}" photon.comm_stack.nvl=false photon.comm_stack.shm=true
   python -m photon_b200.server_app 2>&1 | tee "$PHOTON_SAVE_PATH/server.log"
 else

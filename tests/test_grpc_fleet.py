@@ -1,0 +1,141 @@
+"""Cross-host deployment shape: the server's gRPC fleet link + ``python -m photon_b200.node`` processes (here on 127.0.0.1).
+Parameters inline in the gRPC messages, or through an S3 bucket; a node that dies mid-run leaves the rotation."""
+import os
+import socket
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import pytest
+import torch
+
+from fake_s3 import ACCESS, REGION, SECRET, FakeS3
+from test_federation_cpu import _cfg
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn_nodes(n, port, env=None, extra=()):
+    e = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="", **(env or {}))
+    return [subprocess.Popen([sys.executable, "-m", "photon_b200.node", "--server", f"127.0.0.1:{port}", "--n-workers", "1", "--max-idle-s", "60", *extra],
+                             env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for _ in range(n)]
+
+
+def _reap(procs):
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=60)[0])
+        except subprocess.TimeoutExpired:
+            p.kill()
+            outs.append(p.communicate()[0])
+    return outs
+
+
+COMMON = ["fl.n_rounds=2", "fl.n_clients_per_round=3", "llm_config.save_folder=null", "fl.strategy_name=fedavg", "photon.topology=nodes"]
+
+
+def _reference_model(tmp_path):
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    cfg = _cfg(tmp_path / "local", "run_uuid=fleet", "photon.n_nodes=2", *COMMON)
+    rt = NodeFleetRuntime(cfg)
+    try:
+        run_server(cfg, runtime=rt)
+        return rt.round_backend.global_params().clone()
+    finally:
+        rt.close()
+
+
+@pytest.mark.parametrize("store", ["inline", "s3"])
+def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    want = _reference_model(tmp_path)
+    s3 = FakeS3() if store == "s3" else None
+    env = {"PHOTON_FLEET_TOKEN": "sesame"}
+    if s3 is not None:
+        env.update({"S3_ENDPOINT_URL": s3.endpoint, "AWS_ACCESS_KEY_ID": ACCESS, "AWS_SECRET_ACCESS_KEY": SECRET, "AWS_DEFAULT_REGION": REGION})
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    port = _free_port()
+    procs = _spawn_nodes(2, port, env)          # nodes may start before the server: they keep trying to register
+    cfg = _cfg(tmp_path / "remote", "run_uuid=fleet", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=2",
+               "s3_comm_config.bucket_name=fleetbkt", *COMMON)
+    rt = NodeFleetRuntime(cfg)
+    try:
+        h = run_server(cfg, runtime=rt)
+        fit = h.metrics_distributed_fit
+        assert [v for _, v in fit["server/n_failures"]] == [0, 0] and [v for _, v in fit["server/n_nodes"]] == [2, 2]
+        assert sorted(rt.node_ids()) == [1000, 1001] and len(h.losses_distributed) == 3
+        got = rt.round_backend.global_params().clone()
+    finally:
+        rt.close()
+    outs = _reap(procs)
+    assert all(p.returncode == 0 for p in procs), outs
+    assert torch.allclose(got, want, atol=1e-6), float((got - want).abs().max())
+    if s3 is not None:
+        keys = [k for m, k in s3.requests if m == "PUT"]
+        assert any("fleetbkt/fleet/server/comm_stack/server/parameters.npz" in k for k in keys)          # broadcast went through the bucket
+        assert any("comm_stack/node-1000/client_" in k or "comm_stack/node-1001/client_" in k for k in keys)   # and so did the results
+        assert not [k for k in s3.objects if "/comm_stack/" in k]                                       # receivers released what they fetched
+        s3.stop()
+
+
+def test_wrong_token_is_refused(tmp_path, monkeypatch):
+    from photon_b200.server.grpc_fleet import FleetLink
+
+    link = FleetLink("127.0.0.1:0", cfg={"x": 1}, token="right")
+    try:
+        procs = _spawn_nodes(1, link.port, {"PHOTON_FLEET_TOKEN": "wrong"})
+        out = _reap(procs)[0]
+        assert procs[0].returncode != 0 and "UNAUTHENTICATED" in out and not link.nodes()
+    finally:
+        link.close(grace_s=0.1)
+
+
+def test_node_lost_mid_round_leaves_the_rotation(tmp_path, monkeypatch):
+    """One of two remote nodes is killed while it trains: its client is re-queued on the survivor, the round completes with every
+    sampled client, the dead node is gone from ``node_ids()`` afterwards."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    port = _free_port()
+    procs = _spawn_nodes(2, port)
+    cfg = _cfg(tmp_path, "run_uuid=lost", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=2",
+               "photon.fleet.liveness_timeout_s=4", "photon.fleet.connect_timeout_s=120", "fl.n_rounds=2", "fl.n_clients_per_round=4", "llm_config.save_folder=null", "fl.strategy_name=fedavg",
+               "photon.topology=nodes", "fl.eval_period=null", "llm_config.local_steps=6ba")
+    rt = NodeFleetRuntime(cfg)
+
+    def killer():
+        t0 = time.time()
+        while time.time() - t0 < 120:      # wait until some node holds a training task of round 1, then kill THAT node's process
+            link = rt.link
+            slots = list(link._slots.values()) if link is not None else []
+            busy = [s for s in slots if any(m.kind == "train" for m, _ in list(s.pending.values()))]
+            if len(slots) == 2 and busy:
+                time.sleep(0.3)
+                victim = busy[-1].info["pid"]
+                next(p for p in procs if p.pid == victim).kill()
+                return
+            time.sleep(0.02)
+
+    try:
+        threading.Thread(target=killer, daemon=True).start()
+        h = run_server(cfg, runtime=rt)
+        fit = h.metrics_distributed_fit
+        assert [v for _, v in fit["server/n_failures"]] == [0, 0]
+        assert len(rt.node_ids()) == 1 and [v for _, v in fit["server/n_nodes"]][-1] == 1
+    finally:
+        rt.close()
+    _reap(procs)
