@@ -526,14 +526,26 @@ class B200Engine:
         this runs the torch module that shares the fp32 master weights (bf16 autocast, SDPA); it is an evaluation utility,
         not part of the training step."""
         if self.model is None:
-            raise NotImplementedError("in-context-learning evaluation needs the whole model on one GPU; under full parameter "
-                                      "sharding evaluate the run's checkpoint with an unsharded trainer")
+            # full parameter sharding: the evaluation utility gets a temporary whole-model copy, pulled from the owners by THIS rank's
+            # copy engines (peers only have to leave their shards alone — the trainer keeps them at a barrier during the ICL suite);
+            # it is rebuilt when the parameters have changed and dropped by ``train_mode(True)``
+            ver = self.zero3.version
+            if getattr(self, "_eval_model", None) is None or self._eval_model_version != ver:
+                m = MPTForCausalLM(self.cfg, device=self.device, seed=0)
+                fp = FlatParams(m, device=self.device, with_grad=False)
+                fp.params.copy_(self.flat.full_params())
+                m.train(False)
+                self._eval_model, self._eval_model_version = m, ver
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self._eval_model(ids.to(self.device))
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return self.model(ids.to(self.device))
 
     def train_mode(self, on: bool = True) -> None:
         if self.model is not None:
             self.model.train(on)
+        elif on:
+            self._eval_model = None       # the whole-model evaluation copy (full sharding) does not outlive the evaluation
 
     def close(self) -> None:
         self._graphs.clear()

@@ -217,6 +217,7 @@ class NvlZero3Comm:
         self.resident: list[int | None] = [None, None]      # unit held (or being pulled into) each rotating buffer
         self._ready: list[Any] = [None, None]               # event: the pull into buffer k has finished
         self._rest_valid = False
+        self.version = 0                                     # bumped whenever the parameters change (cached whole-model copies key on it)
         self.norm = torch.zeros(1, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------ views for the engine
@@ -299,6 +300,7 @@ class NvlZero3Comm:
         self.barrier()
         self.resident, self._ready = [None, None], [None, None]
         self._rest_valid = False
+        self.version += 1
 
     def all_reduce_mean_(self, g: torch.Tensor) -> torch.Tensor:
         return g        # every unit was reduced (and averaged) right after its backward

@@ -432,6 +432,10 @@ class Trainer:
         if self.icl_suite is not None:   # llm-foundry's ICL evaluators + EvalGauntlet run as part of every trainer.eval()
             icl = {k: v for k, v in self.icl_suite(st.backend.logits).items() if isinstance(v, (int, float))} if self.rank == 0 else {}
             self.last_icl_metrics = icl
+            if self.world_size > 1 and dist.is_initialized():
+                # the suite runs on rank 0 only and can take minutes: the others wait HERE, on the host, instead of inside the next
+                # step's NVLink kernel (whose peer spins are time-bounded) — and leave their parameter shards alone meanwhile
+                dist.barrier(group=self.process_group)
             self.log({(k if k.startswith("icl/") else f"metrics/icl/{k}"): float(v) for k, v in icl.items()})
             vals = {**vals, **{(k if k.startswith("icl/") else f"icl/{k}"): float(v) for k, v in icl.items()}}
         self._emit("eval_end")

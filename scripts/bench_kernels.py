@@ -42,6 +42,10 @@ def main():
               ("qkv fwd", T, 2304, 768, 0, 0), ("out fwd", T, 768, 768, 0, 0), ("up fwd", T, 3072, 768, 0, 0),
               ("down fwd", T, 768, 3072, 0, 0), ("up dgrad", T, 768, 3072, 0, 1), ("up wgrad", 3072, 768, T, 1, 1),
               ("lmhead fwd", 8192, 50368, 768, 0, 0), ("lmhead dgrad", 8192, 768, 50368, 0, 1), ("lmhead wgrad", 50368, 768, 8192, 1, 1),
+              # the shapes the engine ACTUALLY issues for the head: chunks of 18944 rows = 148 M-tiles, so the three N-tiles of the
+              # dgrad are exactly three full waves (the 8192-row rows above fill 1.3 waves and pay for the tail)
+              ("lmhead fwd (engine chunk)", 18944, 50368, 768, 0, 0), ("lmhead dgrad (engine chunk)", 18944, 768, 50368, 0, 1),
+              ("lmhead wgrad (engine chunk)", 50368, 768, 18944, 1, 1),
               ("square 8192", 8192, 8192, 8192, 0, 0)]
     for name, M, N, K, amn, bmn in shapes:
         a = torch.randn((K, M) if amn else (M, K), device=dev).to(torch.bfloat16)

@@ -102,6 +102,10 @@ def test_sharded_engine_equals_plain_engine(act_ckpt):
         assert (a - b).norm() <= 1e-4 * a.norm() + 1e-9, n
     a, b = plain.eval_stats(ids), shard.eval_stats(ids)
     assert abs(float(a["loss_sum"]) - float(b["loss_sum"])) <= 1e-5 * abs(float(a["loss_sum"]))
+    # the ICL evaluator's logits() path: a temporary whole-model copy assembled from the shards
+    torch.testing.assert_close(shard.logits(ids[:1, :64]).float(), plain.logits(ids[:1, :64]).float(), rtol=1e-3, atol=1e-3)
+    shard.train_mode(True)
+    assert shard._eval_model is None
     comm.close()
 
 
