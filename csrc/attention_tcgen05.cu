@@ -379,6 +379,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
         };
         auto exp_pass = [&](float m_ref) {
           rs0 = 0.f, rs1 = 0.f;
+          if constexpr (POLY == 16 && !ALIBI) {
+            // packed variant: the scale-subtract and the row sum of a pair issue as ONE FFMA2 / FADD2 each (7 instead of 9 issue
+            // slots per pair; the softmax warps are issue / latency bound, not MUFU bound)
+            const float2 scv = make_float2(sc, sc), mneg = make_float2(-m_ref, -m_ref);
+            float2 rs = make_float2(0.f, 0.f);
+            sweep([&](int cc, const uint32_t (&r)[32]) {
+              float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+              for (int t = 0; t < 32; t += 2) {
+                const float v0 = masked(r, cc, t), v1 = masked(r, cc, t + 1);
+                cm0 = fmaxf(cm0, v0);
+                cm1 = fmaxf(cm1, v1);
+                const float2 x = ffma2(make_float2(v0, v1), scv, mneg);
+                const float2 p = make_float2(exp2f(x.x), exp2f(x.y));
+                rs = fadd2(rs, p);
+                pk[cc * 16 + (t >> 1)] = pack_bf16(p.x, p.y);
+              }
+              mx = fmaxf(mx, fmaxf(cm0, cm1));
+            });
+            rs0 = rs.x, rs1 = rs.y;
+            return;
+          }
           sweep([&](int cc, const uint32_t (&r)[32]) {
             float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
@@ -395,7 +417,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __rest
                 cm1 = fmaxf(cm1, v1);
                 x0 = fmaf(v0, sc, -m_ref), x1 = fmaf(v1, sc, -m_ref);
               }
-              if (POLY > 0 && (t >> 1) % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) {
+              if (POLY > 0 && POLY != 16 && (t >> 1) % (POLY > 0 ? POLY : 1) == (POLY > 0 ? POLY : 1) - 1) {
                 p0 = exp2_fma(x0), p1 = exp2_fma(x1);
               } else {
                 p0 = exp2f(x0), p1 = exp2f(x1);
@@ -1000,7 +1022,9 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
   // PB_ATTN_POLY = 4: every 4th pair of exponentials on the FMA pipe (default 0 = all on MUFU). Measured (profiles/attn_exp2_poly.txt):
   // 1/4 -> 0.419 ms, 1/3 -> 0.420, 1/2 -> 0.453 against 0.408 ms with none: the softmax warps are bound by issue slots and
   // fixed-latency dependencies (two warps per scheduler), not by MUFU throughput, so the ~9 extra instructions per element cost
-  // more than the MUFU cycles they free. Kept as a switch for parts with a different MUFU : FMA ratio.
+  // more than the MUFU cycles they free. PB_ATTN_POLY = 16: packed FFMA2 / FADD2 in the exponent loop (7 instead of 9 issue slots per
+  // pair) -> 0.411 ms, no change: the tile time is set by the MMA -> tcgen05.ld -> softmax -> tcgen05.st -> MMA dependency chain, not
+  // by a pipe. Both kept as switches.
   static const int poly = [] { const char* e = std::getenv("PB_ATTN_POLY"); return e ? std::atoi(e) : PB_ATTN_POLY_DEFAULT; }();
 #define PB_FWD(DHV, AL, PL)                                                                                           \
   {                                                                                                                   \
@@ -1012,6 +1036,7 @@ void attention_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, 
 #define PB_FWD_P(DHV, AL)                                                                                             \
   {                                                                                                                   \
     if (poly == 4) PB_FWD(DHV, AL, 4)                                                                                 \
+    else if (poly == 16) PB_FWD(DHV, AL, 16)                                                                          \
     else PB_FWD(DHV, AL, 0)                                                                                           \
   }
   if (dh == 64 && !alibi_slopes) PB_FWD_P(64, false)
