@@ -174,10 +174,41 @@ class FL(_Strict):
         return self
 
 
+class ClientConfig(BaseModel):
+    """Time-outs of the S3 client (ref: base_schema.py:236-247); extra botocore keys are accepted and ignored."""
+
+    model_config = {"extra": "allow"}
+    connect_timeout: float = 3600
+    read_timeout: float = 3600
+
+
+class BackendKwargs(BaseModel):
+    """(ref: base_schema.py:250-262) + what the own S3 client reads: ``endpoint_url`` (else ``S3_ENDPOINT_URL``), ``region_name``
+    (else ``AWS_DEFAULT_REGION``), ``prefix`` inside the bucket."""
+
+    model_config = {"extra": "allow"}
+    client_config: ClientConfig = Field(default_factory=ClientConfig)
+    endpoint_url: str | None = None
+    region_name: str | None = None
+    prefix: str | None = None
+
+
 class S3CommConfig(_Strict):
     bucket_name: str = "checkpoints"
     num_attempts: int = 3
-    backend_kwargs: dict[str, Any] = Field(default_factory=dict)
+    backend_kwargs: BackendKwargs = Field(default_factory=BackendKwargs)
+
+
+class StrategyKWArgs(dict):       # noqa: FURB189 - free-form mappings, named like the reference's schema nodes (ref: base_schema.py:138,336,340)
+    """``fl.strategy_kwargs``: whatever the chosen server optimizer takes."""
+
+
+class Dataset(dict):              # noqa: FURB189
+    """``dataset``: the train / val stream tables (validated by the loaders)."""
+
+
+class LLMConfig(dict):            # noqa: FURB189
+    """``llm_config``: the Composer / llm-foundry style trainer node (validated where it is consumed)."""
 
 
 class WandbSetup(BaseModel):
@@ -269,6 +300,13 @@ class BaseConfig(BaseModel):
         if impl not in ("flash", "torch", "b200"):
             raise ValueError(f"attn_impl={impl!r} unsupported (flash|torch|b200)")
         return self
+
+
+def register_config(name: str = "base_schema") -> None:
+    """The reference registers its schema with Hydra's ConfigStore so YAML files can name it in ``defaults``
+    (ref: base_schema.py:395-398). The own composer validates every composed config against :class:`BaseConfig` anyway
+    (``validate_config``), so there is nothing to register; kept so ``register_config("base_schema")`` call sites keep working."""
+    del name
 
 
 def validate_config(cfg: Any) -> BaseConfig:

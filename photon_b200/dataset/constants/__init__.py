@@ -1,37 +1,20 @@
 """Dataset split tables for the converter: C4 English + the mC4 languages the reference ships
-(ref: photon/dataset/constants/__init__.py:20-34, constants/mc4.py:30-77). Built programmatically:
-every language has the same six folder splits with the same truncation counts."""
+(ref: photon/dataset/constants/__init__.py:20-34). ``DATASETS_CONSTANTS["c4_en"].splits["val_xxsmall"]`` etc.;
+``val`` is accepted as an alias of the reference's ``validation`` key (the folder it is written to)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from photon_b200.dataset.constants.dataset_constants_types import ConcatMode, DatasetConstants, DataSplitConstants  # noqa: F401
+from photon_b200.dataset.constants.mc4 import ALL_CONSTANTS, C4_PATH  # noqa: F401
 
-C4_PATH, MC4_PATH = "allenai/c4", "allenai/c4"
-LANGUAGES = ("en", "it", "zh", "ms", "ur", "sw", "la", "sr", "es", "de", "el", "ru", "hi")
-# folder_split -> (hf_split, truncated_samples)
-SPLIT_TABLE = {"train": ("train", None), "train_small": ("train", 100_000), "val": ("validation", None),
-               "val_small": ("validation", 10_000), "val_xsmall": ("validation", 3_000), "val_xxsmall": ("validation", 100)}
-
-
-@dataclass(frozen=True)
-class DataSplitConstants:
-    path: str
-    name: str
-    split: str
-    folder_split: str
-    truncated_samples: int | None
+# the reference's order
+DATASETS_CONSTANTS: dict[str, DatasetConstants] = {f"c4_{lang}": ALL_CONSTANTS[lang]
+                                                   for lang in ("en", "it", "zh", "ms", "ur", "sw", "la", "sr", "es", "de", "el", "ru", "hi")}
 
 
-@dataclass(frozen=True)
-class DatasetConstants:
-    splits: dict[str, DataSplitConstants] = field(default_factory=dict)
-
-    def __iter__(self):  # noqa: ANN204
-        return iter(self.splits.values())
-
-
-def _lang(lang: str) -> DatasetConstants:
-    return DatasetConstants({fs: DataSplitConstants(C4_PATH if lang == "en" else MC4_PATH, lang, hf, fs, trunc)
-                             for fs, (hf, trunc) in SPLIT_TABLE.items()})
-
-
-DATASETS_CONSTANTS: dict[str, DatasetConstants] = {f"c4_{lang}": _lang(lang) for lang in LANGUAGES}
+def resolve_split(dataset: str, split: str) -> DataSplitConstants:
+    """Table lookup with the ``val`` → ``validation`` alias and a message that lists what exists."""
+    table = DATASETS_CONSTANTS[dataset].splits
+    key = "validation" if split == "val" and "val" not in table else split
+    if key not in table:
+        raise KeyError(f"dataset {dataset} has no split '{split}' (have {sorted(table)})")
+    return table[key]

@@ -18,7 +18,7 @@ from pathlib import Path
 from typing import Any
 
 from photon_b200.data.shards import ShardWriter
-from photon_b200.dataset.constants import DATASETS_CONSTANTS
+from photon_b200.dataset.constants import DATASETS_CONSTANTS, resolve_split
 from photon_b200.dataset.utils import UnigramCounter, build_tokenizer, concat_tokens, iter_text_source
 
 
@@ -92,13 +92,15 @@ def main(argv: list[str] | None = None) -> dict[str, list[int]]:
         if _zstd() is None:
             print("[convert] no zstd codec importable here; writing zlib shards (the reader picks the codec from index.json)")
             args.compression = "zlib"
-    consts = DATASETS_CONSTANTS[args.dataset]
+    if args.dataset not in DATASETS_CONSTANTS:
+        raise SystemExit(f"unknown dataset {args.dataset!r} (have {sorted(DATASETS_CONSTANTS)})")
     tok = build_tokenizer(args.tokenizer, **(json.loads(args.tokenizer_kwargs) if args.tokenizer_kwargs else {}))
     lang = args.dataset.split("_", 1)[1]
     root = Path(args.out_root) / f"c{args.num_clients}" / lang
     out: dict[str, list[int]] = {}
-    for fs in args.splits:
-        sc = consts.splits[fs]
+    for key in args.splits:
+        sc = resolve_split(args.dataset, key)      # table key (reference names; "val" = "validation") -> HF split, folder, truncation
+        fs = sc.folder_split
         src = args.source or args.path or sc.path
         docs = iter_text_source(src, split=sc.split, limit=sc.truncated_samples)
         dirs = [root / f"client_{i}" / fs for i in range(args.num_clients)]

@@ -280,61 +280,44 @@ def add_unigram_metrics(trainer: Any, unigram_freq: dict[int, int] | dict[str, i
 
 
 class RemoteUploaderDownloader:
-    """Object-store façade with the call surface the reference gets from Composer's
-    ``RemoteUploaderDownloader`` (ref: photon/utils.py:955-1014): ``upload_file`` /
-    ``download_file`` / ``list_objects`` / ``delete_object`` with retries. Buckets are directories
-    under ``root`` (this image has no network; an ``s3://`` endpoint would slot in behind the same
-    four calls)."""
+    """Object-store façade with the call surface the reference gets from Composer's ``RemoteUploaderDownloader``
+    (ref: photon/utils.py:955-1014): ``upload_file`` / ``download_file`` / ``list_objects`` / ``delete_object`` with retries, over
+    an :class:`photon_b200.utils.objstore.ObjectStore` — the S3 bucket when an endpoint + credentials are configured
+    (``S3_ENDPOINT_URL`` / ``AWS_*``), a directory under ``root`` otherwise."""
 
-    def __init__(self, root: str | os.PathLike, bucket_name: str, prefix: str = "", num_attempts: int = 3) -> None:
-        from pathlib import Path
+    def __init__(self, root: str | os.PathLike, bucket_name: str, prefix: str = "", num_attempts: int = 3, store: Any = None) -> None:
+        from photon_b200.utils.objstore import DirObjectStore, remote_store_from_cfg
 
-        self.base = Path(root) / bucket_name / prefix
-        self.base.mkdir(parents=True, exist_ok=True)
+        self.remote_bucket_name, self.backend_kwargs = bucket_name, {"prefix": prefix}
         self.num_attempts = max(1, int(num_attempts))
+        if store is None:
+            store = remote_store_from_cfg({"s3_comm_config": {"bucket_name": bucket_name, "num_attempts": num_attempts,
+                                                              "backend_kwargs": {"prefix": prefix}}})
+        self.store = store if store is not None else DirObjectStore(Path(root) / bucket_name / prefix)
         self.run_name: str | None = None
 
     def init(self, run_name: str | None = None) -> None:
         self.run_name = run_name
 
-    def _retry(self, fn: Any) -> Any:
-        import time
+    def _check_workers(self) -> None:      # Composer's uploader has worker processes to check; nothing to do here
+        return None
 
-        err: BaseException | None = None
-        for i in range(self.num_attempts):
-            try:
-                return fn()
-            except OSError as e:  # transient FS errors
-                err = e
-                time.sleep(0.05 * (i + 1))
-        raise RuntimeError(f"object store operation failed after {self.num_attempts} attempts") from err
-
-    def upload_file(self, remote_file_name: str, file_path: str | os.PathLike, overwrite: bool = True) -> None:
-        import shutil
-
-        dst = self.base / remote_file_name
-        if dst.exists() and not overwrite:
-            raise FileExistsError(str(dst))
-        dst.parent.mkdir(parents=True, exist_ok=True)
-        tmp = dst.with_suffix(dst.suffix + ".part")
-        self._retry(lambda: (shutil.copyfile(file_path, tmp), os.replace(tmp, dst)))  # readers never see partial objects
+    def upload_file(self, remote_file_name: str, file_path: str | os.PathLike, overwrite: bool = True, state: Any = None) -> None:
+        del state
+        if not overwrite and self.store.exists(remote_file_name):
+            raise FileExistsError(remote_file_name)
+        self.store.upload(remote_file_name, file_path)      # readers never see partial objects (atomic rename / S3 PUT)
 
     def download_file(self, remote_file_name: str, destination: str | os.PathLike, overwrite: bool = True) -> None:
-        import shutil
-
         if os.path.exists(destination) and not overwrite:
             raise FileExistsError(str(destination))
-        os.makedirs(os.path.dirname(os.path.abspath(destination)), exist_ok=True)
-        self._retry(lambda: shutil.copyfile(self.base / remote_file_name, destination))
+        self.store.download(remote_file_name, destination)
 
     def list_objects(self, prefix: str = "") -> list[str]:
-        root = self.base / prefix
-        if not root.exists():
-            return []
-        return sorted(str(p.relative_to(self.base)) for p in root.rglob("*") if p.is_file() and not p.name.endswith(".part"))
+        return [k for k in self.store.list(prefix) if not k.endswith(".part")]
 
     def delete_object(self, remote_file_name: str) -> None:
-        (self.base / remote_file_name).unlink(missing_ok=True)
+        self.store.delete(remote_file_name)
 
     def close(self) -> None:
         pass
@@ -343,8 +326,100 @@ class RemoteUploaderDownloader:
 def create_remote_up_down(bucket_name: str, prefix: str, run_uuid: str | None, num_attempts: int,
                           client_config: dict[str, Any] | None = None, *, root: str | os.PathLike | None = None,
                           **_unused: Any) -> RemoteUploaderDownloader:
-    """(ref: photon/utils.py:955-1014) ``root`` defaults to ``$PHOTON_SAVE_PATH`` (or ./runs)."""
+    """(ref: photon/utils.py:955-1014) ``root`` (directory fall-back) defaults to ``$PHOTON_SAVE_PATH`` (or ./runs)."""
     del client_config
     r = RemoteUploaderDownloader(root or os.environ.get("PHOTON_SAVE_PATH", "runs"), bucket_name, prefix, num_attempts)
     r.init(run_name=run_uuid)
     return r
+
+
+def upload_file_to_s3(remote_up_down: RemoteUploaderDownloader, remote_file_name: str, local_file_name: str | os.PathLike) -> None:
+    """(ref: photon/utils.py:687-699)"""
+    remote_up_down.upload_file(remote_file_name, local_file_name, overwrite=True)
+
+
+def download_file_from_s3(remote_up_down: RemoteUploaderDownloader, remote_file_name: str, local_file_name: str | os.PathLike) -> None:
+    """(ref: photon/utils.py:673-684)"""
+    remote_up_down.download_file(remote_file_name, local_file_name, overwrite=True)
+
+
+# ------------------------------------------------------------------------------------------- small reference-named helpers
+class NoOpContextManager:
+    """``with NoOpContextManager(): ...`` does nothing (ref: photon/utils.py:56-71)."""
+
+    def __enter__(self) -> None:
+        return None
+
+    def __exit__(self, *exc: Any) -> None:
+        return None
+
+
+def merge_freq_dicts(a: dict[int, int], b: dict[int, int]) -> dict[int, int]:
+    """Token-count maps of two streams added key by key (ref: photon/utils.py:1017-1036); the n-ary, JSON-keyed form used by the
+    client config code is ``clients.llm_config_functions.merge_freq_dicts``."""
+    out = dict(a)
+    for k, v in b.items():
+        out[k] = out.get(k, 0) + v
+    return out
+
+
+def get_unigram_probabilities_tensor(stream_freq_dict: dict[int, int]) -> torch.Tensor:
+    """Dense ``p[token]`` up to the largest token id seen (ref: photon/utils.py:1039-1063). The metrics use
+    ``metrics.language.unigram_log_probs`` (vocabulary-sized, one pseudo-count for unseen ids so the CE stays finite)."""
+    ids = torch.tensor([int(k) for k in stream_freq_dict], dtype=torch.long)
+    counts = torch.tensor([float(v) for v in stream_freq_dict.values()], dtype=torch.float64)
+    p = torch.zeros(int(ids.max()) + 1, dtype=torch.float64)
+    p[ids] = counts / counts.sum()
+    return p.to(torch.float32)
+
+
+def set_parameters(net: torch.nn.Module, parameters: Sequence[np.ndarray], device: str = "cpu") -> None:
+    """Install a sorted-name payload into a plain module (ref: photon/utils.py:764-776): the arrays pair with the module's
+    TRAINABLE parameters in sorted-name order; the module is left in eval mode like the reference's."""
+    net.eval()
+    names = list(get_trainable_params_dict(net))
+    if len(names) != len(parameters):
+        raise ValueError(f"{len(parameters)} arrays for {len(names)} trainable tensors")
+    lookup = {clean_parameter_name(n): p for n, p in net.named_parameters()}
+    with torch.no_grad():
+        for n, a in zip(names, parameters):
+            lookup[n].copy_(torch.as_tensor(a, device=device).to(lookup[n].dtype))
+
+
+def custom_ray_garbage_collector(garbage_queue: Any, list_of_threads: list[Any] | None = None, timeout: float = 300.0, *,
+                                 join_at_the_end: bool = True) -> Any:
+    """Context manager: a background thread frees the parameter locators put on ``garbage_queue`` while the body runs
+    (ref: photon/utils.py:73-144 frees Ray ObjectRefs this way; here the queue carries ``ParamHandle`` s of any side channel —
+    shm segment, npz object, S3 key — and freeing is ``release_remote_parameters``). ``None`` on the queue stops the collector."""
+    import contextlib
+    import queue as _queue
+    import threading
+
+    from photon_b200.server.s3_utils import release_remote_parameters
+
+    @contextlib.contextmanager
+    def _cm() -> Any:
+        stop = threading.Event()
+
+        def loop() -> None:
+            while not stop.is_set() or not garbage_queue.empty():
+                try:
+                    h = garbage_queue.get(timeout=0.05)
+                except _queue.Empty:
+                    continue
+                if h is None:
+                    return
+                release_remote_parameters(h)
+
+        t = threading.Thread(target=loop, name="photon-param-gc", daemon=True)
+        t.start()
+        if list_of_threads is not None:
+            list_of_threads.append(t)
+        try:
+            yield
+        finally:
+            stop.set()
+            if join_at_the_end:
+                t.join(timeout=timeout)
+
+    return _cm()

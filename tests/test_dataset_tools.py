@@ -12,8 +12,22 @@ from photon_b200.dataset.utils import ByteTokenizer, concat_tokens
 
 
 def test_constants_table():
+    from photon_b200.dataset.constants import ConcatMode, resolve_split
+    from photon_b200.dataset.constants import mc4
+
     assert len(DATASETS_CONSTANTS) == 13 and DATASETS_CONSTANTS["c4_en"].splits["train_small"].truncated_samples == 100_000
-    assert DATASETS_CONSTANTS["c4_it"].splits["val_xxsmall"].truncated_samples == 100
+    # the reference's table shape (ref: photon/dataset/constants/mc4.py): six English entries, the two full splits elsewhere;
+    # the full validation set is keyed "validation" and lands in the folder "val"
+    en, it = DATASETS_CONSTANTS["c4_en"], DATASETS_CONSTANTS["c4_it"]
+    assert list(en.splits) == ["train", "train_small", "validation", "val_small", "val_xsmall", "val_xxsmall"]
+    assert [(s.split, s.folder_split, s.truncated_samples) for s in en][2:] == [("validation", "val", None), ("validation", "val_small", 10_000),
+                                                                             ("validation", "val_xsmall", 3_000), ("validation", "val_xxsmall", 100)]
+    assert list(it.splits) == ["train", "validation"] and it.splits["validation"].name == "it"
+    assert resolve_split("c4_it", "val") is it.splits["validation"] and mc4.c4_hi_constants is DATASETS_CONSTANTS["c4_hi"]
+    assert mc4.SERBIAN_CONSTANT == "sr" and ConcatMode("CONCAT_TOKENS") is ConcatMode.CONCAT_TOKENS
+    import pytest
+    with pytest.raises(KeyError, match="has no split"):
+        resolve_split("c4_it", "val_xxsmall")
 
 
 def test_concat_tokens_packs_with_eos():

@@ -1,6 +1,7 @@
 """The S3 REST client (AWS Signature V4, multipart, paging, retries) against AWS's published signing vectors and a local
 S3-compatible endpoint that re-derives every signature; the directory store behind the same interface."""
 import datetime as dt
+import os
 import hashlib
 
 import pytest
@@ -151,3 +152,52 @@ def test_federation_through_an_s3_endpoint_and_resume_on_another_host(tmp_path, 
     cleanup_checkpoints(_cfg(b, *common))
     assert not [k for k in s3.objects if k.startswith("fedbkt/s3run/")]
     assert torch.is_tensor(torch.zeros(1))
+
+
+def test_reference_named_helpers(tmp_path, s3, monkeypatch):
+    """``photon.utils`` names a reference user imports: the uploader façade (directory and S3), the frequency-map helpers, the generic
+    ``set_parameters``, the no-op context manager and the parameter-locator garbage collector."""
+    import queue
+
+    import numpy as np
+    import torch
+
+    from photon_b200.messages import ParamHandle
+    from photon_b200.server.s3_utils import replace_remote_with_parameters_in_recordset
+    from photon_b200.utils import (NoOpContextManager, custom_ray_garbage_collector, download_file_from_s3, get_trainable_params_dict,
+                                   get_unigram_probabilities_tensor, merge_freq_dicts, set_parameters, upload_file_to_s3)
+    from photon_b200.utils.core import create_remote_up_down
+
+    src = tmp_path / "a.bin"
+    src.write_bytes(b"payload")
+    r = create_remote_up_down("bkt", "pre", "run1", 2, root=tmp_path)           # no endpoint: a directory
+    upload_file_to_s3(r, "x/a.bin", src)
+    assert (tmp_path / "bkt" / "pre" / "x" / "a.bin").read_bytes() == b"payload" and r.list_objects("x/") == ["x/a.bin"]
+    for k, v in {"S3_ENDPOINT_URL": s3.endpoint, "AWS_ACCESS_KEY_ID": ACCESS, "AWS_SECRET_ACCESS_KEY": SECRET, "AWS_DEFAULT_REGION": REGION}.items():
+        monkeypatch.setenv(k, v)
+    r3 = create_remote_up_down("bkt", "pre", "run1", 2, root=tmp_path)          # endpoint configured: the bucket
+    upload_file_to_s3(r3, "x/a.bin", src)
+    assert s3.objects["bkt/pre/x/a.bin"] == b"payload"
+    download_file_from_s3(r3, "x/a.bin", tmp_path / "back.bin")
+    assert (tmp_path / "back.bin").read_bytes() == b"payload"
+    r3.delete_object("x/a.bin")
+    assert r3.list_objects() == []
+
+    assert merge_freq_dicts({1: 2, 5: 1}, {5: 3, 9: 4}) == {1: 2, 5: 4, 9: 4}
+    p = get_unigram_probabilities_tensor({0: 1, 3: 3})
+    assert p.tolist() == [0.25, 0.0, 0.0, 0.75]
+    with NoOpContextManager():
+        pass
+    net = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.Linear(2, 1))
+    names = list(get_trainable_params_dict(net))
+    arrays = [np.full(tuple(dict(net.named_parameters())[n].shape), i, dtype=np.float32) for i, n in enumerate(names)]
+    set_parameters(net, arrays)
+    assert all(float(dict(net.named_parameters())[n].mean()) == i for i, n in enumerate(names)) and not net.training
+    # locators put on the queue are released in the background (here: POSIX segments)
+    q: queue.Queue = queue.Queue()
+    with custom_ray_garbage_collector(q, []):
+        for i in range(3):
+            h = replace_remote_with_parameters_in_recordset(ParamHandle("inline", [np.ones(4, np.float32)]), {"shm": True}, endpoint_id=f"gc_test_{os.getpid()}_{i}")
+            assert os.path.exists(f"/dev/shm/{h.data}")
+            q.put(h)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"gc_test_{os.getpid()}_")]
