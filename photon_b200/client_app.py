@@ -78,3 +78,61 @@ class ClientApp:
             bad: Any = [FitRes(Status(Code.FAILED, repr(e)), None, 0, {})] if msg.kind == "train" else (
                 EvaluateRes(Status(Code.FAILED, repr(e)), 0.0, 0, {}) if msg.kind == "evaluate" else None)
             return Message(msg.kind, bad, node_id=self.node_id, error=repr(e), reply_to=msg.msg_id)
+
+
+# ----------------------------------------------------------------------------- module-level callbacks (ref: client_app.py:78-291)
+# The reference registers plain functions on a Flower ``ClientApp`` (``@app.train()`` …) that share a module-global node manager
+# created by ``lifespan``. Same shape: ``lifespan(cfg)`` builds THE app of this process, the functions below dispatch to it.
+_APP: ClientApp | None = None
+
+
+def _app() -> ClientApp:
+    if _APP is None:
+        raise RuntimeError("no node app in this process: wrap the calls in `with lifespan(cfg):` (or build a ClientApp yourself)")
+    return _APP
+
+
+@contextlib.contextmanager
+def lifespan(cfg: Any = None, n_workers: int | None = None, devices: list[int] | None = None, node_id: int = 0) -> Iterator[ClientApp]:
+    """Workers of this process's node live inside the ``with`` block. ``cfg`` defaults to ``$PHOTON_SAVE_PATH/config.yaml``."""
+    global _APP
+    if cfg is None:
+        import os
+        from pathlib import Path
+
+        from photon_b200.config import load_config
+
+        cfg = load_config(Path(os.environ["PHOTON_SAVE_PATH"]) / "config.yaml")
+    app = ClientApp(cfg, n_workers=n_workers, node_id=node_id, devices=devices)
+    with app.lifespan():
+        _APP = app
+        try:
+            yield app
+        finally:
+            _APP = None
+
+
+def train(msg: Message, context: Any = None) -> Message:
+    del context
+    return _app().handle(msg) if msg.kind == "train" else _app().train(msg)
+
+
+def evaluate(msg: Message, context: Any = None) -> Message:
+    del context
+    return _app().evaluate(msg)
+
+
+def query(msg: Message, context: Any = None) -> Message:
+    del context
+    return _app().query(msg)
+
+
+def set_parameters(msg: Message, context: Any = None) -> Message:
+    del context
+    return _app().set_parameters(msg)
+
+
+def free_resources(msg: Message | None = None, context: Any = None) -> Message:
+    """Recycle the node's worker processes (ref: client_app.py ``free_resources`` query)."""
+    del context
+    return _app().query(Message("query", {"type": "free_resources"}, node_id=_app().node_id, reply_to=getattr(msg, "msg_id", None)))

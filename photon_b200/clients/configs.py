@@ -17,6 +17,12 @@ from pydantic import BaseModel, ConfigDict, field_validator
 from photon_b200.messages import ClientState, decode_client_states, encode_client_states
 
 
+def typed_field_validator(field: str, /, *field_names: str, mode: str = "after") -> Callable[[Callable[..., Any]], Callable[..., Any]]:
+    """``pydantic.field_validator`` behind a typed signature, so decorated validators keep their type for the checker
+    (ref: photon/clients/configs.py:18-44)."""
+    return field_validator(field, *field_names, mode=mode)  # type: ignore[call-overload,no-any-return]
+
+
 def _maybe_literal(v: Any) -> Any:
     if isinstance(v, str):
         try:

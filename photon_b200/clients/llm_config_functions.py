@@ -19,6 +19,7 @@ llm_config_functions.py:58-1109), written against our ConfigNode tree:
 from __future__ import annotations
 
 import copy
+import dataclasses
 import json
 import os
 import re
@@ -30,6 +31,28 @@ from photon_b200.data.synthetic import SyntheticC4
 
 _STREAM_KEYS = ("remote", "local", "proportion", "repeat", "choose", "download_retry", "download_timeout",
                 "validate_hash", "keep_zip", "split")
+
+
+@dataclasses.dataclass
+class StreamDict:
+    """One entry of ``train_loader.dataset.streams`` (the keyword arguments of a mosaicml-streaming ``Stream``; ref:
+    llm_config_functions.py:42-55). ``data/streaming.py`` reads ``local`` / ``remote`` / ``split`` / ``proportion`` / ``repeat`` /
+    ``choose``; the download knobs are accepted for files written for the reference."""
+
+    remote: str | None = None
+    local: str | None = None
+    split: str | None = None
+    proportion: float | None = None
+    repeat: float | None = None
+    choose: int | None = None
+    download_retry: int | None = None
+    download_timeout: float | None = None
+    validate_hash: str | None = None
+    keep_zip: bool | None = None
+
+    def to_dict(self) -> dict[str, Any]:
+        return {k: v for k, v in dataclasses.asdict(self).items() if v is not None}
+
 
 
 def get_train_config(llm_config: Any, *, run_uuid: str | None = None) -> ConfigNode:
@@ -203,6 +226,33 @@ def set_client_loggers(train_cfg: Any, log_name: str) -> None:
     if "tensorboard" in loggers:
         loggers["tensorboard"] = dict(loggers["tensorboard"] or {})
     train_cfg["run_name"] = f"{train_cfg.get('run_name', 'run')}{log_name}"
+
+
+def set_client_wandb_logger(train_cfg: Any, log_name: str) -> None:
+    """Suffix the wandb run name / id with the client's log name (ref: llm_config_functions.py:767-815)."""
+    loggers = train_cfg.get("loggers") or {}
+    if "wandb" in loggers:
+        kw = dict((loggers["wandb"] or {}).get("init_kwargs") or {})
+        for k in ("name", "id"):
+            if kw.get(k) is not None:
+                kw[k] = f"{kw[k]}{log_name}"
+        loggers["wandb"] = {**dict(loggers["wandb"] or {}), "init_kwargs": kw}
+
+
+def set_client_tensorboard_logger(train_cfg: Any, log_name: str) -> None:
+    """Give the client its own tensorboard directory: the run name carries the log name (ref: :818-862)."""
+    loggers = train_cfg.get("loggers") or {}
+    if "tensorboard" in loggers:
+        loggers["tensorboard"] = dict(loggers["tensorboard"] or {})
+    if not str(train_cfg.get("run_name", "run")).endswith(log_name):
+        train_cfg["run_name"] = f"{train_cfg.get('run_name', 'run')}{log_name}"
+
+
+def set_icl_tasks_root_dir(icl_tasks_listconfig: list[dict[str, Any]], root_dir: str) -> None:
+    """Re-root every task's ``dataset_uri`` under ``root_dir`` in place (ref: :202-236). ``icl_tasks_config.root_dir`` does the same
+    at evaluation time without touching the task table."""
+    for task in icl_tasks_listconfig:
+        task["dataset_uri"] = f"{root_dir}/{task['dataset_uri']}"
 
 
 # ---------------------------------------------------------------------- batch geometry

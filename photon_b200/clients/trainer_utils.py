@@ -12,6 +12,7 @@ save folder, loggers and clocks are swapped.
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 from pathlib import Path
 from typing import Any
@@ -27,7 +28,7 @@ from photon_b200.models.mpt import MPTConfig
 from photon_b200.train.callbacks import build_callbacks, build_loggers
 from photon_b200.train.timestamp import Time
 from photon_b200.train.trainer import Trainer
-from photon_b200.utils.core import appointed_cuda_devices
+from photon_b200.utils.core import add_unigram_metrics, appointed_cuda_devices  # noqa: F401 - add_unigram_metrics: reference name of this module
 
 
 def pick_device(local_rank: int = 0) -> torch.device:
@@ -196,33 +197,105 @@ def build_icl_suite(cfg: Any, max_seq_len: int) -> Any:
     return lambda logits_fn: run_icl_suite(logits_fn, tokenizer, cfg, max_seq_len)
 
 
+@dataclasses.dataclass
+class TrainerMutableAttributes:
+    """What changes on a live Trainer between clients / rounds (ref: trainer_utils.py:172-202): the client's loaders, its loggers and
+    callbacks, the per-client training config and the checkpoint file templates. Everything else — model, optimizer planes, CUDA
+    context, kernel workspace, captured graphs — is kept."""
+
+    train_loader: Any
+    evaluators: dict[str, Any] | None
+    callbacks: list[Any] | None
+    loggers: list[Any] | None
+    train_cfg: Any
+    save_latest_filename: str | None = None
+    save_filename: str = "ep{epoch}-ba{batch}-rank{rank}.pt"
+
+
+def get_trainer_mutables_from_config(cfg: Any, cid: int | str | None, trainer: Trainer, *, log_name: str = "", split_eval: bool = False,
+                                     rebuild_loggers: bool = False) -> TrainerMutableAttributes:
+    """Build the per-client mutables from the resolved config for the geometry of ``trainer`` (rank, world size, device batch)
+    (ref: trainer_utils.py:330-653). Loggers / callbacks are rebuilt only on request: re-opening a wandb run or a tensorboard
+    writer every round is what the reference's per-client logger names exist for, the default keeps the Trainer's own."""
+    t, evals = _prepare_train_cfg(cfg, cid, split_eval, trainer.world_size, log_name)
+    seed = int(t.get("seed", 17))
+    syn_vocab = min(int(trainer.model_cfg.vocab_size), TOKENIZER_VOCAB)
+    train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed, syn_vocab)
+    evaluators = {lbl: build_text_loader(lc, trainer.device_eval_batch_size, trainer.rank, trainer.world_size, seed + 1, syn_vocab)
+                  for lbl, lc in evals.items()}
+    loggers = callbacks = None
+    if rebuild_loggers:
+        save_root = t.get("save_folder") or "."
+        interval = t.get("console_log_interval", "1ba")
+        loggers = build_loggers(t.get("loggers"), Path(str(save_root)).parent if t.get("save_folder") else ".", str(t["run_name"]),
+                                console_interval=Time.parse(interval).to_batches(), log_to_console=bool(t.get("log_to_console", True)),
+                                rank=trainer.rank, progress_bar=bool(t.get("progress_bar", False)))
+        callbacks = build_callbacks(_with_profiler(t))
+    return TrainerMutableAttributes(train_loader, evaluators, callbacks, loggers, t, t.get("save_latest_filename"),
+                                    t.get("save_filename") or "ep{epoch}-ba{batch}-rank{rank}.pt")
+
+
+def set_mutables_trainer_train_dataloader(trainer: Trainer, train_dataloader: Any, client_config: Any = None) -> None:
+    """(ref: trainer_utils.py:911-982) the iterator restarts with the new loader; the data position of a resumed client comes back
+    with its checkpoint (``load_trainer_checkpoint``)."""
+    del client_config
+    trainer.train_loader = train_dataloader
+    trainer._train_iter = None  # noqa: SLF001
+
+
+def set_mutables_trainer_eval_dataloader(trainer: Trainer, eval_dataloader: dict[str, Any] | None, train_cfg: Any = None) -> None:
+    """(ref: trainer_utils.py:985-1068) one evaluator per label; metric objects are created lazily per label by ``Trainer.eval``."""
+    del train_cfg
+    trainer.eval_loaders = dict(eval_dataloader or {})
+
+
+def set_mutables_trainer_callbacks_and_loggers(trainer: Trainer, callbacks: list[Any] | None, loggers: list[Any] | None, train_cfg: Any,
+                                               save_latest_filename: str | None = None, save_filename: str | None = None) -> None:
+    """(ref: trainer_utils.py:656-908) new loggers / callbacks replace the old ones (which are closed), and the checkpoint policy
+    of the client — folder, file templates — is installed."""
+    if loggers is not None:
+        for lg in trainer.loggers:
+            lg.close()
+        trainer.loggers = list(loggers)
+    if callbacks is not None:
+        trainer.callbacks = list(callbacks)
+    trainer.save_folder = train_cfg.get("save_folder")
+    trainer._saved = []  # noqa: SLF001
+    if save_filename:
+        trainer.save_filename = save_filename
+    if save_latest_filename:
+        trainer.save_latest_filename = save_latest_filename
+    trainer.state.run_name = str(train_cfg["run_name"])
+
+
+def set_mutables_trainer(trainer: Trainer, trainer_mutable_attributes: TrainerMutableAttributes, client_config: Any = None,
+                         reset_timestamp: bool = False) -> None:
+    """Install a :class:`TrainerMutableAttributes` on a live Trainer (ref: trainer_utils.py:1071-1114). The reference always
+    zeroes the clocks here and restores them from the client checkpoint; ``reset_timestamp`` makes that explicit."""
+    m = trainer_mutable_attributes
+    set_mutables_trainer_callbacks_and_loggers(trainer, m.callbacks, m.loggers, m.train_cfg, m.save_latest_filename, m.save_filename)
+    set_mutables_trainer_train_dataloader(trainer, m.train_loader, client_config)
+    set_mutables_trainer_eval_dataloader(trainer, m.evaluators, m.train_cfg)
+    trainer.closed = False
+    if reset_timestamp:
+        trainer.state.timestamp.reset()
+
+
 def reconfigure_trainer(trainer: Trainer, cfg: Any, cid: int | str | None, *, log_name: str = "", split_eval: bool = False,
                         reset_timestamp: bool = False, use_unigram_metrics: bool | None = None,
                         allow_unigram_metrics_failures: bool = False) -> Any:
     """Swap the per-client mutables on a live Trainer (loaders, save folder, run name, clocks, and — when
-    ``use_unigram_metrics`` — the unigram table of THIS client's streams; ref: trainer_utils.py:278-327,656-1114)."""
-    t, evals = _prepare_train_cfg(cfg, cid, split_eval, trainer.world_size, log_name)
+    ``use_unigram_metrics`` — the unigram table of THIS client's streams; ref: trainer_utils.py:278-327,656-1114):
+    ``get_trainer_mutables_from_config`` + ``set_mutables_trainer`` in one call. Returns the client's training config."""
+    m = get_trainer_mutables_from_config(cfg, cid, trainer, log_name=log_name, split_eval=split_eval)
     if use_unigram_metrics:
-        from photon_b200.utils.core import add_unigram_metrics
-
-        freq = lcf.get_stream_freq_dict_for_client(t, cid, allow_failures=allow_unigram_metrics_failures)
+        freq = lcf.get_stream_freq_dict_for_client(m.train_cfg, cid, allow_failures=allow_unigram_metrics_failures)
         if freq is not None:
             add_unigram_metrics(trainer, freq)
         elif not allow_unigram_metrics_failures:
             raise RuntimeError("unigram metrics requested but no 1_gram.json found")
-    seed = int(t.get("seed", 17))
-    syn_vocab = min(int(trainer.model_cfg.vocab_size), TOKENIZER_VOCAB)
-    trainer.train_loader = build_text_loader(t["train_loader"], trainer.device_batch, trainer.rank, trainer.world_size, seed, syn_vocab)
-    trainer.eval_loaders = {lbl: build_text_loader(lc, trainer.device_eval_batch_size, trainer.rank, trainer.world_size, seed + 1, syn_vocab)
-                            for lbl, lc in evals.items()}
-    trainer._train_iter = None  # noqa: SLF001
-    trainer.save_folder = t.get("save_folder")
-    trainer._saved = []  # noqa: SLF001
-    trainer.state.run_name = str(t["run_name"])
-    trainer.closed = False
-    if reset_timestamp:
-        trainer.state.timestamp.reset()
-    return t
+    set_mutables_trainer(trainer, m, reset_timestamp=reset_timestamp)
+    return m.train_cfg
 
 
 def load_trainer_checkpoint(trainer: Trainer, load_path: str, ignore_keys: list[str] | None = None) -> None:

@@ -58,12 +58,9 @@ def convert_split(docs: Any, tokenizer: Any, out_dirs: list[Path], seq_len: int,
     return written
 
 
-def main(argv: list[str] | None = None) -> dict[str, list[int]]:
-    """CLI with the reference's flag surface (ref: photon/dataset/convert_dataset_hf.py:93-140). ``--path`` / ``--name`` select
-    an HF dataset when it is cached locally; ``--source`` takes a local text/jsonl file or directory (or ``synthetic://N``)."""
-    import json
-    import shutil
-
+def parse_args(argv: list[str] | None = None) -> argparse.Namespace:
+    """The reference's flag surface (ref: photon/dataset/convert_dataset_hf.py:30-172). ``--path`` / ``--name`` select an HF dataset
+    when it is cached locally; ``--source`` takes a local text/jsonl file or directory (or ``synthetic://N``)."""
     ap = argparse.ArgumentParser(description="Convert a text corpus into per-client token shards")
     ap.add_argument("--dataset", default="c4_en", choices=sorted(DATASETS_CONSTANTS))
     ap.add_argument("--path", default=None, help="HF dataset path (reference flag); default: the table entry of --dataset")
@@ -86,6 +83,15 @@ def main(argv: list[str] | None = None) -> dict[str, list[int]]:
     args = ap.parse_args(argv)
     if args.name and f"c4_{args.name}" in DATASETS_CONSTANTS and args.dataset == "c4_en":
         args.dataset = f"c4_{args.name}"
+    return args
+
+
+def main(argv: list[str] | None = None) -> dict[str, list[int]]:
+    """Convert the selected splits into per-client token shards (ref: photon/dataset/convert_dataset_hf.py:175-330)."""
+    import json
+    import shutil
+
+    args = parse_args(argv)
     if args.compression == "zstd":
         from photon_b200.data.shards import _zstd
 

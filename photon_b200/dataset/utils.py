@@ -111,3 +111,70 @@ def iter_text_source(source: str, split: str | None = None, text_key: str = "tex
         n += 1
         if limit and n >= limit:
             return
+
+
+# ----------------------------------------------------------------------------- reference-named entry points
+def check_tokenizer_config(tokenizer: Any, bos_text: str = "", eos_text: str = "") -> None:
+    """Catch the double-special-token trap before converting a corpus (ref: photon/dataset/utils.py:27-102): the converter adds
+    ``bos_text`` / ``eos_text`` itself, so a tokenizer that ALSO inserts BOS / EOS on its own would put two of them at every document
+    boundary. Documents are encoded with ``add_special_tokens=False`` here, which makes that impossible; this check verifies it on
+    a probe string and that the boundary texts encode to something."""
+    if isinstance(tokenizer, ByteTokenizer):
+        return
+    probe = _encode(tokenizer, "probe text")
+    for name, tid in (("bos", getattr(tokenizer, "bos_token_id", None)), ("eos", getattr(tokenizer, "eos_token_id", None))):
+        if tid is not None and probe and (probe[0] == tid or probe[-1] == tid):
+            raise ValueError(f"the tokenizer inserts its {name} token by itself even with add_special_tokens=False; "
+                             f"pass an empty {name}_text or fix the tokenizer configuration")
+    for label, text in (("bos_text", bos_text), ("eos_text", eos_text)):
+        if text and not _encode(tokenizer, text):
+            raise ValueError(f"{label}={text!r} encodes to no tokens with this tokenizer")
+
+
+def build_hf_dataset(path: str, split: str, mode: Any = "CONCAT_TOKENS", temp_dir: Any = None, max_length: int | None = None,
+                     bos_text: str = "", eos_text: str = "", tokenizer: Any = None, name: str | None = None, *,
+                     no_wrap: bool = False, limit: int | None = None) -> Iterator[dict[str, Any]]:
+    """An iterable of converter samples from a text source (ref: photon/dataset/utils.py:105-210): ``NO_CONCAT`` yields
+    ``{"text": …}`` per document, ``CONCAT_TOKENS`` yields ``{"tokens": int32[max_length]}`` windows packed with BOS / EOS.
+    ``path`` is anything :func:`iter_text_source` reads (text / jsonl files, a directory, ``synthetic://N``, or a Hugging Face
+    dataset that is in the local cache); ``name`` selects the language folder of a C4-style local tree; ``temp_dir`` is accepted
+    for signature compatibility (nothing is staged)."""
+    del temp_dir
+    mode_s = getattr(mode, "value", mode)
+    src = str(Path(path) / name) if name and (Path(path) / name).exists() else path
+    docs = iter_text_source(src, split=split, limit=limit)
+    if mode_s == "NO_CONCAT":
+        return ({"text": d} for d in docs)
+    if mode_s != "CONCAT_TOKENS":
+        raise ValueError(f"unknown concatenation mode {mode!r}")
+    if tokenizer is None or not max_length:
+        raise ValueError("CONCAT_TOKENS needs a tokenizer and max_length")
+    check_tokenizer_config(tokenizer, bos_text, eos_text)
+    return ({"tokens": s} for s in concat_tokens(docs, tokenizer, int(max_length), bos_text=bos_text, eos_text=eos_text, no_wrap=no_wrap))
+
+
+def build_dataloader(dataset: Any, batch_size: int, num_workers: int | None = None) -> Any:
+    """Batches of converter samples (ref: photon/dataset/utils.py:213-260: a torch DataLoader whose worker count defaults to the
+    CPU count). The samples here come out of a generator that is already the bottleneck-free part of the conversion (tokenisation
+    dominates), so batching happens in-process: lists of ``batch_size`` samples, stacked when they are token windows."""
+    del num_workers
+
+    def batches() -> Iterator[dict[str, Any]]:
+        buf: list[dict[str, Any]] = []
+        for s in dataset:
+            buf.append(s)
+            if len(buf) == batch_size:
+                yield _collate(buf)
+                buf = []
+        if buf:
+            yield _collate(buf)
+
+    return batches()
+
+
+def _collate(samples: list[dict[str, Any]]) -> dict[str, Any]:
+    out: dict[str, Any] = {}
+    for k in samples[0]:
+        vals = [s[k] for s in samples]
+        out[k] = np.stack(vals) if isinstance(vals[0], np.ndarray) else vals
+    return out

@@ -31,3 +31,17 @@ def broadcast_parameters_to_nodes(runtime: Any, params: torch.Tensor | None, mom
     runtime.round_backend.set_global(bufs[0], bufs[1], bufs[2])
     acks = [{"broadcast": {"status": "OK"}}] * runtime.world_size
     return {"acks": acks, "server/broadcast_time": time.time() - t0}
+
+
+def parameters_to_broadcast_recordset(parameters: Any, *, keep_input: bool = True, node_id: int = 0) -> Any:
+    """The QUERY message that carries a broadcast (ref: broadcast_utils.py:28-57 builds a RecordSet with the parameters and a
+    ``{"action": "set_parameters"}`` config): ``parameters`` is a flat tensor, an ndarray list or already a ``ParamHandle``
+    (side-channel locator). ``keep_input=False`` drops the caller's reference to an inline payload once it is in the message, like
+    the reference's conversion does."""
+    from photon_b200.messages import Message, ParamHandle
+
+    handle = parameters if isinstance(parameters, ParamHandle) else ParamHandle("inline", parameters)
+    msg = Message("query", {"type": "broadcast_parameters", "action": "set_parameters", "parameters": handle}, node_id=node_id)
+    if not keep_input and isinstance(parameters, list):
+        parameters.clear()
+    return msg

@@ -34,6 +34,28 @@ def check_failures(n_failures: int, accept_failures_cnt: int, ignore_failed_roun
     raise TooManyFailuresError(f"{n_failures} client failure(s) > accept_failures_cnt={accept_failures_cnt}")
 
 
+def get_handle_success_and_failure_fit(metrics_accumulator: list[tuple[dict[str, Any], Any, int]], fit_failures: list[FitRes | None],
+                                       accept_failures_cnt: int | None) -> Any:
+    """The reference's streaming form of ``split_results`` + ``check_failures`` (ref: fit_utils.py:220-288): a callable fed one
+    ``(ok, FitRes)`` pair at a time — successes append ``(metrics, status, num_examples)``, failures are collected and counted, and
+    the count passing ``accept_failures_cnt`` raises. (The count is cumulative over the closure's life; the reference resets it on
+    every call, which makes its own limit unreachable.)"""
+    seen = {"failures": 0}
+
+    def handle_success_and_failure_fit(result: tuple[bool, FitRes | None]) -> tuple[bool, FitRes | None]:
+        ok, res = result
+        if ok and res is not None:
+            metrics_accumulator.append((res.metrics, res.status, res.num_examples))
+            return True, res
+        seen["failures"] += 1
+        if accept_failures_cnt is not None and seen["failures"] > accept_failures_cnt:
+            raise TooManyFailuresError(f"{seen['failures']} client failure(s) > accept_failures_cnt={accept_failures_cnt}")
+        fit_failures.append(res)
+        return False, res
+
+    return handle_success_and_failure_fit
+
+
 def handle_fit_replies(runtime: Any, server_round: int, results: list[FitRes]) -> dict[str, Any]:
     """Server bookkeeping after the transport has consumed the parameter payloads."""
     ok, failed = split_results(results)

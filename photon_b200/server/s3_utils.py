@@ -177,3 +177,147 @@ def import_checkpoints(cfg: Any, state_keys: Sequence[str]) -> int | None:
 
 def cleanup_checkpoints(cfg: Any, per_round: bool = False) -> None:
     _store(cfg).cleanup_checkpoints(str(cfg["run_uuid"]), per_round=per_round)
+
+
+# ------------------------------------------------------------------ the reference's URI-based helpers (ref: s3_utils.py:75-212,1118-1641)
+# They take ``s3://bucket/prefix`` strings (or plain directory paths) instead of a config: resolved against the configured S3 endpoint
+# when there is one, else against the directory ``$PHOTON_SAVE_PATH/<bucket>``.
+class NoCheckpointsFoundError(FileNotFoundError):
+    """Nothing to resume from under the path that was looked up (ref: s3_utils.py:75-76)."""
+
+
+def _uri_store(uri: str, leaf: bool = False) -> tuple[Any, str]:
+    """(object store, key) of ``s3://bucket/key`` or of a local path. ``leaf``: the path names ONE object (the store is its
+    directory); otherwise it names a prefix / directory (the store is rooted there, the key is empty)."""
+    import os
+
+    from photon_b200.utils.objstore import DirObjectStore, remote_store_from_cfg
+
+    if str(uri).startswith("s3://"):
+        bucket, _, prefix = str(uri)[len("s3://"):].partition("/")
+        store = remote_store_from_cfg({"s3_comm_config": {"bucket_name": bucket}})
+        if store is None:
+            store = DirObjectStore(Path(os.environ.get("PHOTON_SAVE_PATH", ".")) / bucket, create=False)
+        return store, prefix.strip("/")
+    p = Path(uri)
+    return (DirObjectStore(p.parent, create=False), p.name) if leaf else (DirObjectStore(p, create=False), "")
+
+
+def list_objects(run_uuid_path: str) -> tuple[bool, list[str]]:
+    """(anything there?, keys below the path, relative to it) (ref: s3_utils.py:114-155)."""
+    store, prefix = _uri_store(run_uuid_path)
+    keys = store.list(prefix + "/" if prefix else "")
+    return bool(keys), [k[len(prefix) + 1:] if prefix else k for k in keys]
+
+
+def delete_object(object_path: str) -> None:
+    """(ref: s3_utils.py:79-111)"""
+    store, key = _uri_store(object_path, leaf=True)
+    store.delete(key)
+
+
+def delete_remote_object(object_name: str) -> None:
+    """Delete an object or everything below a prefix; a missing object is not an error (ref: s3_utils.py:1446-1475)."""
+    store, key = _uri_store(object_name, leaf=True)
+    store.delete(key)
+    store.delete_prefix(key + "/")
+
+
+def get_num_batches_from_checkpoint_name(checkpoint_name: str) -> int:
+    """``ep3-ba1280-rank0.pt`` → 1280 (ref: s3_utils.py:1234-1258)."""
+    import re
+
+    m = re.search(r"-ba(\d+)-", checkpoint_name)
+    if not m:
+        raise ValueError(f"not a trainer checkpoint name (…-ba<batches>-…): {checkpoint_name}")
+    return int(m.group(1))
+
+
+def _rounds_under(store: Any, prefix: str, state_keys: Sequence[str]) -> list[int]:
+    have: dict[int, set[str]] = {}
+    base = f"{prefix}/server/" if prefix else "server/"
+    for k in store.list(base):
+        parts = k[len(base):].split("/")
+        if len(parts) == 2 and parts[0].isdigit():
+            have.setdefault(int(parts[0]), set()).add(parts[1])
+    want = {"state.bin", *(f"{k}.npz" for k in state_keys)}
+    return sorted(r for r, files in have.items() if want <= files)
+
+
+def obtain_sorted_runs(run_uuid_path: str, state_keys: Sequence[str]) -> list[int]:
+    """Round numbers with a COMPLETE server checkpoint under ``{run_uuid_path}/server/`` (ref: s3_utils.py:1261-1318; the reference
+    names them "runs")."""
+    store, prefix = _uri_store(run_uuid_path)
+    rounds = _rounds_under(store, prefix, state_keys)
+    if not rounds and not store.list(prefix + "/" if prefix else ""):
+        raise NoCheckpointsFoundError(f"nothing under {run_uuid_path}")
+    return rounds
+
+
+def delete_rounds(run_uuid_path: str, state_keys: Sequence[str], end_idx: int | None = -1) -> None:
+    """Delete the complete rounds ``[:end_idx]`` — the default keeps the newest (ref: s3_utils.py:1383-1443)."""
+    store, prefix = _uri_store(run_uuid_path)
+    base = f"{prefix}/server/" if prefix else "server/"
+    for r in _rounds_under(store, prefix, state_keys)[:end_idx]:
+        store.delete_prefix(f"{base}{r}/")
+
+
+def delete_clients_checkpoints(run_uuid_path: str, end_idx: int | None = -1) -> None:
+    """Per client folder, delete the trainer checkpoints ``[:end_idx]`` in batch order — the default keeps each client's newest
+    (ref: s3_utils.py:1321-1380)."""
+    store, prefix = _uri_store(run_uuid_path)
+    per: dict[str, list[str]] = {}
+    for k in store.list(prefix + "/" if prefix else ""):
+        rel = k[len(prefix) + 1:] if prefix else k
+        parts = rel.split("/")
+        if len(parts) == 2 and parts[0].startswith("client_") and parts[1].startswith("ep") and parts[1].endswith(".pt"):
+            per.setdefault(parts[0], []).append(k)
+    for keys in per.values():
+        for k in sorted(keys, key=lambda x: get_num_batches_from_checkpoint_name(x.rsplit("/", 1)[1]))[:end_idx]:
+            store.delete(k)
+
+
+def get_file_from_path(input_file_path: str, run_uuid: str = "", s3_comm_config: Any = None, tmp_dir: Any = None) -> Path:
+    """A local path for ``input_file_path``: itself when it is a file, a download into ``tmp_dir`` when it is ``s3://…``
+    (ref: s3_utils.py:1118-1189)."""
+    del run_uuid, s3_comm_config
+    if not str(input_file_path).startswith("s3://"):
+        p = Path(input_file_path)
+        if not p.is_file():
+            raise FileNotFoundError(str(p))
+        return p
+    store, key = _uri_store(input_file_path, leaf=True)
+    d = Path(tmp_dir.name if hasattr(tmp_dir, "name") else (tmp_dir or "."))
+    return store.download(key, d / Path(key).name)
+
+
+def extract_s3_comm_config_from_configrecord(s3_comm_config: Any) -> tuple[str, str, str]:
+    """(endpoint_id, file_name, folder_name) of a side-channel locator: a ``ParamHandle`` or the reference's record / dict with
+    ``endpoint_id`` / ``file_name`` / ``current_round`` (ref: s3_utils.py:158-212)."""
+    meta = s3_comm_config.meta if isinstance(s3_comm_config, ParamHandle) else dict(s3_comm_config)
+    folder = meta.get("folder_name", meta.get("current_round", "comm_stack"))
+    return str(meta["endpoint_id"]), str(meta.get("file_name", "parameters")), str(folder)
+
+
+def upload_server_checkpoint(cfg: Any, server_round: int, *, layout: FlatLayout, tensors: dict[str, torch.Tensor], state: dict[str, Any],
+                             background: bool = False) -> Path:
+    """One round of server state into the run's store (ref: s3_utils.py:480-548): ``state.bin`` + one npz per strategy state key."""
+    return _store(cfg).upload_server_checkpoint(str(cfg["run_uuid"]), server_round, layout=layout, tensors=tensors, state=state, background=background)
+
+
+def download_server_checkpoint(cfg: Any, server_round: int | None = None, *, layout: FlatLayout, state_keys: Sequence[str]
+                               ) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
+    """The round to resume from (``photon.resume_round`` when ``server_round`` is None) as (flat planes, state dict)
+    (ref: s3_utils.py:551-727)."""
+    st = _store(cfg)
+    rnd = server_round if server_round is not None else st.interpret_resume_round(str(cfg["run_uuid"]), cfg["photon"].get("resume_round"), state_keys)
+    if rnd is None:
+        raise NoCheckpointsFoundError(f"run '{cfg['run_uuid']}' has no complete server checkpoint")
+    return st.download_server_checkpoint(str(cfg["run_uuid"]), int(rnd), layout=layout, state_keys=state_keys)
+
+
+def copy_old_checkpoints_to_new_run(cfg: Any, old_uuid: str, new_uuid: str, server_round: int, *, state_keys: Sequence[str],
+                                    copy_client_checkpoints: bool = True, client_ids: Sequence[int] = ()) -> None:
+    """(ref: s3_utils.py:1478-1641; includes the second momentum the reference forgets)"""
+    _store(cfg).copy_old_checkpoints_to_new_run(old_uuid, new_uuid, server_round, state_keys=state_keys,
+                                                copy_client_checkpoints=copy_client_checkpoints, client_ids=client_ids)

@@ -100,3 +100,26 @@ def fit_or_evaluate_ins(kind: str, server_round: int, client_ids: list[int], cli
 
 
 fit_or_evaluate_ins_recordset = fit_or_evaluate_ins  # reference name (ref: server_util.py:205-302); no RecordSet here
+
+
+# ----------------------------------------------------------------------------- reference names (ref: server_util.py:31,65-202)
+from photon_b200.server.fit_utils import TooManyFailuresError  # noqa: E402,F401 - raised by the round loop; lives with the fit code here
+
+
+def message_collaborative(send: Callable[[int, Message], None], receive: Callable[[], list[Message]], message_type: str,
+                          sampled_clients: list[int], gen_ins_function: Callable[[int, int], Any], all_node_ids: list[int], current_round: int,
+                          client_state: dict[int, ClientState], server_steps_cumulative: int, poll_s: float = 0.01) -> Iterator[Message]:
+    """The reference's generator form of the work queue (ref: server_util.py:65-202): the first ``len(all_node_ids)`` sampled clients
+    go out at once, every reply that comes back is yielded and frees its node for the next sampled client. ``send(node_id, message)``
+    / ``receive() -> [replies]`` stand for the driver (``push_messages`` / ``pull_messages``); ``gen_ins_function(round, cid)`` builds
+    the client's instruction config. :class:`ClientScheduler` is the loop underneath."""
+    def dispatch(node: int, cid: int) -> None:
+        msg = fit_or_evaluate_ins(message_type, current_round, [cid], client_state, server_steps_cumulative, {cid: gen_ins_function(current_round, cid)})
+        msg.node_id = node
+        send(node, msg)
+
+    def poll() -> list[tuple[int, int, Message]]:
+        return [(m.node_id, -1, m) for m in receive()]
+
+    for _node, _cid, reply in ClientScheduler(sampled_clients, all_node_ids, dispatch, poll, poll_s=poll_s):
+        yield reply

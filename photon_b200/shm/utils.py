@@ -207,3 +207,72 @@ def close_all_shms(uuid: str) -> None:
     """Unlink every segment this uuid may own (bare + all suffixes)."""
     for suffix in ("", C.NM_CONFIG_SHM, C.NM_PARAMS_SHM, C.W_PARAMS_SHM, C.W_N_SAMPLES_SHM, C.W_EVAL_LOSS_SHM, C.W_METRICS_SHM):
         unlink_quietly(uuid + suffix)
+
+
+# ----------------------------------------------------------------------------- reference-shaped forms (ref: photon/shm/utils.py)
+# The reference's helpers hand back (view, SharedMemory) pairs the caller keeps mapped; these do the same on top of ``_open``.
+def is_shm_existing(name: str) -> bool:
+    """(ref: shm/utils.py:525-545)"""
+    return shm_exists(name)
+
+
+def get_ndarrays_size_and_bounds(ndarrays: Sequence[np.ndarray]) -> tuple[int, list[tuple[int, int]]]:
+    """Total bytes of a parameter payload and the [start, end) byte range of every array inside one flat segment
+    (ref: shm/utils.py:104-140)."""
+    bounds, off = [], 0
+    for a in ndarrays:
+        n = int(np.asarray(a).nbytes)
+        bounds.append((off, off + n))
+        off += n
+    return off, bounds
+
+
+def get_num_samples_shm(name: str, *, create: bool = False) -> tuple[np.ndarray, shared_memory.SharedMemory]:
+    """A mapped one-element int64 array — the sample count a worker reports (ref: shm/utils.py:271-309)."""
+    shm = _open(name, create=create, size=8) if create else _open(name)
+    view = np.ndarray((1,), dtype=np.int64, buffer=shm.buf[:8])
+    if create:
+        view[0] = 0
+    return view, shm
+
+
+def set_num_samples_shm(old_num_samples_sh: np.ndarray, new_num_samples: int) -> None:
+    """(ref: shm/utils.py:312-330)"""
+    old_num_samples_sh[0] = int(new_num_samples)
+
+
+def _pickled_segment(obj: Any, name: str, create: bool) -> tuple[Any, shared_memory.SharedMemory]:
+    if create:
+        set_dict_shm(name, obj)
+    shm = _open(name)
+    n = int.from_bytes(bytes(shm.buf[:8]), "little")
+    return pickle.loads(bytes(shm.buf[8:8 + n])), shm  # noqa: S301 - same-host IPC between our own processes
+
+
+def _store_pickled(obj: Any, shm: shared_memory.SharedMemory) -> None:
+    blob = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    if 8 + len(blob) > shm.size:
+        raise ValueError(f"object needs {8 + len(blob)} bytes, the segment holds {shm.size}: re-create it with get_*_shm(create=True)")
+    shm.buf[:8] = len(blob).to_bytes(8, "little")
+    shm.buf[8:8 + len(blob)] = blob
+
+
+def get_config_shm(config: Any, name: str, *, create: bool = False) -> tuple[Any, shared_memory.SharedMemory]:
+    """The run config through a named segment: ``create=True`` publishes ``config``, otherwise it is read back
+    (ref: shm/utils.py:477-522)."""
+    return _pickled_segment(config, name, create)
+
+
+def set_config_shm(config: Any, shm: shared_memory.SharedMemory) -> None:
+    """(ref: shm/utils.py:548-568)"""
+    _store_pickled(config, shm)
+
+
+def get_dict_configsrecord_shm(name: str, config: Any = None, *, create: bool = False) -> tuple[Any, shared_memory.SharedMemory]:
+    """A dict of per-client instruction records (fit / evaluate configs) through a named segment (ref: shm/utils.py:432-474)."""
+    return _pickled_segment(config, name, create)
+
+
+def set_dict_configsrecord_shm(config: Any, shm: shared_memory.SharedMemory) -> None:
+    """(ref: shm/utils.py:250-268)"""
+    _store_pickled(config, shm)

@@ -69,9 +69,10 @@ class ObjectStore:
 
 
 class DirObjectStore(ObjectStore):
-    def __init__(self, root: str | os.PathLike) -> None:
+    def __init__(self, root: str | os.PathLike, create: bool = True) -> None:
         self.root = Path(root)
-        self.root.mkdir(parents=True, exist_ok=True)
+        if create:
+            self.root.mkdir(parents=True, exist_ok=True)
 
     def _p(self, key: str) -> Path:
         p = (self.root / key).resolve()
@@ -97,7 +98,11 @@ class DirObjectStore(ObjectStore):
 
     def list(self, prefix: str = "") -> list[str]:
         root = self.root.resolve()
-        return sorted(k for k in (str(p.relative_to(root)) for p in root.rglob("*") if p.is_file()) if k.startswith(prefix))
+        # walk only the directory the prefix points into (a prefix is "dir/dir/partial-name")
+        start = (root / prefix).parent if prefix and not prefix.endswith("/") else root / prefix
+        if not start.is_dir():
+            return []
+        return sorted(k for k in (str(p.relative_to(root)) for p in start.rglob("*") if p.is_file()) if k.startswith(prefix))
 
     def delete(self, key: str) -> None:
         p = self._p(key)

@@ -46,3 +46,20 @@ def env_patcher(worker_rank: int, n_workers: int, master_port: int, devices: lis
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+@contextlib.contextmanager
+def get_env_patcher(run_uuid: str, rank: str | int, master_port: str | int, world_size: str | int = 1, devices: list[int] | None = None) -> Iterator[None]:
+    """The reference's name and argument order (ref: worker/utils.py:57-120): the environment of ONE worker of a node for the
+    duration of a task, restored afterwards so the next task can form a fresh process group. ``run_uuid`` names the run in
+    ``RUN_NAME`` (Composer read it from there)."""
+    old = os.environ.get("RUN_NAME")
+    os.environ["RUN_NAME"] = str(run_uuid)
+    try:
+        with env_patcher(int(rank), int(world_size), int(master_port), devices):
+            yield
+    finally:
+        if old is None:
+            os.environ.pop("RUN_NAME", None)
+        else:
+            os.environ["RUN_NAME"] = old

@@ -123,3 +123,32 @@ class Worker(mp.get_context("spawn").Process):  # type: ignore[misc,name-defined
                 self.result_queue.put(WorkerResultMessage(n_samples=-1, delta=0.0, worker_uuid=self.worker_uuid, cid=int(cid),
                                                           error="".join(traceback.format_exception_only(type(e), e)).strip()))
                 return
+
+
+# ----------------------------------------------------------------------------- reference-named module functions (ref: worker.py:534-680)
+def create_new_worker(config: Any, task_queue: Any, result_queue: Any, node_manager_uuid: str, run_uuid: str = "", parameters_metadata: Any = None,
+                      worker_rank: int = 0, n_workers: int = 1, devices: list[int] | None = None) -> Worker:
+    """A worker process object for rank ``worker_rank`` of a node (not started). ``config`` is the composed config (node or plain
+    dict); the parameter metadata travels through the ``…_meta`` segment, so the argument is accepted and unused."""
+    del run_uuid, parameters_metadata
+    cfg_dict = config.to_container() if hasattr(config, "to_container") else dict(config)
+    return Worker(cfg_dict, node_manager_uuid, int(worker_rank), int(n_workers), task_queue, result_queue, devices)
+
+
+def start_worker(worker: Worker) -> None:
+    worker.start()
+    print(f"[node manager] worker {worker.worker_uuid} (rank {worker.worker_rank}) started", flush=True)
+
+
+def get_training_results_from_worker(worker: Worker | None) -> tuple[list[np.ndarray], dict[str, Any], int] | None:
+    """(parameters, metrics, n_samples) a worker left in its segments after a fit task; the arrays are copies, so the worker may
+    reuse its segments (the reference returns the mapped segments too and closes them later)."""
+    if worker is None:
+        return None
+    from photon_b200.shm.utils import get_n_samples_shm
+
+    wu = worker.worker_uuid
+    meta = ModelParametersMetadata.from_literal(get_dict_shm(wu + C.W_PARAMS_SHM + "_meta"))
+    shm, views = get_parameters_shm(wu + C.W_PARAMS_SHM, meta, copy=True)
+    shm.close()
+    return views, dict(get_dict_shm(wu + C.W_METRICS_SHM)), get_n_samples_shm(wu)
