@@ -1,7 +1,7 @@
 """Import alias for code written against the reference package name: ``import photon.X`` resolves to ``photon_b200.X``
 (the very same module objects — nothing is imported twice), e.g.::
 
-    from photon.strategy.fedadam import FedAdam
+    from photon.strategy.fedadam import FedAdam          # module paths of the reference that are merged here map too
     from photon.utils import get_parameters_from_state
     python -m photon.hydra_resolver run_uuid=demo        # == python -m photon_b200.hydra_resolver
 
@@ -13,6 +13,11 @@ import importlib.util
 import sys
 
 _SRC, _DST = __name__, "photon_b200"
+# reference modules whose content lives in ONE module here: the five server optimizers share an implementation, the unigram
+# metrics sit with the other language metrics (both are fed by the same fused-CE by-products)
+_MOVED = {"strategy.fedadam": "strategy.strategies", "strategy.fedavg_eff": "strategy.strategies", "strategy.fedmom": "strategy.strategies",
+          "strategy.fednestorov": "strategy.strategies", "strategy.fedyogi": "strategy.strategies",
+          "strategy.strategy_with_cfg": "strategy.strategies", "metrics.unigram_normalized_metrics": "metrics.language"}
 
 
 class _AliasLoader(importlib.abc.Loader):
@@ -34,7 +39,8 @@ class _AliasFinder(importlib.abc.MetaPathFinder):
     def find_spec(self, fullname, path=None, target=None):
         if not fullname.startswith(_SRC + "."):
             return None
-        real = _DST + fullname[len(_SRC):]
+        rel = fullname[len(_SRC) + 1:]
+        real = f"{_DST}.{_MOVED.get(rel, rel)}"
         try:
             module = importlib.import_module(real)
         except ModuleNotFoundError as e:

@@ -251,3 +251,9 @@ class FedYogi(ServerStrategy):
 
     def __init__(self, eta: float = 1e-2, beta_1: float = 0.9, beta_2: float = 0.99, tau: float = 1e-3, **kw: Any) -> None:
         super().__init__(eta=eta, beta1=beta_1, beta2=beta_2, tau=tau, **kw)
+
+
+# the reference's name for the common base (Flower ``FedAvg`` + the config-function plumbing, ref: photon/strategy/strategy_with_cfg.py:88-162):
+# here ``ServerStrategy`` carries the fit / evaluate metric aggregation, the failure policy lives in ``server/fit_utils.py`` and the
+# per-round config functions in ``clients/configs.py`` (``get_photon_fit_config_fn`` / ``get_photon_evaluate_config_fn``)
+FedAvgWithConfig = ServerStrategy

@@ -292,7 +292,7 @@ def test_param_side_channel_roundtrip(tmp_path):
 
 
 def test_reference_named_helpers(tmp_path):
-    from photon_b200.metrics.unigram_normalized_metrics import create_wrapped_subclass
+    from photon.metrics.unigram_normalized_metrics import create_wrapped_subclass
     from photon_b200.strategy import (FedAdam, FedAvgEfficient, aggregate_parameters, initialize_strategy,
                                       parameters_to_ndarrays_gen)
     from photon_b200.utils.core import (chunks_idx, get_parameters_from_state, get_trainable_params_dict,
