@@ -17,7 +17,8 @@ _SRC, _DST = __name__, "photon_b200"
 # metrics sit with the other language metrics (both are fed by the same fused-CE by-products)
 _MOVED = {"strategy.fedadam": "strategy.strategies", "strategy.fedavg_eff": "strategy.strategies", "strategy.fedmom": "strategy.strategies",
           "strategy.fednestorov": "strategy.strategies", "strategy.fedyogi": "strategy.strategies",
-          "strategy.strategy_with_cfg": "strategy.strategies", "metrics.unigram_normalized_metrics": "metrics.language"}
+          "strategy.strategy_with_cfg": "strategy.strategies", "metrics.unigram_normalized_metrics": "metrics.language",
+          "conf.base_schema": "config.schema"}
 
 
 class _AliasLoader(importlib.abc.Loader):
