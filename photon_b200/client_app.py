@@ -19,6 +19,11 @@ class ClientApp:
         self.cfg, self.node_id = cfg, node_id
         self.nm = NodeManagerApp(cfg, n_workers=n_workers, devices=devices)
         self.refresh_period = int(cfg["photon"].get("refresh_period", 50))
+        # node-level pre-aggregation (``photon.fleet.node_pre_aggregation``): Σ n_k·x_k and Σ n_k of the clients this node trained in
+        # the current round; only the node's weighted mean travels to the server, once, when it asks (``collect_aggregate``)
+        self._agg: list[Any] | None = None
+        self._agg_w = 0
+        self._agg_round = -1
 
     def alive(self) -> bool:
         """Every worker process of this node is up (what makes the node show up in ``node_ids()``)."""
@@ -55,7 +60,35 @@ class ClientApp:
             self.nm.refresh_workers()                     # shed leaked memory (ref: client_app.py:175-177)
         per_client = getattr(msg, "per_client", {})
         results = self.nm.fit({cid: {"fit_config": fc} for cid, fc in per_client.items()})
+        if getattr(msg, "defer_parameters", False):
+            results = [self._fold(r, server_round) for r in results]
         return Message("train", results, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
+
+    def _fold(self, res: FitRes, server_round: int) -> FitRes:
+        """Keep a successful client's parameters HERE (running weighted sum of the round); the reply carries metrics only."""
+        import numpy as np
+
+        if res.status.code != Code.OK or res.parameters is None:
+            return res
+        if self._agg_round != server_round:
+            self._agg, self._agg_w, self._agg_round = None, 0, server_round
+        n = int(res.num_examples)
+        arrays = [np.asarray(a, dtype=np.float64) * n for a in res.parameters.data]
+        self._agg = arrays if self._agg is None else [x + y for x, y in zip(self._agg, arrays)]
+        self._agg_w += n
+        return FitRes(res.status, ParamHandle("deferred", None, {"node_id": self.node_id}), res.num_examples, res.metrics, res.cid)
+
+    def collect_aggregate(self, msg: Message) -> Message:
+        """Hand over (weighted mean of this round's clients, Σ n_k) and forget it."""
+        import numpy as np
+
+        want = int((msg.content or {}).get("server_round", self._agg_round))
+        if self._agg is None or self._agg_round != want or self._agg_w <= 0:
+            body: Any = {"aggregate": None, "num_examples": 0}
+        else:
+            body = {"aggregate": ParamHandle("inline", [(a / self._agg_w).astype(np.float32) for a in self._agg]), "num_examples": self._agg_w}
+        self._agg, self._agg_w = None, 0
+        return Message("query", body, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
 
     def evaluate(self, msg: Message) -> Message:
         per_client = getattr(msg, "per_client", {})
@@ -66,6 +99,8 @@ class ClientApp:
         kind = (msg.content or {}).get("type")
         if kind == "broadcast_parameters":
             return self.set_parameters(msg)
+        if kind == "collect_aggregate":
+            return self.collect_aggregate(msg)
         if kind == "free_resources":
             self.nm.refresh_workers()
             return Message("query", {"free_resources": {"status": "OK"}}, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)

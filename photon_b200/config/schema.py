@@ -57,6 +57,9 @@ class Fleet(_Strict):
     n_remote_nodes: int = 0
     liveness_timeout_s: float = 30.0      # a node that has not polled for this long is gone (its client goes to another node)
     connect_timeout_s: float = 600.0      # how long the server waits for the remote nodes to register
+    # hierarchical aggregation: a node keeps the weighted sum of the clients it trained in a round and ships ONE model when the
+    # server collects (instead of one per client, as the reference does) — the same global model, 1/clients-per-node of the traffic
+    node_pre_aggregation: bool = False
 
 
 class Photon(_Strict):

@@ -71,6 +71,8 @@ class NodeFleetRuntime(FederationRuntime):
         self.fleet_address = fleet.get("address") or None
         self.n_remote_nodes = int(fleet.get("n_remote_nodes", 0) or 0)
         self.fleet_liveness_s = float(fleet.get("liveness_timeout_s", 30.0) or 30.0)
+        # hierarchical aggregation: nodes keep the weighted sum of the clients they trained, ONE model per node per round travels
+        self.node_pre_aggregation = bool(fleet.get("node_pre_aggregation", False))
         self.link: Any = None
         self._pool: ThreadPoolExecutor | None = None
         self._uid = f"pb200_{uuid.uuid4().hex[:8]}"
@@ -165,6 +167,7 @@ class NodeFleetRuntime(FederationRuntime):
             fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
             msg = fit_or_evaluate_ins("train", server_round, [cid], self.client_states, self.server_steps_cumulative, {cid: fc.to_wire()})
             msg.node_id = node
+            msg.defer_parameters = self.node_pre_aggregation  # type: ignore[attr-defined]
             pending[node] = self._pool.submit(by_id[node].handle, msg)
 
         def poll() -> list[tuple[int, int, Message]]:
@@ -178,12 +181,16 @@ class NodeFleetRuntime(FederationRuntime):
             return out
 
         results: list[FitRes] = []
+        held: dict[int, list[int]] = {}       # node -> positions in ``results`` whose parameters the node is holding back
         t0 = time.time()
         with tracer().span("fit_clients", cat="server", server_round=server_round):
             for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps if a.alive()], dispatch, poll, poll_s=0.01,
                                                      is_alive=lambda n: by_id[n].alive()):
                 for res in reply.content or [FitRes(Status(Code.FAILED, reply.error or "empty reply"), None, 0, {}, cid)]:
-                    if res.status.code == Code.OK and res.parameters is not None:
+                    if res.status.code == Code.OK and res.parameters is not None and res.parameters.kind == "deferred":
+                        held.setdefault(_node, []).append(len(results))
+                        res = FitRes(res.status, ParamHandle(kind=rb.name), res.num_examples, res.metrics, res.cid)
+                    elif res.status.code == Code.OK and res.parameters is not None:
                         flat = torch.zeros(self.layout.total, dtype=torch.float32)
                         if res.parameters.kind != "inline":     # a remote node parked its result in the bucket
                             from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
@@ -195,8 +202,37 @@ class NodeFleetRuntime(FederationRuntime):
                         rb.add_client(flat, res.num_examples)
                         res = FitRes(res.status, ParamHandle(kind=rb.name), res.num_examples, res.metrics, res.cid)
                     results.append(res)
+        if held:
+            self._collect_node_aggregates(server_round, held, results, by_id)
         self.timings["node_training_time_s"] = time.time() - t0
         return results
+
+    def _collect_node_aggregates(self, server_round: int, held: dict[int, list[int]], results: list[FitRes], by_id: dict[int, Any]) -> None:
+        """End of the round under ``node_pre_aggregation``: one ``collect_aggregate`` query per node that holds results; its weighted
+        mean is folded in with the node's total weight. A node that cannot deliver (died after training) turns the clients it
+        held into failures — the round's failure policy decides."""
+        assert self._pool is not None and self.round_backend is not None
+        from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
+
+        futs = {n: self._pool.submit(by_id[n].handle, Message("query", {"type": "collect_aggregate", "server_round": server_round}, node_id=n))
+                for n in held}
+        for n, f in futs.items():
+            rep = f.result()
+            body = rep.content if isinstance(rep.content, dict) else {}
+            want = sum(results[i].num_examples for i in held[n])
+            if rep.error or body.get("aggregate") is None or int(body.get("num_examples", 0)) != want:
+                why = rep.error or f"node {n} delivered {body.get('num_examples', 0)} of {want} examples"
+                for i in held[n]:
+                    results[i] = FitRes(Status(Code.FAILED, f"pre-aggregated result lost: {why}"), None, 0, {}, results[i].cid)
+                continue
+            handle = body["aggregate"]
+            if handle.kind != "inline":
+                parked = handle
+                handle = replace_parameters_in_recordset_with_remote(parked)
+                release_remote_parameters(parked)
+            flat = torch.zeros(self.layout.total, dtype=torch.float32)
+            self.layout.from_ndarrays(flat, handle.data)
+            self.round_backend.add_client(flat, want)
 
     # ----------------------------------------------------------------------- evaluate
     def run_clients_evaluate(self, server_round: int, sampled: list[int]) -> list[EvaluateRes]:

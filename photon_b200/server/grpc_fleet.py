@@ -214,12 +214,22 @@ def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
     from photon_b200.utils.objstore import remote_store_from_cfg
 
     store = remote_store_from_cfg(cfg)
-    if store is None or reply.kind != "train" or not isinstance(reply.content, list):
+    if store is None:
         return reply
     import tempfile
     from pathlib import Path
 
     from photon_b200.utils.core import dump_model_parameters_to_file
+
+    if reply.kind == "query" and isinstance(reply.content, dict) and isinstance(reply.content.get("aggregate"), ParamHandle) \
+            and reply.content["aggregate"].kind == "inline":       # the node's pre-aggregated round result
+        key = f"{cfg['run_uuid']}/server/comm_stack/node-{node_id}/aggregate.npz"
+        with tempfile.TemporaryDirectory() as td:
+            store.upload(key, dump_model_parameters_to_file(Path(td) / "p.npz", list(reply.content["aggregate"].data)))
+        reply.content["aggregate"] = ParamHandle("s3", key, {"bucket": str(cfg["s3_comm_config"]["bucket_name"])})
+        return reply
+    if reply.kind != "train" or not isinstance(reply.content, list):
+        return reply
 
     for res in reply.content:
         if isinstance(res, FitRes) and res.parameters is not None and res.parameters.kind == "inline":

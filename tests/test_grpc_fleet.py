@@ -92,6 +92,63 @@ def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
         s3.stop()
 
 
+@pytest.mark.parametrize("store", ["inline", "s3"])
+def test_node_pre_aggregation_ships_one_model_per_node(tmp_path, store, monkeypatch):
+    """``photon.fleet.node_pre_aggregation``: four sampled clients on two remote nodes -> the train replies carry no parameters, each
+    node answers ONE ``collect_aggregate`` query per round with its weighted mean, and the global model equals the per-client path."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    common = ["fl.n_rounds=2", "fl.n_clients_per_round=4", "llm_config.save_folder=null", "fl.strategy_name=fedavg", "photon.topology=nodes",
+              "fl.eval_period=null"]
+    cfg0 = _cfg(tmp_path / "local", "run_uuid=agg", "photon.n_nodes=2", *common)
+    rt0 = NodeFleetRuntime(cfg0)
+    try:
+        run_server(cfg0, runtime=rt0)
+        want = rt0.round_backend.global_params().clone()
+    finally:
+        rt0.close()
+    s3 = FakeS3() if store == "s3" else None
+    env = {}
+    if s3 is not None:
+        env = {"S3_ENDPOINT_URL": s3.endpoint, "AWS_ACCESS_KEY_ID": ACCESS, "AWS_SECRET_ACCESS_KEY": SECRET, "AWS_DEFAULT_REGION": REGION}
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    port = _free_port()
+    procs = _spawn_nodes(2, port, env)
+    cfg = _cfg(tmp_path / "remote", "run_uuid=agg", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=2",
+               "photon.fleet.node_pre_aggregation=true", "s3_comm_config.bucket_name=aggbkt", *common)
+    rt = NodeFleetRuntime(cfg)
+    seen = {"train_with_params": 0, "collect": 0}
+    try:
+        from photon_b200.server import grpc_fleet
+
+        orig = grpc_fleet.FleetLink._push
+
+        def spy(self, request, context):
+            reply = grpc_fleet._de(request)["reply"]
+            if reply.kind == "train":
+                seen["train_with_params"] += sum(1 for r in reply.content if r.parameters is not None and r.parameters.kind != "deferred")
+            if reply.kind == "query" and isinstance(reply.content, dict) and "aggregate" in reply.content:
+                seen["collect"] += 1
+            return orig(self, request, context)
+
+        monkeypatch.setattr(grpc_fleet.FleetLink, "_push", spy)
+        h = run_server(cfg, runtime=rt)
+        assert [v for _, v in h.metrics_distributed_fit["server/n_failures"]] == [0, 0]
+        got = rt.round_backend.global_params().clone()
+    finally:
+        rt.close()
+    outs = _reap(procs)
+    assert all(p.returncode == 0 for p in procs), outs
+    assert seen["train_with_params"] == 0 and 2 <= seen["collect"] <= 4, seen       # <= one aggregate per node per round, never a client model
+    assert torch.allclose(got, want, atol=1e-5), float((got - want).abs().max())     # a mean of node means: same value, another rounding order
+    if s3 is not None:
+        puts = [k for m, k in s3.requests if m == "PUT"]
+        assert any("/node-1000/aggregate.npz" in k or "/node-1001/aggregate.npz" in k for k in puts) and not any("/client_" in k for k in puts)
+        s3.stop()
+
+
 def test_wrong_token_is_refused(tmp_path, monkeypatch):
     from photon_b200.server.grpc_fleet import FleetLink
 
