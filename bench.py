@@ -391,7 +391,7 @@ def main() -> None:
             emit({"error": "the stock-PyTorch arm did not finish within its time limit; headline printed without it"})
             os._exit(0)
 
-        dog = threading.Timer(max(300.0, 12.0 * t_ours), bail)
+        dog = threading.Timer(min(420.0, max(180.0, 8.0 * t_ours)), bail)     # bounded: the whole invocation stays far below the driver's limit
         dog.daemon = True
         dog.start()
         gc.collect()
