@@ -287,7 +287,15 @@ def get_file_from_path(input_file_path: str, run_uuid: str = "", s3_comm_config:
             raise FileNotFoundError(str(p))
         return p
     store, key = _uri_store(input_file_path, leaf=True)
-    d = Path(tmp_dir.name if hasattr(tmp_dir, "name") else (tmp_dir or "."))
+    import os
+    import tempfile
+
+    if tmp_dir is None:
+        d = Path(tempfile.mkdtemp(prefix="photon_dl_"))
+    elif isinstance(tmp_dir, (str, os.PathLike)):
+        d = Path(tmp_dir)
+    else:
+        d = Path(tmp_dir.name)          # a tempfile.TemporaryDirectory, like the reference passes
     return store.download(key, d / Path(key).name)
 
 
