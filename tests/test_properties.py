@@ -217,3 +217,105 @@ def test_resume_round_resolution(rounds, want):
                 raise AssertionError("an incomplete / missing round must not resolve")
             except FileNotFoundError:
                 pass
+
+
+# ------------------------------------------------------------------------------------------------ full sharding plan
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 6), st.integers(1, 8), st.lists(st.integers(1, 700), min_size=3, max_size=6), st.integers(1, 3000))
+def test_zero3_unit_plan_owns_every_index_exactly_once(n_layers, world, block_sizes, emb):
+    """Any block structure, any world size: units tile the flat space, slices are equal and 256-aligned, the shards of all ranks
+    reassemble the full vector, and the packed buffer of 1-D tensors is rebuilt from pieces of the owners' shards."""
+    from photon_b200.parallel.zero3 import UnitPlan
+
+    named = {}
+    for b in range(n_layers):
+        for j, sz in enumerate(block_sizes):
+            named[f"transformer.blocks.{b}.t{j}.weight"] = (sz, 2) if j % 2 == 0 else (sz,)
+    named["transformer.norm_f.weight"] = (7,)
+    named["transformer.wte.weight"] = (emb, 3)
+    lay = FlatLayout.build(named.items())
+    pl = UnitPlan(lay, n_layers, world)
+    spans = sorted((u.lo, u.hi) for u in pl.units)
+    assert spans[0][0] == 0 and spans[-1][1] == lay.total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert all(u.per % 256 == 0 and u.per * world >= u.hi - u.lo and u.off % 256 == 0 for u in pl.units)
+    full = torch.arange(lay.total, dtype=torch.float32)
+    owners = torch.zeros(lay.total)
+    shards = []
+    for r in range(world):
+        sh = pl.full_to_shard(full, r, torch.empty(pl.shard_len))
+        shards.append(sh)
+        for u in range(len(pl.units)):
+            lo, hi = pl.slice_range(u, r)
+            owners[lo:hi] += 1
+    assert bool((owners == 1).all())
+    rec = torch.full((lay.total,), -1.0)
+    for r in range(world):
+        pl.shard_to_full(shards[r], r, rec)
+    assert torch.equal(rec, full)
+    small = torch.full((pl.small_len,), -1.0)
+    for r, so, do, k in pl.small_copies():
+        assert 0 <= r < world and so + k <= pl.shard_len
+        small[do: do + k] = shards[r][so: so + k]
+    for name, i in pl.small_index.items():
+        o = pl.small_offsets[name]
+        assert torch.equal(small[o: o + lay.numels[i]], full[lay.offsets[i]: lay.offsets[i] + lay.numels[i]])
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 9), st.sampled_from(["put", "get", "pop"])), min_size=1, max_size=60), st.integers(1, 6))
+def test_client_state_cache_never_exceeds_its_budget(ops_, cap):
+    """Whatever the access pattern: at most ``cap`` entries survive, a hit returns what was put last, and the survivors are the most
+    recently used ones."""
+    from photon_b200.federation import ClientStateCache
+
+    one = 2 * 64 * 4
+    c = ClientStateCache(device_bytes=0, host_bytes=cap * one)
+    model: dict[int, int] = {}
+    order: list[int] = []           # least recently used first
+    for cid, op in ops_:
+        if op == "put":
+            stamp = len(order) + 1000 * cid
+            c.put(cid, torch.full((64,), float(stamp)), torch.zeros(64), stamp)
+            model[cid] = stamp
+            order = [x for x in order if x != cid] + [cid]
+            while len(order) > cap:
+                model.pop(order.pop(0))
+        elif op == "get" and cid in model:
+            m, _, step = c.get(cid)
+            assert step == model[cid] and float(m[0]) == float(model[cid])
+            order = [x for x in order if x != cid] + [cid]
+        elif op == "pop":
+            got = c.pop(cid)
+            assert (got is None) == (cid not in model)
+            model.pop(cid, None)
+            order = [x for x in order if x != cid]
+        assert len(c) == len(model) <= cap and all(k in c for k in model)
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.text(alphabet="abcXYZ019 +$&=?#%/._-~é", min_size=1, max_size=30), st.dictionaries(st.sampled_from(["prefix", "list-type", "uploads", "partNumber", "k y"]),
+                                                                                           st.text(alphabet="ab 1/+=&", max_size=8), max_size=3))
+def test_sigv4_signature_is_stable_under_odd_keys_and_queries(key, query):
+    """The signed path / query are exactly what goes on the wire: an independent re-derivation (the test endpoint's) agrees for any key."""
+    import datetime as dt
+    import hashlib
+    import hmac
+    import urllib.parse
+
+    from photon_b200.utils.objstore import _EMPTY_SHA, _quote, sigv4_headers
+
+    now = dt.datetime(2024, 2, 29, 12, 0, 0, tzinfo=dt.timezone.utc)
+    path = "/bkt/" + _quote(key.lstrip("/") or "k", safe="-_.~/")
+    h = sigv4_headers("GET", "host:9000", path, query, {}, _EMPTY_SHA, access_key="AK", secret_key="s/e+c", region="r1", now=now)
+    sig = h["authorization"].rsplit("Signature=", 1)[1]
+    url_query = "&".join(f"{_quote(k)}={_quote(v)}" for k, v in sorted(query.items()))
+    q = sorted(urllib.parse.parse_qsl(url_query, keep_blank_values=True))
+    cq = "&".join(f"{urllib.parse.quote(k, safe='-_.~')}={urllib.parse.quote(v, safe='-_.~')}" for k, v in q)
+    signed = "host;x-amz-content-sha256;x-amz-date"
+    canonical = "\n".join(["GET", path, cq, f"host:host:9000\nx-amz-content-sha256:{_EMPTY_SHA}\nx-amz-date:20240229T120000Z\n", signed, _EMPTY_SHA])
+    to_sign = "\n".join(["AWS4-HMAC-SHA256", "20240229T120000Z", "20240229/r1/s3/aws4_request", hashlib.sha256(canonical.encode()).hexdigest()])
+    k = ("AWS4" + "s/e+c").encode()
+    for part in ("20240229", "r1", "s3", "aws4_request"):
+        k = hmac.new(k, part.encode(), hashlib.sha256).digest()
+    assert hmac.new(k, to_sign.encode(), hashlib.sha256).hexdigest() == sig
+    assert urllib.parse.unquote(path) == "/bkt/" + (key.lstrip("/") or "k")          # the key survives the encoding round trip
