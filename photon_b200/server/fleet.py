@@ -123,20 +123,16 @@ class NodeFleetRuntime(FederationRuntime):
                 handles.append(h)
                 futs += [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": h}, node_id=app.node_id))
                          for app in local]
-            if remote:      # one object in the bucket for every other machine (or, without a store, the arrays in the message)
+            if remote:      # one object for every other machine: in the S3 bucket, or in the link's own object service
                 from photon_b200.utils.objstore import remote_store_from_cfg
 
                 store = remote_store_from_cfg(self.cfg)
                 inline = ParamHandle("inline", self.round_backend.global_params())
-                if store is not None:
-                    h = replace_remote_with_parameters_in_recordset(
-                        inline, "s3", endpoint_id="server", layout=self.layout, store=store, bucket=str(self.cfg["s3_comm_config"]["bucket_name"]),
-                        folder_name=f"{self.cfg['run_uuid']}/server/comm_stack")
-                    handles.append(h)
-                else:
-                    from photon_b200.server.s3_utils import _as_arrays
-
-                    h = ParamHandle("inline", _as_arrays(inline.data, self.layout))
+                h = replace_remote_with_parameters_in_recordset(
+                    inline, "s3" if store is not None else "link", endpoint_id="server", layout=self.layout,
+                    store=store if store is not None else self.link.spool, bucket=str(self.cfg["s3_comm_config"]["bucket_name"]),
+                    folder_name=f"{self.cfg['run_uuid']}/server/comm_stack")
+                handles.append(h)
                 futs += [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": h}, node_id=app.node_id))
                          for app in remote]
             acks = [f.result() for f in futs]

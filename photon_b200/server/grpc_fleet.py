@@ -16,9 +16,11 @@ generic (bytes-in / bytes-out) method handlers — no generated stubs:
 * :func:`serve_node` (node process, ``python -m photon_b200.node``): registers, builds its ``ClientApp`` (node manager + one
   worker per local GPU, DDP / ZeRO inside the node), then pull → handle → push until the server says ``shutdown``.
 
-Parameters never ride inside a control message when an object store is configured (``S3_ENDPOINT_URL`` …): both directions park
-them in the bucket and send the key (``ParamHandle("s3", key)``), like the reference's ``comm_stack.s3``. Without a store they
-travel inline in the gRPC message (pickled ndarrays; fine up to the 2 GiB gRPC frame, i.e. models up to ≈ 500 M parameters).
+Parameters never ride inside a control message: with an object store configured (``S3_ENDPOINT_URL`` …) both directions park them in
+the bucket and send the key (``ParamHandle("s3", key)``), like the reference's ``comm_stack.s3``; without one the LINK ITSELF is the
+object store — the role Ray's object store plays in the reference's ``comm_stack.ray``: the server spools npz objects in a scratch
+directory, nodes pull / push them in 32 MiB chunks over three more RPCs (``ObjGet`` / ``ObjPut`` / ``ObjDel``,
+:class:`LinkObjectStore`), the message carries ``ParamHandle("link", key)``. No size limit (a gRPC frame is never larger than a chunk).
 
 Messages are pickled: the link is for a trusted cluster (as the reference's pickled payloads are). ``PHOTON_FLEET_TOKEN`` — when set
 on both sides — is checked on every call; TLS: pass ``tls=(key, cert)`` / ``tls_ca`` (env ``PHOTON_FLEET_TLS_KEY`` / ``_CERT`` / ``_CA``).
@@ -112,10 +114,18 @@ class FleetLink:
         self._slots: dict[int, _Slot] = {}
         self._lock = threading.Lock()
         self._msg_id = 0
+        import tempfile
+
+        from photon_b200.server import s3_utils
+        from photon_b200.utils.objstore import DirObjectStore
+
+        self._spool_dir = tempfile.mkdtemp(prefix="photon_link_")
+        self.spool = DirObjectStore(self._spool_dir)           # what ObjGet / ObjPut / ObjDel serve; the server reads it directly
+        s3_utils.set_link_store(self.spool)
         self._server = grpc.server(ThreadPoolExecutor(max_workers=64, thread_name_prefix="fleet-link"), options=_OPTS)
         ident = lambda b: b  # noqa: E731 - payloads are already bytes
         handlers = {name: grpc.unary_unary_rpc_method_handler(getattr(self, "_" + name.lower()), request_deserializer=ident, response_serializer=ident)
-                    for name in ("Register", "Pull", "Push", "Beat")}
+                    for name in ("Register", "Pull", "Push", "Beat", "ObjGet", "ObjPut", "ObjDel")}
         self._server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(SERVICE, handlers),))
         if tls is not None:
             key, cert = (open(p, "rb").read() for p in tls)
@@ -179,6 +189,47 @@ class FleetLink:
             entry[1].set_result(reply)
         return _ser(True)
 
+    # ------------------------------------------------------------------ object service (the link as the parameter store)
+    def _obj_path(self, key: str, context: Any) -> Any:
+        import grpc
+        from pathlib import Path
+
+        p = (Path(self._spool_dir) / key).resolve()
+        if Path(self._spool_dir).resolve() not in p.parents:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, "key escapes the spool")
+        return p
+
+    def _objget(self, request: bytes, context: Any) -> bytes:
+        import grpc
+
+        self._auth(context)
+        req = _de(request)
+        p = self._obj_path(req["key"], context)
+        if not p.is_file():
+            context.abort(grpc.StatusCode.NOT_FOUND, f"no such object: {req['key']}")
+        with open(p, "rb") as f:
+            f.seek(int(req["offset"]))
+            data = f.read(int(req["n"]))
+        return _ser({"data": data, "size": p.stat().st_size})
+
+    def _objput(self, request: bytes, context: Any) -> bytes:
+        self._auth(context)
+        req = _de(request)
+        p = self._obj_path(req["key"], context)
+        part = p.with_name(p.name + ".part")
+        p.parent.mkdir(parents=True, exist_ok=True)
+        with open(part, "r+b" if int(req["offset"]) and part.exists() else "wb") as f:
+            f.seek(int(req["offset"]))
+            f.write(req["data"])
+        if req.get("last"):
+            os.replace(part, p)
+        return _ser(True)
+
+    def _objdel(self, request: bytes, context: Any) -> bytes:
+        self._auth(context)
+        self.spool.delete(_de(request)["key"])
+        return _ser(True)
+
     # ------------------------------------------------------------------ server API
     def next_msg_id(self) -> int:
         with self._lock:
@@ -206,14 +257,81 @@ class FleetLink:
         for s in self._slots.values():
             s.gone = True
         self._server.stop(grace=grace_s)
+        import shutil
+
+        from photon_b200.server import s3_utils
+
+        if s3_utils.get_link_store() is self.spool:
+            s3_utils.set_link_store(None)
+        shutil.rmtree(self._spool_dir, ignore_errors=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------- node side
+class LinkObjectStore:
+    """The fleet link's object service seen from a node (same interface as :mod:`photon_b200.utils.objstore`)."""
+
+    CHUNK = int(os.environ.get("PHOTON_LINK_CHUNK", 32 << 20))
+
+    def __init__(self, call: dict[str, Any], md: Any) -> None:
+        self._call, self._md = call, md
+
+    def _rpc(self, name: str, body: dict[str, Any]) -> Any:
+        return _de(self._call[name](_ser(body), metadata=self._md, timeout=3600.0))
+
+    def upload(self, key: str, path: Any) -> None:
+        size, off = os.path.getsize(path), 0
+        with open(path, "rb") as f:
+            while True:
+                data = f.read(self.CHUNK)
+                last = off + len(data) >= size
+                self._rpc("ObjPut", {"key": key, "offset": off, "data": data, "last": last})
+                off += len(data)
+                if last:
+                    return
+
+    def put(self, key: str, data: bytes) -> None:
+        for off in range(0, max(len(data), 1), self.CHUNK):
+            self._rpc("ObjPut", {"key": key, "offset": off, "data": data[off: off + self.CHUNK], "last": off + self.CHUNK >= len(data)})
+
+    def download(self, key: str, path: Any) -> Any:
+        from pathlib import Path
+
+        p = Path(path)
+        p.parent.mkdir(parents=True, exist_ok=True)
+        tmp = p.with_name(f"{p.name}.{os.getpid()}.part")
+        off = 0
+        with open(tmp, "wb") as f:
+            while True:
+                r = self._rpc("ObjGet", {"key": key, "offset": off, "n": self.CHUNK})
+                f.write(r["data"])
+                off += len(r["data"])
+                if off >= r["size"] or not r["data"]:
+                    break
+        os.replace(tmp, p)
+        return p
+
+    def get(self, key: str) -> bytes:
+        out, off = bytearray(), 0
+        while True:
+            r = self._rpc("ObjGet", {"key": key, "offset": off, "n": self.CHUNK})
+            out += r["data"]
+            off += len(r["data"])
+            if off >= r["size"] or not r["data"]:
+                return bytes(out)
+
+    def delete(self, key: str) -> None:
+        self._rpc("ObjDel", {"key": key})
+
+
 def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
     """Node → server parameters through the object store when there is one (key in the message instead of the arrays)."""
     from photon_b200.utils.objstore import remote_store_from_cfg
 
-    store = remote_store_from_cfg(cfg)
+    from photon_b200.server import s3_utils
+
+    store, kind, meta = remote_store_from_cfg(cfg), "s3", {"bucket": str(cfg["s3_comm_config"]["bucket_name"])}
+    if store is None:
+        store, kind, meta = s3_utils.get_link_store(), "link", {}
     if store is None:
         return reply
     import tempfile
@@ -226,7 +344,7 @@ def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
         key = f"{cfg['run_uuid']}/server/comm_stack/node-{node_id}/aggregate.npz"
         with tempfile.TemporaryDirectory() as td:
             store.upload(key, dump_model_parameters_to_file(Path(td) / "p.npz", list(reply.content["aggregate"].data)))
-        reply.content["aggregate"] = ParamHandle("s3", key, {"bucket": str(cfg["s3_comm_config"]["bucket_name"])})
+        reply.content["aggregate"] = ParamHandle(kind, key, dict(meta))
         return reply
     if reply.kind != "train" or not isinstance(reply.content, list):
         return reply
@@ -237,7 +355,7 @@ def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
             with tempfile.TemporaryDirectory() as td:
                 p = dump_model_parameters_to_file(Path(td) / "p.npz", list(res.parameters.data))
                 store.upload(key, p)
-            res.parameters = ParamHandle("s3", key, {"bucket": str(cfg["s3_comm_config"]["bucket_name"])})
+            res.parameters = ParamHandle(kind, key, dict(meta))
     return reply
 
 
@@ -255,7 +373,10 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
     md = (("x-photon-token", token),) if token else ()
     ident = lambda b: b  # noqa: E731
     call = {name: channel.unary_unary(f"/{SERVICE}/{name}", request_serializer=ident, response_deserializer=ident)
-            for name in ("Register", "Pull", "Push", "Beat")}
+            for name in ("Register", "Pull", "Push", "Beat", "ObjGet", "ObjPut", "ObjDel")}
+    from photon_b200.server import s3_utils
+
+    s3_utils.set_link_store(LinkObjectStore(call, md))       # "link" parameter handles resolve through this node's connection
     t0 = time.time()
     while True:     # the server may come up after its nodes (the reference starts the supernodes in any order)
         try:

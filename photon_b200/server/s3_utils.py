@@ -12,6 +12,7 @@ Here the message field is a ``ParamHandle`` and the places are
 ``file``      ``{root}/{folder_name}/{endpoint_id}/{file_name}.npz`` — a directory standing in for the bucket
 ``s3``        key of an npz object in the configured S3 bucket (``utils/objstore.py``); the way parameters reach nodes on
               OTHER hosts (``server/grpc_fleet.py``)
+``link``      key of an npz object in the fleet link's own object service (no S3 configured; the reference's Ray object store role)
 ============  ==========================================================================================
 
 ``replace_remote_with_parameters_in_recordset`` (sender) and ``replace_parameters_in_recordset_with_remote``
@@ -34,6 +35,16 @@ from photon_b200.utils.core import dump_model_parameters_to_file, load_model_par
 from photon_b200.utils.flat import FlatLayout
 
 _LIVE_SEGMENTS: dict[str, Any] = {}  # sender keeps its segments mapped until ``release_remote_parameters``
+_LINK_STORE: Any = None              # the fleet link's object service in this process (server: its spool, node: a LinkObjectStore)
+
+
+def set_link_store(store: Any) -> None:
+    global _LINK_STORE
+    _LINK_STORE = store
+
+
+def get_link_store() -> Any:
+    return _LINK_STORE
 
 
 def _comm_kind(comm_stack: Any) -> str:
@@ -62,7 +73,15 @@ def replace_remote_with_parameters_in_recordset(handle: ParamHandle, comm_stack:
                                                 folder_name: str = "comm_stack", file_name: str = "parameters",
                                                 num_attempts: int = 3, store: Any = None, bucket: str | None = None) -> ParamHandle:
     """SENDER: move an inline payload onto the side channel and return the locator handle. ``store`` (an object store) +
-    ``comm_stack="s3"``: the payload becomes the object ``{folder_name}/{endpoint_id}/{file_name}.npz`` of the bucket."""
+    ``comm_stack="s3"`` / ``"link"``: the payload becomes the object ``{folder_name}/{endpoint_id}/{file_name}.npz`` of the bucket /
+    of the fleet link's object service."""
+    if store is not None and comm_stack == "link" and handle.kind == "inline":
+        import tempfile
+
+        key = f"{folder_name}/{endpoint_id}/{file_name}.npz"
+        with tempfile.TemporaryDirectory() as td:
+            store.upload(key, dump_model_parameters_to_file(Path(td) / "p.npz", _as_arrays(handle.data, layout)))
+        return ParamHandle("link", key, {"endpoint_id": endpoint_id})
     if store is not None and comm_stack == "s3" and handle.kind == "inline":
         import tempfile
 
@@ -103,6 +122,13 @@ def replace_parameters_in_recordset_with_remote(handle: ParamHandle, *, layout: 
         shm, views = get_parameters_shm(str(handle.data), meta, copy=True)
         shm.close()
         arrays = [v.astype(np.float32, copy=False) for v in views]
+    elif handle.kind == "link":
+        import tempfile
+
+        if _LINK_STORE is None:
+            raise RuntimeError(f"parameters were parked in the fleet link's object service ({handle.data}) but this process has no link")
+        with tempfile.TemporaryDirectory() as td:
+            arrays = load_model_parameters_from_file(_LINK_STORE.download(str(handle.data), Path(td) / "p.npz"))
     elif handle.kind == "s3":
         import tempfile
 
@@ -149,6 +175,9 @@ def release_remote_parameters(handle: ParamHandle) -> None:
         unlink_quietly(str(handle.data))
     elif handle.kind == "file":
         Path(str(handle.data)).unlink(missing_ok=True)
+    elif handle.kind == "link":
+        if _LINK_STORE is not None:
+            _LINK_STORE.delete(str(handle.data))
     elif handle.kind == "s3":
         from photon_b200.utils.objstore import remote_store_from_cfg
 

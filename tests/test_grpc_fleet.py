@@ -56,7 +56,7 @@ def _reference_model(tmp_path):
         rt.close()
 
 
-@pytest.mark.parametrize("store", ["inline", "s3"])
+@pytest.mark.parametrize("store", ["link", "s3"])
 def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
     from photon_b200.server.fleet import NodeFleetRuntime
     from photon_b200.server_app import run_server
@@ -69,10 +69,19 @@ def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     port = _free_port()
+    if store == "link":
+        env["PHOTON_LINK_CHUNK"] = "4096"      # many chunks per object: exercises the chunked ObjGet / ObjPut paths
+        monkeypatch.setenv("PHOTON_LINK_CHUNK", "4096")
     procs = _spawn_nodes(2, port, env)          # nodes may start before the server: they keep trying to register
     cfg = _cfg(tmp_path / "remote", "run_uuid=fleet", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=2",
                "s3_comm_config.bucket_name=fleetbkt", *COMMON)
     rt = NodeFleetRuntime(cfg)
+    calls = {"get": 0, "put": 0}
+    from photon_b200.server import grpc_fleet
+
+    og, op = grpc_fleet.FleetLink._objget, grpc_fleet.FleetLink._objput
+    monkeypatch.setattr(grpc_fleet.FleetLink, "_objget", lambda self, r, c: (calls.__setitem__("get", calls["get"] + 1), og(self, r, c))[1])
+    monkeypatch.setattr(grpc_fleet.FleetLink, "_objput", lambda self, r, c: (calls.__setitem__("put", calls["put"] + 1), op(self, r, c))[1])
     try:
         h = run_server(cfg, runtime=rt)
         fit = h.metrics_distributed_fit
@@ -84,6 +93,8 @@ def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
     outs = _reap(procs)
     assert all(p.returncode == 0 for p in procs), outs
     assert torch.allclose(got, want, atol=1e-6), float((got - want).abs().max())
+    if store == "link":
+        assert calls["get"] > 20 and calls["put"] > 20, calls      # broadcast pulled and results pushed through the link, chunk by chunk
     if s3 is not None:
         keys = [k for m, k in s3.requests if m == "PUT"]
         assert any("fleetbkt/fleet/server/comm_stack/server/parameters.npz" in k for k in keys)          # broadcast went through the bucket
@@ -92,7 +103,7 @@ def test_remote_nodes_over_grpc_match_local_nodes(tmp_path, store, monkeypatch):
         s3.stop()
 
 
-@pytest.mark.parametrize("store", ["inline", "s3"])
+@pytest.mark.parametrize("store", ["link", "s3"])
 def test_node_pre_aggregation_ships_one_model_per_node(tmp_path, store, monkeypatch):
     """``photon.fleet.node_pre_aggregation``: four sampled clients on two remote nodes -> the train replies carry no parameters, each
     node answers ONE ``collect_aggregate`` query per round with its weighted mean, and the global model equals the per-client path."""
