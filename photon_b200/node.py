@@ -16,11 +16,26 @@ def main() -> None:
     ap.add_argument("--devices", default=None, help="comma-separated CUDA device indices for the workers (default: all visible)")
     ap.add_argument("--tls-ca", default=None, help="CA certificate: connect with TLS (env PHOTON_FLEET_TLS_CA)")
     ap.add_argument("--max-idle-s", type=float, default=None, help="leave when the server has been unreachable for this long")
+    ap.add_argument("--per-gpu", action="store_true",
+                    help="register ONE NODE PER GPU (each trains its own client) instead of one node whose GPUs collaborate on a client: "
+                         "the right shape for models that fit a GPU — a box then trains as many clients at once as it has GPUs "
+                         "(the server's photon.fleet.n_remote_nodes counts these nodes)")
     a = ap.parse_args()
     from photon_b200.server.grpc_fleet import serve_node
     from photon_b200.utils.core import get_n_cuda_devices
 
     devices = [int(x) for x in a.devices.split(",")] if a.devices else (list(range(get_n_cuda_devices())) or None)
+    if a.per_gpu and devices and len(devices) > 1:
+        import multiprocessing as mp
+
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=serve_node, args=(a.server,), kwargs=dict(n_workers=1, devices=[d], tls_ca=a.tls_ca, max_idle_s=a.max_idle_s),
+                             name=f"photon-node-gpu{d}") for d in devices]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        raise SystemExit(max((p.exitcode or 0) for p in procs))
     serve_node(a.server, n_workers=a.n_workers or (len(devices) if devices else 1), devices=devices, tls_ca=a.tls_ca, max_idle_s=a.max_idle_s)
 
 

@@ -7,4 +7,5 @@
 set -euo pipefail
 SERVER=${1:?usage: photon_node.sh SERVER_HOST:PORT}
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
-exec python -m photon_b200.node --server "$SERVER" ${N_WORKERS:+--n-workers "$N_WORKERS"} ${DEVICES:+--devices "$DEVICES"} ${FLEET_TLS_CA:+--tls-ca "$FLEET_TLS_CA"}
+# PER_GPU=1: one node per GPU (each trains its own client at the same time) instead of all GPUs collaborating on one client
+exec python -m photon_b200.node --server "$SERVER" ${N_WORKERS:+--n-workers "$N_WORKERS"} ${DEVICES:+--devices "$DEVICES"} ${FLEET_TLS_CA:+--tls-ca "$FLEET_TLS_CA"} ${PER_GPU:+--per-gpu}
