@@ -207,3 +207,24 @@ def test_node_lost_mid_round_leaves_the_rotation(tmp_path, monkeypatch):
     finally:
         rt.close()
     _reap(procs)
+
+
+def test_per_gpu_nodes_register_separately(tmp_path):
+    """``--per-gpu``: one process per listed device, each registering as its own node (on this CPU box the "devices" are just labels)."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    port = _free_port()
+    procs = _spawn_nodes(1, port, extra=("--per-gpu", "--devices", "0,1"))
+    cfg = _cfg(tmp_path, "run_uuid=pergpu", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=2",
+               "photon.fleet.connect_timeout_s=120", "fl.n_rounds=1", "fl.n_clients_per_round=2", "llm_config.save_folder=null",
+               "fl.strategy_name=fedavg", "photon.topology=nodes", "fl.eval_period=null")
+    rt = NodeFleetRuntime(cfg)
+    try:
+        h = run_server(cfg, runtime=rt)
+        assert sorted(rt.node_ids()) == [1000, 1001] and h.latest("server/n_failures") == 0
+        assert sorted(s.info["devices"] for s in rt.link._slots.values()) == [[0], [1]]
+    finally:
+        rt.close()
+    outs = _reap(procs)
+    assert procs[0].returncode == 0, outs
