@@ -3,8 +3,8 @@ from another run, cleanup (the role of ref photon/server/s3_utils.py:215-727,126
 
 "Bucket" = a directory (``{saving_path}/{bucket_name}``) that is the working copy; when an S3 endpoint is configured
 (``S3_ENDPOINT_URL`` / ``s3_comm_config.backend_kwargs.endpoint_url`` + ``AWS_*`` credentials → :mod:`photon_b200.utils.objstore`)
-every round is also uploaded under the same keys, rounds that exist only remotely are found and fetched on resume, and clean-up
-deletes both copies. The key layout is the reference's::
+every round is also uploaded under the same keys, rounds that exist only remotely are found and fetched on resume, clean-up
+deletes both copies, and client (trainer) checkpoints are mirrored by :class:`ClientCheckpointMirror`. The key layout is the reference's::
 
     {bucket}/{run_uuid}/server/{round}/state.bin
     {bucket}/{run_uuid}/server/{round}/current_server_parameters.npz      arr_i, sorted-name order
@@ -291,6 +291,67 @@ class CheckpointStore:
             shutil.rmtree(self.bucket / run_uuid, ignore_errors=True)
             if self.remote is not None:
                 self.remote.delete_prefix(f"{run_uuid}/")
+
+
+class ClientCheckpointMirror:
+    """Client (trainer) checkpoints through the object store, under the reference's keys ``{run_uuid}/client_{cid}/ep…-rank{r}.pt``
+    (ref: Composer saves to ``save_folder: s3://…`` through its RemoteUploaderDownloader). With nodes on several machines a client is
+    trained wherever there is a free node: its optimizer moments and data position follow it through the bucket instead of staying
+    on the disk of the machine that trained it last. ``pull`` runs before the mid-round resume / skip decision (which looks at the
+    local folder), ``push`` after the client's training."""
+
+    def __init__(self, remote: Any, run_uuid: str, keep: int = 1) -> None:
+        self.remote, self.run_uuid, self.keep = remote, str(run_uuid), max(1, int(keep))
+
+    def _prefix(self, cid: int | str) -> str:
+        return f"{self.run_uuid}/client_{cid}/"
+
+    @staticmethod
+    def _batches(name: str) -> int:
+        import re
+
+        m = re.search(r"-ba(\d+)-", name)
+        return int(m.group(1)) if m else -1
+
+    def pull(self, cid: int | str, folder: str | Path) -> list[str]:
+        """Fetch the newest ``keep`` checkpoints (every rank file of them) that are not in ``folder`` yet."""
+        names = [k.rsplit("/", 1)[1] for k in self.remote.list(self._prefix(cid)) if k.endswith(".pt")]
+        newest = sorted({self._batches(n) for n in names if self._batches(n) >= 0})[-self.keep:]
+        got = []
+        for n in names:
+            if self._batches(n) in newest and not (Path(folder) / n).exists():
+                self.remote.download(self._prefix(cid) + n, Path(folder) / n)
+                got.append(n)
+        return got
+
+    def push(self, cid: int | str, folder: str | Path) -> list[str]:
+        """Upload the checkpoints of ``folder`` the bucket does not have; drop remote ones older than the newest ``keep``."""
+        p = Path(folder)
+        if not p.is_dir():
+            return []
+        have = {k.rsplit("/", 1)[1] for k in self.remote.list(self._prefix(cid))}
+        sent = []
+        for f in sorted(p.glob("ep*-ba*-rank*.pt")):
+            if f.is_file() and not f.is_symlink() and f.name not in have:
+                self.remote.upload(self._prefix(cid) + f.name, f)
+                sent.append(f.name)
+        names = have | set(sent)
+        newest = sorted({self._batches(n) for n in names if self._batches(n) >= 0})[-self.keep:]
+        for n in names:
+            if n.endswith(".pt") and self._batches(n) not in newest:
+                self.remote.delete(self._prefix(cid) + n)
+        return sent
+
+
+def client_checkpoint_mirror(cfg: Any) -> ClientCheckpointMirror | None:
+    """The mirror of this run, or None when no object store is configured (client checkpoints then stay on the local disk)."""
+    from photon_b200.utils.objstore import remote_store_from_cfg
+
+    remote = remote_store_from_cfg(cfg)
+    if remote is None:
+        return None
+    keep = int((cfg.get("llm_config") or {}).get("save_num_checkpoints_to_keep", 1) or 1)
+    return ClientCheckpointMirror(remote, str(cfg["run_uuid"]), keep=keep if keep > 0 else 1)
 
 
 class _Foreign:

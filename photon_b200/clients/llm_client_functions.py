@@ -12,6 +12,7 @@ Timings reported as metrics keep the reference's names (``client/fit_init_time``
 from __future__ import annotations
 
 import time
+from pathlib import Path
 from typing import Any
 
 import torch
@@ -51,7 +52,23 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
         train_cfg = reconfigure_trainer(trainer, cfg, cid, log_name=f"_client_{cid}", split_eval=fc.split_eval,
                                         use_unigram_metrics=fc.use_unigram_metrics,
                                         allow_unigram_metrics_failures=fc.allow_unigram_metrics_failures)
-    # ---- per-client checkpoint policy: resume mid-round or skip an already finished round
+    # ---- per-client checkpoint policy: resume mid-round or skip an already finished round. With an object store configured the
+    # client's newest checkpoint is fetched first: it may have been written on another machine (cross-host node fleet)
+    from photon_b200.checkpoint.store import client_checkpoint_mirror
+
+    mirror = client_checkpoint_mirror(cfg) if (train_cfg.get("save_folder") and not fc.reset_checkpoint) else None
+    mirror_folder = str(Path(str(train_cfg["save_folder"])) / f"client_{cid}") if mirror is not None else None
+
+    def _ranks_together() -> None:      # the ranks of one client share the folder: nobody lists / uploads it half way
+        if trainer.world_size > 1 and torch.distributed.is_initialized():
+            torch.distributed.barrier(group=trainer.process_group)
+
+    if mirror is not None:
+        if trainer.rank == 0:
+            fetched = mirror.pull(cid, mirror_folder)
+            if fetched:
+                metrics["client/checkpoints_fetched"] = len(fetched)
+        _ranks_together()
     skip_iteration, load_set, _ = set_initial_config_from_fit_config(fc, train_cfg, cid)
     trainer.save_folder = train_cfg.get("save_folder")
     trainer.save_ignore_keys = list(train_cfg.get("save_ignore_keys") or [])   # reset_optimizer → client checkpoints carry no optimizer state
@@ -102,6 +119,10 @@ def llm_fit(trainer: Trainer | None, payload: Payload, fit_config: FitConfig | d
             trainer.fit(duration=f"{remaining}ba")
         steps_done = local_steps       # (no device synchronise here: the last batch of fit() read its loss back, which already waited)
     metrics["client/fit_time"] = _now() - t0
+    if mirror is not None:
+        _ranks_together()
+        if trainer.rank == 0:
+            metrics["client/checkpoints_uploaded"] = len(mirror.push(cid, mirror_folder))
 
     t0 = _now()
     out, n_samples, pm = post_process_client_result(trainer, initial, fc, cid, state, steps_done, as_ndarrays=as_ndarrays)

@@ -201,3 +201,43 @@ def test_reference_named_helpers(tmp_path, s3, monkeypatch):
             assert os.path.exists(f"/dev/shm/{h.data}")
             q.put(h)
     assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"gc_test_{os.getpid()}_")]
+
+
+def test_client_checkpoints_follow_the_client_through_the_bucket(tmp_path, s3, monkeypatch):
+    """Round 1 on "machine A", round 2 on "machine B" (another disk, same bucket), ``fl.reset_optimizer=false``: B fetches every
+    client's newest trainer checkpoint before the resume decision, so the optimizer moments and the data position continue — the
+    result equals a run that stayed on one machine, and differs from one that lost the client state."""
+    import torch
+
+    from photon_b200.federation import FederationRuntime
+    from photon_b200.server_app import run_server
+    from test_federation_cpu import _cfg
+
+    for k, v in {"S3_ENDPOINT_URL": s3.endpoint, "AWS_ACCESS_KEY_ID": ACCESS, "AWS_SECRET_ACCESS_KEY": SECRET, "AWS_DEFAULT_REGION": REGION}.items():
+        monkeypatch.setenv(k, v)
+    common = ["photon.checkpoint=true", "photon.async_checkpoint=false", "fl.eval_period=null", "fl.reset_optimizer=false", "fl.strategy_name=fedavg",
+              "s3_comm_config.bucket_name=ckbkt", "llm_config.optimizer.name=decoupled_adamw", "llm_config.optimizer.lr=1.0e-3",
+              "fl.n_total_clients=2", "fl.n_clients_per_round=2"]      # the same two clients every round
+
+    def run(root, run_uuid, rounds, resume):
+        cfg = _cfg(root, f"run_uuid={run_uuid}", f"fl.n_rounds={rounds}", *(["photon.resume_round=-1"] if resume else []), *common)
+        rt = FederationRuntime(cfg, device=torch.device("cpu"), rank=0, world_size=1)
+        try:
+            run_server(cfg, runtime=rt)
+            return rt.round_backend.global_params().clone()
+        finally:
+            rt.close()
+
+    stay = run(tmp_path / "one", "stay", 2, False)                      # the whole run on one machine
+    run(tmp_path / "A", "move", 1, False)                                # round 1 on A ...
+    assert any(k.startswith("ckbkt/move/client_0/ep") and k.endswith("-rank0.pt") for k in s3.objects), sorted(s3.objects)[:8]
+    moved = run(tmp_path / "B", "move", 2, True)                         # ... round 2 on B: empty disk, same bucket
+    assert (tmp_path / "B" / "clients" / "client_0").is_dir() and list((tmp_path / "B" / "clients" / "client_0").glob("ep*-rank0.pt"))
+    assert torch.allclose(moved, stay, atol=1e-6), float((moved - stay).abs().max())
+    for k in [k for k in s3.objects if "/client_" in k]:                 # the same move with the client checkpoints gone: a different model
+        del s3.objects[k]
+    run(tmp_path / "A2", "lost", 1, False)
+    for k in [k for k in s3.objects if k.startswith("ckbkt/lost/client_")]:
+        del s3.objects[k]
+    lost = run(tmp_path / "B2", "lost", 2, True)
+    assert not torch.allclose(lost, stay, atol=1e-6)
