@@ -101,11 +101,24 @@ class NodeFleetRuntime(FederationRuntime):
         if not self.apps:
             raise ValueError("photon.topology=nodes needs photon.n_nodes >= 1 or photon.fleet.n_remote_nodes >= 1")
         self.n_nodes = len(self.apps)        # what the round loop waits for / reports: in-process + remote
-        self._pool = ThreadPoolExecutor(max_workers=len(self.apps), thread_name_prefix="node")
+        self._pool = ThreadPoolExecutor(max_workers=max(64, len(self.apps)), thread_name_prefix="node")   # room for nodes that join later
         wait_for_nodes_to_connect(len(self.apps), self.node_ids, poll_s=0.05, timeout_s=300.0)
 
     def node_ids(self) -> list[int]:
+        self._admit_new_nodes()
         return [a.node_id for a in self.apps if a.alive()]
+
+    def _admit_new_nodes(self) -> None:
+        """Machines may join a running federation (ref: Flower's ``get_node_ids`` is whoever is connected NOW): a node that
+        registered with the link since the last look gets a handle here; it receives the next broadcast and enters the work queue
+        of the next round."""
+        if self.link is None:
+            return
+        known = {a.node_id for a in self.apps}
+        for node in self.link.nodes():
+            if node.node_id not in known:
+                self.apps.append(node)
+                print(f"[fleet] node {node.node_id} joined the federation", flush=True)
 
     # --------------------------------------------------------------------- broadcast (R2)
     def broadcast_to_nodes(self) -> dict[str, Any]:

@@ -228,3 +228,44 @@ def test_per_gpu_nodes_register_separately(tmp_path):
         rt.close()
     outs = _reap(procs)
     assert procs[0].returncode == 0, outs
+
+
+def test_a_machine_can_join_a_running_federation(tmp_path):
+    """The server waits for ONE remote node (``n_remote_nodes=1``); a second machine that connects later — here: whichever of two
+    registers second — is admitted at the next health check and is part of the following rounds."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    port = _free_port()
+    cfg = _cfg(tmp_path, "run_uuid=join", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=1",
+               "photon.fleet.connect_timeout_s=120", "fl.n_rounds=6", "fl.n_clients_per_round=2", "llm_config.save_folder=null",
+               "fl.strategy_name=fedavg", "photon.topology=nodes", "fl.eval_period=null")
+    rt = NodeFleetRuntime(cfg)
+    procs = _spawn_nodes(1, port)
+
+    def late():
+        t0 = time.time()
+        while time.time() - t0 < 120 and (rt.link is None or not rt.link._slots):
+            time.sleep(0.02)
+        procs.extend(_spawn_nodes(1, port))          # the first node is in (the server is past its wait): a second machine shows up
+
+    try:
+        threading.Thread(target=late, daemon=True).start()
+        orig = rt.node_ids
+
+        def patient_node_ids():                       # keep the test independent of how fast a node process starts on this box
+            if rt.link is not None and len(procs) == 2:
+                t0 = time.time()
+                while len(rt.link._slots) < 2 and time.time() - t0 < 90:
+                    time.sleep(0.05)
+            return orig()
+
+        rt.node_ids = patient_node_ids
+        h = run_server(cfg, runtime=rt)
+        n_nodes = [v for _, v in h.metrics_distributed_fit["server/n_nodes"]]
+        assert n_nodes[-1] == 2 and rt.n_remote_nodes == 1, n_nodes
+        assert all(v == 0 for _, v in h.metrics_distributed_fit["server/n_failures"])
+    finally:
+        rt.close()
+    outs = _reap(procs)
+    assert all(p.returncode == 0 for p in procs), outs
