@@ -134,6 +134,12 @@ class FleetLink:
             self.port = self._server.add_insecure_port(address)
         if not self.port:
             raise RuntimeError(f"fleet link could not bind {address}")
+        host = address.rsplit(":", 1)[0]
+        if not token and host not in ("127.0.0.1", "localhost", "[::1]"):
+            # messages are pickles: whoever can reach the port can run code in this process. Loopback needs nothing; anything else
+            # should carry the shared token (checked before a single byte is unpickled) and, across sites, TLS.
+            print(f"[fleet] WARNING: the link listens on {address} without PHOTON_FLEET_TOKEN — any host that can reach it is trusted",
+                  flush=True)
         self._server.start()
 
     # ------------------------------------------------------------------ rpc handlers
@@ -209,7 +215,7 @@ class FleetLink:
             context.abort(grpc.StatusCode.NOT_FOUND, f"no such object: {req['key']}")
         with open(p, "rb") as f:
             f.seek(int(req["offset"]))
-            data = f.read(int(req["n"]))
+            data = f.read(min(int(req["n"]), 256 << 20))      # a frame stays far below gRPC's 2 GiB limit whatever the caller asks
         return _ser({"data": data, "size": p.stat().st_size})
 
     def _objput(self, request: bytes, context: Any) -> bytes:
