@@ -32,6 +32,8 @@ PICKS = [
     ("comm.cu.o", r"fed_round_kernel", "fed_round"),
     ("comm.cu.o", r"ddp_allreduce_kernel", "ddp_allreduce"),
     ("comm.cu.o", r"ddp_zero_step_kernel", "ddp_zero_step"),
+    ("comm.cu.o", r"zero3_reduce_kernel", "zero3_reduce"),
+    ("attention_tcgen05.cu.o", r"attn_fwd_kernel<64, 2, false, 16>", "attention_fwd_d64_packed_f32x2"),
     ("fp8_ops.cu.o", r"ln_fwd_q8_kernel<3>", "layernorm_fwd_q8_d768"),
     ("fp8_ops.cu.o", r"colsum_quant_kernel<1>", "colsum_quant_e5m2"),
     ("fused_ops.cu.o", r"optim_kernel", "fused_optimizer"),
