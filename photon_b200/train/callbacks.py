@@ -107,25 +107,30 @@ class JSONLLogger(Logger):
 
 
 class TensorBoardLogger(Logger):
+    """Scalars as TensorBoard event files: through ``torch.utils.tensorboard`` when the tensorboard package is there, otherwise through
+    the own writer of the same on-disk format (``utils/tbevents.py``) — either way ``tensorboard --logdir`` reads the run."""
+
     def __init__(self, log_dir: str | Path, flush_interval: int = 10) -> None:
         try:
             from torch.utils.tensorboard import SummaryWriter
 
             self._w: Any = SummaryWriter(str(log_dir), flush_secs=max(1, int(flush_interval)))
-            self._fallback: JSONLLogger | None = None
+            self._native: Any = None
         except Exception:  # noqa: BLE001 - tensorboard missing in this image
+            from photon_b200.utils.tbevents import EventFileWriter
+
             self._w = None
-            self._fallback = JSONLLogger(Path(log_dir) / "scalars.jsonl", flush_interval)
+            self._native = EventFileWriter(log_dir, flush_secs=max(1, int(flush_interval)))
 
     def log_metrics(self, metrics: dict[str, float], step: int) -> None:
         if self._w is not None:
             for k, v in metrics.items():
                 self._w.add_scalar(k, float(v), step)
-        elif self._fallback is not None:
-            self._fallback.log_metrics(metrics, step)
+        else:
+            self._native.add_scalars({k: float(v) for k, v in metrics.items()}, step)
 
     def close(self) -> None:
-        (self._w or self._fallback).close()  # type: ignore[union-attr]
+        (self._w or self._native).close()
 
 
 class WandBLogger(Logger):

@@ -290,3 +290,60 @@ def test_load_weights_only_strict_names_and_train_subset(tmp_path):
     assert ts.batch == 7 and ts.epoch == 2 and ts.batch_in_epoch == 1                 # epochs of 3 batches: 3 + 3 + 1
     for t in (a, b, c, d):
         t.close()
+
+
+def test_tensorboard_event_files_without_the_tensorboard_package(tmp_path):
+    """The own event-file writer: CRC-32C against the standard check value, TFRecord framing, and the hand-encoded ``Event`` messages
+    decoded by an INDEPENDENT protobuf runtime (dynamic descriptors of the public tensorboard schema); the logger falls back to it."""
+    from photon_b200.train.callbacks import TensorBoardLogger
+    from photon_b200.utils.tbevents import EventFileWriter, crc32c, read_events
+
+    assert crc32c(b"123456789") == 0xE3069283 and crc32c(b"") == 0
+    w = EventFileWriter(tmp_path / "tb")
+    w.add_scalars({"loss/train/total": 2.5, "lr": 6e-4}, 7)
+    w.add_scalar("neg", -1.0, 1 << 40)
+    w.close()
+    ev = read_events(w.path)
+    assert ev[0]["file_version"] == "brain.Event:2" and ev[1]["step"] == 7 and ev[1]["scalars"]["loss/train/total"] == 2.5
+    assert abs(ev[1]["scalars"]["lr"] - 6e-4) < 1e-9 and ev[2] == {**ev[2], "step": 1 << 40, "scalars": {"neg": -1.0}}
+    raw = w.path.read_bytes()
+    bad = raw[:20] + bytes([raw[20] ^ 1]) + raw[21:]
+    (tmp_path / "bad").write_bytes(bad)
+    import pytest as _pytest
+    with _pytest.raises(ValueError, match="CRC"):
+        read_events(tmp_path / "bad")
+    # independent decode: google.protobuf with descriptors built from the published schema
+    pb = _pytest.importorskip("google.protobuf")
+    del pb
+    import struct
+
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    fd = descriptor_pb2.FileDescriptorProto(name="tb_event_test.proto", package="tbtest", syntax="proto3")
+    val = fd.message_type.add(name="Value")
+    val.field.add(name="tag", number=1, type=9, label=1)
+    val.field.add(name="simple_value", number=2, type=2, label=1)
+    summ = fd.message_type.add(name="Summary")
+    summ.field.add(name="value", number=1, type=11, label=3, type_name=".tbtest.Value")
+    evd = fd.message_type.add(name="Event")
+    evd.field.add(name="wall_time", number=1, type=1, label=1)
+    evd.field.add(name="step", number=2, type=3, label=1)
+    evd.field.add(name="file_version", number=3, type=9, label=1)
+    evd.field.add(name="summary", number=5, type=11, label=1, type_name=".tbtest.Summary")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    Event = message_factory.GetMessageClass(pool.FindMessageTypeByName("tbtest.Event"))
+    msgs, i = [], 0
+    while i < len(raw):
+        (n,) = struct.unpack("<Q", raw[i: i + 8])
+        m = Event()
+        m.ParseFromString(raw[i + 12: i + 12 + n])
+        msgs.append(m)
+        i += 16 + n
+    assert msgs[0].file_version == "brain.Event:2" and msgs[1].step == 7 and msgs[2].step == 1 << 40
+    assert {v.tag: round(v.simple_value, 6) for v in msgs[1].summary.value} == {"loss/train/total": 2.5, "lr": 0.0006}
+    lg = TensorBoardLogger(tmp_path / "tb2", 1)
+    lg.log_metrics({"a": 1.0}, 3)
+    lg.close()
+    files = list((tmp_path / "tb2").glob("events.out.tfevents.*"))
+    assert files and any(e["scalars"].get("a") == 1.0 and e["step"] == 3 for e in read_events(files[0]))
