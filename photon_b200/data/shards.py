@@ -230,18 +230,24 @@ class MDSReader:
             if kind != "ndarray":
                 raise ValueError(f"column {name!r} has encoding {enc!r}; expected ndarray:<dtype> or bytes")
             dtype = np.dtype(rest.split(":")[0] or "int32")
-            # shape header: 1 byte (rank / width code) + rank × {1,2,4,8}-byte dims; rank is 1 for token rows
-            for width in (0, 1, 2, 4, 8):
-                h = 0 if width == 0 else 1 + width
-                body = ln - h
-                if body < 0 or body % dtype.itemsize:
-                    continue
-                n = body // dtype.itemsize
-                if width and int.from_bytes(payload[1:h], "little") != n:
-                    continue
-                if width == 0 and ":" not in rest:      # no explicit shape in the encoding → a header must be present
-                    continue
-                return np.frombuffer(payload, dtype, n, offset=h).astype(np.int32, copy=False)
+            # dynamic-shape header of mosaicml-streaming's NDArray encoding: ``uint8 ndim | uint8 code of the dims' integer type |
+            # ndim dims`` (dims in the narrowest unsigned type that holds them: 2048 tokens -> uint16), then the C-order data. Token rows
+            # have ndim 1. A one-byte prefix (rank and width packed, or no type code) is accepted as well; either way the dims must
+            # equal the element count the remaining bytes hold, so a mis-parse cannot slip through.
+            for prefix in (2, 1):
+                for width in (1, 2, 4, 8):
+                    h = prefix + width
+                    body = ln - h
+                    if body <= 0 or body % dtype.itemsize:
+                        continue
+                    n = body // dtype.itemsize
+                    if int.from_bytes(payload[prefix:h], "little") != n:
+                        continue
+                    if prefix == 2 and (payload[0] != 1 or payload[1] != {1: 0, 2: 2, 4: 4, 8: 6}[width]):   # ndim 1; uint8/16/32/64 codes
+                        continue
+                    return np.frombuffer(payload, dtype, n, offset=h).astype(np.int32, copy=False)
+            if ":" in rest and ln % dtype.itemsize == 0:      # static shape in the encoding string: no header at all
+                return np.frombuffer(payload, dtype, ln // dtype.itemsize).astype(np.int32, copy=False)
             raise ValueError(f"cannot locate the token payload in a {ln}-byte {enc} column")
         raise KeyError(f"column {self.column!r} not in {names}")
 
@@ -252,6 +258,88 @@ class MDSReader:
         blob, offsets = self._load(s)
         j = idx - int(self._starts[s])
         return self._decode(blob[int(offsets[j]):int(offsets[j + 1])], self._meta[s])
+
+
+class MDSWriter:
+    """Token shards in mosaicml-streaming's MDS layout (``columns={"tokens": "ndarray:int32"}``, optional zstd) — what the reference's
+    converter writes (ref: photon/dataset/convert_dataset_hf.py:323-327) — so a corpus converted HERE can be read by the reference's
+    loaders too. Same context-manager interface as :class:`ShardWriter`.
+
+    A raw shard is ``uint32 n | uint32 offsets[n+1] | json config | samples`` (absolute offsets); a sample is ``uint32 size`` of every
+    variable-size column followed by the payloads; the ``ndarray:int32`` payload is ``uint8 ndim | uint8 code of the dims' integer
+    type | dims | C-order data`` (codes: uint8 0, uint16 2, uint32 4, uint64 6). ``index.json`` (version 2) lists the shards with
+    their raw / compressed basenames and byte counts. Written from the format description (no mosaicml-streaming in this
+    environment); :class:`MDSReader` reads it back."""
+
+    def __init__(self, out_dir: str | os.PathLike, seq_len: int, shard_samples: int | None = None, compression: str | None = "zstd",
+                 size_limit: int = 1 << 26) -> None:
+        if compression not in (None, "zstd"):
+            raise ValueError("MDS shards are written raw or zstd-compressed")
+        if compression == "zstd" and _zstd() is None:
+            raise RuntimeError("zstd shards need pyarrow's codec (no zstandard module in this image)")
+        self.out = Path(out_dir)
+        self.out.mkdir(parents=True, exist_ok=True)
+        self.seq_len, self.compression, self.size_limit = int(seq_len), compression, int(size_limit)
+        self.shard_samples = int(shard_samples) if shard_samples else None
+        self._samples: list[bytes] = []
+        self._bytes = 0
+        self._shards: list[dict[str, Any]] = []
+        self._config = {"version": 2, "format": "mds", "compression": compression, "hashes": [], "size_limit": self.size_limit,
+                        "column_names": ["tokens"], "column_encodings": ["ndarray:int32"], "column_sizes": [None]}
+
+    @staticmethod
+    def _payload(a: np.ndarray) -> bytes:
+        n = int(a.shape[0])
+        code, dt = (0, np.uint8) if n < 1 << 8 else (2, np.uint16) if n < 1 << 16 else (4, np.uint32) if n < 1 << 32 else (6, np.uint64)
+        return bytes([1, code]) + np.array([n], dt).tobytes() + a.tobytes()
+
+    def write(self, tokens: np.ndarray) -> None:
+        a = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32).reshape(-1))
+        if a.size != self.seq_len:
+            raise ValueError(f"sample has {a.size} tokens, expected {self.seq_len}")
+        body = self._payload(a)
+        sample = np.uint32(len(body)).tobytes() + body
+        full = (self.shard_samples is not None and len(self._samples) >= self.shard_samples) or \
+               (self._samples and self._bytes + len(sample) + 4 * (len(self._samples) + 3) > self.size_limit)
+        if full:
+            self._flush()
+        self._samples.append(sample)
+        self._bytes += len(sample)
+
+    def write_many(self, rows: Iterable[np.ndarray]) -> None:
+        for r in rows:
+            self.write(r)
+
+    def _flush(self) -> None:
+        if not self._samples:
+            return
+        cfg = json.dumps(self._config, sort_keys=True).encode()
+        n = len(self._samples)
+        offsets = np.concatenate([[0], np.cumsum([len(x) for x in self._samples])]).astype(np.uint32)
+        offsets += np.uint32(4 + 4 * (n + 1) + len(cfg))
+        raw = np.uint32(n).tobytes() + offsets.tobytes() + cfg + b"".join(self._samples)
+        base = f"shard.{len(self._shards):05d}.mds"
+        entry: dict[str, Any] = {**self._config, "samples": n, "raw_data": {"basename": base, "bytes": len(raw), "hashes": {}}, "zip_data": None}
+        if self.compression == "zstd":
+            z = _zstd().compress(raw, asbytes=True)
+            (self.out / (base + ".zstd")).write_bytes(z)
+            entry["zip_data"] = {"basename": base + ".zstd", "bytes": len(z), "hashes": {}}
+        else:
+            (self.out / base).write_bytes(raw)
+        self._shards.append(entry)
+        self._samples, self._bytes = [], 0
+
+    def finish(self) -> dict[str, Any]:
+        self._flush()
+        index = {"version": 2, "shards": self._shards}
+        (self.out / INDEX_NAME).write_text(json.dumps(index, sort_keys=True))
+        return index
+
+    def __enter__(self) -> "MDSWriter":
+        return self
+
+    def __exit__(self, *exc: Any) -> None:
+        self.finish()
 
 
 def open_shard_dir(directory: str | os.PathLike, validate_hash: bool = False) -> Any:

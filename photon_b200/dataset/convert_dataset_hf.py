@@ -17,14 +17,14 @@ import argparse
 from pathlib import Path
 from typing import Any
 
-from photon_b200.data.shards import ShardWriter
+from photon_b200.data.shards import MDSWriter, ShardWriter
 from photon_b200.dataset.constants import DATASETS_CONSTANTS, resolve_split
 from photon_b200.dataset.utils import UnigramCounter, build_tokenizer, concat_tokens, iter_text_source
 
 
 def convert_split(docs: Any, tokenizer: Any, out_dirs: list[Path], seq_len: int, total_samples: int | None,
                   compression: str | None = "zlib", shard_samples: int = 8192, eos_text: str = "<|endoftext|>",
-                  bos_text: str = "", no_wrap: bool = False, only_client: int | None = None) -> list[int]:
+                  bos_text: str = "", no_wrap: bool = False, only_client: int | None = None, fmt: str = "photon") -> list[int]:
     """Write samples into ``len(out_dirs)`` contiguous partitions. When ``total_samples`` is unknown the
     samples are first counted into memory-light temporary order: we buffer and cut at the end. ``only_client`` writes
     just that partition (its samples are the same ones a full conversion would give it)."""
@@ -44,7 +44,9 @@ def convert_split(docs: Any, tokenizer: Any, out_dirs: list[Path], seq_len: int,
             continue
         counter = UnigramCounter()
         n = 0
-        with ShardWriter(d, seq_len=seq_len, shard_samples=shard_samples, compression=compression) as w:
+        writer = (MDSWriter(d, seq_len=seq_len, compression="zstd" if compression == "zstd" else None) if fmt == "mds"
+                  else ShardWriter(d, seq_len=seq_len, shard_samples=shard_samples, compression=compression))
+        with writer as w:
             for _ in range(quota):
                 try:
                     s = next(it)
@@ -80,6 +82,9 @@ def parse_args(argv: list[str] | None = None) -> argparse.Namespace:
     ap.add_argument("--no_wrap", action="store_true", help="drop the tail of a document that does not fill the current sample instead of carrying it over")
     ap.add_argument("--num_workers", type=int, default=None, help="accepted for flag parity; conversion is a single streaming pass")
     ap.add_argument("--compression", default="zlib", choices=["zlib", "zstd", "none"])
+    ap.add_argument("--format", default="photon", choices=["photon", "mds"],
+                    help="photon = this package's shard format; mds = mosaicml-streaming's layout (what the reference writes and reads; "
+                         "raw or zstd)")
     args = ap.parse_args(argv)
     if args.name and f"c4_{args.name}" in DATASETS_CONSTANTS and args.dataset == "c4_en":
         args.dataset = f"c4_{args.name}"
@@ -111,7 +116,8 @@ def main(argv: list[str] | None = None) -> dict[str, list[int]]:
         docs = iter_text_source(src, split=sc.split, limit=sc.truncated_samples)
         dirs = [root / f"client_{i}" / fs for i in range(args.num_clients)]
         out[fs] = convert_split(docs, tok, dirs, args.concat_tokens, None, None if args.compression == "none" else args.compression,
-                                eos_text=args.eos_text, bos_text=args.bos_text or "", no_wrap=args.no_wrap, only_client=args.client)
+                                eos_text=args.eos_text, bos_text=args.bos_text or "", no_wrap=args.no_wrap, only_client=args.client,
+                                fmt=args.format)
         print(f"[convert] {args.dataset}/{fs}: {out[fs]} samples per client -> {root}")
     tok.save_pretrained(str(Path(args.out_root) / "tokenizer"))
     if args.remote_path:

@@ -1,6 +1,7 @@
 import json
 
 import numpy as np
+import pytest
 import yaml
 
 from photon_b200.data.shards import ShardReader
@@ -75,3 +76,43 @@ def test_stream_partitioner(tmp_path):
     (tmp_path / "in.yaml").write_text(yaml.safe_dump(entries))
     partition_streams(tmp_path / "in.yaml", tmp_path / "out.yaml", 4)
     assert len(yaml.safe_load((tmp_path / "out.yaml").read_text())) == 4
+
+
+@pytest.mark.parametrize("compression", ["zstd", "none"])
+def test_converter_writes_mds_directories_the_loader_reads_back(tmp_path, compression):
+    """``--format mds``: the converter writes mosaicml-streaming's layout (index v2, shard header / offsets / config / samples, the
+    two-byte dynamic-shape header of ``ndarray:int32``); the MDS reader and the streaming loader read the same tokens as from the
+    default shard format."""
+    import json
+
+    from photon_b200.data.shards import MDSReader, MDSWriter, open_shard_dir
+
+    args = ["--dataset", "c4_en", "--splits", "train_small", "--source", "synthetic://60", "--num_clients", "2", "--concat_tokens", "300",
+            "--tokenizer", "byte", "--compression", compression]
+    a = convert_main(args + ["--out_root", str(tmp_path / "own")])
+    b = convert_main(args + ["--out_root", str(tmp_path / "mds"), "--format", "mds"])
+    assert a == b and a["train_small"][0] > 0
+    for c in (0, 1):
+        own = open_shard_dir(tmp_path / "own" / "c2" / "en" / f"client_{c}" / "train_small")
+        mds = open_shard_dir(tmp_path / "mds" / "c2" / "en" / f"client_{c}" / "train_small")
+        assert isinstance(mds, MDSReader) and len(mds) == len(own) == a["train_small"][c] and mds.seq_len == 300
+        assert all(np.array_equal(mds[i], own[i]) for i in range(len(own)))
+    d = tmp_path / "mds" / "c2" / "en" / "client_0" / "train_small"
+    idx = json.loads((d / "index.json").read_text())
+    sh = idx["shards"][0]
+    assert idx["version"] == 2 and sh["format"] == "mds" and sh["column_encodings"] == ["ndarray:int32"] and sh["column_sizes"] == [None]
+    assert (sh["compression"], sh["zip_data"] is None) == (("zstd", False) if compression == "zstd" else (None, True))
+    # byte-level: 300 tokens need a uint16 dim -> header 01 02 2c 01, then 1200 data bytes
+    w = MDSWriter(tmp_path / "one", seq_len=300, compression=None)
+    w.write(np.arange(300, dtype=np.int32))
+    w.finish()
+    raw = (tmp_path / "one" / "shard.00000.mds").read_bytes()
+    n, first, end = np.frombuffer(raw, np.uint32, 3)
+    assert n == 1 and end == len(raw) and raw[first: first + 8] == np.uint32(1204).tobytes() + bytes([1, 2, 0x2C, 0x01])
+    # several shards when the size limit is small; sample order survives
+    w = MDSWriter(tmp_path / "many", seq_len=16, compression=None, size_limit=400)
+    rows = [np.full(16, i, np.int32) for i in range(20)]
+    w.write_many(rows)
+    assert len(w.finish()["shards"]) > 1
+    r = MDSReader(tmp_path / "many")
+    assert len(r) == 20 and all(int(r[i][0]) == i for i in range(20))
