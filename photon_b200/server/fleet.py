@@ -194,7 +194,9 @@ class NodeFleetRuntime(FederationRuntime):
         t0 = time.time()
         with tracer().span("fit_clients", cat="server", server_round=server_round):
             for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps if a.alive()], dispatch, poll, poll_s=0.01,
-                                                     is_alive=lambda n: by_id[n].alive()):
+                                                     # a REMOTE node that stopped polling leaves the rotation (its client is re-queued);
+                                                     # an in-process node manager repairs its own workers and reports what it could not do
+                                                     is_alive=lambda n: by_id[n].alive() if getattr(by_id[n], "remote", False) else True):
                 for res in reply.content or [FitRes(Status(Code.FAILED, reply.error or "empty reply"), None, 0, {}, cid)]:
                     if res.status.code == Code.OK and res.parameters is not None and res.parameters.kind == "deferred":
                         held.setdefault(_node, []).append(len(results))
