@@ -4,7 +4,7 @@ The reference reaches S3 through Composer's ``RemoteUploaderDownloader`` (boto3 
 812-864, configured by ``s3_comm_config`` + the ``S3_ENDPOINT_URL`` / ``AWS_*`` environment, ref: photon/conf/base_schema.py:265-277).
 boto3 is not a dependency here: :class:`S3ObjectStore` speaks the S3 REST API directly (AWS Signature Version 4 over ``http.client``,
 path-style addressing so MinIO / Ceph / AWS all work): PUT / GET / HEAD / DELETE object, ListObjectsV2 with continuation, multipart
-upload for large files (one part in memory at a time, each part retried on its own), ranged streaming downloads, bounded retries
+upload for large files (parts in flight in parallel, each retried on its own), parallel ranged downloads, bounded retries
 with back-off on 5xx / connection errors. :class:`DirObjectStore` is the same interface over a directory (the offline default).
 
 Keys are ``/``-separated strings relative to the store (bucket + optional prefix).
@@ -153,7 +153,7 @@ class S3ObjectStore(ObjectStore):
 
     def __init__(self, bucket: str, *, endpoint_url: str, access_key: str, secret_key: str, region: str = "us-east-1", prefix: str = "",
                  num_attempts: int = 3, connect_timeout: float = 60.0, read_timeout: float = 3600.0, session_token: str | None = None,
-                 part_size: int = 64 << 20, multipart_threshold: int = 128 << 20) -> None:
+                 part_size: int = 64 << 20, multipart_threshold: int = 128 << 20, max_concurrency: int = 8) -> None:
         u = urllib.parse.urlparse(endpoint_url)
         if u.scheme not in ("http", "https") or not u.netloc:
             raise ValueError(f"endpoint_url must be http(s)://host[:port], got {endpoint_url!r}")
@@ -163,6 +163,7 @@ class S3ObjectStore(ObjectStore):
         self.num_attempts = max(1, int(num_attempts))
         self.connect_timeout, self.read_timeout = float(connect_timeout), float(read_timeout)
         self.part_size, self.multipart_threshold = int(part_size), int(multipart_threshold)
+        self.max_concurrency = max(1, int(max_concurrency))     # parts of one large object in flight (upload and ranged download)
 
     # -- plumbing ------------------------------------------------------------------------------------------------
     def _key(self, key: str) -> str:
@@ -280,17 +281,22 @@ class S3ObjectStore(ObjectStore):
         upload_id = root.findtext(f"{ns}UploadId")
         if not upload_id:
             raise ObjectStoreError(f"multipart upload of {key}: no UploadId in the response")
-        etags: list[str] = []
-        try:
+        n_parts = -(-size // self.part_size)
+
+        def send(i: int) -> str:          # part i: its own file handle (positioned reads), its own retries inside _request
             with open(p, "rb") as f:
-                n = 1
-                while True:
-                    part = f.read(self.part_size)
-                    if not part:
-                        break
-                    _, rh, _ = self._request("PUT", key, query={"partNumber": str(n), "uploadId": upload_id}, body=part)
-                    etags.append(rh.get("etag", ""))
-                    n += 1
+                f.seek(i * self.part_size)
+                part = f.read(self.part_size)
+            return self._request("PUT", key, query={"partNumber": str(i + 1), "uploadId": upload_id}, body=part)[1].get("etag", "")
+
+        try:
+            if self.max_concurrency > 1 and n_parts > 1:
+                from concurrent.futures import ThreadPoolExecutor
+
+                with ThreadPoolExecutor(max_workers=min(self.max_concurrency, n_parts), thread_name_prefix="s3-part") as ex:
+                    etags = list(ex.map(send, range(n_parts)))
+            else:
+                etags = [send(i) for i in range(n_parts)]
             body = ("<CompleteMultipartUpload>" + "".join(f"<Part><PartNumber>{i + 1}</PartNumber><ETag>{e}</ETag></Part>"
                                                            for i, e in enumerate(etags)) + "</CompleteMultipartUpload>").encode()
             self._request("POST", key, query={"uploadId": upload_id}, body=body)
@@ -301,13 +307,41 @@ class S3ObjectStore(ObjectStore):
                 pass
             raise
 
+    def size(self, key: str) -> int:
+        try:
+            return int(self._request("HEAD", key)[1].get("content-length", "0"))
+        except ObjectStoreError as e:
+            if e.status == 404:
+                raise ObjectStoreError(f"no such key: {key}", 404) from None
+            raise
+
     def download(self, key: str, path: str | os.PathLike) -> Path:
+        """Stream the object to ``path``; objects above the multipart threshold come as parallel ranged GETs written at their offsets."""
         p = Path(path)
         p.parent.mkdir(parents=True, exist_ok=True)
         tmp = p.with_name(f"{p.name}.{os.getpid()}.part")
         try:
-            with open(tmp, "wb") as f:
-                self._request("GET", key, stream_to=f)
+            total = self.size(key) if self.max_concurrency > 1 else 0
+            if total >= self.multipart_threshold:
+                from concurrent.futures import ThreadPoolExecutor
+
+                with open(tmp, "wb") as f:
+                    f.truncate(total)
+                ranges = [(o, min(total, o + self.part_size) - 1) for o in range(0, total, self.part_size)]
+
+                def fetch(r: tuple[int, int]) -> None:
+                    _, _, data = self._request("GET", key, headers={"Range": f"bytes={r[0]}-{r[1]}"}, ok=(200, 206))
+                    if len(data) != r[1] - r[0] + 1:
+                        raise ObjectStoreError(f"GET {key} bytes={r[0]}-{r[1]}: got {len(data)} bytes")
+                    with open(tmp, "r+b") as f:
+                        f.seek(r[0])
+                        f.write(data)
+
+                with ThreadPoolExecutor(max_workers=min(self.max_concurrency, len(ranges)), thread_name_prefix="s3-range") as ex:
+                    list(ex.map(fetch, ranges))
+            else:
+                with open(tmp, "wb") as f:
+                    self._request("GET", key, stream_to=f)
         except ObjectStoreError as e:
             tmp.unlink(missing_ok=True)
             if e.status == 404:

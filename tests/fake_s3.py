@@ -54,6 +54,7 @@ class _Handler(BaseHTTPRequestHandler):
         self.end_headers()
         if self.command != "HEAD":
             self.wfile.write(body)
+        self.close_connection = self.command == "HEAD"      # a HEAD reply announces a body it does not send
 
     def _verify(self, body: bytes) -> bool:
         auth = self.headers.get("Authorization", "")
@@ -135,7 +136,13 @@ class _Handler(BaseHTTPRequestHandler):
             if self.command in ("GET", "HEAD"):
                 if full not in srv.objects:
                     return self._reply(404, b"<Error><Code>NoSuchKey</Code></Error>")
-                return self._reply(200, srv.objects[full])
+                data = srv.objects[full]
+                rng = self.headers.get("Range")
+                if rng and self.command == "GET":
+                    lo, _, hi = rng.split("=", 1)[1].partition("-")
+                    part = data[int(lo): int(hi) + 1]
+                    return self._reply(206, part, {"Content-Range": f"bytes {lo}-{int(lo) + len(part) - 1}/{len(data)}"})
+                return self._reply(200, data)
             if self.command == "DELETE":
                 srv.objects.pop(full, None)
                 return self._reply(204)
