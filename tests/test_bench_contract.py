@@ -34,3 +34,28 @@ def test_no_silent_cpu_fallback_and_launch_mismatch_is_reported():
     if not torch.cuda.is_available():
         out = _run("--steps", "1", "--warmup", "1")
         assert out.returncode != 0 and "CUDA" in (out.stderr + out.stdout) and not out.stdout.strip().startswith("{")
+
+
+def test_ddp_config_follows_the_sharding_switch():
+    """``--sharding``: plain DDP deletes ``fsdp_config`` (the launch scripts' choice), ``zero1`` / ``zero3`` keep it and name the scheme;
+    ``auto`` shards the 7B config fully and leaves the small ones replicated; ``--global-batch`` reaches the trainer config."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def cfg(model, sharding, impl="ours"):
+        a = argparse.Namespace(model=model, precision="amp_bf16", attention="b200", sharding=sharding)
+        return bench.ddp_cfg(a, impl, 8)
+
+    c = cfg("mpt-125m", "auto")
+    assert not c["llm_config"].get("fsdp_config") and c["kernels"]["param_sharding"] == "auto"
+    c = cfg("mpt-7b", "auto")
+    assert c["llm_config"]["fsdp_config"]["activation_checkpointing"] is True and c["kernels"]["param_sharding"] == "zero3"
+    assert cfg("mpt-1b", "zero1")["kernels"]["param_sharding"] == "zero1" and cfg("mpt-1b", "zero1")["llm_config"].get("fsdp_config")
+    assert not cfg("mpt-7b", "none")["llm_config"].get("fsdp_config")
+    assert not cfg("mpt-7b", "zero3", impl="torch")["llm_config"].get("fsdp_config")      # the stock arm is always plain DDP
+    bench.DDP_GLOBAL_BATCH = 32
+    assert int(cfg("mpt-7b", "auto")["llm_config"]["global_train_batch_size"]) == 32
