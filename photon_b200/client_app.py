@@ -29,6 +29,12 @@ class ClientApp:
         """Every worker process of this node is up (what makes the node show up in ``node_ids()``)."""
         return bool(self.nm.workers) and all(w.is_alive() for w in self.nm.workers)
 
+    def start(self) -> None:
+        self.nm.create_and_start_workers()
+
+    def describe(self) -> str:
+        return f"{len(self.nm.workers)} worker(s)"
+
     def shutdown(self) -> None:
         self.nm.close()
 

@@ -20,7 +20,16 @@ def main() -> None:
                     help="register ONE NODE PER GPU (each trains its own client) instead of one node whose GPUs collaborate on a client: "
                          "the right shape for models that fit a GPU — a box then trains as many clients at once as it has GPUs "
                          "(the server's photon.fleet.n_remote_nodes counts these nodes)")
+    ap.add_argument("--spmd", action="store_true",
+                    help="this process is ONE RANK of a box that joins as a single node running the SPMD runtime inside (fused NVLink "
+                         "aggregation over the box's GPUs, one pre-aggregated model per round towards the server): launch one per GPU "
+                         "with torchrun or `python -m photon_b200.launch --nproc N -m photon_b200.node -- --server host:port --spmd`")
     a = ap.parse_args()
+    if a.spmd:
+        from photon_b200.server.box_node import serve_box
+
+        serve_box(a.server, tls_ca=a.tls_ca, max_idle_s=a.max_idle_s)
+        return
     from photon_b200.server.grpc_fleet import serve_node
     from photon_b200.utils.core import get_n_cuda_devices
 

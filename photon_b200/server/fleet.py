@@ -173,8 +173,11 @@ class NodeFleetRuntime(FederationRuntime):
                                                       None, 0, {}, cid)], node_id=node))
                 pending[node] = f
                 return
-            fc = self.fit_config_fn(server_round, cid, self.client_states, self.server_steps_cumulative)
-            msg = fit_or_evaluate_ins("train", server_round, [cid], self.client_states, self.server_steps_cumulative, {cid: fc.to_wire()})
+            # a node with capacity > 1 (a whole SPMD box: one client per GPU at a time) takes that many clients in ONE task
+            cids = [cid] + [sched.queue.popleft() for _ in range(min(getattr(by_id[node], "capacity", 1) - 1, len(sched.queue)))]
+            batches[node] = cids
+            per = {c: self.fit_config_fn(server_round, c, self.client_states, self.server_steps_cumulative).to_wire() for c in cids}
+            msg = fit_or_evaluate_ins("train", server_round, cids, self.client_states, self.server_steps_cumulative, per)
             msg.node_id = node
             msg.defer_parameters = self.node_pre_aggregation  # type: ignore[attr-defined]
             pending[node] = self._pool.submit(by_id[node].handle, msg)
@@ -186,17 +189,22 @@ class NodeFleetRuntime(FederationRuntime):
                 del pending[n]
                 rep = f.result()
                 cid = rep.content[0].cid if rep.content else -1
+                extra = batches.pop(n, [])[1:]
+                if extra and getattr(by_id[n], "remote", False) and not by_id[n].alive():
+                    sched.queue.extendleft(reversed(extra))      # the scheduler re-queues the first client of a lost node itself
                 out.append((n, int(cid if cid is not None else -1), rep))
             return out
 
         results: list[FitRes] = []
         held: dict[int, list[int]] = {}       # node -> positions in ``results`` whose parameters the node is holding back
+        batches: dict[int, list[int]] = {}    # node -> the clients of the task it is working on
         t0 = time.time()
+        # a REMOTE node that stopped polling leaves the rotation (its clients are re-queued); an in-process node manager repairs its
+        # own workers and reports what it could not do
+        sched = ClientScheduler(sampled, [a.node_id for a in self.apps if a.alive()], dispatch, poll, poll_s=0.01,
+                                is_alive=lambda n: by_id[n].alive() if getattr(by_id[n], "remote", False) else True)
         with tracer().span("fit_clients", cat="server", server_round=server_round):
-            for _node, cid, reply in ClientScheduler(sampled, [a.node_id for a in self.apps if a.alive()], dispatch, poll, poll_s=0.01,
-                                                     # a REMOTE node that stopped polling leaves the rotation (its client is re-queued);
-                                                     # an in-process node manager repairs its own workers and reports what it could not do
-                                                     is_alive=lambda n: by_id[n].alive() if getattr(by_id[n], "remote", False) else True):
+            for _node, cid, reply in sched:
                 for res in reply.content or [FitRes(Status(Code.FAILED, reply.error or "empty reply"), None, 0, {}, cid)]:
                     if res.status.code == Code.OK and res.parameters is not None and res.parameters.kind == "deferred":
                         held.setdefault(_node, []).append(len(results))

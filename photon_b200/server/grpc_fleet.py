@@ -78,6 +78,7 @@ class RemoteNode:
         self._link, self._slot = link, slot
         self.node_id = slot.node_id
         self.remote = True
+        self.capacity = max(1, int(slot.info.get("capacity", 1) or 1))     # clients the node takes per task (a whole SPMD box: its GPUs)
 
     def alive(self) -> bool:
         return not self._slot.gone and time.time() - self._slot.last_seen < self._link.liveness_timeout_s
@@ -366,8 +367,12 @@ def _park_results(reply: Message, cfg: Any, node_id: int) -> Message:
 
 
 def serve_node(server_address: str, *, n_workers: int | None = None, devices: list[int] | None = None, token: str | None = None,
-               tls_ca: str | None = None, first_id: int = 1000, max_idle_s: float | None = None) -> int:
-    """Run one node until the server shuts the fleet down (or is unreachable for ``max_idle_s``). Returns the node id."""
+               tls_ca: str | None = None, first_id: int = 1000, max_idle_s: float | None = None, app_factory: Any = None,
+               info: dict[str, Any] | None = None) -> int:
+    """Run one node until the server shuts the fleet down (or is unreachable for ``max_idle_s``). Returns the node id.
+    ``app_factory(cfg, node_id)`` builds what serves the messages (default: a :class:`ClientApp` — node manager + workers;
+    :mod:`photon_b200.server.box_node` passes the SPMD runtime of a whole box); ``info`` is added to the registration record
+    (``capacity``: clients the node takes per task)."""
     import socket
 
     import grpc
@@ -386,7 +391,7 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
     t0 = time.time()
     while True:     # the server may come up after its nodes (the reference starts the supernodes in any order)
         try:
-            reg = _de(call["Register"](_ser({"host": socket.gethostname(), "pid": os.getpid(), "n_workers": n_workers, "devices": devices, "first_id": first_id}),
+            reg = _de(call["Register"](_ser({"host": socket.gethostname(), "pid": os.getpid(), "n_workers": n_workers, "devices": devices, "first_id": first_id, **(info or {})}),
                                        metadata=md, timeout=30.0))
             break
         except grpc.RpcError as e:
@@ -394,11 +399,14 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
                 raise
             time.sleep(1.0)
     node_id, cfg = int(reg["node_id"]), reg["cfg"]
-    from photon_b200.client_app import ClientApp
+    if app_factory is not None:
+        app = app_factory(cfg, node_id)
+    else:
+        from photon_b200.client_app import ClientApp
 
-    app = ClientApp(cfg, n_workers=n_workers, node_id=node_id, devices=devices)
-    app.nm.create_and_start_workers()
-    print(f"[node {node_id}] connected to {server_address}; {len(app.nm.workers)} worker(s)", flush=True)
+        app = ClientApp(cfg, n_workers=n_workers, node_id=node_id, devices=devices)
+    app.start()
+    print(f"[node {node_id}] connected to {server_address}; {app.describe()}", flush=True)
     last_ok = time.time()
     stop = threading.Event()
 
@@ -439,6 +447,6 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
                     time.sleep(1.0 + attempt)
     finally:
         stop.set()
-        app.nm.close()
+        app.shutdown()
         channel.close()
     return node_id

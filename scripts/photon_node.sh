@@ -7,5 +7,11 @@
 set -euo pipefail
 SERVER=${1:?usage: photon_node.sh SERVER_HOST:PORT}
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
+# SPMD=1: the whole box joins as ONE node that runs the SPMD runtime inside (one process per GPU, fused NVLink aggregation of the
+#         box's clients, one pre-aggregated model per round towards the server) — the shape for multi-box federations of B200 boxes
+if [ -n "${SPMD:-}" ]; then
+  N=${N_GPUS:-$(python -c "import torch; print(max(1, torch.cuda.device_count()))")}
+  exec python -m photon_b200.launch --nproc "$N" --master-port "${BOX_MASTER_PORT:-29600}" -m photon_b200.node -- --server "$SERVER" --spmd ${FLEET_TLS_CA:+--tls-ca "$FLEET_TLS_CA"}
+fi
 # PER_GPU=1: one node per GPU (each trains its own client at the same time) instead of all GPUs collaborating on one client
 exec python -m photon_b200.node --server "$SERVER" ${N_WORKERS:+--n-workers "$N_WORKERS"} ${DEVICES:+--devices "$DEVICES"} ${FLEET_TLS_CA:+--tls-ca "$FLEET_TLS_CA"} ${PER_GPU:+--per-gpu}

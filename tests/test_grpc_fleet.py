@@ -269,3 +269,40 @@ def test_a_machine_can_join_a_running_federation(tmp_path):
         rt.close()
     outs = _reap(procs)
     assert all(p.returncode == 0 for p in procs), outs
+
+
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_a_whole_box_joins_as_one_spmd_node(tmp_path, ranks):
+    """``--spmd``: the box trains its share of the round with the SPMD runtime (one process per device, work queue, its own round
+    transport for the box-level mean) and looks like one pre-aggregating node of capacity ``ranks`` to the server. Same global model
+    as two ordinary in-process nodes."""
+    from photon_b200.server.fleet import NodeFleetRuntime
+    from photon_b200.server_app import run_server
+
+    common = ["fl.n_rounds=2", "fl.n_clients_per_round=4", "llm_config.save_folder=null", "fl.strategy_name=fedavg", "photon.topology=nodes",
+              "fl.eval_period=null"]
+    want = _reference_model(tmp_path, "agg", common)
+    port = _free_port()
+    env = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="")
+    node = [sys.executable, "-m", "photon_b200.node", "--server", f"127.0.0.1:{port}", "--spmd", "--max-idle-s", "60"]
+    if ranks > 1:
+        cmd = [sys.executable, "-m", "photon_b200.launch", "--nproc", str(ranks), "--master-port", str(_free_port()), "-m", "photon_b200.node", "--",
+               *node[3:]]
+    else:
+        cmd = node
+    proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    cfg = _cfg(tmp_path / f"box{ranks}", "run_uuid=agg", "photon.n_nodes=0", f"photon.fleet.address=127.0.0.1:{port}", "photon.fleet.n_remote_nodes=1",
+               "photon.fleet.connect_timeout_s=180", *common)
+    rt = NodeFleetRuntime(cfg)
+    try:
+        h = run_server(cfg, runtime=rt)
+        assert [v for _, v in h.metrics_distributed_fit["server/n_failures"]] == [0, 0]
+        node0 = rt.apps[0]
+        assert node0.capacity == ranks and node0._slot.info["kind"] == "spmd-box"
+        got = rt.round_backend.global_params().clone()
+    finally:
+        rt.close()
+    out = _reap([proc])[0]
+    assert proc.returncode == 0, out[-3000:]
+    assert f"SPMD box, {ranks} rank(s)" in out
+    assert torch.allclose(got, want, atol=1e-5), float((got - want).abs().max())
