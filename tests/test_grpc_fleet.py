@@ -282,6 +282,7 @@ def test_a_whole_box_joins_as_one_spmd_node(tmp_path, ranks):
     common = ["fl.n_rounds=2", "fl.n_clients_per_round=4", "llm_config.save_folder=null", "fl.strategy_name=fedavg", "photon.topology=nodes",
               "fl.eval_period=null"]
     want = _reference_model(tmp_path, "agg", common)
+    common = common[:-1] + ["fl.eval_period=1"]          # the box also serves the federated evaluation
     port = _free_port()
     env = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="")
     node = [sys.executable, "-m", "photon_b200.node", "--server", f"127.0.0.1:{port}", "--spmd", "--max-idle-s", "60"]
@@ -297,6 +298,7 @@ def test_a_whole_box_joins_as_one_spmd_node(tmp_path, ranks):
     try:
         h = run_server(cfg, runtime=rt)
         assert [v for _, v in h.metrics_distributed_fit["server/n_failures"]] == [0, 0]
+        assert len(h.losses_distributed) == 3 and all(2.0 < loss < 12.0 for _, loss in h.losses_distributed), h.losses_distributed
         node0 = rt.apps[0]
         assert node0.capacity == ranks and node0._slot.info["kind"] == "spmd-box"
         got = rt.round_backend.global_params().clone()
