@@ -30,15 +30,27 @@ class ByteTokenizer:
 
 
 def build_tokenizer(name: str = "EleutherAI/gpt-neox-20b", **kwargs: Any) -> Any:
-    """HF tokenizer when its files are locally cached; otherwise the byte-level fallback
-    (there is no network here)."""
+    """HF tokenizer when its files are locally cached (there is no network here). ``name="byte"`` asks for the byte-level tokenizer
+    explicitly; any OTHER name that cannot be loaded falls back to it LOUDLY — a corpus tokenised with the wrong vocabulary trains and
+    evaluates without complaint, so ``PHOTON_STRICT_DATA=1`` (exported by the launch scripts) makes the fall-back an error."""
+    import os
+    import sys
+
+    if str(name).lower() in ("byte", "bytes", "byte-fallback"):
+        return ByteTokenizer()
     try:
         from transformers import AutoTokenizer
 
         tok = AutoTokenizer.from_pretrained(name, local_files_only=True, **kwargs)
         tok.model_max_length = int(1e30)
         return tok
-    except Exception:  # noqa: BLE001
+    except Exception as e:  # noqa: BLE001
+        if os.environ.get("PHOTON_STRICT_DATA", "0") not in ("", "0", "false", "False"):
+            raise RuntimeError(f"tokenizer {name!r} is not available locally ({type(e).__name__}: {str(e)[:160]}); with PHOTON_STRICT_DATA "
+                               "set the byte-level fall-back is not used — cache the tokenizer files or pass --tokenizer byte") from e
+        print(f"[tokenizer] WARNING: {name!r} could not be loaded from the local cache ({type(e).__name__}) -> BYTE-LEVEL fall-back "
+              "(vocabulary 257). Token ids will NOT match a model trained with the real tokenizer. Set PHOTON_STRICT_DATA=1 to make "
+              "this an error, or pass --tokenizer byte to silence it.", file=sys.stderr, flush=True)
         return ByteTokenizer()
 
 

@@ -116,3 +116,15 @@ def test_converter_writes_mds_directories_the_loader_reads_back(tmp_path, compre
     assert len(w.finish()["shards"]) > 1
     r = MDSReader(tmp_path / "many")
     assert len(r) == 20 and all(int(r[i][0]) == i for i in range(20))
+
+
+def test_tokenizer_fallback_is_loud_and_strict_mode_refuses_it(monkeypatch, capsys):
+    from photon_b200.dataset.utils import ByteTokenizer, build_tokenizer
+
+    monkeypatch.delenv("PHOTON_STRICT_DATA", raising=False)
+    assert isinstance(build_tokenizer("byte"), ByteTokenizer) and capsys.readouterr().err == ""       # asked for: silent
+    tok = build_tokenizer("no-such-org/no-such-tokenizer")
+    assert isinstance(tok, ByteTokenizer) and "BYTE-LEVEL fall-back" in capsys.readouterr().err
+    monkeypatch.setenv("PHOTON_STRICT_DATA", "1")
+    with pytest.raises(RuntimeError, match="not available locally"):
+        build_tokenizer("no-such-org/no-such-tokenizer")
