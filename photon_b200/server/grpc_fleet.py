@@ -414,7 +414,7 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
         period = max(0.2, float(reg.get("liveness_timeout_s", 30.0)) / 4.0)
         while not stop.wait(period):
             try:
-                call["Beat"](_ser({"node_id": node_id}), metadata=md, timeout=10.0)
+                call["Beat"](_ser({"node_id": app.node_id}), metadata=md, timeout=10.0)
             except grpc.RpcError:
                 pass
 
@@ -425,7 +425,24 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
                 msg = _de(call["Pull"](_ser({"node_id": node_id, "wait_s": 2.0}), metadata=md, timeout=30.0))
                 last_ok = time.time()
             except grpc.RpcError as e:
-                if e.code() == grpc.StatusCode.NOT_FOUND or (max_idle_s is not None and time.time() - last_ok > max_idle_s):
+                if e.code() == grpc.StatusCode.NOT_FOUND:
+                    # the link answers but does not know this node: the server process was restarted (crash + resume). Join the new
+                    # instance with the workers / runtime that are already up, as long as it is the same run.
+                    try:
+                        reg = _de(call["Register"](_ser({"host": socket.gethostname(), "pid": os.getpid(), "n_workers": n_workers, "devices": devices,
+                                                         "first_id": first_id, "rejoined_from": node_id, **(info or {})}), metadata=md, timeout=30.0))
+                    except grpc.RpcError:
+                        time.sleep(0.5)
+                        continue
+                    if str((reg["cfg"] or {}).get("run_uuid")) != str((cfg or {}).get("run_uuid")):
+                        print(f"[node {node_id}] the link now serves another run ({(reg['cfg'] or {}).get('run_uuid')}); leaving", flush=True)
+                        break
+                    print(f"[node {node_id}] the server was restarted: re-registered as node {reg['node_id']}", flush=True)
+                    node_id = int(reg["node_id"])
+                    app.node_id = node_id
+                    last_ok = time.time()
+                    continue
+                if max_idle_s is not None and time.time() - last_ok > max_idle_s:
                     print(f"[node {node_id}] lost the fleet link ({e.code().name}); leaving", flush=True)
                     break
                 time.sleep(0.5)

@@ -308,3 +308,38 @@ def test_a_whole_box_joins_as_one_spmd_node(tmp_path, ranks):
     assert proc.returncode == 0, out[-3000:]
     assert f"SPMD box, {ranks} rank(s)" in out
     assert torch.allclose(got, want, atol=1e-5), float((got - want).abs().max())
+
+
+def test_node_rejoins_a_restarted_server(tmp_path):
+    """The server process dies without saying goodbye and comes back on the same address (crash + resume): the node keeps its
+    workers, notices that the link no longer knows it and registers again; a node pointed at ANOTHER run leaves instead."""
+    from photon_b200.messages import Message
+    from photon_b200.server.grpc_fleet import FleetLink
+
+    cfg = _cfg(tmp_path, "run_uuid=phoenix", "llm_config.save_folder=null")
+    port = _free_port()
+    first = FleetLink(f"127.0.0.1:{port}", cfg=cfg, liveness_timeout_s=10)
+    procs = _spawn_nodes(1, port)
+    try:
+        (node,) = first.wait_for_nodes(1, timeout_s=120)
+        assert node.handle(Message("query", {"type": "free_resources"})).content == {"free_resources": {"status": "OK"}}
+        first._server.stop(0)                                   # no shutdown message: a crash
+        time.sleep(1.0)
+        second = FleetLink(f"127.0.0.1:{port}", cfg=cfg, liveness_timeout_s=10)
+        try:
+            (again,) = second.wait_for_nodes(1, timeout_s=120)
+            assert second._slots[again.node_id].info["rejoined_from"] == node.node_id and second._slots[again.node_id].info["pid"] == procs[0].pid
+            assert again.handle(Message("query", {"type": "free_resources"})).content == {"free_resources": {"status": "OK"}}
+            second._server.stop(0)
+            time.sleep(1.0)
+            other = FleetLink(f"127.0.0.1:{port}", cfg=_cfg(tmp_path, "run_uuid=someone-else", "llm_config.save_folder=null"))
+            try:
+                out = _reap(procs)[0]
+                assert procs[0].returncode == 0 and "serves another run" in out and "re-registered as node" in out
+            finally:
+                other.close(grace_s=0.1)
+        finally:
+            second.close(grace_s=0.1)
+    finally:
+        first.close(grace_s=0.1)
+        _reap(procs)
