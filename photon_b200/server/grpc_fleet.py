@@ -418,7 +418,8 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
             except grpc.RpcError:
                 pass
 
-    threading.Thread(target=heartbeat, name="photon-node-heartbeat", daemon=True).start()
+    hb = threading.Thread(target=heartbeat, name="photon-node-heartbeat", daemon=True)
+    hb.start()
     try:
         while True:
             try:
@@ -464,6 +465,7 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
                     time.sleep(1.0 + attempt)
     finally:
         stop.set()
+        hb.join(timeout=15.0)       # never tear the channel down under a heartbeat that is inside an RPC (the C++ runtime aborts the process)
         app.shutdown()
         channel.close()
     return node_id
