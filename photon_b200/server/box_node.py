@@ -52,6 +52,10 @@ class BoxApp:
         self._agg_round = -1
         self._op = 0
         self._global: torch.Tensor | None = None      # the server's model of this round (every batch of the round starts from it)
+        if runtime.ctl is not None:
+            # a box waits for work for as long as the server has none: "rank 0 has not spoken for two hours" is not an error here
+            # (a DEAD rank 0 is still noticed — its heartbeat goes stale — and rank 0 keeps ticking while it polls the server)
+            runtime.ctl.exchange_timeout_s = 10 * 365 * 86400.0
 
     # ------------------------------------------------------------------ lifecycle
     def start(self) -> None:
@@ -62,6 +66,12 @@ class BoxApp:
 
     def alive(self) -> bool:
         return True
+
+    def tick(self) -> None:
+        """Called by the serving loop between polls: waiting for the server IS this rank's progress (the control plane stops the
+        heartbeat of a rank whose main thread made none for ``photon.progress_timeout_s``)."""
+        if self.rt.ctl is not None:
+            self.rt.ctl.tick()
 
     def shutdown(self) -> None:
         self._replay({"op": "stop"})

@@ -448,6 +448,7 @@ def serve_node(server_address: str, *, n_workers: int | None = None, devices: li
                     break
                 time.sleep(0.5)
                 continue
+            getattr(app, "tick", lambda: None)()
             if msg is None:
                 continue
             if msg.kind == "shutdown":

@@ -343,3 +343,33 @@ def test_node_rejoins_a_restarted_server(tmp_path):
     finally:
         first.close(grace_s=0.1)
         _reap(procs)
+
+
+def test_an_idle_box_stays_together(tmp_path):
+    """A two-rank box with a 2-second progress time-out sits idle for 7 seconds (the server has no work): rank 0 keeps ticking while it
+    polls, the follower keeps waiting — and the next broadcast, a collective over both ranks, still goes through."""
+    import numpy as np
+
+    from photon_b200.clients.utils import get_initial_parameters
+    from photon_b200.messages import Message
+    from photon_b200.server.grpc_fleet import FleetLink
+
+    cfg = _cfg(tmp_path, "run_uuid=idle", "llm_config.save_folder=null", "photon.progress_timeout_s=2", "photon.liveness_timeout_s=4")
+    port = _free_port()
+    link = FleetLink(f"127.0.0.1:{port}", cfg=cfg, liveness_timeout_s=30)
+    env = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="")
+    proc = subprocess.Popen([sys.executable, "-m", "photon_b200.launch", "--nproc", "2", "--master-port", str(_free_port()), "-m", "photon_b200.node", "--",
+                             "--server", f"127.0.0.1:{port}", "--spmd", "--max-idle-s", "60"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        (node,) = link.wait_for_nodes(1, timeout_s=180)
+        arrays, _ = get_initial_parameters(cfg)
+        ok = {"broadcast": {"status": "OK"}}
+        assert node.handle(Message("query", {"type": "broadcast_parameters", "parameters": [np.asarray(a) for a in arrays]})).content == ok
+        time.sleep(7.0)
+        assert node.alive()
+        again = node.handle(Message("query", {"type": "broadcast_parameters", "parameters": [np.asarray(a) for a in arrays]}))
+        assert again.content == ok and not again.error, again.error
+    finally:
+        link.close()
+    out = _reap([proc])[0]
+    assert proc.returncode == 0, out[-3000:]
