@@ -152,6 +152,9 @@ class NodeFleetRuntime(FederationRuntime):
         finally:
             for h in handles:
                 release_remote_parameters(h)
+        # what crossed the network this round (in-process nodes share a POSIX segment): the quantity the reference's design is about
+        self.timings["comm/param_bytes_to_nodes"] = float(4 * self.layout.total * len(remote))
+        self.timings["comm/param_bytes_from_nodes"] = 0.0
         bad = [a.error for a in acks if a.error or a.content != {"broadcast": {"status": "OK"}}]
         if bad:
             raise RuntimeError(f"broadcast not acknowledged by {len(bad)} node(s): {bad[:2]}")
@@ -210,6 +213,8 @@ class NodeFleetRuntime(FederationRuntime):
                         held.setdefault(_node, []).append(len(results))
                         res = FitRes(res.status, ParamHandle(kind=rb.name), res.num_examples, res.metrics, res.cid)
                     elif res.status.code == Code.OK and res.parameters is not None:
+                        if getattr(by_id[_node], "remote", False):
+                            self.timings["comm/param_bytes_from_nodes"] += float(4 * self.layout.total)
                         flat = torch.zeros(self.layout.total, dtype=torch.float32)
                         if res.parameters.kind != "inline":     # a remote node parked its result in the bucket
                             from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
@@ -252,6 +257,8 @@ class NodeFleetRuntime(FederationRuntime):
             flat = torch.zeros(self.layout.total, dtype=torch.float32)
             self.layout.from_ndarrays(flat, handle.data)
             self.round_backend.add_client(flat, want)
+            if getattr(by_id[n], "remote", False):
+                self.timings["comm/param_bytes_from_nodes"] += float(4 * self.layout.total)
 
     # ----------------------------------------------------------------------- evaluate
     def run_clients_evaluate(self, server_round: int, sampled: list[int]) -> list[EvaluateRes]:

@@ -121,7 +121,9 @@ def run_server(cfg: Any, runtime: FederationRuntime | None = None, n_rounds: int
                 "server/round_time": time.time() - t_round, "server/first_check_nm_time": first_check,
                 "server/second_check_nm_time": time.time() - t_chk, "server/n_nodes_after_round": n_after,
                 # reduce + server optimizer + broadcast of the round (the reference times only its broadcast here)
-                "server/broadcast_post_time": float(runtime.timings.get("aggregate_broadcast_host_s", runtime.timings.get("server/broadcast_time", 0.0)))})
+                "server/broadcast_post_time": float(runtime.timings.get("aggregate_broadcast_host_s", runtime.timings.get("server/broadcast_time", 0.0))),
+                # parameter bytes that crossed the network this round (node-fleet topology with remote nodes)
+                **{k: float(v) for k, v in runtime.timings.items() if k.startswith("comm/")}})
     if store is not None and runtime.rank == 0:
         store.wait()                                               # every round's checkpoint is on disk before the run reports done
     if store is not None and cfg.get("cleanup_checkpoints") and runtime.rank == 0:

@@ -148,6 +148,10 @@ def test_node_pre_aggregation_ships_one_model_per_node(tmp_path, store, monkeypa
         h = run_server(cfg, runtime=rt)
         assert [v for _, v in h.metrics_distributed_fit["server/n_failures"]] == [0, 0]
         got = rt.round_backend.global_params().clone()
+        size = 4 * rt.layout.total
+        inbound = [v for _, v in h.metrics_centralized["comm/param_bytes_from_nodes"]]
+        assert all(size <= b <= 2 * size for b in inbound), (inbound, size)            # at most one model per node, not one per client (4)
+        assert [v for _, v in h.metrics_centralized["comm/param_bytes_to_nodes"]] == [2 * size, 2 * size]
     finally:
         rt.close()
     outs = _reap(procs)
