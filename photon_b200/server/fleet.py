@@ -148,6 +148,7 @@ class NodeFleetRuntime(FederationRuntime):
                 handles.append(h)
                 futs += [self._pool.submit(app.handle, Message("query", {"type": "broadcast_parameters", "parameters": h}, node_id=app.node_id))
                          for app in remote]
+            targets = local + remote
             acks = [f.result() for f in futs]
         finally:
             for h in handles:
@@ -155,9 +156,14 @@ class NodeFleetRuntime(FederationRuntime):
         # what crossed the network this round (in-process nodes share a POSIX segment): the quantity the reference's design is about
         self.timings["comm/param_bytes_to_nodes"] = float(4 * self.layout.total * len(remote))
         self.timings["comm/param_bytes_from_nodes"] = 0.0
-        bad = [a.error for a in acks if a.error or a.content != {"broadcast": {"status": "OK"}}]
+        # a remote node that died during the broadcast is simply out of the rotation (its liveness check fails from now on);
+        # anything else that does not acknowledge is an error
+        bad = [a.error or f"unexpected reply {a.content!r}" for app, a in zip(targets, acks)
+               if (a.error or a.content != {"broadcast": {"status": "OK"}}) and not (getattr(app, "remote", False) and not app.alive())]
         if bad:
             raise RuntimeError(f"broadcast not acknowledged by {len(bad)} node(s): {bad[:2]}")
+        if not any(a.content == {"broadcast": {"status": "OK"}} for a in acks):
+            raise RuntimeError("no node of the fleet received the round's parameters")
         return {"server/broadcast_time": time.time() - t0}
 
     # ---------------------------------------------------------------------------- fit
