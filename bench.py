@@ -299,7 +299,9 @@ def run_ddp(env: Env, args, impl: str, K: int, W: int) -> dict:
     if DDP_GLOBAL_BATCH % env.world:
         raise SystemExit("--gpus must divide 256")
     per_gpu = DDP_GLOBAL_BATCH // env.world
-    mb = args.microbatch or (min(LOCAL_BATCH, per_gpu) if impl == "ours" else "auto")
+    # the reference's device_train_microbatch_size: 32 fits MPT-125M, the larger configs use 8 (ref: conf/llm_config/mpt-{1b,3b,7b}.yaml)
+    default_mb = min(LOCAL_BATCH if args.model == "mpt-125m" else 8, per_gpu)
+    mb = args.microbatch or (default_mb if impl == "ours" else "auto")
     cfg = ddp_cfg(args, impl, mb)
     kw = {}
     if impl != "ours" and env.world > 1:
