@@ -4,8 +4,10 @@
   compression="zstd")`` lays it out (the reference's dataset format, ref: photon/dataset/convert_dataset_hf.py:323-327):
   ``index.json`` (version 2) + ``shard.0000N.mds.zstd``; a raw shard is
   ``uint32 n | uint32 offsets[n+1] | json config | samples``, a sample is ``uint32 sizes of the variable-size columns | payloads``,
-  an ``ndarray:int32`` payload is ``uint8 ndim-and-width header | dims | C-order data``. Written here byte by byte from that
-  description — independently of ``photon_b200.data.shards.MDSReader``, which the test then points at it.
+  an ``ndarray:int32`` payload is ``shape header | C-order data``. The shape header is written here in its ONE-byte form
+  (``uint8 ndim | dims``); ``photon_b200.data.shards.MDSWriter`` writes the two-byte form (``uint8 ndim | uint8 dims-type | dims``)
+  that mosaicml-streaming's NDArray encoding is believed to use — no install was available to settle it, so the reader accepts
+  both and always checks the dims against the payload length. Written byte by byte, independently of the reader under test.
 * ``ref_state/state.bin``  a server-state pickle with the reference's five fields and a ``photon.wandb_history.WandbHistory``
   (a Flower ``History`` subclass) object inside (ref: photon/server/s3_utils.py:374-389), produced with stand-in classes that
   carry the reference's module / class names so the byte stream is what the reference's ``pickle.dump`` emits.
