@@ -377,3 +377,17 @@ def test_an_idle_box_stays_together(tmp_path):
         link.close()
     out = _reap([proc])[0]
     assert proc.returncode == 0, out[-3000:]
+
+
+def test_cross_host_example_script_runs_end_to_end(tmp_path):
+    """``scripts/fed_cross_host_example.sh`` (resolver -> server with fleet link -> two SPMD boxes joining it) on a tiny model."""
+    env = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="", PHOTON_STRICT_DATA="0", N_BOXES="2", N_ROUNDS="2", LOCAL_STEPS="1",
+               N_CLIENTS="2", SAVE_PATH=str(tmp_path), RUN_UUID="xdemo", FLEET_PORT=str(_free_port()), N_GPUS="0",
+               EXTERNAL_CONFIGS="llm_config.model.d_model=64 llm_config.model.n_heads=2 llm_config.model.n_layers=2 llm_config.max_seq_len=64 "
+                                "llm_config.global_train_batch_size=4 llm_config.model.vocab_size=512")
+    env.pop("PHOTON_SAVE_PATH", None)
+    out = subprocess.run(["bash", str(ROOT / "scripts" / "fed_cross_host_example.sh")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
+    assert "[server] done." in out.stdout and "'server/n_nodes': 2" in out.stdout and "'server/n_failures': 0" in out.stdout
+    boxes = [(tmp_path / "xdemo" / f"box_{b}.log").read_text() for b in (0, 1)]
+    assert all("SPMD box, 1 rank(s)" in b for b in boxes)
