@@ -3,7 +3,7 @@
 ``val`` is accepted as an alias of the reference's ``validation`` key (the folder it is written to)."""
 from __future__ import annotations
 
-from photon_b200.dataset.constants.dataset_constants_types import ConcatMode, DatasetConstants, DataSplitConstants  # noqa: F401
+from photon_b200.dataset.dataset_types import ConcatMode, DatasetConstants, DataSplitConstants  # noqa: F401
 from photon_b200.dataset.constants.mc4 import ALL_CONSTANTS, C4_PATH  # noqa: F401
 
 # the reference's order

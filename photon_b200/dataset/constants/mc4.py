@@ -6,7 +6,7 @@ full splits only. Table keys are the reference's (``validation`` is the key of t
 The tables are generated from two small specs instead of thirteen literal blocks; ``c4_<lang>_constants`` names are kept."""
 from __future__ import annotations
 
-from photon_b200.dataset.constants.dataset_constants_types import (TRAIN_CONSTANT, TRAIN_SMALL_CONSTANT, VAL_CONSTANT, VAL_SMALL_CONSTANT,
+from photon_b200.dataset.dataset_types import (TRAIN_CONSTANT, TRAIN_SMALL_CONSTANT, VAL_CONSTANT, VAL_SMALL_CONSTANT,
                                                                    VAL_XSMALL_CONSTANT, VAL_XXSMALL_CONSTANT, VALIDATION_CONSTANT,
                                                                    DatasetConstants, DataSplitConstants)
 
