@@ -18,7 +18,8 @@ _SRC, _DST = __name__, "photon_b200"
 _MOVED = {"strategy.fedadam": "strategy.strategies", "strategy.fedavg_eff": "strategy.strategies", "strategy.fedmom": "strategy.strategies",
           "strategy.fednestorov": "strategy.strategies", "strategy.fedyogi": "strategy.strategies",
           "strategy.strategy_with_cfg": "strategy.strategies", "metrics.unigram_normalized_metrics": "metrics.language",
-          "conf.base_schema": "config.schema", "dataset.constants.dataset_constants_types": "dataset.dataset_types"}
+          "conf.base_schema": "config.schema", "dataset.constants.dataset_constants_types": "dataset.dataset_types",
+          "strategy.constants": "strategy.strategies"}
 
 
 class _AliasLoader(importlib.abc.Loader):

@@ -8,7 +8,7 @@ import torch
 from photon_b200.checkpoint.store import CheckpointStore
 from photon_b200.messages import ClientState, decode_client_states, encode_client_states
 from photon_b200.server.broadcast_utils import broadcast_parameters_to_nodes
-from photon_b200.strategy.constants import MOMENTUM_KEY, SECOND_MOMENTUM_KEY, SERVER_PARAMETERS_KEY
+from photon_b200.strategy.strategies import MOMENTUM_KEY, SECOND_MOMENTUM_KEY, SERVER_PARAMETERS_KEY
 from photon_b200.wandb_history import WandbHistory
 
 

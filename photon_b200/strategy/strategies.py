@@ -29,11 +29,15 @@ import torch
 from photon_b200.messages import Code, EvaluateRes, FitRes
 from photon_b200.strategy.aggregation import (aggregate_inplace, naive_weighted_mean, weighted_average,
                                              weighted_loss_avg)
-from photon_b200.strategy.constants import MOMENTUM_KEY, SECOND_MOMENTUM_KEY, SERVER_PARAMETERS_KEY
 from photon_b200.strategy.metrics import ServerMetricCallback
 from photon_b200.utils.flat import FlatLayout
 
 KINDS = ("fedavg", "nesterov", "fedmom", "fedadam", "fedyogi")
+
+# strategy state keys == the stems of the server checkpoint files (part of the on-disk compatibility surface; the reference keeps
+# them in photon/strategy/constants.py as MODEL_PARAMETERS / FIRST_MOMENTUM / SECOND_MOMENTUM — aliases below)
+SERVER_PARAMETERS_KEY, MOMENTUM_KEY, SECOND_MOMENTUM_KEY = (f"current_{stem}" for stem in ("server_parameters", "momentum_vector", "second_momentum_vector"))
+MODEL_PARAMETERS, FIRST_MOMENTUM, SECOND_MOMENTUM = SERVER_PARAMETERS_KEY, MOMENTUM_KEY, SECOND_MOMENTUM_KEY
 
 
 def server_opt_step(kind: str, x: torch.Tensor, a: torch.Tensor, m: torch.Tensor | None, v: torch.Tensor | None,
