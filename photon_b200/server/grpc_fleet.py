@@ -123,7 +123,9 @@ class FleetLink:
         self._spool_dir = tempfile.mkdtemp(prefix="photon_link_")
         self.spool = DirObjectStore(self._spool_dir)           # what ObjGet / ObjPut / ObjDel serve; the server reads it directly
         s3_utils.set_link_store(self.spool)
-        self._server = grpc.server(ThreadPoolExecutor(max_workers=64, thread_name_prefix="fleet-link"), options=_OPTS)
+        # every connected node parks one long poll here (plus its heartbeats and object chunks): threads, not work
+        self._server = grpc.server(ThreadPoolExecutor(max_workers=int(os.environ.get("PHOTON_FLEET_THREADS", "256")), thread_name_prefix="fleet-link"),
+                                   options=_OPTS)
         ident = lambda b: b  # noqa: E731 - payloads are already bytes
         handlers = {name: grpc.unary_unary_rpc_method_handler(getattr(self, "_" + name.lower()), request_deserializer=ident, response_serializer=ident)
                     for name in ("Register", "Pull", "Push", "Beat", "ObjGet", "ObjPut", "ObjDel")}
