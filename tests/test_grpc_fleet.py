@@ -391,3 +391,46 @@ def test_cross_host_example_script_runs_end_to_end(tmp_path):
     assert "[server] done." in out.stdout and "'server/n_nodes': 2" in out.stdout and "'server/n_failures': 0" in out.stdout
     boxes = [(tmp_path / "xdemo" / f"box_{b}.log").read_text() for b in (0, 1)]
     assert all("SPMD box, 1 rank(s)" in b for b in boxes)
+
+
+def test_fleet_link_over_tls(tmp_path):
+    """``PHOTON_FLEET_TLS_KEY`` / ``_CERT`` on the server, ``--tls-ca`` on the node: the link is encrypted and the node checks the
+    server's certificate (a self-signed one for ``localhost`` here); a node without the CA cannot talk to it."""
+    import datetime as dt
+    import ipaddress
+
+    cryptography = pytest.importorskip("cryptography")
+    del cryptography
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import ec
+    from cryptography.x509.oid import NameOID
+
+    from photon_b200.messages import Message
+    from photon_b200.server.grpc_fleet import FleetLink
+
+    key = ec.generate_private_key(ec.SECP256R1())
+    name = x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, "localhost")])
+    now = dt.datetime.now(dt.timezone.utc)
+    cert = (x509.CertificateBuilder().subject_name(name).issuer_name(name).public_key(key.public_key()).serial_number(x509.random_serial_number())
+            .not_valid_before(now - dt.timedelta(minutes=5)).not_valid_after(now + dt.timedelta(days=1))
+            .add_extension(x509.SubjectAlternativeName([x509.DNSName("localhost"), x509.IPAddress(ipaddress.ip_address("127.0.0.1"))]), critical=False)
+            .add_extension(x509.BasicConstraints(ca=True, path_length=None), critical=True).sign(key, hashes.SHA256()))
+    kp, cp = tmp_path / "key.pem", tmp_path / "cert.pem"
+    kp.write_bytes(key.private_bytes(serialization.Encoding.PEM, serialization.PrivateFormat.PKCS8, serialization.NoEncryption()))
+    cp.write_bytes(cert.public_bytes(serialization.Encoding.PEM))
+    cfg = _cfg(tmp_path, "run_uuid=tls", "llm_config.save_folder=null")
+    port = _free_port()
+    link = FleetLink(f"127.0.0.1:{port}", cfg=cfg, token="t", tls=(str(kp), str(cp)))
+    env = dict(os.environ, PYTHONPATH=str(ROOT), CUDA_VISIBLE_DEVICES="", PHOTON_FLEET_TOKEN="t")
+    base = [sys.executable, "-m", "photon_b200.node", "--server", f"localhost:{port}", "--n-workers", "1", "--max-idle-s", "8"]
+    good = subprocess.Popen(base + ["--tls-ca", str(cp)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        (node,) = link.wait_for_nodes(1, timeout_s=120)
+        assert node.handle(Message("query", {"type": "free_resources"})).content == {"free_resources": {"status": "OK"}}
+        plain = subprocess.Popen(base, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)      # no CA: plaintext to a TLS port
+        out = _reap([plain])[0]
+        assert plain.returncode != 0 and len(link._slots) == 1, out[-800:]
+    finally:
+        link.close()
+    assert _reap([good]) and good.returncode == 0
