@@ -153,7 +153,8 @@ class S3ObjectStore(ObjectStore):
 
     def __init__(self, bucket: str, *, endpoint_url: str, access_key: str, secret_key: str, region: str = "us-east-1", prefix: str = "",
                  num_attempts: int = 3, connect_timeout: float = 60.0, read_timeout: float = 3600.0, session_token: str | None = None,
-                 part_size: int = 64 << 20, multipart_threshold: int = 128 << 20, max_concurrency: int = 8) -> None:
+                 part_size: int = 64 << 20, multipart_threshold: int = 128 << 20, max_concurrency: int = 8,
+                 ca_bundle: str | None = None) -> None:
         u = urllib.parse.urlparse(endpoint_url)
         if u.scheme not in ("http", "https") or not u.netloc:
             raise ValueError(f"endpoint_url must be http(s)://host[:port], got {endpoint_url!r}")
@@ -164,6 +165,11 @@ class S3ObjectStore(ObjectStore):
         self.connect_timeout, self.read_timeout = float(connect_timeout), float(read_timeout)
         self.part_size, self.multipart_threshold = int(part_size), int(multipart_threshold)
         self.max_concurrency = max(1, int(max_concurrency))     # parts of one large object in flight (upload and ranged download)
+        self._ssl: Any = None
+        if self.scheme == "https":
+            import ssl
+
+            self._ssl = ssl.create_default_context(cafile=ca_bundle) if ca_bundle else ssl.create_default_context()   # e.g. a private MinIO CA
 
     # -- plumbing ------------------------------------------------------------------------------------------------
     def _key(self, key: str) -> str:
@@ -187,8 +193,8 @@ class S3ObjectStore(ObjectStore):
             try:
                 hdr = sigv4_headers(method, self.host, path, query, dict(headers or {}), sha, access_key=self.access_key,
                                     secret_key=self.secret_key, region=self.region, session_token=self.session_token)
-                cls = http.client.HTTPSConnection if self.scheme == "https" else http.client.HTTPConnection
-                conn = cls(self.host, timeout=self.connect_timeout)
+                conn = (http.client.HTTPSConnection(self.host, timeout=self.connect_timeout, context=self._ssl) if self.scheme == "https"
+                        else http.client.HTTPConnection(self.host, timeout=self.connect_timeout))
                 conn.connect()
                 conn.sock.settimeout(self.read_timeout)
                 if body:
@@ -354,7 +360,8 @@ class S3ObjectStore(ObjectStore):
 def remote_store_from_cfg(cfg: Any, env: dict[str, str] | None = None) -> ObjectStore | None:
     """The S3 endpoint of this run, or None (directory stand-in). A real store is used when an endpoint is configured —
     ``s3_comm_config.backend_kwargs.endpoint_url`` or ``S3_ENDPOINT_URL`` (the variable Composer's S3 backend reads; AWS itself:
-    ``https://s3.<region>.amazonaws.com``) — and credentials are present (``AWS_ACCESS_KEY_ID`` / ``AWS_SECRET_ACCESS_KEY``)."""
+    ``https://s3.<region>.amazonaws.com``) — and credentials are present (``AWS_ACCESS_KEY_ID`` / ``AWS_SECRET_ACCESS_KEY``). ``AWS_CA_BUNDLE`` (or
+    ``backend_kwargs.verify``) names the CA file of an https endpoint with a private certificate."""
     env = dict(os.environ if env is None else env)
     sc = dict(cfg.get("s3_comm_config") or {})
     bk = dict(sc.get("backend_kwargs") or {})
@@ -369,4 +376,4 @@ def remote_store_from_cfg(cfg: Any, env: dict[str, str] | None = None) -> Object
                          region=str(bk.get("region_name") or env.get("AWS_DEFAULT_REGION") or env.get("AWS_REGION") or "us-east-1"),
                          prefix=str(bk.get("prefix", "") or ""), num_attempts=int(sc.get("num_attempts", 3) or 3),
                          connect_timeout=float(cc.get("connect_timeout", 60) or 60), read_timeout=float(cc.get("read_timeout", 3600) or 3600),
-                         session_token=env.get("AWS_SESSION_TOKEN") or None)
+                         session_token=env.get("AWS_SESSION_TOKEN") or None, ca_bundle=bk.get("verify") or env.get("AWS_CA_BUNDLE") or None)

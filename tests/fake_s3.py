@@ -20,8 +20,16 @@ def _sign(key: bytes, msg: str) -> bytes:
 class FakeS3(ThreadingHTTPServer):
     daemon_threads = True
 
-    def __init__(self, page_size: int = 1000) -> None:
+    def __init__(self, page_size: int = 1000, tls: tuple[str, str] | None = None) -> None:
         super().__init__(("127.0.0.1", 0), _Handler)
+        self.scheme = "http"
+        if tls is not None:          # (key file, certificate file): serve https
+            import ssl
+
+            ctx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+            ctx.load_cert_chain(certfile=tls[1], keyfile=tls[0])
+            self.socket = ctx.wrap_socket(self.socket, server_side=True)
+            self.scheme = "https"
         self.objects: dict[str, bytes] = {}            # "bucket/key" -> data
         self.uploads: dict[str, dict[int, bytes]] = {}
         self.page_size = page_size
@@ -33,7 +41,7 @@ class FakeS3(ThreadingHTTPServer):
 
     @property
     def endpoint(self) -> str:
-        return f"http://127.0.0.1:{self.server_address[1]}"
+        return f"{self.scheme}://127.0.0.1:{self.server_address[1]}"
 
     def stop(self) -> None:
         self.shutdown()

@@ -247,3 +247,39 @@ def test_client_checkpoints_follow_the_client_through_the_bucket(tmp_path, s3, m
         del s3.objects[k]
     lost = run(tmp_path / "B2", "lost", 2, True)
     assert not torch.allclose(lost, stay, atol=1e-6)
+
+
+def test_s3_over_https_with_a_private_ca(tmp_path):
+    """An https endpoint whose certificate comes from a private CA (a lab MinIO): ``AWS_CA_BUNDLE`` makes it trusted, without it the
+    connection is refused."""
+    import datetime
+    import ipaddress
+
+    pytest.importorskip("cryptography")
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import ec
+    from cryptography.x509.oid import NameOID
+
+    key = ec.generate_private_key(ec.SECP256R1())
+    name = x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, "127.0.0.1")])
+    now = datetime.datetime.now(datetime.timezone.utc)
+    cert = (x509.CertificateBuilder().subject_name(name).issuer_name(name).public_key(key.public_key()).serial_number(x509.random_serial_number())
+            .not_valid_before(now - datetime.timedelta(minutes=5)).not_valid_after(now + datetime.timedelta(days=1))
+            .add_extension(x509.SubjectAlternativeName([x509.IPAddress(ipaddress.ip_address("127.0.0.1"))]), critical=False)
+            .add_extension(x509.BasicConstraints(ca=True, path_length=None), critical=True).sign(key, hashes.SHA256()))
+    kp, cp = tmp_path / "k.pem", tmp_path / "c.pem"
+    kp.write_bytes(key.private_bytes(serialization.Encoding.PEM, serialization.PrivateFormat.PKCS8, serialization.NoEncryption()))
+    cp.write_bytes(cert.public_bytes(serialization.Encoding.PEM))
+    srv = FakeS3(tls=(str(kp), str(cp)))
+    try:
+        env = {"S3_ENDPOINT_URL": srv.endpoint, "AWS_ACCESS_KEY_ID": ACCESS, "AWS_SECRET_ACCESS_KEY": SECRET, "AWS_DEFAULT_REGION": REGION}
+        cfg = {"s3_comm_config": {"bucket_name": "bkt", "num_attempts": 1}}
+        trusted = remote_store_from_cfg(cfg, env={**env, "AWS_CA_BUNDLE": str(cp)})
+        trusted.put("k", b"v")
+        assert srv.objects["bkt/k"] == b"v" and trusted.get("k") == b"v" and srv.endpoint.startswith("https://")
+        with pytest.raises(ObjectStoreError, match="giving up"):
+            remote_store_from_cfg(cfg, env=env).put("k2", b"v")           # certificate verify failed
+        assert "bkt/k2" not in srv.objects
+    finally:
+        srv.stop()
