@@ -10,8 +10,8 @@ the same reduction: NVLink / NVSwitch inside a box, the network between boxes â€
 
 Process layout: every rank of the box runs :func:`serve_box` (launched by ``torchrun`` or ``photon_b200.launch``). Rank 0 owns the
 gRPC connection; what it receives is replayed on the other ranks through the runtime's host control plane (``ControlPlane.broadcast``,
-a TCPStore â€” no collective is blocked while the box waits for work), parameters go to the peers with one ``torch.distributed``
-broadcast per round.
+a TCPStore â€” no collective is blocked while the box waits for work), the round's parameters reach the peers through a file in
+``/dev/shm`` (no collective either: a rank that died earlier cannot hold up the install).
 """
 from __future__ import annotations
 
@@ -52,6 +52,7 @@ class BoxApp:
         self._agg_round = -1
         self._op = 0
         self._global: torch.Tensor | None = None      # the server's model of this round (every batch of the round starts from it)
+        self._shm_file: str | None = None
         if runtime.ctl is not None:
             # a box waits for work for as long as the server has none: "rank 0 has not spoken for two hours" is not an error here
             # (a DEAD rank 0 is still noticed â€” its heartbeat goes stale â€” and rank 0 keeps ticking while it polls the server)
@@ -75,6 +76,8 @@ class BoxApp:
 
     def shutdown(self) -> None:
         self._replay({"op": "stop"})
+        if self._shm_file and os.path.exists(self._shm_file):
+            os.unlink(self._shm_file)
         self.rt.close()
 
     # ------------------------------------------------------------------ rank 0 -> followers
@@ -83,16 +86,23 @@ class BoxApp:
             self._op += 1
             self.rt.ctl.broadcast(f"box_op/{self._op}", op)
 
-    def _install(self, arrays: list[np.ndarray] | None) -> None:
-        """The round's global model on every rank of the box (rank 0 holds ``arrays``)."""
-        from photon_b200.server.broadcast_utils import broadcast_parameters_to_nodes
-
-        flat = None
+    def _install(self, arrays: list[np.ndarray] | None, path: str | None = None) -> None:
+        """The round's global model on every rank of the box. Rank 0 holds ``arrays``; the other ranks read the flat vector rank 0 left
+        in ``/dev/shm`` (same machine) â€” no collective, so a rank of the box that died earlier cannot block the ones that are left."""
+        lay = self.rt.layout
         if arrays is not None:
-            lay = self.rt.layout
             flat = torch.zeros(lay.total, dtype=torch.float32)
             lay.from_ndarrays(flat, arrays)
-        broadcast_parameters_to_nodes(self.rt, flat, src=0)
+            if self.rt.ctl is not None:
+                new = f"/dev/shm/photon_box_{os.getpid()}_{self._op + 1}.pt"
+                torch.save(flat, new)
+                self._replay({"op": "install", "path": new})
+                if self._shm_file and os.path.exists(self._shm_file):
+                    os.unlink(self._shm_file)          # everybody has long finished reading the previous round's vector
+                self._shm_file = new
+        else:
+            flat = torch.load(path, map_location="cpu")
+        self.rt.round_backend.set_global(flat.to(self.rt.device), None, None)
         self._global = self.rt.round_backend.global_params().detach().clone()
 
     def _train(self, server_round: int, cids: list[int], client_state: Any, steps: int) -> tuple[list[FitRes], int]:
@@ -127,7 +137,6 @@ class BoxApp:
                     from photon_b200.server.s3_utils import replace_parameters_in_recordset_with_remote
 
                     payload = replace_parameters_in_recordset_with_remote(payload).data
-                self._replay({"op": "install"})
                 self._install(list(payload))
                 return Message("query", {"broadcast": {"status": "OK"}}, node_id=self.node_id, group_id=msg.group_id, reply_to=msg.msg_id)
             if kind == "collect_aggregate":
@@ -185,7 +194,7 @@ class BoxApp:
                 self.rt.close()
                 return
             if op["op"] == "install":
-                self._install(None)
+                self._install(None, op["path"])
             elif op["op"] == "train":
                 self._train(op["round"], op["cids"], op["client_state"], op["steps"])
             elif op["op"] == "evaluate":
